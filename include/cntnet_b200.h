@@ -1,0 +1,192 @@
+/* cntnet_b200 -- C-ABI of the B200-native stick-network hot path.
+ *
+ * The reference (leobrowning92/networksim-cntfet) is pure Python and has no FFI layer; its
+ * seam is the method surface of netsim.py / cnet.py / measure_perc.py.  Each
+ * entry point below replaces the *body* of one or more of those methods and is what a
+ * ctypes binding inside the reference would call (INTEGRATION.md shows the stubs).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer into caller-owned memory (PyTorch CUDA tensors in
+ *    the shipped host layer) unless its name starts with h_;
+ *  - a batch holds B independent networks; per-stick arrays are concatenated and indexed
+ *    through soff[B+1] (int32 prefix offsets), per-junction arrays through joff[B+1];
+ *    stick indices stored in junction tables are LOCAL to their network, exactly the
+ *    reference's post-sort DataFrame index (netsim.py:133-134);
+ *  - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *    synchronises unless documented; the library allocates no device memory: scratch comes
+ *    from caller-provided workspaces sized by the *_workspace_bytes queries;
+ *  - every function returns an int status (CNT_OK == 0); nothing throws;
+ *    cnt_last_error() gives a thread-local message for the last non-zero status;
+ *  - "not percolating" is a normal result (netsim.py:208-218, measure_perc.py:193-197),
+ *    reported per network, never an error.
+ *  - stick kinds: 0 = 'v' (electrode), 1 = 'm', 2 = 's'; junction kind2 = 3*kind[stick1] +
+ *    kind[stick2] (netsim.py:148 `kinds[i]+kinds[j]`).
+ */
+#ifndef CNTNET_B200_H
+#define CNTNET_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CNT_OK 0
+#define CNT_EINVAL 1   /* bad argument                                   */
+#define CNT_ECUDA 2    /* a CUDA runtime call or launch failed           */
+#define CNT_ECAPACITY 3 /* caller-provided buffer / workspace too small   */
+
+#define CNT_ABI_VERSION 1
+
+int cnt_abi_version(void);
+const char *cnt_last_error(void);
+/* number of kernels this library has launched in this process (bench.py `gpu_launches`). */
+int64_t cnt_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------
+ * utilities
+ * ------------------------------------------------------------------------------------- */
+/* exclusive prefix sum of n int32 values; out may alias in; out[n] receives the total when
+ * write_total != 0 (out must then hold n+1 values).  ws: cnt_scan_workspace_bytes(n). */
+int64_t cnt_scan_workspace_bytes(int64_t n);
+int cnt_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int write_total,
+                           void *ws, int64_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (1) stick placement -- replaces make_stick / get_ends / make_sticks (netsim.py:97-125)
+ *     and the length sort of make_intersects_kdtree (netsim.py:132-134).
+ * Counter-based Philox4x32-10 keyed by (seed, net_id0 + b), counter = stick ordinal; law:
+ * kind 'm' iff u<=pm, xc,yc~U(0,1), angle~U(0,2pi), length=|N(0.66,0.44)|/scaling[b]
+ * (len_mode 0) or len_const/scaling[b] (len_mode 1).  Each network gets soff[b+1]-soff[b]
+ * sticks INCLUDING the two electrodes [0.01|0.99, 0.5, pi/2-1e-6, 100, 'v'].
+ * Output order is canonical: source electrode (x=0.01) at local index 0, drain (x=0.99) at
+ * 1, then the body sticks by length descending, ties by generation ordinal; orig[] is the
+ * reference's pre-sort DataFrame index (netsim.py:132: source 0, body 1..n, drain n+1).
+ * ------------------------------------------------------------------------------------- */
+int64_t cnt_gen_sticks_workspace_bytes(int64_t n_sticks_total, int B);
+int cnt_gen_sticks(uint64_t seed, int64_t net_id0, int B, const int32_t *soff, const int32_t *h_soff,
+                   const double *scaling, double pm, int len_mode, double len_const,
+                   double *xc, double *yc, double *angle, double *length, uint8_t *kind,
+                   double *xa, double *ya, double *xb, double *yb, int32_t *orig,
+                   void *ws, int64_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (2) junction finder -- replaces check_intersect (netsim.py:75-94) and the pair loop of
+ *     make_intersects_kdtree (netsim.py:135-150).
+ * A pair (i<j, local post-sort indices) is TESTED iff the squared centre distance is
+ * <= length[i]^2 (the KD-tree ball of netsim.py:142) and is a JUNCTION iff the FP64
+ * slope/intercept predicate holds and 0<=x<=1, 0<=y<=1.  IEEE round-to-nearest, no FMA
+ * contraction: junction sets and coordinates are bit-identical to the reference.
+ * Two calls: _count fills jcount[S] (junctions whose stick1 is that stick) and
+ * ntests[B]; the caller scans jcount into jstart[S+1], allocates J = jstart[S] rows and
+ * calls _fill (SAME workspace, untouched in between: the binned records are reused), which
+ * writes rows sorted by (network, stick1, stick2) and joff[B+1].  jcount holds S+1 ints.
+ * h_soff is the host copy of soff (grid geometry is derived from it on the host).
+ * ------------------------------------------------------------------------------------- */
+int64_t cnt_junction_workspace_bytes(int B, const int32_t *h_soff);
+int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_soff,
+                       const double *xa, const double *ya, const double *xb, const double *yb,
+                       const double *xc, const double *yc, const double *length,
+                       int32_t *jcount, unsigned long long *ntests,
+                       void *ws, int64_t ws_bytes, void *stream);
+int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_soff,
+                      const double *xa, const double *ya, const double *xb, const double *yb,
+                      const double *xc, const double *yc, const double *length, const uint8_t *kind,
+                      const int32_t *jstart, int64_t J,
+                      int32_t *stick1, int32_t *stick2, double *jx, double *jy, uint8_t *kind2,
+                      int32_t *joff, void *ws, int64_t ws_bytes, void *stream);
+/* device pointer (inside ws) of the sortedness flag written by the last _count: non-zero if
+ * some network's table was not sorted by length descending (netsim.py:133 invariant). */
+int cnt_junction_errflag_ptr(int B, const int32_t *h_soff, void *ws, int64_t ws_bytes, int32_t **out);
+
+/* ---------------------------------------------------------------------------------------
+ * (3) clusters -- replaces make_graph's component search (netsim.py:175-179), label_clusters
+ *     (netsim.py:197-206) and the nclust / maxclust lines of measure_perc.py:76-80,148-152.
+ * label[s] = smallest local stick index of the connected component (isolated sticks label
+ * themselves).  stats[b*CNT_NSTAT + k]:
+ * ------------------------------------------------------------------------------------- */
+#define CNT_STAT_PERCOLATING 0  /* sticks 0 and 1 in one component (netsim.py:177-178)       */
+#define CNT_STAT_NCLUST_TRUE 1  /* number of distinct labels                                 */
+#define CNT_STAT_MAXCLUST_TRUE 2 /* largest component                                        */
+#define CNT_STAT_NCLUST_REF 3   /* len(sticks.cluster.drop_duplicates()) (measure_perc.py:76) */
+#define CNT_STAT_MAXCLUST_REF 4 /* len(max(nx.connected_components(g))) (measure_perc.py:78)  */
+#define CNT_STAT_NCOMP 5        /* sticks in the percolating component (0 if none)           */
+#define CNT_STAT_ECOMP 6        /* junctions in the percolating component                    */
+#define CNT_NSTAT 8
+int64_t cnt_cluster_workspace_bytes(int64_t n_sticks_total);
+int cnt_label_clusters(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
+                       const int32_t *stick1, const int32_t *stick2, const int32_t *orig /* may be NULL */,
+                       int32_t *label, int32_t *stats, void *ws, int64_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (4) MNA assembly -- replaces populate_graph (netsim.py:192-195), update_conductivity,
+ *     make_G, make_A, make_z (cnet.py:99-131) in the reduced SPD form
+ *         L_UU V_U = 0.1 * g_{U,source}
+ *     (nodes ascending by stick index, source = stick 0 at 0.1 V, ground = stick 1).
+ * _pattern builds, for every percolating network of the batch, the CSR pattern of L_UU
+ * without its diagonal: rowptr[R+1], col[NNZ] (column = row index LOCAL to the network),
+ * nz_eid[NNZ] (global junction row that owns the entry), per-row src_eid / drn_eid (the
+ * junction to stick 0 / stick 1, -1 if none), urow[S] (global row of a stick, -1 if not an
+ * unknown), roff[B+1] (row offsets per network; empty range if not percolating).
+ * Two-phase like the junction finder: _pattern_count fills rowcnt[R]; caller scans.
+ * _values evaluates one gate configuration: g[e] = gtable[kind2[e]*nlevels + level[e]]
+ * (table computed on the host with the reference's own formula so conductances are
+ * bit-identical), val = -g[nz_eid], diag = row sum incl. electrode contacts, rhs = 0.1*g_src.
+ * ------------------------------------------------------------------------------------- */
+int64_t cnt_assemble_workspace_bytes(int64_t n_sticks_total);
+int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
+                      int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream);
+int cnt_assemble_pattern_count(int B, const int32_t *soff, const int32_t *joff, int64_t J,
+                               const int32_t *stick1, const int32_t *stick2,
+                               const int32_t *urow, int64_t R, int32_t *rowcnt, void *stream);
+int cnt_assemble_pattern_fill(int B, const int32_t *soff, const int32_t *joff, int64_t J,
+                              const int32_t *stick1, const int32_t *stick2,
+                              const int32_t *urow, const int32_t *roff, int64_t R, const int32_t *rowptr,
+                              int32_t *col, int32_t *nz_eid, int32_t *src_eid, int32_t *drn_eid,
+                              void *ws, int64_t ws_bytes, void *stream);
+/* row_stick[r] = local stick index of unknown row r (inverse of urow). */
+int cnt_assemble_row_stick(int B, const int32_t *soff, int64_t S, const int32_t *urow,
+                           int32_t *row_stick, void *stream);
+int cnt_gate_levels(int64_t J, const double *jx, const double *jy, uint8_t *level,
+                    int global_set, uint8_t global_level,
+                    int rect_set, double cx, double cy, double w, double h, uint8_t rect_level, void *stream);
+int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, const double *gtable, int nlevels,
+                        int64_t R, const int32_t *rowptr, const int32_t *nz_eid,
+                        const int32_t *src_eid, const int32_t *drn_eid,
+                        double *g, double *val, double *diag, double *rhs, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (5) solve -- replaces solve_mna (cnet.py:147-149, SuperLU) by a batched Jacobi-PCG.
+ * Value arrays come in NSLAB slabs (one per gate configuration): val + q*NNZ,
+ * diag/rhs/x + q*R, all sharing the batch pattern.  System s = (network h_sys_net[s], slab
+ * h_sys_slab[s]); a (network, slab) pair may appear at most once.  Stops when
+ * ||r||_2 <= rtol*||b||_2 (recurrence residual; see DESIGN.md "PCG accuracy" for why there is
+ * no residual replacement) or after maxit.  x holds the initial guess on entry.
+ * Per system: iters (int32), relres (double), status (0 converged, 1 maxit, 2 breakdown).
+ * Synchronises the stream every `check_every` iterations to poll for completion.
+ * ------------------------------------------------------------------------------------- */
+int64_t cnt_pcg_workspace_bytes(int NSYS, int NSLAB, int64_t R);
+int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
+                  const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,
+                  const double *val, const double *diag, const double *rhs, double *x,
+                  double rtol, int maxit, int check_every,
+                  int32_t *iters, double *relres, int32_t *status,
+                  void *ws, int64_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
+ * (6) write-back -- replaces update_voltages / update_currents (cnet.py:132-146).
+ * V[S]: stick voltage (0.1 source, 0 drain, NaN outside the percolating component);
+ * I[J]: |g (V1 - V2)| per junction (NaN outside the component);
+ * isrc[b*3+0] = sum_j g_0j (0.1 - V_j)  (== x[-1] of the MNA system, cnet.py:135)
+ * isrc[b*3+1] = sum_j g_1j V_j          (current into the ground electrode)
+ * isrc[b*3+2] = sum_e g_e dV_e^2 / 0.1  (dissipated power / Vds)
+ * ------------------------------------------------------------------------------------- */
+int cnt_currents(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
+                 const int32_t *stick1, const int32_t *stick2, const int32_t *label, const int32_t *stats,
+                 const int32_t *urow, const double *g, const double *x,
+                 double *V, double *I, double *isrc, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CNTNET_B200_H */

@@ -1,0 +1,84 @@
+"""In-tree build of libcntnet_b200.so with nvcc for sm_100a (no JIT cache: the built .so
+travels with the repo snapshot to the GPU box).
+
+    python -m networksim_cntfet_b200.build [--force] [--verbose]
+"""
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJDIR = os.path.join(HERE, "_build")
+LIB = os.path.join(HERE, "libcntnet_b200.so")
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+
+SOURCES = ["util.cu", "sticks.cu", "junctions.cu", "clusters.cu", "assemble.cu", "pcg.cu", "pcg_cluster.cu",
+           "currents.cu"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE]
+# bit-exact FP64 predicate: no FMA contraction anywhere in that translation unit (the kernels
+# also use explicit __d*_rn intrinsics; this is belt and braces)
+PER_FILE = {"junctions.cu": ["-fmad=false"]}
+
+
+def nvcc_path():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.isfile(cand):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def _digest(paths, extra):
+    h = hashlib.sha256(extra.encode())
+    for p in sorted(paths):
+        with open(p, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
+def sources():
+    return [s for s in SOURCES if os.path.isfile(os.path.join(CSRC, s))]
+
+
+def build(force=False, verbose=False):
+    """Compile every .cu for sm_100a and link the shared library.  Returns the .so path."""
+    nvcc = nvcc_path()
+    os.makedirs(OBJDIR, exist_ok=True)
+    headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    headers.append(os.path.join(INCLUDE, "cntnet_b200.h"))
+    objs = []
+    rebuilt = False
+    for src in sources():
+        path = os.path.join(CSRC, src)
+        obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
+        flags = COMMON + ARCH + PER_FILE.get(src, [])
+        if verbose:
+            flags = flags + ["-Xptxas", "-v"]
+        stamp = obj + ".sha"
+        dig = _digest([path] + headers, " ".join(flags))
+        if not force and os.path.isfile(obj) and os.path.isfile(stamp) and open(stamp).read() == dig:
+            objs.append(obj)
+            continue
+        cmd = [nvcc] + flags + ["-c", path, "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if verbose or r.returncode:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if r.returncode:
+            raise RuntimeError("nvcc failed on %s" % src)
+        open(stamp, "w").write(dig)
+        objs.append(obj)
+        rebuilt = True
+    if rebuilt or force or not os.path.isfile(LIB):
+        cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError("link failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,238 @@
+// MNA assembly in reduced SPD form  L_UU V_U = 0.1 g_{U,source}.
+// Replaces populate_graph (netsim.py:192-195), update_conductivity / make_G / make_A /
+// make_z (cnet.py:99-131) and the gate setters (cnet.py:159-183).
+//
+// Unknowns = sticks of the percolating component except stick 0 (source, 0.1 V) and stick 1
+// (ground), in ascending stick index (canonical node order).  The CSR pattern
+// (without diagonal) is built once per batch; one gate configuration is a value pass:
+// val = -g[junction of the entry], diag = ordered row sum incl. electrode contacts.
+#include "common.cuh"
+
+namespace {
+
+__global__ void k_row_flags(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ label,
+                            const int32_t *__restrict__ stats, int32_t *__restrict__ flag) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int b = cnt::find_segment(soff, B, (int)s);
+    int i = (int)s - soff[b];
+    flag[s] = (stats[(int64_t)b * CNT_NSTAT + CNT_STAT_PERCOLATING] && i >= 2 && label[s] == 0) ? 1 : 0;
+}
+
+__global__ void k_rows_finish(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ flag,
+                              const int32_t *__restrict__ scan, int32_t *__restrict__ urow,
+                              int32_t *__restrict__ roff) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) urow[s] = flag[s] ? scan[s] : -1;
+    if (s <= B) roff[s] = scan[soff[s]];   // scan has S+1 entries (total at S)
+}
+
+template <bool FILL>
+__global__ void k_pattern(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff, int64_t J,
+                          const int32_t *__restrict__ stick1, const int32_t *__restrict__ stick2,
+                          const int32_t *__restrict__ urow, const int32_t *__restrict__ roff,
+                          const int32_t *__restrict__ rowptr, int32_t *__restrict__ rowcnt /* count or cursor */,
+                          int32_t *__restrict__ col, int32_t *__restrict__ nz_eid, int32_t *__restrict__ src_eid,
+                          int32_t *__restrict__ drn_eid) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= J) return;
+    int b = cnt::find_segment(joff, B, (int)e);
+    int s0 = soff[b];
+    int a = stick1[e], c = stick2[e];
+    int ua = urow[s0 + a], uc = urow[s0 + c];
+    if (ua >= 0 && uc >= 0) {
+        int ka = atomicAdd(rowcnt + ua, 1), kc = atomicAdd(rowcnt + uc, 1);
+        if (FILL) {
+            int r0 = roff[b];
+            col[rowptr[ua] + ka] = uc - r0;
+            nz_eid[rowptr[ua] + ka] = (int)e;
+            col[rowptr[uc] + kc] = ua - r0;
+            nz_eid[rowptr[uc] + kc] = (int)e;
+        }
+    } else if (FILL && uc >= 0) {   // a is an electrode of the percolating component
+        if (a == 0) src_eid[uc] = (int)e;
+        else if (a == 1) drn_eid[uc] = (int)e;
+    }
+}
+
+// sort every row by column (rows are short) so the pattern is deterministic
+__global__ void k_sort_rows(int64_t R, const int32_t *__restrict__ rowptr, int32_t *__restrict__ col,
+                            int32_t *__restrict__ nz_eid) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int k0 = rowptr[r], k1 = rowptr[r + 1];
+    for (int a = k0 + 1; a < k1; a++) {
+        int cc = col[a], ee = nz_eid[a];
+        int c = a - 1;
+        while (c >= k0 && col[c] > cc) {
+            col[c + 1] = col[c];
+            nz_eid[c + 1] = nz_eid[c];
+            c--;
+        }
+        col[c + 1] = cc;
+        nz_eid[c + 1] = ee;
+    }
+}
+
+__global__ void k_row_stick(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ urow,
+                            int32_t *__restrict__ row_stick) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int u = urow[s];
+    if (u >= 0) row_stick[u] = (int)s - soff[cnt::find_segment(soff, B, (int)s)];
+}
+
+__global__ void k_gate_levels(int64_t J, const double *__restrict__ jx, const double *__restrict__ jy,
+                              uint8_t *__restrict__ level, int global_set, uint8_t global_level, int rect_set,
+                              double left, double right, double bottom, double top, uint8_t rect_level) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= J) return;
+    uint8_t l = level[e];
+    if (global_set) l = global_level;
+    if (rect_set) {
+        double x = jx[e], y = jy[e];
+        if (left <= x && x <= right && bottom <= y && y <= top) l = rect_level;   // cnet.py:166-175
+    }
+    level[e] = l;
+}
+
+__global__ void k_conductance(int64_t J, const uint8_t *__restrict__ kind2, const uint8_t *__restrict__ level,
+                              const double *__restrict__ gtable, int nlevels, double *__restrict__ g) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < J) g[e] = gtable[(int)kind2[e] * nlevels + (int)level[e]];
+}
+
+// one thread per row: fixed summation order (columns ascending, then source, then drain)
+__global__ void k_values(int64_t R, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ nz_eid,
+                         const int32_t *__restrict__ src_eid, const int32_t *__restrict__ drn_eid,
+                         const double *__restrict__ g, double *__restrict__ val, double *__restrict__ diag,
+                         double *__restrict__ rhs) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int k0 = rowptr[r], k1 = rowptr[r + 1];
+    double sum = 0.0;
+    for (int k = k0; k < k1; k++) {
+        double ge = g[nz_eid[k]];
+        val[k] = -ge;
+        sum += ge;
+    }
+    int se = src_eid[r], de = drn_eid[r];
+    double gs = se >= 0 ? g[se] : 0.0;
+    double gd = de >= 0 ? g[de] : 0.0;
+    sum += gs;
+    sum += gd;
+    diag[r] = sum;
+    rhs[r] = 0.1 * gs;
+}
+}  // namespace
+
+extern "C" int64_t cnt_assemble_workspace_bytes(int64_t S) {
+    return 2 * cnt::ws_bytes_for(S + 1, 4) + cnt_scan_workspace_bytes(S + 1);
+}
+
+extern "C" int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
+                                 int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && soff && label && stats && urow && roff && ws && S >= B);
+    cnt::Workspace w(ws, ws_bytes);
+    int32_t *flag = w.take<int32_t>(S + 1);
+    int32_t *scan = w.take<int32_t>(S + 1);
+    int64_t sb = cnt_scan_workspace_bytes(S + 1);
+    void *sws = w.take<char>(sb);
+    if (!sws) {
+        cnt::set_error("assemble workspace too small");
+        return CNT_ECAPACITY;
+    }
+    k_row_flags<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, label, stats, flag);
+    CNT_LAUNCHED();
+    int rc = cnt_exclusive_scan_i32(flag, scan, S, 1, sws, sb, stream);
+    if (rc) return rc;
+    k_rows_finish<<<cnt::grid_for(S + 1, 256), 256, 0, st>>>(B, soff, S, flag, scan, urow, roff);
+    CNT_LAUNCHED();
+    return CNT_OK;
+}
+
+extern "C" int cnt_assemble_pattern_count(int B, const int32_t *soff, const int32_t *joff, int64_t J,
+                                          const int32_t *stick1, const int32_t *stick2, const int32_t *urow, int64_t R,
+                                          int32_t *rowcnt, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && soff && joff && urow && rowcnt && R >= 0 && J >= 0);
+    CNT_CUDA(cudaMemsetAsync(rowcnt, 0, 4 * (R + 1), st));
+    if (J > 0) {
+        k_pattern<false><<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, urow, nullptr,
+                                                                nullptr, rowcnt, nullptr, nullptr, nullptr, nullptr);
+        CNT_LAUNCHED();
+    }
+    return CNT_OK;
+}
+
+extern "C" int cnt_assemble_pattern_fill(int B, const int32_t *soff, const int32_t *joff, int64_t J,
+                                         const int32_t *stick1, const int32_t *stick2, const int32_t *urow,
+                                         const int32_t *roff, int64_t R, const int32_t *rowptr, int32_t *col,
+                                         int32_t *nz_eid, int32_t *src_eid, int32_t *drn_eid, void *ws,
+                                         int64_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && soff && joff && urow && roff && rowptr && R >= 0 && J >= 0 && ws);
+    if (R == 0) return CNT_OK;
+    CNT_CHECK_ARG(col && nz_eid && src_eid && drn_eid);
+    cnt::Workspace w(ws, ws_bytes);
+    int32_t *cursor = w.take<int32_t>(R);
+    if (!cursor) {
+        cnt::set_error("assemble workspace too small");
+        return CNT_ECAPACITY;
+    }
+    CNT_CUDA(cudaMemsetAsync(cursor, 0, 4 * R, st));
+    CNT_CUDA(cudaMemsetAsync(src_eid, 0xFF, 4 * R, st));
+    CNT_CUDA(cudaMemsetAsync(drn_eid, 0xFF, 4 * R, st));
+    k_pattern<true><<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, urow, roff, rowptr, cursor,
+                                                           col, nz_eid, src_eid, drn_eid);
+    CNT_LAUNCHED();
+    k_sort_rows<<<cnt::grid_for(R, 128), 128, 0, st>>>(R, rowptr, col, nz_eid);
+    CNT_LAUNCHED();
+    return CNT_OK;
+}
+
+extern "C" int cnt_assemble_row_stick(int B, const int32_t *soff, int64_t S, const int32_t *urow,
+                                      int32_t *row_stick, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && soff && urow && row_stick && S >= 0);
+    if (S > 0) {
+        k_row_stick<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, urow, row_stick);
+        CNT_LAUNCHED();
+    }
+    return CNT_OK;
+}
+
+extern "C" int cnt_gate_levels(int64_t J, const double *jx, const double *jy, uint8_t *level, int global_set,
+                               uint8_t global_level, int rect_set, double cx, double cy, double w, double h,
+                               uint8_t rect_level, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(J >= 0);
+    if (J == 0) return CNT_OK;
+    CNT_CHECK_ARG(jx && jy && level);
+    // rectangle edges exactly as cnet.py:168-171 computes them
+    double right = cx + w / 2, left = cx - w / 2, top = cy + h / 2, bottom = cy - h / 2;
+    k_gate_levels<<<cnt::grid_for(J, 256), 256, 0, st>>>(J, jx, jy, level, global_set, global_level, rect_set, left,
+                                                         right, bottom, top, rect_level);
+    CNT_LAUNCHED();
+    return CNT_OK;
+}
+
+extern "C" int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, const double *gtable,
+                                   int nlevels, int64_t R, const int32_t *rowptr, const int32_t *nz_eid,
+                                   const int32_t *src_eid, const int32_t *drn_eid, double *g, double *val,
+                                   double *diag, double *rhs, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(J >= 0 && R >= 0 && nlevels > 0);
+    if (J > 0) {
+        CNT_CHECK_ARG(kind2 && level && gtable && g);
+        k_conductance<<<cnt::grid_for(J, 256), 256, 0, st>>>(J, kind2, level, gtable, nlevels, g);
+        CNT_LAUNCHED();
+    }
+    if (R > 0) {
+        CNT_CHECK_ARG(rowptr && nz_eid && src_eid && drn_eid && val && diag && rhs);
+        k_values<<<cnt::grid_for(R, 128), 128, 0, st>>>(R, rowptr, nz_eid, src_eid, drn_eid, g, val, diag, rhs);
+        CNT_LAUNCHED();
+    }
+    return CNT_OK;
+}

@@ -1,0 +1,371 @@
+// Batched Jacobi-preconditioned conjugate gradient, multi-launch ("flat") variant.
+// Replaces solve_mna (cnet.py:147-149): the reference's SuperLU solve of the indefinite
+// MNA matrix becomes PCG on the equivalent reduced SPD system.
+//
+// NSYS systems (network x gate configuration) are advanced in lock step by five launches
+// per iteration; every system owns row tiles of TILE rows, per-tile partial dot products
+// are written to memory and reduced in a fixed order by a per-system scalar kernel, so a
+// system's iterates are bit-reproducible and independent of what else is in the batch.
+// Converged systems drop out (their tiles return immediately).  The iteration body is
+// captured once into a CUDA graph of `check_every` iterations; the host polls the per-system
+// done flags between graph launches.
+//
+// Stopping rule: recurrence residual ||r||_2 <= rtol ||b||_2.  No residual replacement on
+// purpose: for these Laplacians the TRUE residual stagnates near 1e-12 ||b|| while the error
+// keeps falling with the recurrence residual ("PCG accuracy").
+#include <vector>
+#include "common.cuh"
+
+namespace {
+constexpr int TILE = 256;
+
+struct Tile {
+    int32_t sys;    // system index
+    int32_t row0;   // first row (global pattern row)
+    int32_t nrows;
+    int32_t slab;   // value / vector slab of the system
+};
+struct Sys {
+    int32_t net, row0, nrows, tile0, ntiles, slab;
+};
+struct Scal {      // per-system scalars
+    double rz, bb, alpha, beta, rr;
+    int32_t done, status, iters, pad;
+};
+
+struct Ctx {
+    const Tile *tiles;
+    const Sys *sys;
+    Scal *scal;
+    int64_t R, NNZ;
+    const int32_t *rowptr, *col;
+    const double *val, *diag, *rhs;
+    double *x, *r, *p, *q;
+    double *part0, *part1;   // per-tile partials
+};
+
+__device__ __forceinline__ double spmv_row(const Ctx &c, int sysi, int net_row0, int row, const double *v) {
+    // sysi = slab; row = global pattern row; slab vectors live at slab*R + row; columns are local
+    const double *vs = v + (int64_t)sysi * c.R + net_row0;
+    const double *vals = c.val + (int64_t)sysi * c.NNZ;
+    int k0 = __ldg(c.rowptr + row), k1 = __ldg(c.rowptr + row + 1);
+    double acc = __ldg(c.diag + (int64_t)sysi * c.R + row) * v[(int64_t)sysi * c.R + row];
+    for (int k = k0; k < k1; k++) acc += __ldg(vals + k) * vs[__ldg(c.col + k)];
+    return acc;
+}
+
+__global__ void __launch_bounds__(TILE) k_init(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    Sys s = c.sys[t.sys];
+    int i = threadIdx.x;
+    double rz = 0, bb = 0, rr = 0;
+    if (i < t.nrows) {
+        int row = t.row0 + i;
+        int64_t v = (int64_t)t.slab * c.R + row;
+        double b = c.rhs[v];
+        double ri = b - spmv_row(c, t.slab, s.row0, row, c.x);
+        double zi = ri / c.diag[v];
+        c.r[v] = ri;
+        c.p[v] = zi;
+        rz = ri * zi;
+        bb = b * b;
+        rr = ri * ri;
+    }
+    rz = cnt::block_sum(rz, sm);
+    bb = cnt::block_sum(bb, sm);
+    rr = cnt::block_sum(rr, sm);
+    if (i == 0) {
+        c.part0[blockIdx.x] = rz;
+        c.part1[blockIdx.x] = bb;
+        c.part1[gridDim.x + blockIdx.x] = rr;   // third partial array lives in part1's second half
+    }
+}
+
+__global__ void k_scal_init(Ctx c, int ntiles_total, double rtol, int nsys) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    Sys sy = c.sys[s];
+    double rz = 0, bb = 0, rr = 0;
+    for (int t = sy.tile0; t < sy.tile0 + sy.ntiles; t++) {
+        rz += c.part0[t];
+        bb += c.part1[t];
+        rr += c.part1[ntiles_total + t];
+    }
+    Scal sc;
+    sc.rz = rz; sc.bb = bb; sc.rr = rr; sc.alpha = 0; sc.beta = 0;
+    sc.iters = 0; sc.status = 0; sc.pad = 0;
+    sc.done = (sy.nrows == 0 || rr <= rtol * rtol * bb) ? 1 : 0;
+    c.scal[s] = sc;
+}
+
+__global__ void __launch_bounds__(TILE) k_spmv(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    if (c.scal[t.sys].done) return;
+    Sys s = c.sys[t.sys];
+    int i = threadIdx.x;
+    double pq = 0;
+    if (i < t.nrows) {
+        int row = t.row0 + i;
+        int64_t v = (int64_t)t.slab * c.R + row;
+        double qi = spmv_row(c, t.slab, s.row0, row, c.p);
+        c.q[v] = qi;
+        pq = c.p[v] * qi;
+    }
+    pq = cnt::block_sum(pq, sm);
+    if (i == 0) c.part0[blockIdx.x] = pq;
+}
+
+__global__ void k_scal_alpha(Ctx c, int nsys) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    Scal *sc = c.scal + s;
+    if (sc->done) return;
+    Sys sy = c.sys[s];
+    double pq = 0;
+    for (int t = sy.tile0; t < sy.tile0 + sy.ntiles; t++) pq += c.part0[t];
+    if (!(pq > 0.0)) {   // breakdown (matrix not SPD or NaN)
+        sc->done = 1;
+        sc->status = 2;
+        return;
+    }
+    sc->alpha = sc->rz / pq;
+}
+
+__global__ void __launch_bounds__(TILE) k_update(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    const Scal *sc = c.scal + t.sys;
+    if (sc->done) return;
+    double alpha = sc->alpha;
+    int i = threadIdx.x;
+    double rz = 0, rr = 0;
+    if (i < t.nrows) {
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
+        c.x[v] += alpha * c.p[v];
+        double ri = c.r[v] - alpha * c.q[v];
+        c.r[v] = ri;
+        rz = ri * (ri / c.diag[v]);
+        rr = ri * ri;
+    }
+    rz = cnt::block_sum(rz, sm);
+    rr = cnt::block_sum(rr, sm);
+    if (i == 0) {
+        c.part0[blockIdx.x] = rz;
+        c.part1[blockIdx.x] = rr;
+    }
+}
+
+__global__ void k_scal_beta(Ctx c, int nsys, double rtol, int maxit) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    Scal *sc = c.scal + s;
+    if (sc->done) return;
+    Sys sy = c.sys[s];
+    double rz = 0, rr = 0;
+    for (int t = sy.tile0; t < sy.tile0 + sy.ntiles; t++) {
+        rz += c.part0[t];
+        rr += c.part1[t];
+    }
+    sc->beta = rz / sc->rz;
+    sc->rz = rz;
+    sc->rr = rr;
+    sc->iters += 1;
+    if (rr <= rtol * rtol * sc->bb) {
+        sc->done = 1;
+        sc->status = 0;
+    } else if (sc->iters >= maxit) {
+        sc->done = 1;
+        sc->status = 1;
+    } else if (!(rr == rr)) {
+        sc->done = 1;
+        sc->status = 2;
+    }
+}
+
+__global__ void __launch_bounds__(TILE) k_pupdate(Ctx c) {
+    Tile t = c.tiles[blockIdx.x];
+    const Scal *sc = c.scal + t.sys;
+    if (sc->done) return;
+    double beta = sc->beta;
+    int i = threadIdx.x;
+    if (i < t.nrows) {
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
+        c.p[v] = c.r[v] / c.diag[v] + beta * c.p[v];
+    }
+}
+
+__global__ void k_export(Ctx c, int nsys, int32_t *iters, double *relres, int32_t *status, int32_t *alldone) {
+    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nsys) return;
+    Scal sc = c.scal[s];
+    iters[s] = sc.iters;
+    relres[s] = sc.bb > 0 ? sqrt(sc.rr / sc.bb) : 0.0;
+    status[s] = sc.done ? sc.status : 1;
+    if (!sc.done) atomicAnd(alldone, 0);
+}
+__global__ void k_set1(int32_t *p) { *p = 1; }
+
+struct Layout {
+    std::vector<Tile> tiles;
+    std::vector<Sys> sys;
+};
+static void make_layout(int NSYS, const int32_t *h_sys_net, const int32_t *h_sys_slab, const int32_t *h_roff,
+                        Layout &L) {
+    L.sys.resize(NSYS);
+    L.tiles.clear();
+    for (int s = 0; s < NSYS; s++) {
+        int b = h_sys_net[s];
+        Sys sy;
+        sy.net = b;
+        sy.row0 = h_roff[b];
+        sy.nrows = h_roff[b + 1] - h_roff[b];
+        sy.tile0 = (int)L.tiles.size();
+        sy.ntiles = (sy.nrows + TILE - 1) / TILE;
+        sy.slab = h_sys_slab[s];
+        for (int t = 0; t < sy.ntiles; t++) {
+            Tile tl;
+            tl.sys = s;
+            tl.row0 = sy.row0 + t * TILE;
+            tl.nrows = sy.nrows - t * TILE < TILE ? sy.nrows - t * TILE : TILE;
+            tl.slab = sy.slab;
+            L.tiles.push_back(tl);
+        }
+        L.sys[s] = sy;
+    }
+}
+// upper bound on the number of tiles: every system has at most R rows
+static int64_t count_tiles(int NSYS, int64_t R) { return (int64_t)NSYS * ((R + TILE - 1) / TILE + 1); }
+}  // namespace
+
+extern "C" int64_t cnt_pcg_workspace_bytes(int NSYS, int NSLAB, int64_t R) {
+    using cnt::ws_bytes_for;
+    int64_t nt = count_tiles(NSYS, R);
+    return ws_bytes_for(nt, sizeof(Tile)) + ws_bytes_for(NSYS, sizeof(Sys)) + ws_bytes_for(NSYS, sizeof(Scal)) +
+           3 * ws_bytes_for((int64_t)NSLAB * R + 1, 8) + ws_bytes_for(nt, 8) + ws_bytes_for(2 * nt, 8) +
+           ws_bytes_for(1, 4);
+}
+
+extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
+                             const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col, const double *val, const double *diag,
+                             const double *rhs, double *x, double rtol, int maxit, int check_every, int32_t *iters,
+                             double *relres, int32_t *status, void *ws, int64_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && R >= 0 && NNZ >= 0 && iters && relres && status && ws);
+    CNT_CHECK_ARG(rtol > 0 && maxit >= 0 && check_every > 0);
+    for (int s = 0; s < NSYS; s++)
+        CNT_CHECK_ARG(h_sys_net[s] >= 0 && h_sys_net[s] < B && h_sys_slab[s] >= 0 && h_sys_slab[s] < NSLAB);
+    CNT_CHECK_ARG(h_roff[B] == R);
+    if (R > 0) CNT_CHECK_ARG(rowptr && diag && rhs && x && (NNZ == 0 || (col && val)));
+    Layout L;
+    make_layout(NSYS, h_sys_net, h_sys_slab, h_roff, L);
+    int64_t nt = (int64_t)L.tiles.size();
+    int64_t nt_alloc = count_tiles(NSYS, R);
+    cnt::Workspace w(ws, ws_bytes);
+    Tile *d_tiles = w.take<Tile>(nt_alloc);
+    Sys *d_sys = w.take<Sys>(NSYS);
+    Scal *d_scal = w.take<Scal>(NSYS);
+    double *r = w.take<double>((int64_t)NSLAB * R + 1);
+    double *p = w.take<double>((int64_t)NSLAB * R + 1);
+    double *q = w.take<double>((int64_t)NSLAB * R + 1);
+    double *part0 = w.take<double>(nt_alloc);
+    double *part1 = w.take<double>(2 * nt_alloc);
+    int32_t *alldone = w.take<int32_t>(1);
+    if (!alldone) {
+        cnt::set_error("pcg workspace too small: have %lld need %lld", (long long)ws_bytes,
+                       (long long)cnt_pcg_workspace_bytes(NSYS, NSLAB, R));
+        return CNT_ECAPACITY;
+    }
+    CNT_CUDA(cudaMemcpyAsync(d_sys, L.sys.data(), sizeof(Sys) * NSYS, cudaMemcpyHostToDevice, st));
+    if (nt > 0) CNT_CUDA(cudaMemcpyAsync(d_tiles, L.tiles.data(), sizeof(Tile) * nt, cudaMemcpyHostToDevice, st));
+    Ctx c;
+    c.tiles = d_tiles; c.sys = d_sys; c.scal = d_scal; c.R = R; c.NNZ = NNZ;
+    c.rowptr = rowptr; c.col = col; c.val = val; c.diag = diag; c.rhs = rhs;
+    c.x = x; c.r = r; c.p = p; c.q = q; c.part0 = part0; c.part1 = part1;
+    unsigned gs = cnt::grid_for(NSYS, 128);
+    if (nt > 0) {
+        k_init<<<(unsigned)nt, TILE, 0, st>>>(c);
+        CNT_LAUNCHED();
+    }
+    k_scal_init<<<gs, 128, 0, st>>>(c, (int)nt, rtol, NSYS);
+    CNT_LAUNCHED();
+
+    auto enqueue_iter = [&]() -> int {
+        k_spmv<<<(unsigned)nt, TILE, 0, st>>>(c);
+        CNT_LAUNCHED();
+        k_scal_alpha<<<gs, 128, 0, st>>>(c, NSYS);
+        CNT_LAUNCHED();
+        k_update<<<(unsigned)nt, TILE, 0, st>>>(c);
+        CNT_LAUNCHED();
+        k_scal_beta<<<gs, 128, 0, st>>>(c, NSYS, rtol, maxit);
+        CNT_LAUNCHED();
+        k_pupdate<<<(unsigned)nt, TILE, 0, st>>>(c);
+        CNT_LAUNCHED();
+        return CNT_OK;
+    };
+
+    int32_t h_alldone = (nt == 0) ? 1 : 0;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    bool use_graph = (st != nullptr) && nt > 0 && maxit > 0 && !getenv("CNT_NO_GRAPH");
+    int rc = CNT_OK;
+    if (use_graph) {
+        cudaError_t e = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) {
+            use_graph = false;
+            cudaGetLastError();
+        } else {
+            for (int k = 0; k < check_every && rc == CNT_OK; k++) rc = enqueue_iter();
+            e = cudaStreamEndCapture(st, &graph);
+            if (rc != CNT_OK) {
+                if (graph) cudaGraphDestroy(graph);
+                return rc;
+            }
+            if (e != cudaSuccess || cudaGraphInstantiate(&gexec, graph, 0) != cudaSuccess) {
+                cnt::set_error("CUDA graph capture/instantiate failed: %s", cudaGetErrorString(cudaGetLastError()));
+                if (graph) cudaGraphDestroy(graph);
+                return CNT_ECUDA;
+            }
+        }
+    }
+    int done_iters = 0;
+    while (!h_alldone && done_iters < maxit) {
+        if (use_graph) {
+            cudaError_t e = cudaGraphLaunch(gexec, st);
+            cnt::count_launch(5 * check_every);
+            if (e != cudaSuccess) {
+                cnt::set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
+                rc = CNT_ECUDA;
+                break;
+            }
+        } else {
+            for (int k = 0; k < check_every && rc == CNT_OK; k++) rc = enqueue_iter();
+            if (rc) break;
+        }
+        done_iters += check_every;
+        k_set1<<<1, 1, 0, st>>>(alldone);
+        k_export<<<gs, 128, 0, st>>>(c, NSYS, iters, relres, status, alldone);
+        cnt::count_launch(2);
+        cudaError_t e = cudaMemcpyAsync(&h_alldone, alldone, 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            cnt::set_error("pcg poll: %s", cudaGetErrorString(e));
+            rc = CNT_ECUDA;
+            break;
+        }
+    }
+    if (rc == CNT_OK) {
+        k_set1<<<1, 1, 0, st>>>(alldone);
+        k_export<<<gs, 128, 0, st>>>(c, NSYS, iters, relres, status, alldone);
+        cnt::count_launch(2);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            cnt::set_error("pcg export: %s", cudaGetErrorString(e));
+            rc = CNT_ECUDA;
+        }
+    }
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+}

@@ -1,0 +1,353 @@
+"""Batched GPU pipeline: the Python side of the C-ABI (device memory = PyTorch tensors).
+
+One `NetworkBatch` holds B independent stick networks concatenated in HBM (SoA, see
+DESIGN.md "Data layout").  `Engine` drives the stages
+
+    sticks -> junctions -> cluster labels -> CSR pattern -> (gate values -> PCG -> currents)*
+
+each of which is one or a few calls into libcntnet_b200.so.  The reference computes the same
+stages inside `RandomConductingNetwork.__init__` (netsim.py:44-47) and
+`ConductionNetwork.update` (cnet.py:150-156), one network per process.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check
+
+AREA_PARTIAL = [0.5, 0, 0.16, 0.667]      # netsim.py:274, measure_perc.py:184
+AREA_TOTAL = [0.217, 0.5, 0.167, 1.2]     # netsim.py:276, measure_perc.py:180
+
+
+def _p(t):
+    """raw device pointer of a contiguous tensor (None -> NULL)"""
+    if t is None:
+        return None
+    assert t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+class NetworkBatch(object):
+    """Device-resident batch of networks.  Attributes are filled in stage by stage."""
+
+    def __init__(self, h_soff):
+        self.h_soff = [int(v) for v in h_soff]
+        self.B = len(self.h_soff) - 1
+        self.S = self.h_soff[-1]
+        self.c_soff = _lib.i32_array(self.h_soff)
+        # stage outputs
+        self.J = None
+        self.R = None
+        self.NNZ = None
+
+    def n_sticks(self, b):
+        return self.h_soff[b + 1] - self.h_soff[b]
+
+
+class GateState(object):
+    """Per-junction gate-voltage state of a batch, as a small table of distinct voltage
+    levels plus one u8 level id per junction (cnet.py:159-165 semantics: set_global_gate
+    overwrites every junction, set_local_gate only those inside the rectangle)."""
+
+    def __init__(self, engine, batch):
+        self.engine = engine
+        self.batch = batch
+        self.levels = [0.0]
+        self.level = torch.zeros(max(batch.J, 1), dtype=torch.uint8, device=engine.device)
+
+    def clone(self):
+        g = GateState.__new__(GateState)
+        g.engine, g.batch, g.levels = self.engine, self.batch, list(self.levels)
+        g.level = self.level.clone()
+        return g
+
+    def _level_id(self, v):
+        v = float(v)
+        for k, lv in enumerate(self.levels):
+            if lv == v:
+                return k
+        if len(self.levels) >= 255:
+            raise ValueError("more than 255 distinct gate voltages in one gate state")
+        self.levels.append(v)
+        return len(self.levels) - 1
+
+    def set_global(self, voltage):
+        self.levels = [float(voltage)]
+        lib = _lib.load()
+        check(lib.cnt_gate_levels(self.batch.J, _p(self.batch.jx), _p(self.batch.jy), _p(self.level), 1, 0,
+                                  0, 0.0, 0.0, 0.0, 0.0, 0, self.engine.stream_ptr))
+        return self
+
+    def set_local(self, area, voltage):
+        k = self._level_id(voltage)
+        lib = _lib.load()
+        check(lib.cnt_gate_levels(self.batch.J, _p(self.batch.jx), _p(self.batch.jy), _p(self.level), 0, 0,
+                                  1, float(area[0]), float(area[1]), float(area[2]), float(area[3]), k,
+                                  self.engine.stream_ptr))
+        return self
+
+
+class Engine(object):
+    """Owns the CUDA stream and workspaces of one GPU (one process per GPU)."""
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.CntError("networksim_cntfet_b200 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
+        torch.cuda.set_device(self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
+
+    # ------------------------------------------------------------------ helpers
+    def _ws(self, nbytes):
+        return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
+
+    def _dev(self, arr, dtype):
+        t = torch.as_tensor(np.ascontiguousarray(arr), dtype=dtype)
+        return t.to(self.device, non_blocking=False)
+
+    def sync(self):
+        self.stream.synchronize()
+
+    # ------------------------------------------------------------------ stage 0: sticks
+    def batch_from_host(self, tables):
+        """tables: list of dicts with xa,ya,xb,yb,xc,yc,length,kind[,orig] in POST-sort order
+        (the reference's `sticks` DataFrame after netsim.py:133-134)."""
+        soff = np.zeros(len(tables) + 1, dtype=np.int64)
+        soff[1:] = np.cumsum([len(t["xc"]) for t in tables])
+        b = NetworkBatch(soff)
+        cat = lambda k, dt: np.concatenate([np.asarray(t[k], dtype=dt) for t in tables]) if tables else np.zeros(0, dt)
+        with torch.cuda.stream(self.stream):
+            b.soff = self._dev(soff, torch.int32)
+            for k in ("xa", "ya", "xb", "yb", "xc", "yc", "length"):
+                setattr(b, k, self._dev(cat(k, np.float64), torch.float64))
+            b.kind = self._dev(cat("kind", np.uint8), torch.uint8)
+            if all("orig" in t for t in tables):
+                b.orig = self._dev(cat("orig", np.int64), torch.int32)
+            else:
+                b.orig = None
+        return b
+
+    # ------------------------------------------------------------------ stage 1: junctions
+    def find_junctions(self, b):
+        """netsim.py:135-150.  Fills b.stick1, stick2, jx, jy, kind2, joff, ntests."""
+        lib = self.lib
+        with torch.cuda.stream(self.stream):
+            wsb = lib.cnt_junction_workspace_bytes(b.B, b.c_soff)
+            b._jws = self._ws(wsb)
+            jcount = torch.empty(b.S + 1, dtype=torch.int32, device=self.device)
+            b.ntests = torch.zeros(b.B, dtype=torch.int64, device=self.device)
+            check(lib.cnt_junction_count(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                         _p(b.xc), _p(b.yc), _p(b.length), _p(jcount), _p(b.ntests),
+                                         _p(b._jws), b._jws.numel(), self.stream_ptr))
+            sws = self._ws(lib.cnt_scan_workspace_bytes(b.S + 1))
+            jstart = torch.empty(b.S + 1, dtype=torch.int32, device=self.device)
+            check(lib.cnt_exclusive_scan_i32(_p(jcount), _p(jstart), b.S, 1, _p(sws), sws.numel(), self.stream_ptr))
+            flagp = C.c_void_p()
+            check(lib.cnt_junction_errflag_ptr(b.B, b.c_soff, _p(b._jws), b._jws.numel(), C.byref(flagp)))
+            off = flagp.value - b._jws.data_ptr()
+            # one small D2H: total junction count + sortedness flag
+            total = int(jstart[b.S].item())
+            unsorted = int(b._jws[off:off + 4].view(torch.int32).item())
+            if unsorted:
+                raise _lib.CntError("stick table is not sorted by length descending (netsim.py:133)")
+            b.J = total
+            b.jstart = jstart
+            n = max(total, 1)
+            b.stick1 = torch.empty(n, dtype=torch.int32, device=self.device)
+            b.stick2 = torch.empty(n, dtype=torch.int32, device=self.device)
+            b.jx = torch.empty(n, dtype=torch.float64, device=self.device)
+            b.jy = torch.empty(n, dtype=torch.float64, device=self.device)
+            b.kind2 = torch.empty(n, dtype=torch.uint8, device=self.device)
+            b.joff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
+            check(lib.cnt_junction_fill(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                        _p(b.xc), _p(b.yc), _p(b.length), _p(b.kind), _p(jstart), total,
+                                        _p(b.stick1), _p(b.stick2), _p(b.jx), _p(b.jy), _p(b.kind2), _p(b.joff),
+                                        _p(b._jws), b._jws.numel(), self.stream_ptr))
+            b._jws = None
+        return b
+
+    # ------------------------------------------------------------------ stage 2: clusters
+    def label_clusters(self, b):
+        """netsim.py:175-179,197-206; measure_perc.py:76-80.  Fills b.label, b.stats."""
+        lib = self.lib
+        with torch.cuda.stream(self.stream):
+            ws = self._ws(lib.cnt_cluster_workspace_bytes(b.S))
+            b.label = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
+            b.stats = torch.zeros(b.B * _lib.CNT_NSTAT, dtype=torch.int32, device=self.device)
+            check(lib.cnt_label_clusters(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2),
+                                         _p(b.orig), _p(b.label), _p(b.stats), _p(ws), ws.numel(), self.stream_ptr))
+        return b
+
+    # ------------------------------------------------------------------ stage 3: CSR pattern
+    def assemble_pattern(self, b):
+        """cnet.py:104-128 structure: unknown rows + CSR pattern of L_UU (no diagonal)."""
+        lib = self.lib
+        with torch.cuda.stream(self.stream):
+            ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
+            b.urow = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
+            b.roff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
+            check(lib.cnt_assemble_rows(b.B, _p(b.soff), b.S, _p(b.label), _p(b.stats), _p(b.urow), _p(b.roff),
+                                        _p(ws), ws.numel(), self.stream_ptr))
+            b.h_roff = [int(v) for v in b.roff.cpu().tolist()]          # D2H sync (B+1 ints)
+            b.c_roff = _lib.i32_array(b.h_roff)
+            b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()
+            b.R = b.h_roff[-1]
+            R = b.R
+            rowcnt = torch.empty(R + 1, dtype=torch.int32, device=self.device)
+            check(lib.cnt_assemble_pattern_count(b.B, _p(b.soff), _p(b.joff), b.J, _p(b.stick1), _p(b.stick2),
+                                                 _p(b.urow), R, _p(rowcnt), self.stream_ptr))
+            sws = self._ws(lib.cnt_scan_workspace_bytes(R + 1))
+            b.rowptr = torch.empty(R + 1, dtype=torch.int32, device=self.device)
+            check(lib.cnt_exclusive_scan_i32(_p(rowcnt), _p(b.rowptr), R, 1, _p(sws), sws.numel(), self.stream_ptr))
+            b.NNZ = int(b.rowptr[R].item())                              # D2H sync (1 int)
+            n = max(b.NNZ, 1)
+            b.col = torch.empty(n, dtype=torch.int32, device=self.device)
+            b.nz_eid = torch.empty(n, dtype=torch.int32, device=self.device)
+            b.src_eid = torch.empty(max(R, 1), dtype=torch.int32, device=self.device)
+            b.drn_eid = torch.empty(max(R, 1), dtype=torch.int32, device=self.device)
+            b.row_stick = torch.empty(max(R, 1), dtype=torch.int32, device=self.device)
+            check(lib.cnt_assemble_pattern_fill(b.B, _p(b.soff), _p(b.joff), b.J, _p(b.stick1), _p(b.stick2),
+                                                _p(b.urow), _p(b.roff), R, _p(b.rowptr), _p(b.col), _p(b.nz_eid),
+                                                _p(b.src_eid), _p(b.drn_eid), _p(ws), ws.numel(), self.stream_ptr))
+            check(lib.cnt_assemble_row_stick(b.B, _p(b.soff), b.S, _p(b.urow), _p(b.row_stick), self.stream_ptr))
+        return b
+
+    def prepare(self, b):
+        """junctions -> labels -> pattern (everything that does not depend on the gate)."""
+        self.find_junctions(b)
+        self.label_clusters(b)
+        self.assemble_pattern(b)
+        return b
+
+    # ------------------------------------------------------------------ stage 4+5: values + solve
+    def assemble_values(self, b, gates, gtables):
+        """One value pass per gate configuration (cnet.py:99-131).  gates: list of GateState,
+        gtables: list of [9, nlevels] float64 arrays.  Returns dict(g[NS,J], val[NS,NNZ],
+        diag[NS,R], rhs[NS,R])."""
+        lib = self.lib
+        NS = len(gates)
+        R, NNZ, J = b.R, b.NNZ, b.J
+        with torch.cuda.stream(self.stream):
+            g = torch.empty((NS, max(J, 1)), dtype=torch.float64, device=self.device)
+            val = torch.empty((NS, max(NNZ, 1)), dtype=torch.float64, device=self.device)
+            diag = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
+            rhs = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
+            for q, (gs, tab) in enumerate(zip(gates, gtables)):
+                tab = np.ascontiguousarray(tab, dtype=np.float64)
+                assert tab.shape == (9, len(gs.levels))
+                dtab = self._dev(tab, torch.float64)
+                check(lib.cnt_assemble_values(J, _p(b.kind2), _p(gs.level), _p(dtab), tab.shape[1], R, _p(b.rowptr),
+                                              _p(b.nz_eid), _p(b.src_eid), _p(b.drn_eid), _p(g[q]), _p(val[q]),
+                                              _p(diag[q]), _p(rhs[q]), self.stream_ptr))
+        return dict(g=g, val=val, diag=diag, rhs=rhs)
+
+    def solve(self, b, sysm, x0=None, rtol=1e-15, maxit=2000000, check_every=250, nets=None):
+        """Batched Jacobi-PCG (replaces cnet.py:147-149).  sysm: output of assemble_values for
+        NS gate configurations.  Every (configuration q, percolating network) pair is one
+        system of a single solver call; system order is configuration-major.  Returns
+        dict(x[NS,R], iters[NS,B], relres[NS,B], status[NS,B]) (non-percolating networks:
+        iters 0, status 0)."""
+        lib = self.lib
+        NS = sysm["val"].shape[0]
+        R, NNZ, B = b.R, b.NNZ, b.B
+        nets = [n for n in (range(B) if nets is None else nets) if b.h_roff[n + 1] > b.h_roff[n]]
+        with torch.cuda.stream(self.stream):
+            x = torch.zeros((NS, max(R, 1)), dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
+            iters = torch.zeros((NS, B), dtype=torch.int32, device=self.device)
+            relres = torch.zeros((NS, B), dtype=torch.float64, device=self.device)
+            status = torch.zeros((NS, B), dtype=torch.int32, device=self.device)
+            if R > 0 and nets:
+                sys_net = [n for q in range(NS) for n in nets]
+                sys_slab = [q for q in range(NS) for n in nets]
+                nsys = len(sys_net)
+                it = torch.zeros(nsys, dtype=torch.int32, device=self.device)
+                rr = torch.zeros(nsys, dtype=torch.float64, device=self.device)
+                stt = torch.zeros(nsys, dtype=torch.int32, device=self.device)
+                ws = self._ws(lib.cnt_pcg_workspace_bytes(nsys, NS, R))
+                check(lib.cnt_pcg_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab), b.c_roff,
+                                        R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]),
+                                        _p(sysm["rhs"]), _p(x), float(rtol), int(maxit), int(check_every),
+                                        _p(it), _p(rr), _p(stt), _p(ws), ws.numel(), self.stream_ptr))
+                idx_q = torch.as_tensor(sys_slab, device=self.device, dtype=torch.long)
+                idx_n = torch.as_tensor(sys_net, device=self.device, dtype=torch.long)
+                iters[idx_q, idx_n] = it
+                relres[idx_q, idx_n] = rr
+                status[idx_q, idx_n] = stt
+        return dict(x=x, iters=iters, relres=relres, status=status)
+
+    # ------------------------------------------------------------------ stage 6: write-back
+    def currents(self, b, g, x):
+        """cnet.py:132-146 for one configuration: V[S], |I|[J], isrc[B,3]."""
+        lib = self.lib
+        with torch.cuda.stream(self.stream):
+            V = torch.empty(max(b.S, 1), dtype=torch.float64, device=self.device)
+            I = torch.empty(max(b.J, 1), dtype=torch.float64, device=self.device)
+            isrc = torch.zeros((b.B, 3), dtype=torch.float64, device=self.device)
+            check(lib.cnt_currents(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2), _p(b.label),
+                                   _p(b.stats), _p(b.urow), _p(g), _p(x), _p(V), _p(I), _p(isrc), self.stream_ptr))
+        return V, I, isrc
+
+    # ------------------------------------------------------------------ measure_fullnet, batched
+    def fullnet_gates(self, b):
+        """The four gate configurations of measure_fullnet (measure_perc.py:166-186):
+        Vg=0, back gate 10, 'total' top gate 10, 'partial' top gate 10."""
+        with torch.cuda.stream(self.stream):
+            g0 = GateState(self, b)
+            gb = GateState(self, b).set_global(10)
+            gt = GateState(self, b).set_global(0).set_local(AREA_TOTAL, 10)
+            gp = GateState(self, b).set_global(0).set_local(AREA_PARTIAL, 10)
+        return [("ion", g0), ("back", gb), ("total", gt), ("partial", gp)]
+
+    def solve_gates(self, b, gates, onoffmap, element, rtol=1e-15, maxit=2000000, check_every=250, want_fields=False):
+        """Assemble + solve + write back a list of GateStates.  Returns dict with isrc[NS,B,3],
+        iters/relres/status[NS,B] (+ V[NS,S], I[NS,J], g[NS,J], x when want_fields)."""
+        from .elements import conductance_table
+        tabs = [conductance_table(element, onoffmap, gs.levels) for gs in gates]
+        sysm = self.assemble_values(b, gates, tabs)
+        sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every)
+        NS = len(gates)
+        out = dict(iters=sol["iters"], relres=sol["relres"], status=sol["status"])
+        isrc = []
+        Vs, Is = [], []
+        for q in range(NS):
+            V, I, cur = self.currents(b, sysm["g"][q], sol["x"][q])
+            isrc.append(cur)
+            if want_fields:
+                Vs.append(V)
+                Is.append(I)
+        with torch.cuda.stream(self.stream):
+            out["isrc"] = torch.stack(isrc)
+            if want_fields:
+                out.update(V=torch.stack(Vs), I=torch.stack(Is), g=sysm["g"], x=sol["x"], sysm=sysm)
+        return out
+
+    def measure_fullnet(self, b, onoffmap=1, element=None, rtol=1e-15, maxit=2000000, check_every=250,
+                        want_fields=False):
+        """Batched body of measure_perc.measure_fullnet (measure_perc.py:140-203) for a prepared
+        batch: returns a dict of host numpy arrays, one entry per network."""
+        from .elements import LinExpTransistor
+        element = element or LinExpTransistor
+        if b.R is None:
+            self.prepare(b)
+        gates = self.fullnet_gates(b)
+        res = self.solve_gates(b, [g for _, g in gates], onoffmap, element, rtol, maxit, check_every, want_fields)
+        self.sync()
+        st = b.h_stats
+        isrc = res["isrc"].cpu().numpy()          # [4, B, 3]
+        perc = st[:, _lib.STAT_PERCOLATING].astype(bool)
+        cur = np.where(perc[None, :], isrc[:, :, 2], 0.0)     # power form (see currents.cu)
+        out = dict(percolating=perc, nclust=st[:, _lib.STAT_NCLUST_REF].copy(),
+                   maxclust=st[:, _lib.STAT_MAXCLUST_REF].copy(),
+                   nclust_true=st[:, _lib.STAT_NCLUST_TRUE].copy(), maxclust_true=st[:, _lib.STAT_MAXCLUST_TRUE].copy(),
+                   ncomp=st[:, _lib.STAT_NCOMP].copy(), ecomp=st[:, _lib.STAT_ECOMP].copy(),
+                   ion=cur[0], ioff_back=cur[1], ioff_total=cur[2], ioff_partial=cur[3],
+                   isrc_all=isrc, iters=res["iters"].cpu().numpy(), relres=res["relres"].cpu().numpy(),
+                   status=res["status"].cpu().numpy(), ntests=b.ntests.cpu().numpy(),
+                   njunctions=np.diff(b.joff.cpu().numpy()))
+        if want_fields:
+            out["fields"] = res
+        return out

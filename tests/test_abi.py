@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library builds, loads, and exports every symbol include/cntnet_b200.h
+declares (no compute calls without a GPU)."""
+import ctypes
+import os
+import re
+
+from conftest import ROOT
+
+
+def header_symbols():
+    txt = open(os.path.join(ROOT, "include", "cntnet_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(cnt_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_build_and_symbols():
+    from networksim_cntfet_b200 import build
+    lib_path = build.build()
+    assert os.path.isfile(lib_path)
+    lib = ctypes.CDLL(lib_path)
+    syms = header_symbols()
+    assert len(syms) >= 20
+    missing = [s for s in syms if not hasattr(lib, s)]
+    assert not missing, missing
+    lib.cnt_abi_version.restype = ctypes.c_int
+    assert lib.cnt_abi_version() == 1
+
+
+def test_binding_covers_header():
+    from networksim_cntfet_b200 import _lib
+    assert sorted(_lib.PROTOTYPES) == header_symbols()
+    lib = _lib.load()
+    lib.cnt_launch_count.restype = ctypes.c_int64
+    assert lib.cnt_launch_count() >= 0
+
+
+def test_workspace_queries_are_host_only():
+    from networksim_cntfet_b200 import _lib
+    lib = _lib.load()
+    assert lib.cnt_scan_workspace_bytes(10 ** 6) >= 4 * 245
+    assert lib.cnt_cluster_workspace_bytes(1000) >= 9000
+    soff = _lib.i32_array([0, 302, 6704])
+    assert lib.cnt_junction_workspace_bytes(2, soff) > 6704 * 64
+
+
+def test_no_cpu_fallback_without_gpu():
+    import pytest
+    import torch
+    from networksim_cntfet_b200 import _lib
+    from networksim_cntfet_b200.engine import Engine
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(_lib.CntError):
+        Engine()

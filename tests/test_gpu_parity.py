@@ -1,0 +1,246 @@
+"""GPU: parity of the CUDA path (through the C-ABI) against the golden vectors produced by
+the unmodified reference and against the numpy oracle on the same seeded inputs.
+
+Bars: junction sets, junction coordinates, kind codes, cluster labels and cluster statistics
+BIT-EXACT; voltages within 1e-9 * Vds (norm-wise), edge currents within 1e-9 relative plus the
+voltage tolerance times the conductance, source current within 1e-9 relative of the refined
+oracle (the raw reference itself is only ~2e-9 accurate at Vg=+10).
+"""
+import numpy as np
+import pytest
+
+from conftest import FULLNET_GATES, golden_element, golden_names, golden_sticks, load_golden
+from oracle import cntnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+NAMES = golden_names()
+VDS = 0.1
+
+
+def _element(name):
+    from networksim_cntfet_b200 import elements
+    return elements.FermiDiracTransistor if name == "fermidirac" else elements.LinExpTransistor
+
+
+def _junction_slices(b):
+    joff = b.joff.cpu().numpy()
+    arr = {k: getattr(b, k).cpu().numpy() for k in ("stick1", "stick2", "jx", "jy", "kind2")}
+    return [{k: v[joff[i]:joff[i + 1]] for k, v in arr.items()} for i in range(b.B)]
+
+
+def _check_junctions(j, g):
+    assert len(j["stick1"]) == len(g["stick1"]), (len(j["stick1"]), len(g["stick1"]))
+    assert np.array_equal(j["stick1"], g["stick1"])
+    assert np.array_equal(j["stick2"], g["stick2"])
+    assert np.array_equal(j["jx"], g["jx"])      # bit-exact FP64 coordinates
+    assert np.array_equal(j["jy"], g["jy"])
+    assert np.array_equal(j["kind2"], g["kind2"])
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_junctions_single(engine, name):
+    g = load_golden(name)
+    b = engine.find_junctions(engine.batch_from_host([golden_sticks(g)]))
+    _check_junctions(_junction_slices(b)[0], g)
+    ref_tests = O.find_junctions(golden_sticks(g))["ntests"]
+    assert int(b.ntests.cpu()[0]) == ref_tests          # same candidate set as the KD-tree ball
+
+
+def test_junctions_and_clusters_ragged_batch(engine):
+    """all goldens in ONE batch (ragged sizes 6 ... 6402 sticks, percolating or not)"""
+    gs = [load_golden(n) for n in NAMES]
+    b = engine.batch_from_host([golden_sticks(g) for g in gs])
+    engine.find_junctions(b)
+    engine.label_clusters(b)
+    js = _junction_slices(b)
+    label = b.label.cpu().numpy()
+    stats = b.stats.cpu().numpy().reshape(b.B, -1)
+    from networksim_cntfet_b200 import _lib
+    for i, g in enumerate(gs):
+        _check_junctions(js[i], g)
+        lab = label[b.h_soff[i]:b.h_soff[i + 1]]
+        assert np.array_equal(lab, g["label"]), g["name"]
+        assert bool(stats[i, _lib.STAT_PERCOLATING]) == bool(g["percolating"])
+        assert stats[i, _lib.STAT_NCLUST_REF] == int(g["nclust_ref"])
+        assert stats[i, _lib.STAT_MAXCLUST_REF] == int(g["maxclust_ref"])
+        sizes = np.bincount(g["label"])
+        assert stats[i, _lib.STAT_NCLUST_TRUE] == int((sizes > 0).sum())
+        assert stats[i, _lib.STAT_MAXCLUST_TRUE] == int(sizes.max())
+        if g["percolating"]:
+            assert stats[i, _lib.STAT_NCOMP] == int((g["label"] == 0).sum())
+            assert stats[i, _lib.STAT_ECOMP] == int((g["label"][g["stick1"]] == 0).sum())
+
+
+def test_scan(engine):
+    import torch
+    from networksim_cntfet_b200 import _lib
+    from networksim_cntfet_b200.engine import _p
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    for n in (1, 5, 4096, 4097, 100003, 3_000_001):
+        a = rng.integers(0, 7, size=n).astype(np.int32)
+        with torch.cuda.stream(engine.stream):
+            t = torch.as_tensor(a).to(engine.device)
+            out = torch.empty(n + 1, dtype=torch.int32, device=engine.device)
+            ws = engine._ws(lib.cnt_scan_workspace_bytes(n))
+            _lib.check(lib.cnt_exclusive_scan_i32(_p(t), _p(out), n, 1, _p(ws), ws.numel(), engine.stream_ptr))
+        engine.sync()
+        ref = np.concatenate([[0], np.cumsum(a)])
+        assert np.array_equal(out.cpu().numpy(), ref)
+
+
+def _oracle_fields(g, tag, gate, vg, refine=3):
+    el, om = golden_element(g), int(g["onoffmap"])
+    vgj = O.gate_voltages(g["jx"], g["jy"], gate, vg)
+    cond = O.conductance(g["kind2"], vgj, om, el)
+    r = O.solve_network(len(g["xc"]), g["stick1"], g["stick2"], cond, g["label"], refine=refine)
+    return cond, r
+
+
+PERC = [n for n in NAMES if "noperc" not in n and "n3600" not in n]
+
+
+@pytest.mark.parametrize("name", PERC)
+def test_assembly_matches_oracle(engine, name):
+    """CSR of L_UU (pattern, values, diagonal, rhs) equals the oracle's matrix entry by entry."""
+    from networksim_cntfet_b200.engine import GateState
+    from networksim_cntfet_b200.elements import conductance_table
+    g = load_golden(name)
+    b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    gs = GateState(engine, b).set_global(10)
+    tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
+    sysm = engine.assemble_values(b, [gs], [tab])
+    engine.sync()
+    cond, r = _oracle_fields(g, "_back", "back", 10.0, refine=0)
+    assert np.array_equal(sysm["g"][0].cpu().numpy()[:b.J], cond)       # bit-identical conductances
+    A = r["A"].tocsr()
+    A.sort_indices()
+    R = A.shape[0]
+    assert b.R == R
+    rowptr = b.rowptr.cpu().numpy()
+    col = b.col.cpu().numpy()[:b.NNZ]
+    val = sysm["val"][0].cpu().numpy()[:b.NNZ]
+    diag = sysm["diag"][0].cpu().numpy()[:R]
+    rhs = sysm["rhs"][0].cpu().numpy()[:R]
+    import scipy.sparse as sp
+    M = sp.csr_matrix((val, col, rowptr), shape=(R, R)) + sp.diags(diag)
+    D = (M - A).tocoo()
+    assert np.all(np.abs(D.data) <= 1e-15 * np.abs(A.diagonal()).max())
+    offd = sp.csr_matrix((val, col, rowptr), shape=(R, R))
+    offd.sort_indices()
+    Aoff = (A - sp.diags(A.diagonal())).tocsr()
+    Aoff.eliminate_zeros()
+    Aoff.sort_indices()
+    assert np.array_equal(offd.indptr, Aoff.indptr) and np.array_equal(offd.indices, Aoff.indices)
+    assert np.array_equal(offd.data, Aoff.data)                           # off-diagonals bit-exact
+    assert np.array_equal(rhs, r["rhs"])
+    assert np.array_equal(b.row_stick.cpu().numpy()[:R], r["nodes_u"])
+
+
+@pytest.mark.parametrize("name", PERC)
+def test_fullnet_solve(engine, name):
+    """measure_fullnet gate sequence: V, |I|, I_source against refined oracle and raw reference."""
+    g = load_golden(name)
+    b = engine.batch_from_host([golden_sticks(g)])
+    res = engine.measure_fullnet(b, onoffmap=int(g["onoffmap"]), element=_element(golden_element(g)),
+                                 want_fields=True)
+    assert res["percolating"][0]
+    assert np.all(res["status"] == 0), res["status"]
+    f = res["fields"]
+    for q, (tag, gate, vg) in enumerate(FULLNET_GATES):
+        cond, r = _oracle_fields(g, tag, gate, vg)
+        V = f["V"][q].cpu().numpy()[:b.S]
+        I = f["I"][q].cpu().numpy()[:b.J]
+        assert np.array_equal(np.isnan(V), np.isnan(r["V"]))
+        m = ~np.isnan(r["V"])
+        assert np.max(np.abs(V[m] - r["V"][m])) <= 1e-9 * VDS, (tag, np.max(np.abs(V[m] - r["V"][m])))
+        me = ~np.isnan(r["I"])
+        assert np.array_equal(np.isnan(I), ~me)
+        assert np.all(np.abs(I[me] - r["I"][me]) <= 1e-9 * np.abs(r["I"][me]) + cond[me] * 2e-10 * VDS)
+        isrc = res["isrc_all"][q, 0]
+        # power form vs refined oracle: 1e-9 relative (north star); drain-side sum agrees too
+        assert abs(isrc[2] - r["I_source"]) <= 1e-9 * r["I_source"], (tag, isrc, r["I_source"])
+        assert abs(isrc[1] - r["I_source"]) <= 1e-7 * r["I_source"]
+        assert abs(isrc[0] - r["I_source"]) <= 1e-5 * r["I_source"]
+        # raw reference (its own solve error dominates at Vg=+10)
+        ref = float(g["isrc0" if tag == "0" else "isrc" + tag])
+        assert abs(isrc[2] - ref) <= (5e-9 if gate == "back" else 1e-9) * ref
+        Vref = g["V0" if tag == "0" else "V" + tag]
+        assert np.max(np.abs(V[m] - Vref[m])) <= 1e-9 * VDS
+
+
+def test_fullnet_batch_matches_single(engine):
+    """A ragged batch gives the same per-network rows as one-network batches (deterministic,
+    batch-composition independent reductions), and non-percolating networks report zeros."""
+    names = ["s5_n300_seed1", "s5_n120_seed5_noperc", "trivial", "s5_n300_seed2_om1", "s20_n3600_seed7"]
+    gs = [load_golden(n) for n in names]
+    b = engine.batch_from_host([golden_sticks(g) for g in gs])
+    res = engine.measure_fullnet(b, onoffmap=1)
+    for i, g in enumerate(gs):
+        one = engine.measure_fullnet(engine.batch_from_host([golden_sticks(g)]), onoffmap=1)
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            assert res[k][i] == one[k][0], (g["name"], k)            # bit-identical
+        assert res["percolating"][i] == bool(g["percolating"])
+        if not g["percolating"]:
+            assert res["ion"][i] == 0.0 and res["ioff_back"][i] == 0.0
+        assert res["nclust"][i] == int(g["nclust_ref"]) and res["maxclust"][i] == int(g["maxclust_ref"])
+
+
+def test_edge_cases(engine):
+    """empty-ish networks: electrodes only; a network without any junction; parallel sticks."""
+    e = dict(xc=np.array([0.01, 0.99]), yc=np.array([0.5, 0.5]), angle=np.full(2, np.pi / 2 - 1e-6),
+             length=np.array([100.0, 100.0]), kind=np.zeros(2, np.uint8))
+    e = O.sticks_with_ends(e)
+    e["orig"] = np.array([0, 1])
+    lone = dict(xc=np.array([0.01, 0.99, 0.5]), yc=np.array([0.5, 0.5, 0.5]),
+                angle=np.array([np.pi / 2 - 1e-6, np.pi / 2 - 1e-6, 0.3]), length=np.array([100.0, 100.0, 0.1]),
+                kind=np.array([0, 0, 2], np.uint8))
+    lone = O.sticks_with_ends(lone)
+    lone["orig"] = np.array([0, 2, 1])
+    vert = dict(xc=np.array([0.01, 0.99, 0.5, 0.5]), yc=np.array([0.5, 0.5, 0.5, 0.5]),
+                angle=np.array([np.pi / 2 - 1e-6, np.pi / 2 - 1e-6, 0.0, 0.0]),
+                length=np.array([100.0, 100.0, 0.99, 0.5]), kind=np.array([0, 0, 1, 2], np.uint8))
+    vert = O.sticks_with_ends(vert)   # two collinear horizontal sticks: equal slopes -> no junction between them
+    vert["orig"] = np.array([0, 3, 1, 2])
+    b = engine.batch_from_host([e, lone, vert])
+    res = engine.measure_fullnet(b, onoffmap=0)
+    for i, s in enumerate((e, lone, vert)):
+        j = O.find_junctions(s, pruner="brute")
+        c = O.label_clusters(len(s["xc"]), j["stick1"], j["stick2"], s["orig"])
+        assert res["njunctions"][i] == len(j["stick1"])
+        assert res["percolating"][i] == c["percolating"]
+        assert res["nclust"][i] == c["nclust_ref"] and res["maxclust"][i] == c["maxclust_ref"]
+    # `vert`: the long horizontal stick touches both electrodes -> percolates through one node
+    m = O.measure_fullnet(vert, onoffmap=0, refine=2)
+    assert res["percolating"][2] and abs(res["ion"][2] - m["ion"]) <= 1e-12 * m["ion"]
+
+
+def test_unsorted_table_is_rejected(engine):
+    from networksim_cntfet_b200._lib import CntError
+    g = load_golden("s5_n300_seed1")
+    s = golden_sticks(g)
+    s = {k: v[::-1].copy() for k, v in s.items()}
+    with pytest.raises(CntError):
+        engine.find_junctions(engine.batch_from_host([s]))
+
+
+@pytest.mark.parametrize("n,scaling,seed", [(2500, 20, 11), (30000, 60, 12)])
+def test_seeded_vs_oracle(engine, n, scaling, seed):
+    """same seeded inputs, sizes the oracle finishes in seconds: full pipeline vs oracle"""
+    s = O.sticks_with_ends(O.canonical_sort(O.make_sticks_mt19937(n, "exp", 0.135, scaling, seed)))
+    b = engine.batch_from_host([s])
+    res = engine.measure_fullnet(b, onoffmap=1)
+    j = O.find_junctions(s)
+    js = _junction_slices(b)[0]
+    _check_junctions(js, dict(stick1=j["stick1"], stick2=j["stick2"], jx=j["x"], jy=j["y"], kind2=j["kind2"]))
+    assert int(res["ntests"][0]) == j["ntests"]
+    c = O.label_clusters(n + 2, j["stick1"], j["stick2"], s["orig"])
+    assert np.array_equal(b.label.cpu().numpy()[:n + 2], c["label"])
+    m = O.measure_fullnet(s, onoffmap=1, junctions=j, refine=3)
+    assert res["percolating"][0] == m["percolating"]
+    assert res["nclust"][0] == m["nclust_ref"] and res["maxclust"][0] == m["maxclust_ref"]
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        if m["percolating"]:
+            assert abs(res[k][0] - m[k]) <= 1e-9 * m[k], (k, res[k][0], m[k])
+        else:
+            assert res[k][0] == 0.0
