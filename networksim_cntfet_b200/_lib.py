@@ -45,8 +45,7 @@ PROTOTYPES = {
 }
 # entry points that may be absent from an older build of the library (checked by tests
 # against the header, never silently replaced)
-OPTIONAL = {"cnt_gen_sticks_workspace_bytes", "cnt_gen_sticks", "cnt_pcg_cluster_workspace_bytes",
-            "cnt_pcg_cluster_solve"}
+OPTIONAL = {"cnt_pcg_cluster_workspace_bytes", "cnt_pcg_cluster_solve"}
 
 
 class CntError(RuntimeError):

@@ -9,6 +9,7 @@ each of which is one or a few calls into libcntnet_b200.so.  The reference compu
 stages inside `RandomConductingNetwork.__init__` (netsim.py:44-47) and
 `ConductionNetwork.update` (cnet.py:150-156), one network per process.
 """
+import contextlib
 import ctypes as C
 
 import numpy as np
@@ -55,12 +56,14 @@ class GateState(object):
         self.engine = engine
         self.batch = batch
         self.levels = [0.0]
-        self.level = torch.zeros(max(batch.J, 1), dtype=torch.uint8, device=engine.device)
+        with engine._work():
+            self.level = torch.zeros(max(batch.J, 1), dtype=torch.uint8, device=engine.device)
 
     def clone(self):
         g = GateState.__new__(GateState)
         g.engine, g.batch, g.levels = self.engine, self.batch, list(self.levels)
-        g.level = self.level.clone()
+        with self.engine._work():
+            g.level = self.level.clone()
         return g
 
     def _level_id(self, v):
@@ -76,16 +79,18 @@ class GateState(object):
     def set_global(self, voltage):
         self.levels = [float(voltage)]
         lib = _lib.load()
-        check(lib.cnt_gate_levels(self.batch.J, _p(self.batch.jx), _p(self.batch.jy), _p(self.level), 1, 0,
-                                  0, 0.0, 0.0, 0.0, 0.0, 0, self.engine.stream_ptr))
+        with self.engine._work():
+            check(lib.cnt_gate_levels(self.batch.J, _p(self.batch.jx), _p(self.batch.jy), _p(self.level), 1, 0,
+                                      0, 0.0, 0.0, 0.0, 0.0, 0, self.engine.stream_ptr))
         return self
 
     def set_local(self, area, voltage):
         k = self._level_id(voltage)
         lib = _lib.load()
-        check(lib.cnt_gate_levels(self.batch.J, _p(self.batch.jx), _p(self.batch.jy), _p(self.level), 0, 0,
-                                  1, float(area[0]), float(area[1]), float(area[2]), float(area[3]), k,
-                                  self.engine.stream_ptr))
+        with self.engine._work():
+            check(lib.cnt_gate_levels(self.batch.J, _p(self.batch.jx), _p(self.batch.jy), _p(self.level), 0, 0,
+                                      1, float(area[0]), float(area[1]), float(area[2]), float(area[3]), k,
+                                      self.engine.stream_ptr))
         return self
 
 
@@ -102,6 +107,22 @@ class Engine(object):
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
 
     # ------------------------------------------------------------------ helpers
+    @contextlib.contextmanager
+    def _work(self):
+        """Run a stage on the engine's stream with stream-ordered semantics towards the caller:
+        the engine stream first waits for the caller's current stream, and on exit the caller's
+        stream waits for the engine stream, so results can be consumed with ordinary torch ops.
+        (A dedicated non-default stream is needed because the PCG loop is captured into a CUDA
+        graph, which the legacy default stream does not allow.)"""
+        cur = torch.cuda.current_stream(self.device)
+        if cur == self.stream:
+            yield
+            return
+        self.stream.wait_stream(cur)
+        with torch.cuda.stream(self.stream):
+            yield
+        cur.wait_stream(self.stream)
+
     def _ws(self, nbytes):
         return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
 
@@ -120,7 +141,7 @@ class Engine(object):
         soff[1:] = np.cumsum([len(t["xc"]) for t in tables])
         b = NetworkBatch(soff)
         cat = lambda k, dt: np.concatenate([np.asarray(t[k], dtype=dt) for t in tables]) if tables else np.zeros(0, dt)
-        with torch.cuda.stream(self.stream):
+        with self._work():
             b.soff = self._dev(soff, torch.int32)
             for k in ("xa", "ya", "xb", "yb", "xc", "yc", "length"):
                 setattr(b, k, self._dev(cat(k, np.float64), torch.float64))
@@ -131,11 +152,48 @@ class Engine(object):
                 b.orig = None
         return b
 
+    def generate(self, ns, scaling, seed, net_id0=0, pm=0.135, l="exp"):
+        """netsim.py:105-134 on the GPU: len(ns) networks, network k has ns[k] body sticks plus
+        the two electrodes, drawn from Philox keyed by (seed, net_id0 + k), sorted canonically
+        (source, drain, then length descending).  `scaling` is a number or one per network."""
+        ns = [int(n) for n in ns]
+        soff = np.zeros(len(ns) + 1, dtype=np.int64)
+        soff[1:] = np.cumsum([n + 2 for n in ns])
+        b = NetworkBatch(soff)
+        sc = np.broadcast_to(np.asarray(scaling, dtype=np.float64), (len(ns),)).copy()
+        lib = self.lib
+        with self._work():
+            b.soff = self._dev(soff, torch.int32)
+            dsc = self._dev(sc, torch.float64)
+            S = max(b.S, 1)
+            for k in ("xa", "ya", "xb", "yb", "xc", "yc", "length", "angle"):
+                setattr(b, k, torch.empty(S, dtype=torch.float64, device=self.device))
+            b.kind = torch.empty(S, dtype=torch.uint8, device=self.device)
+            b.orig = torch.empty(S, dtype=torch.int32, device=self.device)
+            ws = self._ws(lib.cnt_gen_sticks_workspace_bytes(b.S, b.B))
+            len_mode = 0 if isinstance(l, str) else 1
+            if isinstance(l, str) and l != "exp":
+                raise ValueError("invalid L value")          # netsim.py:114-115
+            check(lib.cnt_gen_sticks(int(seed) & (2 ** 64 - 1), int(net_id0), b.B, _p(b.soff), b.c_soff, _p(dsc),
+                                     float(pm), len_mode, 0.0 if len_mode == 0 else float(l),
+                                     _p(b.xc), _p(b.yc), _p(b.angle), _p(b.length), _p(b.kind),
+                                     _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb), _p(b.orig),
+                                     _p(ws), ws.numel(), self.stream_ptr))
+        b.scaling = sc
+        return b
+
+    def sticks_to_host(self, b):
+        """list of per-network dicts of numpy arrays (the reference's `sticks` columns)."""
+        keys = [k for k in ("xc", "yc", "angle", "length", "kind", "xa", "ya", "xb", "yb", "orig")
+                if getattr(b, k, None) is not None]
+        host = {k: getattr(b, k).cpu().numpy() for k in keys}
+        return [{k: host[k][b.h_soff[i]:b.h_soff[i + 1]].copy() for k in keys} for i in range(b.B)]
+
     # ------------------------------------------------------------------ stage 1: junctions
     def find_junctions(self, b):
         """netsim.py:135-150.  Fills b.stick1, stick2, jx, jy, kind2, joff, ntests."""
         lib = self.lib
-        with torch.cuda.stream(self.stream):
+        with self._work():
             wsb = lib.cnt_junction_workspace_bytes(b.B, b.c_soff)
             b._jws = self._ws(wsb)
             jcount = torch.empty(b.S + 1, dtype=torch.int32, device=self.device)
@@ -174,7 +232,7 @@ class Engine(object):
     def label_clusters(self, b):
         """netsim.py:175-179,197-206; measure_perc.py:76-80.  Fills b.label, b.stats."""
         lib = self.lib
-        with torch.cuda.stream(self.stream):
+        with self._work():
             ws = self._ws(lib.cnt_cluster_workspace_bytes(b.S))
             b.label = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.stats = torch.zeros(b.B * _lib.CNT_NSTAT, dtype=torch.int32, device=self.device)
@@ -186,7 +244,7 @@ class Engine(object):
     def assemble_pattern(self, b):
         """cnet.py:104-128 structure: unknown rows + CSR pattern of L_UU (no diagonal)."""
         lib = self.lib
-        with torch.cuda.stream(self.stream):
+        with self._work():
             ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
             b.urow = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.roff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
@@ -231,7 +289,7 @@ class Engine(object):
         lib = self.lib
         NS = len(gates)
         R, NNZ, J = b.R, b.NNZ, b.J
-        with torch.cuda.stream(self.stream):
+        with self._work():
             g = torch.empty((NS, max(J, 1)), dtype=torch.float64, device=self.device)
             val = torch.empty((NS, max(NNZ, 1)), dtype=torch.float64, device=self.device)
             diag = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
@@ -255,7 +313,7 @@ class Engine(object):
         NS = sysm["val"].shape[0]
         R, NNZ, B = b.R, b.NNZ, b.B
         nets = [n for n in (range(B) if nets is None else nets) if b.h_roff[n + 1] > b.h_roff[n]]
-        with torch.cuda.stream(self.stream):
+        with self._work():
             x = torch.zeros((NS, max(R, 1)), dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
             iters = torch.zeros((NS, B), dtype=torch.int32, device=self.device)
             relres = torch.zeros((NS, B), dtype=torch.float64, device=self.device)
@@ -283,7 +341,7 @@ class Engine(object):
     def currents(self, b, g, x):
         """cnet.py:132-146 for one configuration: V[S], |I|[J], isrc[B,3]."""
         lib = self.lib
-        with torch.cuda.stream(self.stream):
+        with self._work():
             V = torch.empty(max(b.S, 1), dtype=torch.float64, device=self.device)
             I = torch.empty(max(b.J, 1), dtype=torch.float64, device=self.device)
             isrc = torch.zeros((b.B, 3), dtype=torch.float64, device=self.device)
@@ -295,7 +353,7 @@ class Engine(object):
     def fullnet_gates(self, b):
         """The four gate configurations of measure_fullnet (measure_perc.py:166-186):
         Vg=0, back gate 10, 'total' top gate 10, 'partial' top gate 10."""
-        with torch.cuda.stream(self.stream):
+        with self._work():
             g0 = GateState(self, b)
             gb = GateState(self, b).set_global(10)
             gt = GateState(self, b).set_global(0).set_local(AREA_TOTAL, 10)
@@ -319,7 +377,7 @@ class Engine(object):
             if want_fields:
                 Vs.append(V)
                 Is.append(I)
-        with torch.cuda.stream(self.stream):
+        with self._work():
             out["isrc"] = torch.stack(isrc)
             if want_fields:
                 out.update(V=torch.stack(Vs), I=torch.stack(Is), g=sysm["g"], x=sol["x"], sysm=sysm)
