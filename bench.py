@@ -1,0 +1,335 @@
+#!/usr/bin/env python3
+"""Headline benchmark: networks/sec on the 100x100 um ensemble (BASELINE.json configs[2]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+A "step" is one pass of the whole hot path over one batch of synthetic networks per GPU:
+Philox stick placement -> cell-list junction finder -> union-find labels -> MNA assembly ->
+the four measure_fullnet solves (Vg=0, back 10, total 10, partial 10; measure_perc.py:166-186)
+by batched Jacobi-PCG -> currents.  Every step draws fresh seeds.  One process per GPU; for
+N>1 launch through torch.distributed.run -- ranks share nothing but a final all-gather of
+the per-network statistics rows (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = networks/s timed with CUDA events on the engine's
+stream (max over ranks); `e2e` = the same through the public host API
+(networksim_cntfet_b200.measure_perc.measure_ensemble: pinned host ns/seeds in, pandas rows
+out, wall clock between synchronisations); `roofline` = the PCG solver's algorithmic bytes
+over its CUDA-event time against the measured HBM peak; `cpu_baseline` = the numpy/scipy
+oracle port of the reference path on the host cores, on a bounded sample.
+
+`--impl reference` times that CPU port with all host cores and prints the same line with
+"impl": "reference" (the unmodified reference needs >10 min per 100x100 um network and does
+not exist on the GPU box; see DESIGN.md "CPU baseline").
+"""
+import argparse
+import json
+import multiprocessing
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "networks/sec at 100x100um ensemble"
+UNIT = "networks/s"
+
+
+def workload(args):
+    return {
+        "workload": "ensemble of %dx%d um networks, n=%d sticks (+2 electrodes) each, density %.3g /um^2, "
+                    "measure_fullnet (4 solves: Vg=0, back/total/partial gate 10 V), LinExp element, onoffmap %d"
+                    % (args.scaling, args.scaling, args.n, args.n / args.scaling ** 2, args.onoffmap),
+        "networks_per_gpu_per_step": args.batch, "n": args.n, "scaling": args.scaling, "onoffmap": args.onoffmap,
+        "pcg_rtol": args.rtol, "solver": args.solver,
+        "l2": "working set per step (%d networks x ~34 MB) exceeds the 126 MB L2; fresh seeds every step"
+              % args.batch,
+    }
+
+
+# ------------------------------------------------------------------------- CPU port (baseline)
+def _cpu_one(job):
+    n, scaling, seed, onoffmap = job
+    from oracle import cntnet_oracle as O
+    s = O.sticks_with_ends(O.canonical_sort(O.make_sticks_mt19937(n, "exp", 0.135, scaling, seed)))
+    m = O.measure_fullnet(s, onoffmap=onoffmap)
+    return m["ion"], m["ntests"]
+
+
+def cpu_run(n, scaling, onoffmap, count, cores, seed0):
+    jobs = [(n, scaling, seed0 + k, onoffmap) for k in range(count)]
+    t0 = time.perf_counter()
+    with multiprocessing.get_context("fork").Pool(cores) as pool:
+        out = pool.map(_cpu_one, jobs, chunksize=1)
+    dt = time.perf_counter() - t0
+    return count / dt, dt, out
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    per_step = min(cores, args.cpu_sample or cores)
+    for k in range(args.warmup):
+        cpu_run(args.n, args.scaling, args.onoffmap, per_step, cores, 10_000 + k * per_step)
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        cpu_run(args.n, args.scaling, args.onoffmap, per_step, cores, 20_000 + k * per_step)
+    dt = time.perf_counter() - t0
+    value = args.steps * per_step / dt
+    sample = ("%d networks per step on %d processes; numpy/scipy oracle port of measure_fullnet "
+              "(MT19937 sticks, cKDTree pruning + vectorised predicate, SuperLU x4)" % (per_step, cores))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------- clocks
+class ClockSampler(object):
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+# ------------------------------------------------------------------------- GPU arm
+PCG_BYTES_PER_NNZ = 12     # val f64 + col i32 per off-diagonal entry
+PCG_BYTES_PER_ROW = 116    # SpMV 28 (rowptr, diag, p, q) + update 56 (x rw, r rw, p, q, diag) + p-update 32
+
+
+def pcg_algorithmic_bytes(res):
+    """sum over systems of iterations x (12*nnz_offdiag + 116*rows); DESIGN.md 'Kernels'"""
+    it = res["iters"].astype("float64")                     # [4, B]
+    per_iter = PCG_BYTES_PER_NNZ * res["nnz_offdiag"].astype("float64") + PCG_BYTES_PER_ROW * res["rows"].astype("float64")
+    return float((it * per_iter[None, :]).sum()), float(it.sum())
+
+
+def gpu_arm(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    from networksim_cntfet_b200 import _lib, measure_perc
+    from networksim_cntfet_b200.engine import Engine, network_seeds
+    eng = Engine("cuda:%d" % local, profile=True)
+    eng.solver = args.solver
+    measure_perc.set_engine(eng)
+    lib = _lib.load()
+    B = args.batch
+    ns = [args.n] * B
+
+    def seeds_for(phase, step):
+        return network_seeds(args.seed + phase, (step * world + rank) * B, B)
+
+    def barrier():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def gather_rows(rows):
+        """the path's only collective: all-gather of the per-network statistics rows"""
+        if world == 1:
+            return rows
+        t = torch.as_tensor(rows, dtype=torch.float64, device=eng.device)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return torch.cat(out).cpu().numpy()
+
+    def device_step(phase, step):
+        res = eng.measure_ensemble(ns, args.scaling, seeds_for(phase, step), onoffmap=args.onoffmap, rtol=args.rtol,
+                                   check_every=args.check_every)
+        rows = np.stack([res["percolating"].astype(np.float64), res["ion"], res["ioff_back"], res["ioff_total"],
+                         res["ioff_partial"], res["nclust"].astype(np.float64), res["maxclust"].astype(np.float64)], 1)
+        gather_rows(rows)
+        return res
+
+    # ---- warm-up
+    for k in range(args.warmup):
+        device_step(0, k)
+    eng.stage_times_ms(reset=True)
+    barrier()
+
+    # ---- timed: device-side value
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = lib.cnt_launch_count()
+    e0 = torch.cuda.Event(enable_timing=True)
+    e1 = torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record(eng.stream)
+    results = [device_step(1, k) for k in range(args.steps)]
+    e1.record(eng.stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = lib.cnt_launch_count() - launches0
+    dev_ms = e0.elapsed_time(e1)
+    stages = eng.stage_times_ms(reset=True)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # ---- timed: end to end through the public host API
+    measure_perc.measure_ensemble(ns, args.scaling, seeds_for(2, 0), onoffmap=args.onoffmap, rtol=args.rtol)  # warm
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for k in range(args.steps):
+        df, io = measure_perc.measure_ensemble(ns, args.scaling, seeds_for(3, k), onoffmap=args.onoffmap,
+                                               rtol=args.rtol, return_io=True)
+        gather_rows(df[["ion", "ioff"]].to_numpy(dtype=np.float64))
+        h2d, d2h = io["h2d_bytes"], io["d2h_bytes"]
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    # ---- reduce over ranks (max time)
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=eng.device)
+    cnt = torch.tensor([float(launches)], dtype=torch.float64, device=eng.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+    dev_ms, e2e_ms, wall_ms = [float(v) for v in tt.cpu()]
+    total_networks = args.steps * B * world
+    value = total_networks / (dev_ms / 1e3)
+    e2e_value = total_networks / (e2e_ms / 1e3)
+
+    if rank == 0:
+        # roofline of the dominant stage (PCG) from this rank's timed steps
+        nbytes = iters = 0.0
+        ntests = 0
+        for res in results:
+            b_, i_ = pcg_algorithmic_bytes(res)
+            nbytes += b_
+            iters += i_
+            ntests += int(res["ntests"].sum())
+        pcg_s = stages.get("pcg", 0.0) / 1e3
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        achieved = nbytes / pcg_s / 1e9 if pcg_s > 0 else 0.0
+        roofline = {"bound": "hbm", "kernel": "batched Jacobi-PCG (%s)" % (eng.last_solver or args.solver), "achieved": achieved,
+                    "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                    "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                    "algorithmic_bytes": nbytes, "pcg_iterations": iters, "pcg_seconds": pcg_s,
+                    "bytes_per_iteration": "12*nnz_offdiag + 116*rows per system"}
+        jt = stages.get("junctions", 0.0) / 1e3
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload(args), "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(cnt.item()), "clocks": clocks,
+            "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
+            "junction_tests_per_s": (ntests / jt) if jt > 0 else None, "junction_tests": ntests,
+            "wall_ms_per_step": wall_ms / max(args.steps, 1),
+            "percolating_fraction": float(np.mean([r["percolating"].mean() for r in results])),
+            "pcg_iters_mean_per_solve": [float(np.mean([r["iters"][q].mean() for r in results])) for q in range(4)],
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            count = min(cores, args.cpu_sample or cores)
+            v, dt, _ = cpu_run(args.n, args.scaling, args.onoffmap, count, cores, 30_000)
+            line["cpu_baseline"] = {
+                "value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                "sample": "%d networks of the same workload on %d processes (%.1f s); numpy/scipy oracle port of "
+                          "measure_fullnet -- the unmodified reference needs ~700 s per network per core at this "
+                          "size (SURVEY.md 8d) and is absent from the GPU box" % (count, cores, dt)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=8, help="networks per GPU per step")
+    ap.add_argument("--n", type=int, default=100000)
+    ap.add_argument("--scaling", type=int, default=100)
+    ap.add_argument("--onoffmap", type=int, default=1)
+    ap.add_argument("--rtol", type=float, default=1e-15)
+    ap.add_argument("--check-every", type=int, default=250)
+    ap.add_argument("--solver", default="auto", choices=["auto", "cluster", "flat"])
+    ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--cpu-sample", type=int, default=0, help="networks in the CPU sample (default: one per core)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return reference_arm(args)
+    return gpu_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

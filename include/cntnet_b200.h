@@ -55,7 +55,8 @@ int cnt_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int write
 /* ---------------------------------------------------------------------------------------
  * (1) stick placement -- replaces make_stick / get_ends / make_sticks (netsim.py:97-125)
  *     and the length sort of make_intersects_kdtree (netsim.py:132-134).
- * Counter-based Philox4x32-10 keyed by (seed, net_id0 + b), counter = stick ordinal; law:
+ * Counter-based Philox4x32-10 keyed by the network's own 64-bit seed seeds[b] (the reference
+ * also hands one seed per network, measure_perc.py:226-233), counter = stick ordinal; law:
  * kind 'm' iff u<=pm, xc,yc~U(0,1), angle~U(0,2pi), length=|N(0.66,0.44)|/scaling[b]
  * (len_mode 0) or len_const/scaling[b] (len_mode 1).  Each network gets soff[b+1]-soff[b]
  * sticks INCLUDING the two electrodes [0.01|0.99, 0.5, pi/2-1e-6, 100, 'v'].
@@ -64,7 +65,7 @@ int cnt_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int write
  * reference's pre-sort DataFrame index (netsim.py:132: source 0, body 1..n, drain n+1).
  * ------------------------------------------------------------------------------------- */
 int64_t cnt_gen_sticks_workspace_bytes(int64_t n_sticks_total, int B);
-int cnt_gen_sticks(uint64_t seed, int64_t net_id0, int B, const int32_t *soff, const int32_t *h_soff,
+int cnt_gen_sticks(const uint64_t *seeds, int B, const int32_t *soff, const int32_t *h_soff,
                    const double *scaling, double pm, int len_mode, double len_const,
                    double *xc, double *yc, double *angle, double *length, uint8_t *kind,
                    double *xa, double *ya, double *xb, double *yb, int32_t *orig,
@@ -136,6 +137,14 @@ int cnt_label_clusters(int B, const int32_t *soff, const int32_t *joff, int64_t 
 int64_t cnt_assemble_workspace_bytes(int64_t n_sticks_total);
 int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
                       int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream);
+/* optional, between _rows and _pattern_count: renumber every network's unknown rows in Z-order
+ * (Morton code) of the stick centres so that neighbouring sticks get neighbouring rows (SpMV
+ * gather locality; lets the cluster PCG kernel keep most gathers in shared memory).  Only
+ * urow changes; roff stays.  The reference's ascending node order (cnet.py:137-139) is a
+ * reporting convention that the write-back reproduces per stick. */
+int64_t cnt_assemble_reorder_workspace_bytes(int64_t R, int B);
+int cnt_assemble_reorder(int B, const int32_t *h_roff, int64_t S, int64_t R, const double *xc, const double *yc,
+                         int32_t *urow, void *ws, int64_t ws_bytes, void *stream);
 int cnt_assemble_pattern_count(int B, const int32_t *soff, const int32_t *joff, int64_t J,
                                const int32_t *stick1, const int32_t *stick2,
                                const int32_t *urow, int64_t R, int32_t *rowcnt, void *stream);
@@ -172,6 +181,22 @@ int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const in
                   double rtol, int maxit, int check_every,
                   int32_t *iters, double *relres, int32_t *status,
                   void *ws, int64_t ws_bytes, void *stream);
+
+/* Persistent thread-block-cluster variant of the same solve (pcg_cluster.cu): ONE launch for
+ * the whole batch; each cluster of CTAs pulls systems from a work queue and keeps p, r, diag
+ * in shared memory and x, q/z in registers for the whole solve (dot products through
+ * distributed shared memory, phase boundaries = hardware cluster barriers).  Same arguments,
+ * stopping rule and per-system outputs as cnt_pcg_solve; nothing synchronises the stream.
+ * Returns CNT_ECAPACITY if a system has more than cnt_pcg_cluster_max_rows() rows (use
+ * cnt_pcg_solve for those). */
+int64_t cnt_pcg_cluster_max_rows(void);
+int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R);
+int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
+                          const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,
+                          const double *val, const double *diag, const double *rhs, double *x,
+                          double rtol, int maxit,
+                          int32_t *iters, double *relres, int32_t *status,
+                          void *ws, int64_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (6) write-back -- replaces update_voltages / update_currents (cnet.py:132-146).

@@ -23,7 +23,7 @@ PROTOTYPES = {
     "cnt_scan_workspace_bytes": (i64, [i64]),
     "cnt_exclusive_scan_i32": (i32, [vp, vp, i64, i32, vp, i64, vp]),
     "cnt_gen_sticks_workspace_bytes": (i64, [i64, i32]),
-    "cnt_gen_sticks": (i32, [u64, i64, i32, vp, I32P, vp, f64, i32, f64] + [vp] * 10 + [vp, i64, vp]),
+    "cnt_gen_sticks": (i32, [vp, i32, vp, I32P, vp, f64, i32, f64] + [vp] * 10 + [vp, i64, vp]),
     "cnt_junction_workspace_bytes": (i64, [i32, I32P]),
     "cnt_junction_count": (i32, [i32, vp, I32P] + [vp] * 7 + [vp, vp, vp, i64, vp]),
     "cnt_junction_fill": (i32, [i32, vp, I32P] + [vp] * 8 + [vp, i64] + [vp] * 5 + [vp, vp, i64, vp]),
@@ -32,6 +32,8 @@ PROTOTYPES = {
     "cnt_label_clusters": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_workspace_bytes": (i64, [i64]),
     "cnt_assemble_rows": (i32, [i32, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+    "cnt_assemble_reorder_workspace_bytes": (i64, [i64, i32]),
+    "cnt_assemble_reorder": (i32, [i32, I32P, i64, i64, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_pattern_count": (i32, [i32, vp, vp, i64, vp, vp, vp, i64, vp, vp]),
     "cnt_assemble_pattern_fill": (i32, [i32, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_row_stick": (i32, [i32, vp, i64, vp, vp, vp]),
@@ -39,13 +41,14 @@ PROTOTYPES = {
     "cnt_assemble_values": (i32, [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cnt_pcg_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, i32, vp, vp, vp, vp, i64, vp]),
+    "cnt_pcg_cluster_max_rows": (i64, []),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i64, vp]),
     "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 # entry points that may be absent from an older build of the library (checked by tests
 # against the header, never silently replaced)
-OPTIONAL = {"cnt_pcg_cluster_workspace_bytes", "cnt_pcg_cluster_solve"}
+OPTIONAL = set()
 
 
 class CntError(RuntimeError):

@@ -152,6 +152,73 @@ extern "C" int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const in
     return CNT_OK;
 }
 
+namespace {
+// 16-bit x 16-bit Morton (Z-order) code of a point of the unit box
+__device__ __forceinline__ uint32_t spread16(uint32_t v) {
+    v &= 0xFFFFu;
+    v = (v | (v << 8)) & 0x00FF00FFu;
+    v = (v | (v << 4)) & 0x0F0F0F0Fu;
+    v = (v | (v << 2)) & 0x33333333u;
+    v = (v | (v << 1)) & 0x55555555u;
+    return v;
+}
+__global__ void k_morton_keys(int64_t S, const int32_t *__restrict__ urow, const double *__restrict__ xc,
+                              const double *__restrict__ yc, unsigned long long *__restrict__ key,
+                              uint32_t *__restrict__ val) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int r = urow[s];
+    if (r < 0) return;
+    double x = xc[s] * 65536.0, y = yc[s] * 65536.0;
+    uint32_t ix = x < 0 ? 0u : (x >= 65535.0 ? 65535u : (uint32_t)x);
+    uint32_t iy = y < 0 ? 0u : (y >= 65535.0 ? 65535u : (uint32_t)y);
+    if (!(x == x)) ix = 0;
+    if (!(y == y)) iy = 0;
+    key[r] = (unsigned long long)(spread16(ix) | (spread16(iy) << 1));
+    val[r] = (uint32_t)s;
+}
+__global__ void k_apply_order(int64_t R, const uint32_t *__restrict__ order, int32_t *__restrict__ urow) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r < R) urow[order[r]] = (int)r;
+}
+}  // namespace
+
+extern "C" int64_t cnt_assemble_reorder_workspace_bytes(int64_t R, int B) {
+    return 2 * cnt::ws_bytes_for(R, 8) + 2 * cnt::ws_bytes_for(R, 4) + cnt::segsort_workspace_bytes(R, B);
+}
+
+// Renumber the unknown rows of every network in Z-order of the stick centres (stable: ties keep
+// ascending stick index).  Neighbouring sticks get neighbouring rows, so the SpMV gathers of
+// p[col] hit the same sectors and a contiguous row block is a compact patch of the device --
+// which is what lets the cluster PCG kernel serve most gathers from its own shared memory.
+// The canonical (ascending stick index) order of the reference is only a reporting convention;
+// results are written back per stick through urow.
+extern "C" int cnt_assemble_reorder(int B, const int32_t *h_roff, int64_t S, int64_t R, const double *xc,
+                                    const double *yc, int32_t *urow, void *ws, int64_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && h_roff && urow && ws && S >= 0 && R >= 0 && h_roff[B] == R);
+    if (R == 0) return CNT_OK;
+    CNT_CHECK_ARG(xc && yc);
+    cnt::Workspace w(ws, ws_bytes);
+    unsigned long long *keyA = w.take<unsigned long long>(R), *keyB = w.take<unsigned long long>(R);
+    uint32_t *valA = w.take<uint32_t>(R), *valB = w.take<uint32_t>(R);
+    int64_t sb = cnt::segsort_workspace_bytes(R, B);
+    void *sws = w.take<char>(sb);
+    if (!sws) {
+        cnt::set_error("assemble_reorder workspace too small");
+        return CNT_ECAPACITY;
+    }
+    k_morton_keys<<<cnt::grid_for(S, 256), 256, 0, st>>>(S, urow, xc, yc, keyA, valA);
+    CNT_LAUNCHED();
+    unsigned long long *ks;
+    uint32_t *order;
+    int rc = cnt::segsort_pairs(B, h_roff, keyA, valA, keyB, valB, 4, sws, sb, st, &ks, &order);
+    if (rc) return rc;
+    k_apply_order<<<cnt::grid_for(R, 256), 256, 0, st>>>(R, order, urow);
+    CNT_LAUNCHED();
+    return CNT_OK;
+}
+
 extern "C" int cnt_assemble_pattern_count(int B, const int32_t *soff, const int32_t *joff, int64_t J,
                                           const int32_t *stick1, const int32_t *stick2, const int32_t *urow, int64_t R,
                                           int32_t *rowcnt, void *stream) {
@@ -224,10 +291,12 @@ extern "C" int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_
                                    double *diag, double *rhs, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(J >= 0 && R >= 0 && nlevels > 0);
-    if (J > 0) {
-        CNT_CHECK_ARG(kind2 && level && gtable && g);
+    if (J > 0 && gtable) {
+        CNT_CHECK_ARG(kind2 && level && g);
         k_conductance<<<cnt::grid_for(J, 256), 256, 0, st>>>(J, kind2, level, gtable, nlevels, g);
         CNT_LAUNCHED();
+    } else if (J > 0) {
+        CNT_CHECK_ARG(g);   // gtable == NULL: g[] is an input (conductances evaluated by the caller)
     }
     if (R > 0) {
         CNT_CHECK_ARG(rowptr && nz_eid && src_eid && drn_eid && val && diag && rhs);

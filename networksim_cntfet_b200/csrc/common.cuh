@@ -38,6 +38,14 @@ void count_launch(int n = 1);
         }                                                                         \
     } while (0)
 
+// segmented stable LSD radix sort of (u64 key, u32 value) pairs (radix.cu); segments are
+// [h_off[s], h_off[s+1]) with h_off[0] == 0; passes cover key bits [0, 8*npasses); buffers
+// ping-pong between A and B and the result pointers are returned
+int64_t segsort_workspace_bytes(int64_t n, int nseg);
+int segsort_pairs(int nseg, const int32_t *h_off, unsigned long long *keyA, uint32_t *valA, unsigned long long *keyB,
+                  uint32_t *valB, int npasses, void *ws, int64_t ws_bytes, cudaStream_t st,
+                  unsigned long long **key_out, uint32_t **val_out);
+
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }
 

@@ -82,16 +82,24 @@ __global__ void __launch_bounds__(TILE) k_init(Ctx c) {
     }
 }
 
+// ---- per-system scalar kernels: ONE WARP per system.  Lane l sums tiles l, l+32, ... in order,
+// then a fixed shuffle tree combines the lanes: the result depends only on the system's own
+// tile count, never on the batch, so iterates stay bit-reproducible.
+__device__ __forceinline__ double warp_tiles_sum(const double *__restrict__ part, int t0, int nt) {
+    int lane = threadIdx.x & 31;
+    double s = 0.0;
+    for (int t = lane; t < nt; t += 32) s += part[t0 + t];
+    return __shfl_sync(0xffffffffu, cnt::warp_sum(s), 0);
+}
+
 __global__ void k_scal_init(Ctx c, int ntiles_total, double rtol, int nsys) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nsys) return;
     Sys sy = c.sys[s];
-    double rz = 0, bb = 0, rr = 0;
-    for (int t = sy.tile0; t < sy.tile0 + sy.ntiles; t++) {
-        rz += c.part0[t];
-        bb += c.part1[t];
-        rr += c.part1[ntiles_total + t];
-    }
+    double rz = warp_tiles_sum(c.part0, sy.tile0, sy.ntiles);
+    double bb = warp_tiles_sum(c.part1, sy.tile0, sy.ntiles);
+    double rr = warp_tiles_sum(c.part1 + ntiles_total, sy.tile0, sy.ntiles);
+    if ((threadIdx.x & 31) != 0) return;
     Scal sc;
     sc.rz = rz; sc.bb = bb; sc.rr = rr; sc.alpha = 0; sc.beta = 0;
     sc.iters = 0; sc.status = 0; sc.pad = 0;
@@ -118,13 +126,13 @@ __global__ void __launch_bounds__(TILE) k_spmv(Ctx c) {
 }
 
 __global__ void k_scal_alpha(Ctx c, int nsys) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nsys) return;
     Scal *sc = c.scal + s;
     if (sc->done) return;
     Sys sy = c.sys[s];
-    double pq = 0;
-    for (int t = sy.tile0; t < sy.tile0 + sy.ntiles; t++) pq += c.part0[t];
+    double pq = warp_tiles_sum(c.part0, sy.tile0, sy.ntiles);
+    if ((threadIdx.x & 31) != 0) return;
     if (!(pq > 0.0)) {   // breakdown (matrix not SPD or NaN)
         sc->done = 1;
         sc->status = 2;
@@ -158,16 +166,14 @@ __global__ void __launch_bounds__(TILE) k_update(Ctx c) {
 }
 
 __global__ void k_scal_beta(Ctx c, int nsys, double rtol, int maxit) {
-    int s = blockIdx.x * blockDim.x + threadIdx.x;
+    int s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= nsys) return;
     Scal *sc = c.scal + s;
     if (sc->done) return;
     Sys sy = c.sys[s];
-    double rz = 0, rr = 0;
-    for (int t = sy.tile0; t < sy.tile0 + sy.ntiles; t++) {
-        rz += c.part0[t];
-        rr += c.part1[t];
-    }
+    double rz = warp_tiles_sum(c.part0, sy.tile0, sy.ntiles);
+    double rr = warp_tiles_sum(c.part1, sy.tile0, sy.ntiles);
+    if ((threadIdx.x & 31) != 0) return;
     sc->beta = rz / sc->rz;
     sc->rz = rz;
     sc->rr = rr;
@@ -283,22 +289,23 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
     c.tiles = d_tiles; c.sys = d_sys; c.scal = d_scal; c.R = R; c.NNZ = NNZ;
     c.rowptr = rowptr; c.col = col; c.val = val; c.diag = diag; c.rhs = rhs;
     c.x = x; c.r = r; c.p = p; c.q = q; c.part0 = part0; c.part1 = part1;
-    unsigned gs = cnt::grid_for(NSYS, 128);
+    unsigned gs = cnt::grid_for(NSYS, 128);            // one thread per system (export)
+    unsigned gw = cnt::grid_for((int64_t)NSYS * 32, 128);   // one warp per system (scalar kernels)
     if (nt > 0) {
         k_init<<<(unsigned)nt, TILE, 0, st>>>(c);
         CNT_LAUNCHED();
     }
-    k_scal_init<<<gs, 128, 0, st>>>(c, (int)nt, rtol, NSYS);
+    k_scal_init<<<gw, 128, 0, st>>>(c, (int)nt, rtol, NSYS);
     CNT_LAUNCHED();
 
     auto enqueue_iter = [&]() -> int {
         k_spmv<<<(unsigned)nt, TILE, 0, st>>>(c);
         CNT_LAUNCHED();
-        k_scal_alpha<<<gs, 128, 0, st>>>(c, NSYS);
+        k_scal_alpha<<<gw, 128, 0, st>>>(c, NSYS);
         CNT_LAUNCHED();
         k_update<<<(unsigned)nt, TILE, 0, st>>>(c);
         CNT_LAUNCHED();
-        k_scal_beta<<<gs, 128, 0, st>>>(c, NSYS, rtol, maxit);
+        k_scal_beta<<<gw, 128, 0, st>>>(c, NSYS, rtol, maxit);
         CNT_LAUNCHED();
         k_pupdate<<<(unsigned)nt, TILE, 0, st>>>(c);
         CNT_LAUNCHED();

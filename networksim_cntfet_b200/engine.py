@@ -22,6 +22,19 @@ AREA_PARTIAL = [0.5, 0, 0.16, 0.667]      # netsim.py:274, measure_perc.py:184
 AREA_TOTAL = [0.217, 0.5, 0.167, 1.2]     # netsim.py:276, measure_perc.py:180
 
 
+def network_seeds(seed, net_id0, count):
+    """Per-network 64-bit seeds derived from (ensemble seed, network id) with splitmix64, so a
+    network's sticks depend only on its id -- not on batch composition or GPU sharding."""
+    mask = (1 << 64) - 1
+    out = np.empty(count, dtype=np.uint64)
+    for k in range(count):
+        z = ((int(seed) & mask) * 0x9E3779B97F4A7C15 + (int(net_id0) + k + 1) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & mask
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & mask
+        out[k] = z ^ (z >> 31)
+    return out
+
+
 def _p(t):
     """raw device pointer of a contiguous tensor (None -> NULL)"""
     if t is None:
@@ -97,7 +110,7 @@ class GateState(object):
 class Engine(object):
     """Owns the CUDA stream and workspaces of one GPU (one process per GPU)."""
 
-    def __init__(self, device=None):
+    def __init__(self, device=None, profile=False):
         if not torch.cuda.is_available():
             raise _lib.CntError("networksim_cntfet_b200 needs a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
@@ -105,23 +118,51 @@ class Engine(object):
         torch.cuda.set_device(self.device)
         self.stream = torch.cuda.Stream(device=self.device)
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
+        self.profile = bool(profile)
+        self._events = []
+        self.solver = "auto"           # 'auto' | 'cluster' | 'flat'  (see Engine.solve)
+        self.last_solver = None
+        self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
 
     # ------------------------------------------------------------------ helpers
     @contextlib.contextmanager
-    def _work(self):
+    def _work(self, stage=None):
         """Run a stage on the engine's stream with stream-ordered semantics towards the caller:
         the engine stream first waits for the caller's current stream, and on exit the caller's
         stream waits for the engine stream, so results can be consumed with ordinary torch ops.
         (A dedicated non-default stream is needed because the PCG loop is captured into a CUDA
         graph, which the legacy default stream does not allow.)"""
         cur = torch.cuda.current_stream(self.device)
+        if self.profile and stage:
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
         if cur == self.stream:
+            if self.profile and stage:
+                e0.record(self.stream)
             yield
+            if self.profile and stage:
+                e1.record(self.stream)
+                self._events.append((stage, e0, e1))
             return
         self.stream.wait_stream(cur)
         with torch.cuda.stream(self.stream):
+            if self.profile and stage:
+                e0.record(self.stream)
             yield
+            if self.profile and stage:
+                e1.record(self.stream)
+                self._events.append((stage, e0, e1))
         cur.wait_stream(self.stream)
+
+    def stage_times_ms(self, reset=True):
+        """CUDA-event time per named stage since the last reset (profile=True only)."""
+        self.stream.synchronize()
+        out = {}
+        for stage, e0, e1 in self._events:
+            out[stage] = out.get(stage, 0.0) + e0.elapsed_time(e1)
+        if reset:
+            self._events = []
+        return out
 
     def _ws(self, nbytes):
         return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=self.device)
@@ -152,17 +193,26 @@ class Engine(object):
                 b.orig = None
         return b
 
-    def generate(self, ns, scaling, seed, net_id0=0, pm=0.135, l="exp"):
+    def generate(self, ns, scaling, seed=None, net_id0=0, pm=0.135, l="exp", seeds=None, seeds_dev=None):
         """netsim.py:105-134 on the GPU: len(ns) networks, network k has ns[k] body sticks plus
-        the two electrodes, drawn from Philox keyed by (seed, net_id0 + k), sorted canonically
-        (source, drain, then length descending).  `scaling` is a number or one per network."""
+        the two electrodes, drawn from Philox keyed by the network's own 64-bit seed, sorted
+        canonically (source, drain, then length descending).  `seeds` gives one seed per
+        network (what measure_async hands out, measure_perc.py:226-233); otherwise they are
+        derived from (seed, net_id0 + k); `seeds_dev` is the same array already on the device
+        (int64 bit patterns).  `scaling` is a number or one per network."""
         ns = [int(n) for n in ns]
+        if seeds is None and seeds_dev is not None:
+            seeds = np.zeros(len(ns), dtype=np.uint64)
+        if seeds is None:
+            seeds = network_seeds(seed, net_id0, len(ns))
+        seeds = np.asarray(seeds, dtype=np.uint64)
+        assert len(seeds) == len(ns)
         soff = np.zeros(len(ns) + 1, dtype=np.int64)
         soff[1:] = np.cumsum([n + 2 for n in ns])
         b = NetworkBatch(soff)
         sc = np.broadcast_to(np.asarray(scaling, dtype=np.float64), (len(ns),)).copy()
         lib = self.lib
-        with self._work():
+        with self._work("generate"):
             b.soff = self._dev(soff, torch.int32)
             dsc = self._dev(sc, torch.float64)
             S = max(b.S, 1)
@@ -174,7 +224,9 @@ class Engine(object):
             len_mode = 0 if isinstance(l, str) else 1
             if isinstance(l, str) and l != "exp":
                 raise ValueError("invalid L value")          # netsim.py:114-115
-            check(lib.cnt_gen_sticks(int(seed) & (2 ** 64 - 1), int(net_id0), b.B, _p(b.soff), b.c_soff, _p(dsc),
+            # seeds travel as int64 bit patterns (torch has no uint64 arithmetic; the kernel reads u64)
+            b.seeds = seeds_dev.contiguous() if seeds_dev is not None else self._dev(seeds.view(np.int64), torch.int64)
+            check(lib.cnt_gen_sticks(_p(b.seeds), b.B, _p(b.soff), b.c_soff, _p(dsc),
                                      float(pm), len_mode, 0.0 if len_mode == 0 else float(l),
                                      _p(b.xc), _p(b.yc), _p(b.angle), _p(b.length), _p(b.kind),
                                      _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb), _p(b.orig),
@@ -193,7 +245,7 @@ class Engine(object):
     def find_junctions(self, b):
         """netsim.py:135-150.  Fills b.stick1, stick2, jx, jy, kind2, joff, ntests."""
         lib = self.lib
-        with self._work():
+        with self._work("junctions"):
             wsb = lib.cnt_junction_workspace_bytes(b.B, b.c_soff)
             b._jws = self._ws(wsb)
             jcount = torch.empty(b.S + 1, dtype=torch.int32, device=self.device)
@@ -232,7 +284,7 @@ class Engine(object):
     def label_clusters(self, b):
         """netsim.py:175-179,197-206; measure_perc.py:76-80.  Fills b.label, b.stats."""
         lib = self.lib
-        with self._work():
+        with self._work("clusters"):
             ws = self._ws(lib.cnt_cluster_workspace_bytes(b.S))
             b.label = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.stats = torch.zeros(b.B * _lib.CNT_NSTAT, dtype=torch.int32, device=self.device)
@@ -244,7 +296,7 @@ class Engine(object):
     def assemble_pattern(self, b):
         """cnet.py:104-128 structure: unknown rows + CSR pattern of L_UU (no diagonal)."""
         lib = self.lib
-        with self._work():
+        with self._work("pattern"):
             ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
             b.urow = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.roff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
@@ -255,6 +307,10 @@ class Engine(object):
             b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()
             b.R = b.h_roff[-1]
             R = b.R
+            if self.spatial_order and R > 0 and getattr(b, "length", None) is not None:
+                rws = self._ws(lib.cnt_assemble_reorder_workspace_bytes(R, b.B))
+                check(lib.cnt_assemble_reorder(b.B, b.c_roff, b.S, R, _p(b.xc), _p(b.yc), _p(b.urow), _p(rws),
+                                               rws.numel(), self.stream_ptr))
             rowcnt = torch.empty(R + 1, dtype=torch.int32, device=self.device)
             check(lib.cnt_assemble_pattern_count(b.B, _p(b.soff), _p(b.joff), b.J, _p(b.stick1), _p(b.stick2),
                                                  _p(b.urow), R, _p(rowcnt), self.stream_ptr))
@@ -289,7 +345,7 @@ class Engine(object):
         lib = self.lib
         NS = len(gates)
         R, NNZ, J = b.R, b.NNZ, b.J
-        with self._work():
+        with self._work("values"):
             g = torch.empty((NS, max(J, 1)), dtype=torch.float64, device=self.device)
             val = torch.empty((NS, max(NNZ, 1)), dtype=torch.float64, device=self.device)
             diag = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
@@ -303,33 +359,55 @@ class Engine(object):
                                               _p(diag[q]), _p(rhs[q]), self.stream_ptr))
         return dict(g=g, val=val, diag=diag, rhs=rhs)
 
-    def solve(self, b, sysm, x0=None, rtol=1e-15, maxit=2000000, check_every=250, nets=None):
+    def solve(self, b, sysm, x0=None, rtol=1e-15, maxit=2000000, check_every=250, nets=None, method=None,
+              slab_priority=None):
         """Batched Jacobi-PCG (replaces cnet.py:147-149).  sysm: output of assemble_values for
         NS gate configurations.  Every (configuration q, percolating network) pair is one
-        system of a single solver call; system order is configuration-major.  Returns
-        dict(x[NS,R], iters[NS,B], relres[NS,B], status[NS,B]) (non-percolating networks:
+        system of a single solver call.  method: 'cluster' (persistent thread-block-cluster
+        kernel, default when every system fits on chip), 'flat' (multi-launch kernels).
+        slab_priority: configurations expected to need more iterations first (work-queue order).
+        Returns dict(x[NS,R], iters[NS,B], relres[NS,B], status[NS,B]) (non-percolating networks:
         iters 0, status 0)."""
         lib = self.lib
         NS = sysm["val"].shape[0]
         R, NNZ, B = b.R, b.NNZ, b.B
         nets = [n for n in (range(B) if nets is None else nets) if b.h_roff[n + 1] > b.h_roff[n]]
-        with self._work():
+        method = method or self.solver
+        with self._work("pcg"):
             x = torch.zeros((NS, max(R, 1)), dtype=torch.float64, device=self.device) if x0 is None else x0.clone()
             iters = torch.zeros((NS, B), dtype=torch.int32, device=self.device)
             relres = torch.zeros((NS, B), dtype=torch.float64, device=self.device)
             status = torch.zeros((NS, B), dtype=torch.int32, device=self.device)
             if R > 0 and nets:
-                sys_net = [n for q in range(NS) for n in nets]
-                sys_slab = [q for q in range(NS) for n in nets]
+                slabs = list(range(NS))
+                if slab_priority is not None:
+                    slabs.sort(key=lambda q: -slab_priority[q])
+                # big systems first inside a configuration: better tail behaviour of the work queue
+                nets_sorted = sorted(nets, key=lambda n: -(b.h_roff[n + 1] - b.h_roff[n]))
+                sys_net = [n for q in slabs for n in nets_sorted]
+                sys_slab = [q for q in slabs for n in nets_sorted]
                 nsys = len(sys_net)
                 it = torch.zeros(nsys, dtype=torch.int32, device=self.device)
                 rr = torch.zeros(nsys, dtype=torch.float64, device=self.device)
                 stt = torch.zeros(nsys, dtype=torch.int32, device=self.device)
-                ws = self._ws(lib.cnt_pcg_workspace_bytes(nsys, NS, R))
-                check(lib.cnt_pcg_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab), b.c_roff,
-                                        R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]),
-                                        _p(sysm["rhs"]), _p(x), float(rtol), int(maxit), int(check_every),
-                                        _p(it), _p(rr), _p(stt), _p(ws), ws.numel(), self.stream_ptr))
+                max_rows = max(b.h_roff[n + 1] - b.h_roff[n] for n in nets)
+                if method == "auto":
+                    method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
+                self.last_solver = method
+                if method == "cluster":
+                    ws = self._ws(lib.cnt_pcg_cluster_workspace_bytes(nsys, NS, R))
+                    check(lib.cnt_pcg_cluster_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab),
+                                                    b.c_roff, R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]),
+                                                    _p(sysm["diag"]), _p(sysm["rhs"]), _p(x), float(rtol), int(maxit),
+                                                    _p(it), _p(rr), _p(stt), _p(ws), ws.numel(), self.stream_ptr))
+                elif method == "flat":
+                    ws = self._ws(lib.cnt_pcg_workspace_bytes(nsys, NS, R))
+                    check(lib.cnt_pcg_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab), b.c_roff,
+                                            R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]),
+                                            _p(sysm["rhs"]), _p(x), float(rtol), int(maxit), int(check_every),
+                                            _p(it), _p(rr), _p(stt), _p(ws), ws.numel(), self.stream_ptr))
+                else:
+                    raise ValueError("unknown solver %r" % method)
                 idx_q = torch.as_tensor(sys_slab, device=self.device, dtype=torch.long)
                 idx_n = torch.as_tensor(sys_net, device=self.device, dtype=torch.long)
                 iters[idx_q, idx_n] = it
@@ -341,7 +419,7 @@ class Engine(object):
     def currents(self, b, g, x):
         """cnet.py:132-146 for one configuration: V[S], |I|[J], isrc[B,3]."""
         lib = self.lib
-        with self._work():
+        with self._work("currents"):
             V = torch.empty(max(b.S, 1), dtype=torch.float64, device=self.device)
             I = torch.empty(max(b.J, 1), dtype=torch.float64, device=self.device)
             isrc = torch.zeros((b.B, 3), dtype=torch.float64, device=self.device)
@@ -366,7 +444,8 @@ class Engine(object):
         from .elements import conductance_table
         tabs = [conductance_table(element, onoffmap, gs.levels) for gs in gates]
         sysm = self.assemble_values(b, gates, tabs)
-        sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every)
+        prio = [max(abs(v) for v in gs.levels) for gs in gates]   # higher |Vg| -> more iterations -> first
+        sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every, slab_priority=prio)
         NS = len(gates)
         out = dict(iters=sol["iters"], relres=sol["relres"], status=sol["status"])
         isrc = []
@@ -409,3 +488,84 @@ class Engine(object):
         if want_fields:
             out["fields"] = res
         return out
+
+    # ------------------------------------------------------------------ generic junction graphs
+    def batch_from_junctions(self, n, stick1, stick2, jx, jy, kind2):
+        """One network given directly as a junction list over n nodes (node 0 = source, node 1 =
+        ground), e.g. a networkx graph handed to cnet.ConductionNetwork.  Rows must be sorted
+        by (stick1, stick2) with stick1 < stick2."""
+        b = NetworkBatch([0, int(n)])
+        J = len(stick1)
+        with self._work():
+            b.soff = self._dev(np.array([0, n]), torch.int32)
+            b.joff = self._dev(np.array([0, J]), torch.int32)
+            pad = lambda a, dt: np.ascontiguousarray(a if J else np.zeros(1), dtype=dt)
+            b.stick1 = self._dev(pad(stick1, np.int32), torch.int32)
+            b.stick2 = self._dev(pad(stick2, np.int32), torch.int32)
+            b.jx = self._dev(pad(jx, np.float64), torch.float64)
+            b.jy = self._dev(pad(jy, np.float64), torch.float64)
+            b.kind2 = self._dev(pad(kind2, np.uint8), torch.uint8)
+            b.ntests = torch.zeros(1, dtype=torch.int64, device=self.device)
+            b.xc = torch.full((max(n, 1),), float("nan"), dtype=torch.float64, device=self.device)
+            b.yc = b.xc.clone()
+            b.orig = None
+        b.J = J
+        return b
+
+    def attach_junctions(self, b, stick1, stick2, jx, jy, kind2):
+        """Use a junction table computed elsewhere (netsim.load_system reads one from CSV,
+        netsim.py:238-249) for a single-network batch; rows sorted by (stick1, stick2)."""
+        assert b.B == 1
+        J = len(stick1)
+        with self._work():
+            pad = lambda a, dt: np.ascontiguousarray(a if J else np.zeros(1), dtype=dt)
+            b.joff = self._dev(np.array([0, J]), torch.int32)
+            b.stick1 = self._dev(pad(stick1, np.int32), torch.int32)
+            b.stick2 = self._dev(pad(stick2, np.int32), torch.int32)
+            b.jx = self._dev(pad(jx, np.float64), torch.float64)
+            b.jy = self._dev(pad(jy, np.float64), torch.float64)
+            b.kind2 = self._dev(pad(kind2, np.uint8), torch.uint8)
+            b.ntests = torch.zeros(1, dtype=torch.int64, device=self.device)
+        b.J = J
+        return b
+
+    def solve_given_conductances(self, b, g_host, rtol=1e-15, maxit=2000000, check_every=250):
+        """update() for conductances evaluated by the caller (one configuration)."""
+        lib = self.lib
+        R, NNZ, J = b.R, b.NNZ, b.J
+        with self._work("values"):
+            g = self._dev(np.asarray(g_host, dtype=np.float64).reshape(1, -1) if J else np.zeros((1, 1)), torch.float64)
+            val = torch.empty((1, max(NNZ, 1)), dtype=torch.float64, device=self.device)
+            diag = torch.empty((1, max(R, 1)), dtype=torch.float64, device=self.device)
+            rhs = torch.empty((1, max(R, 1)), dtype=torch.float64, device=self.device)
+            check(lib.cnt_assemble_values(J, None, None, None, 1, R, _p(b.rowptr), _p(b.nz_eid), _p(b.src_eid),
+                                          _p(b.drn_eid), _p(g[0]), _p(val[0]), _p(diag[0]), _p(rhs[0]),
+                                          self.stream_ptr))
+        sysm = dict(g=g, val=val, diag=diag, rhs=rhs)
+        sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every)
+        V, I, cur = self.currents(b, g[0], sol["x"][0])
+        with self._work():
+            out = dict(iters=sol["iters"], relres=sol["relres"], status=sol["status"], isrc=cur[None],
+                       V=V[None], I=I[None], g=g, x=sol["x"], sysm=sysm)
+        return out
+
+    def measure_ensemble(self, ns, scaling, seeds, onoffmap=1, element=None, l="exp", pm=0.135, rtol=1e-15,
+                         maxit=2000000, check_every=250, seeds_dev=None):
+        """Batched body of measure_perc.measure_async (measure_perc.py:205-242): one network
+        per (ns[k], seeds[k]); generation, junctions, clusters, assembly, the four
+        measure_fullnet solves and the write-back all run on this GPU.  Host in: the ns/seeds
+        arrays; host out: one row of statistics per network (dict of numpy arrays)."""
+        b = self.generate(ns, scaling, seeds=seeds, l=l, pm=pm, seeds_dev=seeds_dev)
+        out = self.measure_fullnet(b, onoffmap=onoffmap, element=element, rtol=rtol, maxit=maxit,
+                                   check_every=check_every)
+        out["sticks"] = np.asarray([int(n) for n in ns])
+        out["seed"] = np.asarray(seeds, dtype=np.uint64)
+        out["rows"] = np.diff(np.asarray(b.h_roff))
+        out["nnz_offdiag"] = self.nnz_per_network(b)
+        return out
+
+    def nnz_per_network(self, b):
+        """off-diagonal non-zeros of every network's reduced matrix (for traffic accounting)"""
+        rp = b.rowptr.cpu().numpy()
+        r = np.asarray(b.h_roff)
+        return rp[r[1:]] - rp[r[:-1]]

@@ -1,0 +1,292 @@
+#!/usr/bin/env python3
+"""Drop-in for the reference's `measure_perc.py` (ensemble driver).
+
+Same functions, arguments and DataFrame / CSV columns as measure_perc.py:39-276.  The
+reference fans independent networks out over `multiprocessing.Pool(cores)`
+(measure_perc.py:230-235); here the whole ensemble is pushed through the GPU in batches
+(`measure_ensemble`), sharded over ranks when torch.distributed is initialised, with one final
+all-gather of the per-network rows.  `cores` is accepted and ignored.
+"""
+import argparse
+import os
+import sys
+import textwrap  # noqa: F401  (kept: the reference module exposes it)
+import traceback
+import uuid as id
+from timeit import default_timer as timer
+
+import numpy as np
+import pandas as pd
+
+from . import get_engine, netsim, set_engine  # noqa: F401
+from .cnet import FermiDiracTransistor, LinExpTransistor
+
+elements = [FermiDiracTransistor, LinExpTransistor]
+FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'ioff', 'gate', 'fname', 'seed',
+                   'onoffmap']
+BATCH_STICKS = 1_200_000      # sticks per GPU batch of the ensemble path (~12 networks at 100x100 um)
+
+
+def checkdir(directoryname):
+    """create the directory if it does not exist (measure_perc.py:28-38)"""
+    if directoryname and not os.path.isdir(directoryname):
+        os.makedirs(directoryname, exist_ok=True)
+
+
+def add_voltagemeas(device, data, vgrange=10, vgnum=3):
+    """three gate types x linspace(-vgrange, vgrange, vgnum) solves (measure_perc.py:39-53)"""
+    gate, gatevoltage, current = [], [], []
+    for g in ['back', 'partial', 'total']:
+        for vg in np.linspace(-vgrange, vgrange, vgnum):
+            current.append(device.gate(vg, g))
+            gate.append(g)
+            gatevoltage.append(vg)
+    data.gate = gate
+    data.gatevoltage = gatevoltage
+    data.current = current
+    return data
+
+
+def _true_maxclust(device):
+    """measure_perc.py:78: len(max(nx.connected_components(g))) == size of the FIRST component,
+    i.e. the one holding the smallest stick index that has a junction."""
+    return int(device._batch.h_stats[0][4])
+
+
+def single_measure(n, scaling, l='exp', dump=False, savedir='test', seed=0, onoffmap=0, v=False,
+                   element=LinExpTransistor, vgrange=10, vgnum=3, rng='philox'):
+    """one device + gate sweeps (measure_perc.py:54-138); returns (DataFrame, fname)"""
+    datacol = ['sticks', 'scaling', 'density', 'current', 'gatevoltage', 'gate', 'nclust', 'maxclust', 'fname',
+               'onoffmap', 'seed', 'runtime', 'element']
+    checkdir(savedir)
+    start = timer()
+    d = n / scaling ** 2
+    if not seed:
+        seed = np.random.randint(low=0, high=2 ** 32)
+    fname = os.path.join(savedir, "mnet{:2.2f}_s{}_l{}_om{}_el{}_seed{:010d}".format(
+        d, scaling, l, onoffmap, elements.index(element), seed))
+    data = pd.DataFrame(columns=datacol)
+    if v:
+        print("=== measurement start ===\nn{:05d}_d{:2.1f}_seed{:010d}".format(n, d, seed))
+    device = netsim.RandomCNTNetwork(n=n, scaling=scaling, notes='run', l=l, seed=seed, onoffmap=onoffmap,
+                                     element=element, rng=rng)
+    if v:
+        print("=== physical device made t = {:0.2}".format(timer() - start))
+        print("percolating : {}".format(device.percolating))
+    device.label_clusters()
+    nclust = len(device.sticks.cluster.drop_duplicates())
+    maxclust = _true_maxclust(device)
+    if dump:
+        try:
+            device.save_system(fname)
+        except Exception as e:
+            if v:
+                print("measurement failed: error saving data")
+                print("ERROR for {} sticks:\n".format(n), e)
+                traceback.print_exc(file=sys.stdout)
+    if device.percolating:
+        data = add_voltagemeas(device, data, vgrange=vgrange, vgnum=vgnum)
+    else:
+        data.current = [0]
+    data.sticks = n
+    data.scaling = scaling
+    data.density = d
+    data.nclust = nclust
+    data.maxclust = maxclust
+    data.seed = seed
+    data.element = element
+    data.onoffmap = onoffmap
+    data.fname = fname
+    data['runtime'] = timer() - start
+    data.to_csv(fname + "_data.csv")
+    if v:
+        print("=== measurement done ===")
+    return data, fname
+
+
+def _rows_from_ensemble(res, ns, scaling, seeds, onoffmap, fnames=None):
+    """per-network statistics -> the reference's measure_fullnet rows (measure_perc.py:190-197)"""
+    rows = []
+    for k, n in enumerate(ns):
+        fname = fnames[k] if fnames else ''
+        base = [n, scaling, n / scaling ** 2, int(res["nclust"][k]), int(res["maxclust"][k])]
+        if res["percolating"][k]:
+            ion = float(res["ion"][k])
+            rows.append(base + [ion, float(res["ioff_back"][k]), 'back', fname, int(seeds[k]), onoffmap])
+            rows.append(base + [ion, float(res["ioff_total"][k]), 'total', fname, int(seeds[k]), onoffmap])
+            rows.append(base + [ion, float(res["ioff_partial"][k]), 'partial', fname, int(seeds[k]), onoffmap])
+        else:
+            rows.append(base + [0, 0, 'back', fname, int(seeds[k]), onoffmap])
+    return pd.DataFrame(rows, columns=FULLNET_COLUMNS)
+
+
+def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l='exp', rtol=1e-15,
+                     return_io=False, engine=None):
+    """GPU body shared by measure_fullnet / measure_async: host arrays (ns, seeds) in, the
+    reference's rows out.  ns/seeds are staged in pinned host memory and copied to the device;
+    results come back as one statistics row per network."""
+    import torch
+    eng = engine or get_engine()
+    ns = [int(n) for n in ns]
+    seeds_np = np.asarray(seeds, dtype=np.uint64)
+    pinned = torch.empty(2 * len(ns), dtype=torch.int64).pin_memory()
+    pinned[:len(ns)] = torch.as_tensor(ns, dtype=torch.int64)
+    pinned[len(ns):] = torch.from_numpy(seeds_np.view(np.int64).copy())
+    dev_in = pinned.to(eng.device, non_blocking=True)          # H2D of this call's inputs
+    frames = []
+    d2h = 0
+    start = 0
+    while start < len(ns):                                     # batches bounded by stick count
+        stop, tot = start, 0
+        while stop < len(ns) and (stop == start or tot + ns[stop] + 2 <= BATCH_STICKS):
+            tot += ns[stop] + 2
+            stop += 1
+        sl = slice(start, stop)
+        res = eng.measure_ensemble(ns[sl], scaling, seeds_np[sl], onoffmap=onoffmap, element=element, l=l, rtol=rtol,
+                                   seeds_dev=dev_in[len(ns) + start:len(ns) + stop])
+        d2h += sum(int(np.asarray(v).nbytes) for k, v in res.items() if isinstance(v, np.ndarray))
+        frames.append(_rows_from_ensemble(res, ns[sl], scaling, seeds_np[sl], onoffmap))
+        start = stop
+    del dev_in
+    df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=FULLNET_COLUMNS)
+    if return_io:
+        return df, {"h2d_bytes": int(pinned.numel() * 8), "d2h_bytes": int(d2h)}
+    return df
+
+
+def measure_fullnet(n, scaling, l='exp', save=False, seed=0, onoffmap=1, v=False, remote=False, rng='philox'):
+    """one network: nclust / maxclust / ion / ioff for back, total and partial gates at 10 V
+    (measure_perc.py:140-203).  `save` (or rng='mt19937') goes through the object API so the
+    stick / junction tables exist on the host; otherwise only statistics leave the GPU."""
+    start = timer()
+    if not seed:
+        seed = np.random.randint(low=0, high=2 ** 32)
+    notes = "{}_{}sticks_{}x{}um_{}L_{}".format(seed, n, scaling, scaling, l, 'run')
+    fname = os.path.join('data', notes)                        # netsim.py:223-226 with notes='run'
+    if save or rng != 'philox':
+        collection = netsim.RandomConductingNetwork(n, scaling=scaling, notes='run', l=l, seed=seed,
+                                                    onoffmap=onoffmap, rng=rng)
+        collection.label_clusters()
+        nclust = len(collection.sticks.cluster.drop_duplicates())
+        maxclust = _true_maxclust(collection)
+        if save:
+            try:
+                checkdir(os.path.dirname(collection.fname))
+                collection.save_system()
+            except Exception as e:
+                if v:
+                    print("measurement failed: error saving data")
+                    print("ERROR for {} sticks:\n".format(n), e)
+                    traceback.print_exc(file=sys.stdout)
+        base = [n, scaling, n / scaling ** 2, nclust, maxclust]
+        rows = []
+        if collection.percolating:
+            c = collection.cnet
+            ion = sum(c.source_currents)
+            c.set_global_gate(10)
+            c.update()
+            rows.append(base + [ion, sum(c.source_currents), 'back', fname, seed, onoffmap])
+            c.set_global_gate(0)
+            c.set_local_gate([0.217, 0.5, 0.167, 1.2], 10)
+            c.update()
+            rows.append(base + [ion, sum(c.source_currents), 'total', fname, seed, onoffmap])
+            c.set_global_gate(0)
+            c.set_local_gate([0.5, 0, 0.16, 0.667], 10)
+            c.update()
+            rows.append(base + [ion, sum(c.source_currents), 'partial', fname, seed, onoffmap])
+        else:
+            rows.append(base + [0, 0, 'back', fname, seed, onoffmap])
+        data = pd.DataFrame(rows, columns=FULLNET_COLUMNS)
+    else:
+        data = measure_ensemble([n], scaling, [seed], onoffmap=onoffmap, l=l)
+        data['fname'] = fname
+    data['runtime'] = timer() - start
+    if fname and os.path.isdir(os.path.dirname(fname)):
+        data.to_csv(fname + "_data.csv")
+    return data
+
+
+def _shard(number):
+    """contiguous shard of range(number) for this rank when torch.distributed is initialised"""
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            r, w = dist.get_rank(), dist.get_world_size()
+            lo, hi = (number * r) // w, (number * (r + 1)) // w
+            return lo, hi, r, w
+    except Exception:
+        pass
+    return 0, number, 0, 1
+
+
+def measure_async(cores, start, step, number, scaling, save=False, onoffmap=[1], seeds=[]):
+    """density sweep n_i = start + i*step, i < number (measure_perc.py:205-242).  Returns the
+    concatenated rows with columns
+    ['sticks','size','density','nclust','maxclust','ion','ioff','gate','fname','seed','onoffmap'].
+    `cores` is ignored: networks are batched on the GPU; under torch.distributed each rank takes
+    a contiguous shard and the rows are all-gathered (every rank returns the full frame)."""
+    if not os.path.isdir("data"):
+        os.makedirs("data", exist_ok=True)
+    uuid = id.uuid4()
+    starttime = timer()
+    nrange = [int(start + i * step) for i in range(number)]
+    if not (len(seeds) == number):
+        seeds = np.random.randint(low=0, high=2 ** 32, size=number)
+    lo, hi, rank, world = _shard(number)
+    if rank == 0 and not os.path.isfile("seeds_{}.csv".format(uuid)):
+        np.savetxt("seeds_{}.csv".format(uuid), seeds, delimiter=",")
+    output = []
+    for omap in onoffmap:
+        if save:
+            part = [measure_fullnet(nrange[i], scaling, 'exp', save, seeds[i], omap) for i in range(lo, hi)]
+            part = pd.concat(part) if part else pd.DataFrame(columns=FULLNET_COLUMNS)
+        else:
+            part = measure_ensemble(nrange[lo:hi], scaling, list(seeds[lo:hi]), onoffmap=omap)
+            part['fname'] = [os.path.join('data', "{}_{}sticks_{}x{}um_{}L_{}".format(s, n, scaling, scaling, 'exp', 'run'))
+                             for s, n in zip(part.seed, part.sticks)]
+        if world > 1:
+            import torch.distributed as dist
+            gathered = [None] * world
+            dist.all_gather_object(gathered, part)
+            part = pd.concat(gathered)
+        output.append(part)
+    print(sum(len(o) for o in output))
+    runtime = timer() - starttime
+    print('finished with a runtime of {:.0f} '.format(runtime))
+    data = pd.concat(output)
+    if save and rank == 0:
+        data.to_csv('measurement_batch_{}.csv'.format(uuid))
+    return data
+
+
+if __name__ == '__main__':
+    parser = argparse.ArgumentParser(formatter_class=argparse.RawDescriptionHelpFormatter, description=__doc__)
+    parser.add_argument("function", type=str, choices=["multicore", "singlecore"])
+    parser.add_argument("-d", '--directory', type=str, default='')
+    parser.add_argument("-t", '--test', action="store_true", default=False)
+    parser.add_argument('-s', '--save', action="store_true", default=False)
+    parser.add_argument('-v', '--verbose', action="store_true", default=False)
+    parser.add_argument("--cores", type=int, default=1)
+    parser.add_argument("--start", type=int)
+    parser.add_argument("--step", type=int, default=0)
+    parser.add_argument('-n', "--number", type=int, default=500)
+    parser.add_argument("--scaling", type=int, default=5)
+    parser.add_argument("--seed", type=int, default=0)
+    parser.add_argument("--onoffmap", type=int, default=0)
+    parser.add_argument("--element", type=int, default=0)
+    parser.add_argument("--vgrange", type=int, default=10)
+    parser.add_argument("--vgnum", type=int, default=3)
+    args = parser.parse_args()
+    if args.function == "multicore":
+        if args.test:
+            measure_async(2, 500, 0, 10, 5, save=True)
+        else:
+            # the reference passes the bare int and crashes iterating it (measure_perc.py:271 vs :232)
+            measure_async(args.cores, args.start, args.step, args.number, args.scaling, args.save, [args.onoffmap])
+    elif args.function == "singlecore":
+        if args.test:
+            single_measure(500, 5, v=True)
+        else:
+            single_measure(args.number, args.scaling, savedir=args.directory, dump=args.save, v=args.verbose,
+                           element=elements[args.element], onoffmap=args.onoffmap, seed=args.seed,
+                           vgrange=args.vgrange, vgnum=args.vgnum)

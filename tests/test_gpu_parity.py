@@ -113,10 +113,16 @@ def test_assembly_matches_oracle(engine, name):
     engine.sync()
     cond, r = _oracle_fields(g, "_back", "back", 10.0, refine=0)
     assert np.array_equal(sysm["g"][0].cpu().numpy()[:b.J], cond)       # bit-identical conductances
-    A = r["A"].tocsr()
-    A.sort_indices()
-    R = A.shape[0]
+    R = r["A"].shape[0]
     assert b.R == R
+    # the GPU numbers its unknowns in Z-order of the stick centres (cnt_assemble_reorder);
+    # row_stick maps them back to the reference's ascending node order
+    row_stick = b.row_stick.cpu().numpy()[:R]
+    assert np.array_equal(np.sort(row_stick), r["nodes_u"])
+    perm = np.searchsorted(r["nodes_u"], row_stick)
+    A = r["A"].tocsr()[perm][:, perm].tocsr()
+    A.sort_indices()
+    r = dict(r, rhs=r["rhs"][perm], nodes_u=r["nodes_u"][perm])
     rowptr = b.rowptr.cpu().numpy()
     col = b.col.cpu().numpy()[:b.NNZ]
     val = sysm["val"][0].cpu().numpy()[:b.NNZ]

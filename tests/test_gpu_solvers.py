@@ -1,0 +1,132 @@
+"""GPU: the two PCG implementations (multi-launch `flat`, persistent thread-block-cluster
+`cluster`) against the refined oracle and against each other; Z-order row numbering."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden_sticks, load_golden
+from oracle import cntnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def solver(engine):
+    old = engine.solver
+    yield engine
+    engine.solver = old
+    os.environ.pop("CNT_CLUSTER_SIZE", None)
+
+
+def _oracle_currents(g, onoffmap):
+    s = golden_sticks(g)
+    j = dict(stick1=g["stick1"], stick2=g["stick2"], x=g["jx"], y=g["jy"], kind2=g["kind2"], ntests=0)
+    return O.measure_fullnet(s, onoffmap=onoffmap, junctions=j, refine=3)
+
+
+@pytest.mark.parametrize("method", ["flat", "cluster"])
+def test_methods_vs_oracle(solver, method):
+    solver.solver = method
+    names = ["trivial", "s5_n300_seed1", "s5_n120_seed5_noperc", "s5_n300_seed2_om1", "s20_n6400_seed5"]
+    gs = [load_golden(n) for n in names]
+    b = solver.batch_from_host([golden_sticks(g) for g in gs])
+    res = solver.measure_fullnet(b, onoffmap=1)
+    assert solver.last_solver == method
+    assert np.all(res["status"] == 0)
+    for i, g in enumerate(gs):
+        m = _oracle_currents(g, 1)
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            if m["percolating"]:
+                assert abs(res[k][i] - m[k]) <= 1e-9 * m[k], (method, g["name"], k, res[k][i], m[k])
+            else:
+                assert res[k][i] == 0.0
+
+
+def test_flat_and_cluster_agree(solver):
+    g = load_golden("s20_n6400_seed5")
+    out = {}
+    for method in ("flat", "cluster"):
+        solver.solver = method
+        b = solver.batch_from_host([golden_sticks(g)])
+        out[method] = solver.measure_fullnet(b, onoffmap=1, want_fields=True)
+    for q in range(4):
+        Vf = out["flat"]["fields"]["V"][q].cpu().numpy()
+        Vc = out["cluster"]["fields"]["V"][q].cpu().numpy()
+        m = ~np.isnan(Vf)
+        assert np.array_equal(np.isnan(Vf), np.isnan(Vc))
+        assert np.max(np.abs(Vf[m] - Vc[m])) <= 1e-11 * 0.1
+    # iteration counts agree up to the different (but fixed) summation trees
+    assert np.all(np.abs(out["flat"]["iters"].astype(int) - out["cluster"]["iters"].astype(int)) <= 0.02 * out["flat"]["iters"] + 5)
+
+
+@pytest.mark.parametrize("csize", [1, 2, 4, 8, 16])
+def test_cluster_sizes(solver, csize):
+    """the same systems on clusters of 1..16 CTAs (row chunks, DSMEM reductions, halo gathers)"""
+    os.environ["CNT_CLUSTER_SIZE"] = str(csize)
+    solver.solver = "cluster"
+    names = ["s5_n300_seed1", "s20_n6400_seed5", "trivial"]
+    gs = [load_golden(n) for n in names]
+    b = solver.batch_from_host([golden_sticks(g) for g in gs])
+    res = solver.measure_fullnet(b, onoffmap=1)
+    assert np.all(res["status"] == 0)
+    for i, g in enumerate(gs):
+        m = _oracle_currents(g, 1)
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            assert abs(res[k][i] - m[k]) <= 1e-9 * m[k], (csize, g["name"], k)
+    # deterministic: a second run gives the same bits
+    b2 = solver.batch_from_host([golden_sticks(g) for g in gs])
+    res2 = solver.measure_fullnet(b2, onoffmap=1)
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert np.array_equal(res[k], res2[k])
+    assert np.array_equal(res["iters"], res2["iters"])
+
+
+def test_many_systems_work_queue(solver):
+    """more systems than resident clusters: every cluster loops over the work queue"""
+    solver.solver = "cluster"
+    ns = [300 + 7 * k for k in range(60)]
+    b = solver.generate(ns, 5.0, seed=5)
+    res = solver.measure_fullnet(b, onoffmap=1)
+    solver.solver = "flat"
+    b2 = solver.generate(ns, 5.0, seed=5)
+    ref = solver.measure_fullnet(b2, onoffmap=1)
+    assert np.array_equal(res["percolating"], ref["percolating"]) and res["percolating"].sum() > 10
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert np.allclose(res[k], ref[k], rtol=1e-10, atol=0)
+    assert np.all(res["status"] == 0) and np.all(ref["status"] == 0)
+
+
+def test_maxit_and_status(solver):
+    g = load_golden("s20_n6400_seed5")
+    for method in ("flat", "cluster"):
+        solver.solver = method
+        b = solver.batch_from_host([golden_sticks(g)])
+        res = solver.measure_fullnet(b, onoffmap=1, maxit=50, check_every=10)
+        assert np.all(res["status"] == 1) and np.all(res["iters"] == 50), (method, res["status"], res["iters"])
+        assert np.all(res["relres"] > 1e-15)
+
+
+def test_z_order_locality(solver):
+    """cnt_assemble_reorder: neighbouring sticks get neighbouring rows"""
+    b = solver.generate([100000], 100.0, seed=1)
+    solver.prepare(b)
+    rp = b.rowptr.cpu().numpy()
+    col = b.col.cpu().numpy()[:b.NNZ]
+    rows = np.repeat(np.arange(b.R), np.diff(rp))
+    dist = np.abs(col - rows)
+    assert np.median(dist) < b.R / 100            # random order would give ~R/3
+    chunk = (b.R + 15) // 16
+    local = (col // chunk) == (rows // chunk)
+    assert local.mean() > 0.85                    # gathers served from the CTA's own chunk (16-CTA cluster)
+    solver.spatial_order = False
+    try:
+        b2 = solver.generate([100000], 100.0, seed=1)
+        solver.prepare(b2)
+        rp2 = b2.rowptr.cpu().numpy()
+        col2 = b2.col.cpu().numpy()[:b2.NNZ]
+        rows2 = np.repeat(np.arange(b2.R), np.diff(rp2))
+        assert np.median(np.abs(col2 - rows2)) > 20 * np.median(dist)
+        assert np.array_equal(b2.row_stick.cpu().numpy()[:b2.R], np.sort(b.row_stick.cpu().numpy()[:b.R]))
+    finally:
+        solver.spatial_order = True
