@@ -190,6 +190,8 @@ int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const in
  * Returns CNT_ECAPACITY if a system has more than cnt_pcg_cluster_max_rows() rows (use
  * cnt_pcg_solve for those). */
 int64_t cnt_pcg_cluster_max_rows(void);
+/* clusters of C CTAs (C = 1,2,4,8,16) that can be resident at once on the current device */
+int cnt_pcg_cluster_active(int C);
 int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R);
 int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
                           const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "cnt_pcg_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, i32, vp, vp, vp, vp, i64, vp]),
     "cnt_pcg_cluster_max_rows": (i64, []),
+    "cnt_pcg_cluster_active": (i32, [i32]),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i64, vp]),
     "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),

@@ -263,6 +263,39 @@ extern "C" int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t 
 // largest system (rows) the cluster kernel can take
 extern "C" int64_t cnt_pcg_cluster_max_rows(void) { return (int64_t)MAXC * CAP; }
 
+static int launch_config(int C, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, cudaStream_t st, int *nclusters) {
+    CNT_CUDA(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    if (C > 8) CNT_CUDA(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    *cfg = cudaLaunchConfig_t{};
+    cfg->blockDim = dim3(CT, 1, 1);
+    cfg->dynamicSmemBytes = SMEM_BYTES;
+    cfg->stream = st;
+    cfg->attrs = attr;
+    cfg->numAttrs = 1;
+    cfg->gridDim = dim3((unsigned)C, 1, 1);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(nclusters, k_pcg_cluster, cfg);
+    if (e != cudaSuccess || *nclusters <= 0) {
+        cnt::set_error("cluster size %d not launchable: %s", C, cudaGetErrorString(e));
+        cudaGetLastError();
+        return CNT_ECUDA;
+    }
+    return CNT_OK;
+}
+
+// number of clusters of C CTAs that can be resident at once on the current device (0 on error)
+extern "C" int cnt_pcg_cluster_active(int C) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute attr[1];
+    int n = 0;
+    if (C < 1 || C > MAXC || (C & (C - 1))) return 0;
+    if (launch_config(C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
+    return n;
+}
+
 extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
                                      const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr,
                                      const int32_t *col, const double *val, const double *diag, const double *rhs,
@@ -304,28 +337,11 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
         int c = atoi(e);
         if (c >= C && c <= MAXC && (c & (c - 1)) == 0) C = c;
     }
-    CNT_CUDA(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    if (C > 8) CNT_CUDA(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-
-    cudaLaunchConfig_t cfg = {};
+    cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.blockDim = dim3(CT, 1, 1);
-    cfg.dynamicSmemBytes = SMEM_BYTES;
-    cfg.stream = st;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    cfg.gridDim = dim3((unsigned)C, 1, 1);
     int nclusters = 0;
-    cudaError_t e = cudaOccupancyMaxActiveClusters(&nclusters, k_pcg_cluster, &cfg);
-    if (e != cudaSuccess || nclusters <= 0) {
-        cnt::set_error("cluster size %d not launchable: %s", C, cudaGetErrorString(e));
-        cudaGetLastError();
-        return CNT_ECUDA;
-    }
+    int rc = launch_config(C, &cfg, attr, st, &nclusters);
+    if (rc) return rc;
     if (nclusters > NSYS) nclusters = NSYS;
     cfg.gridDim = dim3((unsigned)(nclusters * C), 1, 1);
 

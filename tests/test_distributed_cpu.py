@@ -1,0 +1,99 @@
+"""CPU, world_size 2, gloo: the N>1 host logic of the ensemble driver
+(measure_perc.measure_async: contiguous shard per rank, all-gather of the per-network rows).
+The GPU body (`measure_ensemble`) is replaced by a deterministic stub -- here computed with the
+oracle on tiny networks -- because this test runs without a GPU; the sharded result must equal
+the single-process result row for row."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pandas as pd
+import pytest
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _stub_measure_ensemble(ns, scaling, seeds, onoffmap=1, **kw):
+    """stand-in for the GPU body: oracle on the same (n, seed) inputs"""
+    from networksim_cntfet_b200 import measure_perc
+    from oracle import cntnet_oracle as O
+    res = {k: [] for k in ("percolating", "nclust", "maxclust", "ion", "ioff_back", "ioff_total", "ioff_partial")}
+    for n, seed in zip(ns, seeds):
+        s = O.sticks_with_ends(O.canonical_sort(O.make_sticks_mt19937(int(n), "exp", 0.135, scaling, int(seed))))
+        m = O.measure_fullnet(s, onoffmap=onoffmap)
+        res["percolating"].append(m["percolating"])
+        res["nclust"].append(m["nclust_ref"])
+        res["maxclust"].append(m["maxclust_ref"])
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            res[k].append(m[k])
+    res = {k: np.asarray(v) for k, v in res.items()}
+    return measure_perc._rows_from_ensemble(res, [int(n) for n in ns], scaling, np.asarray(seeds, dtype=np.uint64), onoffmap)
+
+
+def _run_async(tmpdir):
+    from networksim_cntfet_b200 import measure_perc
+    measure_perc.measure_ensemble = _stub_measure_ensemble
+    os.chdir(tmpdir)
+    seeds = list(range(40, 51))
+    return measure_perc.measure_async(2, 150, 25, 11, 5, onoffmap=[0, 1], seeds=seeds)
+
+
+def _worker(rank, world, port, tmpdir, q):
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from networksim_cntfet_b200 import measure_perc
+        lo, hi, r, w = measure_perc._shard(11)
+        df = _run_async(os.path.join(tmpdir, "r%d" % rank))
+        q.put((rank, (lo, hi, r, w), df.reset_index(drop=True).to_dict("list")))
+    finally:
+        dist.destroy_process_group()
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+@pytest.mark.timeout(300)
+def test_measure_async_world2_gloo(tmp_path):
+    for r in range(2):
+        os.makedirs(tmp_path / ("r%d" % r))
+    os.makedirs(tmp_path / "single")
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    got.sort()
+    assert got[0][1] == (0, 5, 0, 2) and got[1][1] == (5, 11, 1, 2)        # contiguous, balanced shards
+    frames = [pd.DataFrame(g[2]) for g in got]
+    cwd = os.getcwd()
+    try:
+        single = _run_async(str(tmp_path / "single")).reset_index(drop=True)
+    finally:
+        os.chdir(cwd)
+    for f in frames:                                                       # every rank holds the full result
+        f = f.reset_index(drop=True)
+        assert len(f) == len(single)
+        assert f.sticks.tolist() == single.sticks.tolist() and f.gate.tolist() == single.gate.tolist()
+        assert f.onoffmap.tolist() == single.onoffmap.tolist() and f.seed.tolist() == single.seed.tolist()
+        assert np.allclose(f.ion.values.astype(float), single.ion.values.astype(float), rtol=1e-14, atol=0)
+        assert np.allclose(f.ioff.values.astype(float), single.ioff.values.astype(float), rtol=1e-14, atol=0)
+    assert set(single.sticks) == {150 + 25 * i for i in range(11)}
+    # only rank 0 writes the seeds file (measure_perc.py:226-229)
+    assert any(n.startswith("seeds_") for n in os.listdir(tmp_path / "r0"))
+    assert not any(n.startswith("seeds_") for n in os.listdir(tmp_path / "r1"))
