@@ -132,7 +132,10 @@ int cnt_label_clusters(int B, const int32_t *soff, const int32_t *joff, int64_t 
  * Two-phase like the junction finder: _pattern_count fills rowcnt[R]; caller scans.
  * _values evaluates one gate configuration: g[e] = gtable[kind2[e]*nlevels + level[e]]
  * (table computed on the host with the reference's own formula so conductances are
- * bit-identical), val = -g[nz_eid], diag = row sum incl. electrode contacts, rhs = 0.1*g_src.
+ * bit-identical), val = -g[nz_eid], diag = row sum incl. electrode contacts, rhs = 0.1*g_src;
+ * cls[k] = kind2*nlevels + level of the entry's junction (so val[k] == -gtable[cls[k]]; needs
+ * 9*nlevels <= 256), the compressed form the cluster PCG kernel keeps in shared memory.
+ * gtable == NULL: g[] is an input (conductances evaluated by the caller), cls must be NULL.
  * ------------------------------------------------------------------------------------- */
 int64_t cnt_assemble_workspace_bytes(int64_t n_sticks_total);
 int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
@@ -162,7 +165,8 @@ int cnt_gate_levels(int64_t J, const double *jx, const double *jy, uint8_t *leve
 int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, const double *gtable, int nlevels,
                         int64_t R, const int32_t *rowptr, const int32_t *nz_eid,
                         const int32_t *src_eid, const int32_t *drn_eid,
-                        double *g, double *val, double *diag, double *rhs, void *stream);
+                        double *g, double *val, double *diag, double *rhs, uint8_t *cls /* may be NULL */,
+                        void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (5) solve -- replaces solve_mna (cnet.py:147-149, SuperLU) by a batched Jacobi-PCG.
@@ -174,12 +178,43 @@ int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, c
  * Per system: iters (int32), relres (double), status (0 converged, 1 maxit, 2 breakdown).
  * Synchronises the stream every `check_every` iterations to poll for completion.
  * ------------------------------------------------------------------------------------- */
+/* Two-level preconditioner (optional, both solvers): M^-1 = D^-1 + Z diag(Z^T A Z)^-1 Z^T with
+ * Z the indicator vectors of the aggregates of strongly coupled unknowns (connected components
+ * of the entries with |val| > theta * max|val| of the system).  Jacobi on the fine level plus
+ * Jacobi on the aggregate level: per iteration one segmented sum and one broadcast.  It cuts
+ * the iteration count 5-60x on gated networks (DESIGN.md "Two-level preconditioner") and is
+ * deterministic.  cnt_pcg_aggregates builds the tables (it synchronises the stream once);
+ * system indices stored in seg_sys refer to the h_sys_* arrays given to it, so the solver must
+ * be called with the same system list.  Capacities: agg_of_row, mem: NSLAB*R; seg_*:
+ * NSLAB*R/2 + NSLAB*R/256 + 1; agg_seg0: NSLAB*R/2 + 2; agg_einv: NSLAB*R/2 + 1. */
+typedef struct cnt_aggregates {
+    const int32_t *agg_of_row;   /* [NSLAB*R] aggregate of slab row (slab*R + row), -1 = none      */
+    const int32_t *mem;          /* [NSLAB*R] slab rows sorted by aggregate                        */
+    const int32_t *seg_start;    /* [nseg] first member (index into mem) of a segment (<= 256 rows) */
+    const int32_t *seg_count;    /* [nseg]                                                          */
+    const int32_t *seg_agg;      /* [nseg] aggregate of the segment                                 */
+    const int32_t *seg_sys;      /* [nseg] system of the segment                                    */
+    const int32_t *agg_seg0;     /* [nagg+1] first segment of an aggregate                          */
+    const double *agg_einv;      /* [nagg] 1 / (Z^T A Z)_aa                                         */
+    const int32_t *sys_seg;      /* [2*NSYS] segments of system s: [sys_seg[2s], sys_seg[2s+1])     */
+    int64_t nagg, nseg;
+} cnt_aggregates;
+int64_t cnt_pcg_aggregate_workspace_bytes(int NSYS, int NSLAB, int64_t R);
+int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
+                       const int32_t *h_roff, const int32_t *roff, int64_t R, int64_t NNZ,
+                       const int32_t *rowptr, const int32_t *col, const double *val, const double *diag,
+                       double theta, int32_t *agg_of_row, int32_t *mem, int32_t *seg_start,
+                       int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
+                       double *agg_einv, int32_t *sys_seg /* [2*NSYS] */, int64_t *h_nagg, int64_t *h_nseg,
+                       void *ws, int64_t ws_bytes, void *stream);
+
 int64_t cnt_pcg_workspace_bytes(int NSYS, int NSLAB, int64_t R);
 int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
                   const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,
                   const double *val, const double *diag, const double *rhs, double *x,
                   double rtol, int maxit, int check_every,
                   int32_t *iters, double *relres, int32_t *status,
+                  const cnt_aggregates *agg /* NULL = plain Jacobi */,
                   void *ws, int64_t ws_bytes, void *stream);
 
 /* Persistent thread-block-cluster variant of the same solve (pcg_cluster.cu): ONE launch for
@@ -188,16 +223,22 @@ int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const in
  * distributed shared memory, phase boundaries = hardware cluster barriers).  Same arguments,
  * stopping rule and per-system outputs as cnt_pcg_solve; nothing synchronises the stream.
  * Returns CNT_ECAPACITY if a system has more than cnt_pcg_cluster_max_rows() rows (use
- * cnt_pcg_solve for those). */
+ * cnt_pcg_solve for those).  With cls/gneg (from cnt_assemble_values) every CTA packs its
+ * slice of the matrix into shared memory (16-bit slot + 8-bit class per entry) so that an
+ * iteration touches global memory only for the halo exchange of p; a system whose slice or
+ * halo does not fit gets status 3 and must be re-solved with cnt_pcg_solve. */
 int64_t cnt_pcg_cluster_max_rows(void);
 /* clusters of C CTAs (C = 1,2,4,8,16) that can be resident at once on the current device */
 int cnt_pcg_cluster_active(int C);
 int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R);
 int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
                           const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,
-                          const double *val, const double *diag, const double *rhs, double *x,
+                          const double *val, const uint8_t *cls /* [NSLAB*NNZ] or NULL */,
+                          const double *gneg /* [NSLAB*256] = -gtable, or NULL */,
+                          const double *diag, const double *rhs, double *x,
                           double rtol, int maxit,
                           int32_t *iters, double *relres, int32_t *status,
+                          const cnt_aggregates *agg /* NULL = plain Jacobi; needs cls/gneg */,
                           void *ws, int64_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------

@@ -1,0 +1,317 @@
+// Aggregates of strongly coupled unknowns for the additive two-level preconditioner
+//        M^-1 = D^-1 + Z diag(Z^T A Z)^-1 Z^T            (Z = aggregate indicator vectors)
+// used by the PCG solvers (pcg.cu, pcg_cluster.cu).
+//
+// Why: junction conductances are bimodal (~1 for mm/ss/vm contacts, e^-5 ... e^-10 for gated
+// ms/vs contacts, cnet.py:23-41).  Sticks joined by strong junctions form nearly equipotential
+// clusters that float on a few weak links; each contributes one tiny eigenvalue that plain
+// Jacobi cannot see (217k iterations at Vg=+10 on a 100x100 um network).  Adding Jacobi on the
+// aggregate level (one unknown per cluster, diagonal = total conductance leaving the cluster)
+// brings that to ~4k iterations.  With no contrast there is one aggregate and the method
+// degenerates gracefully to Jacobi plus a constant-mode correction.
+//
+// Everything is deterministic: aggregates = connected components of the strong sub-graph by
+// union-find with minimum-index roots, members ordered by a stable radix sort, per-aggregate
+// sums taken by one warp per segment (<= SEGW members) in a fixed order.
+#include <algorithm>
+#include <vector>
+#include "common.cuh"
+
+namespace {
+constexpr int SEGW = 256;       // members per segment (one warp sums a segment)
+constexpr int TILE = 256;
+
+struct ATile {
+    int32_t sys, row0, nrows, slab;   // row0 = global pattern row
+};
+struct ASys {
+    int32_t net_row0, nrows, slab, pad;
+};
+
+__device__ __forceinline__ int uf_find(int *parent, int x) {
+    int p = ((volatile int *)parent)[x];
+    while (p != x) {
+        int gp = ((volatile int *)parent)[p];
+        if (gp != p) ((volatile int *)parent)[x] = gp;
+        x = p;
+        p = gp;
+    }
+    return x;
+}
+
+__global__ void k_iota(int64_t n, int32_t *parent) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v < n) parent[v] = (int)v;
+}
+
+__global__ void __launch_bounds__(TILE) k_gmax(const ATile *__restrict__ tiles, int64_t NNZ,
+                                                const int32_t *__restrict__ rowptr, const double *__restrict__ val,
+                                                unsigned long long *__restrict__ gmax) {
+    ATile t = tiles[blockIdx.x];
+    double m = 0.0;
+    if (threadIdx.x < t.nrows) {
+        int row = t.row0 + threadIdx.x;
+        const double *v = val + (int64_t)t.slab * NNZ;
+        for (int e = rowptr[row]; e < rowptr[row + 1]; e++) m = fmax(m, fabs(v[e]));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(gmax + t.sys, (unsigned long long)__double_as_longlong(m));
+}
+
+__global__ void __launch_bounds__(TILE) k_strong_union(const ATile *__restrict__ tiles, const ASys *__restrict__ sys,
+                                                        int64_t R, int64_t NNZ, const int32_t *__restrict__ rowptr,
+                                                        const int32_t *__restrict__ col, const double *__restrict__ val,
+                                                        const unsigned long long *__restrict__ gmax, double theta,
+                                                        int32_t *parent) {
+    ATile t = tiles[blockIdx.x];
+    if (threadIdx.x >= t.nrows) return;
+    ASys s = sys[t.sys];
+    double thr = theta * __longlong_as_double((long long)gmax[t.sys]);
+    int row = t.row0 + threadIdx.x;
+    int li = row - s.net_row0;
+    int64_t vb = (int64_t)t.slab * R + s.net_row0;
+    const double *v = val + (int64_t)t.slab * NNZ;
+    for (int e = rowptr[row]; e < rowptr[row + 1]; e++) {
+        int lj = col[e];
+        if (lj <= li || !(fabs(v[e]) > thr)) continue;
+        int a = (int)(vb + li), c = (int)(vb + lj);
+        while (true) {
+            a = uf_find(parent, a);
+            c = uf_find(parent, c);
+            if (a == c) break;
+            int hi = a > c ? a : c, lo = a > c ? c : a;
+            if (atomicCAS(parent + hi, hi, lo) == hi) break;
+            a = hi;
+            c = lo;
+        }
+    }
+}
+
+__global__ void k_roots(int64_t n, int32_t *parent, unsigned long long *__restrict__ key, uint32_t *__restrict__ v32) {
+    int64_t v = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= n) return;
+    key[v] = (unsigned long long)uf_find(parent, (int)v);
+    v32[v] = (uint32_t)v;
+}
+
+__global__ void k_fill_i32(int64_t n, int32_t *p, int32_t v) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+
+// one warp per segment: mark the members' aggregate
+__global__ void k_mark(int64_t nseg, const int32_t *__restrict__ seg_start, const int32_t *__restrict__ seg_count,
+                       const int32_t *__restrict__ seg_agg, const uint32_t *__restrict__ mem,
+                       int32_t *__restrict__ agg_of_row) {
+    int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nseg) return;
+    int lane = threadIdx.x & 31;
+    int s0 = seg_start[s], n = seg_count[s], a = seg_agg[s];
+    for (int k = lane; k < n; k += 32) agg_of_row[mem[s0 + k]] = a;
+}
+
+// one warp per segment: sum over members of (diag + entries that stay inside the aggregate)
+__global__ void k_seg_E(int64_t nseg, const int32_t *__restrict__ seg_start, const int32_t *__restrict__ seg_count,
+                        const int32_t *__restrict__ seg_agg, const uint32_t *__restrict__ mem,
+                        const int32_t *__restrict__ agg_of_row, int B, const int32_t *__restrict__ roff, int64_t R,
+                        int64_t NNZ, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ col,
+                        const double *__restrict__ val, const double *__restrict__ diag, double *__restrict__ segE) {
+    int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nseg) return;
+    int lane = threadIdx.x & 31;
+    int s0 = seg_start[s], n = seg_count[s], a = seg_agg[s];
+    double acc = 0.0;
+    for (int k = lane; k < n; k += 32) {
+        int64_t v = mem[s0 + k];
+        int slab = (int)(v / R), row = (int)(v - (int64_t)slab * R);
+        int net0 = roff[cnt::find_segment(roff, B, row)];
+        int64_t vb = (int64_t)slab * R + net0;
+        const double *vv = val + (int64_t)slab * NNZ;
+        double e = diag[v];
+        for (int q = rowptr[row]; q < rowptr[row + 1]; q++)
+            if (agg_of_row[vb + col[q]] == a) e += vv[q];
+        acc += e;
+    }
+    acc = cnt::warp_sum(acc);
+    if (lane == 0) segE[s] = acc;
+}
+
+__global__ void k_agg_einv(int64_t nagg, const int32_t *__restrict__ agg_seg0, const double *__restrict__ segE,
+                           double *__restrict__ einv) {
+    int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (a >= nagg) return;
+    double e = 0.0;
+    for (int s = agg_seg0[a]; s < agg_seg0[a + 1]; s++) e += segE[s];
+    // E is a difference of large numbers (internal strong links cancel): accuracy is irrelevant
+    // for a preconditioner, positivity is not
+    einv[a] = (e > 0.0 && e == e) ? 1.0 / e : 0.0;
+}
+}  // namespace
+
+extern "C" int64_t cnt_pcg_aggregate_workspace_bytes(int NSYS, int NSLAB, int64_t R) {
+    using cnt::ws_bytes_for;
+    int64_t n = (int64_t)NSLAB * R;
+    int64_t nt = (int64_t)NSYS * ((R + TILE - 1) / TILE + 1);
+    return ws_bytes_for(n, 4) + ws_bytes_for(NSYS, 8) + 2 * ws_bytes_for(n, 8) + 2 * ws_bytes_for(n, 4) +
+           ws_bytes_for(nt, sizeof(ATile)) + ws_bytes_for(NSYS, sizeof(ASys)) + ws_bytes_for(n / 2 + n / SEGW + 2, 8) +
+           cnt::segsort_workspace_bytes(n, 2 * NSYS + 2);
+}
+
+// Capacity the caller must provide: agg_of_row, mem: NSLAB*R; seg_*: NSLAB*R/2 + NSLAB*R/256 + 1;
+// agg_seg0: NSLAB*R/2 + 2; agg_einv: NSLAB*R/2 + 1.  Synchronises the stream (the run structure
+// of the sorted roots is read back once to build the segment tables).
+extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
+                                  const int32_t *h_roff, const int32_t *roff, int64_t R, int64_t NNZ,
+                                  const int32_t *rowptr, const int32_t *col, const double *val, const double *diag,
+                                  double theta, int32_t *agg_of_row, int32_t *mem, int32_t *seg_start,
+                                  int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
+                                  double *agg_einv, int32_t *sys_seg,
+                                  int64_t *h_nagg, int64_t *h_nseg, void *ws, int64_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && roff && R >= 0 && h_nagg &&
+                  h_nseg && ws && theta > 0);
+    *h_nagg = 0;
+    *h_nseg = 0;
+    int64_t n = (int64_t)NSLAB * R;
+    if (n == 0) return CNT_OK;
+    CNT_CHECK_ARG(n < ((int64_t)1 << 31));
+    CNT_CHECK_ARG(rowptr && diag && agg_of_row && mem && seg_start && seg_count && seg_agg && seg_sys && agg_seg0 &&
+                  agg_einv && sys_seg);
+    // systems sorted by (slab, network) are the sort segments; tiles for the row kernels
+    std::vector<ASys> sys(NSYS);
+    std::vector<ATile> tiles;
+    std::vector<std::pair<int64_t, int>> order(NSYS);
+    for (int s = 0; s < NSYS; s++) {
+        int b = h_sys_net[s];
+        CNT_CHECK_ARG(b >= 0 && b < B && h_sys_slab[s] >= 0 && h_sys_slab[s] < NSLAB);
+        sys[s].net_row0 = h_roff[b];
+        sys[s].nrows = h_roff[b + 1] - h_roff[b];
+        sys[s].slab = h_sys_slab[s];
+        sys[s].pad = 0;
+        order[s] = {(int64_t)h_sys_slab[s] * R + h_roff[b], s};
+        for (int t = 0; t * TILE < sys[s].nrows; t++) {
+            ATile tl;
+            tl.sys = s;
+            tl.row0 = sys[s].net_row0 + t * TILE;
+            tl.nrows = sys[s].nrows - t * TILE < TILE ? sys[s].nrows - t * TILE : TILE;
+            tl.slab = sys[s].slab;
+            tiles.push_back(tl);
+        }
+    }
+    std::sort(order.begin(), order.end());
+    // sort segments must tile [0, n): systems plus the gaps between them (rows of pairs that are
+    // not being solved stay singletons)
+    std::vector<int32_t> h_off;
+    h_off.push_back(0);
+    for (int k = 0; k < NSYS; k++) {
+        int64_t lo = order[k].first, hi = lo + sys[order[k].second].nrows;
+        if (lo < h_off.back()) {
+            cnt::set_error("duplicate (network, slab) system");
+            return CNT_EINVAL;
+        }
+        if (lo > h_off.back()) h_off.push_back((int32_t)lo);
+        if (hi > h_off.back()) h_off.push_back((int32_t)hi);
+    }
+    if (h_off.back() < n) h_off.push_back((int32_t)n);
+    int nsortseg = (int)h_off.size() - 1;
+    int64_t nt = (int64_t)tiles.size();
+
+    cnt::Workspace w(ws, ws_bytes);
+    int32_t *parent = w.take<int32_t>(n);
+    unsigned long long *gmax = w.take<unsigned long long>(NSYS);
+    unsigned long long *keyA = w.take<unsigned long long>(n), *keyB = w.take<unsigned long long>(n);
+    uint32_t *valA = w.take<uint32_t>(n), *valB = w.take<uint32_t>(n);
+    ATile *d_tiles = w.take<ATile>((int64_t)NSYS * ((R + TILE - 1) / TILE + 1));
+    ASys *d_sys = w.take<ASys>(NSYS);
+    double *segE = w.take<double>(n / 2 + n / SEGW + 2);
+    int64_t sb = cnt::segsort_workspace_bytes(n, 2 * NSYS + 2);
+    void *sws = w.take<char>(sb);
+    if (!sws || nsortseg > 2 * NSYS + 1) {
+        cnt::set_error("aggregate workspace too small");
+        return CNT_ECAPACITY;
+    }
+    CNT_CUDA(cudaMemcpyAsync(d_sys, sys.data(), sizeof(ASys) * NSYS, cudaMemcpyHostToDevice, st));
+    if (nt) CNT_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(ATile) * nt, cudaMemcpyHostToDevice, st));
+    CNT_CUDA(cudaMemsetAsync(gmax, 0, 8 * NSYS, st));
+    k_iota<<<cnt::grid_for(n, 256), 256, 0, st>>>(n, parent);
+    CNT_LAUNCHED();
+    if (nt && NNZ > 0) {
+        k_gmax<<<(unsigned)nt, TILE, 0, st>>>(d_tiles, NNZ, rowptr, val, gmax);
+        CNT_LAUNCHED();
+        k_strong_union<<<(unsigned)nt, TILE, 0, st>>>(d_tiles, d_sys, R, NNZ, rowptr, col, val, gmax, theta, parent);
+        CNT_LAUNCHED();
+    }
+    k_roots<<<cnt::grid_for(n, 256), 256, 0, st>>>(n, parent, keyA, valA);
+    CNT_LAUNCHED();
+    int bits = 1;
+    while (((int64_t)1 << bits) < n) bits++;
+    unsigned long long *ks;
+    uint32_t *vs;
+    int rc = cnt::segsort_pairs(nsortseg, h_off.data(), keyA, valA, keyB, valB, (bits + 7) / 8, sws, sb, st, &ks, &vs);
+    if (rc) return rc;
+    // members in aggregate order -> caller's `mem`; sorted roots -> host
+    CNT_CUDA(cudaMemcpyAsync(mem, vs, 4 * n, cudaMemcpyDeviceToDevice, st));
+    std::vector<unsigned long long> roots(n);
+    CNT_CUDA(cudaMemcpyAsync(roots.data(), ks, 8 * n, cudaMemcpyDeviceToHost, st));
+    CNT_CUDA(cudaStreamSynchronize(st));
+    std::vector<int32_t> h_seg_start, h_seg_count, h_seg_agg, h_seg_sys, h_agg_seg0;
+    // position -> system: `order` holds the systems sorted by first position
+    auto sys_of = [&](int64_t pos) {
+        int lo = 0, hi = NSYS - 1;
+        while (lo < hi) {
+            int mid = (lo + hi + 1) >> 1;
+            if (order[mid].first <= pos) lo = mid; else hi = mid - 1;
+        }
+        return order[lo].second;
+    };
+    int64_t i = 0;
+    while (i < n) {
+        int64_t j = i + 1;
+        while (j < n && roots[j] == roots[i]) j++;
+        if (j - i >= 2) {
+            int a = (int)h_agg_seg0.size();
+            int sidx = sys_of((int64_t)roots[i]);
+            h_agg_seg0.push_back((int32_t)h_seg_start.size());
+            for (int64_t p0 = i; p0 < j; p0 += SEGW) {
+                h_seg_start.push_back((int32_t)p0);
+                h_seg_count.push_back((int32_t)((j - p0) < SEGW ? (j - p0) : SEGW));
+                h_seg_agg.push_back(a);
+                h_seg_sys.push_back(sidx);
+            }
+        }
+        i = j;
+    }
+    int64_t nagg = (int64_t)h_agg_seg0.size(), nseg = (int64_t)h_seg_start.size();
+    // segments of one system are contiguous (the member array is ordered by system)
+    std::vector<int32_t> h_sys_seg(2 * (size_t)NSYS, 0);
+    for (int64_t q = 0; q < nseg; q++) {
+        int sidx = h_seg_sys[q];
+        if (h_sys_seg[2 * sidx + 1] == 0) h_sys_seg[2 * sidx] = (int32_t)q;
+        h_sys_seg[2 * sidx + 1] = (int32_t)q + 1;
+    }
+    CNT_CUDA(cudaMemcpyAsync(sys_seg, h_sys_seg.data(), 4 * 2 * (size_t)NSYS, cudaMemcpyHostToDevice, st));
+    h_agg_seg0.push_back((int32_t)nseg);
+    *h_nagg = nagg;
+    *h_nseg = nseg;
+    k_fill_i32<<<cnt::grid_for(n, 256), 256, 0, st>>>(n, agg_of_row, -1);
+    CNT_LAUNCHED();
+    CNT_CUDA(cudaMemcpyAsync(agg_seg0, h_agg_seg0.data(), 4 * (nagg + 1), cudaMemcpyHostToDevice, st));
+    if (nseg > 0) {
+        CNT_CUDA(cudaMemcpyAsync(seg_start, h_seg_start.data(), 4 * nseg, cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(seg_count, h_seg_count.data(), 4 * nseg, cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(seg_agg, h_seg_agg.data(), 4 * nseg, cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(seg_sys, h_seg_sys.data(), 4 * nseg, cudaMemcpyHostToDevice, st));
+        unsigned gwarp = cnt::grid_for(nseg * 32, 256);
+        k_mark<<<gwarp, 256, 0, st>>>(nseg, seg_start, seg_count, seg_agg, (const uint32_t *)mem, agg_of_row);
+        CNT_LAUNCHED();
+        k_seg_E<<<gwarp, 256, 0, st>>>(nseg, seg_start, seg_count, seg_agg, (const uint32_t *)mem, agg_of_row, B, roff, R,
+                                       NNZ, rowptr, col, val, diag, segE);
+        CNT_LAUNCHED();
+        k_agg_einv<<<cnt::grid_for(nagg, 256), 256, 0, st>>>(nagg, agg_seg0, segE, agg_einv);
+        CNT_LAUNCHED();
+    }
+    // host vectors must outlive the async uploads
+    CNT_CUDA(cudaStreamSynchronize(st));
+    return CNT_OK;
+}

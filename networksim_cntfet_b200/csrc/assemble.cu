@@ -106,14 +106,17 @@ __global__ void k_conductance(int64_t J, const uint8_t *__restrict__ kind2, cons
 __global__ void k_values(int64_t R, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ nz_eid,
                          const int32_t *__restrict__ src_eid, const int32_t *__restrict__ drn_eid,
                          const double *__restrict__ g, double *__restrict__ val, double *__restrict__ diag,
-                         double *__restrict__ rhs) {
+                         double *__restrict__ rhs, const uint8_t *__restrict__ kind2,
+                         const uint8_t *__restrict__ level, int nlevels, uint8_t *__restrict__ cls) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     int k0 = rowptr[r], k1 = rowptr[r + 1];
     double sum = 0.0;
     for (int k = k0; k < k1; k++) {
-        double ge = g[nz_eid[k]];
+        int e = nz_eid[k];
+        double ge = g[e];
         val[k] = -ge;
+        if (cls) cls[k] = (uint8_t)((int)kind2[e] * nlevels + (int)level[e]);   // index into the value table
         sum += ge;
     }
     int se = src_eid[r], de = drn_eid[r];
@@ -288,7 +291,7 @@ extern "C" int cnt_gate_levels(int64_t J, const double *jx, const double *jy, ui
 extern "C" int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, const double *gtable,
                                    int nlevels, int64_t R, const int32_t *rowptr, const int32_t *nz_eid,
                                    const int32_t *src_eid, const int32_t *drn_eid, double *g, double *val,
-                                   double *diag, double *rhs, void *stream) {
+                                   double *diag, double *rhs, uint8_t *cls, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(J >= 0 && R >= 0 && nlevels > 0);
     if (J > 0 && gtable) {
@@ -300,7 +303,9 @@ extern "C" int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_
     }
     if (R > 0) {
         CNT_CHECK_ARG(rowptr && nz_eid && src_eid && drn_eid && val && diag && rhs);
-        k_values<<<cnt::grid_for(R, 128), 128, 0, st>>>(R, rowptr, nz_eid, src_eid, drn_eid, g, val, diag, rhs);
+        if (cls) CNT_CHECK_ARG(gtable && kind2 && level && 9 * nlevels <= 256);
+        k_values<<<cnt::grid_for(R, 128), 128, 0, st>>>(R, rowptr, nz_eid, src_eid, drn_eid, g, val, diag, rhs, kind2,
+                                                        level, nlevels, cls);
         CNT_LAUNCHED();
     }
     return CNT_OK;

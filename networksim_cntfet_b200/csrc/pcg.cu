@@ -42,6 +42,9 @@ struct Ctx {
     const double *val, *diag, *rhs;
     double *x, *r, *p, *q;
     double *part0, *part1;   // per-tile partials
+    // two-level preconditioner (agg.nseg == 0: plain Jacobi)
+    cnt_aggregates agg;
+    double *segS;            // per-segment sums of r
 };
 
 __device__ __forceinline__ double spmv_row(const Ctx &c, int sysi, int net_row0, int row, const double *v) {
@@ -202,6 +205,114 @@ __global__ void __launch_bounds__(TILE) k_pupdate(Ctx c) {
     }
 }
 
+// ---------------- two-level preconditioner: z = r/d + (sum of r over the row's aggregate) * einv
+__global__ void k_seg_sum(Ctx c) {
+    int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= c.agg.nseg) return;
+    if (c.scal[c.agg.seg_sys[s]].done) return;
+    int lane = threadIdx.x & 31;
+    int s0 = c.agg.seg_start[s], n = c.agg.seg_count[s];
+    double acc = 0.0;
+    for (int k = lane; k < n; k += 32) acc += c.r[c.agg.mem[s0 + k]];   // fixed order: lane-strided + tree
+    acc = cnt::warp_sum(acc);
+    if (lane == 0) c.segS[s] = acc;
+}
+
+__device__ __forceinline__ double coarse_term(const Ctx &c, int64_t v) {
+    int a = c.agg.agg_of_row[v];
+    if (a < 0) return 0.0;
+    double S = 0.0;
+    for (int s = c.agg.agg_seg0[a]; s < c.agg.agg_seg0[a + 1]; s++) S += c.segS[s];
+    return S * c.agg.agg_einv[a];
+}
+
+__global__ void __launch_bounds__(TILE) k_init_r(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    Sys s = c.sys[t.sys];
+    int i = threadIdx.x;
+    double bb = 0, rr = 0;
+    if (i < t.nrows) {
+        int row = t.row0 + i;
+        int64_t v = (int64_t)t.slab * c.R + row;
+        double b = c.rhs[v];
+        double ri = b - spmv_row(c, t.slab, s.row0, row, c.x);
+        c.r[v] = ri;
+        bb = b * b;
+        rr = ri * ri;
+    }
+    bb = cnt::block_sum(bb, sm);
+    rr = cnt::block_sum(rr, sm);
+    if (i == 0) {
+        c.part1[blockIdx.x] = bb;
+        c.part1[gridDim.x + blockIdx.x] = rr;
+    }
+}
+
+__global__ void __launch_bounds__(TILE) k_init_z(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    int i = threadIdx.x;
+    double rz = 0;
+    if (i < t.nrows) {
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
+        double ri = c.r[v];
+        double zi = ri / c.diag[v] + coarse_term(c, v);
+        c.p[v] = zi;
+        rz = ri * zi;
+    }
+    rz = cnt::block_sum(rz, sm);
+    if (i == 0) c.part0[blockIdx.x] = rz;
+}
+
+__global__ void __launch_bounds__(TILE) k_update_r(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    const Scal *sc = c.scal + t.sys;
+    if (sc->done) return;
+    double alpha = sc->alpha;
+    int i = threadIdx.x;
+    double rr = 0;
+    if (i < t.nrows) {
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
+        c.x[v] += alpha * c.p[v];
+        double ri = c.r[v] - alpha * c.q[v];
+        c.r[v] = ri;
+        rr = ri * ri;
+    }
+    rr = cnt::block_sum(rr, sm);
+    if (i == 0) c.part1[blockIdx.x] = rr;
+}
+
+__global__ void __launch_bounds__(TILE) k_zdot(Ctx c) {
+    __shared__ double sm[32];
+    Tile t = c.tiles[blockIdx.x];
+    if (c.scal[t.sys].done) return;
+    int i = threadIdx.x;
+    double rz = 0;
+    if (i < t.nrows) {
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
+        double ri = c.r[v];
+        double zi = ri / c.diag[v] + coarse_term(c, v);
+        c.q[v] = zi;               // q is free after k_update_r: reuse it for z
+        rz = ri * zi;
+    }
+    rz = cnt::block_sum(rz, sm);
+    if (i == 0) c.part0[blockIdx.x] = rz;
+}
+
+__global__ void __launch_bounds__(TILE) k_pupdate_z(Ctx c) {
+    Tile t = c.tiles[blockIdx.x];
+    const Scal *sc = c.scal + t.sys;
+    if (sc->done) return;
+    double beta = sc->beta;
+    int i = threadIdx.x;
+    if (i < t.nrows) {
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
+        c.p[v] = c.q[v] + beta * c.p[v];
+    }
+}
+
 __global__ void k_export(Ctx c, int nsys, int32_t *iters, double *relres, int32_t *status, int32_t *alldone) {
     int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= nsys) return;
@@ -250,13 +361,14 @@ extern "C" int64_t cnt_pcg_workspace_bytes(int NSYS, int NSLAB, int64_t R) {
     int64_t nt = count_tiles(NSYS, R);
     return ws_bytes_for(nt, sizeof(Tile)) + ws_bytes_for(NSYS, sizeof(Sys)) + ws_bytes_for(NSYS, sizeof(Scal)) +
            3 * ws_bytes_for((int64_t)NSLAB * R + 1, 8) + ws_bytes_for(nt, 8) + ws_bytes_for(2 * nt, 8) +
-           ws_bytes_for(1, 4);
+           ws_bytes_for(1, 4) + ws_bytes_for((int64_t)NSLAB * R / 2 + (int64_t)NSLAB * R / 256 + 2, 8);
 }
 
 extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
                              const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col, const double *val, const double *diag,
                              const double *rhs, double *x, double rtol, int maxit, int check_every, int32_t *iters,
-                             double *relres, int32_t *status, void *ws, int64_t ws_bytes, void *stream) {
+                             double *relres, int32_t *status, const cnt_aggregates *agg, void *ws, int64_t ws_bytes,
+                             void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && R >= 0 && NNZ >= 0 && iters && relres && status && ws);
     CNT_CHECK_ARG(rtol > 0 && maxit >= 0 && check_every > 0);
@@ -278,7 +390,9 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
     double *part0 = w.take<double>(nt_alloc);
     double *part1 = w.take<double>(2 * nt_alloc);
     int32_t *alldone = w.take<int32_t>(1);
-    if (!alldone) {
+    const bool two_level = agg && agg->nseg > 0;
+    double *segS = w.take<double>(two_level ? agg->nseg : 1);
+    if (!alldone || !segS) {
         cnt::set_error("pcg workspace too small: have %lld need %lld", (long long)ws_bytes,
                        (long long)cnt_pcg_workspace_bytes(NSYS, NSLAB, R));
         return CNT_ECAPACITY;
@@ -289,10 +403,22 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
     c.tiles = d_tiles; c.sys = d_sys; c.scal = d_scal; c.R = R; c.NNZ = NNZ;
     c.rowptr = rowptr; c.col = col; c.val = val; c.diag = diag; c.rhs = rhs;
     c.x = x; c.r = r; c.p = p; c.q = q; c.part0 = part0; c.part1 = part1;
+    c.segS = segS;
+    if (two_level) c.agg = *agg; else { c.agg = cnt_aggregates{}; }
+    unsigned gseg = two_level ? cnt::grid_for(agg->nseg * 32, 256) : 0;
     unsigned gs = cnt::grid_for(NSYS, 128);            // one thread per system (export)
     unsigned gw = cnt::grid_for((int64_t)NSYS * 32, 128);   // one warp per system (scalar kernels)
-    if (nt > 0) {
+    if (nt > 0 && !two_level) {
         k_init<<<(unsigned)nt, TILE, 0, st>>>(c);
+        CNT_LAUNCHED();
+    } else if (nt > 0) {
+        k_init_r<<<(unsigned)nt, TILE, 0, st>>>(c);
+        CNT_LAUNCHED();
+        // every system is live here: Scal is not initialised yet, so zero the done flags first
+        CNT_CUDA(cudaMemsetAsync(d_scal, 0, sizeof(Scal) * NSYS, st));
+        k_seg_sum<<<gseg, 256, 0, st>>>(c);
+        CNT_LAUNCHED();
+        k_init_z<<<(unsigned)nt, TILE, 0, st>>>(c);
         CNT_LAUNCHED();
     }
     k_scal_init<<<gw, 128, 0, st>>>(c, (int)nt, rtol, NSYS);
@@ -303,12 +429,25 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
         CNT_LAUNCHED();
         k_scal_alpha<<<gw, 128, 0, st>>>(c, NSYS);
         CNT_LAUNCHED();
-        k_update<<<(unsigned)nt, TILE, 0, st>>>(c);
-        CNT_LAUNCHED();
-        k_scal_beta<<<gw, 128, 0, st>>>(c, NSYS, rtol, maxit);
-        CNT_LAUNCHED();
-        k_pupdate<<<(unsigned)nt, TILE, 0, st>>>(c);
-        CNT_LAUNCHED();
+        if (!two_level) {
+            k_update<<<(unsigned)nt, TILE, 0, st>>>(c);
+            CNT_LAUNCHED();
+            k_scal_beta<<<gw, 128, 0, st>>>(c, NSYS, rtol, maxit);
+            CNT_LAUNCHED();
+            k_pupdate<<<(unsigned)nt, TILE, 0, st>>>(c);
+            CNT_LAUNCHED();
+        } else {
+            k_update_r<<<(unsigned)nt, TILE, 0, st>>>(c);
+            CNT_LAUNCHED();
+            k_seg_sum<<<gseg, 256, 0, st>>>(c);
+            CNT_LAUNCHED();
+            k_zdot<<<(unsigned)nt, TILE, 0, st>>>(c);
+            CNT_LAUNCHED();
+            k_scal_beta<<<gw, 128, 0, st>>>(c, NSYS, rtol, maxit);
+            CNT_LAUNCHED();
+            k_pupdate_z<<<(unsigned)nt, TILE, 0, st>>>(c);
+            CNT_LAUNCHED();
+        }
         return CNT_OK;
     };
 
@@ -340,7 +479,7 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
     while (!h_alldone && done_iters < maxit) {
         if (use_graph) {
             cudaError_t e = cudaGraphLaunch(gexec, st);
-            cnt::count_launch(5 * check_every);
+            cnt::count_launch((two_level ? 7 : 5) * check_every);
             if (e != cudaSuccess) {
                 cnt::set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
                 rc = CNT_ECUDA;

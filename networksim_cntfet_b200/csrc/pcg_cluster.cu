@@ -41,7 +41,13 @@ struct CArgs {
     int64_t R, NNZ;
     const int32_t *rowptr, *col;
     const double *val, *diag, *rhs;
+    const uint8_t *cls;      // v2: class code per entry (val == gneg[cls])
+    const double *gneg;      // v2: [NSLAB][256]
     double *x, *pglob;
+    // two-level preconditioner (TWO kernels only)
+    cnt_aggregates agg;
+    double *rglob;           // [NSLAB*R] r published once per iteration for the segment sums
+    double *segS;            // [nseg]
     double rtol;
     int maxit;
     int32_t *iters, *status;
@@ -53,6 +59,9 @@ struct Shared {
     double bcast[4];       // cluster-wide sums, broadcast inside the CTA
     double warp[32];       // block reduction scratch
     int next;              // next system (valid in CTA rank 0)
+    int nhalo;             // v2: halo references collected by this CTA
+    int ovf;               // v2: slice / halo did not fit
+    int pad;
 };
 
 // deterministic block sums of up to 3 values at once; results valid in thread 0
@@ -247,37 +256,340 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster(CArgs a) {
     }
 }
 
+
+// =====================================================================================
+// v2: the CTA's slice of the matrix lives in shared memory for the whole solve.
+// Per entry one 32-bit word: (slot << 8) | class, where slot indexes p_ext[] -- the CTA's own
+// p values followed by the halo values it needs from other CTAs -- and class indexes a
+// 256-entry table of -g (conductances take only a handful of distinct values per gate
+// configuration: junction kind x gate level).  An iteration then touches global memory only
+// to publish p (8 B/row), refresh the halo (one coalesced pass of L2 loads) and update x.
+// =====================================================================================
+constexpr int MAXR2 = 5;               // rows per thread
+constexpr int CAP2 = CT * MAXR2;       // rows per CTA (5120)
+constexpr int ECAP = 20480;            // packed entries per CTA
+constexpr int HCAP = 2048;             // halo references per CTA
+
+__device__ __forceinline__ int block_excl_scan_i(int v, int *sm /*34 ints*/, int *total) {
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) sm[w] = incl;
+    __syncthreads();
+    if (w == 0) {
+        int sv = sm[lane];                 // CT/32 == 32 warps
+        int si = sv;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int u = __shfl_up_sync(0xffffffffu, si, o);
+            if (lane >= o) si += u;
+        }
+        sm[lane] = si - sv;
+        if (lane == 31) sm[32] = si;
+    }
+    __syncthreads();
+    int r = sm[w] + incl - v;
+    *total = sm[32];
+    __syncthreads();
+    return r;
+}
+
+// z = r/d + einv[a] * (sum of r over the row's aggregate): the segment sums of this system are
+// taken by all warps of the cluster from the published r (fixed order inside a segment), the
+// per-row combination adds the aggregate's segments in order -> deterministic.
+__device__ __forceinline__ void cluster_segment_sums(const CArgs &a, int sys_index, int crank, int C) {
+    const int lane = threadIdx.x & 31;
+    const int gwarp = crank * (CT >> 5) + (threadIdx.x >> 5);
+    const int s_begin = __ldg(a.agg.sys_seg + 2 * sys_index), s_end = __ldg(a.agg.sys_seg + 2 * sys_index + 1);
+    for (int sg = s_begin + gwarp; sg < s_end; sg += C * (CT >> 5)) {
+        int m0 = __ldg(a.agg.seg_start + sg), n = __ldg(a.agg.seg_count + sg);
+        double acc = 0.0;
+        for (int k = lane; k < n; k += 32) acc += __ldcg(a.rglob + __ldg(a.agg.mem + m0 + k));
+        acc = cnt::warp_sum(acc);
+        if (lane == 0) a.segS[sg] = acc;
+    }
+}
+__device__ __forceinline__ double cluster_coarse_term(const CArgs &a, int64_t v) {
+    int ag = __ldg(a.agg.agg_of_row + v);
+    if (ag < 0) return 0.0;
+    double S = 0.0;
+    int q0 = __ldg(a.agg.agg_seg0 + ag), q1 = __ldg(a.agg.agg_seg0 + ag + 1);
+    for (int q = q0; q < q1; q++) S += __ldcg(a.segS + q);
+    return S * __ldg(a.agg.agg_einv + ag);
+}
+
+template <bool TWO>
+__global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int C = (int)cluster.num_blocks();
+    const int crank = (int)cluster.block_rank();
+    Shared *sh = reinterpret_cast<Shared *>(smem_raw);
+    double *scratch = reinterpret_cast<double *>(smem_raw + sizeof(Shared));   // 4*32 doubles
+    double *gval = scratch + 128;                                               // 256
+    double *p_ext = gval + 256;                                                 // CAP2 + HCAP
+    double *r_s = p_ext + (CAP2 + HCAP);                                        // CAP2
+    uint32_t *ent = reinterpret_cast<uint32_t *>(r_s + CAP2);                   // ECAP
+    int32_t *halo_col = reinterpret_cast<int32_t *>(ent + ECAP);                // HCAP
+    int *iscr = reinterpret_cast<int *>(halo_col + HCAP);                       // 34 (+2 pad)
+    uint16_t *rowoff = reinterpret_cast<uint16_t *>(iscr + 36);                 // CAP2 + 2
+    const int t = threadIdx.x;
+
+    while (true) {
+        if (crank == 0 && t == 0) sh->next = atomicAdd(a.counter, 1);
+        cluster.sync();
+        const int sidx = cluster.map_shared_rank(sh, 0)->next;
+        cluster.sync();
+        if (sidx >= a.nsys) break;
+        const CSys sy = a.sys[sidx];
+        const int chunk = (sy.nrows + C - 1) / C;
+        const int own0 = crank * chunk;
+        const int nown = max(0, min(chunk, sy.nrows - own0));
+        const int64_t vbase = (int64_t)sy.slab * a.R + sy.row0;
+        const uint8_t *cls = a.cls + (int64_t)sy.slab * a.NNZ;
+        const double *diag = a.diag + vbase;
+        const double *rhs = a.rhs + vbase;
+        double *x = a.x + vbase;
+        double *pg = a.pglob + vbase;
+        const int32_t *rowptr = a.rowptr + sy.row0;
+
+        // ---- setup: value table, local CSR offsets, packed entries, halo list
+        if (t == 0) { sh->nhalo = 0; sh->ovf = 0; }
+        if (t < 256) gval[t] = a.gneg[(int64_t)sy.slab * 256 + t];
+        int k0_r[MAXR2], len_r[MAXR2], off_r[MAXR2];
+        int base = 0;
+#pragma unroll
+        for (int k = 0; k < MAXR2; k++) {
+            int li = t + k * CT;
+            int k0 = 0, len = 0;
+            if (li < nown) {
+                k0 = __ldg(rowptr + own0 + li);
+                len = __ldg(rowptr + own0 + li + 1) - k0;
+            }
+            int total;
+            int off = base + block_excl_scan_i(len, iscr, &total);
+            k0_r[k] = k0; len_r[k] = len; off_r[k] = off;
+            if (li < nown && off <= 65535) rowoff[li] = (uint16_t)off;
+            base += total;
+        }
+        const bool fits = base <= ECAP;
+        if (t == 0) rowoff[nown] = (uint16_t)(fits ? base : 0);
+        __syncthreads();
+        if (fits) {
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                for (int j = 0; j < len_r[k]; j++) {
+                    int e = k0_r[k] + j;
+                    int c = __ldg(a.col + e);
+                    unsigned cl = __ldg(cls + e);
+                    unsigned lc = (unsigned)(c - own0);
+                    unsigned slot;
+                    if (lc < (unsigned)nown) {
+                        slot = lc;
+                    } else {
+                        int h = atomicAdd(&sh->nhalo, 1);
+                        if (h < HCAP) {
+                            halo_col[h] = c;
+                            slot = (unsigned)(nown + h);
+                        } else {
+                            slot = 0;
+                            sh->ovf = 1;
+                        }
+                    }
+                    ent[off_r[k] + j] = (slot << 8) | cl;
+                }
+            }
+        }
+        __syncthreads();
+        const int nhalo = min(sh->nhalo, HCAP);
+        const double my_ovf = (!fits || sh->ovf) ? 1.0 : 0.0;
+
+        // ---- r = b - A x0, z = r / d, p = z   (x0 gathered from global memory)
+        double d_r[MAXR2], di_r[MAXR2], qz_r[MAXR2];
+        double acc[4] = {0.0, 0.0, 0.0, my_ovf};    // rz, bb, rr, overflow flag
+#pragma unroll
+        for (int k = 0; k < MAXR2; k++) {
+            int li = t + k * CT;
+            d_r[k] = 1.0; di_r[k] = 1.0; qz_r[k] = 0.0;
+            if (li < nown) {
+                int gi = own0 + li;
+                double di = diag[gi], xi = x[gi], bi = rhs[gi];
+                double ax = di * xi;
+                for (int j = 0; j < len_r[k]; j++) {
+                    int e = k0_r[k] + j;
+                    ax += gval[__ldg(cls + e)] * x[__ldg(a.col + e)];
+                }
+                double ri = bi - ax, dinv = 1.0 / di, zi = ri * dinv;
+                d_r[k] = di; di_r[k] = dinv;
+                r_s[li] = ri;
+                acc[1] += bi * bi;
+                acc[2] += ri * ri;
+                if (TWO) {
+                    a.rglob[vbase + gi] = ri;
+                } else {
+                    p_ext[li] = zi;
+                    pg[gi] = zi;
+                    acc[0] += ri * zi;
+                }
+            }
+        }
+        if (TWO) {
+            cluster.sync();                                     // r published
+            cluster_segment_sums(a, sidx, crank, C);
+            cluster.sync();                                     // segment sums published
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                int li = t + k * CT;
+                if (li < nown) {
+                    int gi = own0 + li;
+                    double ri = r_s[li];
+                    double zi = ri * di_r[k] + cluster_coarse_term(a, vbase + gi);
+                    p_ext[li] = zi;
+                    pg[gi] = zi;
+                    acc[0] += ri * zi;
+                }
+            }
+        }
+        cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // barrier also publishes p
+        double rz = acc[0];
+        const double bb = acc[1];
+        double rr = acc[2];
+        const double tol2 = a.rtol * a.rtol * bb;
+        int it = 0, status = 0;
+        bool done = (sy.nrows == 0) || (rr <= tol2);
+        if (acc[3] > 0.0) { done = true; status = 3; }          // does not fit on chip: caller re-solves
+        if (!done && a.maxit <= 0) { done = true; status = 1; }
+
+        while (!done) {
+            // ---- phase 0: refresh the halo copies of p (written by their owners before the barrier)
+            for (int h = t; h < nhalo; h += CT) p_ext[nown + h] = __ldcg(pg + halo_col[h]);
+            __syncthreads();
+            // ---- phase 1: q = A p from shared memory, pq = p.q
+            double s1[1] = {0.0};
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                int li = t + k * CT;
+                if (li < nown) {
+                    double pi = p_ext[li];
+                    double q = d_r[k] * pi;
+                    int e0 = rowoff[li], e1 = rowoff[li + 1];
+                    for (int e = e0; e < e1; e++) {
+                        unsigned u = ent[e];
+                        q += gval[u & 255u] * p_ext[u >> 8];
+                    }
+                    qz_r[k] = q;
+                    s1[0] += pi * q;
+                }
+            }
+            cluster_sum_n<1>(cluster, sh, 1, s1, scratch, C);
+            const double pq = s1[0];
+            if (!(pq > 0.0)) { status = 2; break; }
+            const double alpha = rz / pq;
+            // ---- phase 2: x += alpha p (global), r -= alpha q, z = r / d
+            double s2[2] = {0.0, 0.0};
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                int li = t + k * CT;
+                if (li < nown) {
+                    x[own0 + li] += alpha * p_ext[li];
+                    double ri = r_s[li] - alpha * qz_r[k];
+                    r_s[li] = ri;
+                    s2[1] += ri * ri;
+                    if (TWO) {
+                        a.rglob[vbase + own0 + li] = ri;
+                    } else {
+                        double zi = ri * di_r[k];
+                        qz_r[k] = zi;
+                        s2[0] += ri * zi;
+                    }
+                }
+            }
+            if (TWO) {
+                cluster.sync();                                 // r published
+                cluster_segment_sums(a, sidx, crank, C);
+                cluster.sync();                                 // segment sums published
+#pragma unroll
+                for (int k = 0; k < MAXR2; k++) {
+                    int li = t + k * CT;
+                    if (li < nown) {
+                        double ri = r_s[li];
+                        double zi = ri * di_r[k] + cluster_coarse_term(a, vbase + own0 + li);
+                        qz_r[k] = zi;
+                        s2[0] += ri * zi;
+                    }
+                }
+            }
+            cluster_sum_n<2>(cluster, sh, 0, s2, scratch, C);
+            const double beta = s2[0] / rz;
+            rz = s2[0];
+            rr = s2[1];
+            it++;
+            if (rr <= tol2) { status = 0; break; }
+            if (it >= a.maxit) { status = 1; break; }
+            if (!(rr == rr)) { status = 2; break; }
+            // ---- phase 3: p = z + beta p, publish for the halo refresh of the other CTAs
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                int li = t + k * CT;
+                if (li < nown) {
+                    double pn = qz_r[k] + beta * p_ext[li];
+                    p_ext[li] = pn;
+                    pg[own0 + li] = pn;
+                }
+            }
+            cluster.sync();
+        }
+        if (crank == 0 && t == 0) {
+            a.iters[sy.out] = it;
+            a.status[sy.out] = status;
+            a.relres[sy.out] = bb > 0 ? sqrt(rr / bb) : 0.0;
+        }
+        cluster.sync();
+    }
+}
+
+constexpr size_t SMEM2_BYTES = sizeof(Shared) + (128 + 256 + (size_t)CAP2 + HCAP + CAP2) * sizeof(double) +
+                               (size_t)ECAP * 4 + (size_t)HCAP * 4 + 36 * 4 + ((size_t)CAP2 + 2) * 2 + 16;
+
 constexpr size_t SMEM_BYTES = sizeof(Shared) + 96 * sizeof(double) + 3 * (size_t)CAP * sizeof(double);
 
-static int pick_cluster(int max_rows) {
+static int pick_cluster(int max_rows, int cap) {
     int c = 1;
-    while (c < MAXC && (int64_t)c * CAP < max_rows) c <<= 1;
+    while (c < MAXC && (int64_t)c * cap < max_rows) c <<= 1;
     return c;
 }
 }  // namespace
 
 extern "C" int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R) {
-    return cnt::ws_bytes_for(NSYS, sizeof(CSys)) + cnt::ws_bytes_for((int64_t)NSLAB * R + 1, 8) + cnt::ws_bytes_for(1, 4);
+    int64_t n = (int64_t)NSLAB * R;
+    return cnt::ws_bytes_for(NSYS, sizeof(CSys)) + 2 * cnt::ws_bytes_for(n + 1, 8) + cnt::ws_bytes_for(1, 4) +
+           cnt::ws_bytes_for(n / 2 + n / 256 + 2, 8);
 }
 
 // largest system (rows) the cluster kernel can take
-extern "C" int64_t cnt_pcg_cluster_max_rows(void) { return (int64_t)MAXC * CAP; }
+extern "C" int64_t cnt_pcg_cluster_max_rows(void) { return (int64_t)MAXC * CAP2; }
 
-static int launch_config(int C, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr, cudaStream_t st, int *nclusters) {
-    CNT_CUDA(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    if (C > 8) CNT_CUDA(cudaFuncSetAttribute(k_pcg_cluster, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+typedef void (*kernel_t)(CArgs);
+static int launch_config(kernel_t kern, size_t smem, int C, cudaLaunchConfig_t *cfg, cudaLaunchAttribute *attr,
+                         cudaStream_t st, int *nclusters) {
+    CNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (C > 8) CNT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)C;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     *cfg = cudaLaunchConfig_t{};
     cfg->blockDim = dim3(CT, 1, 1);
-    cfg->dynamicSmemBytes = SMEM_BYTES;
+    cfg->dynamicSmemBytes = smem;
     cfg->stream = st;
     cfg->attrs = attr;
     cfg->numAttrs = 1;
     cfg->gridDim = dim3((unsigned)C, 1, 1);
-    cudaError_t e = cudaOccupancyMaxActiveClusters(nclusters, k_pcg_cluster, cfg);
+    cudaError_t e = cudaOccupancyMaxActiveClusters(nclusters, kern, cfg);
     if (e != cudaSuccess || *nclusters <= 0) {
         cnt::set_error("cluster size %d not launchable: %s", C, cudaGetErrorString(e));
         cudaGetLastError();
@@ -292,15 +604,17 @@ extern "C" int cnt_pcg_cluster_active(int C) {
     cudaLaunchAttribute attr[1];
     int n = 0;
     if (C < 1 || C > MAXC || (C & (C - 1))) return 0;
-    if (launch_config(C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
+    if (launch_config(k_pcg_cluster2<true>, SMEM2_BYTES, C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
     return n;
 }
 
 extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
                                      const int32_t *h_roff, int64_t R, int64_t NNZ, const int32_t *rowptr,
-                                     const int32_t *col, const double *val, const double *diag, const double *rhs,
+                                     const int32_t *col, const double *val, const uint8_t *cls, const double *gneg,
+                                     const double *diag, const double *rhs,
                                      double *x, double rtol, int maxit, int32_t *iters, double *relres,
-                                     int32_t *status, void *ws, int64_t ws_bytes, void *stream) {
+                                     int32_t *status, const cnt_aggregates *agg, void *ws, int64_t ws_bytes,
+                                     void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && R >= 0 && NNZ >= 0 && iters &&
                   relres && status && ws);
@@ -317,22 +631,27 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
         sys[s].out = s;
         if (sys[s].nrows > max_rows) max_rows = sys[s].nrows;
     }
-    if (max_rows > MAXC * CAP) {
-        cnt::set_error("system with %d rows exceeds the cluster kernel's on-chip capacity (%d)", max_rows, MAXC * CAP);
+    const bool v2 = cls && gneg && !getenv("CNT_CLUSTER_V1");
+    const bool two = v2 && agg && agg->nseg > 0;
+    const int cap = v2 ? CAP2 : CAP;
+    if (max_rows > MAXC * cap) {
+        cnt::set_error("system with %d rows exceeds the cluster kernel's on-chip capacity (%d)", max_rows, MAXC * cap);
         return CNT_ECAPACITY;
     }
     cnt::Workspace w(ws, ws_bytes);
     CSys *d_sys = w.take<CSys>(NSYS);
     double *pglob = w.take<double>((int64_t)NSLAB * R + 1);
+    double *rglob = w.take<double>((int64_t)NSLAB * R + 1);
     int *counter = w.take<int>(1);
-    if (!counter) {
+    double *segS = w.take<double>(two ? agg->nseg : 1);
+    if (!counter || !segS) {
         cnt::set_error("pcg_cluster workspace too small");
         return CNT_ECAPACITY;
     }
     CNT_CUDA(cudaMemcpyAsync(d_sys, sys.data(), sizeof(CSys) * NSYS, cudaMemcpyHostToDevice, st));
     CNT_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
 
-    int C = pick_cluster(max_rows);
+    int C = pick_cluster(max_rows, cap);
     if (const char *e = getenv("CNT_CLUSTER_SIZE")) {
         int c = atoi(e);
         if (c >= C && c <= MAXC && (c & (c - 1)) == 0) C = c;
@@ -340,17 +659,20 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     int nclusters = 0;
-    int rc = launch_config(C, &cfg, attr, st, &nclusters);
+    kernel_t kern = two ? k_pcg_cluster2<true> : (v2 ? k_pcg_cluster2<false> : k_pcg_cluster);
+    int rc = launch_config(kern, v2 ? SMEM2_BYTES : SMEM_BYTES, C, &cfg, attr, st, &nclusters);
     if (rc) return rc;
     if (nclusters > NSYS) nclusters = NSYS;
     cfg.gridDim = dim3((unsigned)(nclusters * C), 1, 1);
 
     CArgs a;
     a.sys = d_sys; a.nsys = NSYS; a.counter = counter; a.R = R; a.NNZ = NNZ;
-    a.rowptr = rowptr; a.col = col; a.val = val; a.diag = diag; a.rhs = rhs;
+    a.rowptr = rowptr; a.col = col; a.val = val; a.diag = diag; a.rhs = rhs; a.cls = cls; a.gneg = gneg;
     a.x = x; a.pglob = pglob; a.rtol = rtol; a.maxit = maxit;
+    a.rglob = rglob; a.segS = segS;
+    if (two) a.agg = *agg; else a.agg = cnt_aggregates{};
     a.iters = iters; a.status = status; a.relres = relres;
-    CNT_CUDA(cudaLaunchKernelEx(&cfg, k_pcg_cluster, a));
+    CNT_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     CNT_LAUNCHED();
     return CNT_OK;
 }

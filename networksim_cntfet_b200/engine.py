@@ -121,6 +121,9 @@ class Engine(object):
         self.profile = bool(profile)
         self._events = []
         self.solver = "auto"           # 'auto' | 'cluster' | 'flat'  (see Engine.solve)
+        self.precond = "twolevel"      # 'twolevel' (Jacobi + aggregate-level Jacobi) | 'jacobi'
+        self.theta = 0.1               # strong-coupling threshold of the aggregates (relative to max |val|)
+        self.cluster_compressed = True  # cluster kernel keeps its matrix slice in shared memory (class codes)
         self.last_solver = None
         self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
 
@@ -350,17 +353,54 @@ class Engine(object):
             val = torch.empty((NS, max(NNZ, 1)), dtype=torch.float64, device=self.device)
             diag = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
             rhs = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
+            # compressed values for the cluster kernel: one class byte per entry + a 256-entry
+            # table of -g per configuration (possible while 9 * nlevels <= 256)
+            use_cls = all(9 * len(gs.levels) <= 256 for gs in gates)
+            cls = torch.empty((NS, max(NNZ, 1)), dtype=torch.uint8, device=self.device) if use_cls else None
+            gneg = np.zeros((NS, 256), dtype=np.float64)
             for q, (gs, tab) in enumerate(zip(gates, gtables)):
                 tab = np.ascontiguousarray(tab, dtype=np.float64)
                 assert tab.shape == (9, len(gs.levels))
                 dtab = self._dev(tab, torch.float64)
+                if use_cls:
+                    gneg[q, :tab.size] = -tab.ravel()
                 check(lib.cnt_assemble_values(J, _p(b.kind2), _p(gs.level), _p(dtab), tab.shape[1], R, _p(b.rowptr),
                                               _p(b.nz_eid), _p(b.src_eid), _p(b.drn_eid), _p(g[q]), _p(val[q]),
-                                              _p(diag[q]), _p(rhs[q]), self.stream_ptr))
-        return dict(g=g, val=val, diag=diag, rhs=rhs)
+                                              _p(diag[q]), _p(rhs[q]), _p(cls[q]) if use_cls else None,
+                                              self.stream_ptr))
+            out = dict(g=g, val=val, diag=diag, rhs=rhs)
+            if use_cls:
+                out.update(cls=cls, gneg=self._dev(np.nan_to_num(gneg, nan=0.0), torch.float64))
+        return out
+
+    def _aggregates(self, b, sysm, sys_net, sys_slab):
+        """tables of the two-level preconditioner (cnt_pcg_aggregates); returns (struct, keepalive)"""
+        lib = self.lib
+        NS = sysm["val"].shape[0]
+        n = NS * b.R
+        nsys = len(sys_net)
+        cap_seg = n // 2 + n // 256 + 2
+        i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
+        t = dict(agg_of_row=i32(n), mem=i32(n), seg_start=i32(cap_seg), seg_count=i32(cap_seg), seg_agg=i32(cap_seg),
+                 seg_sys=i32(cap_seg), agg_seg0=i32(n // 2 + 2), sys_seg=i32(2 * nsys),
+                 agg_einv=torch.empty(n // 2 + 2, dtype=torch.float64, device=self.device))
+        ws = self._ws(lib.cnt_pcg_aggregate_workspace_bytes(nsys, NS, b.R))
+        nagg, nseg = C.c_int64(0), C.c_int64(0)
+        check(lib.cnt_pcg_aggregates(b.B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab), b.c_roff,
+                                     _p(b.roff), b.R, b.NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]),
+                                     float(self.theta), _p(t["agg_of_row"]), _p(t["mem"]), _p(t["seg_start"]),
+                                     _p(t["seg_count"]), _p(t["seg_agg"]), _p(t["seg_sys"]), _p(t["agg_seg0"]),
+                                     _p(t["agg_einv"]), _p(t["sys_seg"]), C.byref(nagg), C.byref(nseg), _p(ws), ws.numel(),
+                                     self.stream_ptr))
+        st = _lib.Aggregates(t["agg_of_row"].data_ptr(), t["mem"].data_ptr(), t["seg_start"].data_ptr(),
+                             t["seg_count"].data_ptr(), t["seg_agg"].data_ptr(), t["seg_sys"].data_ptr(),
+                             t["agg_seg0"].data_ptr(), t["agg_einv"].data_ptr(), t["sys_seg"].data_ptr(),
+                             nagg.value, nseg.value)
+        self.last_aggregates = (nagg.value, nseg.value)
+        return st, t
 
     def solve(self, b, sysm, x0=None, rtol=1e-15, maxit=2000000, check_every=250, nets=None, method=None,
-              slab_priority=None):
+              slab_priority=None, precond=None):
         """Batched Jacobi-PCG (replaces cnet.py:147-149).  sysm: output of assemble_values for
         NS gate configurations.  Every (configuration q, percolating network) pair is one
         system of a single solver call.  method: 'cluster' (persistent thread-block-cluster
@@ -391,6 +431,8 @@ class Engine(object):
                 rr = torch.zeros(nsys, dtype=torch.float64, device=self.device)
                 stt = torch.zeros(nsys, dtype=torch.int32, device=self.device)
                 max_rows = max(b.h_roff[n + 1] - b.h_roff[n] for n in nets)
+                precond = self.precond if precond is None else precond
+                agg = self._aggregates(b, sysm, sys_net, sys_slab) if precond == "twolevel" else None
                 if method == "auto":
                     method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
                 self.last_solver = method
@@ -398,14 +440,21 @@ class Engine(object):
                     ws = self._ws(lib.cnt_pcg_cluster_workspace_bytes(nsys, NS, R))
                     check(lib.cnt_pcg_cluster_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab),
                                                     b.c_roff, R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]),
+                                                    _p(sysm.get("cls")) if self.cluster_compressed else None,
+                                                    _p(sysm.get("gneg")) if self.cluster_compressed else None,
                                                     _p(sysm["diag"]), _p(sysm["rhs"]), _p(x), float(rtol), int(maxit),
-                                                    _p(it), _p(rr), _p(stt), _p(ws), ws.numel(), self.stream_ptr))
+                                                    _p(it), _p(rr), _p(stt),
+                                                    C.byref(agg[0]) if (agg and self.cluster_compressed and
+                                                                        "cls" in sysm) else None,
+                                                    _p(ws), ws.numel(), self.stream_ptr))
+                    self._cluster_fallback(b, sysm, x, sys_net, sys_slab, it, rr, stt, rtol, maxit, check_every)
                 elif method == "flat":
                     ws = self._ws(lib.cnt_pcg_workspace_bytes(nsys, NS, R))
                     check(lib.cnt_pcg_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab), b.c_roff,
                                             R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]),
                                             _p(sysm["rhs"]), _p(x), float(rtol), int(maxit), int(check_every),
-                                            _p(it), _p(rr), _p(stt), _p(ws), ws.numel(), self.stream_ptr))
+                                            _p(it), _p(rr), _p(stt), C.byref(agg[0]) if agg else None,
+                                            _p(ws), ws.numel(), self.stream_ptr))
                 else:
                     raise ValueError("unknown solver %r" % method)
                 idx_q = torch.as_tensor(sys_slab, device=self.device, dtype=torch.long)
@@ -414,6 +463,32 @@ class Engine(object):
                 relres[idx_q, idx_n] = rr
                 status[idx_q, idx_n] = stt
         return dict(x=x, iters=iters, relres=relres, status=status)
+
+    def _cluster_fallback(self, b, sysm, x, sys_net, sys_slab, it, rr, stt, rtol, maxit, check_every):
+        """systems the cluster kernel reported as not fitting on chip (status 3) are re-solved by
+        the multi-launch kernels; costs one small D2H of the status vector"""
+        lib = self.lib
+        st = stt.cpu().numpy()
+        bad = np.flatnonzero(st == 3)
+        if len(bad) == 0:
+            return
+        NS = sysm["val"].shape[0]
+        net2 = [sys_net[k] for k in bad]
+        slab2 = [sys_slab[k] for k in bad]
+        n2 = len(bad)
+        it2 = torch.zeros(n2, dtype=torch.int32, device=self.device)
+        rr2 = torch.zeros(n2, dtype=torch.float64, device=self.device)
+        st2 = torch.zeros(n2, dtype=torch.int32, device=self.device)
+        ws = self._ws(lib.cnt_pcg_workspace_bytes(n2, NS, b.R))
+        check(lib.cnt_pcg_solve(b.B, n2, NS, _lib.i32_array(net2), _lib.i32_array(slab2), b.c_roff, b.R, b.NNZ,
+                                _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]), _p(sysm["rhs"]), _p(x),
+                                float(rtol), int(maxit), int(check_every), _p(it2), _p(rr2), _p(st2), None, _p(ws),
+                                ws.numel(), self.stream_ptr))
+        idx = torch.as_tensor(bad, device=self.device, dtype=torch.long)
+        it[idx] = it2
+        rr[idx] = rr2
+        stt[idx] = st2
+        self.last_solver = "cluster+flat"
 
     # ------------------------------------------------------------------ stage 6: write-back
     def currents(self, b, g, x):
@@ -539,7 +614,7 @@ class Engine(object):
             diag = torch.empty((1, max(R, 1)), dtype=torch.float64, device=self.device)
             rhs = torch.empty((1, max(R, 1)), dtype=torch.float64, device=self.device)
             check(lib.cnt_assemble_values(J, None, None, None, 1, R, _p(b.rowptr), _p(b.nz_eid), _p(b.src_eid),
-                                          _p(b.drn_eid), _p(g[0]), _p(val[0]), _p(diag[0]), _p(rhs[0]),
+                                          _p(b.drn_eid), _p(g[0]), _p(val[0]), _p(diag[0]), _p(rhs[0]), None,
                                           self.stream_ptr))
         sysm = dict(g=g, val=val, diag=diag, rhs=rhs)
         sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every)

@@ -13,9 +13,9 @@ pytestmark = pytest.mark.gpu
 
 @pytest.fixture()
 def solver(engine):
-    old = engine.solver
+    old, oldp = engine.solver, engine.precond
     yield engine
-    engine.solver = old
+    engine.solver, engine.precond = old, oldp
     os.environ.pop("CNT_CLUSTER_SIZE", None)
 
 
@@ -44,6 +44,7 @@ def test_methods_vs_oracle(solver, method):
 
 
 def test_flat_and_cluster_agree(solver):
+    solver.precond = "jacobi"
     g = load_golden("s20_n6400_seed5")
     out = {}
     for method in ("flat", "cluster"):
@@ -130,3 +131,67 @@ def test_z_order_locality(solver):
         assert np.array_equal(b2.row_stick.cpu().numpy()[:b2.R], np.sort(b.row_stick.cpu().numpy()[:b.R]))
     finally:
         solver.spatial_order = True
+
+
+def test_cluster_v1_uncompressed_path(solver):
+    """the uncompressed cluster kernel (values streamed from L2) stays available: it serves
+    caller-supplied conductances (cnet.ConductionNetwork built from a networkx graph)"""
+    solver.solver = "cluster"
+    solver.cluster_compressed = False
+    try:
+        g = load_golden("s20_n6400_seed5")
+        b = solver.batch_from_host([golden_sticks(g)])
+        res = solver.measure_fullnet(b, onoffmap=1)
+        m = _oracle_currents(g, 1)
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            assert abs(res[k][0] - m[k]) <= 1e-9 * m[k]
+    finally:
+        solver.cluster_compressed = True
+
+
+def test_cluster_overflow_falls_back_to_flat(solver):
+    """a dense network (38 junctions per stick) does not fit the CTA's shared-memory slice:
+    the cluster kernel reports status 3 and the engine re-solves with the multi-launch kernels"""
+    solver.solver = "cluster"
+    b = solver.generate([6000], 10.0, seed=9, l=1.0)
+    res = solver.measure_fullnet(b, onoffmap=1)
+    assert solver.last_solver == "cluster+flat"
+    assert res["percolating"][0] and np.all(res["status"] == 0)
+    s = solver.sticks_to_host(b)[0]
+    m = O.measure_fullnet(s, onoffmap=1, refine=3)
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert abs(res[k][0] - m[k]) <= 1e-9 * m[k]
+
+
+@pytest.mark.parametrize("method", ["flat", "cluster"])
+@pytest.mark.parametrize("n,scaling", [(6400, 20.0), (100000, 100.0)])
+def test_two_level_preconditioner(solver, n, scaling, method):
+    """M^-1 = D^-1 + Z diag(Z^T A Z)^-1 Z^T on strong-link aggregates: same answers as plain
+    Jacobi-PCG and as the refined oracle, in far fewer iterations; bit-reproducible"""
+    solver.solver = method
+    out = {}
+    for precond in ("jacobi", "twolevel"):
+        if precond == "jacobi" and n > 50000:
+            continue                                  # 340k iterations: covered by the cluster tests
+        solver.precond = precond
+        b = solver.generate([n], scaling, seed=3)
+        out[precond] = solver.measure_fullnet(b, onoffmap=1)
+        assert np.all(out[precond]["status"] == 0)
+    s = solver.sticks_to_host(b)[0]
+    m = O.measure_fullnet(s, onoffmap=1, refine=3)
+    two = out["twolevel"]
+    assert two["percolating"][0] == m["percolating"]
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert abs(two[k][0] - m[k]) <= 1e-9 * m[k], (k, two[k][0], m[k], two["iters"][:, 0])
+    assert solver.last_aggregates[0] > 0
+    if "jacobi" in out:
+        jac = out["jacobi"]
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            assert abs(two[k][0] - jac[k][0]) <= 1e-9 * jac[k][0]
+        assert two["iters"][1, 0] * 4 < jac["iters"][1, 0]      # back gate: >4x fewer iterations
+    else:
+        assert two["iters"].max() < 12000                       # plain Jacobi: ~200k at Vg=+10
+    again = solver.measure_fullnet(solver.generate([n], scaling, seed=3), onoffmap=1)
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert again[k][0] == two[k][0]
+    assert np.array_equal(again["iters"], two["iters"])

@@ -10,6 +10,7 @@ from networksim_cntfet_b200.elements import LinExpTransistor, conductance_table
 nets = int(os.environ.get("PROBE_NETS", "8")); maxit = int(os.environ.get("PROBE_MAXIT", "2000"))
 n = int(os.environ.get("PROBE_N", "100000")); scaling = float(os.environ.get("PROBE_SCALING", "100"))
 methods = os.environ.get("PROBE_METHODS", "cluster,flat").split(",")
+preconds = os.environ.get("PROBE_PRECOND", "twolevel,jacobi").split(",")
 eng = Engine(profile=True)
 lib = _lib.load()
 print("active clusters:", {c: lib.cnt_pcg_cluster_active(c) for c in (1, 2, 4, 8, 16)}, flush=True)
@@ -20,13 +21,23 @@ tabs = [conductance_table(LinExpTransistor, 1, g.levels) for g in gates]
 sysm = eng.assemble_values(b, gates, tabs)
 rows = np.diff(np.asarray(b.h_roff)); nnz = eng.nnz_per_network(b)
 print("rows", rows.tolist(), "nnz_off", nnz.tolist(), flush=True)
-for method in methods:
+# aggregate setup time
+with eng._work():
+    sys_net = [k for q in range(4) for k in range(nets)]; sys_slab = [q for q in range(4) for k in range(nets)]
     for rep in range(2):
-        eng.stage_times_ms()
-        sol = eng.solve(b, sysm, rtol=1e-30, maxit=maxit, method=method, slab_priority=[0, 3, 2, 1])
-        t = eng.stage_times_ms()["pcg"]
-        it = sol["iters"].cpu().numpy()
-        tot = it.sum()
-        byt = float((it * (12.0 * nnz + 116.0 * rows)[None, :]).sum())
-        print("%-8s rep%d: %.1f ms for %d system-iterations -> %.3f us/system-iteration, %.0f GB/s algorithmic (C=%s)"
-              % (method, rep, t, tot, 1e3 * t / tot, byt / t / 1e6, os.environ.get("CNT_CLUSTER_SIZE", "auto")), flush=True)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        agg = eng._aggregates(b, sysm, sys_net, sys_slab)
+        torch.cuda.synchronize(); print("aggregates setup: %.1f ms, (nagg, nseg) = %s" % (1e3 * (time.perf_counter() - t0), eng.last_aggregates), flush=True)
+for precond in preconds:
+    for method in methods:
+        for rep in range(2):
+            eng.stage_times_ms()
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            sol = eng.solve(b, sysm, rtol=1e-30, maxit=maxit, method=method, slab_priority=[0, 3, 2, 1], precond=precond)
+            torch.cuda.synchronize(); wall = 1e3 * (time.perf_counter() - t0)
+            t = eng.stage_times_ms()["pcg"]
+            it = sol["iters"].cpu().numpy()
+            tot = it.sum()
+            byt = float((it * (12.0 * nnz + 116.0 * rows)[None, :]).sum())
+            print("%-8s %-8s rep%d: %.1f ms (wall %.1f) for %d system-iterations -> %.3f us/system-iteration, %.0f GB/s algorithmic"
+                  % (precond, method, rep, t, wall, tot, 1e3 * t / tot, byt / t / 1e6), flush=True)
