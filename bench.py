@@ -196,7 +196,7 @@ def gpu_arm(args):
         """the path's only collective: all-gather of the per-network statistics rows"""
         if world == 1:
             return rows
-        t = torch.as_tensor(rows, dtype=torch.float64, device=eng.device)
+        t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=eng.device)
         out = [torch.empty_like(t) for _ in range(world)]
         dist.all_gather(out, t)
         return torch.cat(out).cpu().numpy()
@@ -241,7 +241,9 @@ def gpu_arm(args):
     for k in range(args.steps):
         df, io = measure_perc.measure_ensemble(ns, args.scaling, seeds_for(3, k), onoffmap=args.onoffmap,
                                                rtol=args.rtol, return_io=True)
-        gather_rows(df[["ion", "ioff"]].to_numpy(dtype=np.float64))
+        fixed = np.full((3 * B, 2), np.nan)                      # <= 3 rows per network; equal shape on every rank
+        fixed[:len(df)] = df[["ion", "ioff"]].to_numpy(dtype=np.float64)
+        gather_rows(fixed)
         h2d, d2h = io["h2d_bytes"], io["d2h_bytes"]
     barrier()
     e2e_s = time.perf_counter() - t0

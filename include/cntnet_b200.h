@@ -197,7 +197,13 @@ typedef struct cnt_aggregates {
     const int32_t *agg_seg0;     /* [nagg+1] first segment of an aggregate                          */
     const double *agg_einv;      /* [nagg] 1 / (Z^T A Z)_aa                                         */
     const int32_t *sys_seg;      /* [2*NSYS] segments of system s: [sys_seg[2s], sys_seg[2s+1])     */
+    /* cluster solver only (chunk_C > 0): segments never straddle the row chunks of a C-CTA cluster */
+    const int32_t *row_q;        /* [2*NSLAB*R] (first segment, segment count) of the row's aggregate */
+    const double *row_einv;      /* [NSLAB*R] 1/E of the row's aggregate (0 = none)                  */
+    const int32_t *cta_seg_off;  /* [NSYS*chunk_C+1] segments owned by CTA c of system s             */
+    const int32_t *cta_seg;      /* [4*nseg] (segment id, first member, count, 0) in CTA order        */
     int64_t nagg, nseg;
+    int32_t chunk_C, pad;
 } cnt_aggregates;
 int64_t cnt_pcg_aggregate_workspace_bytes(int NSYS, int NSLAB, int64_t R);
 int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
@@ -205,7 +211,10 @@ int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, con
                        const int32_t *rowptr, const int32_t *col, const double *val, const double *diag,
                        double theta, int32_t *agg_of_row, int32_t *mem, int32_t *seg_start,
                        int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
-                       double *agg_einv, int32_t *sys_seg /* [2*NSYS] */, int64_t *h_nagg, int64_t *h_nseg,
+                       double *agg_einv, int32_t *sys_seg /* [2*NSYS] */,
+                       int chunk_C /* cluster size the tables are built for (cnt_pcg_cluster_size), 0 = flat only */,
+                       int32_t *row_q, double *row_einv, int32_t *cta_seg_off, int32_t *cta_seg,
+                       int64_t *h_nagg, int64_t *h_nseg,
                        void *ws, int64_t ws_bytes, void *stream);
 
 int64_t cnt_pcg_workspace_bytes(int NSYS, int NSLAB, int64_t R);
@@ -228,6 +237,8 @@ int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const in
  * iteration touches global memory only for the halo exchange of p; a system whose slice or
  * halo does not fit gets status 3 and must be re-solved with cnt_pcg_solve. */
 int64_t cnt_pcg_cluster_max_rows(void);
+/* cluster size (CTAs) the cluster solver uses for a batch whose largest system has max_rows rows */
+int cnt_pcg_cluster_size(int64_t max_rows);
 /* clusters of C CTAs (C = 1,2,4,8,16) that can be resident at once on the current device */
 int cnt_pcg_cluster_active(int C);
 int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R);

@@ -137,6 +137,26 @@ __global__ void k_seg_E(int64_t nseg, const int32_t *__restrict__ seg_start, con
     if (lane == 0) segE[s] = acc;
 }
 
+// per aggregated row: (first segment, number of segments) of its aggregate and 1/E -- the
+// coarse term then needs one coalesced load + the segment sums instead of a 4-deep chain
+__global__ void k_row_tables(int64_t nseg, const int32_t *__restrict__ seg_start, const int32_t *__restrict__ seg_count,
+                             const int32_t *__restrict__ seg_agg, const uint32_t *__restrict__ mem,
+                             const int32_t *__restrict__ agg_seg0, const double *__restrict__ einv,
+                             int32_t *__restrict__ row_q, double *__restrict__ row_einv) {
+    int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (s >= nseg) return;
+    int lane = threadIdx.x & 31;
+    int s0 = seg_start[s], n = seg_count[s], a = seg_agg[s];
+    int q0 = agg_seg0[a], qn = agg_seg0[a + 1] - q0;
+    double e = einv[a];
+    for (int k = lane; k < n; k += 32) {
+        int64_t v = mem[s0 + k];
+        row_q[2 * v] = q0;
+        row_q[2 * v + 1] = qn;
+        row_einv[v] = e;
+    }
+}
+
 __global__ void k_agg_einv(int64_t nagg, const int32_t *__restrict__ agg_seg0, const double *__restrict__ segE,
                            double *__restrict__ einv) {
     int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -166,7 +186,8 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
                                   const int32_t *rowptr, const int32_t *col, const double *val, const double *diag,
                                   double theta, int32_t *agg_of_row, int32_t *mem, int32_t *seg_start,
                                   int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
-                                  double *agg_einv, int32_t *sys_seg,
+                                  double *agg_einv, int32_t *sys_seg, int chunk_C, int32_t *row_q, double *row_einv,
+                                  int32_t *cta_seg_off, int32_t *cta_seg,
                                   int64_t *h_nagg, int64_t *h_nseg, void *ws, int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && roff && R >= 0 && h_nagg &&
@@ -177,7 +198,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
     if (n == 0) return CNT_OK;
     CNT_CHECK_ARG(n < ((int64_t)1 << 31));
     CNT_CHECK_ARG(rowptr && diag && agg_of_row && mem && seg_start && seg_count && seg_agg && seg_sys && agg_seg0 &&
-                  agg_einv && sys_seg);
+                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (row_q && row_einv && cta_seg_off && cta_seg)));
     // systems sorted by (slab, network) are the sort segments; tiles for the row kernels
     std::vector<ASys> sys(NSYS);
     std::vector<ATile> tiles;
@@ -253,9 +274,11 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
     // members in aggregate order -> caller's `mem`; sorted roots -> host
     CNT_CUDA(cudaMemcpyAsync(mem, vs, 4 * n, cudaMemcpyDeviceToDevice, st));
     std::vector<unsigned long long> roots(n);
+    std::vector<uint32_t> members(chunk_C > 0 ? n : 0);
     CNT_CUDA(cudaMemcpyAsync(roots.data(), ks, 8 * n, cudaMemcpyDeviceToHost, st));
+    if (chunk_C > 0) CNT_CUDA(cudaMemcpyAsync(members.data(), vs, 4 * n, cudaMemcpyDeviceToHost, st));
     CNT_CUDA(cudaStreamSynchronize(st));
-    std::vector<int32_t> h_seg_start, h_seg_count, h_seg_agg, h_seg_sys, h_agg_seg0;
+    std::vector<int32_t> h_seg_start, h_seg_count, h_seg_agg, h_seg_sys, h_seg_cta, h_agg_seg0;
     // position -> system: `order` holds the systems sorted by first position
     auto sys_of = [&](int64_t pos) {
         int lo = 0, hi = NSYS - 1;
@@ -273,11 +296,21 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
             int a = (int)h_agg_seg0.size();
             int sidx = sys_of((int64_t)roots[i]);
             h_agg_seg0.push_back((int32_t)h_seg_start.size());
-            for (int64_t p0 = i; p0 < j; p0 += SEGW) {
+            // segments: <= SEGW members, and (cluster solver) never across a CTA chunk boundary
+            const ASys &sy = sys[sidx];
+            const int64_t vb0 = (int64_t)sy.slab * R + sy.net_row0;
+            const int chunk = chunk_C > 0 ? (sy.nrows + chunk_C - 1) / chunk_C : 0;
+            int64_t p0 = i;
+            while (p0 < j) {
+                int64_t p1 = p0 + 1;
+                int cta = chunk ? (int)((members[p0] - vb0) / chunk) : 0;
+                while (p1 < j && p1 - p0 < SEGW && (!chunk || (int)((members[p1] - vb0) / chunk) == cta)) p1++;
                 h_seg_start.push_back((int32_t)p0);
-                h_seg_count.push_back((int32_t)((j - p0) < SEGW ? (j - p0) : SEGW));
+                h_seg_count.push_back((int32_t)(p1 - p0));
                 h_seg_agg.push_back(a);
                 h_seg_sys.push_back(sidx);
+                h_seg_cta.push_back(cta);
+                p0 = p1;
             }
         }
         i = j;
@@ -310,6 +343,31 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         CNT_LAUNCHED();
         k_agg_einv<<<cnt::grid_for(nagg, 256), 256, 0, st>>>(nagg, agg_seg0, segE, agg_einv);
         CNT_LAUNCHED();
+    }
+    std::vector<int32_t> h_cta_off, h_cta_seg;
+    if (chunk_C > 0) {
+        // per (system, CTA): its segments as (segment id, first member, count, 0) quadruples
+        CNT_CUDA(cudaMemsetAsync(row_q, 0, 8 * n, st));
+        CNT_CUDA(cudaMemsetAsync(row_einv, 0, 8 * n, st));
+        h_cta_off.assign((size_t)NSYS * chunk_C + 1, 0);
+        for (int64_t q = 0; q < nseg; q++) h_cta_off[(size_t)h_seg_sys[q] * chunk_C + h_seg_cta[q] + 1]++;
+        for (size_t k = 1; k < h_cta_off.size(); k++) h_cta_off[k] += h_cta_off[k - 1];
+        std::vector<int32_t> cur(h_cta_off.begin(), h_cta_off.end() - 1);
+        h_cta_seg.assign(4 * (size_t)(nseg > 0 ? nseg : 1), 0);
+        for (int64_t q = 0; q < nseg; q++) {
+            int32_t pos = cur[(size_t)h_seg_sys[q] * chunk_C + h_seg_cta[q]]++;
+            h_cta_seg[4 * (size_t)pos + 0] = (int32_t)q;
+            h_cta_seg[4 * (size_t)pos + 1] = h_seg_start[q];
+            h_cta_seg[4 * (size_t)pos + 2] = h_seg_count[q];
+        }
+        CNT_CUDA(cudaMemcpyAsync(cta_seg_off, h_cta_off.data(), 4 * h_cta_off.size(), cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(cta_seg, h_cta_seg.data(), 4 * h_cta_seg.size(), cudaMemcpyHostToDevice, st));
+        if (nseg > 0) {
+            k_row_tables<<<cnt::grid_for(nseg * 32, 256), 256, 0, st>>>(nseg, seg_start, seg_count, seg_agg,
+                                                                        (const uint32_t *)mem, agg_seg0, agg_einv,
+                                                                        row_q, row_einv);
+            CNT_LAUNCHED();
+        }
     }
     // host vectors must outlive the async uploads
     CNT_CUDA(cudaStreamSynchronize(st));

@@ -298,28 +298,30 @@ __device__ __forceinline__ int block_excl_scan_i(int v, int *sm /*34 ints*/, int
     return r;
 }
 
-// z = r/d + einv[a] * (sum of r over the row's aggregate): the segment sums of this system are
-// taken by all warps of the cluster from the published r (fixed order inside a segment), the
-// per-row combination adds the aggregate's segments in order -> deterministic.
-__device__ __forceinline__ void cluster_segment_sums(const CArgs &a, int sys_index, int crank, int C) {
-    const int lane = threadIdx.x & 31;
-    const int gwarp = crank * (CT >> 5) + (threadIdx.x >> 5);
-    const int s_begin = __ldg(a.agg.sys_seg + 2 * sys_index), s_end = __ldg(a.agg.sys_seg + 2 * sys_index + 1);
-    for (int sg = s_begin + gwarp; sg < s_end; sg += C * (CT >> 5)) {
-        int m0 = __ldg(a.agg.seg_start + sg), n = __ldg(a.agg.seg_count + sg);
+// z = r/d + einv[a] * (sum of r over the row's aggregate).  The aggregate tables are built for
+// this cluster size: a segment never straddles two CTAs' row chunks, so every CTA sums ITS
+// segments straight from its shared-memory copy of r (fixed order inside a segment); after one
+// cluster barrier each row adds the segments of its aggregate in order -> deterministic.
+__device__ __forceinline__ void local_segment_sums(const CArgs &a, int sys_index, int crank, int C, int64_t row_base,
+                                                   const double *r_s) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int q0 = __ldg(a.agg.cta_seg_off + sys_index * C + crank);
+    const int q1 = __ldg(a.agg.cta_seg_off + sys_index * C + crank + 1);
+    const int4 *list = reinterpret_cast<const int4 *>(a.agg.cta_seg);
+    for (int q = q0 + w; q < q1; q += (CT >> 5)) {
+        int4 sg = __ldg(list + q);                  // (segment id, first member, count, -)
         double acc = 0.0;
-        for (int k = lane; k < n; k += 32) acc += __ldcg(a.rglob + __ldg(a.agg.mem + m0 + k));
+        for (int k = lane; k < sg.z; k += 32) acc += r_s[(int64_t)__ldg(a.agg.mem + sg.y + k) - row_base];
         acc = cnt::warp_sum(acc);
-        if (lane == 0) a.segS[sg] = acc;
+        if (lane == 0) a.segS[sg.x] = acc;
     }
 }
 __device__ __forceinline__ double cluster_coarse_term(const CArgs &a, int64_t v) {
-    int ag = __ldg(a.agg.agg_of_row + v);
-    if (ag < 0) return 0.0;
+    int2 rq = __ldg(reinterpret_cast<const int2 *>(a.agg.row_q) + v);
+    if (rq.y == 0) return 0.0;
     double S = 0.0;
-    int q0 = __ldg(a.agg.agg_seg0 + ag), q1 = __ldg(a.agg.agg_seg0 + ag + 1);
-    for (int q = q0; q < q1; q++) S += __ldcg(a.segS + q);
-    return S * __ldg(a.agg.agg_einv + ag);
+    for (int q = 0; q < rq.y; q++) S += __ldcg(a.segS + rq.x + q);
+    return S * __ldg(a.agg.row_einv + v);
 }
 
 template <bool TWO>
@@ -428,9 +430,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 r_s[li] = ri;
                 acc[1] += bi * bi;
                 acc[2] += ri * ri;
-                if (TWO) {
-                    a.rglob[vbase + gi] = ri;
-                } else {
+                if (!TWO) {
                     p_ext[li] = zi;
                     pg[gi] = zi;
                     acc[0] += ri * zi;
@@ -438,8 +438,8 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             }
         }
         if (TWO) {
-            cluster.sync();                                     // r published
-            cluster_segment_sums(a, sidx, crank, C);
+            __syncthreads();                                    // r_s complete in this CTA
+            local_segment_sums(a, sidx, crank, C, vbase + own0, r_s);
             cluster.sync();                                     // segment sums published
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
@@ -499,9 +499,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     double ri = r_s[li] - alpha * qz_r[k];
                     r_s[li] = ri;
                     s2[1] += ri * ri;
-                    if (TWO) {
-                        a.rglob[vbase + own0 + li] = ri;
-                    } else {
+                    if (!TWO) {
                         double zi = ri * di_r[k];
                         qz_r[k] = zi;
                         s2[0] += ri * zi;
@@ -509,8 +507,8 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 }
             }
             if (TWO) {
-                cluster.sync();                                 // r published
-                cluster_segment_sums(a, sidx, crank, C);
+                __syncthreads();                                // r_s complete in this CTA
+                local_segment_sums(a, sidx, crank, C, vbase + own0, r_s);
                 cluster.sync();                                 // segment sums published
 #pragma unroll
                 for (int k = 0; k < MAXR2; k++) {
@@ -598,6 +596,17 @@ static int launch_config(kernel_t kern, size_t smem, int C, cudaLaunchConfig_t *
     return CNT_OK;
 }
 
+static int cluster_size_for(int64_t max_rows, int cap) {
+    int C = pick_cluster((int)max_rows, cap);
+    if (const char *e = getenv("CNT_CLUSTER_SIZE")) {
+        int c = atoi(e);
+        if (c >= C && c <= MAXC && (c & (c - 1)) == 0) C = c;
+    }
+    return C;
+}
+// cluster size used for a batch whose largest system has max_rows rows (compressed kernel)
+extern "C" int cnt_pcg_cluster_size(int64_t max_rows) { return cluster_size_for(max_rows, CAP2); }
+
 // number of clusters of C CTAs that can be resident at once on the current device (0 on error)
 extern "C" int cnt_pcg_cluster_active(int C) {
     cudaLaunchConfig_t cfg;
@@ -651,10 +660,10 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     CNT_CUDA(cudaMemcpyAsync(d_sys, sys.data(), sizeof(CSys) * NSYS, cudaMemcpyHostToDevice, st));
     CNT_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
 
-    int C = pick_cluster(max_rows, cap);
-    if (const char *e = getenv("CNT_CLUSTER_SIZE")) {
-        int c = atoi(e);
-        if (c >= C && c <= MAXC && (c & (c - 1)) == 0) C = c;
+    int C = cluster_size_for(max_rows, cap);
+    if (two && agg->chunk_C != C) {
+        cnt::set_error("aggregate tables were built for cluster size %d, the batch needs %d", agg->chunk_C, C);
+        return CNT_EINVAL;
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];

@@ -373,7 +373,7 @@ class Engine(object):
                 out.update(cls=cls, gneg=self._dev(np.nan_to_num(gneg, nan=0.0), torch.float64))
         return out
 
-    def _aggregates(self, b, sysm, sys_net, sys_slab):
+    def _aggregates(self, b, sysm, sys_net, sys_slab, chunk_C=0):
         """tables of the two-level preconditioner (cnt_pcg_aggregates); returns (struct, keepalive)"""
         lib = self.lib
         NS = sysm["val"].shape[0]
@@ -383,6 +383,9 @@ class Engine(object):
         i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
         t = dict(agg_of_row=i32(n), mem=i32(n), seg_start=i32(cap_seg), seg_count=i32(cap_seg), seg_agg=i32(cap_seg),
                  seg_sys=i32(cap_seg), agg_seg0=i32(n // 2 + 2), sys_seg=i32(2 * nsys),
+                 row_q=i32(2 * n if chunk_C else 1), cta_seg_off=i32(nsys * chunk_C + 1),
+                 cta_seg=i32(4 * (cap_seg + nsys * chunk_C) if chunk_C else 1),
+                 row_einv=torch.empty(n if chunk_C else 1, dtype=torch.float64, device=self.device),
                  agg_einv=torch.empty(n // 2 + 2, dtype=torch.float64, device=self.device))
         ws = self._ws(lib.cnt_pcg_aggregate_workspace_bytes(nsys, NS, b.R))
         nagg, nseg = C.c_int64(0), C.c_int64(0)
@@ -390,12 +393,15 @@ class Engine(object):
                                      _p(b.roff), b.R, b.NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]), _p(sysm["diag"]),
                                      float(self.theta), _p(t["agg_of_row"]), _p(t["mem"]), _p(t["seg_start"]),
                                      _p(t["seg_count"]), _p(t["seg_agg"]), _p(t["seg_sys"]), _p(t["agg_seg0"]),
-                                     _p(t["agg_einv"]), _p(t["sys_seg"]), C.byref(nagg), C.byref(nseg), _p(ws), ws.numel(),
+                                     _p(t["agg_einv"]), _p(t["sys_seg"]), int(chunk_C), _p(t["row_q"]), _p(t["row_einv"]),
+                                     _p(t["cta_seg_off"]), _p(t["cta_seg"]), C.byref(nagg), C.byref(nseg), _p(ws),
+                                     ws.numel(),
                                      self.stream_ptr))
         st = _lib.Aggregates(t["agg_of_row"].data_ptr(), t["mem"].data_ptr(), t["seg_start"].data_ptr(),
                              t["seg_count"].data_ptr(), t["seg_agg"].data_ptr(), t["seg_sys"].data_ptr(),
                              t["agg_seg0"].data_ptr(), t["agg_einv"].data_ptr(), t["sys_seg"].data_ptr(),
-                             nagg.value, nseg.value)
+                             t["row_q"].data_ptr(), t["row_einv"].data_ptr(), t["cta_seg_off"].data_ptr(),
+                             t["cta_seg"].data_ptr(), nagg.value, nseg.value, int(chunk_C), 0)
         self.last_aggregates = (nagg.value, nseg.value)
         return st, t
 
@@ -432,9 +438,11 @@ class Engine(object):
                 stt = torch.zeros(nsys, dtype=torch.int32, device=self.device)
                 max_rows = max(b.h_roff[n + 1] - b.h_roff[n] for n in nets)
                 precond = self.precond if precond is None else precond
-                agg = self._aggregates(b, sysm, sys_net, sys_slab) if precond == "twolevel" else None
                 if method == "auto":
                     method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
+                compressed = method == "cluster" and self.cluster_compressed and "cls" in sysm
+                chunk_C = lib.cnt_pcg_cluster_size(max_rows) if compressed else 0
+                agg = self._aggregates(b, sysm, sys_net, sys_slab, chunk_C) if precond == "twolevel" else None
                 self.last_solver = method
                 if method == "cluster":
                     ws = self._ws(lib.cnt_pcg_cluster_workspace_bytes(nsys, NS, R))

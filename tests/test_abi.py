@@ -52,3 +52,34 @@ def test_no_cpu_fallback_without_gpu():
         pytest.skip("GPU present")
     with pytest.raises(_lib.CntError):
         Engine()
+
+
+def header_param_counts():
+    txt = open(os.path.join(ROOT, "include", "cntnet_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    out = {}
+    for m in re.finditer(r"\b(cnt_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", txt, flags=re.S):
+        args = m.group(2).strip()
+        out[m.group(1)] = 0 if args in ("", "void") else len(args.split(","))
+    return out
+
+
+def test_prototype_arity_matches_header():
+    """every ctypes prototype has exactly as many arguments as the C declaration"""
+    from networksim_cntfet_b200 import _lib
+    counts = header_param_counts()
+    bad = {n: (len(a), counts.get(n)) for n, (_, a) in _lib.PROTOTYPES.items() if counts.get(n) != len(a)}
+    assert not bad, bad
+
+
+def test_aggregates_struct_matches_header():
+    from networksim_cntfet_b200 import _lib
+    txt = open(os.path.join(ROOT, "include", "cntnet_b200.h")).read()
+    body = re.search(r"typedef struct cnt_aggregates \{(.*?)\} cnt_aggregates;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip().replace("const ", "")
+        if decl:
+            names += [n.strip().lstrip("*").strip() for n in decl.split(" ", 1)[1].split(",")]
+    assert names == [f[0] for f in _lib.Aggregates._fields_], (names, [f[0] for f in _lib.Aggregates._fields_])
