@@ -282,6 +282,7 @@ def gpu_arm(args):
                     "algorithmic_bytes": nbytes, "pcg_iterations": iters, "pcg_seconds": pcg_s,
                     "bytes_per_iteration": "12*nnz_offdiag + 116*rows per system"}
         jt = stages.get("junctions", 0.0) / 1e3
+        fp64_peak = eng.fp64_peak_tflops()
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": dev_ms / max(args.steps, 1), "higher_is_better": True,
@@ -291,6 +292,12 @@ def gpu_arm(args):
             "gpu_launches": int(cnt.item()), "clocks": clocks,
             "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
             "junction_tests_per_s": (ntests / jt) if jt > 0 else None, "junction_tests": ntests,
+            "junction_roofline": {"bound": "fp64", "unit": "TFLOP/s", "flops_per_test": 17,
+                                  "achieved": (17.0 * ntests / jt / 1e12) if jt > 0 else None,
+                                  "peak": fp64_peak, "peak_source": "measured DFMA probe (cnt_fp64_peak)",
+                                  "frac": (17.0 * ntests / jt / 1e12 / fp64_peak) if jt > 0 and fp64_peak else None,
+                                  "note": "whole junction stage (binning + count + scan + fill); 4 of the 17 flops are "
+                                          "IEEE divisions (~30 instructions each)"},
             "wall_ms_per_step": wall_ms / max(args.steps, 1),
             "percolating_fraction": float(np.mean([r["percolating"].mean() for r in results])),
             "pcg_iters_mean_per_solve": [float(np.mean([r["iters"][q].mean() for r in results])) for q in range(4)],

@@ -52,6 +52,10 @@ int64_t cnt_scan_workspace_bytes(int64_t n);
 int cnt_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n, int write_total,
                            void *ws, int64_t ws_bytes, void *stream);
 
+/* FP64 FMA peak of the device (TFLOP/s, best of `reps` launches of a register-resident DFMA
+ * kernel): roofline denominator of the junction kernel.  scratch: >= 606208 doubles.  Synchronises. */
+int cnt_fp64_peak(double *scratch, int reps, double *h_tflops, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * (1) stick placement -- replaces make_stick / get_ends / make_sticks (netsim.py:97-125)
  *     and the length sort of make_intersects_kdtree (netsim.py:132-134).
@@ -202,6 +206,9 @@ typedef struct cnt_aggregates {
     const double *row_einv;      /* [NSLAB*R] 1/E of the row's aggregate (0 = none)                  */
     const int32_t *cta_seg_off;  /* [NSYS*chunk_C+1] segments owned by CTA c of system s             */
     const int32_t *cta_seg;      /* [4*nseg] (segment id, first member, count, 0) in CTA order        */
+    const int32_t *cta_agg_off;  /* [NSYS*chunk_C+1] aggregates touched by CTA c of system s          */
+    const int32_t *cta_agg;      /* aggregate ids in CTA order (<= nseg entries)                      */
+    const int32_t *row_slot;     /* [NSLAB*R] slot of the row's aggregate in its CTA's list, -1 none  */
     int64_t nagg, nseg;
     int32_t chunk_C, pad;
 } cnt_aggregates;
@@ -214,6 +221,7 @@ int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, con
                        double *agg_einv, int32_t *sys_seg /* [2*NSYS] */,
                        int chunk_C /* cluster size the tables are built for (cnt_pcg_cluster_size), 0 = flat only */,
                        int32_t *row_q, double *row_einv, int32_t *cta_seg_off, int32_t *cta_seg,
+                       int32_t *cta_agg_off, int32_t *cta_agg /* capacity of seg_* */, int32_t *row_slot,
                        int64_t *h_nagg, int64_t *h_nseg,
                        void *ws, int64_t ws_bytes, void *stream);
 
@@ -237,6 +245,9 @@ int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const in
  * iteration touches global memory only for the halo exchange of p; a system whose slice or
  * halo does not fit gets status 3 and must be re-solved with cnt_pcg_solve. */
 int64_t cnt_pcg_cluster_max_rows(void);
+/* debug: device buffer [grid][16] of int64 that receives per-phase cycle sums (thread 0 of every CTA) of the
+ * following cluster launches; NULL switches the instrumentation off (default) */
+void cnt_pcg_cluster_set_phase_buffer(long long *buf);
 /* cluster size (CTAs) the cluster solver uses for a batch whose largest system has max_rows rows */
 int cnt_pcg_cluster_size(int64_t max_rows);
 /* clusters of C CTAs (C = 1,2,4,8,16) that can be resident at once on the current device */

@@ -20,6 +20,7 @@ PROTOTYPES = {
     "cnt_abi_version": (i32, []),
     "cnt_last_error": (C.c_char_p, []),
     "cnt_launch_count": (i64, []),
+    "cnt_fp64_peak": (i32, [vp, i32, C.POINTER(f64), vp]),
     "cnt_scan_workspace_bytes": (i64, [i64]),
     "cnt_exclusive_scan_i32": (i32, [vp, vp, i64, i32, vp, i64, vp]),
     "cnt_gen_sticks_workspace_bytes": (i64, [i64, i32]),
@@ -41,10 +42,11 @@ PROTOTYPES = {
     "cnt_assemble_values": (i32, [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cnt_pcg_aggregate_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_aggregates": (i32, [i32, i32, i32, I32P, I32P, I32P, vp, i64, i64, vp, vp, vp, vp, f64] + [vp] * 9 +
-                           [i32, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
+                           [i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
     "cnt_pcg_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_pcg_cluster_max_rows": (i64, []),
+    "cnt_pcg_cluster_set_phase_buffer": (None, [vp]),
     "cnt_pcg_cluster_active": (i32, [i32]),
     "cnt_pcg_cluster_size": (i32, [i64]),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
@@ -60,7 +62,8 @@ class Aggregates(C.Structure):
     """mirror of `struct cnt_aggregates` (include/cntnet_b200.h)"""
     _fields_ = [("agg_of_row", vp), ("mem", vp), ("seg_start", vp), ("seg_count", vp), ("seg_agg", vp),
                 ("seg_sys", vp), ("agg_seg0", vp), ("agg_einv", vp), ("sys_seg", vp), ("row_q", vp), ("row_einv", vp),
-                ("cta_seg_off", vp), ("cta_seg", vp), ("nagg", i64), ("nseg", i64), ("chunk_C", C.c_int32),
+                ("cta_seg_off", vp), ("cta_seg", vp), ("cta_agg_off", vp), ("cta_agg", vp), ("row_slot", vp),
+                ("nagg", i64), ("nseg", i64), ("chunk_C", C.c_int32),
                 ("pad", C.c_int32)]
 
 

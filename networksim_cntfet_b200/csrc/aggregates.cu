@@ -187,7 +187,8 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
                                   double theta, int32_t *agg_of_row, int32_t *mem, int32_t *seg_start,
                                   int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
                                   double *agg_einv, int32_t *sys_seg, int chunk_C, int32_t *row_q, double *row_einv,
-                                  int32_t *cta_seg_off, int32_t *cta_seg,
+                                  int32_t *cta_seg_off, int32_t *cta_seg, int32_t *cta_agg_off, int32_t *cta_agg,
+                                  int32_t *row_slot,
                                   int64_t *h_nagg, int64_t *h_nseg, void *ws, int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && roff && R >= 0 && h_nagg &&
@@ -198,7 +199,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
     if (n == 0) return CNT_OK;
     CNT_CHECK_ARG(n < ((int64_t)1 << 31));
     CNT_CHECK_ARG(rowptr && diag && agg_of_row && mem && seg_start && seg_count && seg_agg && seg_sys && agg_seg0 &&
-                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (row_q && row_einv && cta_seg_off && cta_seg)));
+                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (row_q && row_einv && cta_seg_off && cta_seg && cta_agg_off && cta_agg && row_slot)));
     // systems sorted by (slab, network) are the sort segments; tiles for the row kernels
     std::vector<ASys> sys(NSYS);
     std::vector<ATile> tiles;
@@ -344,7 +345,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         k_agg_einv<<<cnt::grid_for(nagg, 256), 256, 0, st>>>(nagg, agg_seg0, segE, agg_einv);
         CNT_LAUNCHED();
     }
-    std::vector<int32_t> h_cta_off, h_cta_seg;
+    std::vector<int32_t> h_cta_off, h_cta_seg, h_cta_agg_off, h_cta_agg, h_row_slot;
     if (chunk_C > 0) {
         // per (system, CTA): its segments as (segment id, first member, count, 0) quadruples
         CNT_CUDA(cudaMemsetAsync(row_q, 0, 8 * n, st));
@@ -360,6 +361,29 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
             h_cta_seg[4 * (size_t)pos + 1] = h_seg_start[q];
             h_cta_seg[4 * (size_t)pos + 2] = h_seg_count[q];
         }
+        // per (system, CTA): the aggregates it touches (dedup of its segments' aggregates, which are
+        // adjacent because segment ids are contiguous per aggregate) and, per row, the slot of its
+        // aggregate in that CTA-local list
+        h_cta_agg_off.assign((size_t)NSYS * chunk_C + 1, 0);
+        h_row_slot.assign((size_t)n, -1);
+        for (size_t c = 0; c + 1 < h_cta_off.size(); c++) {
+            int prev = -1, nloc = 0;
+            for (int32_t q = h_cta_off[c]; q < h_cta_off[c + 1]; q++) {
+                int sg = h_cta_seg[4 * (size_t)q];
+                int ag = h_seg_agg[sg];
+                if (ag != prev) {
+                    h_cta_agg.push_back(ag);
+                    prev = ag;
+                    nloc++;
+                }
+                for (int k = 0; k < h_seg_count[sg]; k++) h_row_slot[members[h_seg_start[sg] + k]] = nloc - 1;
+            }
+            h_cta_agg_off[c + 1] = (int32_t)h_cta_agg.size();
+        }
+        if (h_cta_agg.empty()) h_cta_agg.push_back(0);
+        CNT_CUDA(cudaMemcpyAsync(cta_agg_off, h_cta_agg_off.data(), 4 * h_cta_agg_off.size(), cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(cta_agg, h_cta_agg.data(), 4 * h_cta_agg.size(), cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(row_slot, h_row_slot.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_seg_off, h_cta_off.data(), 4 * h_cta_off.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_seg, h_cta_seg.data(), 4 * h_cta_seg.size(), cudaMemcpyHostToDevice, st));
         if (nseg > 0) {

@@ -48,6 +48,9 @@ struct CArgs {
     cnt_aggregates agg;
     double *rglob;           // [NSLAB*R] r published once per iteration for the segment sums
     double *segS;            // [nseg]
+    long long *dbg;          // [gridDim.x][16] per-phase cycle sums (NULL = off)
+    int *assert_flag;        // first failed in-kernel bounds check (0 = none)
+    int dbg_stage;           // debug bisecting: 1 = stop after setup, 2 = stop after the initial residual
     double rtol;
     int maxit;
     int32_t *iters, *status;
@@ -62,7 +65,22 @@ struct Shared {
     int nhalo;             // v2: halo references collected by this CTA
     int ovf;               // v2: slice / halo did not fit
     int pad;
+    long long tlast;       // phase timing (debug): last timestamp, per-phase cycle sums
+    long long tacc[16];
 };
+// phase timing: thread 0 of every CTA accumulates clock64() deltas per phase when a debug
+// buffer is given (tools/pcg_probe.py); costs one predictable branch otherwise
+// cheap in-kernel bounds assertions (compute-sanitizer is not available on the target pool):
+// the first failing check id is recorded and the access is skipped
+#define KCHECK(id, cond) ((cond) ? true : (atomicCAS(a.assert_flag, 0, (id)), false))
+#define PHASE(i)                                                   \
+    do {                                                           \
+        if (a.dbg && threadIdx.x == 0) {                           \
+            long long c_ = clock64();                              \
+            sh->tacc[i] += c_ - sh->tlast;                         \
+            sh->tlast = c_;                                        \
+        }                                                          \
+    } while (0)
 
 // deterministic block sums of up to 3 values at once; results valid in thread 0
 template <int N>
@@ -319,9 +337,49 @@ __device__ __forceinline__ void local_segment_sums(const CArgs &a, int sys_index
 __device__ __forceinline__ double cluster_coarse_term(const CArgs &a, int64_t v) {
     int2 rq = __ldg(reinterpret_cast<const int2 *>(a.agg.row_q) + v);
     if (rq.y == 0) return 0.0;
-    double S = 0.0;
-    for (int q = 0; q < rq.y; q++) S += __ldcg(a.segS + rq.x + q);
+    double S = __ldcg(a.segS + rq.x);                       // most aggregates have one segment
+    for (int q = 1; q < rq.y; q++) S += __ldcg(a.segS + rq.x + q);
     return S * __ldg(a.agg.row_einv + v);
+}
+
+constexpr int SORTN = 8192;             // power of two >= CAP2 (bitonic sort of the CTA's rows)
+constexpr int LCAP = 512;               // two-level: local segments / local aggregates per CTA
+constexpr int MCAP = CAP2;              // two-level: aggregated rows per CTA (all of them may be aggregated)
+
+// two-level phases from shared memory: one warp per local segment sums its members of r in a
+// fixed order; after the cluster barrier one thread per local aggregate combines the aggregate's
+// segment sums (its own and other CTAs', in segment order) into the coarse value
+__device__ __forceinline__ void smem_segment_sums(double *segS, const double *r_s, const uint16_t *segm,
+                                                  const uint16_t *segoff, const int32_t *segid, int nseg_loc,
+                                                  int *flag, int64_t nseg_glob) {
+    const int lane = threadIdx.x & 31;
+    for (int sgi = threadIdx.x >> 5; sgi < nseg_loc; sgi += (CT >> 5)) {
+        int o0 = segoff[sgi], o1 = segoff[sgi + 1];
+        double acc = 0.0;
+        for (int q = o0 + lane; q < o1; q += 32) {
+            unsigned m = segm[q < MCAP ? q : 0];
+            if (m < (unsigned)CAP2 && q < MCAP) acc += r_s[m]; else atomicCAS(flag, 0, 11);
+        }
+        acc = cnt::warp_sum(acc);
+        if (lane == 0) {
+            if (segid[sgi] >= 0 && segid[sgi] < nseg_glob) segS[segid[sgi]] = acc; else atomicCAS(flag, 0, 12);
+        }
+    }
+}
+__device__ __forceinline__ void smem_coarse_values(const double *segS, const int32_t *la_q0, const uint16_t *la_qn,
+                                                   const float *la_einv, double *c_loc, int nla, int *flag,
+                                                   int64_t nseg_glob) {
+    for (int i = threadIdx.x; i < nla; i += CT) {
+        int q0 = la_q0[i], qn = la_qn[i];
+        double S = 0.0;
+        if (q0 >= 0 && q0 + qn <= nseg_glob) {
+            S = __ldcg(segS + q0);
+            for (int q = 1; q < qn; q++) S += __ldcg(segS + q0 + q);
+        } else {
+            atomicCAS(flag, 0, 13);
+        }
+        c_loc[i] = S * (double)la_einv[i];
+    }
 }
 
 template <bool TWO>
@@ -335,11 +393,24 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     double *gval = scratch + 128;                                               // 256
     double *p_ext = gval + 256;                                                 // CAP2 + HCAP
     double *r_s = p_ext + (CAP2 + HCAP);                                        // CAP2
-    uint32_t *ent = reinterpret_cast<uint32_t *>(r_s + CAP2);                   // ECAP
+    uint32_t *ent = reinterpret_cast<uint32_t *>(r_s + CAP2);                   // ECAP (sort keys during setup)
     int32_t *halo_col = reinterpret_cast<int32_t *>(ent + ECAP);                // HCAP
-    int *iscr = reinterpret_cast<int *>(halo_col + HCAP);                       // 34 (+2 pad)
-    uint16_t *rowoff = reinterpret_cast<uint16_t *>(iscr + 36);                 // CAP2 + 2
-    const int t = threadIdx.x;
+    int *iscr = reinterpret_cast<int *>(halo_col + HCAP);                       // 36
+    int *gbase = iscr + 36;                                                     // CAP2 / 32
+    uint16_t *slot_s = reinterpret_cast<uint16_t *>(gbase + CAP2 / 32);         // CAP2: row -> local aggregate
+    // two-level tables of this CTA (shared memory only in the iteration)
+    double *c_loc = reinterpret_cast<double *>(slot_s + CAP2);                  // LCAP coarse values
+    int32_t *segid = reinterpret_cast<int32_t *>(c_loc + LCAP);                 // LCAP global segment ids
+    int32_t *la_q0 = segid + LCAP;                                              // LCAP first segment of aggregate
+    float *la_einv = reinterpret_cast<float *>(la_q0 + LCAP);                   // LCAP 1/E (FP32 is plenty for M)
+    uint16_t *la_qn = reinterpret_cast<uint16_t *>(la_einv + LCAP);             // LCAP segments of aggregate
+    uint16_t *segoff = la_qn + LCAP;                                            // LCAP + 2
+    uint16_t *segm = segoff + LCAP + 2;                                         // MCAP member rows (local index)
+    const int t = threadIdx.x, lane = t & 31;
+    if (t == 0) {
+        for (int i = 0; i < 16; i++) sh->tacc[i] = 0;
+        sh->tlast = clock64();
+    }
 
     while (true) {
         if (crank == 0 && t == 0) sh->next = atomicAdd(a.counter, 1);
@@ -353,56 +424,149 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         const int nown = max(0, min(chunk, sy.nrows - own0));
         const int64_t vbase = (int64_t)sy.slab * a.R + sy.row0;
         const uint8_t *cls = a.cls + (int64_t)sy.slab * a.NNZ;
-        const double *diag = a.diag + vbase;
-        const double *rhs = a.rhs + vbase;
-        double *x = a.x + vbase;
+        const double *diag = a.diag + vbase + own0;
+        const double *rhs = a.rhs + vbase + own0;
+        double *x = a.x + vbase;                   // network-local index (gathers of x0 use columns)
         double *pg = a.pglob + vbase;
-        const int32_t *rowptr = a.rowptr + sy.row0;
+        const int32_t *rowptr = a.rowptr + sy.row0 + own0;
 
-        // ---- setup: value table, local CSR offsets, packed entries, halo list
+        // ================= setup (once per system) =================
+        PHASE(0);                                               // queue / idle
         if (t == 0) { sh->nhalo = 0; sh->ovf = 0; }
         if (t < 256) gval[t] = a.gneg[(int64_t)sy.slab * 256 + t];
-        int k0_r[MAXR2], len_r[MAXR2], off_r[MAXR2];
+        // (1) sort the CTA's rows by length, longest first, ties by row index: every warp then
+        //     works on 32 rows of (almost) equal length -> no divergence in the SpMV loop
+        for (int i = t; i < SORTN; i += CT) {
+            unsigned key = 0;                                   // padding sorts last
+            if (i < nown) {
+                unsigned len = (unsigned)(__ldg(rowptr + i + 1) - __ldg(rowptr + i));
+                key = (len << 13) | (unsigned)(8191 - i);
+            }
+            ent[i] = 0xFFFFFFFFu - key;
+        }
+        __syncthreads();
+        for (int k = 2; k <= SORTN; k <<= 1) {
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = t; i < SORTN; i += CT) {
+                    int ixj = i ^ j;
+                    if (ixj > i) {
+                        unsigned va = ent[i], vb = ent[ixj];
+                        bool up = (i & k) == 0;
+                        if ((va > vb) == up) { ent[i] = vb; ent[ixj] = va; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // (2) per slot: row, length; group bases of the warp-interleaved entry layout
+        // "snake" assignment of the sorted rows to (thread, slot): odd slots run backwards so that
+        // every warp gets a similar total row length
+        int meta_r[MAXR2];                                      // li | len << 16   (-1: inactive slot)
         int base = 0;
+        bool bad = false;
 #pragma unroll
         for (int k = 0; k < MAXR2; k++) {
-            int li = t + k * CT;
-            int k0 = 0, len = 0;
-            if (li < nown) {
-                k0 = __ldg(rowptr + own0 + li);
-                len = __ldg(rowptr + own0 + li + 1) - k0;
+            int p = k * CT + ((k & 1) ? (CT - 1 - t) : t);
+            int len = 0;
+            meta_r[k] = -1;
+            if (p < nown) {
+                unsigned key = 0xFFFFFFFFu - ent[p];
+                len = (int)(key >> 13);
+                int li = 8191 - (int)(key & 8191u);
+                if (len > 255) { bad = true; len = 255; }
+                meta_r[k] = li | (len << 16);
             }
             int total;
-            int off = base + block_excl_scan_i(len, iscr, &total);
-            k0_r[k] = k0; len_r[k] = len; off_r[k] = off;
-            if (li < nown && off <= 65535) rowoff[li] = (uint16_t)off;
+            // group = 32 consecutive positions; its longest row is the one with the smallest position
+            const bool leader = (p & 31) == 0;
+            int off = base + block_excl_scan_i(leader ? 32 * len : 0, iscr, &total);
+            if (leader) gbase[p >> 5] = off;
             base += total;
         }
+        if (bad) sh->ovf = 1;
         const bool fits = base <= ECAP;
-        if (t == 0) rowoff[nown] = (uint16_t)(fits ? base : 0);
-        __syncthreads();
+        __syncthreads();                                        // sort keys consumed, gbase visible
+        // (3) packed entries: (slot << 8) | class at gbase + j*32 + lane
         if (fits) {
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
-                for (int j = 0; j < len_r[k]; j++) {
-                    int e = k0_r[k] + j;
-                    int c = __ldg(a.col + e);
-                    unsigned cl = __ldg(cls + e);
-                    unsigned lc = (unsigned)(c - own0);
-                    unsigned slot;
-                    if (lc < (unsigned)nown) {
-                        slot = lc;
-                    } else {
-                        int h = atomicAdd(&sh->nhalo, 1);
-                        if (h < HCAP) {
-                            halo_col[h] = c;
-                            slot = (unsigned)(nown + h);
+                if (meta_r[k] >= 0) {
+                    int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
+                    int k0 = __ldg(rowptr + li);
+                    const int p = k * CT + ((k & 1) ? (CT - 1 - t) : t);
+                    unsigned *dst = ent + gbase[p >> 5] + (p & 31);
+                    for (int j = 0; j < len; j++) {
+                        int c = __ldg(a.col + k0 + j);
+                        unsigned cl = __ldg(cls + k0 + j);
+                        unsigned lc = (unsigned)(c - own0);
+                        unsigned slot;
+                        if (lc < (unsigned)nown) {
+                            slot = lc;
                         } else {
-                            slot = 0;
-                            sh->ovf = 1;
+                            int h = atomicAdd(&sh->nhalo, 1);
+                            if (h < HCAP) {
+                                halo_col[h] = c;
+                                slot = (unsigned)(nown + h);
+                            } else {
+                                slot = 0;
+                                sh->ovf = 1;
+                            }
                         }
+                        if (KCHECK(4, (dst - ent) + j * 32 < ECAP)) dst[j * 32] = (slot << 8) | cl;
                     }
-                    ent[off_r[k] + j] = (slot << 8) | cl;
+                }
+            }
+        }
+        int nseg_loc = 0, nla = 0;
+        if (TWO) {
+            // (4) this CTA's segments (member lists as local row indices) and aggregates
+            const int cidx = sidx * C + crank;
+            const int sq0 = __ldg(a.agg.cta_seg_off + cidx), la0 = __ldg(a.agg.cta_agg_off + cidx);
+            nseg_loc = __ldg(a.agg.cta_seg_off + cidx + 1) - sq0;
+            nla = __ldg(a.agg.cta_agg_off + cidx + 1) - la0;
+            const int4 *list = reinterpret_cast<const int4 *>(a.agg.cta_seg) + sq0;
+            const bool cap_ok = nseg_loc <= LCAP && nla <= LCAP;
+            int4 sg = make_int4(0, 0, 0, 0);
+            if (cap_ok && t < nseg_loc) sg = __ldg(list + t);
+            int total;
+            int off = block_excl_scan_i(sg.z, iscr, &total);
+            const bool tw_ok = cap_ok && total <= MCAP;
+            if (!tw_ok) {
+                // tables do not fit: the system gets status 3 once the cluster has agreed on it; until
+                // then the phases below must see consistent (empty) tables
+                if (t == 0) sh->ovf = 1;
+                nseg_loc = 0;
+                nla = 0;
+                for (int i = t; i < nown; i += CT) slot_s[i] = (uint16_t)0xFFFF;
+            } else {
+                if (t < nseg_loc) {
+                    KCHECK(7, sg.x >= 0 && sg.x < a.agg.nseg && sg.y >= 0 && sg.z > 0 && sg.z <= 256);
+                    segoff[t] = (uint16_t)off;
+                    segid[t] = sg.x;
+                }
+                if (t == 0) segoff[nseg_loc] = (uint16_t)total;
+                for (int i = t; i < nla; i += CT) {
+                    int aid = __ldg(a.agg.cta_agg + la0 + i);
+                    KCHECK(5, aid >= 0 && aid < a.agg.nagg);
+                    int q0 = __ldg(a.agg.agg_seg0 + aid);
+                    KCHECK(6, q0 >= 0 && q0 < a.agg.nseg);
+                    la_q0[i] = q0;
+                    la_qn[i] = (uint16_t)(__ldg(a.agg.agg_seg0 + aid + 1) - q0);
+                    la_einv[i] = (float)__ldg(a.agg.agg_einv + aid);
+                }
+                for (int i = t; i < nown; i += CT) {
+                    int sl = __ldg(a.agg.row_slot + vbase + own0 + i);
+                    KCHECK(3, sl < nla);
+                    slot_s[i] = (sl < 0 || sl >= nla) ? (uint16_t)0xFFFF : (uint16_t)sl;
+                }
+            }
+            __syncthreads();
+            for (int sgi = (t >> 5); sgi < nseg_loc; sgi += (CT >> 5)) {
+                int4 g4 = __ldg(list + sgi);
+                int o = segoff[sgi];
+                for (int q = lane; q < g4.z; q += 32) {
+                    int64_t loc = (int64_t)__ldg(a.agg.mem + g4.y + q) - (vbase + own0);
+                    if (KCHECK(1, o + q < MCAP)) segm[o + q] = KCHECK(2, loc >= 0 && loc < nown) ? (uint16_t)loc : (uint16_t)0;
                 }
             }
         }
@@ -410,50 +574,57 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         const int nhalo = min(sh->nhalo, HCAP);
         const double my_ovf = (!fits || sh->ovf) ? 1.0 : 0.0;
 
-        // ---- r = b - A x0, z = r / d, p = z   (x0 gathered from global memory)
+        if (a.dbg_stage == 1) {            // bisecting aid: setup only
+            cluster.sync();
+            continue;
+        }
+        // ================= r = b - A x0, z = M^-1 r, p = z =================
         double d_r[MAXR2], di_r[MAXR2], qz_r[MAXR2];
         double acc[4] = {0.0, 0.0, 0.0, my_ovf};    // rz, bb, rr, overflow flag
+        bool done_dbg = false;
 #pragma unroll
         for (int k = 0; k < MAXR2; k++) {
-            int li = t + k * CT;
             d_r[k] = 1.0; di_r[k] = 1.0; qz_r[k] = 0.0;
-            if (li < nown) {
-                int gi = own0 + li;
-                double di = diag[gi], xi = x[gi], bi = rhs[gi];
+            if (meta_r[k] >= 0) {
+                int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
+                double di = diag[li], xi = x[own0 + li], bi = rhs[li];
                 double ax = di * xi;
-                for (int j = 0; j < len_r[k]; j++) {
-                    int e = k0_r[k] + j;
-                    ax += gval[__ldg(cls + e)] * x[__ldg(a.col + e)];
-                }
-                double ri = bi - ax, dinv = 1.0 / di, zi = ri * dinv;
+                int k0 = __ldg(rowptr + li);
+                for (int j = 0; j < len; j++) ax += gval[__ldg(cls + k0 + j)] * x[__ldg(a.col + k0 + j)];
+                double ri = bi - ax, dinv = 1.0 / di;
                 d_r[k] = di; di_r[k] = dinv;
                 r_s[li] = ri;
                 acc[1] += bi * bi;
                 acc[2] += ri * ri;
                 if (!TWO) {
+                    double zi = ri * dinv;
                     p_ext[li] = zi;
-                    pg[gi] = zi;
                     acc[0] += ri * zi;
                 }
             }
         }
         if (TWO) {
             __syncthreads();                                    // r_s complete in this CTA
-            local_segment_sums(a, sidx, crank, C, vbase + own0, r_s);
+            if (a.dbg_stage != 3) smem_segment_sums(a.segS, r_s, segm, segoff, segid, nseg_loc, a.assert_flag, a.agg.nseg);
             cluster.sync();                                     // segment sums published
+            if (a.dbg_stage != 4 && a.dbg_stage != 3)
+                smem_coarse_values(a.segS, la_q0, la_qn, la_einv, c_loc, nla, a.assert_flag, a.agg.nseg);
+            __syncthreads();
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
-                int li = t + k * CT;
-                if (li < nown) {
-                    int gi = own0 + li;
+                if (meta_r[k] >= 0) {
+                    int li = meta_r[k] & 0xFFFF;
                     double ri = r_s[li];
-                    double zi = ri * di_r[k] + cluster_coarse_term(a, vbase + gi);
+                    unsigned sl = slot_s[li];
+                    double zi = ri * di_r[k] + ((sl != 0xFFFFu && a.dbg_stage < 3) ? c_loc[sl] : 0.0);
                     p_ext[li] = zi;
-                    pg[gi] = zi;
                     acc[0] += ri * zi;
                 }
             }
+            if (a.dbg_stage >= 3) done_dbg = true;
         }
+        __syncthreads();
+        for (int i = t; i < nown; i += CT) pg[own0 + i] = p_ext[i];      // coalesced publication of p
         cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // barrier also publishes p
         double rz = acc[0];
         const double bb = acc[1];
@@ -463,39 +634,59 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         bool done = (sy.nrows == 0) || (rr <= tol2);
         if (acc[3] > 0.0) { done = true; status = 3; }          // does not fit on chip: caller re-solves
         if (!done && a.maxit <= 0) { done = true; status = 1; }
+        if (a.dbg_stage == 2 || done_dbg) done = true;
+        PHASE(1);                                               // setup + initial residual
 
         while (!done) {
             // ---- phase 0: refresh the halo copies of p (written by their owners before the barrier)
-            for (int h = t; h < nhalo; h += CT) p_ext[nown + h] = __ldcg(pg + halo_col[h]);
+            for (int h = t; h < nhalo; h += CT) {
+                int hc = halo_col[h];
+                if (KCHECK(21, hc >= 0 && hc < sy.nrows && nown + h < CAP2 + HCAP)) p_ext[nown + h] = __ldcg(pg + hc);
+            }
             __syncthreads();
+            PHASE(2);                                           // halo refresh
             // ---- phase 1: q = A p from shared memory, pq = p.q
             double s1[1] = {0.0};
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
-                int li = t + k * CT;
-                if (li < nown) {
+                if (meta_r[k] >= 0) {
+                    int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
                     double pi = p_ext[li];
                     double q = d_r[k] * pi;
-                    int e0 = rowoff[li], e1 = rowoff[li + 1];
-                    for (int e = e0; e < e1; e++) {
-                        unsigned u = ent[e];
+                    const int p = k * CT + ((k & 1) ? (CT - 1 - t) : t);
+                    const unsigned *e = ent + gbase[p >> 5] + (p & 31);
+                    for (int j = 0; j < len; j++) {
+                        unsigned u = e[j * 32];
                         q += gval[u & 255u] * p_ext[u >> 8];
                     }
+                    KCHECK(20, (e - ent) + (len - 1) * 32 < ECAP || len == 0);
                     qz_r[k] = q;
                     s1[0] += pi * q;
                 }
             }
+            PHASE(3);                                           // SpMV (thread 0's warp)
+            double xv[MAXR2];                                   // x loads fly during the reduction
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                int i = t + k * CT;
+                xv[k] = i < nown ? __ldcg(x + own0 + i) : 0.0;
+            }
             cluster_sum_n<1>(cluster, sh, 1, s1, scratch, C);
+            PHASE(4);                                           // reduction 1 incl. waiting for the cluster
             const double pq = s1[0];
             if (!(pq > 0.0)) { status = 2; break; }
             const double alpha = rz / pq;
-            // ---- phase 2: x += alpha p (global), r -= alpha q, z = r / d
+            // ---- phase 2: x += alpha p (coalesced, any thread/row pairing), r -= alpha q
+#pragma unroll
+            for (int k = 0; k < MAXR2; k++) {
+                int i = t + k * CT;
+                if (i < nown) x[own0 + i] = xv[k] + alpha * p_ext[i];
+            }
             double s2[2] = {0.0, 0.0};
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
-                int li = t + k * CT;
-                if (li < nown) {
-                    x[own0 + li] += alpha * p_ext[li];
+                if (meta_r[k] >= 0) {
+                    int li = meta_r[k] & 0xFFFF;
                     double ri = r_s[li] - alpha * qz_r[k];
                     r_s[li] = ri;
                     s2[1] += ri * ri;
@@ -506,22 +697,30 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     }
                 }
             }
+            PHASE(5);                                           // x, r update
             if (TWO) {
                 __syncthreads();                                // r_s complete in this CTA
-                local_segment_sums(a, sidx, crank, C, vbase + own0, r_s);
+                smem_segment_sums(a.segS, r_s, segm, segoff, segid, nseg_loc, a.assert_flag, a.agg.nseg);
+                PHASE(6);                                       // segment sums
                 cluster.sync();                                 // segment sums published
+                PHASE(7);                                       // barrier
+                smem_coarse_values(a.segS, la_q0, la_qn, la_einv, c_loc, nla, a.assert_flag, a.agg.nseg);
+                __syncthreads();
 #pragma unroll
                 for (int k = 0; k < MAXR2; k++) {
-                    int li = t + k * CT;
-                    if (li < nown) {
+                    if (meta_r[k] >= 0) {
+                        int li = meta_r[k] & 0xFFFF;
                         double ri = r_s[li];
-                        double zi = ri * di_r[k] + cluster_coarse_term(a, vbase + own0 + li);
+                        unsigned sl = slot_s[li];
+                        double zi = ri * di_r[k] + (sl != 0xFFFFu ? c_loc[sl] : 0.0);
                         qz_r[k] = zi;
                         s2[0] += ri * zi;
                     }
                 }
+                PHASE(8);                                       // coarse term + z
             }
             cluster_sum_n<2>(cluster, sh, 0, s2, scratch, C);
+            PHASE(9);                                           // reduction 2
             const double beta = s2[0] / rz;
             rz = s2[0];
             rr = s2[1];
@@ -529,17 +728,19 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             if (rr <= tol2) { status = 0; break; }
             if (it >= a.maxit) { status = 1; break; }
             if (!(rr == rr)) { status = 2; break; }
-            // ---- phase 3: p = z + beta p, publish for the halo refresh of the other CTAs
+            // ---- phase 3: p = z + beta p, then publish it (coalesced) for the other CTAs' halos
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
-                int li = t + k * CT;
-                if (li < nown) {
-                    double pn = qz_r[k] + beta * p_ext[li];
-                    p_ext[li] = pn;
-                    pg[own0 + li] = pn;
+                if (meta_r[k] >= 0) {
+                    int li = meta_r[k] & 0xFFFF;
+                    p_ext[li] = qz_r[k] + beta * p_ext[li];
                 }
             }
+            __syncthreads();
+            for (int i = t; i < nown; i += CT) pg[own0 + i] = p_ext[i];
+            PHASE(10);                                          // p update + publish
             cluster.sync();
+            PHASE(11);                                          // barrier
         }
         if (crank == 0 && t == 0) {
             a.iters[sy.out] = it;
@@ -548,10 +749,14 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         }
         cluster.sync();
     }
+    if (a.dbg && t == 0)
+        for (int i = 0; i < 16; i++) a.dbg[(int64_t)blockIdx.x * 16 + i] = sh->tacc[i];
 }
 
 constexpr size_t SMEM2_BYTES = sizeof(Shared) + (128 + 256 + (size_t)CAP2 + HCAP + CAP2) * sizeof(double) +
-                               (size_t)ECAP * 4 + (size_t)HCAP * 4 + 36 * 4 + ((size_t)CAP2 + 2) * 2 + 16;
+                               (size_t)ECAP * 4 + (size_t)HCAP * 4 + (36 + CAP2 / 32) * 4 + (size_t)CAP2 * 2 +
+                               (size_t)LCAP * (8 + 4 + 4 + 4 + 2) + ((size_t)LCAP + 2) * 2 + (size_t)MCAP * 2 + 16;
+static_assert(SMEM2_BYTES <= 232448, "cluster kernel exceeds the 227 KB shared-memory limit");
 
 constexpr size_t SMEM_BYTES = sizeof(Shared) + 96 * sizeof(double) + 3 * (size_t)CAP * sizeof(double);
 
@@ -564,9 +769,13 @@ static int pick_cluster(int max_rows, int cap) {
 
 extern "C" int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R) {
     int64_t n = (int64_t)NSLAB * R;
-    return cnt::ws_bytes_for(NSYS, sizeof(CSys)) + 2 * cnt::ws_bytes_for(n + 1, 8) + cnt::ws_bytes_for(1, 4) +
+    return cnt::ws_bytes_for(NSYS, sizeof(CSys)) + 2 * cnt::ws_bytes_for(n + 1, 8) + 2 * cnt::ws_bytes_for(1, 4) +
            cnt::ws_bytes_for(n / 2 + n / 256 + 2, 8);
 }
+
+// debug: device buffer [grid][16] receiving per-phase cycle sums of the next launches (NULL = off)
+static long long *g_phase_dbg = nullptr;
+extern "C" void cnt_pcg_cluster_set_phase_buffer(long long *buf) { g_phase_dbg = buf; }
 
 // largest system (rows) the cluster kernel can take
 extern "C" int64_t cnt_pcg_cluster_max_rows(void) { return (int64_t)MAXC * CAP2; }
@@ -652,6 +861,7 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     double *pglob = w.take<double>((int64_t)NSLAB * R + 1);
     double *rglob = w.take<double>((int64_t)NSLAB * R + 1);
     int *counter = w.take<int>(1);
+    int *assert_flag = w.take<int>(1);
     double *segS = w.take<double>(two ? agg->nseg : 1);
     if (!counter || !segS) {
         cnt::set_error("pcg_cluster workspace too small");
@@ -659,6 +869,7 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     }
     CNT_CUDA(cudaMemcpyAsync(d_sys, sys.data(), sizeof(CSys) * NSYS, cudaMemcpyHostToDevice, st));
     CNT_CUDA(cudaMemsetAsync(counter, 0, sizeof(int), st));
+    CNT_CUDA(cudaMemsetAsync(assert_flag, 0, sizeof(int), st));
 
     int C = cluster_size_for(max_rows, cap);
     if (two && agg->chunk_C != C) {
@@ -679,9 +890,21 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     a.rowptr = rowptr; a.col = col; a.val = val; a.diag = diag; a.rhs = rhs; a.cls = cls; a.gneg = gneg;
     a.x = x; a.pglob = pglob; a.rtol = rtol; a.maxit = maxit;
     a.rglob = rglob; a.segS = segS;
+    a.dbg = g_phase_dbg;
+    a.assert_flag = assert_flag;
+    a.dbg_stage = getenv("CNT_DBG_STAGE") ? atoi(getenv("CNT_DBG_STAGE")) : 0;
     if (two) a.agg = *agg; else a.agg = cnt_aggregates{};
     a.iters = iters; a.status = status; a.relres = relres;
     CNT_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
     CNT_LAUNCHED();
+    if (getenv("CNT_CLUSTER_ASSERT")) {       // debugging aid: synchronise and report in-kernel bounds checks
+        int h = 0;
+        cudaError_t e = cudaMemcpyAsync(&h, assert_flag, sizeof(int), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess || h != 0) {
+            cnt::set_error("cluster kernel: %s, in-kernel check %d failed", cudaGetErrorString(e), h);
+            return CNT_ECUDA;
+        }
+    }
     return CNT_OK;
 }

@@ -141,3 +141,45 @@ extern "C" int cnt_exclusive_scan_i32(const int32_t *in, int32_t *out, int64_t n
     CNT_LAUNCHED();
     return CNT_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// FP64 FMA peak probe: the junction kernel's roofline denominator (MEASURED_PEAKS.json has no
+// FP64 figure).  Every thread runs 8 independent DFMA chains; returns through *tflops the
+// best of `reps` timed launches.  Synchronises.
+// ---------------------------------------------------------------------------------------
+namespace {
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6,
+           x7 = x0 + 7;
+    for (int i = 0; i < iters; i++) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+extern "C" int cnt_fp64_peak(double *scratch /* >= 148*16*256 doubles */, int reps, double *h_tflops, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(scratch && h_tflops && reps > 0);
+    const int blocks = 148 * 16, iters = 20000;
+    cudaEvent_t e0, e1;
+    CNT_CUDA(cudaEventCreate(&e0));
+    CNT_CUDA(cudaEventCreate(&e1));
+    double best = 0.0;
+    for (int r = 0; r < reps + 1; r++) {
+        CNT_CUDA(cudaEventRecord(e0, st));
+        k_fp64_peak<<<blocks, 256, 0, st>>>(scratch, iters, 0.999999, 1e-9);
+        CNT_LAUNCHED();
+        CNT_CUDA(cudaEventRecord(e1, st));
+        CNT_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CNT_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8 * (double)iters * blocks * 256 / (ms * 1e-3) / 1e12;
+        if (r > 0 && tf > best) best = tf;     // first launch is warm-up
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *h_tflops = best;
+    return CNT_OK;
+}

@@ -3,6 +3,7 @@
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
+from ctypes import c_void_p as C_void_p
 from networksim_cntfet_b200 import _lib
 from networksim_cntfet_b200.engine import Engine
 from networksim_cntfet_b200.elements import LinExpTransistor, conductance_table
@@ -41,3 +42,21 @@ for precond in preconds:
             byt = float((it * (12.0 * nnz + 116.0 * rows)[None, :]).sum())
             print("%-8s %-8s rep%d: %.1f ms (wall %.1f) for %d system-iterations -> %.3f us/system-iteration, %.0f GB/s algorithmic"
                   % (precond, method, rep, t, wall, tot, 1e3 * t / tot, byt / t / 1e6), flush=True)
+
+# ---- per-phase cycle breakdown of the cluster kernel (thread 0 of every CTA)
+if "cluster" in methods:
+    names = ["idle/queue", "setup+init", "halo refresh", "SpMV", "reduce1(+wait)", "x,r update", "segment sums",
+             "barrier(seg)", "coarse+z", "reduce2(+wait)", "p update+publish", "barrier(p)"]
+    dbg = torch.zeros(148 * 16, dtype=torch.int64, device=eng.device)
+    lib.cnt_pcg_cluster_set_phase_buffer(C_void_p(dbg.data_ptr()))
+    sol = eng.solve(b, sysm, rtol=1e-30, maxit=maxit, method="cluster", slab_priority=[0, 3, 2, 1], precond=preconds[0])
+    torch.cuda.synchronize()
+    lib.cnt_pcg_cluster_set_phase_buffer(None)
+    d = dbg.cpu().numpy().reshape(148, 16)
+    d = d[d.sum(1) > 0]
+    its = sol["iters"].cpu().numpy().sum() / max(len(d) // 16, 1)   # iterations per cluster (approx)
+    print("phase breakdown (%s), %d CTAs, ~%.0f iterations per cluster; cycles per iteration: mean / max over CTAs"
+          % (preconds[0], len(d), its))
+    for i, nm in enumerate(names):
+        print("  %-18s %8.0f %8.0f" % (nm, d[:, i].mean() / its, d[:, i].max() / its))
+    print("  %-18s %8.0f" % ("total", d.sum(1).mean() / its))
