@@ -178,6 +178,7 @@ def gpu_arm(args):
     from networksim_cntfet_b200.engine import Engine, network_seeds
     eng = Engine("cuda:%d" % local, profile=True)
     eng.solver = args.solver
+    eng.initial_guess = args.guess
     measure_perc.set_engine(eng)
     lib = _lib.load()
     B = args.batch
@@ -324,7 +325,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=8, help="networks per GPU per step")
+    ap.add_argument("--batch", type=int, default=14,
+                    help="networks per GPU per step (14 x 4 solves = 8 full rounds of the 7 resident clusters)")
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--scaling", type=int, default=100)
     ap.add_argument("--onoffmap", type=int, default=1)
@@ -332,6 +334,7 @@ def main():
     ap.add_argument("--check-every", type=int, default=250)
     ap.add_argument("--solver", default="auto", choices=["auto", "cluster", "flat"])
     ap.add_argument("--seed", type=int, default=2024)
+    ap.add_argument("--guess", default="zero", choices=["linear", "zero"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="networks in the CPU sample (default: one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -349,22 +349,32 @@ constexpr int MCAP = CAP2;              // two-level: aggregated rows per CTA (a
 // two-level phases from shared memory: one warp per local segment sums its members of r in a
 // fixed order; after the cluster barrier one thread per local aggregate combines the aggregate's
 // segment sums (its own and other CTAs', in segment order) into the coarse value
+constexpr int SEG_SMALL = 8;     // segments up to this size are summed by one thread, larger ones by a warp
 __device__ __forceinline__ void smem_segment_sums(double *segS, const double *r_s, const uint16_t *segm,
                                                   const uint16_t *segoff, const int32_t *segid, int nseg_loc,
                                                   int *flag, int64_t nseg_glob) {
+    // small segments: one thread each, members added in list order
+    for (int sgi = threadIdx.x; sgi < nseg_loc; sgi += CT) {
+        int o0 = segoff[sgi], o1 = segoff[sgi + 1];
+        if (o1 - o0 <= SEG_SMALL) {
+            double acc = 0.0;
+            for (int q = o0; q < o1; q++) acc += r_s[segm[q]];
+            segS[segid[sgi]] = acc;
+        }
+    }
+    // large segments: one warp each, lane-strided partial sums + fixed shuffle tree
     const int lane = threadIdx.x & 31;
     for (int sgi = threadIdx.x >> 5; sgi < nseg_loc; sgi += (CT >> 5)) {
         int o0 = segoff[sgi], o1 = segoff[sgi + 1];
-        double acc = 0.0;
-        for (int q = o0 + lane; q < o1; q += 32) {
-            unsigned m = segm[q < MCAP ? q : 0];
-            if (m < (unsigned)CAP2 && q < MCAP) acc += r_s[m]; else atomicCAS(flag, 0, 11);
-        }
-        acc = cnt::warp_sum(acc);
-        if (lane == 0) {
-            if (segid[sgi] >= 0 && segid[sgi] < nseg_glob) segS[segid[sgi]] = acc; else atomicCAS(flag, 0, 12);
+        if (o1 - o0 > SEG_SMALL) {
+            double acc = 0.0;
+            for (int q = o0 + lane; q < o1; q += 32) acc += r_s[segm[q]];
+            acc = cnt::warp_sum(acc);
+            if (lane == 0) segS[segid[sgi]] = acc;
         }
     }
+    (void)flag;
+    (void)nseg_glob;
 }
 __device__ __forceinline__ void smem_coarse_values(const double *segS, const int32_t *la_q0, const uint16_t *la_qn,
                                                    const float *la_einv, double *c_loc, int nla, int *flag,

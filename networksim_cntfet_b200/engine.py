@@ -121,6 +121,8 @@ class Engine(object):
         self.profile = bool(profile)
         self._events = []
         self.solver = "auto"           # 'auto' | 'cluster' | 'flat'  (see Engine.solve)
+        self.initial_guess = "zero"    # 'zero' | 'linear' (linear potential drop along x: measured to need ~8 % MORE
+                                       # iterations, the stopping rule being relative to ||b||; kept as an option)
         self.precond = "twolevel"      # 'twolevel' (Jacobi + aggregate-level Jacobi) | 'jacobi'
         self.theta = 0.1               # strong-coupling threshold of the aggregates (relative to max |val|)
         self.cluster_compressed = True  # cluster kernel keeps its matrix slice in shared memory (class codes)
@@ -533,6 +535,22 @@ class Engine(object):
             gp = GateState(self, b).set_global(0).set_local(AREA_PARTIAL, 10)
         return [("ion", g0), ("back", gb), ("total", gt), ("partial", gp)]
 
+    def linear_guess(self, b, NS):
+        """x0[q, row] = 0.1 * (0.99 - xc) / 0.98 clipped to [0, 0.1]: the potential of a homogeneous
+        sheet between the electrodes at x=0.01 (0.1 V) and x=0.99 (0 V) (netsim.py:121-124,181-182).
+        Any x0 gives the same answer; a good one saves iterations."""
+        with self._work():
+            R = b.R
+            if R == 0 or getattr(b, "length", None) is None:
+                return None
+            roff = torch.as_tensor(b.h_roff, device=self.device, dtype=torch.int64)
+            soff = torch.as_tensor(b.h_soff, device=self.device, dtype=torch.int64)
+            rows = torch.arange(R, device=self.device, dtype=torch.int64)
+            net = torch.bucketize(rows, roff[1:], right=True)
+            stick = b.row_stick[:R].to(torch.int64) + soff[net]
+            v = (0.1 * (0.99 - b.xc[stick]) / 0.98).clamp_(0.0, 0.1)
+            return v.unsqueeze(0).repeat(NS, 1).contiguous()
+
     def solve_gates(self, b, gates, onoffmap, element, rtol=1e-15, maxit=2000000, check_every=250, want_fields=False):
         """Assemble + solve + write back a list of GateStates.  Returns dict with isrc[NS,B,3],
         iters/relres/status[NS,B] (+ V[NS,S], I[NS,J], g[NS,J], x when want_fields)."""
@@ -540,7 +558,8 @@ class Engine(object):
         tabs = [conductance_table(element, onoffmap, gs.levels) for gs in gates]
         sysm = self.assemble_values(b, gates, tabs)
         prio = [max(abs(v) for v in gs.levels) for gs in gates]   # higher |Vg| -> more iterations -> first
-        sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every, slab_priority=prio)
+        x0 = self.linear_guess(b, len(gates)) if self.initial_guess == "linear" else None
+        sol = self.solve(b, sysm, x0=x0, rtol=rtol, maxit=maxit, check_every=check_every, slab_priority=prio)
         NS = len(gates)
         out = dict(iters=sol["iters"], relres=sol["relres"], status=sol["status"])
         isrc = []
