@@ -36,9 +36,14 @@ def checkdir(directoryname):
 def add_voltagemeas(device, data, vgrange=10, vgnum=3):
     """three gate types x linspace(-vgrange, vgrange, vgnum) solves (measure_perc.py:39-53)"""
     gate, gatevoltage, current = [], [], []
+    vgs = np.linspace(-vgrange, vgrange, vgnum)
+    if hasattr(device, "gate_sweep"):
+        # all 3*vgnum gate steps as one batched GPU solve (same numbers as gate() one by one)
+        current = device.gate_sweep(vgs, ['back', 'partial', 'total'])
     for g in ['back', 'partial', 'total']:
-        for vg in np.linspace(-vgrange, vgrange, vgnum):
-            current.append(device.gate(vg, g))
+        for vg in vgs:
+            if not hasattr(device, "gate_sweep"):
+                current.append(device.gate(vg, g))
             gate.append(g)
             gatevoltage.append(vg)
     data.gate = gate

@@ -317,6 +317,43 @@ class RandomCNTNetwork(RandomConductingNetwork):
         self.cnet.update()
         return sum(self.cnet.source_currents)
 
+    def gate_sweep(self, vgs, gates=('back', 'partial', 'total')):
+        """All gate steps of a sweep (measure_perc.add_voltagemeas, measure_perc.py:39-53) as ONE
+        batched solve: every (gate, vg) pair is a value slab over the shared CSR pattern.  Returns
+        the source currents in the order `for g in gates: for vg in vgs` -- the same numbers
+        `gate(vg, g)` gives one by one.  Afterwards the device is in the state of the last step."""
+        from .engine import AREA_PARTIAL, AREA_TOTAL, GateState
+        eng, b = self._engine, self._batch
+        states, steps = [], []
+        for g in gates:
+            for vg in vgs:
+                st = GateState(eng, b).set_global(0)
+                if g == 'back':
+                    st.set_global(vg)
+                elif g == 'partial':
+                    st.set_local(AREA_PARTIAL, vg)
+                elif g == 'total':
+                    st.set_local(AREA_TOTAL, vg)
+                states.append(st)
+                steps.append((g, vg))
+        if not states:
+            return []
+        res = eng.solve_gates(b, states, self.onoffmap, self.element, want_fields=True)
+        eng.sync()
+        cur = res["isrc"][:, 0, 2].cpu().numpy()
+        self.sweep_status = res["status"][:, 0].cpu().numpy()
+        # leave the object as the last gate() call would
+        self.gatetype, self.gatevoltage = steps[-1]
+        c = self.cnet
+        c._gate = states[-1]
+        c.gate_areas = [] if steps[-1][0] == 'back' else [[AREA_PARTIAL if steps[-1][0] == 'partial' else AREA_TOTAL,
+                                                             steps[-1][1]]]
+        c._last = {k: (v[-1:] if hasattr(v, "shape") and v.shape[0] == len(states) else v) for k, v in res.items()
+                   if k != "sysm"}
+        c.source_currents = np.array([cur[-1]])
+        c._graph_dirty = True
+        return [float(v) for v in cur]
+
     def gate(self, vg, gate):
         self.gatetype = gate
         self.gatevoltage = vg

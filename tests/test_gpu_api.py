@@ -165,3 +165,27 @@ def test_conduction_network_from_networkx(api):
     assert len(x) == 5 and abs(x[-1] - 0.1 / req) <= 1e-12
     A = net.make_A(net.make_G())
     assert A.shape == (5, 5)
+
+
+def test_gate_sweep_batched_equals_sequential(api):
+    """config 4 (slurm/gatesweep.sh: --vgnum=11): the batched sweep gives the same currents as
+    gate() step by step, and the reference's own sweep values for a replayed seed"""
+    netsim, _, mp = api
+    g = load_golden("s5_n300_seed1")
+    net = netsim.RandomCNTNetwork(n=300, scaling=5, seed=1, onoffmap=0, rng="mt19937")
+    cur = net.gate_sweep(g["sweep_vg"])
+    ref = g["sweep_current"]
+    assert len(cur) == 9
+    for k in range(9):
+        tol = 5e-9 if (k < 3 and g["sweep_vg"][k % 3] > 0) else 1e-9      # back gate at +10 V: reference's own error
+        assert abs(cur[k] - ref[k]) <= tol * ref[k], (k, cur[k], ref[k])
+    assert net.gatetype == "total" and net.gatevoltage == g["sweep_vg"][-1]
+    assert abs(sum(net.cnet.source_currents) - cur[-1]) == 0
+    seq = [net.gate(vg, gate) for gate in ("back", "partial", "total") for vg in g["sweep_vg"]]
+    assert np.allclose(seq, cur, rtol=1e-12, atol=0)
+    # 11-point sweep on a Philox device through the measure_perc driver
+    data, fname = mp.single_measure(400, 5, seed=4242, onoffmap=0, vgnum=11, savedir="sweep11")
+    if len(data) == 33:
+        assert data.gate.tolist() == ["back"] * 11 + ["partial"] * 11 + ["total"] * 11
+        back = data.current.values[:11]
+        assert np.all(np.diff(back) < 0) and np.all(back > 0)

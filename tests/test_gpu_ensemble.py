@@ -1,0 +1,49 @@
+"""GPU: BASELINE config 2 -- an ensemble of 20x20 um networks swept across the percolation
+threshold (measure_perc.py density sweep, slurm/batchmeasure.sh:6-14) in ONE ragged batch, and
+config 1 (example.py: 5x5 um, n=300); a sample of the networks is re-done by the oracle."""
+import numpy as np
+import pytest
+
+from oracle import cntnet_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def test_density_sweep_20um(engine):
+    ns = [int(400 * d) for d in np.arange(1.0, 20.01, 0.25)]        # density 1 .. 20 /um^2, step 0.25: 77 networks
+    seeds = np.arange(1, len(ns) + 1, dtype=np.uint64) * 7919
+    res = engine.measure_ensemble(ns, 20.0, seeds, onoffmap=1)
+    perc = res["percolating"]
+    dens = np.array(ns) / 400.0
+    assert not perc[dens <= 6].any() and perc[dens >= 13].all()      # threshold ~9 sticks/um^2
+    assert np.all(res["status"] == 0)
+    assert np.all(res["ion"][~perc] == 0) and np.all(res["ion"][perc] > 0)
+    assert np.all(res["ioff_back"][perc] < res["ion"][perc])        # gating at +10 V lowers the current
+    assert np.all(np.diff(res["njunctions"]) > -0.2 * res["njunctions"][1:])   # junctions grow ~ n^2
+    # every 8th network again, through the oracle, from the very same sticks
+    for k in range(0, len(ns), 8):
+        b = engine.generate([ns[k]], 20.0, seeds=seeds[k:k + 1])
+        s = engine.sticks_to_host(b)[0]
+        m = O.measure_fullnet(s, onoffmap=1, refine=3)
+        assert m["percolating"] == bool(perc[k])
+        assert m["njunctions"] == res["njunctions"][k] and m["ntests"] == res["ntests"][k]
+        assert m["nclust_ref"] == res["nclust"][k] and m["maxclust_ref"] == res["maxclust"][k]
+        for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            if m["percolating"]:
+                assert abs(res[key][k] - m[key]) <= 1e-9 * m[key], (k, key, res[key][k], m[key])
+            else:
+                assert res[key][k] == 0.0
+
+
+def test_example_config_5um(engine):
+    """example.py:2 -- n=300, 5x5 um; 64 independent seeds in one batch"""
+    seeds = np.arange(100, 164, dtype=np.uint64)
+    res = engine.measure_ensemble([300] * 64, 5.0, seeds, onoffmap=0)
+    assert res["percolating"].mean() > 0.5
+    for k in (0, 17, 63):
+        s = engine.sticks_to_host(engine.generate([300], 5.0, seeds=seeds[k:k + 1]))[0]
+        m = O.measure_fullnet(s, onoffmap=0, refine=3)
+        assert m["percolating"] == bool(res["percolating"][k])
+        for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+            if m["percolating"]:
+                assert abs(res[key][k] - m[key]) <= 1e-9 * m[key]
