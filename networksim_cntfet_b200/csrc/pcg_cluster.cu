@@ -50,7 +50,6 @@ struct CArgs {
     double *segS;            // [nseg]
     long long *dbg;          // [gridDim.x][16] per-phase cycle sums (NULL = off)
     int *assert_flag;        // first failed in-kernel bounds check (0 = none)
-    int dbg_stage;           // debug bisecting: 1 = stop after setup, 2 = stop after the initial residual
     double rtol;
     int maxit;
     int32_t *iters, *status;
@@ -379,17 +378,24 @@ __device__ __forceinline__ void smem_segment_sums(double *segS, const double *r_
 __device__ __forceinline__ void smem_coarse_values(const double *segS, const int32_t *la_q0, const uint16_t *la_qn,
                                                    const float *la_einv, double *c_loc, int nla, int *flag,
                                                    int64_t nseg_glob) {
-    for (int i = threadIdx.x; i < nla; i += CT) {
-        int q0 = la_q0[i], qn = la_qn[i];
-        double S = 0.0;
-        if (q0 >= 0 && q0 + qn <= nseg_glob) {
-            S = __ldcg(segS + q0);
-            for (int q = 1; q < qn; q++) S += __ldcg(segS + q0 + q);
-        } else {
-            atomicCAS(flag, 0, 13);
+    // single-segment aggregates (the vast majority): one thread, one L2 load
+    for (int i = threadIdx.x; i < nla; i += CT)
+        if (la_qn[i] == 1) c_loc[i] = __ldcg(segS + la_q0[i]) * (double)la_einv[i];
+    // multi-segment aggregates (large clusters, clusters spanning CTAs): one warp each, all loads
+    // in flight at once, lane-strided partial sums + fixed shuffle tree (same order in every CTA)
+    const int lane = threadIdx.x & 31;
+    for (int i = threadIdx.x >> 5; i < nla; i += (CT >> 5)) {
+        int qn = la_qn[i];
+        if (qn > 1) {
+            int q0 = la_q0[i];
+            double S = 0.0;
+            for (int q = lane; q < qn; q += 32) S += __ldcg(segS + q0 + q);
+            S = cnt::warp_sum(S);
+            if (lane == 0) c_loc[i] = S * (double)la_einv[i];
         }
-        c_loc[i] = S * (double)la_einv[i];
     }
+    (void)flag;
+    (void)nseg_glob;
 }
 
 template <bool TWO>
@@ -437,7 +443,6 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         const double *diag = a.diag + vbase + own0;
         const double *rhs = a.rhs + vbase + own0;
         double *x = a.x + vbase;                   // network-local index (gathers of x0 use columns)
-        double *pg = a.pglob + vbase;
         const int32_t *rowptr = a.rowptr + sy.row0 + own0;
 
         // ================= setup (once per system) =================
@@ -515,7 +520,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                         } else {
                             int h = atomicAdd(&sh->nhalo, 1);
                             if (h < HCAP) {
-                                halo_col[h] = c;
+                                halo_col[h] = ((c / chunk) << 16) | (c % chunk);   // owner CTA, its local row
                                 slot = (unsigned)(nown + h);
                             } else {
                                 slot = 0;
@@ -584,14 +589,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         const int nhalo = min(sh->nhalo, HCAP);
         const double my_ovf = (!fits || sh->ovf) ? 1.0 : 0.0;
 
-        if (a.dbg_stage == 1) {            // bisecting aid: setup only
-            cluster.sync();
-            continue;
-        }
         // ================= r = b - A x0, z = M^-1 r, p = z =================
         double d_r[MAXR2], di_r[MAXR2], qz_r[MAXR2];
         double acc[4] = {0.0, 0.0, 0.0, my_ovf};    // rz, bb, rr, overflow flag
-        bool done_dbg = false;
 #pragma unroll
         for (int k = 0; k < MAXR2; k++) {
             d_r[k] = 1.0; di_r[k] = 1.0; qz_r[k] = 0.0;
@@ -615,10 +615,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         }
         if (TWO) {
             __syncthreads();                                    // r_s complete in this CTA
-            if (a.dbg_stage != 3) smem_segment_sums(a.segS, r_s, segm, segoff, segid, nseg_loc, a.assert_flag, a.agg.nseg);
+            smem_segment_sums(a.segS, r_s, segm, segoff, segid, nseg_loc, a.assert_flag, a.agg.nseg);
             cluster.sync();                                     // segment sums published
-            if (a.dbg_stage != 4 && a.dbg_stage != 3)
-                smem_coarse_values(a.segS, la_q0, la_qn, la_einv, c_loc, nla, a.assert_flag, a.agg.nseg);
+            smem_coarse_values(a.segS, la_q0, la_qn, la_einv, c_loc, nla, a.assert_flag, a.agg.nseg);
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
@@ -626,16 +625,13 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     int li = meta_r[k] & 0xFFFF;
                     double ri = r_s[li];
                     unsigned sl = slot_s[li];
-                    double zi = ri * di_r[k] + ((sl != 0xFFFFu && a.dbg_stage < 3) ? c_loc[sl] : 0.0);
+                    double zi = ri * di_r[k] + (sl != 0xFFFFu ? c_loc[sl] : 0.0);
                     p_ext[li] = zi;
                     acc[0] += ri * zi;
                 }
             }
-            if (a.dbg_stage >= 3) done_dbg = true;
         }
-        __syncthreads();
-        for (int i = t; i < nown; i += CT) pg[own0 + i] = p_ext[i];      // coalesced publication of p
-        cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // barrier also publishes p
+        cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // barrier also publishes p (shared memory)
         double rz = acc[0];
         const double bb = acc[1];
         double rr = acc[2];
@@ -644,14 +640,15 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         bool done = (sy.nrows == 0) || (rr <= tol2);
         if (acc[3] > 0.0) { done = true; status = 3; }          // does not fit on chip: caller re-solves
         if (!done && a.maxit <= 0) { done = true; status = 1; }
-        if (a.dbg_stage == 2 || done_dbg) done = true;
         PHASE(1);                                               // setup + initial residual
 
         while (!done) {
             // ---- phase 0: refresh the halo copies of p (written by their owners before the barrier)
+            // halo values straight from the owners' shared memory (DSMEM), no trip through L2
             for (int h = t; h < nhalo; h += CT) {
                 int hc = halo_col[h];
-                if (KCHECK(21, hc >= 0 && hc < sy.nrows && nown + h < CAP2 + HCAP)) p_ext[nown + h] = __ldcg(pg + hc);
+                const double *peer = cluster.map_shared_rank(p_ext, hc >> 16);
+                p_ext[nown + h] = peer[hc & 0xFFFF];
             }
             __syncthreads();
             PHASE(2);                                           // halo refresh
@@ -746,10 +743,8 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     p_ext[li] = qz_r[k] + beta * p_ext[li];
                 }
             }
-            __syncthreads();
-            for (int i = t; i < nown; i += CT) pg[own0 + i] = p_ext[i];
-            PHASE(10);                                          // p update + publish
-            cluster.sync();
+            PHASE(10);                                          // p update
+            cluster.sync();                                     // own p visible to the cluster
             PHASE(11);                                          // barrier
         }
         if (crank == 0 && t == 0) {
@@ -902,7 +897,6 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     a.rglob = rglob; a.segS = segS;
     a.dbg = g_phase_dbg;
     a.assert_flag = assert_flag;
-    a.dbg_stage = getenv("CNT_DBG_STAGE") ? atoi(getenv("CNT_DBG_STAGE")) : 0;
     if (two) a.agg = *agg; else a.agg = cnt_aggregates{};
     a.iters = iters; a.status = status; a.relres = relres;
     CNT_CUDA(cudaLaunchKernelEx(&cfg, kern, a));

@@ -24,7 +24,8 @@ from .cnet import FermiDiracTransistor, LinExpTransistor
 elements = [FermiDiracTransistor, LinExpTransistor]
 FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'ioff', 'gate', 'fname', 'seed',
                    'onoffmap']
-BATCH_STICKS = 1_200_000      # sticks per GPU batch of the ensemble path (~12 networks at 100x100 um)
+BATCH_STICKS = 1_450_000      # sticks per GPU batch of the ensemble path (14 networks at 100x100 um = 8 full rounds
+                              # of the 7 resident 16-CTA clusters)
 
 
 def checkdir(directoryname):
