@@ -209,6 +209,7 @@ typedef struct cnt_aggregates {
     const int32_t *cta_agg_off;  /* [NSYS*chunk_C+1] aggregates touched by CTA c of system s          */
     const int32_t *cta_agg;      /* aggregate ids in CTA order (<= nseg entries)                      */
     const int32_t *row_slot;     /* [NSLAB*R] slot of the row's aggregate in its CTA's list, -1 none  */
+    const int32_t *seg_home;     /* [nseg] (owning CTA << 16) | index in that CTA's segment list      */
     int64_t nagg, nseg;
     int32_t chunk_C, pad;
 } cnt_aggregates;
@@ -222,6 +223,7 @@ int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, con
                        int chunk_C /* cluster size the tables are built for (cnt_pcg_cluster_size), 0 = flat only */,
                        int32_t *row_q, double *row_einv, int32_t *cta_seg_off, int32_t *cta_seg,
                        int32_t *cta_agg_off, int32_t *cta_agg /* capacity of seg_* */, int32_t *row_slot,
+                       int32_t *seg_home /* capacity of seg_* */,
                        int64_t *h_nagg, int64_t *h_nseg,
                        void *ws, int64_t ws_bytes, void *stream);
 

@@ -42,7 +42,7 @@ PROTOTYPES = {
     "cnt_assemble_values": (i32, [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cnt_pcg_aggregate_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_aggregates": (i32, [i32, i32, i32, I32P, I32P, I32P, vp, i64, i64, vp, vp, vp, vp, f64] + [vp] * 9 +
-                           [i32, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
+                           [i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
     "cnt_pcg_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_pcg_cluster_max_rows": (i64, []),
@@ -63,6 +63,7 @@ class Aggregates(C.Structure):
     _fields_ = [("agg_of_row", vp), ("mem", vp), ("seg_start", vp), ("seg_count", vp), ("seg_agg", vp),
                 ("seg_sys", vp), ("agg_seg0", vp), ("agg_einv", vp), ("sys_seg", vp), ("row_q", vp), ("row_einv", vp),
                 ("cta_seg_off", vp), ("cta_seg", vp), ("cta_agg_off", vp), ("cta_agg", vp), ("row_slot", vp),
+                ("seg_home", vp),
                 ("nagg", i64), ("nseg", i64), ("chunk_C", C.c_int32),
                 ("pad", C.c_int32)]
 

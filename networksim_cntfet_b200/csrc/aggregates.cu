@@ -188,7 +188,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
                                   int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
                                   double *agg_einv, int32_t *sys_seg, int chunk_C, int32_t *row_q, double *row_einv,
                                   int32_t *cta_seg_off, int32_t *cta_seg, int32_t *cta_agg_off, int32_t *cta_agg,
-                                  int32_t *row_slot,
+                                  int32_t *row_slot, int32_t *seg_home,
                                   int64_t *h_nagg, int64_t *h_nseg, void *ws, int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && roff && R >= 0 && h_nagg &&
@@ -199,7 +199,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
     if (n == 0) return CNT_OK;
     CNT_CHECK_ARG(n < ((int64_t)1 << 31));
     CNT_CHECK_ARG(rowptr && diag && agg_of_row && mem && seg_start && seg_count && seg_agg && seg_sys && agg_seg0 &&
-                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (row_q && row_einv && cta_seg_off && cta_seg && cta_agg_off && cta_agg && row_slot)));
+                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (row_q && row_einv && cta_seg_off && cta_seg && cta_agg_off && cta_agg && row_slot && seg_home)));
     // systems sorted by (slab, network) are the sort segments; tiles for the row kernels
     std::vector<ASys> sys(NSYS);
     std::vector<ATile> tiles;
@@ -345,7 +345,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         k_agg_einv<<<cnt::grid_for(nagg, 256), 256, 0, st>>>(nagg, agg_seg0, segE, agg_einv);
         CNT_LAUNCHED();
     }
-    std::vector<int32_t> h_cta_off, h_cta_seg, h_cta_agg_off, h_cta_agg, h_row_slot;
+    std::vector<int32_t> h_cta_off, h_cta_seg, h_cta_agg_off, h_cta_agg, h_row_slot, h_seg_home;
     if (chunk_C > 0) {
         // per (system, CTA): its segments as (segment id, first member, count, 0) quadruples
         CNT_CUDA(cudaMemsetAsync(row_q, 0, 8 * n, st));
@@ -355,11 +355,14 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         for (size_t k = 1; k < h_cta_off.size(); k++) h_cta_off[k] += h_cta_off[k - 1];
         std::vector<int32_t> cur(h_cta_off.begin(), h_cta_off.end() - 1);
         h_cta_seg.assign(4 * (size_t)(nseg > 0 ? nseg : 1), 0);
+        h_seg_home.assign((size_t)(nseg > 0 ? nseg : 1), 0);
         for (int64_t q = 0; q < nseg; q++) {
             int32_t pos = cur[(size_t)h_seg_sys[q] * chunk_C + h_seg_cta[q]]++;
             h_cta_seg[4 * (size_t)pos + 0] = (int32_t)q;
             h_cta_seg[4 * (size_t)pos + 1] = h_seg_start[q];
             h_cta_seg[4 * (size_t)pos + 2] = h_seg_count[q];
+            // home of the segment: owning CTA and its index in that CTA's list (DSMEM exchange)
+            h_seg_home[(size_t)q] = (h_seg_cta[q] << 16) | (pos - h_cta_off[(size_t)h_seg_sys[q] * chunk_C + h_seg_cta[q]]);
         }
         // per (system, CTA): the aggregates it touches (dedup of its segments' aggregates, which are
         // adjacent because segment ids are contiguous per aggregate) and, per row, the slot of its
@@ -384,6 +387,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         CNT_CUDA(cudaMemcpyAsync(cta_agg_off, h_cta_agg_off.data(), 4 * h_cta_agg_off.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_agg, h_cta_agg.data(), 4 * h_cta_agg.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(row_slot, h_row_slot.data(), 4 * (size_t)n, cudaMemcpyHostToDevice, st));
+        CNT_CUDA(cudaMemcpyAsync(seg_home, h_seg_home.data(), 4 * h_seg_home.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_seg_off, h_cta_off.data(), 4 * h_cta_off.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_seg, h_cta_seg.data(), 4 * h_cta_seg.size(), cudaMemcpyHostToDevice, st));
         if (nseg > 0) {

@@ -22,8 +22,11 @@
 namespace cg = cooperative_groups;
 
 namespace {
-constexpr int CT = 1024;             // threads per CTA
-constexpr int MAXR = 6;              // rows per thread
+#ifndef CNT_CLUSTER_THREADS
+#define CNT_CLUSTER_THREADS 1024
+#endif
+constexpr int CT = CNT_CLUSTER_THREADS;   // threads per CTA
+constexpr int MAXR = 6144 / CT;       // rows per thread
 constexpr int CAP = CT * MAXR;       // rows per CTA (6144)
 constexpr int MAXC = 16;             // largest cluster (non-portable size, opt-in)
 
@@ -282,7 +285,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster(CArgs a) {
 // configuration: junction kind x gate level).  An iteration then touches global memory only
 // to publish p (8 B/row), refresh the halo (one coalesced pass of L2 loads) and update x.
 // =====================================================================================
-constexpr int MAXR2 = 5;               // rows per thread
+constexpr int MAXR2 = 5120 / CT;       // rows per thread
 constexpr int CAP2 = CT * MAXR2;       // rows per CTA (5120)
 constexpr int ECAP = 20480;            // packed entries per CTA
 constexpr int HCAP = 2048;             // halo references per CTA
@@ -298,7 +301,7 @@ __device__ __forceinline__ int block_excl_scan_i(int v, int *sm /*34 ints*/, int
     if (lane == 31) sm[w] = incl;
     __syncthreads();
     if (w == 0) {
-        int sv = sm[lane];                 // CT/32 == 32 warps
+        int sv = lane < (CT >> 5) ? sm[lane] : 0;
         int si = sv;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -349,16 +352,16 @@ constexpr int MCAP = CAP2;              // two-level: aggregated rows per CTA (a
 // fixed order; after the cluster barrier one thread per local aggregate combines the aggregate's
 // segment sums (its own and other CTAs', in segment order) into the coarse value
 constexpr int SEG_SMALL = 8;     // segments up to this size are summed by one thread, larger ones by a warp
-__device__ __forceinline__ void smem_segment_sums(double *segS, const double *r_s, const uint16_t *segm,
-                                                  const uint16_t *segoff, const int32_t *segid, int nseg_loc,
-                                                  int *flag, int64_t nseg_glob) {
+constexpr int RCAP = 512;        // two-level: segment references of the CTA's multi-segment aggregates
+__device__ __forceinline__ void smem_segment_sums(double *seg_loc, const double *r_s, const uint16_t *segm,
+                                                  const uint16_t *segoff, int nseg_loc) {
     // small segments: one thread each, members added in list order
     for (int sgi = threadIdx.x; sgi < nseg_loc; sgi += CT) {
         int o0 = segoff[sgi], o1 = segoff[sgi + 1];
         if (o1 - o0 <= SEG_SMALL) {
             double acc = 0.0;
             for (int q = o0; q < o1; q++) acc += r_s[segm[q]];
-            segS[segid[sgi]] = acc;
+            seg_loc[sgi] = acc;
         }
     }
     // large segments: one warp each, lane-strided partial sums + fixed shuffle tree
@@ -369,33 +372,34 @@ __device__ __forceinline__ void smem_segment_sums(double *segS, const double *r_
             double acc = 0.0;
             for (int q = o0 + lane; q < o1; q += 32) acc += r_s[segm[q]];
             acc = cnt::warp_sum(acc);
-            if (lane == 0) segS[segid[sgi]] = acc;
+            if (lane == 0) seg_loc[sgi] = acc;
         }
     }
-    (void)flag;
-    (void)nseg_glob;
 }
-__device__ __forceinline__ void smem_coarse_values(const double *segS, const int32_t *la_q0, const uint16_t *la_qn,
-                                                   const float *la_einv, double *c_loc, int nla, int *flag,
-                                                   int64_t nseg_glob) {
-    // single-segment aggregates (the vast majority): one thread, one L2 load
+// coarse value of every local aggregate = 1/E * (sum of the aggregate's segment sums, in global
+// segment order).  Segment sums live in the shared memory of the CTA that owns the segment:
+// single-segment aggregates read their own CTA's array, multi-segment ones follow the reference
+// list built at setup (owner CTA, index) through DSMEM -- no global memory on this path.
+__device__ __forceinline__ void smem_coarse_values(cg::cluster_group &cluster, double *seg_loc, const uint16_t *la_a,
+                                                   const uint16_t *la_qn, const float *la_einv, const uint32_t *refs,
+                                                   double *c_loc, int nla) {
     for (int i = threadIdx.x; i < nla; i += CT)
-        if (la_qn[i] == 1) c_loc[i] = __ldcg(segS + la_q0[i]) * (double)la_einv[i];
-    // multi-segment aggregates (large clusters, clusters spanning CTAs): one warp each, all loads
-    // in flight at once, lane-strided partial sums + fixed shuffle tree (same order in every CTA)
+        if (la_qn[i] == 1) c_loc[i] = seg_loc[la_a[i]] * (double)la_einv[i];
     const int lane = threadIdx.x & 31;
     for (int i = threadIdx.x >> 5; i < nla; i += (CT >> 5)) {
         int qn = la_qn[i];
         if (qn > 1) {
-            int q0 = la_q0[i];
+            int r0 = la_a[i];
             double S = 0.0;
-            for (int q = lane; q < qn; q += 32) S += __ldcg(segS + q0 + q);
+            for (int q = lane; q < qn; q += 32) {
+                uint32_t ref = refs[r0 + q];
+                const double *home = cluster.map_shared_rank(seg_loc, ref >> 16);
+                S += home[ref & 0xFFFFu];
+            }
             S = cnt::warp_sum(S);
             if (lane == 0) c_loc[i] = S * (double)la_einv[i];
         }
     }
-    (void)flag;
-    (void)nseg_glob;
 }
 
 template <bool TWO>
@@ -416,11 +420,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     uint16_t *slot_s = reinterpret_cast<uint16_t *>(gbase + CAP2 / 32);         // CAP2: row -> local aggregate
     // two-level tables of this CTA (shared memory only in the iteration)
     double *c_loc = reinterpret_cast<double *>(slot_s + CAP2);                  // LCAP coarse values
-    int32_t *segid = reinterpret_cast<int32_t *>(c_loc + LCAP);                 // LCAP global segment ids
-    int32_t *la_q0 = segid + LCAP;                                              // LCAP first segment of aggregate
-    float *la_einv = reinterpret_cast<float *>(la_q0 + LCAP);                   // LCAP 1/E (FP32 is plenty for M)
+    double *seg_loc = c_loc + LCAP;                                             // LCAP sums of this CTA's segments
+    uint32_t *refs = reinterpret_cast<uint32_t *>(seg_loc + LCAP);              // RCAP (owner CTA << 16 | index)
+    float *la_einv = reinterpret_cast<float *>(refs + RCAP);                    // LCAP 1/E (FP32 is plenty for M)
     uint16_t *la_qn = reinterpret_cast<uint16_t *>(la_einv + LCAP);             // LCAP segments of aggregate
-    uint16_t *segoff = la_qn + LCAP;                                            // LCAP + 2
+    uint16_t *la_a = la_qn + LCAP;                                              // LCAP own segment / first reference
+    uint16_t *segoff = la_a + LCAP;                                             // LCAP + 2
     uint16_t *segm = segoff + LCAP + 2;                                         // MCAP member rows (local index)
     const int t = threadIdx.x, lane = t & 31;
     if (t == 0) {
@@ -545,7 +550,17 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             if (cap_ok && t < nseg_loc) sg = __ldg(list + t);
             int total;
             int off = block_excl_scan_i(sg.z, iscr, &total);
-            const bool tw_ok = cap_ok && total <= MCAP;
+            bool tw_ok = cap_ok && total <= MCAP;
+            // references of the multi-segment aggregates: exclusive scan of their segment counts
+            int myq0 = 0, myqn = 0;
+            if (cap_ok && t < nla) {
+                int aid = __ldg(a.agg.cta_agg + la0 + t);
+                myq0 = __ldg(a.agg.agg_seg0 + aid);
+                myqn = __ldg(a.agg.agg_seg0 + aid + 1) - myq0;
+            }
+            int rtotal;
+            int roff = block_excl_scan_i(myqn > 1 ? myqn : 0, iscr, &rtotal);
+            tw_ok = tw_ok && rtotal <= RCAP;
             if (!tw_ok) {
                 // tables do not fit: the system gets status 3 once the cluster has agreed on it; until
                 // then the phases below must see consistent (empty) tables
@@ -557,17 +572,25 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 if (t < nseg_loc) {
                     KCHECK(7, sg.x >= 0 && sg.x < a.agg.nseg && sg.y >= 0 && sg.z > 0 && sg.z <= 256);
                     segoff[t] = (uint16_t)off;
-                    segid[t] = sg.x;
                 }
                 if (t == 0) segoff[nseg_loc] = (uint16_t)total;
-                for (int i = t; i < nla; i += CT) {
-                    int aid = __ldg(a.agg.cta_agg + la0 + i);
-                    KCHECK(5, aid >= 0 && aid < a.agg.nagg);
-                    int q0 = __ldg(a.agg.agg_seg0 + aid);
-                    KCHECK(6, q0 >= 0 && q0 < a.agg.nseg);
-                    la_q0[i] = q0;
-                    la_qn[i] = (uint16_t)(__ldg(a.agg.agg_seg0 + aid + 1) - q0);
-                    la_einv[i] = (float)__ldg(a.agg.agg_einv + aid);
+                if (t < nla) {
+                    int aid = __ldg(a.agg.cta_agg + la0 + t);
+                    la_qn[t] = (uint16_t)myqn;
+                    la_einv[t] = (float)__ldg(a.agg.agg_einv + aid);
+                    if (myqn == 1) {
+                        // its only segment is owned by this CTA: index in the local list
+                        int home = __ldg(a.agg.seg_home + myq0);
+                        KCHECK(5, (home >> 16) == crank && (home & 0xFFFF) < nseg_loc);
+                        la_a[t] = (uint16_t)(home & 0xFFFF);
+                    } else {
+                        la_a[t] = (uint16_t)roff;
+                        for (int q = 0; q < myqn; q++) {
+                            int home = __ldg(a.agg.seg_home + myq0 + q);
+                            KCHECK(6, (home >> 16) < C && (home & 0xFFFF) < LCAP);
+                            refs[roff + q] = (uint32_t)home;
+                        }
+                    }
                 }
                 for (int i = t; i < nown; i += CT) {
                     int sl = __ldg(a.agg.row_slot + vbase + own0 + i);
@@ -615,9 +638,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         }
         if (TWO) {
             __syncthreads();                                    // r_s complete in this CTA
-            smem_segment_sums(a.segS, r_s, segm, segoff, segid, nseg_loc, a.assert_flag, a.agg.nseg);
+            smem_segment_sums(seg_loc, r_s, segm, segoff, nseg_loc);
             cluster.sync();                                     // segment sums published
-            smem_coarse_values(a.segS, la_q0, la_qn, la_einv, c_loc, nla, a.assert_flag, a.agg.nseg);
+            smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, c_loc, nla);
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < MAXR2; k++) {
@@ -707,11 +730,11 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             PHASE(5);                                           // x, r update
             if (TWO) {
                 __syncthreads();                                // r_s complete in this CTA
-                smem_segment_sums(a.segS, r_s, segm, segoff, segid, nseg_loc, a.assert_flag, a.agg.nseg);
+                smem_segment_sums(seg_loc, r_s, segm, segoff, nseg_loc);
                 PHASE(6);                                       // segment sums
                 cluster.sync();                                 // segment sums published
                 PHASE(7);                                       // barrier
-                smem_coarse_values(a.segS, la_q0, la_qn, la_einv, c_loc, nla, a.assert_flag, a.agg.nseg);
+                smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, c_loc, nla);
                 __syncthreads();
 #pragma unroll
                 for (int k = 0; k < MAXR2; k++) {
@@ -760,7 +783,8 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 
 constexpr size_t SMEM2_BYTES = sizeof(Shared) + (128 + 256 + (size_t)CAP2 + HCAP + CAP2) * sizeof(double) +
                                (size_t)ECAP * 4 + (size_t)HCAP * 4 + (36 + CAP2 / 32) * 4 + (size_t)CAP2 * 2 +
-                               (size_t)LCAP * (8 + 4 + 4 + 4 + 2) + ((size_t)LCAP + 2) * 2 + (size_t)MCAP * 2 + 16;
+                               (size_t)LCAP * (8 + 8 + 4 + 2 + 2) + (size_t)RCAP * 4 + ((size_t)LCAP + 2) * 2 +
+                               (size_t)MCAP * 2 + 16;
 static_assert(SMEM2_BYTES <= 232448, "cluster kernel exceeds the 227 KB shared-memory limit");
 
 constexpr size_t SMEM_BYTES = sizeof(Shared) + 96 * sizeof(double) + 3 * (size_t)CAP * sizeof(double);

@@ -396,7 +396,7 @@ class Engine(object):
                  row_q=i32(2 * n if chunk_C else 1), cta_seg_off=i32(nsys * chunk_C + 1),
                  cta_seg=i32(4 * (cap_seg + nsys * chunk_C) if chunk_C else 1),
                  cta_agg_off=i32(nsys * chunk_C + 1), cta_agg=i32(cap_seg if chunk_C else 1),
-                 row_slot=i32(n if chunk_C else 1),
+                 row_slot=i32(n if chunk_C else 1), seg_home=i32(cap_seg if chunk_C else 1),
                  row_einv=torch.empty(n if chunk_C else 1, dtype=torch.float64, device=self.device),
                  agg_einv=torch.empty(n // 2 + 2, dtype=torch.float64, device=self.device))
         ws = self._ws(lib.cnt_pcg_aggregate_workspace_bytes(nsys, NS, b.R))
@@ -407,7 +407,7 @@ class Engine(object):
                                      _p(t["seg_count"]), _p(t["seg_agg"]), _p(t["seg_sys"]), _p(t["agg_seg0"]),
                                      _p(t["agg_einv"]), _p(t["sys_seg"]), int(chunk_C), _p(t["row_q"]), _p(t["row_einv"]),
                                      _p(t["cta_seg_off"]), _p(t["cta_seg"]), _p(t["cta_agg_off"]), _p(t["cta_agg"]),
-                                     _p(t["row_slot"]), C.byref(nagg), C.byref(nseg), _p(ws),
+                                     _p(t["row_slot"]), _p(t["seg_home"]), C.byref(nagg), C.byref(nseg), _p(ws),
                                      ws.numel(),
                                      self.stream_ptr))
         st = _lib.Aggregates(t["agg_of_row"].data_ptr(), t["mem"].data_ptr(), t["seg_start"].data_ptr(),
@@ -415,7 +415,8 @@ class Engine(object):
                              t["agg_seg0"].data_ptr(), t["agg_einv"].data_ptr(), t["sys_seg"].data_ptr(),
                              t["row_q"].data_ptr(), t["row_einv"].data_ptr(), t["cta_seg_off"].data_ptr(),
                              t["cta_seg"].data_ptr(), t["cta_agg_off"].data_ptr(), t["cta_agg"].data_ptr(),
-                             t["row_slot"].data_ptr(), nagg.value, nseg.value, int(chunk_C), 0)
+                             t["row_slot"].data_ptr(), t["seg_home"].data_ptr(), nagg.value, nseg.value,
+                             int(chunk_C), 0)
         self.last_aggregates = (nagg.value, nseg.value)
         return st, t
 

@@ -47,3 +47,25 @@ def test_example_config_5um(engine):
         for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
             if m["percolating"]:
                 assert abs(res[key][k] - m[key]) <= 1e-9 * m[key]
+
+
+@pytest.mark.parametrize("n,onoffmap,element", [(120000, 1, "linexp"), (100000, 0, "fermidirac"), (90000, 2, "linexp")])
+def test_full_size_variants(engine, n, onoffmap, element):
+    """100x100 um at other densities / on-off maps / elements (slurm/batchmeasure_multi.sh sweeps density
+    8..12): n = 120k does not fit the cluster kernel's on-chip capacity and takes the multi-launch
+    solver automatically; all against the refined oracle from the same sticks"""
+    from networksim_cntfet_b200 import elements
+    el = elements.FermiDiracTransistor if element == "fermidirac" else elements.LinExpTransistor
+    b = engine.generate([n], 100.0, seed=77)
+    res = engine.measure_fullnet(b, onoffmap=onoffmap, element=el)
+    rows = b.h_roff[1]
+    from networksim_cntfet_b200 import _lib
+    expect = "cluster" if rows <= _lib.load().cnt_pcg_cluster_max_rows() else "flat"
+    assert engine.last_solver.startswith(expect), (engine.last_solver, rows)
+    assert np.all(res["status"] == 0)
+    s = engine.sticks_to_host(b)[0]
+    m = O.measure_fullnet(s, onoffmap=onoffmap, element=element, refine=3)
+    assert m["percolating"] == bool(res["percolating"][0])
+    assert m["njunctions"] == res["njunctions"][0] and m["ntests"] == res["ntests"][0]
+    for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert abs(res[key][0] - m[key]) <= 1e-9 * m[key], (key, res[key][0], m[key], res["iters"][:, 0])
