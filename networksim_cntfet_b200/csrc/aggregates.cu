@@ -199,7 +199,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
     if (n == 0) return CNT_OK;
     CNT_CHECK_ARG(n < ((int64_t)1 << 31));
     CNT_CHECK_ARG(rowptr && diag && agg_of_row && mem && seg_start && seg_count && seg_agg && seg_sys && agg_seg0 &&
-                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (row_q && row_einv && cta_seg_off && cta_seg && cta_agg_off && cta_agg && row_slot && seg_home)));
+                  agg_einv && sys_seg && chunk_C >= 0 && (chunk_C == 0 || (cta_seg_off && cta_seg && cta_agg_off && cta_agg && row_slot && seg_home)));
     // systems sorted by (slab, network) are the sort segments; tiles for the row kernels
     std::vector<ASys> sys(NSYS);
     std::vector<ATile> tiles;
@@ -345,11 +345,20 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         k_agg_einv<<<cnt::grid_for(nagg, 256), 256, 0, st>>>(nagg, agg_seg0, segE, agg_einv);
         CNT_LAUNCHED();
     }
+    if (row_q && row_einv) {
+        // per-row (first segment, segment count, 1/E): short load chain for the coarse term
+        CNT_CUDA(cudaMemsetAsync(row_q, 0, 8 * n, st));
+        CNT_CUDA(cudaMemsetAsync(row_einv, 0, 8 * n, st));
+        if (nseg > 0) {
+            k_row_tables<<<cnt::grid_for(nseg * 32, 256), 256, 0, st>>>(nseg, seg_start, seg_count, seg_agg,
+                                                                        (const uint32_t *)mem, agg_seg0, agg_einv,
+                                                                        row_q, row_einv);
+            CNT_LAUNCHED();
+        }
+    }
     std::vector<int32_t> h_cta_off, h_cta_seg, h_cta_agg_off, h_cta_agg, h_row_slot, h_seg_home;
     if (chunk_C > 0) {
         // per (system, CTA): its segments as (segment id, first member, count, 0) quadruples
-        CNT_CUDA(cudaMemsetAsync(row_q, 0, 8 * n, st));
-        CNT_CUDA(cudaMemsetAsync(row_einv, 0, 8 * n, st));
         h_cta_off.assign((size_t)NSYS * chunk_C + 1, 0);
         for (int64_t q = 0; q < nseg; q++) h_cta_off[(size_t)h_seg_sys[q] * chunk_C + h_seg_cta[q] + 1]++;
         for (size_t k = 1; k < h_cta_off.size(); k++) h_cta_off[k] += h_cta_off[k - 1];
@@ -390,12 +399,6 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         CNT_CUDA(cudaMemcpyAsync(seg_home, h_seg_home.data(), 4 * h_seg_home.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_seg_off, h_cta_off.data(), 4 * h_cta_off.size(), cudaMemcpyHostToDevice, st));
         CNT_CUDA(cudaMemcpyAsync(cta_seg, h_cta_seg.data(), 4 * h_cta_seg.size(), cudaMemcpyHostToDevice, st));
-        if (nseg > 0) {
-            k_row_tables<<<cnt::grid_for(nseg * 32, 256), 256, 0, st>>>(nseg, seg_start, seg_count, seg_agg,
-                                                                        (const uint32_t *)mem, agg_seg0, agg_einv,
-                                                                        row_q, row_einv);
-            CNT_LAUNCHED();
-        }
     }
     // host vectors must outlive the async uploads
     CNT_CUDA(cudaStreamSynchronize(st));

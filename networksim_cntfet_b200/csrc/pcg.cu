@@ -206,19 +206,41 @@ __global__ void __launch_bounds__(TILE) k_pupdate(Ctx c) {
 }
 
 // ---------------- two-level preconditioner: z = r/d + (sum of r over the row's aggregate) * einv
+// segment sums of r: one THREAD per segment of <= 8 rows (the vast majority), one warp per larger
+// segment -- members are added in list order / lane-strided + fixed tree, so the result is
+// deterministic either way
+constexpr int SEG_SMALL = 8;
+__global__ void k_seg_sum_small(Ctx c) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= c.agg.nseg) return;
+    int n = c.agg.seg_count[s];
+    if (n > SEG_SMALL || c.scal[c.agg.seg_sys[s]].done) return;
+    int s0 = c.agg.seg_start[s];
+    double acc = 0.0;
+    for (int k = 0; k < n; k++) acc += c.r[c.agg.mem[s0 + k]];
+    c.segS[s] = acc;
+}
 __global__ void k_seg_sum(Ctx c) {
     int64_t s = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (s >= c.agg.nseg) return;
-    if (c.scal[c.agg.seg_sys[s]].done) return;
+    int n = c.agg.seg_count[s];
+    if (n <= SEG_SMALL || c.scal[c.agg.seg_sys[s]].done) return;
     int lane = threadIdx.x & 31;
-    int s0 = c.agg.seg_start[s], n = c.agg.seg_count[s];
+    int s0 = c.agg.seg_start[s];
     double acc = 0.0;
-    for (int k = lane; k < n; k += 32) acc += c.r[c.agg.mem[s0 + k]];   // fixed order: lane-strided + tree
+    for (int k = lane; k < n; k += 32) acc += c.r[c.agg.mem[s0 + k]];
     acc = cnt::warp_sum(acc);
     if (lane == 0) c.segS[s] = acc;
 }
 
 __device__ __forceinline__ double coarse_term(const Ctx &c, int64_t v) {
+    if (c.agg.row_q) {      // precomputed (first segment, count, 1/E) per row
+        int2 rq = __ldg(reinterpret_cast<const int2 *>(c.agg.row_q) + v);
+        if (rq.y == 0) return 0.0;
+        double S = c.segS[rq.x];
+        for (int q = 1; q < rq.y; q++) S += c.segS[rq.x + q];
+        return S * __ldg(c.agg.row_einv + v);
+    }
     int a = c.agg.agg_of_row[v];
     if (a < 0) return 0.0;
     double S = 0.0;
@@ -406,6 +428,7 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
     c.segS = segS;
     if (two_level) c.agg = *agg; else { c.agg = cnt_aggregates{}; }
     unsigned gseg = two_level ? cnt::grid_for(agg->nseg * 32, 256) : 0;
+    unsigned gseg_small = two_level ? cnt::grid_for(agg->nseg, 256) : 0;
     unsigned gs = cnt::grid_for(NSYS, 128);            // one thread per system (export)
     unsigned gw = cnt::grid_for((int64_t)NSYS * 32, 128);   // one warp per system (scalar kernels)
     if (nt > 0 && !two_level) {
@@ -416,6 +439,8 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
         CNT_LAUNCHED();
         // every system is live here: Scal is not initialised yet, so zero the done flags first
         CNT_CUDA(cudaMemsetAsync(d_scal, 0, sizeof(Scal) * NSYS, st));
+        k_seg_sum_small<<<gseg_small, 256, 0, st>>>(c);
+        CNT_LAUNCHED();
         k_seg_sum<<<gseg, 256, 0, st>>>(c);
         CNT_LAUNCHED();
         k_init_z<<<(unsigned)nt, TILE, 0, st>>>(c);
@@ -438,6 +463,8 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
             CNT_LAUNCHED();
         } else {
             k_update_r<<<(unsigned)nt, TILE, 0, st>>>(c);
+            CNT_LAUNCHED();
+            k_seg_sum_small<<<gseg_small, 256, 0, st>>>(c);
             CNT_LAUNCHED();
             k_seg_sum<<<gseg, 256, 0, st>>>(c);
             CNT_LAUNCHED();
@@ -479,7 +506,7 @@ extern "C" int cnt_pcg_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_ne
     while (!h_alldone && done_iters < maxit) {
         if (use_graph) {
             cudaError_t e = cudaGraphLaunch(gexec, st);
-            cnt::count_launch((two_level ? 7 : 5) * check_every);
+            cnt::count_launch((two_level ? 8 : 5) * check_every);
             if (e != cudaSuccess) {
                 cnt::set_error("cudaGraphLaunch: %s", cudaGetErrorString(e));
                 rc = CNT_ECUDA;

@@ -393,11 +393,11 @@ class Engine(object):
         i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
         t = dict(agg_of_row=i32(n), mem=i32(n), seg_start=i32(cap_seg), seg_count=i32(cap_seg), seg_agg=i32(cap_seg),
                  seg_sys=i32(cap_seg), agg_seg0=i32(n // 2 + 2), sys_seg=i32(2 * nsys),
-                 row_q=i32(2 * n if chunk_C else 1), cta_seg_off=i32(nsys * chunk_C + 1),
+                 row_q=i32(2 * n), cta_seg_off=i32(nsys * chunk_C + 1),
                  cta_seg=i32(4 * (cap_seg + nsys * chunk_C) if chunk_C else 1),
                  cta_agg_off=i32(nsys * chunk_C + 1), cta_agg=i32(cap_seg if chunk_C else 1),
                  row_slot=i32(n if chunk_C else 1), seg_home=i32(cap_seg if chunk_C else 1),
-                 row_einv=torch.empty(n if chunk_C else 1, dtype=torch.float64, device=self.device),
+                 row_einv=torch.empty(max(n, 1), dtype=torch.float64, device=self.device),
                  agg_einv=torch.empty(n // 2 + 2, dtype=torch.float64, device=self.device))
         ws = self._ws(lib.cnt_pcg_aggregate_workspace_bytes(nsys, NS, b.R))
         nagg, nseg = C.c_int64(0), C.c_int64(0)
