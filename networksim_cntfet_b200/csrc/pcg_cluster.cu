@@ -838,7 +838,7 @@ static int cluster_size_for(int64_t max_rows, int cap) {
     int C = pick_cluster((int)max_rows, cap);
     if (const char *e = getenv("CNT_CLUSTER_SIZE")) {
         int c = atoi(e);
-        if (c >= C && c <= MAXC && (c & (c - 1)) == 0) C = c;
+        if (c >= 1 && c <= MAXC && (int64_t)c * cap >= max_rows) C = c;     // any size that holds the rows
     }
     return C;
 }
@@ -850,7 +850,7 @@ extern "C" int cnt_pcg_cluster_active(int C) {
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     int n = 0;
-    if (C < 1 || C > MAXC || (C & (C - 1))) return 0;
+    if (C < 1 || C > MAXC) return 0;
     if (launch_config(k_pcg_cluster2<true>, SMEM2_BYTES, C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
     return n;
 }
