@@ -578,27 +578,43 @@ class Engine(object):
         return out
 
     def measure_fullnet(self, b, onoffmap=1, element=None, rtol=1e-15, maxit=2000000, check_every=250,
-                        want_fields=False):
+                        want_fields=False, slab_shard=None):
         """Batched body of measure_perc.measure_fullnet (measure_perc.py:140-203) for a prepared
-        batch: returns a dict of host numpy arrays, one entry per network."""
+        batch: returns a dict of host numpy arrays, one entry per network.
+        slab_shard=(rank, world): solve only the gate configurations q with q % world == rank (the
+        others are left zero) -- used to spread ONE large network over several GPUs: every rank
+        builds the same network from the same seed and the currents are summed afterwards."""
         from .elements import LinExpTransistor
         element = element or LinExpTransistor
         if b.R is None:
             self.prepare(b)
         gates = self.fullnet_gates(b)
-        res = self.solve_gates(b, [g for _, g in gates], onoffmap, element, rtol, maxit, check_every, want_fields)
-        self.sync()
+        mine = list(range(len(gates)))
+        if slab_shard is not None:
+            mine = [q for q in mine if q % slab_shard[1] == slab_shard[0]]
         st = b.h_stats
-        isrc = res["isrc"].cpu().numpy()          # [4, B, 3]
         perc = st[:, _lib.STAT_PERCOLATING].astype(bool)
+        ng = len(gates)
+        isrc = np.zeros((ng, b.B, 3))
+        iters = np.zeros((ng, b.B), dtype=np.int32)
+        relres = np.zeros((ng, b.B))
+        status = np.zeros((ng, b.B), dtype=np.int32)
+        res = None
+        if mine:
+            res = self.solve_gates(b, [gates[q][1] for q in mine], onoffmap, element, rtol, maxit, check_every,
+                                   want_fields)
+            self.sync()
+            isrc[mine] = res["isrc"].cpu().numpy()
+            iters[mine] = res["iters"].cpu().numpy()
+            relres[mine] = res["relres"].cpu().numpy()
+            status[mine] = res["status"].cpu().numpy()
         cur = np.where(perc[None, :], isrc[:, :, 2], 0.0)     # power form (see currents.cu)
         out = dict(percolating=perc, nclust=st[:, _lib.STAT_NCLUST_REF].copy(),
                    maxclust=st[:, _lib.STAT_MAXCLUST_REF].copy(),
                    nclust_true=st[:, _lib.STAT_NCLUST_TRUE].copy(), maxclust_true=st[:, _lib.STAT_MAXCLUST_TRUE].copy(),
                    ncomp=st[:, _lib.STAT_NCOMP].copy(), ecomp=st[:, _lib.STAT_ECOMP].copy(),
                    ion=cur[0], ioff_back=cur[1], ioff_total=cur[2], ioff_partial=cur[3],
-                   isrc_all=isrc, iters=res["iters"].cpu().numpy(), relres=res["relres"].cpu().numpy(),
-                   status=res["status"].cpu().numpy(), ntests=b.ntests.cpu().numpy(),
+                   isrc_all=isrc, iters=iters, relres=relres, status=status, ntests=b.ntests.cpu().numpy(),
                    njunctions=np.diff(b.joff.cpu().numpy()))
         if want_fields:
             out["fields"] = res

@@ -212,6 +212,30 @@ def measure_fullnet(n, scaling, l='exp', save=False, seed=0, onoffmap=1, v=False
     return data
 
 
+def measure_fullnet_distributed(n, scaling, seed, onoffmap=1, element=LinExpTransistor, l='exp', engine=None):
+    """ONE (large) network on all ranks of an initialised torch.distributed job: every rank
+    regenerates the network from `seed` (counter-based RNG: identical sticks, junctions, labels and
+    CSR pattern everywhere, no exchange), solves the gate configurations q with q % world == rank,
+    and one small all-reduce sums the per-configuration currents.  Returns measure_fullnet's rows on
+    every rank.  (The reference has no way to spread one network over several workers.)"""
+    import torch
+    import torch.distributed as dist
+    eng = engine or get_engine()
+    rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
+    b = eng.generate([int(n)], scaling, seeds=[int(seed)], l=l)
+    res = eng.measure_fullnet(b, onoffmap=onoffmap, element=element, slab_shard=(rank, world))
+    cur = torch.as_tensor(np.stack([res["ion"], res["ioff_back"], res["ioff_total"], res["ioff_partial"]]),
+                          dtype=torch.float64, device=eng.device)
+    its = torch.as_tensor(res["iters"].astype(np.float64), device=eng.device)
+    if world > 1:
+        dist.all_reduce(cur)
+        dist.all_reduce(its)
+    cur = cur.cpu().numpy()
+    res.update(ion=cur[0], ioff_back=cur[1], ioff_total=cur[2], ioff_partial=cur[3], iters=its.cpu().numpy().astype(np.int32))
+    df = _rows_from_ensemble(res, [int(n)], scaling, np.asarray([seed], dtype=np.uint64), onoffmap)
+    return df, res
+
+
 def _shard(number):
     """contiguous shard of range(number) for this rank when torch.distributed is initialised"""
     try:

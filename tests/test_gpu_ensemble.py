@@ -69,3 +69,23 @@ def test_full_size_variants(engine, n, onoffmap, element):
     assert m["njunctions"] == res["njunctions"][0] and m["ntests"] == res["ntests"][0]
     for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
         assert abs(res[key][0] - m[key]) <= 1e-9 * m[key], (key, res[key][0], m[key], res["iters"][:, 0])
+
+
+def test_gate_configuration_sharding(engine):
+    """one network spread over ranks by gate configuration (measure_perc.measure_fullnet_distributed):
+    the shards of a 2-rank split add up to the unsharded result bit for bit"""
+    full = engine.measure_fullnet(engine.generate([20000], 45.0, seeds=[11]), onoffmap=1)
+    parts = [engine.measure_fullnet(engine.generate([20000], 45.0, seeds=[11]), onoffmap=1, slab_shard=(r, 2))
+             for r in range(2)]
+    assert full["percolating"][0]
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert parts[0][k][0] + parts[1][k][0] == full[k][0]
+        assert (parts[0][k][0] == 0.0) != (parts[1][k][0] == 0.0)          # each configuration solved exactly once
+    assert np.array_equal(parts[0]["iters"] + parts[1]["iters"], full["iters"])
+    # without torch.distributed the distributed entry point degenerates to the plain one
+    import networksim_cntfet_b200 as pkg
+    from networksim_cntfet_b200 import measure_perc
+    pkg.set_engine(engine)
+    df, res = measure_perc.measure_fullnet_distributed(20000, 45.0, seed=11)
+    assert res["ion"][0] == full["ion"][0] and df.ioff.tolist() == [full["ioff_back"][0], full["ioff_total"][0],
+                                                                   full["ioff_partial"][0]]

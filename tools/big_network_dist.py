@@ -1,0 +1,21 @@
+#!/usr/bin/env python3
+"""One large network spread over the ranks of a torchrun job (gate configurations sharded)."""
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch, torch.distributed as dist
+local = int(os.environ.get("LOCAL_RANK", "0")); torch.cuda.set_device(local)
+os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+import networksim_cntfet_b200 as pkg
+from networksim_cntfet_b200 import measure_perc
+from networksim_cntfet_b200.engine import Engine
+eng = pkg.set_engine(Engine("cuda:%d" % local))
+side = float(os.environ.get("BIG_SIDE", "300")); n = int(10 * side * side)
+for rep in range(2):
+    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    df, res = measure_perc.measure_fullnet_distributed(n, side, seed=5)
+    torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
+    if dist.get_rank() == 0:
+        print("rep%d world %d: %gx%g um n=%d in %.2f s; ion %.12e ioff %s iters %s" % (rep, dist.get_world_size(), side, side, n, dt,
+              res["ion"][0], df.ioff.tolist(), res["iters"][:, 0].tolist()), flush=True)
+dist.destroy_process_group()

@@ -1,8 +1,6 @@
 #!/bin/bash
-# N-GPU run of the bench (torchrun, NCCL all-gather of the statistics rows)
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
 N=${NGPU:-2}
-nvidia-smi -L > gpurun_out/gpus.txt
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_${N}gpu.log 2> gpurun_out/bench_${N}gpu.err; echo "exit $?" >> gpurun_out/bench_${N}gpu.err
-wc -l gpurun_out/gpus.txt; cat gpurun_out/bench_${N}gpu.log; tail -3 gpurun_out/bench_${N}gpu.err
+BIG_SIDE=${BIG_SIDE:-300} timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 tools/big_network_dist.py > gpurun_out/big_dist.log 2> gpurun_out/big_dist.err; echo "exit $?" >> gpurun_out/big_dist.err
+cat gpurun_out/big_dist.log; grep -v "^W\|^\*\|OMP_NUM" gpurun_out/big_dist.err | tail -5
