@@ -124,6 +124,21 @@ int cnt_label_clusters(int B, const int32_t *soff, const int32_t *joff, int64_t 
                        int32_t *label, int32_t *stats, void *ws, int64_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (3b) optional exact reduction before assembly: dangling sticks (left with one junction once
+ *     their own dangling neighbours are removed) carry no current, so they are peeled off the
+ *     percolating component until its 2-core + the two electrodes remain.  The reference keeps
+ *     them in the matrix (cnet.py:104-131); the solution on the remaining sticks is the same and
+ *     a peeled stick takes the voltage of the stick it hangs on (cnt_currents, attach[]).
+ *     alive[S] u8: 1 = stays an MNA node (electrodes always); attach[S]: global stick index of
+ *     the attachment point of a peeled stick, -1 otherwise.  h_rounds (host, optional): peeling
+ *     rounds run.  Synchronises the stream.
+ * ------------------------------------------------------------------------------------- */
+int64_t cnt_prune_workspace_bytes(int64_t n_sticks_total);
+int cnt_prune_leaves(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
+                     const int32_t *stick1, const int32_t *stick2, const int32_t *label, const int32_t *stats,
+                     uint8_t *alive, int32_t *attach, int32_t *h_rounds, void *ws, int64_t ws_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * (4) MNA assembly -- replaces populate_graph (netsim.py:192-195), update_conductivity,
  *     make_G, make_A, make_z (cnet.py:99-131) in the reduced SPD form
  *         L_UU V_U = 0.1 * g_{U,source}
@@ -143,6 +158,7 @@ int cnt_label_clusters(int B, const int32_t *soff, const int32_t *joff, int64_t 
  * ------------------------------------------------------------------------------------- */
 int64_t cnt_assemble_workspace_bytes(int64_t n_sticks_total);
 int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
+                      const uint8_t *alive /* from cnt_prune_leaves, or NULL = whole component */,
                       int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream);
 /* optional, between _rows and _pattern_count: renumber every network's unknown rows in Z-order
  * (Morton code) of the stick centres so that neighbouring sticks get neighbouring rows (SpMV
@@ -250,8 +266,9 @@ int64_t cnt_pcg_cluster_max_rows(void);
 /* debug: device buffer [grid][16] of int64 that receives per-phase cycle sums (thread 0 of every CTA) of the
  * following cluster launches; NULL switches the instrumentation off (default) */
 void cnt_pcg_cluster_set_phase_buffer(long long *buf);
-/* cluster size (CTAs) the cluster solver uses for a batch whose largest system has max_rows rows */
-int cnt_pcg_cluster_size(int64_t max_rows);
+/* cluster size (CTAs) for a batch whose largest system has max_rows rows and max_nnz off-diagonal
+ * entries (0 = unknown: rows only); pass it as cluster_C below and as chunk_C to cnt_pcg_aggregates */
+int cnt_pcg_cluster_size(int64_t max_rows, int64_t max_nnz);
 /* clusters of C CTAs (C = 1,2,4,8,16) that can be resident at once on the current device */
 int cnt_pcg_cluster_active(int C);
 int64_t cnt_pcg_cluster_workspace_bytes(int NSYS, int NSLAB, int64_t R);
@@ -263,6 +280,7 @@ int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, 
                           double rtol, int maxit,
                           int32_t *iters, double *relres, int32_t *status,
                           const cnt_aggregates *agg /* NULL = plain Jacobi; needs cls/gneg */,
+                          int cluster_C /* CTAs per cluster, 0 = smallest that holds the rows */,
                           void *ws, int64_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -275,8 +293,8 @@ int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, 
  * ------------------------------------------------------------------------------------- */
 int cnt_currents(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
                  const int32_t *stick1, const int32_t *stick2, const int32_t *label, const int32_t *stats,
-                 const int32_t *urow, const double *g, const double *x,
-                 double *V, double *I, double *isrc, void *stream);
+                 const int32_t *urow, const int32_t *attach /* from cnt_prune_leaves, or NULL */,
+                 const double *g, const double *x, double *V, double *I, double *isrc, void *stream);
 
 #ifdef __cplusplus
 }

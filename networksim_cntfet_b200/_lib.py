@@ -32,7 +32,9 @@ PROTOTYPES = {
     "cnt_cluster_workspace_bytes": (i64, [i64]),
     "cnt_label_clusters": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_workspace_bytes": (i64, [i64]),
-    "cnt_assemble_rows": (i32, [i32, vp, i64, vp, vp, vp, vp, vp, i64, vp]),
+    "cnt_prune_workspace_bytes": (i64, [i64]),
+    "cnt_prune_leaves": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "cnt_assemble_rows": (i32, [i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_reorder_workspace_bytes": (i64, [i64, i32]),
     "cnt_assemble_reorder": (i32, [i32, I32P, i64, i64, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_pattern_count": (i32, [i32, vp, vp, i64, vp, vp, vp, i64, vp, vp]),
@@ -48,10 +50,10 @@ PROTOTYPES = {
     "cnt_pcg_cluster_max_rows": (i64, []),
     "cnt_pcg_cluster_set_phase_buffer": (None, [vp]),
     "cnt_pcg_cluster_active": (i32, [i32]),
-    "cnt_pcg_cluster_size": (i32, [i64]),
+    "cnt_pcg_cluster_size": (i32, [i64, i64]),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
-    "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, vp, i64, vp]),
-    "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i32, vp, i64, vp]),
+    "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 # entry points that may be absent from an older build of the library (checked by tests
 # against the header, never silently replaced)

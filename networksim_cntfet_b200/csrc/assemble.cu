@@ -11,12 +11,15 @@
 namespace {
 
 __global__ void k_row_flags(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ label,
-                            const int32_t *__restrict__ stats, int32_t *__restrict__ flag) {
+                            const int32_t *__restrict__ stats, const uint8_t *__restrict__ alive,
+                            int32_t *__restrict__ flag) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int b = cnt::find_segment(soff, B, (int)s);
     int i = (int)s - soff[b];
-    flag[s] = (stats[(int64_t)b * CNT_NSTAT + CNT_STAT_PERCOLATING] && i >= 2 && label[s] == 0) ? 1 : 0;
+    bool in = stats[(int64_t)b * CNT_NSTAT + CNT_STAT_PERCOLATING] && i >= 2 && label[s] == 0;
+    if (alive) in = in && alive[s];     // dangling sticks pruned by cnt_prune_leaves
+    flag[s] = in ? 1 : 0;
 }
 
 __global__ void k_rows_finish(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ flag,
@@ -134,7 +137,7 @@ extern "C" int64_t cnt_assemble_workspace_bytes(int64_t S) {
 }
 
 extern "C" int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
-                                 int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream) {
+                                 const uint8_t *alive, int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && soff && label && stats && urow && roff && ws && S >= B);
     cnt::Workspace w(ws, ws_bytes);
@@ -146,7 +149,7 @@ extern "C" int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const in
         cnt::set_error("assemble workspace too small");
         return CNT_ECAPACITY;
     }
-    k_row_flags<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, label, stats, flag);
+    k_row_flags<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, label, stats, alive, flag);
     CNT_LAUNCHED();
     int rc = cnt_exclusive_scan_i32(flag, scan, S, 1, sws, sb, stream);
     if (rc) return rc;

@@ -834,8 +834,11 @@ static int launch_config(kernel_t kern, size_t smem, int C, cudaLaunchConfig_t *
     return CNT_OK;
 }
 
-static int cluster_size_for(int64_t max_rows, int cap) {
+// smallest power-of-two cluster whose CTAs hold max_rows rows and (v2) the packed entries of a
+// system with max_nnz off-diagonal entries (15 % allowance for group padding and uneven chunks)
+static int cluster_size_for(int64_t max_rows, int cap, int64_t max_nnz = 0) {
     int C = pick_cluster((int)max_rows, cap);
+    while (C < MAXC && (double)C * ECAP < 1.15 * (double)max_nnz) C <<= 1;
     if (const char *e = getenv("CNT_CLUSTER_SIZE")) {
         int c = atoi(e);
         if (c >= 1 && c <= MAXC && (int64_t)c * cap >= max_rows) C = c;     // any size that holds the rows
@@ -843,7 +846,9 @@ static int cluster_size_for(int64_t max_rows, int cap) {
     return C;
 }
 // cluster size used for a batch whose largest system has max_rows rows (compressed kernel)
-extern "C" int cnt_pcg_cluster_size(int64_t max_rows) { return cluster_size_for(max_rows, CAP2); }
+extern "C" int cnt_pcg_cluster_size(int64_t max_rows, int64_t max_nnz) {
+    return cluster_size_for(max_rows, CAP2, max_nnz);
+}
 
 // number of clusters of C CTAs that can be resident at once on the current device (0 on error)
 extern "C" int cnt_pcg_cluster_active(int C) {
@@ -860,8 +865,8 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
                                      const int32_t *col, const double *val, const uint8_t *cls, const double *gneg,
                                      const double *diag, const double *rhs,
                                      double *x, double rtol, int maxit, int32_t *iters, double *relres,
-                                     int32_t *status, const cnt_aggregates *agg, void *ws, int64_t ws_bytes,
-                                     void *stream) {
+                                     int32_t *status, const cnt_aggregates *agg, int cluster_C, void *ws,
+                                     int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && R >= 0 && NNZ >= 0 && iters &&
                   relres && status && ws);
@@ -901,6 +906,10 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     CNT_CUDA(cudaMemsetAsync(assert_flag, 0, sizeof(int), st));
 
     int C = cluster_size_for(max_rows, cap);
+    if (cluster_C > 0) {
+        CNT_CHECK_ARG(cluster_C <= MAXC && (int64_t)cluster_C * cap >= max_rows);
+        C = cluster_C;
+    }
     if (two && agg->chunk_C != C) {
         cnt::set_error("aggregate tables were built for cluster size %d, the batch needs %d", agg->chunk_C, C);
         return CNT_EINVAL;

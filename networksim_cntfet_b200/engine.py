@@ -128,6 +128,7 @@ class Engine(object):
         self.cluster_compressed = True  # cluster kernel keeps its matrix slice in shared memory (class codes)
         self.last_solver = None
         self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
+        self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
 
     # ------------------------------------------------------------------ helpers
     @contextlib.contextmanager
@@ -313,8 +314,19 @@ class Engine(object):
             ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
             b.urow = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.roff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
-            check(lib.cnt_assemble_rows(b.B, _p(b.soff), b.S, _p(b.label), _p(b.stats), _p(b.urow), _p(b.roff),
-                                        _p(ws), ws.numel(), self.stream_ptr))
+            b.alive = b.attach = None
+            if self.prune and b.S > 0:
+                pws = self._ws(lib.cnt_prune_workspace_bytes(b.S))
+                b.alive = torch.empty(b.S, dtype=torch.uint8, device=self.device)
+                b.attach = torch.empty(b.S, dtype=torch.int32, device=self.device)
+                rounds = C.c_int32(0)
+                check(lib.cnt_prune_leaves(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2),
+                                           _p(b.label), _p(b.stats), _p(b.alive), _p(b.attach), C.byref(rounds),
+                                           _p(pws), pws.numel(), self.stream_ptr))
+                b.prune_rounds = rounds.value
+            ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
+            check(lib.cnt_assemble_rows(b.B, _p(b.soff), b.S, _p(b.label), _p(b.stats), _p(b.alive), _p(b.urow),
+                                        _p(b.roff), _p(ws), ws.numel(), self.stream_ptr))
             b.h_roff = [int(v) for v in b.roff.cpu().tolist()]          # D2H sync (B+1 ints)
             b.c_roff = _lib.i32_array(b.h_roff)
             b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()
@@ -330,7 +342,10 @@ class Engine(object):
             sws = self._ws(lib.cnt_scan_workspace_bytes(R + 1))
             b.rowptr = torch.empty(R + 1, dtype=torch.int32, device=self.device)
             check(lib.cnt_exclusive_scan_i32(_p(rowcnt), _p(b.rowptr), R, 1, _p(sws), sws.numel(), self.stream_ptr))
-            b.NNZ = int(b.rowptr[R].item())                              # D2H sync (1 int)
+            # off-diagonal entries up to every network's first row: D2H sync (B+1 ints)
+            b.h_nzoff = [int(v) for v in b.rowptr[torch.as_tensor(b.h_roff, device=self.device,
+                                                                  dtype=torch.long)].cpu().tolist()]
+            b.NNZ = b.h_nzoff[-1]
             n = max(b.NNZ, 1)
             b.col = torch.empty(n, dtype=torch.int32, device=self.device)
             b.nz_eid = torch.empty(n, dtype=torch.int32, device=self.device)
@@ -453,10 +468,14 @@ class Engine(object):
                 stt = torch.zeros(nsys, dtype=torch.int32, device=self.device)
                 max_rows = max(b.h_roff[n + 1] - b.h_roff[n] for n in nets)
                 precond = self.precond if precond is None else precond
-                if method == "auto":
+                auto = method == "auto"
+                if auto:
                     method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
                 compressed = method == "cluster" and self.cluster_compressed and "cls" in sysm
-                chunk_C = lib.cnt_pcg_cluster_size(max_rows) if compressed else 0
+                max_nnz = max(b.h_nzoff[n + 1] - b.h_nzoff[n] for n in nets)
+                chunk_C = lib.cnt_pcg_cluster_size(max_rows, max_nnz) if compressed else 0
+                if auto and compressed and lib.cnt_pcg_cluster_active(chunk_C) <= 0:
+                    method, compressed, chunk_C = "flat", False, 0      # cluster launch not possible here
                 agg = self._aggregates(b, sysm, sys_net, sys_slab, chunk_C) if precond == "twolevel" else None
                 self.last_solver = method
                 if method == "cluster":
@@ -469,7 +488,7 @@ class Engine(object):
                                                     _p(it), _p(rr), _p(stt),
                                                     C.byref(agg[0]) if (agg and self.cluster_compressed and
                                                                         "cls" in sysm) else None,
-                                                    _p(ws), ws.numel(), self.stream_ptr))
+                                                    chunk_C, _p(ws), ws.numel(), self.stream_ptr))
                     self._cluster_fallback(b, sysm, x, sys_net, sys_slab, it, rr, stt, rtol, maxit, check_every)
                 elif method == "flat":
                     ws = self._ws(lib.cnt_pcg_workspace_bytes(nsys, NS, R))
@@ -522,7 +541,8 @@ class Engine(object):
             I = torch.empty(max(b.J, 1), dtype=torch.float64, device=self.device)
             isrc = torch.zeros((b.B, 3), dtype=torch.float64, device=self.device)
             check(lib.cnt_currents(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2), _p(b.label),
-                                   _p(b.stats), _p(b.urow), _p(g), _p(x), _p(V), _p(I), _p(isrc), self.stream_ptr))
+                                   _p(b.stats), _p(b.urow), _p(getattr(b, "attach", None)), _p(g), _p(x), _p(V), _p(I),
+                                   _p(isrc), self.stream_ptr))
         return V, I, isrc
 
     # ------------------------------------------------------------------ measure_fullnet, batched
@@ -697,6 +717,4 @@ class Engine(object):
 
     def nnz_per_network(self, b):
         """off-diagonal non-zeros of every network's reduced matrix (for traffic accounting)"""
-        rp = b.rowptr.cpu().numpy()
-        r = np.asarray(b.h_roff)
-        return rp[r[1:]] - rp[r[:-1]]
+        return np.diff(np.asarray(b.h_nzoff))

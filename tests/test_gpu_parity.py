@@ -106,7 +106,11 @@ def test_assembly_matches_oracle(engine, name):
     from networksim_cntfet_b200.engine import GateState
     from networksim_cntfet_b200.elements import conductance_table
     g = load_golden(name)
-    b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    engine.prune = False           # the reference's matrix: every stick of the component is a node
+    try:
+        b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    finally:
+        engine.prune = True
     gs = GateState(engine, b).set_global(10)
     tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
     sysm = engine.assemble_values(b, [gs], [tab])
@@ -141,6 +145,79 @@ def test_assembly_matches_oracle(engine, name):
     assert np.array_equal(offd.data, Aoff.data)                           # off-diagonals bit-exact
     assert np.array_equal(rhs, r["rhs"])
     assert np.array_equal(b.row_stick.cpu().numpy()[:R], r["nodes_u"])
+
+
+def _two_core(n, s1, s2, comp):
+    """numpy peeling: sticks of the component left after removing dangling sticks repeatedly
+    (electrodes 0 and 1 are never removed); returns (alive mask, attachment stick or -1)"""
+    alive = comp.copy()
+    attach = np.full(n, -1, np.int64)
+    parent = np.full(n, -1, np.int64)
+    while True:
+        m = alive[s1] & alive[s2]
+        deg = np.bincount(np.r_[s1[m], s2[m]], minlength=n)
+        leaf = alive & (deg == 1) & (np.arange(n) >= 2)
+        if not leaf.any():
+            break
+        for a, c in ((s1[m], s2[m]), (s2[m], s1[m])):
+            k = leaf[a]
+            parent[a[k]] = c[k]
+        # two leaves joined to each other cannot occur inside a percolating component
+        alive &= ~leaf
+    for s in np.nonzero(parent >= 0)[0]:
+        p = parent[s]
+        while not alive[p]:
+            p = parent[p]
+        attach[s] = p
+    return alive, attach
+
+
+@pytest.mark.parametrize("name", PERC)
+def test_pruned_assembly(engine, name):
+    """cnt_prune_leaves: the unknowns are the 2-core of the percolating component, the matrix is
+    the oracle's matrix restricted to them with the dangling junctions' conductance taken off the
+    diagonal, and pruned sticks are attached to the stick they hang on."""
+    import scipy.sparse as sp
+    from networksim_cntfet_b200.engine import GateState
+    from networksim_cntfet_b200.elements import conductance_table
+    g = load_golden(name)
+    assert engine.prune
+    b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    gs = GateState(engine, b).set_global(10)
+    tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
+    sysm = engine.assemble_values(b, [gs], [tab])
+    engine.sync()
+    cond, r = _oracle_fields(g, "_back", "back", 10.0, refine=0)
+    n = len(g["xc"])
+    comp = g["label"] == 0
+    alive, attach = _two_core(n, g["stick1"].astype(np.int64), g["stick2"].astype(np.int64), comp)
+    assert np.array_equal(b.alive.cpu().numpy().astype(bool), alive)
+    assert np.array_equal(b.attach.cpu().numpy(), attach)
+    keep = alive[r["nodes_u"]]
+    R = int(keep.sum())
+    assert b.R == R and R <= r["A"].shape[0]
+    row_stick = b.row_stick.cpu().numpy()[:R]
+    nodes = r["nodes_u"][keep]
+    assert np.array_equal(np.sort(row_stick), nodes)
+    perm = np.searchsorted(nodes, row_stick)
+    A = r["A"].tocsr()[keep][:, keep].tocsr()[perm][:, perm].tocsr()
+    offd = sp.csr_matrix((sysm["val"][0].cpu().numpy()[:b.NNZ], b.col.cpu().numpy()[:b.NNZ], b.rowptr.cpu().numpy()),
+                         shape=(R, R))
+    offd.sort_indices()
+    Aoff = (A - sp.diags(A.diagonal())).tocsr()
+    Aoff.eliminate_zeros()
+    Aoff.sort_indices()
+    assert np.array_equal(offd.indptr, Aoff.indptr) and np.array_equal(offd.indices, Aoff.indices)
+    assert np.array_equal(offd.data, Aoff.data)
+    # diagonal: the full one minus the conductance of the junctions to pruned sticks
+    s1, s2 = g["stick1"].astype(np.int64), g["stick2"].astype(np.int64)
+    dang = comp[s1] & comp[s2] & (alive[s1] != alive[s2])
+    off = np.zeros(n)
+    np.add.at(off, np.where(alive[s1[dang]], s1[dang], s2[dang]), cond[dang])
+    want = A.diagonal() - off[row_stick]
+    diag = sysm["diag"][0].cpu().numpy()[:R]
+    assert np.all(np.abs(diag - want) <= 4e-16 * np.abs(A.diagonal()).max())
+    assert np.array_equal(sysm["rhs"][0].cpu().numpy()[:R], r["rhs"][keep][perm])
 
 
 @pytest.mark.parametrize("name", PERC)

@@ -153,6 +153,7 @@ def test_cluster_overflow_falls_back_to_flat(solver):
     """a dense network (38 junctions per stick) does not fit the CTA's shared-memory slice:
     the cluster kernel reports status 3 and the engine re-solves with the multi-launch kernels"""
     solver.solver = "cluster"
+    os.environ["CNT_CLUSTER_SIZE"] = "2"      # holds the rows but not the entries
     b = solver.generate([6000], 10.0, seed=9, l=1.0)
     res = solver.measure_fullnet(b, onoffmap=1)
     assert solver.last_solver == "cluster+flat"
