@@ -60,9 +60,7 @@ struct CArgs {
 };
 
 struct Shared {
-    double red[2][4];      // [phase parity][value]: this CTA's partial sums, read by cluster peers
-    double bcast[4];       // cluster-wide sums, broadcast inside the CTA
-    double warp[32];       // block reduction scratch
+    double red[2][4][16];  // [phase parity][value][CTA rank]: partial sums pushed by the cluster peers
     int next;              // next system (valid in CTA rank 0)
     int nhalo;             // v2: halo references collected by this CTA
     int ovf;               // v2: slice / halo did not fit
@@ -84,57 +82,46 @@ struct Shared {
         }                                                          \
     } while (0)
 
-// deterministic block sums of up to 3 values at once; results valid in thread 0
+// cluster-wide sum of N values, bit-identical in every thread of every CTA.
+// Warp sums -> warp 0 adds the CTA's 32 warp partials -> lanes 0..C-1 PUSH the CTA's partial
+// into slot [rank] of every peer's red[][] through DSMEM (remote stores retire asynchronously,
+// the cluster barrier's release/acquire makes them visible) -> after the barrier every warp adds
+// the C partials from its OWN shared memory in a fixed tree over ranks.  No remote load and no
+// CTA barrier after the cluster barrier: 2 % faster per iteration than pulling the partials.
+// `slot` alternates between consecutive reductions: a peer may already be pushing the next
+// reduction's partials while this CTA still reads the current ones.  scratch[] needs no guard
+// barrier: its readers (warp 0) are done before this reduction's cluster barrier, its next
+// writers start after it.
 template <int N>
-__device__ __forceinline__ void block_sum_n(double (&v)[N], double *scratch /* 32*N */) {
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+__device__ __forceinline__ void cluster_sum_n(cg::cluster_group &cluster, Shared *sh, int slot, double (&v)[N],
+                                                 double *scratch /* 32*N */, int C) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
 #pragma unroll
     for (int k = 0; k < N; k++) v[k] = cnt::warp_sum(v[k]);
-    __syncthreads();
     if (lane == 0) {
 #pragma unroll
         for (int k = 0; k < N; k++) scratch[k * 32 + w] = v[k];
     }
     __syncthreads();
     if (w == 0) {
+        const int crank = (int)cluster.block_rank();
+        Shared *peer = lane < C ? cluster.map_shared_rank(sh, lane) : sh;
 #pragma unroll
         for (int k = 0; k < N; k++) {
             double t = lane < (CT >> 5) ? scratch[k * 32 + lane] : 0.0;
-            v[k] = cnt::warp_sum(t);
+            t = cnt::warp_sum(t);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (lane < C) peer->red[slot][k][crank] = t;
         }
-    }
-}
-
-// cluster-wide sum of N values: every CTA publishes its partials in sh->red[slot], the cluster
-// barrier makes them visible, warp 0 of every CTA reads all C partials through DSMEM and adds
-// them in rank order.  Every CTA obtains bit-identical results.
-template <int N>
-__device__ __forceinline__ void cluster_sum_n(cg::cluster_group &cluster, Shared *sh, int slot, double (&v)[N],
-                                              double *scratch, int C) {
-    block_sum_n<N>(v, scratch);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < N; k++) sh->red[slot][k] = v[k];
     }
     cluster.sync();
-    if (threadIdx.x < 32) {
-        int lane = threadIdx.x;
 #pragma unroll
-        for (int k = 0; k < N; k++) {
-            double t = 0.0;
-            if (lane < C) {
-                const Shared *peer = cluster.map_shared_rank(sh, lane);
-                t = peer->red[slot][k];
-            }
-            // fixed-order tree over ranks 0..C-1 (C <= 16)
+    for (int k = 0; k < N; k++) {
+        double t = lane < C ? sh->red[slot][k][lane] : 0.0;
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-            if (lane == 0) sh->bcast[k] = t;
-        }
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        v[k] = __shfl_sync(0xffffffffu, t, 0);
     }
-    __syncthreads();
-#pragma unroll
-    for (int k = 0; k < N; k++) v[k] = sh->bcast[k];
 }
 
 __global__ void __launch_bounds__(CT, 1) k_pcg_cluster(CArgs a) {
@@ -348,61 +335,106 @@ constexpr int SORTN = 8192;             // power of two >= CAP2 (bitonic sort of
 constexpr int LCAP = 512;               // two-level: local segments / local aggregates per CTA
 constexpr int MCAP = CAP2;              // two-level: aggregated rows per CTA (all of them may be aggregated)
 
-// two-level phases from shared memory: one warp per local segment sums its members of r in a
-// fixed order; after the cluster barrier one thread per local aggregate combines the aggregate's
-// segment sums (its own and other CTAs', in segment order) into the coarse value
-constexpr int SEG_SMALL = 8;     // segments up to this size are summed by one thread, larger ones by a warp
+// two-level phases from shared memory
 constexpr int RCAP = 512;        // two-level: segment references of the CTA's multi-segment aggregates
-__device__ __forceinline__ void smem_segment_sums(double *seg_loc, const double *r_s, const uint16_t *segm,
-                                                  const uint16_t *segoff, int nseg_loc) {
-    // small segments: one thread each, members added in list order
-    for (int sgi = threadIdx.x; sgi < nseg_loc; sgi += CT) {
-        int o0 = segoff[sgi], o1 = segoff[sgi + 1];
-        if (o1 - o0 <= SEG_SMALL) {
-            double acc = 0.0;
-            for (int q = o0; q < o1; q++) acc += r_s[segm[q]];
-            seg_loc[sgi] = acc;
-        }
+// ---- segment sums as a block-wide segmented reduction -------------------------------------
+// The CTA's segments are stored back to back in segm[0..M) (member rows, local indices).  Thread
+// t owns the K consecutive members t*K .. t*K+K-1 whatever segment they belong to, so every
+// thread does the same work for any distribution of segment sizes (a CTA holds a few hundred
+// segments of 2..256 rows).  meta (loop invariant, one register): index of the segment of the
+// thread's first member | K bits "member q is the last one of its segment" << 16.
+// Inside a thread: running sum, closed at every end flag.  Across threads: an open run (members
+// after the thread's last end flag, or all of them if it has none) is carried to the thread that
+// closes it by a segmented warp scan (shuffles, reset at threads that have an end flag) and one
+// more over the 32 warp aggregates.  Fixed summation tree -> deterministic.
+// returns the sum of the run that is open when the thread's first member starts
+__device__ __forceinline__ double block_open_run_carry(double trail, bool has_end, double *scratch /* 64 */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned R = __ballot_sync(0xffffffffu, has_end);
+    const unsigned below = R & (0xFFFFFFFFu >> (31 - lane));         // resets in lanes 0..lane
+    const int dist = below ? lane - (31 - __clz(below)) : lane;      // lanes that may be added from the left
+    double incl = trail;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (o <= dist) incl += up;
     }
-    // large segments: one warp each, lane-strided partial sums + fixed shuffle tree
-    const int lane = threadIdx.x & 31;
-    for (int sgi = threadIdx.x >> 5; sgi < nseg_loc; sgi += (CT >> 5)) {
-        int o0 = segoff[sgi], o1 = segoff[sgi + 1];
-        if (o1 - o0 > SEG_SMALL) {
-            double acc = 0.0;
-            for (int q = o0 + lane; q < o1; q += 32) acc += r_s[segm[q]];
-            acc = cnt::warp_sum(acc);
-            if (lane == 0) seg_loc[sgi] = acc;
-        }
+    double prev = __shfl_up_sync(0xffffffffu, incl, 1);              // open run at the end of lane-1
+    if (lane == 31) {
+        scratch[w] = incl;
+        scratch[32 + w] = R ? 1.0 : 0.0;
     }
+    __syncthreads();
+    // the same scan over the warp aggregates (every warp computes it; it needs lanes 0..w-1 only)
+    double aw = scratch[lane];
+    const unsigned RW = __ballot_sync(0xffffffffu, scratch[32 + lane] != 0.0);
+    const unsigned beloww = RW & (0xFFFFFFFFu >> (31 - lane));
+    const int distw = beloww ? lane - (31 - __clz(beloww)) : lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double up = __shfl_up_sync(0xffffffffu, aw, o);
+        if (o <= distw) aw += up;
+    }
+    double carry_w = __shfl_sync(0xffffffffu, aw, w > 0 ? w - 1 : 0);
+    if (w == 0) carry_w = 0.0;
+    double carry = lane > 0 ? prev : 0.0;
+    if ((R & ((1u << lane) - 1u)) == 0u) carry += carry_w;           // no end flag in lanes 0..lane-1
+    return carry;
 }
+
+template <int K>
+__device__ __forceinline__ void smem_segscan_sums(double *seg_loc, double *scratch, const double *r_s,
+                                                  const uint16_t *segm, int meta, int M) {
+    const int base = (int)threadIdx.x * K;
+    double v[K];
+#pragma unroll
+    for (int q = 0; q < K; q++) v[q] = base + q < M ? r_s[segm[base + q]] : 0.0;
+    const int ef = meta >> 16;
+    int sidx = meta & 0xFFFF;
+    double run = 0.0, first = 0.0;
+    bool got = false;
+#pragma unroll
+    for (int q = 0; q < K; q++) {
+        run += v[q];
+        if ((ef >> q) & 1) {
+            if (!got) { first = run; got = true; }
+            else seg_loc[sidx] = run;                                 // run opened and closed in this thread
+            if (got) sidx++;
+            run = 0.0;
+        }
+    }
+    const double carry = block_open_run_carry(run, ef != 0, scratch);
+    if (ef != 0) seg_loc[meta & 0xFFFF] = carry + first;
+}
+
 // coarse value of every local aggregate = 1/E * (sum of the aggregate's segment sums, in global
-// segment order).  Segment sums live in the shared memory of the CTA that owns the segment:
-// single-segment aggregates read their own CTA's array, multi-segment ones follow the reference
-// list built at setup (owner CTA, index) through DSMEM -- no global memory on this path.
+// segment order).  Segment sums live in the shared memory of the CTA that owns the segment.
+// Single-segment aggregates (the bulk) read their own CTA's array.  The references of the
+// multi-segment aggregates (owner CTA, index; stored back to back per aggregate) are pulled
+// through DSMEM by one thread each -- ONE round trip for the CTA -- and added per aggregate with
+// the same segmented block reduction as the segment sums.  ref_meta (one register): local
+// aggregate index | "last reference of its aggregate" << 15.
 __device__ __forceinline__ void smem_coarse_values(cg::cluster_group &cluster, double *seg_loc, const uint16_t *la_a,
                                                    const uint16_t *la_qn, const float *la_einv, const uint32_t *refs,
-                                                   double *c_loc, int nla) {
+                                                   double *scratch, double *c_loc, int nla, int nrefs, int ref_meta) {
+    double v = 0.0;
+    if ((int)threadIdx.x < nrefs) {
+        uint32_t ref = refs[threadIdx.x];
+        const double *home = cluster.map_shared_rank(seg_loc, ref >> 16);
+        v = home[ref & 0xFFFFu];
+    }
     for (int i = threadIdx.x; i < nla; i += CT)
         if (la_qn[i] == 1) c_loc[i] = seg_loc[la_a[i]] * (double)la_einv[i];
-    const int lane = threadIdx.x & 31;
-    for (int i = threadIdx.x >> 5; i < nla; i += (CT >> 5)) {
-        int qn = la_qn[i];
-        if (qn > 1) {
-            int r0 = la_a[i];
-            double S = 0.0;
-            for (int q = lane; q < qn; q += 32) {
-                uint32_t ref = refs[r0 + q];
-                const double *home = cluster.map_shared_rank(seg_loc, ref >> 16);
-                S += home[ref & 0xFFFFu];
-            }
-            S = cnt::warp_sum(S);
-            if (lane == 0) c_loc[i] = S * (double)la_einv[i];
-        }
+    const bool is_end = (int)threadIdx.x < nrefs && ((ref_meta >> 15) & 1);
+    const double carry = block_open_run_carry(is_end ? 0.0 : v, is_end, scratch);
+    if (is_end) {
+        int ai = ref_meta & 0x7FFF;
+        c_loc[ai] = (carry + v) * (double)la_einv[ai];
     }
 }
 
-template <bool TWO>
+// NR = row slots per thread (registers): 4 when every CTA's chunk has at most 4*CT rows, else 5
+template <bool TWO, int NR>
 __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -419,9 +451,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     int *gbase = iscr + 36;                                                     // CAP2 / 32
     uint16_t *slot_s = reinterpret_cast<uint16_t *>(gbase + CAP2 / 32);         // CAP2: row -> local aggregate
     // two-level tables of this CTA (shared memory only in the iteration)
-    double *c_loc = reinterpret_cast<double *>(slot_s + CAP2);                  // LCAP coarse values
-    double *seg_loc = c_loc + LCAP;                                             // LCAP sums of this CTA's segments
-    uint32_t *refs = reinterpret_cast<uint32_t *>(seg_loc + LCAP);              // RCAP (owner CTA << 16 | index)
+    double *seg_loc = reinterpret_cast<double *>(slot_s + CAP2);                // LCAP sums of this CTA's segments
+    double *c_loc = seg_loc + LCAP;                                             // LCAP coarse values
+    uint32_t *refs = reinterpret_cast<uint32_t *>(c_loc + LCAP);                // RCAP (owner CTA << 16 | index)
     float *la_einv = reinterpret_cast<float *>(refs + RCAP);                    // LCAP 1/E (FP32 is plenty for M)
     uint16_t *la_qn = reinterpret_cast<uint16_t *>(la_einv + LCAP);             // LCAP segments of aggregate
     uint16_t *la_a = la_qn + LCAP;                                              // LCAP own segment / first reference
@@ -481,11 +513,11 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         // (2) per slot: row, length; group bases of the warp-interleaved entry layout
         // "snake" assignment of the sorted rows to (thread, slot): odd slots run backwards so that
         // every warp gets a similar total row length
-        int meta_r[MAXR2];                                      // li | len << 16   (-1: inactive slot)
+        int meta_r[NR];                                      // li | len << 16   (-1: inactive slot)
         int base = 0;
         bool bad = false;
 #pragma unroll
-        for (int k = 0; k < MAXR2; k++) {
+        for (int k = 0; k < NR; k++) {
             int p = k * CT + ((k & 1) ? (CT - 1 - t) : t);
             int len = 0;
             meta_r[k] = -1;
@@ -509,7 +541,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         // (3) packed entries: (slot << 8) | class at gbase + j*32 + lane
         if (fits) {
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
                     int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
                     int k0 = __ldg(rowptr + li);
@@ -537,7 +569,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 }
             }
         }
-        int nseg_loc = 0, nla = 0;
+        int nseg_loc = 0, nla = 0, nrefs = 0, seg_meta = 0, seg_M = 0, ref_meta = 0;
         if (TWO) {
             // (4) this CTA's segments (member lists as local row indices) and aggregates
             const int cidx = sidx * C + crank;
@@ -561,6 +593,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             int rtotal;
             int roff = block_excl_scan_i(myqn > 1 ? myqn : 0, iscr, &rtotal);
             tw_ok = tw_ok && rtotal <= RCAP;
+            nrefs = tw_ok ? rtotal : 0;
             if (!tw_ok) {
                 // tables do not fit: the system gets status 3 once the cluster has agreed on it; until
                 // then the phases below must see consistent (empty) tables
@@ -585,10 +618,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                         la_a[t] = (uint16_t)(home & 0xFFFF);
                     } else {
                         la_a[t] = (uint16_t)roff;
+                        uint16_t *rmeta = reinterpret_cast<uint16_t *>(c_loc);      // setup-time overlay
                         for (int q = 0; q < myqn; q++) {
                             int home = __ldg(a.agg.seg_home + myq0 + q);
                             KCHECK(6, (home >> 16) < C && (home & 0xFFFF) < LCAP);
                             refs[roff + q] = (uint32_t)home;
+                            rmeta[roff + q] = (uint16_t)(t | (q == myqn - 1 ? 0x8000 : 0));
                         }
                     }
                 }
@@ -607,16 +642,37 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     if (KCHECK(1, o + q < MCAP)) segm[o + q] = KCHECK(2, loc >= 0 && loc < nown) ? (uint16_t)loc : (uint16_t)0;
                 }
             }
+            if (t < nrefs) ref_meta = reinterpret_cast<const uint16_t *>(c_loc)[t];
+            // segmented-reduction meta of this thread (see smem_segscan_sums)
+            {
+                const int M = tw_ok ? total : 0;
+                const int mb = t * NR;
+                seg_meta = 0;
+                if (mb < M) {
+                    int lo = 0, hi = nseg_loc;                  // segment s with segoff[s] <= mb < segoff[s+1]
+                    while (hi - lo > 1) {
+                        int mid = (lo + hi) >> 1;
+                        if ((int)segoff[mid] <= mb) lo = mid; else hi = mid;
+                    }
+                    int sc = lo, ef = 0;
+#pragma unroll
+                    for (int q = 0; q < NR; q++) {
+                        if (mb + q < M && mb + q + 1 == (int)segoff[sc + 1]) { ef |= 1 << q; sc++; }
+                    }
+                    seg_meta = lo | (ef << 16);
+                }
+                seg_M = M;
+            }
         }
         __syncthreads();
         const int nhalo = min(sh->nhalo, HCAP);
         const double my_ovf = (!fits || sh->ovf) ? 1.0 : 0.0;
 
         // ================= r = b - A x0, z = M^-1 r, p = z =================
-        double d_r[MAXR2], di_r[MAXR2], qz_r[MAXR2];
+        double d_r[NR], di_r[NR], qz_r[NR];
         double acc[4] = {0.0, 0.0, 0.0, my_ovf};    // rz, bb, rr, overflow flag
 #pragma unroll
-        for (int k = 0; k < MAXR2; k++) {
+        for (int k = 0; k < NR; k++) {
             d_r[k] = 1.0; di_r[k] = 1.0; qz_r[k] = 0.0;
             if (meta_r[k] >= 0) {
                 int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
@@ -638,12 +694,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         }
         if (TWO) {
             __syncthreads();                                    // r_s complete in this CTA
-            smem_segment_sums(seg_loc, r_s, segm, segoff, nseg_loc);
+            smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
             cluster.sync();                                     // segment sums published
-            smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, c_loc, nla);
+            smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, scratch, c_loc, nla, nrefs, ref_meta);
             __syncthreads();
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
                     int li = meta_r[k] & 0xFFFF;
                     double ri = r_s[li];
@@ -678,7 +734,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             // ---- phase 1: q = A p from shared memory, pq = p.q
             double s1[1] = {0.0};
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
                     int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
                     double pi = p_ext[li];
@@ -695,9 +751,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 }
             }
             PHASE(3);                                           // SpMV (thread 0's warp)
-            double xv[MAXR2];                                   // x loads fly during the reduction
+            double xv[NR];                                   // x loads fly during the reduction
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 int i = t + k * CT;
                 xv[k] = i < nown ? __ldcg(x + own0 + i) : 0.0;
             }
@@ -708,13 +764,13 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             const double alpha = rz / pq;
             // ---- phase 2: x += alpha p (coalesced, any thread/row pairing), r -= alpha q
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 int i = t + k * CT;
                 if (i < nown) x[own0 + i] = xv[k] + alpha * p_ext[i];
             }
             double s2[2] = {0.0, 0.0};
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
                     int li = meta_r[k] & 0xFFFF;
                     double ri = r_s[li] - alpha * qz_r[k];
@@ -730,14 +786,17 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             PHASE(5);                                           // x, r update
             if (TWO) {
                 __syncthreads();                                // r_s complete in this CTA
-                smem_segment_sums(seg_loc, r_s, segm, segoff, nseg_loc);
+                PHASE(12);                                      // (debug) wait for the CTA's other warps
+                smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
                 PHASE(6);                                       // segment sums
                 cluster.sync();                                 // segment sums published
                 PHASE(7);                                       // barrier
-                smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, c_loc, nla);
+                smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, scratch, c_loc, nla, nrefs, ref_meta);
+                PHASE(13);                                      // (debug) coarse values, this warp
                 __syncthreads();
+                PHASE(14);                                      // (debug) wait for the CTA's other warps
 #pragma unroll
-                for (int k = 0; k < MAXR2; k++) {
+                for (int k = 0; k < NR; k++) {
                     if (meta_r[k] >= 0) {
                         int li = meta_r[k] & 0xFFFF;
                         double ri = r_s[li];
@@ -760,7 +819,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             if (!(rr == rr)) { status = 2; break; }
             // ---- phase 3: p = z + beta p, then publish it (coalesced) for the other CTAs' halos
 #pragma unroll
-            for (int k = 0; k < MAXR2; k++) {
+            for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
                     int li = meta_r[k] & 0xFFFF;
                     p_ext[li] = qz_r[k] + beta * p_ext[li];
@@ -856,7 +915,7 @@ extern "C" int cnt_pcg_cluster_active(int C) {
     cudaLaunchAttribute attr[1];
     int n = 0;
     if (C < 1 || C > MAXC) return 0;
-    if (launch_config(k_pcg_cluster2<true>, SMEM2_BYTES, C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
+    if (launch_config(k_pcg_cluster2<true, MAXR2>, SMEM2_BYTES, C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
     return n;
 }
 
@@ -917,7 +976,11 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
     int nclusters = 0;
-    kernel_t kern = two ? k_pcg_cluster2<true> : (v2 ? k_pcg_cluster2<false> : k_pcg_cluster);
+    // chunks of at most 4*CT rows run the variant with 4 row slots per thread (no register spills)
+    const bool small = ((int64_t)max_rows + C - 1) / C <= 4 * CT && !getenv("CNT_CLUSTER_NR5");
+    kernel_t kern = !v2 ? k_pcg_cluster
+                        : two ? (small ? k_pcg_cluster2<true, 4> : k_pcg_cluster2<true, MAXR2>)
+                              : (small ? k_pcg_cluster2<false, 4> : k_pcg_cluster2<false, MAXR2>);
     int rc = launch_config(kern, v2 ? SMEM2_BYTES : SMEM_BYTES, C, &cfg, attr, st, &nclusters);
     if (rc) return rc;
     if (nclusters > NSYS) nclusters = NSYS;

@@ -29,9 +29,18 @@ with eng._work():
         torch.cuda.synchronize(); t0 = time.perf_counter()
         agg = eng._aggregates(b, sysm, sys_net, sys_slab)
         torch.cuda.synchronize(); print("aggregates setup: %.1f ms, (nagg, nseg) = %s" % (1e3 * (time.perf_counter() - t0), eng.last_aggregates), flush=True)
+# A/B switches: PROBE_AB="CNT_CLUSTER_NR5" runs every case with the variable set and unset, interleaved
+ab = os.environ.get("PROBE_AB", "")
+variants = [(ab, "1"), (ab, None)] if ab else [("", None)]
 for precond in preconds:
     for method in methods:
-        for rep in range(2):
+        for rep in range(3 * len(variants)):
+            var, val = variants[rep % len(variants)]
+            if var:
+                os.environ.pop(var, None)
+                if val is not None:
+                    os.environ[var] = val
+                print("[%s=%s] " % (var, val), end="")
             eng.stage_times_ms()
             torch.cuda.synchronize(); t0 = time.perf_counter()
             sol = eng.solve(b, sysm, rtol=1e-30, maxit=maxit, method=method, slab_priority=[0, 3, 2, 1], precond=precond)
@@ -46,7 +55,8 @@ for precond in preconds:
 # ---- per-phase cycle breakdown of the cluster kernel (thread 0 of every CTA)
 if "cluster" in methods:
     names = ["idle/queue", "setup+init", "halo refresh", "SpMV", "reduce1(+wait)", "x,r update", "segment sums",
-             "barrier(seg)", "coarse+z", "reduce2(+wait)", "p update+publish", "barrier(p)"]
+             "barrier(seg)", "coarse+z", "reduce2(+wait)", "p update+publish", "barrier(p)", "  wait warps(r)", "  coarse values",
+             "  wait warps(c)"]
     dbg = torch.zeros(148 * 16, dtype=torch.int64, device=eng.device)
     lib.cnt_pcg_cluster_set_phase_buffer(C_void_p(dbg.data_ptr()))
     sol = eng.solve(b, sysm, rtol=1e-30, maxit=maxit, method="cluster", slab_priority=[0, 3, 2, 1], precond=preconds[0])
@@ -60,3 +70,10 @@ if "cluster" in methods:
     for i, nm in enumerate(names):
         print("  %-18s %8.0f %8.0f" % (nm, d[:, i].mean() / its, d[:, i].max() / its))
     print("  %-18s %8.0f" % ("total", d.sum(1).mean() / its))
+    # work phases by CTA rank (mean over the clusters): systematic imbalance shows up here
+    full = dbg.cpu().numpy().reshape(148, 16)[:len(d)]
+    nclu = len(d) // 16
+    by_rank = full.reshape(nclu, 16, 16).mean(0) / its
+    print("  cycles per iteration by CTA rank:  " + " ".join("%6s" % nm[:6] for nm in ("halo", "SpMV", "x,r", "segsum", "coarse", "p upd")))
+    for r in range(16):
+        print("    rank %2d                        " % r + " ".join("%6.0f" % by_rank[r, i] for i in (2, 3, 5, 6, 8, 10)))
