@@ -64,7 +64,9 @@ struct Shared {
     int next;              // next system (valid in CTA rank 0)
     int nhalo;             // v2: halo references collected by this CTA
     int ovf;               // v2: slice / halo did not fit
-    int pad;
+    int npush;             // v2: halo values this CTA pushes to its peers (filled by the peers at setup)
+    int nrpush;            // v2: segment sums this CTA pushes to its peers
+    int pad[3];
     long long tlast;       // phase timing (debug): last timestamp, per-phase cycle sums
     long long tacc[16];
 };
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster(CArgs a) {
 // =====================================================================================
 constexpr int MAXR2 = 5120 / CT;       // rows per thread
 constexpr int CAP2 = CT * MAXR2;       // rows per CTA (5120)
-constexpr int ECAP = 20480;            // packed entries per CTA
+constexpr int ECAP = 20224;            // packed entries per CTA
 constexpr int HCAP = 2048;             // halo references per CTA
 
 __device__ __forceinline__ int block_excl_scan_i(int v, int *sm /*34 ints*/, int *total) {
@@ -348,37 +350,39 @@ constexpr int RCAP = 512;        // two-level: segment references of the CTA's m
 // closes it by a segmented warp scan (shuffles, reset at threads that have an end flag) and one
 // more over the 32 warp aggregates.  Fixed summation tree -> deterministic.
 // returns the sum of the run that is open when the thread's first member starts
-__device__ __forceinline__ double block_open_run_carry(double trail, bool has_end, double *scratch /* 64 */) {
+__device__ __forceinline__ double block_open_run_carry(double trail, bool has_end, double *scratch /* 64 */,
+                                                       int nactive /* threads that hold elements */) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const unsigned R = __ballot_sync(0xffffffffu, has_end);
-    const unsigned below = R & (0xFFFFFFFFu >> (31 - lane));         // resets in lanes 0..lane
-    const int dist = below ? lane - (31 - __clz(below)) : lane;      // lanes that may be added from the left
-    double incl = trail;
+    const bool active = w * 32 < nactive;                            // warp-uniform
+    unsigned R = 0;
+    double prev = 0.0;
+    if (active) {
+        R = __ballot_sync(0xffffffffu, has_end);
+        const unsigned below = R & (0xFFFFFFFFu >> (31 - lane));     // resets in lanes 0..lane
+        const int dist = below ? lane - (31 - __clz(below)) : lane;  // lanes that may be added from the left
+        double incl = trail;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double up = __shfl_up_sync(0xffffffffu, incl, o);
-        if (o <= dist) incl += up;
-    }
-    double prev = __shfl_up_sync(0xffffffffu, incl, 1);              // open run at the end of lane-1
-    if (lane == 31) {
-        scratch[w] = incl;
-        scratch[32 + w] = R ? 1.0 : 0.0;
+        for (int o = 1; o < 32; o <<= 1) {
+            double up = __shfl_up_sync(0xffffffffu, incl, o);
+            if (o <= dist) incl += up;
+        }
+        prev = __shfl_up_sync(0xffffffffu, incl, 1);                 // open run at the end of lane-1
+        if (lane == 31) {
+            scratch[w] = incl;
+            scratch[32 + w] = R ? 1.0 : 0.0;
+        }
     }
     __syncthreads();
-    // the same scan over the warp aggregates (every warp computes it; it needs lanes 0..w-1 only)
-    double aw = scratch[lane];
-    const unsigned RW = __ballot_sync(0xffffffffu, scratch[32 + lane] != 0.0);
-    const unsigned beloww = RW & (0xFFFFFFFFu >> (31 - lane));
-    const int distw = beloww ? lane - (31 - __clz(beloww)) : lane;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        double up = __shfl_up_sync(0xffffffffu, aw, o);
-        if (o <= distw) aw += up;
-    }
-    double carry_w = __shfl_sync(0xffffffffu, aw, w > 0 ? w - 1 : 0);
-    if (w == 0) carry_w = 0.0;
+    if (!active) return 0.0;
     double carry = lane > 0 ? prev : 0.0;
-    if ((R & ((1u << lane) - 1u)) == 0u) carry += carry_w;           // no end flag in lanes 0..lane-1
+    if ((R & ((1u << lane) - 1u)) == 0u) {
+        // no end flag in lanes 0..lane-1: the run was opened in an earlier warp; walk back over the
+        // warps it spans (a segment covers a few warps at most)
+        for (int j = w - 1; j >= 0; j--) {
+            carry += scratch[j];
+            if (scratch[32 + j] != 0.0) break;
+        }
+    }
     return carry;
 }
 
@@ -403,33 +407,45 @@ __device__ __forceinline__ void smem_segscan_sums(double *seg_loc, double *scrat
             run = 0.0;
         }
     }
-    const double carry = block_open_run_carry(run, ef != 0, scratch);
+    const double carry = block_open_run_carry(run, ef != 0, scratch, (M + K - 1) / K);
     if (ef != 0) seg_loc[meta & 0xFFFF] = carry + first;
 }
 
 // coarse value of every local aggregate = 1/E * (sum of the aggregate's segment sums, in global
 // segment order).  Segment sums live in the shared memory of the CTA that owns the segment.
-// Single-segment aggregates (the bulk) read their own CTA's array.  The references of the
-// multi-segment aggregates (owner CTA, index; stored back to back per aggregate) are pulled
-// through DSMEM by one thread each -- ONE round trip for the CTA -- and added per aggregate with
-// the same segmented block reduction as the segment sums.  ref_meta (one register): local
+// Single-segment aggregates (the bulk) read their own CTA's array.  The segment sums of the
+// multi-segment aggregates were pushed into ref_val[] by their owners before the barrier (one
+// slot per reference, stored back to back per aggregate); they are added per aggregate with the
+// same segmented block reduction as the segment sums.  ref_meta (one register): local
 // aggregate index | "last reference of its aggregate" << 15.
-__device__ __forceinline__ void smem_coarse_values(cg::cluster_group &cluster, double *seg_loc, const uint16_t *la_a,
-                                                   const uint16_t *la_qn, const float *la_einv, const uint32_t *refs,
+__device__ __forceinline__ void smem_coarse_values(const double *seg_loc, const uint16_t *la_a,
+                                                   const uint16_t *la_qn, const float *la_einv, const double *ref_val,
                                                    double *scratch, double *c_loc, int nla, int nrefs, int ref_meta) {
-    double v = 0.0;
-    if ((int)threadIdx.x < nrefs) {
-        uint32_t ref = refs[threadIdx.x];
-        const double *home = cluster.map_shared_rank(seg_loc, ref >> 16);
-        v = home[ref & 0xFFFFu];
-    }
+    const double v = (int)threadIdx.x < nrefs ? ref_val[threadIdx.x] : 0.0;
     for (int i = threadIdx.x; i < nla; i += CT)
         if (la_qn[i] == 1) c_loc[i] = seg_loc[la_a[i]] * (double)la_einv[i];
     const bool is_end = (int)threadIdx.x < nrefs && ((ref_meta >> 15) & 1);
-    const double carry = block_open_run_carry(is_end ? 0.0 : v, is_end, scratch);
+    const double carry = block_open_run_carry(is_end ? 0.0 : v, is_end, scratch, nrefs);
     if (is_end) {
         int ai = ref_meta & 0x7FFF;
         c_loc[ai] = (carry + v) * (double)la_einv[ai];
+    }
+}
+
+// owner-side pushes (lists built at setup): plain remote stores, made visible by the cluster
+// barrier that follows; the caller has made the source values visible inside the CTA
+__device__ __forceinline__ void push_halo(cg::cluster_group &cluster, double *p_ext, const uint32_t *push_list,
+                                          int npush) {
+    for (int k = threadIdx.x; k < npush; k += CT) {
+        uint32_t e = push_list[k];
+        cluster.map_shared_rank(p_ext, e >> 26)[(e >> 13) & 8191u] = p_ext[e & 8191u];
+    }
+}
+__device__ __forceinline__ void push_segment_sums(cg::cluster_group &cluster, const double *seg_loc, double *ref_val,
+                                                  const uint32_t *rpush_list, int nrpush) {
+    for (int k = threadIdx.x; k < nrpush; k += CT) {
+        uint32_t e = rpush_list[k];
+        cluster.map_shared_rank(ref_val, e >> 18)[(e >> 9) & 511u] = seg_loc[e & 511u];
     }
 }
 
@@ -446,15 +462,18 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     double *p_ext = gval + 256;                                                 // CAP2 + HCAP
     double *r_s = p_ext + (CAP2 + HCAP);                                        // CAP2
     uint32_t *ent = reinterpret_cast<uint32_t *>(r_s + CAP2);                   // ECAP (sort keys during setup)
-    int32_t *halo_col = reinterpret_cast<int32_t *>(ent + ECAP);                // HCAP
-    int *iscr = reinterpret_cast<int *>(halo_col + HCAP);                       // 36
+    uint32_t *push_list = ent + ECAP;                                           // HCAP: consumer << 26 | its slot << 13 | own row
+    int32_t *halo_tmp = reinterpret_cast<int32_t *>(r_s);                       // setup only: owner << 16 | its row
+    int *iscr = reinterpret_cast<int *>(push_list + HCAP);                       // 36
     int *gbase = iscr + 36;                                                     // CAP2 / 32
     uint16_t *slot_s = reinterpret_cast<uint16_t *>(gbase + CAP2 / 32);         // CAP2: row -> local aggregate
     // two-level tables of this CTA (shared memory only in the iteration)
     double *seg_loc = reinterpret_cast<double *>(slot_s + CAP2);                // LCAP sums of this CTA's segments
     double *c_loc = seg_loc + LCAP;                                             // LCAP coarse values
-    uint32_t *refs = reinterpret_cast<uint32_t *>(c_loc + LCAP);                // RCAP (owner CTA << 16 | index)
-    float *la_einv = reinterpret_cast<float *>(refs + RCAP);                    // LCAP 1/E (FP32 is plenty for M)
+    double *ref_val = c_loc + LCAP;                                             // RCAP segment sums pushed by their owners
+    uint32_t *rpush_list = reinterpret_cast<uint32_t *>(ref_val + RCAP);        // RCAP: consumer << 18 | its reference << 9 | own segment
+    uint32_t *refs = reinterpret_cast<uint32_t *>(r_s) + HCAP;                  // setup only: owner CTA << 16 | index
+    float *la_einv = reinterpret_cast<float *>(rpush_list + RCAP);                    // LCAP 1/E (FP32 is plenty for M)
     uint16_t *la_qn = reinterpret_cast<uint16_t *>(la_einv + LCAP);             // LCAP segments of aggregate
     uint16_t *la_a = la_qn + LCAP;                                              // LCAP own segment / first reference
     uint16_t *segoff = la_a + LCAP;                                             // LCAP + 2
@@ -484,7 +503,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 
         // ================= setup (once per system) =================
         PHASE(0);                                               // queue / idle
-        if (t == 0) { sh->nhalo = 0; sh->ovf = 0; }
+        if (t == 0) { sh->nhalo = 0; sh->ovf = 0; sh->npush = 0; sh->nrpush = 0; }
         if (t < 256) gval[t] = a.gneg[(int64_t)sy.slab * 256 + t];
         // (1) sort the CTA's rows by length, longest first, ties by row index: every warp then
         //     works on 32 rows of (almost) equal length -> no divergence in the SpMV loop
@@ -557,7 +576,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                         } else {
                             int h = atomicAdd(&sh->nhalo, 1);
                             if (h < HCAP) {
-                                halo_col[h] = ((c / chunk) << 16) | (c % chunk);   // owner CTA, its local row
+                                halo_tmp[h] = ((c / chunk) << 16) | (c % chunk);   // owner CTA, its local row
                                 slot = (unsigned)(nown + h);
                             } else {
                                 slot = 0;
@@ -665,7 +684,35 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             }
         }
         __syncthreads();
-        const int nhalo = min(sh->nhalo, HCAP);
+        // ---- turn the consumers' lists around: every owner gets the list of values it has to PUSH
+        // (halo copies of p; segment sums of aggregates that continue in other CTAs), so that an
+        // iteration has no remote load -- remote stores retire behind the cluster barrier that
+        // follows them anyway.  Entry order depends on the atomics' order; every entry writes its
+        // own destination, so results do not.
+        cluster.sync();                                         // lists complete, counters reset everywhere
+        {
+            const int nh = min(sh->nhalo, HCAP);
+            for (int h = t; h < nh; h += CT) {
+                int hc = halo_tmp[h];
+                Shared *osh = cluster.map_shared_rank(sh, hc >> 16);
+                int k = atomicAdd(&osh->npush, 1);
+                if (k < HCAP) cluster.map_shared_rank(push_list, hc >> 16)[k] =
+                    ((uint32_t)crank << 26) | ((uint32_t)(nown + h) << 13) | (uint32_t)(hc & 0xFFFF);
+                else osh->ovf = 1;
+            }
+            if (TWO) {
+                for (int j = t; j < nrefs; j += CT) {
+                    uint32_t ref = refs[j];
+                    Shared *osh = cluster.map_shared_rank(sh, ref >> 16);
+                    int k = atomicAdd(&osh->nrpush, 1);
+                    if (k < RCAP) cluster.map_shared_rank(rpush_list, ref >> 16)[k] =
+                        ((uint32_t)crank << 18) | ((uint32_t)j << 9) | (ref & 0x1FFu);
+                    else osh->ovf = 1;
+                }
+            }
+        }
+        cluster.sync();                                         // push lists complete
+        const int npush = min(sh->npush, HCAP), nrpush = min(sh->nrpush, RCAP);
         const double my_ovf = (!fits || sh->ovf) ? 1.0 : 0.0;
 
         // ================= r = b - A x0, z = M^-1 r, p = z =================
@@ -695,8 +742,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         if (TWO) {
             __syncthreads();                                    // r_s complete in this CTA
             smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
+            __syncthreads();
+            push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
             cluster.sync();                                     // segment sums published
-            smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, scratch, c_loc, nla, nrefs, ref_meta);
+            smem_coarse_values(seg_loc, la_a, la_qn, la_einv, ref_val, scratch, c_loc, nla, nrefs, ref_meta);
             __syncthreads();
 #pragma unroll
             for (int k = 0; k < NR; k++) {
@@ -710,7 +759,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 }
             }
         }
-        cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // barrier also publishes p (shared memory)
+        __syncthreads();                                        // own p complete in this CTA
+        push_halo(cluster, p_ext, push_list, npush);
+        cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // its barrier also publishes the halo copies of p
         double rz = acc[0];
         const double bb = acc[1];
         double rr = acc[2];
@@ -722,15 +773,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         PHASE(1);                                               // setup + initial residual
 
         while (!done) {
-            // ---- phase 0: refresh the halo copies of p (written by their owners before the barrier)
-            // halo values straight from the owners' shared memory (DSMEM), no trip through L2
-            for (int h = t; h < nhalo; h += CT) {
-                int hc = halo_col[h];
-                const double *peer = cluster.map_shared_rank(p_ext, hc >> 16);
-                p_ext[nown + h] = peer[hc & 0xFFFF];
-            }
-            __syncthreads();
-            PHASE(2);                                           // halo refresh
+            PHASE(2);                                           // (halo copies of p arrive as pushes)
             // ---- phase 1: q = A p from shared memory, pq = p.q
             double s1[1] = {0.0};
 #pragma unroll
@@ -788,10 +831,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 __syncthreads();                                // r_s complete in this CTA
                 PHASE(12);                                      // (debug) wait for the CTA's other warps
                 smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
+                __syncthreads();
+                push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
                 PHASE(6);                                       // segment sums
                 cluster.sync();                                 // segment sums published
                 PHASE(7);                                       // barrier
-                smem_coarse_values(cluster, seg_loc, la_a, la_qn, la_einv, refs, scratch, c_loc, nla, nrefs, ref_meta);
+                smem_coarse_values(seg_loc, la_a, la_qn, la_einv, ref_val, scratch, c_loc, nla, nrefs, ref_meta);
                 PHASE(13);                                      // (debug) coarse values, this warp
                 __syncthreads();
                 PHASE(14);                                      // (debug) wait for the CTA's other warps
@@ -825,8 +870,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     p_ext[li] = qz_r[k] + beta * p_ext[li];
                 }
             }
-            PHASE(10);                                          // p update
-            cluster.sync();                                     // own p visible to the cluster
+            __syncthreads();                                    // own p complete in this CTA
+            push_halo(cluster, p_ext, push_list, npush);
+            PHASE(10);                                          // p update + halo push
+            cluster.sync();                                     // halo copies visible to their consumers
             PHASE(11);                                          // barrier
         }
         if (crank == 0 && t == 0) {
@@ -843,7 +890,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 constexpr size_t SMEM2_BYTES = sizeof(Shared) + (128 + 256 + (size_t)CAP2 + HCAP + CAP2) * sizeof(double) +
                                (size_t)ECAP * 4 + (size_t)HCAP * 4 + (36 + CAP2 / 32) * 4 + (size_t)CAP2 * 2 +
                                (size_t)LCAP * (8 + 8 + 4 + 2 + 2) + (size_t)RCAP * 4 + ((size_t)LCAP + 2) * 2 +
-                               (size_t)MCAP * 2 + 16;
+                               (size_t)MCAP * 2 + (size_t)RCAP * 8 + 16;
 static_assert(SMEM2_BYTES <= 232448, "cluster kernel exceeds the 227 KB shared-memory limit");
 
 constexpr size_t SMEM_BYTES = sizeof(Shared) + 96 * sizeof(double) + 3 * (size_t)CAP * sizeof(double);
