@@ -52,6 +52,7 @@ struct CArgs {
     double *rglob;           // [NSLAB*R] r published once per iteration for the segment sums
     double *segS;            // [nseg]
     long long *dbg;          // [gridDim.x][16] per-phase cycle sums (NULL = off)
+    int mb;                  // 1: transaction barriers instead of cluster barriers inside the iteration
     int *assert_flag;        // first failed in-kernel bounds check (0 = none)
     double rtol;
     int maxit;
@@ -67,6 +68,7 @@ struct Shared {
     int npush;             // v2: halo values this CTA pushes to its peers (filled by the peers at setup)
     int nrpush;            // v2: segment sums this CTA pushes to its peers
     int pad[3];
+    unsigned long long mbar[4];   // v2: transaction barriers: reductions (2 slots), halo of p, segment sums
     long long tlast;       // phase timing (debug): last timestamp, per-phase cycle sums
     long long tacc[16];
 };
@@ -83,6 +85,83 @@ struct Shared {
             sh->tlast = c_;                                        \
         }                                                          \
     } while (0)
+
+// ---- point-to-point synchronisation: transaction barriers (mbarrier) in shared memory ------
+// A value pushed to a peer with st.async carries the address of an mbarrier in the peer's shared
+// memory and completes 8 bytes of that barrier's transaction count when it lands.  The receiver
+// posts the number of bytes it expects (one arrive.expect_tx per phase) and waits on its OWN
+// barrier: it continues as soon as ITS inputs are there -- no cluster-wide rendezvous, no
+// barrier.cluster round trip (~1000 cycles with 16 CTAs here), and the stores need not drain
+// before anything.  Bytes that land before expect_tx is posted are accounted for (the count is
+// signed); a phase cannot complete before the local arrive.
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// bounded wait: a protocol error must not hang the GPU -- record it and abort the kernel
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity, int *assert_flag, int id) {
+    for (int i = 0; i < (1 << 24); i++)
+        if (mbar_try_wait(bar, parity)) return;
+    atomicCAS(assert_flag, 0, id);
+    __trap();
+}
+__device__ __forceinline__ uint32_t map_cluster_u32(uint32_t local_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void st_async_f64(uint32_t remote_addr, double v, uint32_t remote_bar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];" ::"r"(remote_addr),
+                 "l"(__double_as_longlong(v)), "r"(remote_bar)
+                 : "memory");
+}
+
+// cluster-wide sum over transaction barriers: same arithmetic (and bits) as cluster_sum_n
+template <int N>
+__device__ __forceinline__ void cluster_sum_mb(Shared *sh, int slot, uint32_t parity, double (&v)[N],
+                                               double *scratch /* 32*N */, int C, int crank, int *assert_flag) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < N; k++) v[k] = cnt::warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < N; k++) scratch[k * 32 + w] = v[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+        if (lane == 0) mbar_expect_tx(&sh->mbar[slot], (uint32_t)(C * N * 8));
+        const uint32_t rbar = map_cluster_u32(smem_u32(&sh->mbar[slot]), lane < C ? lane : 0);
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            double t = lane < (CT >> 5) ? scratch[k * 32 + lane] : 0.0;
+            t = cnt::warp_sum(t);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (lane < C) st_async_f64(map_cluster_u32(smem_u32(&sh->red[slot][k][crank]), lane), t, rbar);
+        }
+    }
+    mbar_wait(&sh->mbar[slot], parity, assert_flag, 30 + slot);
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+        double t = lane < C ? sh->red[slot][k][lane] : 0.0;
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
+        v[k] = __shfl_sync(0xffffffffu, t, 0);
+    }
+}
 
 // cluster-wide sum of N values, bit-identical in every thread of every CTA.
 // Warp sums -> warp 0 adds the CTA's 32 warp partials -> lanes 0..C-1 PUSH the CTA's partial
@@ -441,6 +520,24 @@ __device__ __forceinline__ void push_halo(cg::cluster_group &cluster, double *p_
         cluster.map_shared_rank(p_ext, e >> 26)[(e >> 13) & 8191u] = p_ext[e & 8191u];
     }
 }
+__device__ __forceinline__ void push_halo_mb(double *p_ext, const uint32_t *push_list, int npush,
+                                             unsigned long long *bar) {
+    const uint32_t pbase = smem_u32(p_ext), lbar = smem_u32(bar);
+    for (int k = threadIdx.x; k < npush; k += CT) {
+        uint32_t e = push_list[k];
+        st_async_f64(map_cluster_u32(pbase + 8u * ((e >> 13) & 8191u), e >> 26), p_ext[e & 8191u],
+                     map_cluster_u32(lbar, e >> 26));
+    }
+}
+__device__ __forceinline__ void push_segment_sums_mb(const double *seg_loc, double *ref_val, const uint32_t *rpush_list,
+                                                     int nrpush, unsigned long long *bar) {
+    const uint32_t rbase = smem_u32(ref_val), lbar = smem_u32(bar);
+    for (int k = threadIdx.x; k < nrpush; k += CT) {
+        uint32_t e = rpush_list[k];
+        st_async_f64(map_cluster_u32(rbase + 8u * ((e >> 9) & 511u), e >> 18), seg_loc[e & 511u],
+                     map_cluster_u32(lbar, e >> 18));
+    }
+}
 __device__ __forceinline__ void push_segment_sums(cg::cluster_group &cluster, const double *seg_loc, double *ref_val,
                                                   const uint32_t *rpush_list, int nrpush) {
     for (int k = threadIdx.x; k < nrpush; k += CT) {
@@ -482,7 +579,31 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     if (t == 0) {
         for (int i = 0; i < 16; i++) sh->tacc[i] = 0;
         sh->tlast = clock64();
+        for (int i = 0; i < 4; i++) mbar_init(&sh->mbar[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");   // ordered by the first cluster barrier
     }
+    uint32_t mpar = 0;                  // bit i: parity of the next phase of mbar[i]
+    const bool mb = a.mb != 0;
+    // cluster-wide sum / wait for pushed data: transaction barriers, or cluster barriers (reference path)
+#define CSUM(N, slot, arr)                                                                                  \
+    do {                                                                                                    \
+        if (mb) {                                                                                           \
+            cluster_sum_mb<N>(sh, slot, (mpar >> (slot)) & 1u, arr, scratch, C, crank, a.assert_flag);      \
+            mpar ^= 1u << (slot);                                                                           \
+        } else {                                                                                            \
+            cluster_sum_n<N>(cluster, sh, slot, arr, scratch, C);                                           \
+        }                                                                                                   \
+    } while (0)
+#define WAIT_PUSHED(i, count)                                                                               \
+    do {                                                                                                    \
+        if (mb) {                                                                                           \
+            if (t == 0) mbar_expect_tx(&sh->mbar[i], (uint32_t)(count) * 8u);                               \
+            mbar_wait(&sh->mbar[i], (mpar >> (i)) & 1u, a.assert_flag, 30 + (i));                           \
+            mpar ^= 1u << (i);                                                                              \
+        } else {                                                                                            \
+            cluster.sync();                                                                                 \
+        }                                                                                                   \
+    } while (0)
 
     while (true) {
         if (crank == 0 && t == 0) sh->next = atomicAdd(a.counter, 1);
@@ -503,7 +624,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 
         // ================= setup (once per system) =================
         PHASE(0);                                               // queue / idle
-        if (t == 0) { sh->nhalo = 0; sh->ovf = 0; sh->npush = 0; sh->nrpush = 0; }
+        if (t == 0) { sh->nhalo = 0; sh->ovf = 0; sh->npush = 0; sh->nrpush = 0; sh->pad[0] = 0; sh->pad[1] = 0; }
         if (t < 256) gval[t] = a.gneg[(int64_t)sy.slab * 256 + t];
         // (1) sort the CTA's rows by length, longest first, ties by row index: every warp then
         //     works on 32 rows of (almost) equal length -> no divergence in the SpMV loop
@@ -696,23 +817,32 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 int hc = halo_tmp[h];
                 Shared *osh = cluster.map_shared_rank(sh, hc >> 16);
                 int k = atomicAdd(&osh->npush, 1);
-                if (k < HCAP) cluster.map_shared_rank(push_list, hc >> 16)[k] =
-                    ((uint32_t)crank << 26) | ((uint32_t)(nown + h) << 13) | (uint32_t)(hc & 0xFFFF);
-                else osh->ovf = 1;
+                if (k < HCAP) {
+                    cluster.map_shared_rank(push_list, hc >> 16)[k] =
+                        ((uint32_t)crank << 26) | ((uint32_t)(nown + h) << 13) | (uint32_t)(hc & 0xFFFF);
+                    atomicAdd(&sh->pad[0], 1);                  // halo values that will actually arrive
+                } else {
+                    osh->ovf = 1;
+                }
             }
             if (TWO) {
                 for (int j = t; j < nrefs; j += CT) {
                     uint32_t ref = refs[j];
                     Shared *osh = cluster.map_shared_rank(sh, ref >> 16);
                     int k = atomicAdd(&osh->nrpush, 1);
-                    if (k < RCAP) cluster.map_shared_rank(rpush_list, ref >> 16)[k] =
-                        ((uint32_t)crank << 18) | ((uint32_t)j << 9) | (ref & 0x1FFu);
-                    else osh->ovf = 1;
+                    if (k < RCAP) {
+                        cluster.map_shared_rank(rpush_list, ref >> 16)[k] =
+                            ((uint32_t)crank << 18) | ((uint32_t)j << 9) | (ref & 0x1FFu);
+                        atomicAdd(&sh->pad[1], 1);              // segment sums that will actually arrive
+                    } else {
+                        osh->ovf = 1;
+                    }
                 }
             }
         }
         cluster.sync();                                         // push lists complete
         const int npush = min(sh->npush, HCAP), nrpush = min(sh->nrpush, RCAP);
+        const int nhalo_in = sh->pad[0], nref_in = sh->pad[1];
         const double my_ovf = (!fits || sh->ovf) ? 1.0 : 0.0;
 
         // ================= r = b - A x0, z = M^-1 r, p = z =================
@@ -743,8 +873,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             __syncthreads();                                    // r_s complete in this CTA
             smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
             __syncthreads();
-            push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
-            cluster.sync();                                     // segment sums published
+            if (mb) push_segment_sums_mb(seg_loc, ref_val, rpush_list, nrpush, &sh->mbar[3]);
+            else push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
+            WAIT_PUSHED(3, nref_in);                            // segment sums of the other CTAs are here
             smem_coarse_values(seg_loc, la_a, la_qn, la_einv, ref_val, scratch, c_loc, nla, nrefs, ref_meta);
             __syncthreads();
 #pragma unroll
@@ -760,8 +891,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             }
         }
         __syncthreads();                                        // own p complete in this CTA
-        push_halo(cluster, p_ext, push_list, npush);
-        cluster_sum_n<4>(cluster, sh, 0, acc, scratch, C);     // its barrier also publishes the halo copies of p
+        if (mb) push_halo_mb(p_ext, push_list, npush, &sh->mbar[2]);
+        else push_halo(cluster, p_ext, push_list, npush);
+        CSUM(4, 0, acc);                                        // (cluster barrier: also publishes the halo copies of p)
+        if (mb) WAIT_PUSHED(2, nhalo_in);
         double rz = acc[0];
         const double bb = acc[1];
         double rr = acc[2];
@@ -800,7 +933,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 int i = t + k * CT;
                 xv[k] = i < nown ? __ldcg(x + own0 + i) : 0.0;
             }
-            cluster_sum_n<1>(cluster, sh, 1, s1, scratch, C);
+            CSUM(1, 1, s1);
             PHASE(4);                                           // reduction 1 incl. waiting for the cluster
             const double pq = s1[0];
             if (!(pq > 0.0)) { status = 2; break; }
@@ -832,9 +965,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 PHASE(12);                                      // (debug) wait for the CTA's other warps
                 smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
                 __syncthreads();
-                push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
+                if (mb) push_segment_sums_mb(seg_loc, ref_val, rpush_list, nrpush, &sh->mbar[3]);
+                else push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
                 PHASE(6);                                       // segment sums
-                cluster.sync();                                 // segment sums published
+                WAIT_PUSHED(3, nref_in);                        // segment sums of the other CTAs are here
                 PHASE(7);                                       // barrier
                 smem_coarse_values(seg_loc, la_a, la_qn, la_einv, ref_val, scratch, c_loc, nla, nrefs, ref_meta);
                 PHASE(13);                                      // (debug) coarse values, this warp
@@ -853,7 +987,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 }
                 PHASE(8);                                       // coarse term + z
             }
-            cluster_sum_n<2>(cluster, sh, 0, s2, scratch, C);
+            CSUM(2, 0, s2);
             PHASE(9);                                           // reduction 2
             const double beta = s2[0] / rz;
             rz = s2[0];
@@ -871,9 +1005,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 }
             }
             __syncthreads();                                    // own p complete in this CTA
-            push_halo(cluster, p_ext, push_list, npush);
+            if (mb) push_halo_mb(p_ext, push_list, npush, &sh->mbar[2]);
+            else push_halo(cluster, p_ext, push_list, npush);
             PHASE(10);                                          // p update + halo push
-            cluster.sync();                                     // halo copies visible to their consumers
+            WAIT_PUSHED(2, nhalo_in);                           // halo copies of the neighbours' p are here
             PHASE(11);                                          // barrier
         }
         if (crank == 0 && t == 0) {
@@ -1040,6 +1175,7 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     a.rglob = rglob; a.segS = segS;
     a.dbg = g_phase_dbg;
     a.assert_flag = assert_flag;
+    a.mb = getenv("CNT_CLUSTER_NOMB") ? 0 : 1;     // reference path: cluster barriers
     if (two) a.agg = *agg; else a.agg = cnt_aggregates{};
     a.iters = iters; a.status = status; a.relres = relres;
     CNT_CUDA(cudaLaunchKernelEx(&cfg, kern, a));

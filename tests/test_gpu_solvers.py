@@ -17,6 +17,7 @@ def solver(engine):
     yield engine
     engine.solver, engine.precond = old, oldp
     os.environ.pop("CNT_CLUSTER_SIZE", None)
+    os.environ.pop("CNT_CLUSTER_NOMB", None)
 
 
 def _oracle_currents(g, onoffmap):
@@ -81,6 +82,27 @@ def test_cluster_sizes(solver, csize):
     for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
         assert np.array_equal(res[k], res2[k])
     assert np.array_equal(res["iters"], res2["iters"])
+
+
+def test_transaction_barriers_equal_cluster_barriers(solver):
+    """the iteration synchronises through mbarrier transaction counts (st.async pushes); the
+    reference path with cluster barriers does the same arithmetic -> identical bits"""
+    solver.solver = "cluster"
+    names = ["s5_n300_seed1", "s20_n6400_seed5", "trivial", "s20_n3600_seed7"]
+    gs = [load_golden(n) for n in names]
+    out = {}
+    for mode in ("mb", "barrier"):
+        os.environ.pop("CNT_CLUSTER_NOMB", None)
+        if mode == "barrier":
+            os.environ["CNT_CLUSTER_NOMB"] = "1"
+        for csize in (2, 16):
+            os.environ["CNT_CLUSTER_SIZE"] = str(csize)
+            b = solver.batch_from_host([golden_sticks(g) for g in gs])
+            out[mode, csize] = solver.measure_fullnet(b, onoffmap=1)
+            assert solver.last_solver == "cluster"
+    for csize in (2, 16):
+        for k in ("ion", "ioff_back", "ioff_total", "ioff_partial", "iters"):
+            assert np.array_equal(out["mb", csize][k], out["barrier", csize][k]), (csize, k)
 
 
 def test_many_systems_work_queue(solver):
