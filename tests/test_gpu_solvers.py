@@ -18,6 +18,7 @@ def solver(engine):
     engine.solver, engine.precond = old, oldp
     os.environ.pop("CNT_CLUSTER_SIZE", None)
     os.environ.pop("CNT_CLUSTER_NOMB", None)
+    os.environ.pop("CNT_AGG_HOST", None)
 
 
 def _oracle_currents(g, onoffmap):
@@ -82,6 +83,43 @@ def test_cluster_sizes(solver, csize):
     for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
         assert np.array_equal(res[k], res2[k])
     assert np.array_equal(res["iters"], res2["iters"])
+
+
+@pytest.mark.parametrize("chunk_C", [0, 2, 16])
+def test_aggregate_tables_device_equals_host(solver, chunk_C):
+    """segment / CTA tables of the two-level preconditioner: the device builder (flags + scans)
+    reproduces the host reference builder entry by entry"""
+    from networksim_cntfet_b200.elements import LinExpTransistor, conductance_table
+    names = ["s5_n300_seed1", "s20_n6400_seed5", "s5_n120_seed5_noperc", "s20_n3600_seed7"]
+    b = solver.prepare(solver.batch_from_host([golden_sticks(load_golden(n)) for n in names]))
+    gates = [g for _, g in solver.fullnet_gates(b)]
+    tabs = [conductance_table(LinExpTransistor, 1, g.levels) for g in gates]
+    sysm = solver.assemble_values(b, gates, tabs)
+    nets = [n for n in range(b.B) if b.h_roff[n + 1] > b.h_roff[n]]
+    sys_net = [n for q in range(4) for n in nets]
+    sys_slab = [q for q in range(4) for n in nets]
+    out = {}
+    for mode in ("device", "host"):
+        os.environ.pop("CNT_AGG_HOST", None)
+        if mode == "host":
+            os.environ["CNT_AGG_HOST"] = "1"
+        with solver._work():
+            st, t = solver._aggregates(b, sysm, sys_net, sys_slab, chunk_C)
+        solver.sync()
+        out[mode] = (st.nagg, st.nseg, {k: v.cpu().numpy() for k, v in t.items()})
+    os.environ.pop("CNT_AGG_HOST", None)
+    (na, ns, d), (na2, ns2, h) = out["device"], out["host"]
+    assert (na, ns) == (na2, ns2) and na > 0 and ns >= na
+    nsys = len(sys_net)
+    lens = dict(agg_of_row=None, mem=None, seg_start=ns, seg_count=ns, seg_agg=ns, seg_sys=ns, agg_seg0=na + 1,
+                sys_seg=2 * nsys, row_q=None, row_einv=None, agg_einv=na)
+    if chunk_C:
+        nloc = int(h["cta_agg_off"][nsys * chunk_C])
+        lens.update(cta_seg_off=nsys * chunk_C + 1, cta_seg=4 * ns, cta_agg_off=nsys * chunk_C + 1, cta_agg=nloc,
+                    row_slot=None, seg_home=ns)
+    for k, n in lens.items():
+        a, c = (d[k], h[k]) if n is None else (d[k][:n], h[k][:n])
+        assert np.array_equal(a, c), (chunk_C, k, np.flatnonzero(a != c)[:5])
 
 
 def test_transaction_barriers_equal_cluster_barriers(solver):
