@@ -570,6 +570,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     double *ref_val = c_loc + LCAP;                                             // RCAP segment sums pushed by their owners
     uint32_t *rpush_list = reinterpret_cast<uint32_t *>(ref_val + RCAP);        // RCAP: consumer << 18 | its reference << 9 | own segment
     uint32_t *refs = reinterpret_cast<uint32_t *>(r_s) + HCAP;                  // setup only: owner CTA << 16 | index
+    uint16_t *pos_of = reinterpret_cast<uint16_t *>(r_s) + 2 * (HCAP + RCAP);   // setup only: local row -> position
     float *la_einv = reinterpret_cast<float *>(rpush_list + RCAP);                    // LCAP 1/E (FP32 is plenty for M)
     uint16_t *la_qn = reinterpret_cast<uint16_t *>(la_einv + LCAP);             // LCAP segments of aggregate
     uint16_t *la_a = la_qn + LCAP;                                              // LCAP own segment / first reference
@@ -667,6 +668,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 int li = 8191 - (int)(key & 8191u);
                 if (len > 255) { bad = true; len = 255; }
                 meta_r[k] = li | (len << 16);
+                pos_of[li] = (uint16_t)p;
             }
             int total;
             // group = 32 consecutive positions; its longest row is the one with the smallest position
@@ -693,7 +695,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                         unsigned lc = (unsigned)(c - own0);
                         unsigned slot;
                         if (lc < (unsigned)nown) {
-                            slot = lc;
+                            slot = pos_of[lc];                  // vectors are stored by position
                         } else {
                             int h = atomicAdd(&sh->nhalo, 1);
                             if (h < HCAP) {
@@ -770,7 +772,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 for (int i = t; i < nown; i += CT) {
                     int sl = __ldg(a.agg.row_slot + vbase + own0 + i);
                     KCHECK(3, sl < nla);
-                    slot_s[i] = (sl < 0 || sl >= nla) ? (uint16_t)0xFFFF : (uint16_t)sl;
+                    slot_s[pos_of[i]] = (sl < 0 || sl >= nla) ? (uint16_t)0xFFFF : (uint16_t)sl;
                 }
             }
             __syncthreads();
@@ -779,7 +781,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 int o = segoff[sgi];
                 for (int q = lane; q < g4.z; q += 32) {
                     int64_t loc = (int64_t)__ldg(a.agg.mem + g4.y + q) - (vbase + own0);
-                    if (KCHECK(1, o + q < MCAP)) segm[o + q] = KCHECK(2, loc >= 0 && loc < nown) ? (uint16_t)loc : (uint16_t)0;
+                    if (KCHECK(1, o + q < MCAP)) segm[o + q] = KCHECK(2, loc >= 0 && loc < nown) ? pos_of[loc] : (uint16_t)0;
                 }
             }
             if (t < nrefs) ref_meta = reinterpret_cast<const uint16_t *>(c_loc)[t];
@@ -818,8 +820,9 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 Shared *osh = cluster.map_shared_rank(sh, hc >> 16);
                 int k = atomicAdd(&osh->npush, 1);
                 if (k < HCAP) {
+                    const uint32_t opos = cluster.map_shared_rank(pos_of, hc >> 16)[hc & 0xFFFF];   // owner's position
                     cluster.map_shared_rank(push_list, hc >> 16)[k] =
-                        ((uint32_t)crank << 26) | ((uint32_t)(nown + h) << 13) | (uint32_t)(hc & 0xFFFF);
+                        ((uint32_t)crank << 26) | ((uint32_t)(nown + h) << 13) | opos;
                     atomicAdd(&sh->pad[0], 1);                  // halo values that will actually arrive
                 } else {
                     osh->ovf = 1;
@@ -847,6 +850,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 
         // ================= r = b - A x0, z = M^-1 r, p = z =================
         double d_r[NR], di_r[NR], qz_r[NR];
+#define POS(k) ((k) * CT + (((k) & 1) ? (CT - 1 - t) : t))      /* position of the thread's k-th row */
         double acc[4] = {0.0, 0.0, 0.0, my_ovf};    // rz, bb, rr, overflow flag
 #pragma unroll
         for (int k = 0; k < NR; k++) {
@@ -859,12 +863,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                 for (int j = 0; j < len; j++) ax += gval[__ldg(cls + k0 + j)] * x[__ldg(a.col + k0 + j)];
                 double ri = bi - ax, dinv = 1.0 / di;
                 d_r[k] = di; di_r[k] = dinv;
-                r_s[li] = ri;
+                r_s[POS(k)] = ri;
                 acc[1] += bi * bi;
                 acc[2] += ri * ri;
                 if (!TWO) {
                     double zi = ri * dinv;
-                    p_ext[li] = zi;
+                    p_ext[POS(k)] = zi;
                     acc[0] += ri * zi;
                 }
             }
@@ -881,11 +885,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 #pragma unroll
             for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
-                    int li = meta_r[k] & 0xFFFF;
-                    double ri = r_s[li];
-                    unsigned sl = slot_s[li];
+                    double ri = r_s[POS(k)];
+                    unsigned sl = slot_s[POS(k)];
                     double zi = ri * di_r[k] + (sl != 0xFFFFu ? c_loc[sl] : 0.0);
-                    p_ext[li] = zi;
+                    p_ext[POS(k)] = zi;
                     acc[0] += ri * zi;
                 }
             }
@@ -903,6 +906,18 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         bool done = (sy.nrows == 0) || (rr <= tol2);
         if (acc[3] > 0.0) { done = true; status = 3; }          // does not fit on chip: caller re-solves
         if (!done && a.maxit <= 0) { done = true; status = 1; }
+        // x lives in position order while the system is being solved (every thread then touches
+        // only its own, coalesced, conflict-free locations); everybody has read x0 by now
+        const bool entered = !done;
+        if (entered) {
+            double xin[NR];
+#pragma unroll
+            for (int k = 0; k < NR; k++) xin[k] = meta_r[k] >= 0 ? __ldcg(x + own0 + (meta_r[k] & 0xFFFF)) : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                if (meta_r[k] >= 0) x[own0 + POS(k)] = xin[k];
+        }
         PHASE(1);                                               // setup + initial residual
 
         while (!done) {
@@ -912,10 +927,10 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 #pragma unroll
             for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
-                    int li = meta_r[k] & 0xFFFF, len = meta_r[k] >> 16;
-                    double pi = p_ext[li];
+                    const int len = meta_r[k] >> 16;
+                    const int p = POS(k);
+                    double pi = p_ext[p];
                     double q = d_r[k] * pi;
-                    const int p = k * CT + ((k & 1) ? (CT - 1 - t) : t);
                     const unsigned *e = ent + gbase[p >> 5] + (p & 31);
                     for (int j = 0; j < len; j++) {
                         unsigned u = e[j * 32];
@@ -929,28 +944,21 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             PHASE(3);                                           // SpMV (thread 0's warp)
             double xv[NR];                                   // x loads fly during the reduction
 #pragma unroll
-            for (int k = 0; k < NR; k++) {
-                int i = t + k * CT;
-                xv[k] = i < nown ? __ldcg(x + own0 + i) : 0.0;
-            }
+            for (int k = 0; k < NR; k++) xv[k] = meta_r[k] >= 0 ? __ldcg(x + own0 + POS(k)) : 0.0;
             CSUM(1, 1, s1);
             PHASE(4);                                           // reduction 1 incl. waiting for the cluster
             const double pq = s1[0];
             if (!(pq > 0.0)) { status = 2; break; }
             const double alpha = rz / pq;
-            // ---- phase 2: x += alpha p (coalesced, any thread/row pairing), r -= alpha q
-#pragma unroll
-            for (int k = 0; k < NR; k++) {
-                int i = t + k * CT;
-                if (i < nown) x[own0 + i] = xv[k] + alpha * p_ext[i];
-            }
+            // ---- phase 2: x += alpha p (x is stored by position while the system is being solved), r -= alpha q
             double s2[2] = {0.0, 0.0};
 #pragma unroll
             for (int k = 0; k < NR; k++) {
                 if (meta_r[k] >= 0) {
-                    int li = meta_r[k] & 0xFFFF;
-                    double ri = r_s[li] - alpha * qz_r[k];
-                    r_s[li] = ri;
+                    const int p = POS(k);
+                    x[own0 + p] = xv[k] + alpha * p_ext[p];
+                    double ri = r_s[p] - alpha * qz_r[k];
+                    r_s[p] = ri;
                     s2[1] += ri * ri;
                     if (!TWO) {
                         double zi = ri * di_r[k];
@@ -977,9 +985,8 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
 #pragma unroll
                 for (int k = 0; k < NR; k++) {
                     if (meta_r[k] >= 0) {
-                        int li = meta_r[k] & 0xFFFF;
-                        double ri = r_s[li];
-                        unsigned sl = slot_s[li];
+                        double ri = r_s[POS(k)];
+                        unsigned sl = slot_s[POS(k)];
                         double zi = ri * di_r[k] + (sl != 0xFFFFu ? c_loc[sl] : 0.0);
                         qz_r[k] = zi;
                         s2[0] += ri * zi;
@@ -999,10 +1006,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             // ---- phase 3: p = z + beta p, then publish it (coalesced) for the other CTAs' halos
 #pragma unroll
             for (int k = 0; k < NR; k++) {
-                if (meta_r[k] >= 0) {
-                    int li = meta_r[k] & 0xFFFF;
-                    p_ext[li] = qz_r[k] + beta * p_ext[li];
-                }
+                if (meta_r[k] >= 0) p_ext[POS(k)] = qz_r[k] + beta * p_ext[POS(k)];
             }
             __syncthreads();                                    // own p complete in this CTA
             if (mb) push_halo_mb(p_ext, push_list, npush, &sh->mbar[2]);
@@ -1010,6 +1014,15 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             PHASE(10);                                          // p update + halo push
             WAIT_PUSHED(2, nhalo_in);                           // halo copies of the neighbours' p are here
             PHASE(11);                                          // barrier
+        }
+        if (entered) {                                          // back to row order (a permutation inside the chunk)
+            double xf[NR];
+#pragma unroll
+            for (int k = 0; k < NR; k++) xf[k] = meta_r[k] >= 0 ? __ldcg(x + own0 + POS(k)) : 0.0;
+            __syncthreads();
+#pragma unroll
+            for (int k = 0; k < NR; k++)
+                if (meta_r[k] >= 0) x[own0 + (meta_r[k] & 0xFFFF)] = xf[k];
         }
         if (crank == 0 && t == 0) {
             a.iters[sy.out] = it;
