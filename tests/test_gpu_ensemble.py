@@ -71,6 +71,84 @@ def test_full_size_variants(engine, n, onoffmap, element):
         assert abs(res[key][0] - m[key]) <= 1e-9 * m[key], (key, res[key][0], m[key], res["iters"][:, 0])
 
 
+def test_full_size_properties(engine):
+    """BASELINE size (3 networks of 100x100 um, n = 100k, measure_fullnet): size-independent
+    properties of the answer, checked from the returned fields alone (torch ops on V, I, g and the
+    junction table -- nothing of the solver is reused):
+    Kirchhoff's current law at every stick of the component (dangling sticks included), the three
+    source-current estimators agree, maximum principle 0 <= V <= Vds, pruned sticks sit at their
+    attachment point, gating can only lower the current (Rayleigh monotonicity: every LinExp
+    conductance falls with Vg), currents are unsigned, and the run is bit-reproducible."""
+    import torch
+    b = engine.generate([100000, 100000, 100000], 100.0, seed=2024)
+    res = engine.measure_fullnet(b, onoffmap=1, want_fields=True)
+    assert np.all(res["status"] == 0) and np.all(res["percolating"])
+    f = res["fields"]
+    S, J = b.S, b.J
+    soff = torch.as_tensor(b.h_soff, device=engine.device, dtype=torch.int64)
+    net_of_j = torch.bucketize(torch.arange(J, device=engine.device), b.joff[1:].to(torch.int64), right=True)
+    a = b.stick1[:J].to(torch.int64) + soff[net_of_j]
+    c = b.stick2[:J].to(torch.int64) + soff[net_of_j]
+    local = torch.arange(S, device=engine.device) - soff[torch.bucketize(torch.arange(S, device=engine.device), soff[1:], right=True)]
+    for q in range(4):
+        V, I, g = f["V"][q][:S], f["I"][q][:J], f["g"][q][:J]
+        inc = ~torch.isnan(V)
+        assert torch.equal(inc, b.label[:S] == 0)                       # exactly the percolating component
+        e = inc[a] & inc[c]
+        assert torch.equal(~torch.isnan(I), e)
+        Vz = torch.nan_to_num(V)
+        flow = torch.where(e, g * (Vz[a] - Vz[c]), torch.zeros_like(g))  # signed current a -> c
+        assert torch.all(I[e] >= 0) and torch.allclose(I[e], flow[e].abs(), rtol=0, atol=0)
+        net = torch.zeros(S, dtype=torch.float64, device=engine.device)
+        net.index_add_(0, a, flow)
+        net.index_add_(0, c, -flow)
+        inner = inc & (local >= 2)
+        gsum = torch.zeros(S, dtype=torch.float64, device=engine.device)
+        ge = torch.where(e, g, torch.zeros_like(g))
+        gsum.index_add_(0, a, ge)
+        gsum.index_add_(0, c, ge)
+        # KCL: what flows into a stick flows out (residual relative to the current through the network)
+        for k in range(b.B):
+            m = inner & (torch.arange(S, device=engine.device) >= b.h_soff[k]) & (torch.arange(S, device=engine.device) < b.h_soff[k + 1])
+            itot = res["isrc_all"][q, k, 2]
+            # node-wise: the imbalance is what a voltage error of 1e-11 Vds at that stick would cause
+            # (sum of its conductances x 1e-12 V); the parity bar on V itself is 1e-9 Vds
+            assert bool(torch.all(net[m].abs() <= 1e-12 * gsum[m])), (q, k, float((net[m].abs() / gsum[m]).max()), itot)
+            src, drn, pw = res["isrc_all"][q, k]
+            assert abs(src - pw) <= 1e-6 * pw and abs(drn - pw) <= 1e-7 * pw
+            # current leaving the source electrode == current entering the drain (from the fields)
+            assert abs(float(net[b.h_soff[k]]) - pw) <= 1e-6 * pw and abs(float(-net[b.h_soff[k] + 1]) - pw) <= 1e-7 * pw
+        # maximum principle up to the attainable accuracy of V (see the comparison with the oracle below)
+        assert float(V[inc].min()) >= -1e-9 and float(V[inc].max()) <= 0.1 + 1e-9
+        pr = b.attach[:S] >= 0
+        assert int(pr.sum()) > 10000 and torch.equal(V[pr], V[b.attach[:S][pr].to(torch.int64)])
+    # a local gate lowers the conductances of a subset of the junctions the back gate lowers
+    for key in ("ioff_partial", "ioff_total"):
+        assert np.all(res["ion"] > res[key]) and np.all(res[key] > res["ioff_back"])
+    assert np.all(res["ioff_back"] > 0)
+    # voltages of the first network against the refined oracle (SuperLU + 3 refinement steps, itself
+    # within 3e-13 Vds of an extended-precision solve).  At Vg = 0 and under the local gates: 1e-9 Vds.
+    # Under the back gate at +10 V the whole interior floats on ~100 contacts of e^-10: the rounding of
+    # the 58k diagonal sums (1e-16 each) is a spurious leak comparable to that stiffness, so the
+    # solution of the FP64 matrix is itself defined only to a few 1e-9 Vds -- two summation orders of
+    # the diagonal differ by 3e-9, and the reference's own SuperLU answer is 5e-9 off (DESIGN section 2).
+    # Currents are insensitive (1e-12).
+    s = engine.sticks_to_host(b)[0]
+    jn = O.find_junctions(s)
+    lab = O.label_clusters(len(s["xc"]), jn["stick1"], jn["stick2"])["label"]
+    for q, (gate, vgv, tol) in enumerate(((None, 0.0, 1e-9), ("back", 10.0, 8e-9), ("total", 10.0, 1e-9), ("partial", 10.0, 1e-9))):
+        cond = O.conductance(jn["kind2"], O.gate_voltages(jn["x"], jn["y"], gate, vgv), 1, "linexp")
+        r = O.solve_network(len(s["xc"]), jn["stick1"], jn["stick2"], cond, lab, refine=3)
+        V = f["V"][q][:b.h_soff[1]].cpu().numpy()
+        m = ~np.isnan(r["V"])
+        err = np.abs(V[m] - r["V"][m])
+        assert err.max() <= tol * 0.1, (gate, err.max() / 0.1)
+        assert abs(res["isrc_all"][q, 0, 2] - r["I_source"]) <= 1e-12 * r["I_source"]
+    again = engine.measure_fullnet(engine.generate([100000, 100000, 100000], 100.0, seed=2024), onoffmap=1)
+    for key in ("ion", "ioff_back", "ioff_total", "ioff_partial", "iters"):
+        assert np.array_equal(res[key], again[key]), key
+
+
 def test_gate_configuration_sharding(engine):
     """one network spread over ranks by gate configuration (measure_perc.measure_fullnet_distributed):
     the shards of a 2-rank split add up to the unsharded result bit for bit"""
