@@ -23,7 +23,7 @@ namespace cg = cooperative_groups;
 
 namespace {
 #ifndef CNT_CLUSTER_THREADS
-#define CNT_CLUSTER_THREADS 1024
+#define CNT_CLUSTER_THREADS 512
 #endif
 constexpr int CT = CNT_CLUSTER_THREADS;   // threads per CTA
 constexpr int MAXR = 6144 / CT;       // rows per thread
@@ -52,6 +52,7 @@ struct CArgs {
     double *rglob;           // [NSLAB*R] r published once per iteration for the segment sums
     double *segS;            // [nseg]
     long long *dbg;          // [gridDim.x][16] per-phase cycle sums (NULL = off)
+    int bankopt;             // 1: bank-aware entry order (setup)
     int mb;                  // 1: transaction barriers instead of cluster barriers inside the iteration
     int *assert_flag;        // first failed in-kernel bounds check (0 = none)
     double rtol;
@@ -79,7 +80,7 @@ struct Shared {
 #define KCHECK(id, cond) ((cond) ? true : (atomicCAS(a.assert_flag, 0, (id)), false))
 #define PHASE(i)                                                   \
     do {                                                           \
-        if (a.dbg && threadIdx.x == 0) {                           \
+        if (PROF && a.dbg && threadIdx.x == 0) {                           \
             long long c_ = clock64();                              \
             sh->tacc[i] += c_ - sh->tlast;                         \
             sh->tlast = c_;                                        \
@@ -355,6 +356,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster(CArgs a) {
 // =====================================================================================
 constexpr int MAXR2 = 5120 / CT;       // rows per thread
 constexpr int CAP2 = CT * MAXR2;       // rows per CTA (5120)
+constexpr int NRS = 4096 / CT;         // row slots of the variant for chunks of up to 4096 rows
 constexpr int ECAP = 20224;            // packed entries per CTA
 constexpr int HCAP = 2048;             // halo references per CTA
 
@@ -546,8 +548,9 @@ __device__ __forceinline__ void push_segment_sums(cg::cluster_group &cluster, co
     }
 }
 
-// NR = row slots per thread (registers): 4 when every CTA's chunk has at most 4*CT rows, else 5
-template <bool TWO, int NR>
+// NR = row slots per thread (registers): 4 when every CTA's chunk has at most 4*CT rows, else 5;
+// PROF = per-phase cycle accumulators compiled in (launched only when a phase buffer is set)
+template <bool TWO, int NR, bool PROF>
 __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     cg::cluster_group cluster = cg::this_cluster();
@@ -706,8 +709,54 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                                 sh->ovf = 1;
                             }
                         }
-                        if (KCHECK(4, (dst - ent) + j * 32 < ECAP)) dst[j * 32] = (slot << 8) | cl;
+                        if (KCHECK(4, (dst - ent) + j * 32 < ECAP)) dst[j * 32] = (slot << 14) | (cl << 3);   // byte offsets: p_ext << 11 | gval
                     }
+                }
+            }
+        }
+        // (3b) bank-aware entry order: the SpMV gathers p_ext[slot] of the j-th entries of 32 rows at
+        // once; 16 random 8-byte words per half-warp hit the 16 bank pairs ~3 deep.  Row sums do not
+        // care about the order of a row's entries, so every row (lanes one after the other, first
+        // 8 columns) greedily puts into column j the entry whose bank is least used in that column
+        // (deterministic; costs ~8 iterations' worth of setup per system, gains 1.3 % per iteration).
+        if (fits && a.bankopt) {
+            __syncthreads();                                    // all entries packed, halo slots assigned
+            uint8_t *tab = reinterpret_cast<uint8_t *>(r_s) + 24576 + (t >> 5) * 256;   // [half][col < 8][bank pair]
+#pragma unroll
+            for (int k = 0; k < NR; k++) {
+                reinterpret_cast<unsigned long long *>(tab)[lane] = 0ull;
+                __syncwarp();
+                const int p = k * CT + ((k & 1) ? (CT - 1 - t) : t);
+                const int n8 = meta_r[k] >= 0 ? min(meta_r[k] >> 16, 8) : 0;
+                unsigned *dst = ent + gbase[p >> 5] + (p & 31);
+                uint8_t *tb = tab + (lane >> 4) * 128;
+                for (int L = 0; L < 32; L++) {
+                    if (lane == L) {
+                        // halo slots are handed out by an atomic counter: only the entries that point at
+                        // the CTA's own rows (deterministic positions) take part; they move to the front
+                        // (stable), the halo entries keep their order behind them
+                        int nl = 0;
+                        for (int i = 0; i < n8; i++) {
+                            unsigned u = dst[i * 32];
+                            if ((int)(u >> 14) < nown) {
+                                for (int m = i; m > nl; m--) dst[m * 32] = dst[(m - 1) * 32];
+                                dst[nl * 32] = u;
+                                nl++;
+                            }
+                        }
+                        for (int j = 0; j < nl; j++) {
+                            int best = j, bestc = 256;
+                            for (int i = j; i < nl; i++) {
+                                int c = tb[j * 16 + ((dst[i * 32] >> 14) & 15u)];
+                                if (c < bestc) { bestc = c; best = i; }
+                            }
+                            unsigned eb = dst[best * 32];
+                            dst[best * 32] = dst[j * 32];
+                            dst[j * 32] = eb;
+                            tb[j * 16 + ((eb >> 14) & 15u)]++;
+                        }
+                    }
+                    __syncwarp();
                 }
             }
         }
@@ -932,11 +981,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     double pi = p_ext[p];
                     double q = d_r[k] * pi;
                     const unsigned *e = ent + gbase[p >> 5] + (p & 31);
+                    const char *gb = reinterpret_cast<const char *>(gval), *pb = reinterpret_cast<const char *>(p_ext);
+#pragma unroll 2
                     for (int j = 0; j < len; j++) {
-                        unsigned u = e[j * 32];
-                        q += gval[u & 255u] * p_ext[u >> 8];
+                        unsigned u = e[j * 32];             // (byte offset into p_ext) << 11 | byte offset into gval
+                        q += *reinterpret_cast<const double *>(gb + (u & 2047u)) * *reinterpret_cast<const double *>(pb + (u >> 11));
                     }
-                    KCHECK(20, (e - ent) + (len - 1) * 32 < ECAP || len == 0);
                     qz_r[k] = q;
                     s1[0] += pi * q;
                 }
@@ -1110,7 +1160,7 @@ extern "C" int cnt_pcg_cluster_active(int C) {
     cudaLaunchAttribute attr[1];
     int n = 0;
     if (C < 1 || C > MAXC) return 0;
-    if (launch_config(k_pcg_cluster2<true, MAXR2>, SMEM2_BYTES, C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
+    if (launch_config(k_pcg_cluster2<true, MAXR2, false>, SMEM2_BYTES, C, &cfg, attr, nullptr, &n) != CNT_OK) return 0;
     return n;
 }
 
@@ -1172,10 +1222,13 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     cudaLaunchAttribute attr[1];
     int nclusters = 0;
     // chunks of at most 4*CT rows run the variant with 4 row slots per thread (no register spills)
-    const bool small = ((int64_t)max_rows + C - 1) / C <= 4 * CT && !getenv("CNT_CLUSTER_NR5");
+    const bool small = ((int64_t)max_rows + C - 1) / C <= NRS * CT && !getenv("CNT_CLUSTER_NR5");
     kernel_t kern = !v2 ? k_pcg_cluster
-                        : two ? (small ? k_pcg_cluster2<true, 4> : k_pcg_cluster2<true, MAXR2>)
-                              : (small ? k_pcg_cluster2<false, 4> : k_pcg_cluster2<false, MAXR2>);
+                        : g_phase_dbg
+                              ? (two ? (small ? k_pcg_cluster2<true, NRS, true> : k_pcg_cluster2<true, MAXR2, true>)
+                                     : (small ? k_pcg_cluster2<false, NRS, true> : k_pcg_cluster2<false, MAXR2, true>))
+                              : (two ? (small ? k_pcg_cluster2<true, NRS, false> : k_pcg_cluster2<true, MAXR2, false>)
+                                     : (small ? k_pcg_cluster2<false, NRS, false> : k_pcg_cluster2<false, MAXR2, false>));
     int rc = launch_config(kern, v2 ? SMEM2_BYTES : SMEM_BYTES, C, &cfg, attr, st, &nclusters);
     if (rc) return rc;
     if (nclusters > NSYS) nclusters = NSYS;
@@ -1188,6 +1241,7 @@ extern "C" int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *
     a.rglob = rglob; a.segS = segS;
     a.dbg = g_phase_dbg;
     a.assert_flag = assert_flag;
+    a.bankopt = getenv("CNT_CLUSTER_NOBANKOPT") ? 0 : 1;     // measured: 1.3 % per iteration
     a.mb = getenv("CNT_CLUSTER_NOMB") ? 0 : 1;     // reference path: cluster barriers
     if (two) a.agg = *agg; else a.agg = cnt_aggregates{};
     a.iters = iters; a.status = status; a.relres = relres;

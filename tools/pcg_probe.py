@@ -31,7 +31,7 @@ with eng._work():
         torch.cuda.synchronize(); print("aggregates setup: %.1f ms, (nagg, nseg) = %s" % (1e3 * (time.perf_counter() - t0), eng.last_aggregates), flush=True)
 # A/B switches: PROBE_AB="CNT_CLUSTER_NR5" runs every case with the variable set and unset, interleaved
 ab = os.environ.get("PROBE_AB", "")
-variants = [(ab, "1"), (ab, None)] if ab else [("", None)]
+variants = [(ab, v) for v in os.environ.get("PROBE_AB_VALUES", "1").split(",")] + [(ab, None)] if ab else [("", None)]
 for precond in preconds:
     for method in methods:
         for rep in range(3 * len(variants)):
