@@ -72,7 +72,9 @@ struct Shared {
     unsigned long long mbar[4];   // v2: transaction barriers: reductions (2 slots), halo of p, segment sums
     long long tlast;       // phase timing (debug): last timestamp, per-phase cycle sums
     long long tacc[16];
+    long long pad16;       // sizeof(Shared) is a multiple of 16: the arrays behind it stay 16-byte aligned
 };
+static_assert(sizeof(Shared) % 16 == 0, "shared-memory layout alignment");
 // phase timing: thread 0 of every CTA accumulates clock64() deltas per phase when a debug
 // buffer is given (tools/pcg_probe.py); costs one predictable branch otherwise
 // cheap in-kernel bounds assertions (compute-sanitizer is not available on the target pool):
@@ -467,29 +469,37 @@ __device__ __forceinline__ double block_open_run_carry(double trail, bool has_en
     return carry;
 }
 
-template <int K>
+template <int K, bool PAD>
 __device__ __forceinline__ void smem_segscan_sums(double *seg_loc, double *scratch, const double *r_s,
                                                   const uint16_t *segm, int meta, int M) {
     const int base = (int)threadIdx.x * K;
     double v[K];
+    if (K == 8 && PAD) {
+        // PAD: members M .. K*CT-1 of the list point at a slot of r_s that holds 0 -> no bounds checks,
+        // and the thread's 8 indices are one 16-byte load
+        const uint4 w = *reinterpret_cast<const uint4 *>(segm + base);
+        v[0] = r_s[w.x & 0xFFFFu]; v[1] = r_s[w.x >> 16]; v[2] = r_s[w.y & 0xFFFFu]; v[3] = r_s[w.y >> 16];
+        v[4] = r_s[w.z & 0xFFFFu]; v[5] = r_s[w.z >> 16]; v[6] = r_s[w.w & 0xFFFFu]; v[7] = r_s[w.w >> 16];
+    } else {
 #pragma unroll
-    for (int q = 0; q < K; q++) v[q] = base + q < M ? r_s[segm[base + q]] : 0.0;
-    const int ef = meta >> 16;
-    int sidx = meta & 0xFFFF;
+        for (int q = 0; q < K; q++) v[q] = base + q < M ? r_s[segm[base + q]] : 0.0;
+    }
+    // branch-free walk: running sum, closed at every end flag; the first closed run still needs the
+    // carry from the threads before, later ones are complete and go straight to seg_loc
+    const unsigned ef = (unsigned)meta >> 16;
+    const int s0 = meta & 0xFFFF;
     double run = 0.0, first = 0.0;
-    bool got = false;
 #pragma unroll
     for (int q = 0; q < K; q++) {
         run += v[q];
-        if ((ef >> q) & 1) {
-            if (!got) { first = run; got = true; }
-            else seg_loc[sidx] = run;                                 // run opened and closed in this thread
-            if (got) sidx++;
-            run = 0.0;
-        }
+        const bool fl = (ef >> q) & 1u;
+        const unsigned before = ef & ((1u << q) - 1u);
+        if (fl && before == 0u) first = run;
+        if (fl && before != 0u) seg_loc[s0 + __popc(before)] = run;
+        if (fl) run = 0.0;
     }
-    const double carry = block_open_run_carry(run, ef != 0, scratch, (M + K - 1) / K);
-    if (ef != 0) seg_loc[meta & 0xFFFF] = carry + first;
+    const double carry = block_open_run_carry(run, ef != 0u, scratch, (M + K - 1) / K);
+    if (ef != 0u) seg_loc[s0] = carry + first;
 }
 
 // coarse value of every local aggregate = 1/E * (sum of the aggregate's segment sums, in global
@@ -568,7 +578,8 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     int *gbase = iscr + 36;                                                     // CAP2 / 32
     uint16_t *slot_s = reinterpret_cast<uint16_t *>(gbase + CAP2 / 32);         // CAP2: row -> local aggregate
     // two-level tables of this CTA (shared memory only in the iteration)
-    double *seg_loc = reinterpret_cast<double *>(slot_s + CAP2);                // LCAP sums of this CTA's segments
+    uint16_t *segm = slot_s + CAP2;                                             // MCAP member rows (positions), 16-byte aligned
+    double *seg_loc = reinterpret_cast<double *>(segm + MCAP);                  // LCAP sums of this CTA's segments
     double *c_loc = seg_loc + LCAP;                                             // LCAP coarse values
     double *ref_val = c_loc + LCAP;                                             // RCAP segment sums pushed by their owners
     uint32_t *rpush_list = reinterpret_cast<uint32_t *>(ref_val + RCAP);        // RCAP: consumer << 18 | its reference << 9 | own segment
@@ -578,7 +589,6 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
     uint16_t *la_qn = reinterpret_cast<uint16_t *>(la_einv + LCAP);             // LCAP segments of aggregate
     uint16_t *la_a = la_qn + LCAP;                                              // LCAP own segment / first reference
     uint16_t *segoff = la_a + LCAP;                                             // LCAP + 2
-    uint16_t *segm = segoff + LCAP + 2;                                         // MCAP member rows (local index)
     const int t = threadIdx.x, lane = t & 31;
     if (t == 0) {
         for (int i = 0; i < 16; i++) sh->tacc[i] = 0;
@@ -853,6 +863,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
                     seg_meta = lo | (ef << 16);
                 }
                 seg_M = M;
+                if (NR == NRS) {
+                    // padding of the member list (see smem_segscan_sums): positions of this variant stay
+                    // below NRS*CT, so the last slot of r_s is free to hold the zero the padding points at
+                    for (int i = M + t; i < NRS * CT; i += CT) segm[i] = (uint16_t)(CAP2 - 1);
+                    if (t == 0) r_s[CAP2 - 1] = 0.0;
+                }
             }
         }
         __syncthreads();
@@ -924,7 +940,7 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
         }
         if (TWO) {
             __syncthreads();                                    // r_s complete in this CTA
-            smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
+            smem_segscan_sums<NR, NR == NRS>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
             __syncthreads();
             if (mb) push_segment_sums_mb(seg_loc, ref_val, rpush_list, nrpush, &sh->mbar[3]);
             else push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
@@ -1021,11 +1037,12 @@ __global__ void __launch_bounds__(CT, 1) k_pcg_cluster2(CArgs a) {
             if (TWO) {
                 __syncthreads();                                // r_s complete in this CTA
                 PHASE(12);                                      // (debug) wait for the CTA's other warps
-                smem_segscan_sums<NR>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
+                smem_segscan_sums<NR, NR == NRS>(seg_loc, scratch, r_s, segm, seg_meta, seg_M);
                 __syncthreads();
+                PHASE(15);                                      // (debug) segmented reduction alone
                 if (mb) push_segment_sums_mb(seg_loc, ref_val, rpush_list, nrpush, &sh->mbar[3]);
                 else push_segment_sums(cluster, seg_loc, ref_val, rpush_list, nrpush);
-                PHASE(6);                                       // segment sums
+                PHASE(6);                                       // pushes of the segment sums
                 WAIT_PUSHED(3, nref_in);                        // segment sums of the other CTAs are here
                 PHASE(7);                                       // barrier
                 smem_coarse_values(seg_loc, la_a, la_qn, la_einv, ref_val, scratch, c_loc, nla, nrefs, ref_meta);

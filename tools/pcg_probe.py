@@ -56,7 +56,7 @@ for precond in preconds:
 if "cluster" in methods:
     names = ["idle/queue", "setup+init", "halo refresh", "SpMV", "reduce1(+wait)", "x,r update", "segment sums",
              "barrier(seg)", "coarse+z", "reduce2(+wait)", "p update+publish", "barrier(p)", "  wait warps(r)", "  coarse values",
-             "  wait warps(c)"]
+             "  wait warps(c)", "  segmented reduction"]
     dbg = torch.zeros(148 * 16, dtype=torch.int64, device=eng.device)
     lib.cnt_pcg_cluster_set_phase_buffer(C_void_p(dbg.data_ptr()))
     sol = eng.solve(b, sysm, rtol=1e-30, maxit=maxit, method="cluster", slab_priority=[0, 3, 2, 1], precond=preconds[0])
