@@ -130,6 +130,16 @@ class Engine(object):
         self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
         self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
 
+    def twin(self):
+        """A second Engine on the same GPU (own stream and events, same settings).  Two engines
+        driven by two host threads pipeline an ensemble: while the persistent PCG kernel of one
+        batch holds 112 SMs, the generation / junction / assembly kernels of the next batch run on
+        the SMs it leaves free and the host work of both overlaps (run_pipelined)."""
+        other = Engine(self.device, profile=self.profile)
+        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune"):
+            setattr(other, k, getattr(self, k))
+        return other
+
     # ------------------------------------------------------------------ helpers
     @contextlib.contextmanager
     def _work(self, stage=None):
@@ -713,6 +723,45 @@ class Engine(object):
         out["seed"] = np.asarray(seeds, dtype=np.uint64)
         out["rows"] = np.diff(np.asarray(b.h_roff))
         out["nnz_offdiag"] = self.nnz_per_network(b)
+        return out
+
+    def run_pipelined(self, jobs, fn, other=None):
+        """Run fn(engine, job) for every job, alternating between this engine and its twin on two
+        host threads (job k on engine k % 2), each thread inside its engine's stream so that
+        nothing is ordered through the shared default stream.  Results in job order.  Networks
+        are independent and seeded individually, so the results do not depend on the split."""
+        import threading
+        if len(jobs) < 2:
+            return [fn(self, j) for j in jobs]
+        if other is None:
+            if getattr(self, "_twin", None) is None:
+                self._twin = self.twin()
+            other = self._twin
+        engines = (self, other)
+        cur = torch.cuda.current_stream(self.device)
+        out = [None] * len(jobs)
+        err = []
+
+        def worker(w):
+            eng = engines[w]
+            try:
+                torch.cuda.set_device(eng.device)
+                eng.stream.wait_stream(cur)
+                with torch.cuda.stream(eng.stream):
+                    for k in range(w, len(jobs), 2):
+                        out[k] = fn(eng, jobs[k])
+            except BaseException as e:      # re-raised in the caller
+                err.append(e)
+
+        threads = [threading.Thread(target=worker, args=(w,)) for w in range(2)]
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        for eng in engines:
+            cur.wait_stream(eng.stream)
+        if err:
+            raise err[0]
         return out
 
     def nnz_per_network(self, b):

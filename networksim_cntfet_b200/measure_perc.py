@@ -24,6 +24,8 @@ from .cnet import FermiDiracTransistor, LinExpTransistor
 elements = [FermiDiracTransistor, LinExpTransistor]
 FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'ioff', 'gate', 'fname', 'seed',
                    'onoffmap']
+PIPELINE = False              # True: the batches of a call alternate between two engines / host threads (measured
+                              # gain at 100x100 um: 0.7-2 %, the step is one long kernel already; results identical)
 BATCH_STICKS = 1_450_000      # sticks per GPU batch of the ensemble path (14 networks at 100x100 um = 8 full rounds
                               # of the 7 resident 16-CTA clusters)
 
@@ -139,20 +141,28 @@ def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l
     pinned[:len(ns)] = torch.as_tensor(ns, dtype=torch.int64)
     pinned[len(ns):] = torch.from_numpy(seeds_np.view(np.int64).copy())
     dev_in = pinned.to(eng.device, non_blocking=True)          # H2D of this call's inputs
-    frames = []
-    d2h = 0
+    batches = []
     start = 0
     while start < len(ns):                                     # batches bounded by stick count
         stop, tot = start, 0
         while stop < len(ns) and (stop == start or tot + ns[stop] + 2 <= BATCH_STICKS):
             tot += ns[stop] + 2
             stop += 1
-        sl = slice(start, stop)
-        res = eng.measure_ensemble(ns[sl], scaling, seeds_np[sl], onoffmap=onoffmap, element=element, l=l, rtol=rtol,
-                                   seeds_dev=dev_in[len(ns) + start:len(ns) + stop])
+        batches.append(slice(start, stop))
+        start = stop
+
+    def one(e, sl):
+        return e.measure_ensemble(ns[sl], scaling, seeds_np[sl], onoffmap=onoffmap, element=element, l=l, rtol=rtol,
+                                  seeds_dev=dev_in[len(ns) + sl.start:len(ns) + sl.stop])
+
+    # two engines on two host threads: the next batch is generated and assembled while the PCG
+    # kernel of the current one runs (Engine.run_pipelined)
+    results = eng.run_pipelined(batches, one) if PIPELINE else [one(eng, sl) for sl in batches]
+    frames = []
+    d2h = 0
+    for sl, res in zip(batches, results):
         d2h += sum(int(np.asarray(v).nbytes) for k, v in res.items() if isinstance(v, np.ndarray))
         frames.append(_rows_from_ensemble(res, ns[sl], scaling, seeds_np[sl], onoffmap))
-        start = stop
     del dev_in
     df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=FULLNET_COLUMNS)
     if return_io:

@@ -149,6 +149,24 @@ def test_full_size_properties(engine):
         assert np.array_equal(res[key], again[key]), key
 
 
+def test_pipelined_batches_equal_sequential(engine, monkeypatch):
+    """measure_perc.PIPELINE: the batches of one call alternate between two engines on two host
+    threads (Engine.run_pipelined); every network is seeded individually -> identical rows"""
+    import networksim_cntfet_b200 as pkg
+    from networksim_cntfet_b200 import measure_perc
+    pkg.set_engine(engine)
+    ns = [3000, 3600, 4000, 4400, 5200, 6400, 3800, 4100]
+    seeds = list(range(501, 509))
+    monkeypatch.setattr(measure_perc, "BATCH_STICKS", 9000)        # 2 networks per batch -> 4+ batches
+    monkeypatch.setattr(measure_perc, "PIPELINE", False)
+    a = measure_perc.measure_ensemble(ns, 20, seeds, onoffmap=1)
+    monkeypatch.setattr(measure_perc, "PIPELINE", True)
+    b = measure_perc.measure_ensemble(ns, 20, seeds, onoffmap=1)
+    assert len(a) == len(b) and len(a) >= len(ns)
+    for col in ("sticks", "nclust", "maxclust", "ion", "ioff", "gate", "seed"):
+        assert a[col].tolist() == b[col].tolist(), col
+
+
 def test_gate_configuration_sharding(engine):
     """one network spread over ranks by gate configuration (measure_perc.measure_fullnet_distributed):
     the shards of a 2-rank split add up to the unsharded result bit for bit"""
