@@ -486,11 +486,13 @@ class Engine(object):
                 chunk_C = lib.cnt_pcg_cluster_size(max_rows, max_nnz) if compressed else 0
                 if auto and compressed and lib.cnt_pcg_cluster_active(chunk_C) <= 0:
                     method, compressed, chunk_C = "flat", False, 0      # cluster launch not possible here
-                agg = self._aggregates(b, sysm, sys_net, sys_slab, chunk_C) if precond == "twolevel" else None
+                with self._work("pcg_aggregates"):
+                    agg = self._aggregates(b, sysm, sys_net, sys_slab, chunk_C) if precond == "twolevel" else None
                 self.last_solver = method
                 if method == "cluster":
                     ws = self._ws(lib.cnt_pcg_cluster_workspace_bytes(nsys, NS, R))
-                    check(lib.cnt_pcg_cluster_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab),
+                    with self._work("pcg_kernel"):
+                      check(lib.cnt_pcg_cluster_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab),
                                                     b.c_roff, R, NNZ, _p(b.rowptr), _p(b.col), _p(sysm["val"]),
                                                     _p(sysm.get("cls")) if self.cluster_compressed else None,
                                                     _p(sysm.get("gneg")) if self.cluster_compressed else None,
