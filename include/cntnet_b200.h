@@ -138,6 +138,21 @@ int cnt_prune_leaves(int B, const int32_t *soff, const int32_t *joff, int64_t S,
                      const int32_t *stick1, const int32_t *stick2, const int32_t *label, const int32_t *stats,
                      uint8_t *alive, int32_t *attach, int32_t *h_rounds, void *ws, int64_t ws_bytes, void *stream);
 
+/* (3c) optional second exact reduction: series elimination.  A stick of the 2-core with exactly
+ *     two junctions, both to ordinary sticks, is replaced by ONE virtual junction between its two
+ *     neighbours (conductance g1 g2 / (g1 + g2), evaluated per gate configuration by
+ *     cnt_assemble_values); afterwards V = (g1 V_a + g2 V_c) / (g1 + g2) (cnt_currents).  Only an
+ *     independent set is eliminated (no chains), chosen from the topology alone.
+ *     elim_vid[S]: virtual junction of an eliminated stick, -1 otherwise; voff[B+1]: virtual
+ *     junctions per network; va, vc [capacity S]: the neighbours (network-local, va < vc);
+ *     ve1, ve2: the stick's junctions to va / vc (rows of the junction table).  Entries of virtual
+ *     junction v carry the junction id J + v in nz_eid.  Synchronises the stream. */
+int64_t cnt_series_workspace_bytes(int64_t n_sticks_total);
+int cnt_series_select(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
+                      const int32_t *stick1, const int32_t *stick2, const uint8_t *alive,
+                      int32_t *elim_vid, int32_t *voff, int32_t *va, int32_t *vc, int32_t *ve1, int32_t *ve2,
+                      int64_t *h_nv, void *ws, int64_t ws_bytes, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * (4) MNA assembly -- replaces populate_graph (netsim.py:192-195), update_conductivity,
  *     make_G, make_A, make_z (cnet.py:99-131) in the reduced SPD form
@@ -159,6 +174,7 @@ int cnt_prune_leaves(int B, const int32_t *soff, const int32_t *joff, int64_t S,
 int64_t cnt_assemble_workspace_bytes(int64_t n_sticks_total);
 int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
                       const uint8_t *alive /* from cnt_prune_leaves, or NULL = whole component */,
+                      const int32_t *elim_vid /* from cnt_series_select, or NULL */,
                       int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream);
 /* optional, between _rows and _pattern_count: renumber every network's unknown rows in Z-order
  * (Morton code) of the stick centres so that neighbouring sticks get neighbouring rows (SpMV
@@ -170,11 +186,14 @@ int cnt_assemble_reorder(int B, const int32_t *h_roff, int64_t S, int64_t R, con
                          int32_t *urow, void *ws, int64_t ws_bytes, void *stream);
 int cnt_assemble_pattern_count(int B, const int32_t *soff, const int32_t *joff, int64_t J,
                                const int32_t *stick1, const int32_t *stick2,
-                               const int32_t *urow, int64_t R, int32_t *rowcnt, void *stream);
+                               const int32_t *urow, int64_t R, int32_t *rowcnt,
+                               int64_t NV, const int32_t *voff, const int32_t *va, const int32_t *vc /* virtual junctions or 0/NULL */,
+                               void *stream);
 int cnt_assemble_pattern_fill(int B, const int32_t *soff, const int32_t *joff, int64_t J,
                               const int32_t *stick1, const int32_t *stick2,
                               const int32_t *urow, const int32_t *roff, int64_t R, const int32_t *rowptr,
                               int32_t *col, int32_t *nz_eid, int32_t *src_eid, int32_t *drn_eid,
+                              int64_t NV, const int32_t *voff, const int32_t *va, const int32_t *vc,
                               void *ws, int64_t ws_bytes, void *stream);
 /* row_stick[r] = local stick index of unknown row r (inverse of urow). */
 int cnt_assemble_row_stick(int B, const int32_t *soff, int64_t S, const int32_t *urow,
@@ -186,6 +205,8 @@ int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, c
                         int64_t R, const int32_t *rowptr, const int32_t *nz_eid,
                         const int32_t *src_eid, const int32_t *drn_eid,
                         double *g, double *val, double *diag, double *rhs, uint8_t *cls /* may be NULL */,
+                        const int32_t *ve1, const int32_t *ve2 /* from cnt_series_select, or NULL; then the classes
+                        9*nlevels ... are the pairs (c1 <= c2) of base classes in row-major triangular order */,
                         void *stream);
 
 /* ---------------------------------------------------------------------------------------
@@ -294,6 +315,8 @@ int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, 
 int cnt_currents(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
                  const int32_t *stick1, const int32_t *stick2, const int32_t *label, const int32_t *stats,
                  const int32_t *urow, const int32_t *attach /* from cnt_prune_leaves, or NULL */,
+                 const int32_t *elim_vid, const int32_t *va, const int32_t *vc, const int32_t *ve1,
+                 const int32_t *ve2 /* from cnt_series_select, or all NULL */,
                  const double *g, const double *x, double *V, double *I, double *isrc, void *stream);
 
 #ifdef __cplusplus

@@ -34,14 +34,16 @@ PROTOTYPES = {
     "cnt_assemble_workspace_bytes": (i64, [i64]),
     "cnt_prune_workspace_bytes": (i64, [i64]),
     "cnt_prune_leaves": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
-    "cnt_assemble_rows": (i32, [i32, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "cnt_series_workspace_bytes": (i64, [i64]),
+    "cnt_series_select": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "cnt_assemble_rows": (i32, [i32, vp, i64, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_reorder_workspace_bytes": (i64, [i64, i32]),
     "cnt_assemble_reorder": (i32, [i32, I32P, i64, i64, vp, vp, vp, vp, i64, vp]),
-    "cnt_assemble_pattern_count": (i32, [i32, vp, vp, i64, vp, vp, vp, i64, vp, vp]),
-    "cnt_assemble_pattern_fill": (i32, [i32, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "cnt_assemble_pattern_count": (i32, [i32, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp, vp, vp, vp]),
+    "cnt_assemble_pattern_fill": (i32, [i32, vp, vp, i64, vp, vp, vp, vp, i64, vp, vp, vp, vp, vp, i64, vp, vp, vp, vp, i64, vp]),
     "cnt_assemble_row_stick": (i32, [i32, vp, i64, vp, vp, vp]),
     "cnt_gate_levels": (i32, [i64, vp, vp, vp, i32, u8, i32, f64, f64, f64, f64, u8, vp]),
-    "cnt_assemble_values": (i32, [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cnt_assemble_values": (i32, [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cnt_pcg_aggregate_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_aggregates": (i32, [i32, i32, i32, I32P, I32P, I32P, vp, i64, i64, vp, vp, vp, vp, f64] + [vp] * 9 +
                            [i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
@@ -53,7 +55,7 @@ PROTOTYPES = {
     "cnt_pcg_cluster_size": (i32, [i64, i64]),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i32, vp, i64, vp]),
-    "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 # entry points that may be absent from an older build of the library (checked by tests
 # against the header, never silently replaced)

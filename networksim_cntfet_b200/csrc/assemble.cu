@@ -12,13 +12,14 @@ namespace {
 
 __global__ void k_row_flags(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ label,
                             const int32_t *__restrict__ stats, const uint8_t *__restrict__ alive,
-                            int32_t *__restrict__ flag) {
+                            const int32_t *__restrict__ elim_vid, int32_t *__restrict__ flag) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int b = cnt::find_segment(soff, B, (int)s);
     int i = (int)s - soff[b];
     bool in = stats[(int64_t)b * CNT_NSTAT + CNT_STAT_PERCOLATING] && i >= 2 && label[s] == 0;
     if (alive) in = in && alive[s];     // dangling sticks pruned by cnt_prune_leaves
+    if (elim_vid) in = in && elim_vid[s] < 0;     // series sticks eliminated by cnt_series_select
     flag[s] = in ? 1 : 0;
 }
 
@@ -36,7 +37,7 @@ __global__ void k_pattern(int B, const int32_t *__restrict__ soff, const int32_t
                           const int32_t *__restrict__ urow, const int32_t *__restrict__ roff,
                           const int32_t *__restrict__ rowptr, int32_t *__restrict__ rowcnt /* count or cursor */,
                           int32_t *__restrict__ col, int32_t *__restrict__ nz_eid, int32_t *__restrict__ src_eid,
-                          int32_t *__restrict__ drn_eid) {
+                          int32_t *__restrict__ drn_eid, int eid_base) {
     int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= J) return;
     int b = cnt::find_segment(joff, B, (int)e);
@@ -48,9 +49,9 @@ __global__ void k_pattern(int B, const int32_t *__restrict__ soff, const int32_t
         if (FILL) {
             int r0 = roff[b];
             col[rowptr[ua] + ka] = uc - r0;
-            nz_eid[rowptr[ua] + ka] = (int)e;
+            nz_eid[rowptr[ua] + ka] = eid_base + (int)e;
             col[rowptr[uc] + kc] = ua - r0;
-            nz_eid[rowptr[uc] + kc] = (int)e;
+            nz_eid[rowptr[uc] + kc] = eid_base + (int)e;
         }
     } else if (FILL && uc >= 0) {   // a is an electrode of the percolating component
         if (a == 0) src_eid[uc] = (int)e;
@@ -58,7 +59,8 @@ __global__ void k_pattern(int B, const int32_t *__restrict__ soff, const int32_t
     }
 }
 
-// sort every row by column (rows are short) so the pattern is deterministic
+// sort every row by (column, junction) (rows are short) so the pattern is deterministic even
+// with parallel entries (a virtual series junction next to a real one)
 __global__ void k_sort_rows(int64_t R, const int32_t *__restrict__ rowptr, int32_t *__restrict__ col,
                             int32_t *__restrict__ nz_eid) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -67,7 +69,7 @@ __global__ void k_sort_rows(int64_t R, const int32_t *__restrict__ rowptr, int32
     for (int a = k0 + 1; a < k1; a++) {
         int cc = col[a], ee = nz_eid[a];
         int c = a - 1;
-        while (c >= k0 && col[c] > cc) {
+        while (c >= k0 && (col[c] > cc || (col[c] == cc && nz_eid[c] > ee))) {
             col[c + 1] = col[c];
             nz_eid[c + 1] = nz_eid[c];
             c--;
@@ -105,21 +107,44 @@ __global__ void k_conductance(int64_t J, const uint8_t *__restrict__ kind2, cons
     if (e < J) g[e] = gtable[(int)kind2[e] * nlevels + (int)level[e]];
 }
 
-// one thread per row: fixed summation order (columns ascending, then source, then drain)
+// conductance of two junctions in series, with fixed roundings (the host builds the same table)
+__device__ __forceinline__ double series_g(double g1, double g2) {
+    return __ddiv_rn(__dmul_rn(g1, g2), __dadd_rn(g1, g2));
+}
+// one thread per row: fixed summation order (columns ascending, then source, then drain).
+// Entries with junction id >= J are virtual series junctions: conductance g1 g2 / (g1 + g2) of the
+// eliminated stick's two junctions; their class is the pair class nb + tri(c1, c2) (c1 <= c2) of
+// the two base classes, nb = 9 * nlevels.
 __global__ void k_values(int64_t R, const int32_t *__restrict__ rowptr, const int32_t *__restrict__ nz_eid,
                          const int32_t *__restrict__ src_eid, const int32_t *__restrict__ drn_eid,
                          const double *__restrict__ g, double *__restrict__ val, double *__restrict__ diag,
                          double *__restrict__ rhs, const uint8_t *__restrict__ kind2,
-                         const uint8_t *__restrict__ level, int nlevels, uint8_t *__restrict__ cls) {
+                         const uint8_t *__restrict__ level, int nlevels, uint8_t *__restrict__ cls, int64_t J,
+                         const int32_t *__restrict__ ve1, const int32_t *__restrict__ ve2) {
     int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= R) return;
     int k0 = rowptr[r], k1 = rowptr[r + 1];
+    const int nb = 9 * nlevels;
     double sum = 0.0;
     for (int k = k0; k < k1; k++) {
         int e = nz_eid[k];
-        double ge = g[e];
+        double ge;
+        int c;
+        if (e < J) {
+            ge = g[e];
+            c = cls ? (int)kind2[e] * nlevels + (int)level[e] : 0;
+        } else {
+            int e1 = ve1[e - J], e2 = ve2[e - J];
+            ge = series_g(g[e1], g[e2]);
+            c = 0;
+            if (cls) {
+                int c1 = (int)kind2[e1] * nlevels + (int)level[e1], c2 = (int)kind2[e2] * nlevels + (int)level[e2];
+                if (c1 > c2) { int t = c1; c1 = c2; c2 = t; }
+                c = nb + c1 * nb - c1 * (c1 - 1) / 2 + (c2 - c1);
+            }
+        }
         val[k] = -ge;
-        if (cls) cls[k] = (uint8_t)((int)kind2[e] * nlevels + (int)level[e]);   // index into the value table
+        if (cls) cls[k] = (uint8_t)c;                    // index into the value table
         sum += ge;
     }
     int se = src_eid[r], de = drn_eid[r];
@@ -137,7 +162,7 @@ extern "C" int64_t cnt_assemble_workspace_bytes(int64_t S) {
 }
 
 extern "C" int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const int32_t *label, const int32_t *stats,
-                                 const uint8_t *alive, int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream) {
+                                 const uint8_t *alive, const int32_t *elim_vid, int32_t *urow, int32_t *roff, void *ws, int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && soff && label && stats && urow && roff && ws && S >= B);
     cnt::Workspace w(ws, ws_bytes);
@@ -149,7 +174,7 @@ extern "C" int cnt_assemble_rows(int B, const int32_t *soff, int64_t S, const in
         cnt::set_error("assemble workspace too small");
         return CNT_ECAPACITY;
     }
-    k_row_flags<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, label, stats, alive, flag);
+    k_row_flags<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, label, stats, alive, elim_vid, flag);
     CNT_LAUNCHED();
     int rc = cnt_exclusive_scan_i32(flag, scan, S, 1, sws, sb, stream);
     if (rc) return rc;
@@ -227,13 +252,20 @@ extern "C" int cnt_assemble_reorder(int B, const int32_t *h_roff, int64_t S, int
 
 extern "C" int cnt_assemble_pattern_count(int B, const int32_t *soff, const int32_t *joff, int64_t J,
                                           const int32_t *stick1, const int32_t *stick2, const int32_t *urow, int64_t R,
-                                          int32_t *rowcnt, void *stream) {
+                                          int32_t *rowcnt, int64_t NV, const int32_t *voff, const int32_t *va,
+                                          const int32_t *vc, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && soff && joff && urow && rowcnt && R >= 0 && J >= 0);
     CNT_CUDA(cudaMemsetAsync(rowcnt, 0, 4 * (R + 1), st));
     if (J > 0) {
         k_pattern<false><<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, urow, nullptr,
-                                                                nullptr, rowcnt, nullptr, nullptr, nullptr, nullptr);
+                                                                nullptr, rowcnt, nullptr, nullptr, nullptr, nullptr, 0);
+        CNT_LAUNCHED();
+    }
+    if (NV > 0) {     // virtual junctions of the series elimination: a second junction table
+        CNT_CHECK_ARG(voff && va && vc);
+        k_pattern<false><<<cnt::grid_for(NV, 256), 256, 0, st>>>(B, soff, voff, NV, va, vc, urow, nullptr, nullptr,
+                                                                 rowcnt, nullptr, nullptr, nullptr, nullptr, 0);
         CNT_LAUNCHED();
     }
     return CNT_OK;
@@ -242,7 +274,8 @@ extern "C" int cnt_assemble_pattern_count(int B, const int32_t *soff, const int3
 extern "C" int cnt_assemble_pattern_fill(int B, const int32_t *soff, const int32_t *joff, int64_t J,
                                          const int32_t *stick1, const int32_t *stick2, const int32_t *urow,
                                          const int32_t *roff, int64_t R, const int32_t *rowptr, int32_t *col,
-                                         int32_t *nz_eid, int32_t *src_eid, int32_t *drn_eid, void *ws,
+                                         int32_t *nz_eid, int32_t *src_eid, int32_t *drn_eid, int64_t NV,
+                                         const int32_t *voff, const int32_t *va, const int32_t *vc, void *ws,
                                          int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && soff && joff && urow && roff && rowptr && R >= 0 && J >= 0 && ws);
@@ -257,9 +290,17 @@ extern "C" int cnt_assemble_pattern_fill(int B, const int32_t *soff, const int32
     CNT_CUDA(cudaMemsetAsync(cursor, 0, 4 * R, st));
     CNT_CUDA(cudaMemsetAsync(src_eid, 0xFF, 4 * R, st));
     CNT_CUDA(cudaMemsetAsync(drn_eid, 0xFF, 4 * R, st));
-    k_pattern<true><<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, urow, roff, rowptr, cursor,
-                                                           col, nz_eid, src_eid, drn_eid);
-    CNT_LAUNCHED();
+    if (J > 0) {
+        k_pattern<true><<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, urow, roff, rowptr,
+                                                               cursor, col, nz_eid, src_eid, drn_eid, 0);
+        CNT_LAUNCHED();
+    }
+    if (NV > 0) {     // entries of the virtual junctions carry the ids J, J+1, ...
+        CNT_CHECK_ARG(voff && va && vc);
+        k_pattern<true><<<cnt::grid_for(NV, 256), 256, 0, st>>>(B, soff, voff, NV, va, vc, urow, roff, rowptr, cursor, col,
+                                                                nz_eid, src_eid, drn_eid, (int)J);
+        CNT_LAUNCHED();
+    }
     k_sort_rows<<<cnt::grid_for(R, 128), 128, 0, st>>>(R, rowptr, col, nz_eid);
     CNT_LAUNCHED();
     return CNT_OK;
@@ -294,7 +335,8 @@ extern "C" int cnt_gate_levels(int64_t J, const double *jx, const double *jy, ui
 extern "C" int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_t *level, const double *gtable,
                                    int nlevels, int64_t R, const int32_t *rowptr, const int32_t *nz_eid,
                                    const int32_t *src_eid, const int32_t *drn_eid, double *g, double *val,
-                                   double *diag, double *rhs, uint8_t *cls, void *stream) {
+                                   double *diag, double *rhs, uint8_t *cls, const int32_t *ve1, const int32_t *ve2,
+                                   void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(J >= 0 && R >= 0 && nlevels > 0);
     if (J > 0 && gtable) {
@@ -306,9 +348,10 @@ extern "C" int cnt_assemble_values(int64_t J, const uint8_t *kind2, const uint8_
     }
     if (R > 0) {
         CNT_CHECK_ARG(rowptr && nz_eid && src_eid && drn_eid && val && diag && rhs);
-        if (cls) CNT_CHECK_ARG(gtable && kind2 && level && 9 * nlevels <= 256);
+        const int nb = 9 * nlevels;
+        if (cls) CNT_CHECK_ARG(gtable && kind2 && level && (ve1 ? nb + nb * (nb + 1) / 2 : nb) <= 256);
         k_values<<<cnt::grid_for(R, 128), 128, 0, st>>>(R, rowptr, nz_eid, src_eid, drn_eid, g, val, diag, rhs, kind2,
-                                                        level, nlevels, cls);
+                                                        level, nlevels, cls, J, ve1, ve2);
         CNT_LAUNCHED();
     }
     return CNT_OK;

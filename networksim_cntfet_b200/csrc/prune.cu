@@ -81,7 +81,130 @@ __global__ void k_prune_attach(int64_t S, const uint8_t *__restrict__ alive, con
     while (!alive[p]) p = parent[p];
     attach[s] = p;
 }
+
+// ---------------------------------------------------------------------------------------
+// Series elimination (second exact reduction).  A stick of the 2-core with exactly two junctions,
+// both to ordinary sticks (not electrodes), is a series connection: eliminating it leaves one
+// junction between its neighbours a, c with conductance g1 g2 / (g1 + g2), and afterwards
+// V = (g1 V_a + g2 V_c) / (g1 + g2).  Only an independent set is eliminated (a candidate goes if
+// none of its neighbours is a candidate with a smaller index), so the two neighbours of an
+// eliminated stick always stay unknowns and no chains have to be walked: one virtual junction per
+// eliminated stick.  Topology only -- the same sticks go in every gate configuration; the
+// conductances are combined per configuration in cnt_assemble_values.
+// ---------------------------------------------------------------------------------------
+__global__ void k_series_adj(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff, int64_t J,
+                             const int32_t *__restrict__ stick1, const int32_t *__restrict__ stick2,
+                             const uint8_t *__restrict__ alive, int32_t *__restrict__ cnt, int32_t *__restrict__ nbr,
+                             int32_t *__restrict__ ned) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= J) return;
+    int b = cnt::find_segment(joff, B, (int)e);
+    int a = soff[b] + stick1[e], c = soff[b] + stick2[e];
+    if (!alive[a] || !alive[c]) return;
+    int sa = atomicAdd(cnt + a, 1), sc = atomicAdd(cnt + c, 1);
+    if (sa < 2) { nbr[2 * (int64_t)a + sa] = c; ned[2 * (int64_t)a + sa] = (int32_t)e; }
+    if (sc < 2) { nbr[2 * (int64_t)c + sc] = a; ned[2 * (int64_t)c + sc] = (int32_t)e; }
+}
+__device__ __forceinline__ bool series_candidate(int B, const int32_t *__restrict__ soff, const uint8_t *__restrict__ alive,
+                                                 const int32_t *__restrict__ cnt, const int32_t *__restrict__ nbr,
+                                                 int64_t s) {
+    if (!alive[s] || cnt[s] != 2) return false;
+    int b = cnt::find_segment(soff, B, (int)s);
+    int s0 = soff[b];
+    return (int)s - s0 >= 2 && nbr[2 * s] - s0 >= 2 && nbr[2 * s + 1] - s0 >= 2;     // no electrode involved
+}
+__global__ void k_series_cand(int B, const int32_t *__restrict__ soff, int64_t S, const uint8_t *__restrict__ alive,
+                              const int32_t *__restrict__ cnt, const int32_t *__restrict__ nbr,
+                              uint8_t *__restrict__ cand) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < S) cand[s] = series_candidate(B, soff, alive, cnt, nbr, s) ? 1 : 0;
+}
+__global__ void k_series_pick(int64_t S, const uint8_t *__restrict__ cand, const int32_t *__restrict__ nbr,
+                              int32_t *__restrict__ flag) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    int f = 0;
+    if (cand[s]) {
+        int n0 = nbr[2 * s], n1 = nbr[2 * s + 1];
+        f = !(cand[n0] && n0 < s) && !(cand[n1] && n1 < s);
+    }
+    flag[s] = f;
+}
+__global__ void k_series_emit(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ scan,
+                              const int32_t *__restrict__ nbr, const int32_t *__restrict__ ned,
+                              int32_t *__restrict__ elim_vid, int32_t *__restrict__ voff, int32_t *__restrict__ va,
+                              int32_t *__restrict__ vc, int32_t *__restrict__ ve1, int32_t *__restrict__ ve2) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s <= B) voff[s] = scan[soff[s]];
+    if (s >= S) return;
+    int v = scan[s];
+    if (scan[s + 1] == v) {
+        elim_vid[s] = -1;
+        return;
+    }
+    int s0 = soff[cnt::find_segment(soff, B, (int)s)];
+    int n0 = nbr[2 * s], n1 = nbr[2 * s + 1], e0 = ned[2 * s], e1 = ned[2 * s + 1];
+    if (n0 > n1) {     // the two slots were filled in atomic order: normalise
+        int t = n0; n0 = n1; n1 = t;
+        t = e0; e0 = e1; e1 = t;
+    }
+    elim_vid[s] = v;
+    va[v] = n0 - s0;
+    vc[v] = n1 - s0;
+    ve1[v] = e0;
+    ve2[v] = e1;
+}
 }  // namespace
+
+extern "C" int64_t cnt_series_workspace_bytes(int64_t S) {
+    return cnt::ws_bytes_for(S, 4) + 2 * cnt::ws_bytes_for(2 * S, 4) + cnt::ws_bytes_for(S, 1) +
+           2 * cnt::ws_bytes_for(S + 1, 4) + cnt_scan_workspace_bytes(S + 1);
+}
+
+// elim_vid[S]: index of the virtual junction that replaces an eliminated stick, -1 otherwise;
+// voff[B+1]: virtual junctions per network (offsets); va, vc [<= S]: the two neighbours (network-local
+// stick indices, va < vc); ve1, ve2: the eliminated stick's junctions to va / vc (rows of the junction
+// table).  *h_nv: number of virtual junctions.  Synchronises the stream (one 4-byte read).
+extern "C" int cnt_series_select(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
+                                 const int32_t *stick1, const int32_t *stick2, const uint8_t *alive,
+                                 int32_t *elim_vid, int32_t *voff, int32_t *va, int32_t *vc, int32_t *ve1,
+                                 int32_t *ve2, int64_t *h_nv, void *ws, int64_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && soff && joff && alive && elim_vid && voff && va && vc && ve1 && ve2 && h_nv && ws && S >= B &&
+                  J >= 0);
+    *h_nv = 0;
+    cnt::Workspace w(ws, ws_bytes);
+    int32_t *cnt_ = w.take<int32_t>(S);
+    int32_t *nbr = w.take<int32_t>(2 * S), *ned = w.take<int32_t>(2 * S);
+    uint8_t *cand = w.take<uint8_t>(S);
+    int32_t *flag = w.take<int32_t>(S + 1), *scan = w.take<int32_t>(S + 1);
+    int64_t sb = cnt_scan_workspace_bytes(S + 1);
+    void *sws = w.take<char>(sb);
+    if (!sws) {
+        cnt::set_error("series workspace too small");
+        return CNT_ECAPACITY;
+    }
+    CNT_CUDA(cudaMemsetAsync(cnt_, 0, 4 * S, st));
+    CNT_CUDA(cudaMemsetAsync(nbr, 0, 8 * S, st));
+    if (J > 0) {
+        k_series_adj<<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, alive, cnt_, nbr, ned);
+        CNT_LAUNCHED();
+    }
+    const unsigned gs = cnt::grid_for(S + 1, 256);
+    k_series_cand<<<gs, 256, 0, st>>>(B, soff, S, alive, cnt_, nbr, cand);
+    CNT_LAUNCHED();
+    k_series_pick<<<gs, 256, 0, st>>>(S, cand, nbr, flag);
+    CNT_LAUNCHED();
+    int rc = cnt_exclusive_scan_i32(flag, scan, S, 1, sws, sb, stream);
+    if (rc) return rc;
+    k_series_emit<<<gs, 256, 0, st>>>(B, soff, S, scan, nbr, ned, elim_vid, voff, va, vc, ve1, ve2);
+    CNT_LAUNCHED();
+    int32_t h = 0;
+    CNT_CUDA(cudaMemcpyAsync(&h, scan + S, 4, cudaMemcpyDeviceToHost, st));
+    CNT_CUDA(cudaStreamSynchronize(st));
+    *h_nv = h;
+    return CNT_OK;
+}
 
 extern "C" int64_t cnt_prune_workspace_bytes(int64_t S) { return 2 * cnt::ws_bytes_for(S, 4) + cnt::ws_bytes_for(1, 4); }
 

@@ -129,6 +129,8 @@ class Engine(object):
         self.last_solver = None
         self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
         self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
+        self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
+                                       # needs prune)
 
     def twin(self):
         """A second Engine on the same GPU (own stream and events, same settings).  Two engines
@@ -136,7 +138,7 @@ class Engine(object):
         batch holds 112 SMs, the generation / junction / assembly kernels of the next batch run on
         the SMs it leaves free and the host work of both overlaps (run_pipelined)."""
         other = Engine(self.device, profile=self.profile)
-        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune"):
+        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series"):
             setattr(other, k, getattr(self, k))
         return other
 
@@ -334,9 +336,22 @@ class Engine(object):
                                            _p(b.label), _p(b.stats), _p(b.alive), _p(b.attach), C.byref(rounds),
                                            _p(pws), pws.numel(), self.stream_ptr))
                 b.prune_rounds = rounds.value
+            b.elim_vid = b.voff = b.va = b.vc = b.ve1 = b.ve2 = None
+            b.NV = 0
+            if self.series and b.alive is not None and b.J > 0:
+                sws_ = self._ws(lib.cnt_series_workspace_bytes(b.S))
+                i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
+                b.elim_vid, b.voff, b.va, b.vc, b.ve1, b.ve2 = i32(b.S), i32(b.B + 1), i32(b.S), i32(b.S), i32(b.S), i32(b.S)
+                nv = C.c_int64(0)
+                check(lib.cnt_series_select(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2),
+                                            _p(b.alive), _p(b.elim_vid), _p(b.voff), _p(b.va), _p(b.vc), _p(b.ve1),
+                                            _p(b.ve2), C.byref(nv), _p(sws_), sws_.numel(), self.stream_ptr))
+                b.NV = int(nv.value)
+                if b.NV == 0:
+                    b.elim_vid = b.voff = b.va = b.vc = b.ve1 = b.ve2 = None
             ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
-            check(lib.cnt_assemble_rows(b.B, _p(b.soff), b.S, _p(b.label), _p(b.stats), _p(b.alive), _p(b.urow),
-                                        _p(b.roff), _p(ws), ws.numel(), self.stream_ptr))
+            check(lib.cnt_assemble_rows(b.B, _p(b.soff), b.S, _p(b.label), _p(b.stats), _p(b.alive), _p(b.elim_vid),
+                                        _p(b.urow), _p(b.roff), _p(ws), ws.numel(), self.stream_ptr))
             b.h_roff = [int(v) for v in b.roff.cpu().tolist()]          # D2H sync (B+1 ints)
             b.c_roff = _lib.i32_array(b.h_roff)
             b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()
@@ -348,7 +363,8 @@ class Engine(object):
                                                rws.numel(), self.stream_ptr))
             rowcnt = torch.empty(R + 1, dtype=torch.int32, device=self.device)
             check(lib.cnt_assemble_pattern_count(b.B, _p(b.soff), _p(b.joff), b.J, _p(b.stick1), _p(b.stick2),
-                                                 _p(b.urow), R, _p(rowcnt), self.stream_ptr))
+                                                 _p(b.urow), R, _p(rowcnt), b.NV, _p(b.voff), _p(b.va), _p(b.vc),
+                                                 self.stream_ptr))
             sws = self._ws(lib.cnt_scan_workspace_bytes(R + 1))
             b.rowptr = torch.empty(R + 1, dtype=torch.int32, device=self.device)
             check(lib.cnt_exclusive_scan_i32(_p(rowcnt), _p(b.rowptr), R, 1, _p(sws), sws.numel(), self.stream_ptr))
@@ -364,7 +380,8 @@ class Engine(object):
             b.row_stick = torch.empty(max(R, 1), dtype=torch.int32, device=self.device)
             check(lib.cnt_assemble_pattern_fill(b.B, _p(b.soff), _p(b.joff), b.J, _p(b.stick1), _p(b.stick2),
                                                 _p(b.urow), _p(b.roff), R, _p(b.rowptr), _p(b.col), _p(b.nz_eid),
-                                                _p(b.src_eid), _p(b.drn_eid), _p(ws), ws.numel(), self.stream_ptr))
+                                                _p(b.src_eid), _p(b.drn_eid), b.NV, _p(b.voff), _p(b.va), _p(b.vc),
+                                                _p(ws), ws.numel(), self.stream_ptr))
             check(lib.cnt_assemble_row_stick(b.B, _p(b.soff), b.S, _p(b.urow), _p(b.row_stick), self.stream_ptr))
         return b
 
@@ -390,7 +407,12 @@ class Engine(object):
             rhs = torch.empty((NS, max(R, 1)), dtype=torch.float64, device=self.device)
             # compressed values for the cluster kernel: one class byte per entry + a 256-entry
             # table of -g per configuration (possible while 9 * nlevels <= 256)
-            use_cls = all(9 * len(gs.levels) <= 256 for gs in gates)
+            nv = getattr(b, "NV", 0)
+
+            def nclasses(nl):       # base classes + (with virtual series junctions) their unordered pairs
+                nb = 9 * nl
+                return nb + nb * (nb + 1) // 2 if nv else nb
+            use_cls = all(nclasses(len(gs.levels)) <= 256 for gs in gates)
             cls = torch.empty((NS, max(NNZ, 1)), dtype=torch.uint8, device=self.device) if use_cls else None
             gneg = np.zeros((NS, 256), dtype=np.float64)
             for q, (gs, tab) in enumerate(zip(gates, gtables)):
@@ -398,10 +420,16 @@ class Engine(object):
                 assert tab.shape == (9, len(gs.levels))
                 dtab = self._dev(tab, torch.float64)
                 if use_cls:
-                    gneg[q, :tab.size] = -tab.ravel()
+                    flat = tab.ravel()
+                    gneg[q, :flat.size] = -flat
+                    if nv:          # pair classes in the order k_values numbers them: (c1, c2), c1 <= c2, row-major
+                        i1, i2 = np.triu_indices(flat.size)
+                        with np.errstate(invalid="ignore", divide="ignore"):
+                            gneg[q, flat.size:flat.size + len(i1)] = -((flat[i1] * flat[i2]) / (flat[i1] + flat[i2]))
                 check(lib.cnt_assemble_values(J, _p(b.kind2), _p(gs.level), _p(dtab), tab.shape[1], R, _p(b.rowptr),
                                               _p(b.nz_eid), _p(b.src_eid), _p(b.drn_eid), _p(g[q]), _p(val[q]),
                                               _p(diag[q]), _p(rhs[q]), _p(cls[q]) if use_cls else None,
+                                              _p(getattr(b, "ve1", None)), _p(getattr(b, "ve2", None)),
                                               self.stream_ptr))
             out = dict(g=g, val=val, diag=diag, rhs=rhs)
             if use_cls:
@@ -553,8 +581,10 @@ class Engine(object):
             I = torch.empty(max(b.J, 1), dtype=torch.float64, device=self.device)
             isrc = torch.zeros((b.B, 3), dtype=torch.float64, device=self.device)
             check(lib.cnt_currents(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2), _p(b.label),
-                                   _p(b.stats), _p(b.urow), _p(getattr(b, "attach", None)), _p(g), _p(x), _p(V), _p(I),
-                                   _p(isrc), self.stream_ptr))
+                                   _p(b.stats), _p(b.urow), _p(getattr(b, "attach", None)),
+                                   _p(getattr(b, "elim_vid", None)), _p(getattr(b, "va", None)),
+                                   _p(getattr(b, "vc", None)), _p(getattr(b, "ve1", None)), _p(getattr(b, "ve2", None)),
+                                   _p(g), _p(x), _p(V), _p(I), _p(isrc), self.stream_ptr))
         return V, I, isrc
 
     # ------------------------------------------------------------------ measure_fullnet, batched
@@ -703,7 +733,7 @@ class Engine(object):
             rhs = torch.empty((1, max(R, 1)), dtype=torch.float64, device=self.device)
             check(lib.cnt_assemble_values(J, None, None, None, 1, R, _p(b.rowptr), _p(b.nz_eid), _p(b.src_eid),
                                           _p(b.drn_eid), _p(g[0]), _p(val[0]), _p(diag[0]), _p(rhs[0]), None,
-                                          self.stream_ptr))
+                                          _p(getattr(b, "ve1", None)), _p(getattr(b, "ve2", None)), self.stream_ptr))
         sysm = dict(g=g, val=val, diag=diag, rhs=rhs)
         sol = self.solve(b, sysm, rtol=rtol, maxit=maxit, check_every=check_every)
         V, I, cur = self.currents(b, g[0], sol["x"][0])

@@ -106,11 +106,11 @@ def test_assembly_matches_oracle(engine, name):
     from networksim_cntfet_b200.engine import GateState
     from networksim_cntfet_b200.elements import conductance_table
     g = load_golden(name)
-    engine.prune = False           # the reference's matrix: every stick of the component is a node
+    engine.prune = engine.series = False           # the reference's matrix: every stick of the component is a node
     try:
         b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
     finally:
-        engine.prune = True
+        engine.prune = engine.series = True
     gs = GateState(engine, b).set_global(10)
     tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
     sysm = engine.assemble_values(b, [gs], [tab])
@@ -182,7 +182,11 @@ def test_pruned_assembly(engine, name):
     from networksim_cntfet_b200.elements import conductance_table
     g = load_golden(name)
     assert engine.prune
-    b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    engine.series = False
+    try:
+        b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    finally:
+        engine.series = True
     gs = GateState(engine, b).set_global(10)
     tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
     sysm = engine.assemble_values(b, [gs], [tab])
@@ -218,6 +222,90 @@ def test_pruned_assembly(engine, name):
     diag = sysm["diag"][0].cpu().numpy()[:R]
     assert np.all(np.abs(diag - want) <= 4e-16 * np.abs(A.diagonal()).max())
     assert np.array_equal(sysm["rhs"][0].cpu().numpy()[:R], r["rhs"][keep][perm])
+
+
+def _series_set(n, s1, s2, alive):
+    """numpy restatement of cnt_series_select: candidates are the non-electrode sticks of the
+    2-core with exactly two junctions inside it, both to non-electrode sticks; a candidate is
+    eliminated unless one of its two neighbours is a candidate with a smaller index."""
+    m = alive[s1] & alive[s2]
+    a, c, e = s1[m], s2[m], np.nonzero(m)[0]
+    deg = np.bincount(np.r_[a, c], minlength=n)
+    nb = [[] for _ in range(n)]
+    for x, y, k in zip(np.r_[a, c].tolist(), np.r_[c, a].tolist(), np.r_[e, e].tolist()):
+        if deg[x] == 2:
+            nb[x].append((y, k))
+    cand = np.zeros(n, bool)
+    for s in range(2, n):
+        if alive[s] and deg[s] == 2 and nb[s][0][0] >= 2 and nb[s][1][0] >= 2:
+            cand[s] = True
+    out = {}
+    for s in np.nonzero(cand)[0].tolist():
+        (n0, e0), (n1, e1) = sorted(nb[s])
+        if not (cand[n0] and n0 < s) and not (cand[n1] and n1 < s):
+            out[s] = (n0, n1, e0, e1)
+    return out
+
+
+@pytest.mark.parametrize("name", PERC)
+def test_series_assembly(engine, name):
+    """cnt_series_select: an independent set of degree-2 sticks of the 2-core leaves the system; the
+    matrix is the Schur complement of the pruned matrix over them (one virtual junction of
+    conductance g1 g2 / (g1 + g2) per eliminated stick)."""
+    import scipy.sparse as sp
+    from networksim_cntfet_b200.engine import GateState
+    from networksim_cntfet_b200.elements import conductance_table
+    g = load_golden(name)
+    assert engine.prune and engine.series
+    b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    gs = GateState(engine, b).set_global(10)
+    tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
+    sysm = engine.assemble_values(b, [gs], [tab])
+    engine.sync()
+    cond, r = _oracle_fields(g, "_back", "back", 10.0, refine=0)
+    n = len(g["xc"])
+    s1, s2 = g["stick1"].astype(np.int64), g["stick2"].astype(np.int64)
+    alive, _ = _two_core(n, s1, s2, g["label"] == 0)
+    want = _series_set(n, s1, s2, alive)
+    assert b.NV == len(want)
+    if b.NV == 0:
+        assert b.elim_vid is None
+        return
+    vid = b.elim_vid.cpu().numpy()[:n]
+    assert np.array_equal(np.nonzero(vid >= 0)[0], np.array(sorted(want)))
+    assert np.array_equal(vid[vid >= 0], np.arange(b.NV))                # numbered in stick order
+    va, vc, ve1, ve2 = (t.cpu().numpy()[:b.NV] for t in (b.va, b.vc, b.ve1, b.ve2))
+    for s, (n0, n1, e0, e1) in want.items():
+        assert (va[vid[s]], vc[vid[s]], ve1[vid[s]], ve2[vid[s]]) == (n0, n1, e0, e1)
+    assert b.voff.cpu().numpy().tolist() == [0, b.NV]
+    elim = vid >= 0
+    keep_a = alive[r["nodes_u"]]
+    A = r["A"].tocsr()[keep_a][:, keep_a].tocsr()                            # pruned matrix, ascending sticks
+    nodes = r["nodes_u"][keep_a]
+    dang = (g["label"] == 0)[s1] & (g["label"] == 0)[s2] & (alive[s1] != alive[s2])
+    off = np.zeros(n)
+    np.add.at(off, np.where(alive[s1[dang]], s1[dang], s2[dang]), cond[dang])
+    A = (A - sp.diags(off[nodes])).tocsr()
+    ke, kk = elim[nodes], ~elim[nodes]
+    Aee = A[ke][:, ke]
+    assert (Aee - sp.diags(Aee.diagonal())).nnz == 0 or np.all((Aee - sp.diags(Aee.diagonal())).data == 0)   # independent
+    S = (A[kk][:, kk] - A[kk][:, ke] @ sp.diags(1.0 / Aee.diagonal()) @ A[ke][:, kk]).tocsr()
+    R = int(kk.sum())
+    assert b.R == R
+    row_stick = b.row_stick.cpu().numpy()[:R]
+    assert np.array_equal(np.sort(row_stick), nodes[kk])
+    perm = np.searchsorted(nodes[kk], row_stick)
+    S = S[perm][:, perm].tocsr()
+    M = sp.csr_matrix((sysm["val"][0].cpu().numpy()[:b.NNZ], b.col.cpu().numpy()[:b.NNZ], b.rowptr.cpu().numpy()),
+                      shape=(R, R)) + sp.diags(sysm["diag"][0].cpu().numpy()[:R])
+    D = (M - S).tocoo()
+    assert np.all(np.abs(D.data) <= 4e-16 * np.abs(A.diagonal()).max())
+    assert np.array_equal(sysm["rhs"][0].cpu().numpy()[:R], r["rhs"][keep_a][kk][perm])
+    # class-compressed values of the cluster kernel reproduce val exactly
+    if "cls" in sysm:
+        cls = sysm["cls"][0].cpu().numpy()[:b.NNZ]
+        gneg = sysm["gneg"][0].cpu().numpy() if hasattr(sysm["gneg"], "cpu") else np.asarray(sysm["gneg"])[0]
+        assert np.array_equal(gneg[cls], sysm["val"][0].cpu().numpy()[:b.NNZ])
 
 
 @pytest.mark.parametrize("name", PERC)
