@@ -305,6 +305,69 @@ int cnt_pcg_cluster_solve(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, 
                           void *ws, int64_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (5b) ONE very large network sharded over several GPUs (BASELINE config 5; no counterpart in the
+ *      reference -- extends solve_mna, cnet.py:147-149).  Every rank owns a contiguous range of
+ *      the Z-ordered unknown rows (a compact spatial patch) of the same system, keeps its slice of
+ *      the matrix with LOCAL column indices (own rows 0..n_own-1, then the n_halo remote rows it
+ *      references) and advances the NS gate configurations together.  The library provides the
+ *      per-rank phases; the caller performs the exchange named after each phase between them
+ *      (networksim_cntfet_b200/slab.py does it with torch.distributed over NCCL):
+ *        cnt_slab_init                    -> all-reduce(red2)   -> cnt_slab_direction(first=1) -> all-gather(sendbuf -> recvbuf)
+ *        per iteration: cnt_slab_spmv     -> all-reduce(red_pq) -> cnt_slab_update             -> all-reduce(red2)
+ *                       -> cnt_slab_direction(first=0)          -> all-gather(sendbuf -> recvbuf)
+ *      Nothing synchronises the stream.  Aggregates (two-level preconditioner, cnt_pcg_aggregates on
+ *      the replicated system) are renumbered per rank: local aggregate = one with members among the
+ *      own rows; shared = one with members on more than one rank (same numbering on all ranks).
+ *      All [NS, ...] arrays are dense with the stated row length.
+ * ------------------------------------------------------------------------------------- */
+enum { CNT_SLAB_RZ = 0, CNT_SLAB_BB = 1, CNT_SLAB_RR = 2, CNT_SLAB_BETA = 3, CNT_SLAB_ITERS = 4,
+       CNT_SLAB_STATUS = 5, CNT_SLAB_NSCAL = 8 };
+#define CNT_SLAB_BIGAGG 256     /* local aggregates with more members are summed by one block each */
+typedef struct cnt_slab_ctx {
+    int32_t NS, nblk;                 /* gate configurations; ceil(max(n_own,1) / cnt_slab_block_rows()) */
+    int64_t n_own, n_halo;
+    int64_t val_stride;               /* elements between the value arrays of two configurations */
+    const int32_t *rowptr;            /* [n_own+1] local */
+    const int32_t *col;               /* local column: < n_own own row, else n_own + halo index */
+    const double *val;                /* configuration q at val + q*val_stride */
+    const double *diag, *rhs;         /* [NS, n_own] */
+    double *x, *r, *q, *dinv;         /* [NS, n_own] */
+    double *p;                        /* [NS, n_own + n_halo] */
+    /* aggregates of the own rows */
+    int64_t maxL, maxSh, maxBig;      /* row lengths (>= 1) of the aggregate tables below */
+    const int32_t *nloc, *nsh, *nbig; /* [NS] local / shared / big local aggregates of configuration q */
+    int32_t max_nbig, pad0;           /* max over q of nbig[q] (host copy) */
+    const int32_t *aggptr;            /* [NS, maxL+1] members of local aggregate a: aggmem[aggptr[a] .. aggptr[a+1]) */
+    const int32_t *aggmem;            /* [NS, n_own] own rows sorted by local aggregate */
+    const int32_t *row_agg;           /* [NS, n_own] local aggregate of the row, -1 = none */
+    const int32_t *agg_shared;        /* [NS, maxL] shared slot of the local aggregate, -1 = lives on this rank only */
+    const double *einv;               /* [NS, maxL] 1 / (Z^T A Z)_aa */
+    const int32_t *shared_local;      /* [NS, maxSh] local aggregate of shared slot s, -1 = no member here */
+    const double *einv_sh;            /* [NS, maxSh] */
+    const int32_t *bigagg;            /* [NS, maxBig] local aggregates with > CNT_SLAB_BIGAGG members */
+    double *S;                        /* [NS, maxL] sums of r over the aggregates */
+    /* reductions */
+    double *part;                     /* [NS, 3, nblk] block partials */
+    double *red_pq;                   /* [NS]              all-reduce (sum) after cnt_slab_spmv */
+    double *red2;                     /* [NS, 2 + maxSh]   all-reduce (sum) after cnt_slab_init / cnt_slab_update */
+    double *scal;                     /* [NS, CNT_SLAB_NSCAL] */
+    int32_t *done;                    /* [NS] */
+    /* halo exchange of p */
+    int64_t n_exp, emax;              /* exported own rows; row length of the send buffer (max n_exp over ranks, >= 1) */
+    const int32_t *exp_rows;          /* [n_exp] own rows other ranks reference */
+    double *sendbuf;                  /* [NS, emax]        all-gather after cnt_slab_direction */
+    const double *recvbuf;            /* [world, NS, emax] */
+    const int64_t *halo_src;          /* [n_halo] index into recvbuf of halo row h for configuration 0 */
+    double rtol;
+    int32_t maxit, pad1;
+} cnt_slab_ctx;
+int cnt_slab_block_rows(void);
+int cnt_slab_init(const cnt_slab_ctx *c, void *stream);
+int cnt_slab_direction(const cnt_slab_ctx *c, int first, void *stream);
+int cnt_slab_spmv(const cnt_slab_ctx *c, void *stream);
+int cnt_slab_update(const cnt_slab_ctx *c, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * (6) write-back -- replaces update_voltages / update_currents (cnet.py:132-146).
  * V[S]: stick voltage (0.1 source, 0 drain, NaN outside the percolating component);
  * I[J]: |g (V1 - V2)| per junction (NaN outside the component);

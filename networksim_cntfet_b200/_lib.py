@@ -12,6 +12,12 @@ LIB_PATH = os.path.join(HERE, "libcntnet_b200.so")
 CNT_NSTAT = 8
 STAT_PERCOLATING, STAT_NCLUST_TRUE, STAT_MAXCLUST_TRUE, STAT_NCLUST_REF, STAT_MAXCLUST_REF, STAT_NCOMP, STAT_ECOMP = range(7)
 
+# cnt_slab_ctx (sharded solve of one large network): scalar slots and the size above which a local
+# aggregate is summed by a whole block
+CNT_SLAB_RZ, CNT_SLAB_BB, CNT_SLAB_RR, CNT_SLAB_BETA, CNT_SLAB_ITERS, CNT_SLAB_STATUS = range(6)
+CNT_SLAB_NSCAL = 8
+CNT_SLAB_BIGAGG = 256
+
 vp, i32, i64, u64, f64, u8 = C.c_void_p, C.c_int, C.c_int64, C.c_uint64, C.c_double, C.c_uint8
 I32P = C.POINTER(C.c_int32)
 
@@ -55,6 +61,11 @@ PROTOTYPES = {
     "cnt_pcg_cluster_size": (i32, [i64, i64]),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i32, vp, i64, vp]),
+    "cnt_slab_block_rows": (i32, []),
+    "cnt_slab_init": (i32, [vp, vp]),
+    "cnt_slab_direction": (i32, [vp, i32, vp]),
+    "cnt_slab_spmv": (i32, [vp, vp]),
+    "cnt_slab_update": (i32, [vp, vp]),
     "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
 }
 # entry points that may be absent from an older build of the library (checked by tests

@@ -546,6 +546,46 @@ class Engine(object):
                 status[idx_q, idx_n] = stt
         return dict(x=x, iters=iters, relres=relres, status=status)
 
+    def solve_sharded(self, b, sysm, comm, rtol=1e-15, maxit=2000000, check_every=50):
+        """Two-level PCG of ONE network (b.B == 1) whose unknown rows are sharded over the ranks of
+        `comm` (slab.DistComm: one rank per process / GPU over NCCL; slab.LocalComm(W): W ranks inside
+        this process).  Every rank holds the same prepared batch and the same assembled values; it
+        keeps its row range of them, and p's boundary values plus three small sums are exchanged
+        per iteration (networksim_cntfet_b200/slab.py, csrc/pcg_slab.cu).  Same outputs as solve()."""
+        from . import slab
+        assert b.B == 1, "solve_sharded takes one network"
+        NS = sysm["val"].shape[0]
+        R, NNZ = b.R, b.NNZ
+        with self._work("pcg"):
+            iters = torch.zeros((NS, 1), dtype=torch.int32, device=self.device)
+            relres = torch.zeros((NS, 1), dtype=torch.float64, device=self.device)
+            status = torch.zeros((NS, 1), dtype=torch.int32, device=self.device)
+            if R == 0:
+                return dict(x=torch.zeros((NS, 1), dtype=torch.float64, device=self.device), iters=iters,
+                            relres=relres, status=status)
+            agg_of_row = agg_einv = keep = None
+            if self.precond == "twolevel":
+                with self._work("pcg_aggregates"):
+                    _, keep = self._aggregates(b, sysm, [0] * NS, list(range(NS)), 0)
+                    agg_of_row = keep["agg_of_row"][:NS * R]
+                    agg_einv = keep["agg_einv"][:max(int(self.last_aggregates[0]), 1)]
+            ph = slab.CudaPhases(self.stream_ptr)
+            with self._work("slab_plan"):
+                states = slab.build_states(b.rowptr[:R + 1], b.col[:max(NNZ, 1)], sysm["val"][:, :NNZ],
+                                           sysm["diag"][:, :R], sysm["rhs"][:, :R], agg_of_row, agg_einv, comm,
+                                           ph.block_rows(), rtol, maxit)
+            with self._work("slab_pcg"):
+                slab.run_pcg(states, comm, ph, check_every)
+                x = slab.gather_solution(states, comm, R)
+            sc = states[0].scal
+            iters[:, 0] = sc[:, _lib.CNT_SLAB_ITERS].to(torch.int32)
+            status[:, 0] = sc[:, _lib.CNT_SLAB_STATUS].to(torch.int32)
+            bb = sc[:, _lib.CNT_SLAB_BB]
+            relres[:, 0] = torch.where(bb > 0, (sc[:, _lib.CNT_SLAB_RR] / bb.clamp(min=1e-300)).sqrt(), torch.zeros_like(bb))
+            self.last_solver = "slab x%d" % comm.world
+            self.last_slab_states = states
+        return dict(x=x, iters=iters, relres=relres, status=status)
+
     def _cluster_fallback(self, b, sysm, x, sys_net, sys_slab, it, rr, stt, rtol, maxit, check_every):
         """systems the cluster kernel reported as not fitting on chip (status 3) are re-solved by
         the multi-launch kernels; costs one small D2H of the status vector"""
@@ -614,7 +654,8 @@ class Engine(object):
             v = (0.1 * (0.99 - b.xc[stick]) / 0.98).clamp_(0.0, 0.1)
             return v.unsqueeze(0).repeat(NS, 1).contiguous()
 
-    def solve_gates(self, b, gates, onoffmap, element, rtol=1e-15, maxit=2000000, check_every=250, want_fields=False):
+    def solve_gates(self, b, gates, onoffmap, element, rtol=1e-15, maxit=2000000, check_every=250, want_fields=False,
+                    row_shard=None):
         """Assemble + solve + write back a list of GateStates.  Returns dict with isrc[NS,B,3],
         iters/relres/status[NS,B] (+ V[NS,S], I[NS,J], g[NS,J], x when want_fields)."""
         from .elements import conductance_table
@@ -622,7 +663,10 @@ class Engine(object):
         sysm = self.assemble_values(b, gates, tabs)
         prio = [max(abs(v) for v in gs.levels) for gs in gates]   # higher |Vg| -> more iterations -> first
         x0 = self.linear_guess(b, len(gates)) if self.initial_guess == "linear" else None
-        sol = self.solve(b, sysm, x0=x0, rtol=rtol, maxit=maxit, check_every=check_every, slab_priority=prio)
+        if row_shard is not None:      # one network, rows sharded over the ranks of a communicator
+            sol = self.solve_sharded(b, sysm, row_shard, rtol=rtol, maxit=maxit, check_every=min(check_every, 50))
+        else:
+            sol = self.solve(b, sysm, x0=x0, rtol=rtol, maxit=maxit, check_every=check_every, slab_priority=prio)
         NS = len(gates)
         out = dict(iters=sol["iters"], relres=sol["relres"], status=sol["status"])
         isrc = []
@@ -640,12 +684,15 @@ class Engine(object):
         return out
 
     def measure_fullnet(self, b, onoffmap=1, element=None, rtol=1e-15, maxit=2000000, check_every=250,
-                        want_fields=False, slab_shard=None):
+                        want_fields=False, slab_shard=None, row_shard=None):
         """Batched body of measure_perc.measure_fullnet (measure_perc.py:140-203) for a prepared
         batch: returns a dict of host numpy arrays, one entry per network.
         slab_shard=(rank, world): solve only the gate configurations q with q % world == rank (the
         others are left zero) -- used to spread ONE large network over several GPUs: every rank
-        builds the same network from the same seed and the currents are summed afterwards."""
+        builds the same network from the same seed and the currents are summed afterwards.
+        row_shard=comm (slab.DistComm / slab.LocalComm): all configurations are solved together with
+        the unknown rows sharded over the communicator's ranks (solve_sharded); every rank returns
+        the full result."""
         from .elements import LinExpTransistor
         element = element or LinExpTransistor
         if b.R is None:
@@ -664,7 +711,7 @@ class Engine(object):
         res = None
         if mine:
             res = self.solve_gates(b, [gates[q][1] for q in mine], onoffmap, element, rtol, maxit, check_every,
-                                   want_fields)
+                                   want_fields, row_shard=row_shard)
             self.sync()
             isrc[mine] = res["isrc"].cpu().numpy()
             iters[mine] = res["iters"].cpu().numpy()

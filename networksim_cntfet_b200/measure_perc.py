@@ -222,17 +222,30 @@ def measure_fullnet(n, scaling, l='exp', save=False, seed=0, onoffmap=1, v=False
     return data
 
 
-def measure_fullnet_distributed(n, scaling, seed, onoffmap=1, element=LinExpTransistor, l='exp', engine=None):
+def measure_fullnet_distributed(n, scaling, seed, onoffmap=1, element=LinExpTransistor, l='exp', engine=None,
+                                mode="gates"):
     """ONE (large) network on all ranks of an initialised torch.distributed job: every rank
     regenerates the network from `seed` (counter-based RNG: identical sticks, junctions, labels and
-    CSR pattern everywhere, no exchange), solves the gate configurations q with q % world == rank,
-    and one small all-reduce sums the per-configuration currents.  Returns measure_fullnet's rows on
-    every rank.  (The reference has no way to spread one network over several workers.)"""
+    CSR pattern everywhere, no exchange).  mode="gates": rank r solves the gate configurations q with
+    q % world == r and one small all-reduce sums the per-configuration currents (at most 4 ranks do
+    useful work).  mode="rows": the unknown rows of the system -- Z-ordered, i.e. compact spatial
+    patches of the device -- are sharded over ALL ranks and the four configurations are solved
+    together with per-iteration halo exchange of the search direction and two small all-reduces over
+    NCCL (Engine.solve_sharded, slab.py).  Returns measure_fullnet's rows on every rank.  (The
+    reference has no way to spread one network over several workers.)"""
     import torch
     import torch.distributed as dist
     eng = engine or get_engine()
     rank, world = (dist.get_rank(), dist.get_world_size()) if dist.is_initialized() else (0, 1)
     b = eng.generate([int(n)], scaling, seeds=[int(seed)], l=l)
+    if mode == "rows":
+        from . import slab
+        comm = slab.DistComm() if dist.is_initialized() else slab.LocalComm(1)
+        res = eng.measure_fullnet(b, onoffmap=onoffmap, element=element, row_shard=comm)
+        df = _rows_from_ensemble(res, [int(n)], scaling, np.asarray([seed], dtype=np.uint64), onoffmap)
+        return df, res
+    if mode != "gates":
+        raise ValueError("mode must be 'gates' or 'rows'")
     res = eng.measure_fullnet(b, onoffmap=onoffmap, element=element, slab_shard=(rank, world))
     cur = torch.as_tensor(np.stack([res["ion"], res["ioff_back"], res["ioff_total"], res["ioff_partial"]]),
                           dtype=torch.float64, device=eng.device)

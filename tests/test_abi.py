@@ -83,3 +83,20 @@ def test_aggregates_struct_matches_header():
         if decl:
             names += [n.strip().lstrip("*").strip() for n in decl.split(" ", 1)[1].split(",")]
     assert names == [f[0] for f in _lib.Aggregates._fields_], (names, [f[0] for f in _lib.Aggregates._fields_])
+
+
+def test_slab_ctx_struct_matches_header():
+    """field names and order of slab.SlabCtx mirror struct cnt_slab_ctx"""
+    from networksim_cntfet_b200 import slab
+    txt = open(os.path.join(ROOT, "include", "cntnet_b200.h")).read()
+    body = re.search(r"typedef struct cnt_slab_ctx \{(.*?)\} cnt_slab_ctx;", txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip().replace("const ", "")
+        if decl:
+            names += [n.strip().lstrip("*").strip() for n in decl.split(" ", 1)[1].split(",")]
+    assert names == [f[0] for f in slab.SlabCtx._fields_], (names, [f[0] for f in slab.SlabCtx._fields_])
+    import ctypes
+    # 8-byte members only after the two leading int32 pairs: no hidden padding
+    assert ctypes.sizeof(slab.SlabCtx) == sum(ctypes.sizeof(f[1]) for f in slab.SlabCtx._fields_)
