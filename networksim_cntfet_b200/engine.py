@@ -10,6 +10,7 @@ stages inside `RandomConductingNetwork.__init__` (netsim.py:44-47) and
 `ConductionNetwork.update` (cnet.py:150-156), one network per process.
 """
 import contextlib
+import os
 import ctypes as C
 
 import numpy as np
@@ -129,6 +130,8 @@ class Engine(object):
         self.last_solver = None
         self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
         self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
+        self.slab_graph = os.environ.get("CNT_SLAB_GRAPH", "1") != "0"   # solve_sharded: replay blocks of iterations
+                                       # (kernels + collectives) as one CUDA graph
         self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
                                        # needs prune)
 
@@ -138,7 +141,7 @@ class Engine(object):
         batch holds 112 SMs, the generation / junction / assembly kernels of the next batch run on
         the SMs it leaves free and the host work of both overlaps (run_pipelined)."""
         other = Engine(self.device, profile=self.profile)
-        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series"):
+        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series", "slab_graph"):
             setattr(other, k, getattr(self, k))
         return other
 
@@ -575,7 +578,8 @@ class Engine(object):
                                            sysm["diag"][:, :R], sysm["rhs"][:, :R], agg_of_row, agg_einv, comm,
                                            ph.block_rows(), rtol, maxit)
             with self._work("slab_pcg"):
-                slab.run_pcg(states, comm, ph, check_every)
+                self.last_slab_info = {}
+                slab.run_pcg(states, comm, ph, check_every, graph=self.slab_graph, info=self.last_slab_info)
                 x = slab.gather_solution(states, comm, R)
             sc = states[0].scal
             iters[:, 0] = sc[:, _lib.CNT_SLAB_ITERS].to(torch.int32)

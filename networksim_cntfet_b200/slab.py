@@ -301,9 +301,24 @@ class CudaPhases(object):
 
 
 # --------------------------------------------------------------------------- schedule
-def run_pcg(states, comm, phases, check_every=50):
+def _iteration(states, comm, phases):
+    for st in states:
+        phases.spmv(st)
+    comm.all_reduce([st.red_pq for st in states])
+    for st in states:
+        phases.update(st)
+    comm.all_reduce([st.red2 for st in states])
+    for st in states:
+        phases.direction(st, 0)
+    comm.all_gather([st.recvbuf for st in states], [st.sendbuf for st in states])
+
+
+def run_pcg(states, comm, phases, check_every=50, graph=False, info=None):
     """Advance all local ranks in lock step until every configuration has stopped.  Returns the
-    number of iterations issued."""
+    number of iterations issued.  graph=True (CUDA): the first block of `check_every` iterations
+    runs eagerly (it also warms up the communicator), then one block -- kernels of all phases and
+    the collectives between them -- is captured into a CUDA graph on the current stream and
+    replayed; the host only polls the done flags between replays."""
     for st in states:
         phases.init(st)
     comm.all_reduce([st.red2 for st in states])
@@ -312,20 +327,24 @@ def run_pcg(states, comm, phases, check_every=50):
     comm.all_gather([st.recvbuf for st in states], [st.sendbuf for st in states])
     issued = 0
     maxit = states[0].maxit
+    g = None
     while issued < maxit:
-        for _ in range(check_every):
-            for st in states:
-                phases.spmv(st)
-            comm.all_reduce([st.red_pq for st in states])
-            for st in states:
-                phases.update(st)
-            comm.all_reduce([st.red2 for st in states])
-            for st in states:
-                phases.direction(st, 0)
-            comm.all_gather([st.recvbuf for st in states], [st.sendbuf for st in states])
+        if g is not None:
+            g.replay()
+        else:
+            for _ in range(check_every):
+                _iteration(states, comm, phases)
         issued += check_every
         if bool(states[0].done.all()):        # D2H sync; the flags are identical on every rank
             break
+        if graph and g is None:
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=torch.cuda.current_stream(), capture_error_mode="thread_local"):
+                for _ in range(check_every):
+                    _iteration(states, comm, phases)
+    if info is not None:
+        info["graph"] = g is not None
+        info["issued"] = issued
     return issued
 
 

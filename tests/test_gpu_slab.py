@@ -119,6 +119,23 @@ def test_sharded_full_size_100um(engine):
         assert abs(res[key][0] - ref[key][0]) <= 1e-9 * ref[key][0], (key, res[key][0], ref[key][0])
 
 
+def test_graph_replay_equals_eager(engine):
+    """blocks of iterations replayed as a CUDA graph (kernels + the in-process collectives) give the
+    bits of the eager schedule"""
+    out = []
+    for graph in (False, True):
+        engine.slab_graph = graph
+        try:
+            res = engine.measure_fullnet(engine.generate([6400], 20.0, seed=5), onoffmap=1, want_fields=True,
+                                         row_shard=slab.LocalComm(3))
+        finally:
+            engine.slab_graph = True
+        assert engine.last_slab_info["graph"] == graph
+        out.append(res)
+    assert np.array_equal(out[0]["iters"], out[1]["iters"])
+    assert torch.equal(out[0]["fields"]["x"], out[1]["fields"]["x"])
+
+
 def test_non_percolating_network_sharded(engine):
     b = engine.generate([120], 5.0, seed=5)
     res = engine.measure_fullnet(b, onoffmap=1, row_shard=slab.LocalComm(3))
