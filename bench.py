@@ -281,7 +281,7 @@ def gpu_arm(args):
         # this very command (profiles/): the cluster kernel keeps vectors and matrix slices on chip
         traffic = traffic_note = None
         try:
-            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_pcg_cluster_bench_launch_ncu.json")))
+            cap = json.load(open(os.path.join(ROOT, "profiles", "r01_pcg_cluster_series_bench_launch_ncu.json")))
             if (eng.last_solver or "").startswith("cluster") and args.batch == 14 and world == 1:
                 traffic = cap["dram_bytes_total"]
                 traffic_note = "ncu dram__bytes_read+write of one launch (%s)" % cap["command"]

@@ -667,6 +667,12 @@ class Engine(object):
         sysm = self.assemble_values(b, gates, tabs)
         prio = [max(abs(v) for v in gs.levels) for gs in gates]   # higher |Vg| -> more iterations -> first
         x0 = self.linear_guess(b, len(gates)) if self.initial_guess == "linear" else None
+        if (row_shard is None and b.B == 1 and self.solver == "auto" and self.precond == "twolevel" and
+                b.R > self.lib.cnt_pcg_cluster_max_rows()):
+            # one network beyond the cluster kernel's on-chip capacity: the row-slab solver with a single
+            # rank advances all configurations together (measured 2x the multi-launch solver at 10M sticks)
+            from . import slab
+            row_shard = slab.LocalComm(1)
         if row_shard is not None:      # one network, rows sharded over the ranks of a communicator
             sol = self.solve_sharded(b, sysm, row_shard, rtol=rtol, maxit=maxit, check_every=min(check_every, 50))
         else:

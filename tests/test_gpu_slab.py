@@ -119,6 +119,19 @@ def test_sharded_full_size_100um(engine):
         assert abs(res[key][0] - ref[key][0]) <= 1e-9 * ref[key][0], (key, res[key][0], ref[key][0])
 
 
+def test_large_single_network_takes_slab_solver(engine):
+    """a single network beyond the cluster kernel's capacity (160x160 um, ~118k unknowns) is solved by
+    the row-slab solver with one rank; currents against the refined oracle"""
+    b = engine.generate([256000], 160.0, seed=3)
+    res = engine.measure_fullnet(b, onoffmap=1)
+    from networksim_cntfet_b200 import _lib
+    assert b.R > _lib.load().cnt_pcg_cluster_max_rows() and engine.last_solver == "slab x1"
+    assert np.all(res["status"] == 0)
+    m = O.measure_fullnet(engine.sticks_to_host(b)[0], onoffmap=1, refine=3)
+    for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert abs(res[key][0] - m[key]) <= 1e-9 * m[key], (key, res[key][0], m[key])
+
+
 def test_graph_replay_equals_eager(engine):
     """blocks of iterations replayed as a CUDA graph (kernels + the in-process collectives) give the
     bits of the eager schedule"""
