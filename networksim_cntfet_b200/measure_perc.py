@@ -26,8 +26,9 @@ FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'io
                    'onoffmap']
 PIPELINE = False              # True: the batches of a call alternate between two engines / host threads (measured
                               # gain at 100x100 um: 0.7-2 %, the step is one long kernel already; results identical)
-BATCH_STICKS = 1_450_000      # sticks per GPU batch of the ensemble path (14 networks at 100x100 um = 8 full rounds
-                              # of the 7 resident 16-CTA clusters)
+BATCH_STICKS = 5_800_000      # sticks per GPU batch of the ensemble path (56 networks at 100x100 um = 32 systems for
+                              # each of the 7 resident 16-CTA clusters; measured 53.6 / 55.7 / 57.1 networks/s at
+                              # 14 / 28 / 56 networks per batch: the tail of the work queue is amortised; ~2 GB)
 
 
 def checkdir(directoryname):
