@@ -142,8 +142,8 @@ def build_states(rowptr, col, val, diag, rhs, agg_of_row, agg_einv, comm, block_
         cl = torch.where(inside, cg - lo, n_own + torch.searchsorted(st.halo_rows, cg))
         st.col = cl.to(i32).contiguous()
         st.val = val[:, k0:k1].contiguous()
-        st.diag = diag[:, lo:hi].contiguous()
-        st.rhs = rhs[:, lo:hi].contiguous()
+        st.diag = diag[:, lo:hi].contiguous() if n_own else torch.ones((NS, 1), dtype=f64, device=dev)
+        st.rhs = rhs[:, lo:hi].contiguous() if n_own else torch.zeros((NS, 1), dtype=f64, device=dev)
         # the matrix is symmetric: the rows other ranks need from me are my rows with a remote column
         rowid = torch.repeat_interleave(torch.arange(n_own, device=dev, dtype=i64), st.rowptr.to(i64).diff())
         st.exp_rows = torch.unique(rowid[~inside]).to(i32).contiguous()

@@ -41,8 +41,8 @@ class TorchPhases(object):
         st.done.zero_()
         st.p.zero_()
         st.x.zero_()
-        st.dinv[:, :n] = 1.0 / st.diag
-        st.r[:, :n] = st.rhs
+        st.dinv[:, :n] = 1.0 / st.diag[:, :n]
+        st.r[:, :n] = st.rhs[:, :n]
         self._sums(st)
 
     def update(self, st):
@@ -103,7 +103,7 @@ class TorchPhases(object):
                 st.red_pq[q] = 0.0
                 continue
             rows = torch.repeat_interleave(torch.arange(n, device=st.p.device), st.rowptr.long().diff())
-            acc = st.diag[q] * st.p[q, :n]
+            acc = st.diag[q, :n] * st.p[q, :n]
             acc = acc.index_add(0, rows, st.val[q] * st.p[q, st.col.long()])
             st.q[q, :n] = acc
             st.red_pq[q] = (st.p[q, :n] * acc).sum()

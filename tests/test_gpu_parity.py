@@ -11,6 +11,7 @@ import pytest
 
 from conftest import FULLNET_GATES, golden_element, golden_names, golden_sticks, load_golden
 from oracle import cntnet_oracle as O
+from reductions_ref import two_core, series_set  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 NAMES = golden_names()
@@ -147,31 +148,6 @@ def test_assembly_matches_oracle(engine, name):
     assert np.array_equal(b.row_stick.cpu().numpy()[:R], r["nodes_u"])
 
 
-def _two_core(n, s1, s2, comp):
-    """numpy peeling: sticks of the component left after removing dangling sticks repeatedly
-    (electrodes 0 and 1 are never removed); returns (alive mask, attachment stick or -1)"""
-    alive = comp.copy()
-    attach = np.full(n, -1, np.int64)
-    parent = np.full(n, -1, np.int64)
-    while True:
-        m = alive[s1] & alive[s2]
-        deg = np.bincount(np.r_[s1[m], s2[m]], minlength=n)
-        leaf = alive & (deg == 1) & (np.arange(n) >= 2)
-        if not leaf.any():
-            break
-        for a, c in ((s1[m], s2[m]), (s2[m], s1[m])):
-            k = leaf[a]
-            parent[a[k]] = c[k]
-        # two leaves joined to each other cannot occur inside a percolating component
-        alive &= ~leaf
-    for s in np.nonzero(parent >= 0)[0]:
-        p = parent[s]
-        while not alive[p]:
-            p = parent[p]
-        attach[s] = p
-    return alive, attach
-
-
 @pytest.mark.parametrize("name", PERC)
 def test_pruned_assembly(engine, name):
     """cnt_prune_leaves: the unknowns are the 2-core of the percolating component, the matrix is
@@ -194,7 +170,7 @@ def test_pruned_assembly(engine, name):
     cond, r = _oracle_fields(g, "_back", "back", 10.0, refine=0)
     n = len(g["xc"])
     comp = g["label"] == 0
-    alive, attach = _two_core(n, g["stick1"].astype(np.int64), g["stick2"].astype(np.int64), comp)
+    alive, attach = two_core(n, g["stick1"].astype(np.int64), g["stick2"].astype(np.int64), comp)
     assert np.array_equal(b.alive.cpu().numpy().astype(bool), alive)
     assert np.array_equal(b.attach.cpu().numpy(), attach)
     keep = alive[r["nodes_u"]]
@@ -224,29 +200,6 @@ def test_pruned_assembly(engine, name):
     assert np.array_equal(sysm["rhs"][0].cpu().numpy()[:R], r["rhs"][keep][perm])
 
 
-def _series_set(n, s1, s2, alive):
-    """numpy restatement of cnt_series_select: candidates are the non-electrode sticks of the
-    2-core with exactly two junctions inside it, both to non-electrode sticks; a candidate is
-    eliminated unless one of its two neighbours is a candidate with a smaller index."""
-    m = alive[s1] & alive[s2]
-    a, c, e = s1[m], s2[m], np.nonzero(m)[0]
-    deg = np.bincount(np.r_[a, c], minlength=n)
-    nb = [[] for _ in range(n)]
-    for x, y, k in zip(np.r_[a, c].tolist(), np.r_[c, a].tolist(), np.r_[e, e].tolist()):
-        if deg[x] == 2:
-            nb[x].append((y, k))
-    cand = np.zeros(n, bool)
-    for s in range(2, n):
-        if alive[s] and deg[s] == 2 and nb[s][0][0] >= 2 and nb[s][1][0] >= 2:
-            cand[s] = True
-    out = {}
-    for s in np.nonzero(cand)[0].tolist():
-        (n0, e0), (n1, e1) = sorted(nb[s])
-        if not (cand[n0] and n0 < s) and not (cand[n1] and n1 < s):
-            out[s] = (n0, n1, e0, e1)
-    return out
-
-
 @pytest.mark.parametrize("name", PERC)
 def test_series_assembly(engine, name):
     """cnt_series_select: an independent set of degree-2 sticks of the 2-core leaves the system; the
@@ -265,8 +218,8 @@ def test_series_assembly(engine, name):
     cond, r = _oracle_fields(g, "_back", "back", 10.0, refine=0)
     n = len(g["xc"])
     s1, s2 = g["stick1"].astype(np.int64), g["stick2"].astype(np.int64)
-    alive, _ = _two_core(n, s1, s2, g["label"] == 0)
-    want = _series_set(n, s1, s2, alive)
+    alive, _ = two_core(n, s1, s2, g["label"] == 0)
+    want = series_set(n, s1, s2, alive)
     assert b.NV == len(want)
     if b.NV == 0:
         assert b.elim_vid is None

@@ -42,6 +42,20 @@ def test_cuda_phases_match_direct_solve(engine, world, precond):
         assert torch.equal(st.scal, states[0].scal)
 
 
+def test_more_ranks_than_rows(engine):
+    """ranks that own no row at all take part in the exchanges with empty slices"""
+    system = slab_ref.random_network_system(n=3, seed=1, nconf=2)          # 9 unknowns
+    comm = slab.LocalComm(12)
+    with engine._work():
+        ph = slab.CudaPhases(engine.stream_ptr)
+        states = slab_ref.to_states(system, comm, ph, device=engine.device)
+        slab.run_pcg(states, comm, ph, check_every=5)
+        x = slab.gather_solution(states, comm, 9)
+    engine.sync()
+    assert sum(st.n_own == 0 for st in states) >= 3
+    assert np.max(np.abs(x.cpu().numpy() - _direct(system))) <= 1e-10 * VDS
+
+
 def test_cuda_phases_step_by_step_against_torch(engine):
     """every phase leaves the same numbers in the shared state as the torch restatement"""
     system = slab_ref.random_network_system(n=32, seed=11, nconf=2)

@@ -41,6 +41,18 @@ def test_inprocess_ranks_match_direct_solve(world, precond):
         assert torch.equal(st.scal, states[0].scal)
 
 
+def test_more_ranks_than_rows():
+    """ranks that own no row at all take part in the exchanges with empty slices"""
+    system = slab_ref.random_network_system(n=3, seed=1, nconf=2)          # 9 unknowns
+    comm = slab.LocalComm(12)
+    ph = slab_ref.TorchPhases()
+    states = slab_ref.to_states(system, comm, ph)
+    assert sum(st.n_own == 0 for st in states) >= 3
+    slab.run_pcg(states, comm, ph, check_every=5)
+    x = slab.gather_solution(states, comm, 9).numpy()
+    assert np.max(np.abs(x - _solve_direct(system[5], system[4]))) <= 1e-10 * 0.1
+
+
 def test_rank_count_does_not_change_iteration_count_much():
     """the preconditioner is the same operator for any number of ranks (shared aggregates are
     reduced exactly), so the iteration counts agree up to rounding effects"""
