@@ -347,7 +347,7 @@ def main():
     ap.add_argument("--onoffmap", type=int, default=1)
     ap.add_argument("--rtol", type=float, default=1e-15)
     ap.add_argument("--check-every", type=int, default=250)
-    ap.add_argument("--solver", default="auto", choices=["auto", "cluster", "flat"])
+    ap.add_argument("--solver", default="auto", choices=["auto", "cluster", "flat", "direct"])
     ap.add_argument("--seed", type=int, default=2024)
     ap.add_argument("--guess", default="zero", choices=["linear", "zero"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="networks in the CPU sample (default: one per core)")

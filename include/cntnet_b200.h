@@ -368,6 +368,42 @@ int cnt_slab_spmv(const cnt_slab_ctx *c, void *stream);
 int cnt_slab_update(const cnt_slab_ctx *c, void *stream);
 
 /* ---------------------------------------------------------------------------------------
+ * (5c) direct solve by parallel star-mesh elimination -- replaces solve_mna (cnet.py:147-149) by
+ *      sparse Cholesky written on the conductances (every quantity a sum of positive terms).
+ *      The symbolic phase (networksim_cntfet_b200/starmesh.py; topology only, shared by all gate
+ *      configurations) eliminates an independent set of unknowns per round and describes a round by
+ *      the index lists below; the numeric phase is these entry points, for NS configurations at once.
+ *      Nothing synchronises the stream; the host struct arrays are read during the call only.
+ * ------------------------------------------------------------------------------------- */
+typedef struct cnt_sm_round {
+    int64_t nelim, nE_new, ntarget;   /* eliminated unknowns; edges after the round; updated neighbours */
+    int64_t ebase, gbase;             /* offsets of the round in the dinv / gE pools */
+    const int32_t *E;                 /* [nelim] eliminated rows */
+    const int32_t *nptr;              /* [nelim+1] their neighbour lists: nbr / eslot [nptr[m] .. nptr[m+1]) */
+    const int32_t *nbr;               /* neighbour rows */
+    const int32_t *eslot;             /* edge (slot in the round's edge array) to that neighbour */
+    const int32_t *copy_src;          /* [nE_new] old slot of a surviving edge, -1 = new edge */
+    const int32_t *cptr;              /* [nE_new+1] star-mesh contributions g[ca] g[cb] / d[cm] to the new edge */
+    const int32_t *cm, *ca, *cb;
+    const int32_t *tn;                /* [ntarget] rows whose c, b are updated */
+    const int32_t *tptr;              /* [ntarget+1] contributions g[tslot] c[E[tm]] / d[tm] */
+    const int32_t *tm, *tslot;
+} cnt_sm_round;
+int cnt_sm_edges0(int NS, int64_t nE, const int32_t *ptr, const int32_t *src, const double *val,
+                  int64_t val_stride, double *g, int64_t g_stride, void *stream);
+/* c = gs + gd (conductances to source and drain); leak != 0 adds the rounding error of the assembled
+ * FP64 diagonal (cnt_assemble_values' summation order), i.e. the direct solve then answers the same
+ * floating-point matrix as the iterative solvers */
+int cnt_sm_coupling(int NS, int64_t R, const int32_t *rowptr, const double *val, int64_t val_stride,
+                    const double *gs, const double *gd, int leak, double *c, void *stream);
+int cnt_sm_forward(int NS, int nrounds, const cnt_sm_round *rounds, int64_t R, double *g0, double *g1,
+                   int64_t g_stride, double *c, double *b, double *dinv, int64_t pool_e_stride, double *gE,
+                   int64_t pool_g_stride, void *stream);
+int cnt_sm_backward(int NS, int nrounds, const cnt_sm_round *rounds, int64_t R, const double *b,
+                    const double *dinv, int64_t pool_e_stride, const double *gE, int64_t pool_g_stride,
+                    double *x, void *stream);
+
+/* ---------------------------------------------------------------------------------------
  * (6) write-back -- replaces update_voltages / update_currents (cnet.py:132-146).
  * V[S]: stick voltage (0.1 source, 0 drain, NaN outside the percolating component);
  * I[J]: |g (V1 - V2)| per junction (NaN outside the component);

@@ -132,6 +132,8 @@ class Engine(object):
         self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
         self.slab_graph = os.environ.get("CNT_SLAB_GRAPH", "1") != "0"   # solve_sharded: replay blocks of iterations
                                        # (kernels + collectives) as one CUDA graph
+        self.direct_leak = True        # direct solver: answer the assembled FP64 matrix (rounded diagonal, like the
+                                       # iterative solvers and the reference); False = the exact-arithmetic system
         self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
                                        # needs prune)
 
@@ -141,7 +143,7 @@ class Engine(object):
         batch holds 112 SMs, the generation / junction / assembly kernels of the next batch run on
         the SMs it leaves free and the host work of both overlaps (run_pipelined)."""
         other = Engine(self.device, profile=self.profile)
-        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series", "slab_graph"):
+        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series", "slab_graph", "direct_leak"):
             setattr(other, k, getattr(self, k))
         return other
 
@@ -518,9 +520,12 @@ class Engine(object):
                 if auto and compressed and lib.cnt_pcg_cluster_active(chunk_C) <= 0:
                     method, compressed, chunk_C = "flat", False, 0      # cluster launch not possible here
                 with self._work("pcg_aggregates"):
-                    agg = self._aggregates(b, sysm, sys_net, sys_slab, chunk_C) if precond == "twolevel" else None
+                    agg = (self._aggregates(b, sysm, sys_net, sys_slab, chunk_C)
+                           if precond == "twolevel" and method != "direct" else None)
                 self.last_solver = method
-                if method == "cluster":
+                if method == "direct":
+                    x = self._direct_solve(b, sysm)
+                elif method == "cluster":
                     ws = self._ws(lib.cnt_pcg_cluster_workspace_bytes(nsys, NS, R))
                     with self._work("pcg_kernel"):
                       check(lib.cnt_pcg_cluster_solve(B, nsys, NS, _lib.i32_array(sys_net), _lib.i32_array(sys_slab),
@@ -548,6 +553,34 @@ class Engine(object):
                 relres[idx_q, idx_n] = rr
                 status[idx_q, idx_n] = stt
         return dict(x=x, iters=iters, relres=relres, status=status)
+
+    def _direct_solve(self, b, sysm):
+        """Star-mesh elimination (starmesh.py, csrc/starmesh.cu) of all systems of the batch at once:
+        symbolic phase once per batch pattern (cached on the batch: gate sweeps reuse it), numeric
+        phase for all configurations of sysm together.  Returns x [NS, R]."""
+        from . import starmesh
+        R, NNZ = b.R, b.NNZ
+        plan = getattr(b, "_sm_plan", None)
+        if plan is None:
+            with self._work("direct_symbolic"):
+                i64 = torch.int64
+                rowptr = b.rowptr[:R + 1].to(i64)
+                roff = torch.as_tensor(b.h_roff, device=self.device, dtype=i64)
+                rows = torch.arange(R, device=self.device, dtype=i64)
+                net0 = roff[torch.bucketize(rows, roff[1:], right=True)]            # first row of the row's network
+                colg = b.col[:NNZ].to(i64) + torch.repeat_interleave(net0, rowptr.diff())
+                plan = starmesh.finalize(starmesh.symbolic(rowptr, colg, R))
+                b._sm_plan = plan
+        with self._work("direct_numeric"):
+            g = sysm["g"]
+            se, de = b.src_eid[:R].to(torch.int64), b.drn_eid[:R].to(torch.int64)
+            zero = torch.zeros((), dtype=torch.float64, device=self.device)
+            gs = torch.where(se >= 0, g[:, se.clamp(min=0)], zero).contiguous()
+            gd = torch.where(de >= 0, g[:, de.clamp(min=0)], zero).contiguous()
+            x = starmesh.solve_cuda(plan, self.lib, self.stream_ptr, b.rowptr, sysm["val"], gs, gd, sysm["rhs"],
+                                    leak=self.direct_leak)
+        self.last_direct = dict(rounds=plan.nrounds, nnzL=plan.nnzL, max_deg=plan.max_deg, npairs=plan.npairs)
+        return x
 
     def solve_sharded(self, b, sysm, comm, rtol=1e-15, maxit=2000000, check_every=50):
         """Two-level PCG of ONE network (b.B == 1) whose unknown rows are sharded over the ranks of

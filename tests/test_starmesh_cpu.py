@@ -1,0 +1,102 @@
+"""CPU: symbolic phase of the star-mesh direct solver (networksim_cntfet_b200/starmesh.py) with the
+torch restatement of its numeric phase (tests/starmesh_ref.py) against scipy's direct solve."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import torch
+from scipy.sparse.linalg import spsolve
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import slab_ref  # noqa: E402
+import starmesh_ref  # noqa: E402
+from networksim_cntfet_b200 import starmesh  # noqa: E402
+
+
+def _coupling(system):
+    """c = diag - sum of the conductances of a row (what couples the unknown to fixed potentials)"""
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    rows = np.repeat(np.arange(R), np.diff(rowptr))
+    return diag + np.stack([np.bincount(rows, weights=v, minlength=R) for v in val])
+
+
+@pytest.mark.parametrize("n,seed", [(3, 0), (12, 1), (30, 2)])
+def test_grid_systems(n, seed):
+    system = slab_ref.random_network_system(n=n, seed=seed, nconf=3)
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+    plan = starmesh.symbolic(t(rowptr, torch.int64), t(col, torch.int64), R)
+    # every unknown is eliminated exactly once, in independent sets
+    E = torch.cat([r.E for r in plan.rounds])
+    assert np.array_equal(np.sort(E.numpy()), np.arange(R))
+    A0 = (mats[0] != 0).astype(int)
+    for r in plan.rounds[:3]:
+        sub = A0[r.E.numpy()][:, r.E.numpy()]
+        assert (sub - sp.diags(sub.diagonal())).nnz == 0
+    x = starmesh_ref.solve(plan, t(val, torch.float64), t(_coupling(system), torch.float64), t(rhs, torch.float64)).numpy()
+    want = np.stack([spsolve(A.tocsc(), b) for A, b in zip(mats, rhs)])
+    assert np.max(np.abs(x - want)) <= 1e-12 * 0.1
+
+
+def test_batch_of_networks_and_parallel_entries():
+    """two disconnected networks in one pattern (global indices) and duplicate entries of a pair
+    (a virtual series junction next to a real one) are summed"""
+    rng = np.random.default_rng(5)
+    blocks, R = [], 0
+    rows, cols, vals = [], [], []
+    for nn in (17, 9):
+        # ring + chords, some pairs twice
+        e = [(i, (i + 1) % nn) for i in range(nn)] + [(0, nn // 2), (1, nn // 2), (0, nn // 2)]
+        for a, c in e:
+            g = float(np.exp(-5 * rng.random()))
+            rows += [R + a, R + c]
+            cols += [R + c, R + a]
+            vals += [-g, -g]
+        R += nn
+    order = np.lexsort((cols, rows))
+    rows, cols, vals = np.array(rows)[order], np.array(cols)[order], np.array(vals)[order]
+    rowptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=R))]
+    c = np.zeros(R)
+    b = np.zeros(R)
+    c[[0, 20]] = 0.3
+    b[[0, 20]] = 0.03
+    c[[8, 25]] = 0.2
+    A = sp.coo_matrix((vals, (rows, cols)), shape=(R, R)).tocsr()
+    A = A + sp.diags(c - np.asarray(A.sum(1)).ravel())
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+    plan = starmesh.symbolic(t(rowptr, torch.int64), t(cols, torch.int64), R)
+    x = starmesh_ref.solve(plan, t(vals[None], torch.float64), t(c[None], torch.float64), t(b[None], torch.float64)).numpy()[0]
+    assert np.max(np.abs(x - spsolve(A.tocsc(), b))) <= 1e-13
+    plan = starmesh.finalize(plan, keep64=True)
+    assert plan.pool.dtype == torch.int32 and plan.nrounds == len(plan.rounds) and plan.nE_max >= plan.nE0
+
+
+def test_floating_cluster_is_componentwise_accurate():
+    """a strongly connected cluster hanging on the electrodes by 1e-12 contacts: the elimination has no
+    cancellation, the answer is the weighted mean of the electrode potentials to machine precision
+    (an LU of the assembled matrix loses ~1e-16 / 1e-12 here)"""
+    n = 50
+    rows, cols, vals = [], [], []
+    for i in range(n - 1):
+        rows += [i, i + 1]
+        cols += [i + 1, i]
+        vals += [-1.0, -1.0]
+    rowptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=n))]
+    order = np.lexsort((cols, rows))
+    cols, vals = np.array(cols)[order], np.array(vals)[order]
+    c = np.zeros(n)
+    b = np.zeros(n)
+    c[0], b[0] = 1e-12, 0.1 * 1e-12          # source contact
+    c[n - 1] = 3e-12                           # drain contact
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+    plan = starmesh.symbolic(t(rowptr, torch.int64), t(cols, torch.int64), n)
+    x = starmesh_ref.solve(plan, t(vals[None], torch.float64), t(c[None], torch.float64), t(b[None], torch.float64)).numpy()[0]
+    # exact: series of g_s = 1e-12, (n-1) unit conductances, g_d = 3e-12
+    rs, rd = 1 / 1e-12, 1 / 3e-12
+    total = rs + (n - 1) + rd
+    want = 0.1 * (1 - (rs + np.arange(n)) / total)
+    assert np.max(np.abs(x - want) / want) <= 1e-13
