@@ -221,6 +221,7 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.cnt_launch_count()
+    direct_bytes0 = getattr(eng, "direct_bytes_total", 0)
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
@@ -230,6 +231,9 @@ def gpu_arm(args):
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.cnt_launch_count() - launches0
+    direct_bytes = getattr(eng, "direct_bytes_total", 0) - direct_bytes0
+    solver_used = eng.last_solver
+    direct_info = dict(getattr(eng, "last_direct", None) or {})
     dev_ms = e0.elapsed_time(e1)
     stages = eng.stage_times_ms(reset=True)
     clocks = sampler.stop() if rank == 0 else None
@@ -282,12 +286,12 @@ def gpu_arm(args):
         traffic = traffic_note = None
         try:
             cap = json.load(open(os.path.join(ROOT, "profiles", "r01_pcg_cluster_series_bench_launch_ncu.json")))
-            if (eng.last_solver or "").startswith("cluster") and args.batch == 56 and world == 1:
+            if (solver_used or "").startswith("cluster") and args.batch == 56 and world == 1:
                 traffic = cap["dram_bytes_total"]
                 traffic_note = "ncu dram__bytes_read+write of one launch (%s)" % cap["command"]
         except Exception:
             pass
-        roofline = {"bound": "hbm", "kernel": "batched Jacobi-PCG (%s)" % (eng.last_solver or args.solver), "achieved": achieved,
+        roofline = {"bound": "hbm", "kernel": "batched Jacobi-PCG (%s)" % (solver_used or args.solver), "achieved": achieved,
                     "peak": peak, "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
                     "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                     "algorithmic_bytes_per_launch": nbytes / max(args.steps, 1),
@@ -296,6 +300,28 @@ def gpu_arm(args):
                             "shared memory / registers (DRAM traffic ~0), so this is an equivalent-work rate",
                     "algorithmic_bytes": nbytes, "pcg_iterations": iters, "pcg_seconds": pcg_s,
                     "bytes_per_iteration": "12*nnz_offdiag + 116*rows per system"}
+        if solver_used == "direct":
+            # default path: star-mesh direct solve.  Its time is ~95 % the symbolic phase (about 100 rounds of
+            # ~40 small sort / unique / searchsorted / scatter launches on shrinking edge lists) -- latency
+            # bound, far from any bandwidth roof; stated as measured
+            d_s = (stages.get("direct_symbolic", 0.0) + stages.get("direct_numeric", 0.0)) / 1e3
+            achieved = direct_bytes / d_s / 1e9 if d_s > 0 else 0.0
+            roofline = {"bound": "hbm", "kernel": "star-mesh direct solve (symbolic: torch sort/unique/searchsorted of edge "
+                                                  "keys on the device; numeric: k_sm_pivot/newedges/targets/back)",
+                        "achieved": achieved, "peak": peak,
+                        "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
+                        "frac": achieved / peak, "traffic": None,
+                        "algorithmic_bytes_per_launch": direct_bytes / max(args.steps, 1),
+                        "algorithmic_bytes": direct_bytes, "seconds": d_s,
+                        "symbolic_ms_per_step": stages.get("direct_symbolic", 0.0) / max(args.steps, 1),
+                        "numeric_ms_per_step": stages.get("direct_numeric", 0.0) / max(args.steps, 1),
+                        "last_batch": direct_info,
+                        "note": "algorithmic bytes = sorted edge keys of every elimination round read+written once, index "
+                                "lists written once and read once, per gate configuration the edge values of every round, "
+                                "the factor entries and the operands of every star-mesh contribution (starmesh."
+                                "algorithmic_bytes); the stage is latency bound (rounds x small launches), not bandwidth "
+                                "bound; the iterative solvers (--solver cluster: 57 networks/s, equivalent-work rate above "
+                                "the HBM peak because the kernel works out of shared memory) are kept for dense networks"}
         jt = stages.get("junctions", 0.0) / 1e3
         fp64_peak = eng.fp64_peak_tflops()
         line = {

@@ -132,6 +132,9 @@ class Engine(object):
         self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
         self.slab_graph = os.environ.get("CNT_SLAB_GRAPH", "1") != "0"   # solve_sharded: replay blocks of iterations
                                        # (kernels + collectives) as one CUDA graph
+        self.direct_auto = True        # solver 'auto' takes the direct solver when the pattern is sparse enough
+        self.direct_max_degree = 8.0   # ... i.e. at most this many off-diagonal entries per unknown on average
+        self.direct_max_fill = 12.0    # ... and the elimination creates at most this many contributions per edge
         self.direct_leak = True        # direct solver: answer the assembled FP64 matrix (rounded diagonal, like the
                                        # iterative solvers and the reference); False = the exact-arithmetic system
         self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
@@ -143,7 +146,8 @@ class Engine(object):
         batch holds 112 SMs, the generation / junction / assembly kernels of the next batch run on
         the SMs it leaves free and the host work of both overlaps (run_pipelined)."""
         other = Engine(self.device, profile=self.profile)
-        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series", "slab_graph", "direct_leak"):
+        for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series", "slab_graph", "direct_leak", "direct_auto",
+                  "direct_max_degree", "direct_max_fill"):
             setattr(other, k, getattr(self, k))
         return other
 
@@ -512,7 +516,12 @@ class Engine(object):
                 max_rows = max(b.h_roff[n + 1] - b.h_roff[n] for n in nets)
                 precond = self.precond if precond is None else precond
                 auto = method == "auto"
-                if auto:
+                xd = None
+                if method == "direct" or (auto and self._direct_ok(b)):
+                    xd = self._direct_solve(b, sysm, max_fill=self.direct_max_fill if auto else None)
+                    if xd is not None:
+                        method = "direct"
+                if auto and xd is None:
                     method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
                 compressed = method == "cluster" and self.cluster_compressed and "cls" in sysm
                 max_nnz = max(b.h_nzoff[n + 1] - b.h_nzoff[n] for n in nets)
@@ -524,7 +533,7 @@ class Engine(object):
                            if precond == "twolevel" and method != "direct" else None)
                 self.last_solver = method
                 if method == "direct":
-                    x = self._direct_solve(b, sysm)
+                    x = xd
                 elif method == "cluster":
                     ws = self._ws(lib.cnt_pcg_cluster_workspace_bytes(nsys, NS, R))
                     with self._work("pcg_kernel"):
@@ -554,13 +563,21 @@ class Engine(object):
                 status[idx_q, idx_n] = stt
         return dict(x=x, iters=iters, relres=relres, status=status)
 
-    def _direct_solve(self, b, sysm):
+    def _direct_ok(self, b):
+        """auto: is the batch pattern sparse enough for the direct solver?"""
+        return bool(self.direct_auto and b.R and b.NNZ <= self.direct_max_degree * b.R)
+
+    def _direct_solve(self, b, sysm, max_fill=None):
         """Star-mesh elimination (starmesh.py, csrc/starmesh.cu) of all systems of the batch at once:
         symbolic phase once per batch pattern (cached on the batch: gate sweeps reuse it), numeric
         phase for all configurations of sysm together.  Returns x [NS, R]."""
         from . import starmesh
         R, NNZ = b.R, b.NNZ
         plan = getattr(b, "_sm_plan", None)
+        if plan is False:
+            if max_fill is not None:
+                return None             # an earlier attempt exceeded the fill budget
+            plan = None
         if plan is None:
             with self._work("direct_symbolic"):
                 i64 = torch.int64
@@ -569,7 +586,11 @@ class Engine(object):
                 rows = torch.arange(R, device=self.device, dtype=i64)
                 net0 = roff[torch.bucketize(rows, roff[1:], right=True)]            # first row of the row's network
                 colg = b.col[:NNZ].to(i64) + torch.repeat_interleave(net0, rowptr.diff())
-                plan = starmesh.finalize(starmesh.symbolic(rowptr, colg, R))
+                plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill)
+                if plan is None:
+                    b._sm_plan = False
+                    return None
+                plan = starmesh.finalize(plan)
                 b._sm_plan = plan
         with self._work("direct_numeric"):
             g = sysm["g"]
@@ -579,7 +600,10 @@ class Engine(object):
             gd = torch.where(de >= 0, g[:, de.clamp(min=0)], zero).contiguous()
             x = starmesh.solve_cuda(plan, self.lib, self.stream_ptr, b.rowptr, sysm["val"], gs, gd, sysm["rhs"],
                                     leak=self.direct_leak)
-        self.last_direct = dict(rounds=plan.nrounds, nnzL=plan.nnzL, max_deg=plan.max_deg, npairs=plan.npairs)
+        sym, num = starmesh.algorithmic_bytes(plan, sysm["val"].shape[0])
+        self.last_direct = dict(rounds=plan.nrounds, nnzL=plan.nnzL, max_deg=plan.max_deg, npairs=plan.npairs,
+                                bytes_symbolic=sym, bytes_numeric=num)
+        self.direct_bytes_total = getattr(self, "direct_bytes_total", 0) + sym + num
         return x
 
     def solve_sharded(self, b, sysm, comm, rtol=1e-15, maxit=2000000, check_every=50):
@@ -701,7 +725,7 @@ class Engine(object):
         prio = [max(abs(v) for v in gs.levels) for gs in gates]   # higher |Vg| -> more iterations -> first
         x0 = self.linear_guess(b, len(gates)) if self.initial_guess == "linear" else None
         if (row_shard is None and b.B == 1 and self.solver == "auto" and self.precond == "twolevel" and
-                b.R > self.lib.cnt_pcg_cluster_max_rows()):
+                b.R > self.lib.cnt_pcg_cluster_max_rows() and not self._direct_ok(b)):
             # one network beyond the cluster kernel's on-chip capacity: the row-slab solver with a single
             # rank advances all configurations together (measured 2x the multi-launch solver at 10M sticks)
             from . import slab

@@ -53,12 +53,14 @@ def _ragged_arange(counts):
     return torch.arange(owner.numel(), device=counts.device) - start[owner], owner
 
 
-def symbolic(rowptr, col, R):
+def symbolic(rowptr, col, R, max_fill=None):
     """rowptr [R+1], col [NNZ] (global row indices of the batch; symmetric pattern, no diagonal).
     Every round eliminates the unknowns whose (degree, hash, index) is the smallest among their
     neighbours: an independent set, low degrees first (a parallel minimum-degree ordering; measured on
     a 100x100 um system: 85 rounds, 1.6 entries of L per entry of A, largest pivot degree 18 --
-    the same fill as a sequential minimum-degree ordering).  Returns a Plan."""
+    the same fill as a sequential minimum-degree ordering).  Returns a Plan, or None when the number of
+    star-mesh contributions exceeds max_fill times the number of edges (dense, mesh-like networks far
+    above the percolation threshold: the caller then uses an iterative solver)."""
     dev = rowptr.device
     i64 = torch.int64
     rowptr = rowptr.to(i64)
@@ -80,6 +82,7 @@ def symbolic(rowptr, col, R):
     h = (ids * 2654435761) % 1048573                     # fixed pseudo-random tie break
     gbase = 0
     n_alive = R
+    npairs = 0
     while n_alive > 0:
         nE = int(eu.numel())
         deg = torch.bincount(eu, minlength=R) + torch.bincount(ew, minlength=R)
@@ -106,6 +109,9 @@ def symbolic(rowptr, col, R):
         # all pairs (i < j) of every eliminated unknown's neighbours
         pos = torch.arange(v.numel(), device=dev, dtype=i64) - nptr[m]
         partners = cnt[m] - 1 - pos
+        npairs += int(partners.sum())
+        if max_fill is not None and npairs > max_fill * max(plan.nE0, 1) + 100000:
+            return None
         off, ia = _ragged_arange(partners)
         ib = ia + off + 1
         pkey = o[ia] * R + o[ib]                          # neighbours ascending inside a node: o[ia] < o[ib]
@@ -183,6 +189,8 @@ def finalize(plan, keep64=False):
     plan.round_sizes = [int(r.E.numel()) for r in plan.rounds]
     plan.npairs = sum(int(r.cm.numel()) for r in plan.rounds)
     plan.nrounds = len(plan.rounds)
+    plan.pool_entries = int(pool.numel())
+    plan.sum_nE = sum(int(r.nE_old) + int(r.nE_new) for r in plan.rounds)
     if not keep64:
         plan.rounds = None          # the 64-bit lists are not needed any more
         plan.e0_ptr = plan.e0_src = None
@@ -216,3 +224,14 @@ def solve_cuda(plan, lib, stream_ptr, rowptr, val, gs, gd, rhs, leak=True):
     check(lib.cnt_sm_backward(NS, plan.nrounds, plan.c_rounds, R, vp(b.data_ptr()), vp(dinv.data_ptr()), dinv.stride(0),
                               vp(gE.data_ptr()), gE.stride(0), vp(x.data_ptr()), stream_ptr))
     return x
+
+
+def algorithmic_bytes(plan, NS):
+    """bytes the direct stage has to move at least once: symbolic -- the sorted edge keys of every round
+    read and written once (8 B each) and the index lists written once (4 B per entry); numeric -- the
+    index lists read once, and per configuration the edge values of every round read and written
+    once, the factor entries (gE) written and read, the three operands of every star-mesh contribution
+    and 8 vectors of R doubles"""
+    sym = 16 * plan.sum_nE + 4 * plan.pool_entries
+    num = 4 * plan.pool_entries + 8 * NS * (plan.sum_nE + 3 * plan.nnzL + 3 * plan.npairs + 8 * plan.R)
+    return sym, num

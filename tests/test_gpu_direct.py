@@ -80,7 +80,7 @@ def test_fullnet_direct_vs_goldens(direct, name):
 def test_direct_full_size_vs_cluster_and_oracle(direct):
     """3 networks of 100x100 um: currents against the iterative cluster solver and the refined oracle;
     voltages of the assembled FP64 matrix (leak on) against the cluster solver's"""
-    direct.solver = "auto"
+    direct.solver = "cluster"
     ref = direct.measure_fullnet(direct.generate([100000] * 3, 100.0, seed=31), onoffmap=1, want_fields=True)
     direct.solver = "direct"
     b = direct.generate([100000] * 3, 100.0, seed=31)

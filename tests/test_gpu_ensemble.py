@@ -52,16 +52,14 @@ def test_example_config_5um(engine):
 @pytest.mark.parametrize("n,onoffmap,element", [(120000, 1, "linexp"), (100000, 0, "fermidirac"), (90000, 2, "linexp")])
 def test_full_size_variants(engine, n, onoffmap, element):
     """100x100 um at other densities / on-off maps / elements (slurm/batchmeasure_multi.sh sweeps density
-    8..12); a network beyond the cluster kernel's on-chip capacity takes the row-slab solver
-    automatically; all against the refined oracle from the same sticks"""
+    8..12) through the default (direct) solver; all against the refined oracle from the same sticks"""
     from networksim_cntfet_b200 import elements
     el = elements.FermiDiracTransistor if element == "fermidirac" else elements.LinExpTransistor
     b = engine.generate([n], 100.0, seed=77)
     res = engine.measure_fullnet(b, onoffmap=onoffmap, element=el)
     rows = b.h_roff[1]
     from networksim_cntfet_b200 import _lib
-    expect = "cluster" if rows <= _lib.load().cnt_pcg_cluster_max_rows() else "slab"
-    assert engine.last_solver.startswith(expect), (engine.last_solver, rows)
+    assert engine.last_solver == "direct", (engine.last_solver, rows)      # sparse pattern: star-mesh direct solver
     assert np.all(res["status"] == 0)
     s = engine.sticks_to_host(b)[0]
     m = O.measure_fullnet(s, onoffmap=onoffmap, element=element, refine=3)

@@ -124,7 +124,12 @@ def test_sharded_fullnet_matches_oracle_and_unsharded(engine, world):
 
 def test_sharded_full_size_100um(engine):
     """100x100 um (46k unknowns after the exact reductions) on 8 ranks vs the cluster solver"""
-    ref = engine.measure_fullnet(engine.generate([100000], 100.0, seed=9), onoffmap=1)
+    engine.direct_auto = False          # reference: the iterative cluster solver
+    try:
+        ref = engine.measure_fullnet(engine.generate([100000], 100.0, seed=9), onoffmap=1)
+        assert engine.last_solver.startswith("cluster")
+    finally:
+        engine.direct_auto = True
     res = engine.measure_fullnet(engine.generate([100000], 100.0, seed=9), onoffmap=1, row_shard=slab.LocalComm(8))
     assert np.all(res["status"] == 0)
     states = engine.last_slab_states
@@ -137,7 +142,11 @@ def test_large_single_network_takes_slab_solver(engine):
     """a single network beyond the cluster kernel's capacity (160x160 um, ~118k unknowns) is solved by
     the row-slab solver with one rank; currents against the refined oracle"""
     b = engine.generate([256000], 160.0, seed=3)
-    res = engine.measure_fullnet(b, onoffmap=1)
+    engine.direct_auto = False          # the iterative route (the direct solver would take it otherwise)
+    try:
+        res = engine.measure_fullnet(b, onoffmap=1)
+    finally:
+        engine.direct_auto = True
     from networksim_cntfet_b200 import _lib
     assert b.R > _lib.load().cnt_pcg_cluster_max_rows() and engine.last_solver == "slab x1"
     assert np.all(res["status"] == 0)
