@@ -586,7 +586,7 @@ class Engine(object):
                 rows = torch.arange(R, device=self.device, dtype=i64)
                 net0 = roff[torch.bucketize(rows, roff[1:], right=True)]            # first row of the row's network
                 colg = b.col[:NNZ].to(i64) + torch.repeat_interleave(net0, rowptr.diff())
-                plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill)
+                plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill, local_ids=rows - net0)
                 if plan is None:
                     b._sm_plan = False
                     return None

@@ -53,14 +53,16 @@ def _ragged_arange(counts):
     return torch.arange(owner.numel(), device=counts.device) - start[owner], owner
 
 
-def symbolic(rowptr, col, R, max_fill=None):
+def symbolic(rowptr, col, R, max_fill=None, local_ids=None):
     """rowptr [R+1], col [NNZ] (global row indices of the batch; symmetric pattern, no diagonal).
     Every round eliminates the unknowns whose (degree, hash, index) is the smallest among their
     neighbours: an independent set, low degrees first (a parallel minimum-degree ordering; measured on
     a 100x100 um system: 85 rounds, 1.6 entries of L per entry of A, largest pivot degree 18 --
     the same fill as a sequential minimum-degree ordering).  Returns a Plan, or None when the number of
     star-mesh contributions exceeds max_fill times the number of edges (dense, mesh-like networks far
-    above the percolation threshold: the caller then uses an iterative solver)."""
+    above the percolation threshold: the caller then uses an iterative solver).
+    local_ids [R]: index of every row inside its own network; the tie-break hash is taken from it, so a
+    network is eliminated in the same order -- and gives the same bits -- whatever else is in the batch."""
     dev = rowptr.device
     i64 = torch.int64
     rowptr = rowptr.to(i64)
@@ -78,7 +80,7 @@ def symbolic(rowptr, col, R, max_fill=None):
     plan.e0_ptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.bincount(inv, minlength=plan.nE0).cumsum(0)])
     eu, ew = ukey // R, ukey % R
     alive = torch.ones(R, dtype=torch.bool, device=dev)
-    ids = torch.arange(R, device=dev, dtype=i64)
+    ids = torch.arange(R, device=dev, dtype=i64) if local_ids is None else local_ids.to(i64)
     h = (ids * 2654435761) % 1048573                     # fixed pseudo-random tie break
     gbase = 0
     n_alive = R
