@@ -399,6 +399,13 @@ int cnt_sm_coupling(int NS, int64_t R, const int32_t *rowptr, const double *val,
 int cnt_sm_forward(int NS, int nrounds, const cnt_sm_round *rounds, int64_t R, double *g0, double *g1,
                    int64_t g_stride, double *c, double *b, double *dinv, int64_t pool_e_stride, double *gE,
                    int64_t pool_g_stride, void *stream);
+/* dense tail: the unknowns left after the sparse rounds (a few hundred per network), one CTA per
+ * (network, configuration); doff[nnet+1]: offsets of the n_b x n_b matrices in the pool G [NS, gpool];
+ * dptr[nnet+1] / dnodes: the remaining rows of every network (ascending); epos[nE]: position of every
+ * remaining edge in the pool; g: edge values after the last round; writes x of the remaining rows */
+int cnt_sm_dense(int NS, int64_t R, int nnet, const int64_t *doff, const int32_t *dptr, const int32_t *dnodes,
+                 int64_t nE, const int64_t *epos, const double *g, int64_t g_stride, double *G, int64_t gpool,
+                 const double *c, const double *b, double *x, int nmax, void *stream);
 int cnt_sm_backward(int NS, int nrounds, const cnt_sm_round *rounds, int64_t R, const double *b,
                     const double *dinv, int64_t pool_e_stride, const double *gE, int64_t pool_g_stride,
                     double *x, void *stream);

@@ -64,6 +64,7 @@ PROTOTYPES = {
     "cnt_sm_edges0": (i32, [i32, i64, vp, vp, vp, i64, vp, i64, vp]),
     "cnt_sm_coupling": (i32, [i32, i64, vp, vp, i64, vp, vp, i32, vp, vp]),
     "cnt_sm_forward": (i32, [i32, i32, vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp]),
+    "cnt_sm_dense": (i32, [i32, i64, i32, vp, vp, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i32, vp]),
     "cnt_sm_backward": (i32, [i32, i32, vp, i64, vp, vp, i64, vp, i64, vp, vp]),
     "cnt_slab_block_rows": (i32, []),
     "cnt_slab_init": (i32, [vp, vp]),

@@ -118,6 +118,77 @@ __global__ void k_sm_back(RoundArgs a) {
     x[v] = s * a.dinv[(int64_t)q * a.pool_e_stride + a.ebase + m];
 }
 
+// ---- dense tail: once every network is down to a few hundred unknowns (the dense core that the
+// rounds would take one handful at a time), one CTA per (network, configuration) finishes the same
+// star-mesh elimination on a dense upper-triangular conductance matrix G [n x n] in global memory
+// (L2 resident), in ascending row order, and back-substitutes.  A warp takes one neighbour row of the
+// pivot at a time; rows without a junction to the pivot are skipped, so the cost follows the actual
+// degrees.  Same formulas as the sparse rounds: sums of positive terms only.
+constexpr int DENSE_TB = 256;
+__global__ void k_sm_dense_fill(int64_t nE, const long long *__restrict__ epos, const double *__restrict__ g,
+                                int64_t g_stride, double *__restrict__ G, int64_t gpool) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= nE) return;
+    G[(int64_t)blockIdx.y * gpool + epos[e]] = g[(int64_t)blockIdx.y * g_stride + e];
+}
+__global__ void __launch_bounds__(DENSE_TB) k_sm_dense(int64_t R, const long long *__restrict__ doff,
+                                                       const int32_t *__restrict__ dptr, const int32_t *__restrict__ dnodes,
+                                                       double *__restrict__ Gall, int64_t gpool, const double *__restrict__ c_in,
+                                                       const double *__restrict__ b_in, double *__restrict__ x_out, int nmax) {
+    extern __shared__ double smd[];
+    double *rowk = smd, *cc = smd + nmax, *bb = smd + 2 * nmax, *dinv = smd + 3 * nmax, *red = smd + 4 * nmax;
+    const int net = blockIdx.x, q = blockIdx.y;
+    const int n = dptr[net + 1] - dptr[net];
+    if (n <= 0) return;
+    const int32_t *nodes = dnodes + dptr[net];
+    double *G = Gall + (int64_t)q * gpool + doff[net];
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = DENSE_TB >> 5;
+    for (int i = t; i < n; i += DENSE_TB) {
+        cc[i] = c_in[(int64_t)q * R + nodes[i]];
+        bb[i] = b_in[(int64_t)q * R + nodes[i]];
+    }
+    __syncthreads();
+    for (int k = 0; k < n; k++) {
+        // pivot row (upper part) into shared memory, d_k = c_k + its sum (fixed order)
+        double part = 0.0;
+        for (int j = k + 1 + t; j < n; j += DENSE_TB) {
+            double v = G[(int64_t)k * n + j];
+            rowk[j] = v;
+            part += v;
+        }
+        part = cnt::block_sum(part, red);
+        if (t == 0) {
+            double d = cc[k] + part;
+            dinv[k] = 1.0 / d;
+        }
+        __syncthreads();
+        const double di = dinv[k], ck = cc[k], bk = bb[k];
+        for (int i = k + 1 + w; i < n; i += nw) {          // one warp per neighbour row
+            const double gi = rowk[i];
+            if (gi == 0.0) continue;
+            const double f = gi * di;
+            for (int j = i + 1 + lane; j < n; j += 32) {
+                const double gj = rowk[j];
+                if (gj != 0.0) G[(int64_t)i * n + j] += f * gj;
+            }
+            if (lane == 0) {
+                cc[i] += f * ck;
+                bb[i] += f * bk;
+            }
+        }
+        __syncthreads();
+    }
+    // back-substitution: x_k = (b_k + sum_{j>k} G[k][j] x_j) / d_k; x kept in rowk
+    for (int k = n - 1; k >= 0; k--) {
+        double part = 0.0;
+        for (int j = k + 1 + t; j < n; j += DENSE_TB) part += G[(int64_t)k * n + j] * rowk[j];
+        part = cnt::block_sum(part, red);
+        if (t == 0) rowk[k] = (bb[k] + part) * dinv[k];
+        __syncthreads();
+    }
+    for (int i = t; i < n; i += DENSE_TB) x_out[(int64_t)q * R + nodes[i]] = rowk[i];
+}
+
 RoundArgs make_args(const cnt_sm_round *r, int64_t R, int64_t g_stride, int64_t pool_e_stride, int64_t pool_g_stride,
                     const double *g_old, double *g_new, double *c, double *b, double *x, double *dinv, double *gE) {
     RoundArgs a;
@@ -194,5 +265,24 @@ extern "C" int cnt_sm_backward(int NS, int nrounds, const cnt_sm_round *rounds, 
         k_sm_back<<<dim3(cnt::grid_for(r->nelim, TB), NS, 1), TB, 0, st>>>(a);
         CNT_LAUNCHED();
     }
+    return CNT_OK;
+}
+
+// dense tail (see k_sm_dense): g = edge values after the last sparse round; epos[e] = position of edge e in
+// the pool of dense matrices; c, b as left by the sparse rounds; writes x of the remaining unknowns
+extern "C" int cnt_sm_dense(int NS, int64_t R, int nnet, const int64_t *doff, const int32_t *dptr, const int32_t *dnodes,
+                            int64_t nE, const int64_t *epos, const double *g, int64_t g_stride, double *G, int64_t gpool,
+                            const double *c, const double *b, double *x, int nmax, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(NS > 0 && nnet > 0 && doff && dptr && dnodes && G && c && b && x && nmax > 0 && nmax <= 1400 && gpool > 0);
+    CNT_CUDA(cudaMemsetAsync(G, 0, sizeof(double) * (size_t)NS * (size_t)gpool, st));
+    if (nE > 0) {
+        CNT_CHECK_ARG(epos && g);
+        k_sm_dense_fill<<<dim3(cnt::grid_for(nE, TB), NS, 1), TB, 0, st>>>(nE, (const long long *)epos, g, g_stride, G, gpool);
+        CNT_LAUNCHED();
+    }
+    size_t smem = sizeof(double) * (4 * (size_t)nmax + 32);
+    k_sm_dense<<<dim3(nnet, NS, 1), DENSE_TB, smem, st>>>(R, (const long long *)doff, dptr, dnodes, G, gpool, c, b, x, nmax);
+    CNT_LAUNCHED();
     return CNT_OK;
 }

@@ -135,6 +135,8 @@ class Engine(object):
         self.direct_auto = True        # solver 'auto' takes the direct solver when the pattern is sparse enough
         self.direct_max_degree = 8.0   # ... i.e. at most this many off-diagonal entries per unknown on average
         self.direct_max_fill = 12.0    # ... and the elimination creates at most this many contributions per edge
+        self.direct_dense_max = 384    # ... and finishes with one dense elimination per network once <= this many unknowns
+                                       # are left in every network (0 = sparse rounds to the end)
         self.direct_leak = True        # direct solver: answer the assembled FP64 matrix (rounded diagonal, like the
                                        # iterative solvers and the reference); False = the exact-arithmetic system
         self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
@@ -147,7 +149,7 @@ class Engine(object):
         the SMs it leaves free and the host work of both overlaps (run_pipelined)."""
         other = Engine(self.device, profile=self.profile)
         for k in ("solver", "initial_guess", "precond", "theta", "cluster_compressed", "spatial_order", "prune", "series", "slab_graph", "direct_leak", "direct_auto",
-                  "direct_max_degree", "direct_max_fill"):
+                  "direct_max_degree", "direct_max_fill", "direct_dense_max"):
             setattr(other, k, getattr(self, k))
         return other
 
@@ -584,9 +586,11 @@ class Engine(object):
                 rowptr = b.rowptr[:R + 1].to(i64)
                 roff = torch.as_tensor(b.h_roff, device=self.device, dtype=i64)
                 rows = torch.arange(R, device=self.device, dtype=i64)
-                net0 = roff[torch.bucketize(rows, roff[1:], right=True)]            # first row of the row's network
+                net_idx = torch.bucketize(rows, roff[1:], right=True)
+                net0 = roff[net_idx]                                                 # first row of the row's network
                 colg = b.col[:NNZ].to(i64) + torch.repeat_interleave(net0, rowptr.diff())
-                plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill, local_ids=rows - net0)
+                plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill, local_ids=rows - net0, net_ids=net_idx,
+                                         nnet=b.B, dense_max=int(self.direct_dense_max))
                 if plan is None:
                     b._sm_plan = False
                     return None
@@ -602,6 +606,7 @@ class Engine(object):
                                     leak=self.direct_leak)
         sym, num = starmesh.algorithmic_bytes(plan, sysm["val"].shape[0])
         self.last_direct = dict(rounds=plan.nrounds, nnzL=plan.nnzL, max_deg=plan.max_deg, npairs=plan.npairs,
+                                dense_nmax=plan.dense["nmax"] if plan.dense else 0,
                                 bytes_symbolic=sym, bytes_numeric=num)
         self.direct_bytes_total = getattr(self, "direct_bytes_total", 0) + sym + num
         return x

@@ -53,7 +53,7 @@ def _ragged_arange(counts):
     return torch.arange(owner.numel(), device=counts.device) - start[owner], owner
 
 
-def symbolic(rowptr, col, R, max_fill=None, local_ids=None):
+def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1, dense_max=0):
     """rowptr [R+1], col [NNZ] (global row indices of the batch; symmetric pattern, no diagonal).
     Every round eliminates the unknowns whose (degree, hash, index) is the smallest among their
     neighbours: an independent set, low degrees first (a parallel minimum-degree ordering; measured on
@@ -62,7 +62,10 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None):
     star-mesh contributions exceeds max_fill times the number of edges (dense, mesh-like networks far
     above the percolation threshold: the caller then uses an iterative solver).
     local_ids [R]: index of every row inside its own network; the tie-break hash is taken from it, so a
-    network is eliminated in the same order -- and gives the same bits -- whatever else is in the batch."""
+    network is eliminated in the same order -- and gives the same bits -- whatever else is in the batch.
+    net_ids [R], nnet, dense_max: as soon as no network has more than dense_max unknowns left, the rounds
+    stop and the rest -- the dense core the rounds would take a handful at a time -- is described as one
+    small dense system per network (plan.dense; csrc/starmesh.cu k_sm_dense)."""
     dev = rowptr.device
     i64 = torch.int64
     rowptr = rowptr.to(i64)
@@ -85,7 +88,23 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None):
     gbase = 0
     n_alive = R
     npairs = 0
+    plan.dense = None
+    if net_ids is None:
+        net_ids = torch.zeros(R, dtype=i64, device=dev)
     while n_alive > 0:
+        if dense_max and n_alive <= dense_max * nnet:
+            an = torch.nonzero(alive).flatten()
+            nid = net_ids[an]
+            cntb = torch.zeros(nnet, dtype=i64, device=dev).scatter_add_(0, nid, torch.ones_like(nid))
+            if int(cntb.max()) <= dense_max:
+                dptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), cntb.cumsum(0)])
+                loc = torch.full((R,), -1, dtype=i64, device=dev)
+                loc[an] = torch.arange(an.numel(), device=dev, dtype=i64) - dptr[nid]
+                doff = torch.cat([torch.zeros(1, dtype=i64, device=dev), (cntb * cntb).cumsum(0)])
+                enet = net_ids[eu]
+                plan.dense = dict(dptr=dptr, dnodes=an, doff=doff, epos=doff[enet] + loc[eu] * cntb[enet] + loc[ew],
+                                  nE=int(eu.numel()), nmax=int(cntb.max()), gpool=max(int(doff[-1]), 1), nnet=int(nnet))
+                break
         nE = int(eu.numel())
         deg = torch.bincount(eu, minlength=R) + torch.bincount(ew, minlength=R)
         cand = alive
@@ -187,10 +206,17 @@ def finalize(plan, keep64=False):
             k += 1
     plan.c_rounds = arr
     plan.nE_max = max([plan.nE0] + [int(r.nE_new) for r in plan.rounds] + [1])
+    plan.max_deg = max(plan.max_deg, plan.dense["nmax"] if plan.dense else 0)
     # the symbolic lists are no longer needed on the device in 64-bit form
     plan.round_sizes = [int(r.E.numel()) for r in plan.rounds]
     plan.npairs = sum(int(r.cm.numel()) for r in plan.rounds)
     plan.nrounds = len(plan.rounds)
+    if plan.dense is not None:
+        d = plan.dense
+        d["dptr32"] = d["dptr"].to(torch.int32)
+        d["dnodes32"] = d["dnodes"].to(torch.int32)
+        d["doff"] = d["doff"].contiguous()
+        d["epos"] = d["epos"].contiguous()
     plan.pool_entries = int(pool.numel())
     plan.sum_nE = sum(int(r.nE_old) + int(r.nE_new) for r in plan.rounds)
     if not keep64:
@@ -223,6 +249,14 @@ def solve_cuda(plan, lib, stream_ptr, rowptr, val, gs, gd, rhs, leak=True):
     check(lib.cnt_sm_forward(NS, plan.nrounds, plan.c_rounds, R, vp(g0.data_ptr()), vp(g1.data_ptr()), plan.nE_max,
                              vp(c.data_ptr()), vp(b.data_ptr()), vp(dinv.data_ptr()), dinv.stride(0), vp(gE.data_ptr()),
                              gE.stride(0), stream_ptr))
+    if plan.dense is not None:
+        d = plan.dense
+        cur = g0 if plan.nrounds % 2 == 0 else g1
+        G = torch.empty((NS, d["gpool"]), dtype=f64, device=dev)
+        check(lib.cnt_sm_dense(NS, R, d["nnet"], vp(d["doff"].data_ptr()), vp(d["dptr32"].data_ptr()),
+                               vp(d["dnodes32"].data_ptr()), d["nE"], vp(d["epos"].data_ptr()) if d["nE"] else None,
+                               vp(cur.data_ptr()), plan.nE_max, vp(G.data_ptr()), d["gpool"], vp(c.data_ptr()),
+                               vp(b.data_ptr()), vp(x.data_ptr()), d["nmax"], stream_ptr))
     check(lib.cnt_sm_backward(NS, plan.nrounds, plan.c_rounds, R, vp(b.data_ptr()), vp(dinv.data_ptr()), dinv.stride(0),
                               vp(gE.data_ptr()), gE.stride(0), vp(x.data_ptr()), stream_ptr))
     return x
@@ -236,4 +270,6 @@ def algorithmic_bytes(plan, NS):
     and 8 vectors of R doubles"""
     sym = 16 * plan.sum_nE + 4 * plan.pool_entries
     num = 4 * plan.pool_entries + 8 * NS * (plan.sum_nE + 3 * plan.nnzL + 3 * plan.npairs + 8 * plan.R)
+    if plan.dense is not None:        # dense tail: every matrix written (zero + fill) and read once
+        num += 8 * NS * 2 * plan.dense["gpool"]
     return sym, num

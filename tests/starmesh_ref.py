@@ -43,7 +43,38 @@ def solve(plan, val, c, b):
         b[:, r.tn] += _segsum_exact(w * b[:, r.E][:, r.tm], r.tptr)
         g = gn
     x = torch.zeros_like(b)
+    if getattr(plan, "dense", None) is not None:
+        _dense_tail(plan.dense, g, c, b, x)
     for r, dinv in zip(reversed(plan.rounds), reversed(dinvs)):
         ge = gE[:, r.gbase:r.gbase + r.eslot.numel()]
         x[:, r.E] = (b[:, r.E] + _segsum_exact(ge * x[:, r.nbr], r.nptr)) * dinv
     return x
+
+
+def _dense_tail(d, g, c, b, x):
+    """the unknowns left after the sparse rounds: the same star-mesh elimination on one dense
+    upper-triangular conductance matrix per network, ascending rows (k_sm_dense)"""
+    NS = g.shape[0]
+    dptr, nodes, doff, epos = d["dptr"], d["dnodes"], d["doff"], d["epos"]
+    pool = torch.zeros((NS, d["gpool"]), dtype=g.dtype, device=g.device)
+    if d["nE"]:
+        pool[:, epos] = g[:, :d["nE"]]
+    for net in range(d["nnet"]):
+        n = int(dptr[net + 1] - dptr[net])
+        if n == 0:
+            continue
+        rows = nodes[int(dptr[net]):int(dptr[net + 1])]
+        G = pool[:, int(doff[net]):int(doff[net]) + n * n].reshape(NS, n, n).clone()
+        cc, bb = c[:, rows].clone(), b[:, rows].clone()
+        dinv = torch.zeros((NS, n), dtype=g.dtype, device=g.device)
+        for k in range(n):
+            row = G[:, k, k + 1:]
+            dinv[:, k] = 1.0 / (cc[:, k] + row.sum(1))
+            f = row * dinv[:, k:k + 1]
+            G[:, k + 1:, k + 1:] += torch.triu(f[:, :, None] * row[:, None, :], diagonal=1)
+            cc[:, k + 1:] += f * cc[:, k:k + 1]
+            bb[:, k + 1:] += f * bb[:, k:k + 1]
+        xs = torch.zeros((NS, n), dtype=g.dtype, device=g.device)
+        for k in range(n - 1, -1, -1):
+            xs[:, k] = (bb[:, k] + (G[:, k, k + 1:] * xs[:, k + 1:]).sum(1)) * dinv[:, k]
+        x[:, rows] = xs

@@ -55,6 +55,52 @@ def test_cuda_numeric_equals_torch_restatement(engine):
     assert float((x.cpu() - want).abs().max()) <= 1e-13 * VDS
 
 
+@pytest.mark.parametrize("dense_max", [40, 1000])
+def test_cuda_dense_tail_equals_torch_restatement(engine, dense_max):
+    """batch of two copies of a system; sparse rounds down to dense_max unknowns per network, then k_sm_dense"""
+    system = slab_ref.random_network_system(n=16, seed=9, nconf=3)
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    rows = np.repeat(np.arange(R), np.diff(rowptr))
+    c = diag + np.stack([np.bincount(rows, weights=v, minlength=R) for v in val])
+    rowptr2, col2 = np.r_[rowptr, rowptr[-1] + rowptr[1:]], np.r_[col, col + R]
+    t = lambda a, dt, dev: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
+    out = {}
+    for dev in ("cpu", engine.device):
+        kw = dict(local_ids=t(np.r_[np.arange(R), np.arange(R)], torch.int64, dev),
+                  net_ids=t(np.repeat([0, 1], R), torch.int64, dev), nnet=2, dense_max=dense_max)
+        if dev == "cpu":
+            plan = starmesh.symbolic(t(rowptr2, torch.int64, dev), t(col2, torch.int64, dev), 2 * R, **kw)
+            out[dev] = starmesh_ref.solve(plan, t(np.c_[val, val], torch.float64, dev), t(np.c_[c, c], torch.float64, dev),
+                                          t(np.c_[rhs, rhs], torch.float64, dev))
+        else:
+            with engine._work():
+                plan = starmesh.finalize(starmesh.symbolic(t(rowptr2, torch.int64, dev), t(col2, torch.int64, dev), 2 * R, **kw))
+                gd = t(np.c_[c, c], torch.float64, dev)
+                out["gpu"] = starmesh.solve_cuda(plan, engine.lib, engine.stream_ptr, t(rowptr2, torch.int32, dev),
+                                                 t(np.c_[val, val], torch.float64, dev), torch.zeros_like(gd), gd,
+                                                 t(np.c_[rhs, rhs], torch.float64, dev), leak=False)
+            engine.sync()
+            assert plan.dense is not None and plan.dense["nmax"] <= dense_max
+    x = out["gpu"].cpu()
+    assert float((x - out["cpu"]).abs().max()) <= 1e-13 * VDS
+    assert torch.equal(x[:, :R], x[:, R:])
+
+
+def test_dense_tail_switch_does_not_change_the_answer(direct):
+    """sparse rounds to the end vs the dense tail: same currents to rounding (20x20 um batch)"""
+    res = {}
+    for dm in (0, 384):
+        direct.direct_dense_max = dm
+        try:
+            res[dm] = direct.measure_fullnet(direct.generate([6400, 5000, 3000], 20.0, seed=8), onoffmap=1)
+            assert (direct.last_direct["dense_nmax"] > 0) == (dm > 0)
+        finally:
+            direct.direct_dense_max = 384
+    for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert np.all(np.abs(res[0][key] - res[384][key]) <= 1e-12 * np.abs(res[0][key]))
+
+
 @pytest.mark.parametrize("name", PERC)
 def test_fullnet_direct_vs_goldens(direct, name):
     """measure_fullnet with the direct solver: V, |I|, I_source against the refined oracle and the raw reference"""

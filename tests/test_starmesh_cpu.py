@@ -42,6 +42,34 @@ def test_grid_systems(n, seed):
     assert np.max(np.abs(x - want)) <= 1e-12 * 0.1
 
 
+@pytest.mark.parametrize("dense_max", [4, 40, 1000])
+def test_dense_tail(dense_max):
+    """the rounds stop when no network has more than dense_max unknowns left; the rest is one dense
+    star-mesh elimination per network (dense_max = 1000: no sparse round at all)"""
+    system = slab_ref.random_network_system(n=14, seed=6, nconf=2)
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    # two copies of the system as a batch of two networks
+    rowptr2 = np.r_[rowptr, rowptr[-1] + rowptr[1:]]
+    col2 = np.r_[col, col + R]
+    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
+    net_ids = t(np.repeat([0, 1], R), torch.int64)
+    local = t(np.r_[np.arange(R), np.arange(R)], torch.int64)
+    plan = starmesh.symbolic(t(rowptr2, torch.int64), t(col2, torch.int64), 2 * R, local_ids=local, net_ids=net_ids, nnet=2,
+                             dense_max=dense_max)
+    assert plan.dense is not None and plan.dense["nmax"] <= dense_max
+    if dense_max >= R:
+        assert len(plan.rounds) == 0
+    c = _coupling(system)
+    x = starmesh_ref.solve(plan, t(np.c_[val, val], torch.float64), t(np.c_[c, c], torch.float64),
+                           t(np.c_[rhs, rhs], torch.float64)).numpy()
+    want = np.stack([spsolve(A.tocsc(), b) for A, b in zip(mats, rhs)])
+    assert np.max(np.abs(x[:, :R] - want)) <= 1e-12 * 0.1
+    assert np.array_equal(x[:, :R], x[:, R:])                 # same network, same bits, wherever it sits in the batch
+    plan = starmesh.finalize(plan, keep64=True)
+    assert plan.dense["dptr32"].dtype == torch.int32
+
+
 def test_batch_of_networks_and_parallel_entries():
     """two disconnected networks in one pattern (global indices) and duplicate entries of a pair
     (a virtual series junction next to a real one) are summed"""
