@@ -46,6 +46,11 @@ class Plan(object):
         self.max_deg = 0
 
 
+def _count(idx, n):
+    """histogram of idx over [0, n) without the host synchronisation of torch.bincount"""
+    return torch.zeros(int(n), dtype=torch.int64, device=idx.device).scatter_add_(0, idx, torch.ones_like(idx))
+
+
 def _ragged_arange(counts):
     """[0..c0-1, 0..c1-1, ...] and the owner index of every element"""
     owner = torch.repeat_interleave(torch.arange(counts.numel(), device=counts.device), counts)
@@ -88,6 +93,7 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
     gbase = 0
     n_alive = R
     npairs = 0
+    maxdeg_t = torch.zeros((), dtype=i64, device=dev)
     plan.dense = None
     if net_ids is None:
         net_ids = torch.zeros(R, dtype=i64, device=dev)
@@ -106,7 +112,7 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
                                   nE=int(eu.numel()), nmax=int(cntb.max()), gpool=max(int(doff[-1]), 1), nnet=int(nnet))
                 break
         nE = int(eu.numel())
-        deg = torch.bincount(eu, minlength=R) + torch.bincount(ew, minlength=R)
+        deg = _count(eu, R) + _count(ew, R)
         cand = alive
         pri = (deg * 1048573 + h) * R + ids
         both = cand[eu] & cand[ew]
@@ -125,7 +131,7 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         srt = torch.argsort(v * R + o)
         v, o, slot = v[srt], o[srt], slot[srt]
         m = mid[v]
-        cnt = torch.bincount(m, minlength=int(E.numel()))
+        cnt = _count(m, E.numel())
         nptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), cnt.cumsum(0)])
         # all pairs (i < j) of every eliminated unknown's neighbours
         pos = torch.arange(v.numel(), device=dev, dtype=i64) - nptr[m]
@@ -138,16 +144,26 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         pkey = o[ia] * R + o[ib]                          # neighbours ascending inside a node: o[ia] < o[ib]
         keep = ~inc
         kept = torch.nonzero(keep).flatten()
-        okey = eu[kept] * R + ew[kept]
-        newkey = torch.unique(torch.cat([okey, pkey]))
-        nE_new = int(newkey.numel())
+        okey = eu[kept] * R + ew[kept]                    # ascending (subset of the sorted key list)
+        # merge the surviving edges with the NEW pairs instead of sorting everything again: the pairs are few
+        pk = torch.unique(pkey)
+        if okey.numel() and pk.numel():
+            at = torch.searchsorted(okey, pk).clamp(max=int(okey.numel()) - 1)
+            pnew = pk[okey[at] != pk]
+        else:
+            pnew = pk
+        opos = torch.arange(okey.numel(), device=dev, dtype=i64) + (torch.searchsorted(pnew, okey) if pnew.numel() else 0)
+        ppos = torch.arange(pnew.numel(), device=dev, dtype=i64) + (torch.searchsorted(okey, pnew) if okey.numel() else 0)
+        nE_new = int(okey.numel() + pnew.numel())
+        newkey = torch.empty(nE_new, dtype=i64, device=dev)
+        newkey[opos] = okey
+        newkey[ppos] = pnew
         copy_src = torch.full((nE_new,), -1, dtype=i64, device=dev)
-        if kept.numel():
-            copy_src[torch.searchsorted(newkey, okey)] = kept
+        copy_src[opos] = kept
         pslot = torch.searchsorted(newkey, pkey) if pkey.numel() else pkey
         po = torch.sort(pslot, stable=True)[1]
         cptr = torch.cat([torch.zeros(1, dtype=i64, device=dev),
-                          torch.bincount(pslot, minlength=nE_new).cumsum(0)]) if nE_new else torch.zeros(1, dtype=i64, device=dev)
+                          _count(pslot, nE_new).cumsum(0)]) if nE_new else torch.zeros(1, dtype=i64, device=dev)
         tn, tinv = torch.unique(o, return_inverse=True)
         to = torch.sort(tinv, stable=True)[1]
         r = Round()
@@ -156,16 +172,17 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         r.copy_src, r.cptr = copy_src, cptr
         r.cm, r.ca, r.cb = m[ia][po], slot[ia][po], slot[ib][po]
         r.tn = tn
-        r.tptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.bincount(tinv, minlength=int(tn.numel())).cumsum(0)])
+        r.tptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), _count(tinv, tn.numel()).cumsum(0)])
         r.tm, r.tslot = m[to], slot[to]
         r.gbase = gbase
         gbase += int(v.numel())
-        plan.max_deg = max(plan.max_deg, int(cnt.max()) if cnt.numel() else 0)
+        maxdeg_t = torch.maximum(maxdeg_t, cnt.max()) if cnt.numel() else maxdeg_t
         plan.rounds.append(r)
         alive[E] = False
         n_alive -= int(E.numel())
         eu, ew = newkey // R, newkey % R
     plan.nnzL = gbase
+    plan.max_deg = int(maxdeg_t)
     return plan
 
 
