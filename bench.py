@@ -6,14 +6,14 @@
 A "step" is one pass of the whole hot path over one batch of synthetic networks per GPU:
 Philox stick placement -> cell-list junction finder -> union-find labels -> MNA assembly ->
 the four measure_fullnet solves (Vg=0, back 10, total 10, partial 10; measure_perc.py:166-186)
-by batched Jacobi-PCG -> currents.  Every step draws fresh seeds.  One process per GPU; for
+by the star-mesh direct solver (--solver cluster / flat: batched two-level PCG) -> currents.  Every step draws fresh seeds.  One process per GPU; for
 N>1 launch through torch.distributed.run -- ranks share nothing but a final all-gather of
 the per-network statistics rows (weak scaling).
 
 Prints ONE JSON line (rank 0).  `value` = networks/s timed with CUDA events on the engine's
 stream (max over ranks); `e2e` = the same through the public host API
 (networksim_cntfet_b200.measure_perc.measure_ensemble: pinned host ns/seeds in, pandas rows
-out, wall clock between synchronisations); `roofline` = the PCG solver's algorithmic bytes
+out, wall clock between synchronisations); `roofline` = the solve stage's algorithmic bytes
 over its CUDA-event time against the measured HBM peak; `cpu_baseline` = the numpy/scipy
 oracle port of the reference path on the host cores, on a bounded sample.
 
