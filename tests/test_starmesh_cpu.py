@@ -128,3 +128,20 @@ def test_floating_cluster_is_componentwise_accurate():
     total = rs + (n - 1) + rd
     want = 0.1 * (1 - (rs + np.arange(n)) / total)
     assert np.max(np.abs(x - want) / want) <= 1e-13
+
+
+def test_fill_budget_rejects_dense_graphs():
+    """a dense, mesh-like pattern exceeds the contribution budget: symbolic() returns None and the
+    engine falls back to the iterative solvers (Engine.solve, 'auto')"""
+    n = 60
+    rows, cols = np.nonzero(~np.eye(n, dtype=bool))
+    rowptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=n))]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int64)
+    # complete graph: eliminating one vertex pairs up all the others; far more than 100000 + 0.5 per edge
+    # only for big graphs, so shrink the constant part by scaling the problem: 40 disjoint copies
+    R = 40 * n
+    rowptr_b = np.r_[0, np.cumsum(np.tile(np.diff(rowptr), 40))]
+    cols_b = np.concatenate([cols + k * n for k in range(40)])
+    assert starmesh.symbolic(t(rowptr_b), t(cols_b), R, max_fill=0.5) is None
+    plan = starmesh.symbolic(t(rowptr_b), t(cols_b), R, max_fill=None)
+    assert plan is not None and plan.max_deg == n - 1
