@@ -110,7 +110,7 @@ class ClockSampler(object):
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -129,6 +129,13 @@ class ClockSampler(object):
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        if not self.rows:           # timed region shorter than the polling interval: one sample right after it
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS,
+                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10)
+                self.rows = [l.strip() for l in r.stdout.splitlines() if l.strip()]
+            except Exception:
+                pass
         sm, mx, reasons, power = [], [], set(), []
         for r in self.rows:
             f = [x.strip() for x in r.split(",")]
@@ -362,7 +369,7 @@ def gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=56,
