@@ -145,3 +145,55 @@ def test_fill_budget_rejects_dense_graphs():
     assert starmesh.symbolic(t(rowptr_b), t(cols_b), R, max_fill=0.5) is None
     plan = starmesh.symbolic(t(rowptr_b), t(cols_b), R, max_fill=None)
     assert plan is not None and plan.max_deg == n - 1
+
+
+def test_plan_invariants():
+    """structure of the index lists every numeric kernel relies on (guards refactors of the symbolic phase)"""
+    system = slab_ref.random_network_system(n=18, seed=12, nconf=1)
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int64)
+    plan = starmesh.symbolic(t(rowptr), t(col), R, net_ids=torch.zeros(R, dtype=torch.int64), nnet=1, dense_max=30)
+    assert plan.dense is not None and 0 < plan.dense["nmax"] <= 30
+    A = (mats[0] != 0).astype(np.int64).tolil()
+    A.setdiag(0)
+    adj = {i: set(A.rows[i]) - {i} for i in range(R)}             # current graph, updated round by round
+    seen = np.zeros(R, bool)
+    gbase = 0
+    for r in plan.rounds:
+        E = r.E.numpy()
+        assert np.all(np.diff(E) > 0) and not seen[E].any()
+        seen[E] = True
+        nptr, nbr, eslot = r.nptr.numpy(), r.nbr.numpy(), r.eslot.numpy()
+        assert nptr[0] == 0 and nptr[-1] == len(nbr) and r.gbase == gbase
+        gbase += len(nbr)
+        for m, v in enumerate(E):
+            nb = nbr[nptr[m]:nptr[m + 1]]
+            assert np.all(np.diff(nb) > 0) and set(nb.tolist()) == adj[int(v)]      # ascending, the true neighbourhood
+            assert not (set(nb.tolist()) & set(E.tolist()))                          # independent set
+        assert len(np.unique(eslot)) == len(eslot) and eslot.max(initial=-1) < r.nE_old
+        # new edge list: every surviving edge copied exactly once, every pair contribution lands on an edge
+        cs = r.copy_src.numpy()
+        kept = cs[cs >= 0]
+        assert len(np.unique(kept)) == len(kept) and not (set(kept.tolist()) & set(eslot.tolist()))
+        assert len(kept) + len(eslot) == r.nE_old
+        cptr = r.cptr.numpy()
+        assert cptr[0] == 0 and cptr[-1] == r.cm.numel() and np.all(np.diff(cptr) >= 0) and len(cptr) == r.nE_new + 1
+        assert np.all((cs >= 0) | (np.diff(cptr) > 0))                               # a new edge has at least one contribution
+        inc = set(eslot.tolist())
+        assert set(r.ca.numpy().tolist()) <= inc and set(r.cb.numpy().tolist()) <= inc
+        tn = r.tn.numpy()
+        assert np.all(np.diff(tn) > 0) and set(tn.tolist()) == set(nbr.tolist())
+        assert r.tptr.numpy()[-1] == len(nbr) and sorted(r.tslot.numpy().tolist()) == sorted(eslot.tolist())
+        # update the graph: star-mesh
+        for v in E:
+            nb = adj.pop(int(v))
+            for a in nb:
+                adj[a].discard(int(v))
+                adj[a] |= nb - {a}
+        assert r.nE_new == sum(len(s) for s in adj.values()) // 2
+    d = plan.dense
+    rest = d["dnodes"].numpy()
+    assert not seen[rest].any() and seen.sum() + len(rest) == R
+    assert d["nE"] == sum(len(s) for s in adj.values()) // 2 and len(np.unique(d["epos"].numpy())) == d["nE"]
+    assert plan.nnzL == gbase
