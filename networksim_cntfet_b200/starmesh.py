@@ -145,8 +145,16 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         keep = ~inc
         kept = torch.nonzero(keep).flatten()
         okey = eu[kept] * R + ew[kept]                    # ascending (subset of the sorted key list)
-        # merge the surviving edges with the NEW pairs instead of sorting everything again: the pairs are few
-        pk = torch.unique(pkey)
+        # merge the surviving edges with the NEW pairs instead of sorting everything again: the pairs are few.
+        # One stable sort of the pair keys serves both the list of distinct pairs and the grouping of the
+        # contributions by target edge
+        spk, po = torch.sort(pkey, stable=True)
+        if spk.numel():
+            firstp = torch.ones(spk.numel(), dtype=torch.bool, device=dev)
+            firstp[1:] = spk[1:] != spk[:-1]
+            pk = spk[firstp]
+        else:
+            pk = spk
         if okey.numel() and pk.numel():
             at = torch.searchsorted(okey, pk).clamp(max=int(okey.numel()) - 1)
             pnew = pk[okey[at] != pk]
@@ -160,19 +168,27 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         newkey[ppos] = pnew
         copy_src = torch.full((nE_new,), -1, dtype=i64, device=dev)
         copy_src[opos] = kept
-        pslot = torch.searchsorted(newkey, pkey) if pkey.numel() else pkey
-        po = torch.sort(pslot, stable=True)[1]
+        pslot = torch.searchsorted(newkey, spk) if spk.numel() else spk           # ascending, like spk
         cptr = torch.cat([torch.zeros(1, dtype=i64, device=dev),
                           _count(pslot, nE_new).cumsum(0)]) if nE_new else torch.zeros(1, dtype=i64, device=dev)
-        tn, tinv = torch.unique(o, return_inverse=True)
-        to = torch.sort(tinv, stable=True)[1]
+        # neighbours whose c, b change: one stable sort of the incident list by neighbour
+        so, to = torch.sort(o, stable=True)
+        if so.numel():
+            firstt = torch.ones(so.numel(), dtype=torch.bool, device=dev)
+            firstt[1:] = so[1:] != so[:-1]
+            tstart = torch.nonzero(firstt).flatten()
+            tn = so[tstart]
+            tptr = torch.cat([tstart, torch.full((1,), so.numel(), dtype=i64, device=dev)])
+        else:
+            tn = so
+            tptr = torch.zeros(1, dtype=i64, device=dev)
         r = Round()
         r.E, r.nptr, r.nbr, r.eslot = E, nptr, o, slot
         r.nE_old, r.nE_new = nE, nE_new
         r.copy_src, r.cptr = copy_src, cptr
         r.cm, r.ca, r.cb = m[ia][po], slot[ia][po], slot[ib][po]
         r.tn = tn
-        r.tptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), _count(tinv, tn.numel()).cumsum(0)])
+        r.tptr = tptr
         r.tm, r.tslot = m[to], slot[to]
         r.gbase = gbase
         gbase += int(v.numel())
