@@ -86,7 +86,9 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
     plan.nE0 = int(ukey.numel())
     plan.e0_src = nz[order]
     plan.e0_ptr = torch.cat([torch.zeros(1, dtype=i64, device=dev), torch.bincount(inv, minlength=plan.nE0).cumsum(0)])
+    curkey = ukey
     eu, ew = ukey // R, ukey % R
+    deg = _count(eu, R) + _count(ew, R)                  # maintained incrementally below
     alive = torch.ones(R, dtype=torch.bool, device=dev)
     ids = torch.arange(R, device=dev, dtype=i64) if local_ids is None else local_ids.to(i64)
     h = (ids * 2654435761) % 1048573                     # fixed pseudo-random tie break
@@ -112,14 +114,11 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
                                   nE=int(eu.numel()), nmax=int(cntb.max()), gpool=max(int(doff[-1]), 1), nnet=int(nnet))
                 break
         nE = int(eu.numel())
-        deg = _count(eu, R) + _count(ew, R)
-        cand = alive
         pri = (deg * 1048573 + h) * R + ids
-        both = cand[eu] & cand[ew]
-        loser = torch.where(pri[eu] > pri[ew], eu, ew)[both]
+        loser = torch.where(pri[eu] > pri[ew], eu, ew)     # every edge of the list joins two live unknowns
         blocked = torch.zeros(R, dtype=torch.bool, device=dev)
         blocked[loser] = True
-        sel = cand & ~blocked
+        sel = alive & ~blocked
         E = torch.nonzero(sel).flatten()
         mid = torch.full((R,), -1, dtype=i64, device=dev)
         mid[E] = torch.arange(E.numel(), device=dev, dtype=i64)
@@ -144,7 +143,7 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         pkey = o[ia] * R + o[ib]                          # neighbours ascending inside a node: o[ia] < o[ib]
         keep = ~inc
         kept = torch.nonzero(keep).flatten()
-        okey = eu[kept] * R + ew[kept]                    # ascending (subset of the sorted key list)
+        okey = curkey[kept]                               # ascending (subset of the sorted key list)
         # merge the surviving edges with the NEW pairs instead of sorting everything again: the pairs are few.
         # One stable sort of the pair keys serves both the list of distinct pairs and the grouping of the
         # contributions by target edge
@@ -196,6 +195,13 @@ def symbolic(rowptr, col, R, max_fill=None, local_ids=None, net_ids=None, nnet=1
         plan.rounds.append(r)
         alive[E] = False
         n_alive -= int(E.numel())
+        # degrees: every neighbour loses its edge to the pivot and gains the NEW edges among the neighbours
+        deg.scatter_add_(0, o, torch.full_like(o, -1))
+        if pnew.numel():
+            one = torch.ones_like(pnew)
+            deg.scatter_add_(0, pnew // R, one)
+            deg.scatter_add_(0, pnew % R, one)
+        curkey = newkey
         eu, ew = newkey // R, newkey % R
     plan.nnzL = gbase
     plan.max_deg = int(maxdeg_t)
