@@ -353,6 +353,64 @@ def solve_network(n, stick1, stick2, g, label, refine=0):
                 A=A, rhs=rhs, nodes_u=nodes_u)
 
 
+def solve_network_exact(n, stick1, stick2, g, label, dtype=np.longdouble):
+    """Voltages of the IDEAL network (exact-arithmetic conductances, no assembled matrix): sequential
+    minimum-degree star-mesh elimination in extended precision.  Every quantity is a sum of positive
+    terms, so the result is accurate to a few ulp of `dtype` whatever the conditioning -- unlike
+    `solve_network`, whose answer (refined or not) is the solution of the ASSEMBLED FP64 matrix and
+    inherits the rounding of its diagonal (1e-8 Vds on back-gated 100x100 um networks).  Same physics
+    as cnet.py:104-149 (source = stick 0 at 0.1 V, ground = stick 1).  Returns V[n] (nan outside the
+    percolating component).  Pure Python loops: meant for checks, not for timing."""
+    import heapq
+    stick1 = np.asarray(stick1, dtype=np.int64)
+    stick2 = np.asarray(stick2, dtype=np.int64)
+    g = np.asarray(g)
+    comp = label == label[0]
+    V = np.full(n, np.nan)
+    V[0], V[1] = VDS, 0.0
+    adj = {int(i): {} for i in np.flatnonzero(comp) if i >= 2}
+    c = {i: dtype(0) for i in adj}          # conductance to the fixed potentials
+    b = {i: dtype(0) for i in adj}          # sum of conductance x fixed potential
+    for a, w, ge in zip(stick1.tolist(), stick2.tolist(), g.tolist()):
+        if not comp[a]:
+            continue
+        ge = dtype(ge)
+        if a < 2:                           # stick 0 / 1 is always stick1 of its junctions
+            c[w] += ge
+            b[w] += ge * dtype(VDS if a == 0 else 0.0)
+        else:
+            adj[a][w] = adj[a].get(w, dtype(0)) + ge
+            adj[w][a] = adj[w].get(a, dtype(0)) + ge
+    heap = [(len(nb), i) for i, nb in adj.items()]
+    heapq.heapify(heap)
+    order, done = [], set()
+    while heap:
+        d, v = heapq.heappop(heap)
+        if v in done or d != len(adj[v]):
+            continue                        # stale entry
+        done.add(v)
+        nb = adj[v]
+        dv = c[v] + sum(nb.values(), dtype(0))
+        order.append((v, dict(nb), dv))
+        items = list(nb.items())
+        for u, gu in items:
+            del adj[u][v]
+            f = gu / dv
+            c[u] += f * c[v]
+            b[u] += f * b[v]
+            for w, gw in items:
+                if w != u:
+                    adj[u][w] = adj[u].get(w, dtype(0)) + f * gw
+        for u, _ in items:
+            heapq.heappush(heap, (len(adj[u]), u))
+    x = {}
+    for v, nb, dv in reversed(order):
+        x[v] = (b[v] + sum((gu * x[u] for u, gu in nb.items()), dtype(0))) / dv
+    for v, xv in x.items():
+        V[v] = float(xv)
+    return V
+
+
 # --------------------------------------------------------------------------------------
 # A17: measure_fullnet (measure_perc.py:140-203), numeric columns only
 # --------------------------------------------------------------------------------------

@@ -113,3 +113,36 @@ def test_generator_law():
         assert np.array_equal(t[k][o], g[k])
     s = O.canonical_sort(O.make_sticks_mt19937(300, "exp", 0.135, 5, 1))
     assert s["xc"][0] == 0.01 and s["xc"][1] == 0.99 and np.all(np.diff(s["length"][2:]) <= 0)
+
+
+@pytest.mark.parametrize("name", [n for n in golden_names() if "noperc" not in n and "n3600" not in n and "n6400" not in n])
+def test_exact_star_mesh_oracle_agrees_with_reference_goldens(name):
+    """extended-precision star-mesh elimination of the ideal network (oracle.solve_network_exact) vs the
+    voltages of the unmodified reference: on these small, well-conditioned networks both are right"""
+    g = load_golden(name)
+    for tag, gate, vg in FULLNET_GATES:
+        cond = O.conductance(g["kind2"], O.gate_voltages(g["jx"], g["jy"], gate, vg), int(g["onoffmap"]),
+                             golden_element(g))
+        V = O.solve_network_exact(len(g["xc"]), g["stick1"], g["stick2"], cond, g["label"])
+        Vref = g["V0" if tag == "0" else "V" + tag]
+        ok = ~np.isnan(Vref)
+        assert np.array_equal(np.isnan(V), ~ok)
+        assert np.max(np.abs(V[ok] - Vref[ok])) <= 1e-9 * 0.1, (tag, np.max(np.abs(V[ok] - Vref[ok])))
+
+
+def test_exact_oracle_on_a_floating_cluster():
+    """50 sticks in a chain hanging on the electrodes by 1e-12 contacts: the exact oracle gives the
+    analytic answer, the LU of the assembled matrix does not"""
+    n = 52
+    s1 = np.r_[0, np.arange(2, n - 1), 1]
+    s2 = np.r_[2, np.arange(3, n), n - 1]
+    order = np.lexsort((s2, s1))
+    s1, s2 = s1[order], s2[order]
+    g = np.where(s1 < 2, np.where(s1 == 0, 1e-12, 3e-12), 1.0)
+    label = np.zeros(n, dtype=np.int64)
+    V = O.solve_network_exact(n, s1, s2, g, label)
+    rs, rd = 1 / 1e-12, 1 / 3e-12
+    want = 0.1 * (1 - (rs + np.arange(n - 2)) / (rs + (n - 3) + rd))
+    assert np.max(np.abs(V[2:] - want) / want) <= 1e-15
+    lu = O.solve_network(n, s1, s2, g, label, refine=0)["V"]
+    assert np.max(np.abs(lu[2:] - want) / want) > 1e-9
