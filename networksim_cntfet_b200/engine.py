@@ -590,7 +590,7 @@ class Engine(object):
                 net0 = roff[net_idx]                                                 # first row of the row's network
                 colg = b.col[:NNZ].to(i64) + torch.repeat_interleave(net0, rowptr.diff())
                 plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill, local_ids=rows - net0, net_ids=net_idx,
-                                         nnet=b.B, dense_max=int(self.direct_dense_max))
+                                         nnet=b.B, dense_max=int(min(self.direct_dense_max, 1024)))      # k_sm_dense: <= 1400 rows
                 if plan is None:
                     b._sm_plan = False
                     return None
