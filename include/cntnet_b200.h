@@ -36,7 +36,7 @@ extern "C" {
 #define CNT_ECUDA 2    /* a CUDA runtime call or launch failed           */
 #define CNT_ECAPACITY 3 /* caller-provided buffer / workspace too small   */
 
-#define CNT_ABI_VERSION 1
+#define CNT_ABI_VERSION 2
 
 int cnt_abi_version(void);
 const char *cnt_last_error(void);
@@ -369,46 +369,84 @@ int cnt_slab_update(const cnt_slab_ctx *c, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (5c) direct solve by parallel star-mesh elimination -- replaces solve_mna (cnet.py:147-149) by
- *      sparse Cholesky written on the conductances (every quantity a sum of positive terms).
- *      The symbolic phase (networksim_cntfet_b200/starmesh.py; topology only, shared by all gate
- *      configurations) eliminates an independent set of unknowns per round and describes a round by
- *      the index lists below; the numeric phase is these entry points, for NS configurations at once.
- *      Nothing synchronises the stream; the host struct arrays are read during the call only.
+ *      sparse Cholesky written on the conductances (every quantity a sum of positive terms):
+ *        eliminate v (neighbours u_i, conductances g_i, electrode coupling c_v):
+ *          d_v = c_v + sum g_i;  g(u_i,u_j) += g_i g_j / d_v;  c_ui += g_i c_v / d_v;  b_ui += g_i b_v / d_v
+ *        back-substitution:  x_v = (b_v + sum g_i x_ui) / d_v
+ *      cnt_sm_symbolic (csrc/starmesh_sym.cu; topology only, shared by all gate configurations)
+ *      eliminates per round the independent set of unknowns whose (degree, hash, index) is the
+ *      smallest among their neighbours, for all networks of the batch at once, and writes the PLAN:
+ *      index lists over edge SLOTS that never move (round-0 edges first, fill edges appended in a
+ *      deterministic order).  A network stops as soon as it has <= dense_max unknowns left; what is
+ *      left is finished by one dense elimination per (network, configuration).  cnt_sm_solve is the
+ *      numeric phase for NS gate configurations at once: every sum runs in a fixed order
+ *      (deterministic bits, independent of what else is in the batch).
+ *
+ *      Plan = one caller-owned device buffer of cnt_sm_plan_layout(...) bytes holding the int32
+ *      arrays below (offsets from cnt_sm_plan_layout; all indices global to the batch):
+ *        PIV[nelim] eliminated row by pivot index m (rounds back to back, rows ascending inside a round)
+ *        NPTR[nelim+1], NBR[nlist], ESLOT[nlist]: neighbours of pivot m (ascending) and the edge slots to them
+ *        TGT[nge], CPTR[nge+1], CM/CA/CB[ncontrib]: edge slot receiving the contributions
+ *            g[CA] g[CB] / d[CM], contributions of a target ordered by pivot
+ *        TN[ngn], TPTR[ngn+1], TM/TSLOT[nlist]: row receiving g[TSLOT] {c,b}[PIV[TM]] / d[TM], ordered by pivot
+ *        E0PTR[nE0+1], E0SRC: round-0 edge e = sum of the CSR entries E0SRC[E0PTR[e] .. E0PTR[e+1])
+ *        DPTR[B+1], DNODES: rows left to the dense tail per network (ascending); DSLOT/DEPOS[dense_nE]:
+ *            remaining edge slots and their position in the pool of dense matrices; DOFF[B+1] (int64)
+ *        INFO: device copy of cnt_sm_info
  * ------------------------------------------------------------------------------------- */
+#define CNT_SM_MAX_ROUNDS 1024
+enum {
+    CNT_SM_PIV = 0, CNT_SM_NPTR, CNT_SM_NBR, CNT_SM_ESLOT, CNT_SM_TGT, CNT_SM_CPTR, CNT_SM_CM, CNT_SM_CA, CNT_SM_CB,
+    CNT_SM_TN, CNT_SM_TPTR, CNT_SM_TM, CNT_SM_TSLOT, CNT_SM_E0PTR, CNT_SM_E0SRC, CNT_SM_DPTR, CNT_SM_DNODES,
+    CNT_SM_DSLOT, CNT_SM_DOFF, CNT_SM_DEPOS, CNT_SM_INFO, CNT_SM_NARR
+};
+/* error bits of cnt_sm_info.error */
+#define CNT_SM_ERR_SLOTS 1     /* more edge slots than cap_slots */
+#define CNT_SM_ERR_CONTRIB 2   /* more star-mesh contributions than cap_contrib (the fill budget) */
+#define CNT_SM_ERR_ITEMS 4     /* a single round has more (pairs + incident entries) than cap_items */
+#define CNT_SM_ERR_HASH 8      /* edge hash table full */
+#define CNT_SM_ERR_SCAN 16     /* device-wide scan watchdog */
+#define CNT_SM_ERR_ROUNDS 32   /* more than CNT_SM_MAX_ROUNDS - 1 rounds */
 typedef struct cnt_sm_round {
-    int64_t nelim, nE_new, ntarget;   /* eliminated unknowns; edges after the round; updated neighbours */
-    int64_t ebase, gbase;             /* offsets of the round in the dinv / gE pools */
-    const int32_t *E;                 /* [nelim] eliminated rows */
-    const int32_t *nptr;              /* [nelim+1] their neighbour lists: nbr / eslot [nptr[m] .. nptr[m+1]) */
-    const int32_t *nbr;               /* neighbour rows */
-    const int32_t *eslot;             /* edge (slot in the round's edge array) to that neighbour */
-    const int32_t *copy_src;          /* [nE_new] old slot of a surviving edge, -1 = new edge */
-    const int32_t *cptr;              /* [nE_new+1] star-mesh contributions g[ca] g[cb] / d[cm] to the new edge */
-    const int32_t *cm, *ca, *cb;
-    const int32_t *tn;                /* [ntarget] rows whose c, b are updated */
-    const int32_t *tptr;              /* [ntarget+1] contributions g[tslot] c[E[tm]] / d[tm] */
-    const int32_t *tm, *tslot;
+    int32_t nelim, nlist, npairs;       /* pivots, incident entries (sum of degrees), neighbour pairs of this round */
+    int32_t nge, ngn, nnew;             /* edge-target groups, node-target groups, new (fill) edge slots */
+    int32_t ebase, lbase, cbase;        /* running totals before this round: pivots, incident entries, contributions */
+    int32_t gebase, gnbase, sbase;      /* ... edge groups, node groups, edge slots */
+    int32_t nlive, nnodes;              /* live edges / unknowns still in play at the start of the round */
+    int32_t pad[2];
 } cnt_sm_round;
-int cnt_sm_edges0(int NS, int64_t nE, const int32_t *ptr, const int32_t *src, const double *val,
-                  int64_t val_stride, double *g, int64_t g_stride, void *stream);
-/* c = gs + gd (conductances to source and drain); leak != 0 adds the rounding error of the assembled
- * FP64 diagonal (cnt_assemble_values' summation order), i.e. the direct solve then answers the same
- * floating-point matrix as the iterative solvers */
-int cnt_sm_coupling(int NS, int64_t R, const int32_t *rowptr, const double *val, int64_t val_stride,
-                    const double *gs, const double *gd, int leak, double *c, void *stream);
-int cnt_sm_forward(int NS, int nrounds, const cnt_sm_round *rounds, int64_t R, double *g0, double *g1,
-                   int64_t g_stride, double *c, double *b, double *dinv, int64_t pool_e_stride, double *gE,
-                   int64_t pool_g_stride, void *stream);
-/* dense tail: the unknowns left after the sparse rounds (a few hundred per network), one CTA per
- * (network, configuration); doff[nnet+1]: offsets of the n_b x n_b matrices in the pool G [NS, gpool];
- * dptr[nnet+1] / dnodes: the remaining rows of every network (ascending); epos[nE]: position of every
- * remaining edge in the pool; g: edge values after the last round; writes x of the remaining rows */
-int cnt_sm_dense(int NS, int64_t R, int nnet, const int64_t *doff, const int32_t *dptr, const int32_t *dnodes,
-                 int64_t nE, const int64_t *epos, const double *g, int64_t g_stride, double *G, int64_t gpool,
-                 const double *c, const double *b, double *x, int nmax, void *stream);
-int cnt_sm_backward(int NS, int nrounds, const cnt_sm_round *rounds, int64_t R, const double *b,
-                    const double *dinv, int64_t pool_e_stride, const double *gE, int64_t pool_g_stride,
-                    double *x, void *stream);
+typedef struct cnt_sm_info {
+    int32_t done, error, nrounds, max_deg;
+    int32_t R, nE0, nslots, nelim;      /* unknowns, round-0 edges, edge slots, eliminated by the sparse rounds */
+    int32_t nlist, ncontrib, nge, ngn;  /* totals over the rounds (nlist = nnz of the factor) */
+    int32_t dense_nnet, dense_nmax, dense_nnodes, dense_nE;
+    int64_t dense_gpool;                /* sum over the networks of (remaining unknowns)^2 */
+    int64_t reserved;
+    cnt_sm_round rounds[CNT_SM_MAX_ROUNDS];
+} cnt_sm_info;
+/* byte offsets of the CNT_SM_NARR plan arrays into offsets[0..CNT_SM_NARR); returns the buffer size */
+int64_t cnt_sm_plan_layout(int64_t R, int B, int64_t NNZ, int64_t cap_slots, int64_t cap_contrib, int64_t *offsets);
+int64_t cnt_sm_symbolic_workspace_bytes(int64_t R, int B, int64_t NNZ, int64_t cap_slots, int64_t cap_contrib,
+                                        int64_t cap_items);
+/* roff[B+1] (device): first row of every network; rowptr[R+1] / col[NNZ] (device): symmetric off-diagonal
+ * pattern, columns network-local and ascending inside a row (cnt_assemble_pattern_fill).  rounds_hint: number of
+ * rounds launched before the header is read back for the first time (one stream synchronisation per read-back;
+ * rounds beyond the last needed one exit immediately).  Returns CNT_ECAPACITY with h_info->error set when a
+ * capacity was exceeded (the caller retries with larger capacities or takes an iterative solver). */
+int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,
+                    int dense_max, int rounds_hint, int64_t cap_slots, int64_t cap_contrib, int64_t cap_items,
+                    void *plan, int64_t plan_bytes, void *ws, int64_t ws_bytes, cnt_sm_info *h_info, void *stream);
+int64_t cnt_sm_solve_workspace_bytes(int NS, const cnt_sm_info *h_info);
+/* numeric phase.  val [NS, val_stride]: CSR off-diagonal values (-g) of cnt_assemble_values; electrode coupling of
+ * row r = g[src_eid[r]] + g[drn_eid[r]] (either may be < 0 = none; src_eid / drn_eid / g may be NULL) + coupling[q, r]
+ * (optional [NS, R]); leak != 0 adds the rounding error of the assembled FP64 diagonal (cnt_assemble_values'
+ * summation order), i.e. the direct solve then answers the same floating-point matrix as the iterative solvers;
+ * rhs [NS, rhs_stride]; x [NS, R] out.  Nothing synchronises the stream. */
+int cnt_sm_solve(int NS, int B, int64_t R, int64_t NNZ, const cnt_sm_info *h_info, const void *plan,
+                 int64_t cap_slots, int64_t cap_contrib, const int32_t *rowptr, const double *val, int64_t val_stride,
+                 const int32_t *src_eid, const int32_t *drn_eid, const double *g, int64_t g_stride,
+                 const double *coupling, const double *rhs, int64_t rhs_stride, int leak, double *x, void *ws,
+                 int64_t ws_bytes, void *stream);
 
 /* ---------------------------------------------------------------------------------------
  * (6) write-back -- replaces update_voltages / update_currents (cnet.py:132-146).

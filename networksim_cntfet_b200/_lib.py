@@ -61,11 +61,12 @@ PROTOTYPES = {
     "cnt_pcg_cluster_size": (i32, [i64, i64]),
     "cnt_pcg_cluster_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i32, vp, i64, vp]),
-    "cnt_sm_edges0": (i32, [i32, i64, vp, vp, vp, i64, vp, i64, vp]),
-    "cnt_sm_coupling": (i32, [i32, i64, vp, vp, i64, vp, vp, i32, vp, vp]),
-    "cnt_sm_forward": (i32, [i32, i32, vp, i64, vp, vp, i64, vp, vp, vp, i64, vp, i64, vp]),
-    "cnt_sm_dense": (i32, [i32, i64, i32, vp, vp, vp, i64, vp, vp, i64, vp, i64, vp, vp, vp, i32, vp]),
-    "cnt_sm_backward": (i32, [i32, i32, vp, i64, vp, vp, i64, vp, i64, vp, vp]),
+    "cnt_sm_plan_layout": (i64, [i64, i32, i64, i64, i64, C.POINTER(i64)]),
+    "cnt_sm_symbolic_workspace_bytes": (i64, [i64, i32, i64, i64, i64, i64]),
+    "cnt_sm_symbolic": (i32, [i32, vp, i64, i64, vp, vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, vp]),
+    "cnt_sm_solve_workspace_bytes": (i64, [i32, vp]),
+    "cnt_sm_solve": (i32, [i32, i32, i64, i64, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp,
+                           i64, vp]),
     "cnt_slab_block_rows": (i32, []),
     "cnt_slab_init": (i32, [vp, vp]),
     "cnt_slab_direction": (i32, [vp, i32, vp]),

@@ -15,7 +15,7 @@ OBJDIR = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libcntnet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["util.cu", "radix.cu", "sticks.cu", "junctions.cu", "clusters.cu", "prune.cu", "assemble.cu", "aggregates.cu", "pcg.cu", "pcg_cluster.cu", "pcg_slab.cu", "starmesh.cu",
+SOURCES = ["util.cu", "radix.cu", "sticks.cu", "junctions.cu", "clusters.cu", "prune.cu", "assemble.cu", "aggregates.cu", "pcg.cu", "pcg_cluster.cu", "pcg_slab.cu", "starmesh.cu", "starmesh_sym.cu",
            "currents.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE]

@@ -1,0 +1,897 @@
+// Symbolic phase of the star-mesh direct solver (replaces solve_mna, cnet.py:147-149; numeric phase
+// in starmesh.cu).  Topology only: one plan serves every gate configuration of a batch.
+//
+// State: an edge pool whose SLOTS never move (round-0 edges, then fill edges in a deterministic
+// order), an insert-only open-addressing hash (u, w) -> slot, per-unknown degree, a compact list of
+// the live edges and a compact ascending list of the unknowns still in play.  A round is eight
+// launches of fixed-size grids that read their sizes from device memory (no host round trip):
+//
+//   k_mark      live edges: the endpoint with the larger (degree, hash, index) is blocked
+//   k_select    unknowns in play: unblocked -> pivot (an independent set of local minima);
+//               one chained scan numbers the pivots, sizes their incident lists and pair ranges
+//               and compacts the survivors
+//   k_incident  live edges: an edge of a pivot goes to the pivot's incident list, the rest survive
+//   k_pivots    per pivot: neighbours ascending; degrees of the neighbours, unknowns left per network
+//   k_items_a   per neighbour pair (u, w) of a pivot: find-or-insert (u, w) in the hash and link the
+//               pair into the target's list; per incident entry: link into the neighbour's list
+//   k_items_b   the last arrival of every list counts it and names its owner (smallest item)
+//   k_items_scan  chained scan over the owners: group numbers, offsets, new slot numbers
+//   k_items_c   per owner: members ordered by item index (= by pivot), written as the contribution
+//               list of the target edge / the update list of the neighbour; new edges get their slot
+//
+// Everything the numeric phase sums is ordered by pivot index, and pivot order inside a network does
+// not depend on what else is in the batch, so the bits of the solution do not either.  The plan
+// layout itself is deterministic (the only nondeterministic orders -- arrival in the lists, position in
+// the live-edge list -- are internal).  A network freezes once it has <= dense_max unknowns left; the
+// frozen remainders are handed to the dense tail (k_final_*).
+#include "starmesh_plan.cuh"
+
+namespace {
+using cnt::sm::Plan;
+
+constexpr int TB = 256;
+constexpr int IPT = 8;                 // items per thread of the chained scans
+constexpr int TILE = TB * IPT;
+constexpr int SAT = 1 << 29;           // saturation of the pair counter (overflow detection)
+constexpr int GRID = 148 * 6;          // fixed grid of the device-sized kernels
+
+struct __align__(16) HEnt {
+    unsigned long long key;            // (u << 32) | w, u < w global rows; all ones = empty
+    int slot;                          // edge slot, -1 = inserted this round, not numbered yet
+    int head;                          // last arrived pair item of the current round, -1 = none
+};
+constexpr unsigned long long HEMPTY = ~0ull;
+
+struct __align__(16) V4 {
+    int a, b, c, d;
+};
+__device__ __forceinline__ V4 v4(int a, int b, int c, int d) {
+    V4 r;
+    r.a = a; r.b = b; r.c = c; r.d = d;
+    return r;
+}
+__device__ __forceinline__ V4 operator+(V4 x, V4 y) {
+    V4 r;
+    r.a = x.a + y.a;
+    r.b = x.b + y.b;
+    int c = x.c + y.c;
+    r.c = c > SAT ? SAT : c;
+    r.d = x.d + y.d;
+    return r;
+}
+__device__ __forceinline__ V4 shfl_up4(V4 v, int o) {
+    return v4(__shfl_up_sync(~0u, v.a, o), __shfl_up_sync(~0u, v.b, o), __shfl_up_sync(~0u, v.c, o),
+              __shfl_up_sync(~0u, v.d, o));
+}
+__device__ __forceinline__ V4 shfl_down4(V4 v, int o) {
+    return v4(__shfl_down_sync(~0u, v.a, o), __shfl_down_sync(~0u, v.b, o), __shfl_down_sync(~0u, v.c, o),
+              __shfl_down_sync(~0u, v.d, o));
+}
+__device__ __forceinline__ V4 shfl4(V4 v, int l) {
+    return v4(__shfl_sync(~0u, v.a, l), __shfl_sync(~0u, v.b, l), __shfl_sync(~0u, v.c, l), __shfl_sync(~0u, v.d, l));
+}
+__device__ __forceinline__ void st_release(int *p, int v) {
+    asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire(const int *p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ V4 ld_v4(const V4 *p) {
+    int4 t = __ldcg(reinterpret_cast<const int4 *>(p));
+    return v4(t.x, t.y, t.z, t.w);
+}
+
+// everything the kernels need, by value
+struct Sym {
+    int B, R, NNZ, dense_max;
+    int capS, capC, capI;
+    unsigned hcap;
+    const int32_t *roff, *rowptr, *col;
+    Plan p;
+    // workspace
+    int32_t *eu, *ew;                  // [capS] endpoints of every slot (global rows, eu < ew)
+    int32_t *deg, *mid, *blocked, *rnet, *fill, *nhead, *loc;     // [R]
+    int32_t *lm;                       // [capS] pivot index of every incident entry
+    int32_t *live[2];                  // [capS] live edge slots (ping-pong)
+    int32_t *nodes[2];                 // [R] unknowns in play, ascending (ping-pong)
+    int32_t *nalive;                   // [B] unknowns left per network
+    int32_t *nlive;                    // [MAX_ROUNDS + 2] size of the live list at the start of round r
+    HEnt *htab;
+    int32_t *pent, *pnext, *gsz, *ghead, *pm, *pa, *pb, *gidx, *goff, *gnew;     // [capI] per item of a round
+    int32_t *pptr;                     // [R + 1] first pair of every pivot of the round
+    // chained scans
+    int32_t *tickets;                  // one per scan invocation
+    int32_t *sflag;
+    V4 *sagg, *sinc;
+};
+
+__device__ __forceinline__ unsigned long long priority(int deg, int lid) {
+    unsigned h = ((unsigned)lid * 2654435761u) >> 12;                 // 20-bit tie-break hash of the network-local index
+    unsigned long long d = (unsigned long long)(deg < (1 << 18) - 1 ? deg : (1 << 18) - 1);
+    return (d << 46) | ((unsigned long long)h << 26) | (unsigned long long)(unsigned)lid;
+}
+__device__ __forceinline__ unsigned hash_pos(unsigned long long key, unsigned hcap) {
+    unsigned long long z = key * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9ull;
+    z ^= z >> 32;
+    return (unsigned)(((z & 0xFFFFFFFFull) * (unsigned long long)hcap) >> 32);
+}
+// entry of key, inserted when absent (slot stays -1); -1 when the table is full
+__device__ __forceinline__ int hash_find_or_insert(const Sym &s, unsigned long long key) {
+    unsigned h = hash_pos(key, s.hcap);
+    for (unsigned probes = 0; probes < s.hcap; probes++) {
+        unsigned long long old = s.htab[h].key;
+        if (old == key) return (int)h;
+        if (old == HEMPTY) {
+            old = atomicCAS(&s.htab[h].key, HEMPTY, key);
+            if (old == HEMPTY || old == key) return (int)h;
+        }
+        h = h + 1 == s.hcap ? 0u : h + 1;
+    }
+    atomicOr(&s.p.info->error, CNT_SM_ERR_HASH);
+    return -1;
+}
+// position of a new element in a list with an atomic counter, one atomic per warp.  Must be called
+// by all 32 lanes.
+__device__ __forceinline__ int warp_append(int *counter, bool pred) {
+    unsigned m = __ballot_sync(~0u, pred);
+    if (!m) return -1;
+    int lane = threadIdx.x & 31, leader = __ffs(m) - 1, base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(m));
+    base = __shfl_sync(~0u, base, leader);
+    return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// ---------------------------------------------------------------------------------------
+// Device-wide exclusive scan of one V4 per item in ONE launch (chained scan with decoupled
+// look-back): tiles are handed out by an atomic ticket, so the predecessors of a tile are always
+// being processed by running CTAs (no deadlock whatever the grid size); a tile publishes its
+// aggregate, looks back over its predecessors a warp at a time, then publishes its inclusive
+// prefix.  Flags carry the invocation's epoch, so the status buffers are never cleared.
+//   f(i) -> V4 value of item i;  g(i, exclusive prefix, own value);  fin(grand total) once.
+// ---------------------------------------------------------------------------------------
+template <class F, class G, class H>
+__device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int *sflag, V4 *sagg, V4 *sinc, int *err,
+                                             F f, G g, H fin) {
+    __shared__ int s_tile;
+    __shared__ V4 s_prefix, s_total;
+    __shared__ V4 s_warp[TB / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ntiles = (n + TILE - 1) / TILE;
+    const V4 zero = v4(0, 0, 0, 0);
+    if (ntiles == 0) {
+        if (blockIdx.x == 0 && tid == 0) fin(zero);
+        return;
+    }
+    for (;;) {
+        __syncthreads();
+        if (tid == 0) s_tile = atomicAdd(ticket, 1);
+        __syncthreads();
+        const int tile = s_tile;
+        if (tile >= ntiles) break;
+        const int i0 = tile * TILE + tid * IPT;
+        V4 v[IPT];
+        V4 sum = zero;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            v[k] = i0 + k < n ? f(i0 + k) : zero;
+            sum = sum + v[k];
+        }
+        V4 inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            V4 t = shfl_up4(inc, o);
+            if (lane >= o) inc = t + inc;
+        }
+        V4 ex = shfl_up4(inc, 1);
+        if (lane == 0) ex = zero;
+        if (lane == 31) s_warp[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            V4 w = lane < TB / 32 ? s_warp[lane] : zero;
+            V4 wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                V4 t = shfl_up4(wi, o);
+                if (lane >= o) wi = t + wi;
+            }
+            V4 wex = shfl_up4(wi, 1);
+            if (lane == 0) wex = zero;
+            if (lane < TB / 32) s_warp[lane] = wex;
+            const V4 total = shfl4(wi, TB / 32 - 1);
+            V4 prefix = zero;
+            if (tile == 0) {
+                if (lane == 0) {
+                    sinc[0] = total;
+                    st_release(&sflag[0], epoch * 4 + 2);
+                }
+            } else {
+                if (lane == 0) {
+                    sagg[tile] = total;
+                    st_release(&sflag[tile], epoch * 4 + 1);
+                }
+                int look = tile - 1;
+                for (;;) {
+                    const int idx = look - lane;
+                    int state = 2;
+                    V4 val = zero;
+                    if (idx >= 0) {
+                        int fl, spins = 0;
+                        do {
+                            fl = ld_acquire(&sflag[idx]);
+                            if ((fl >> 2) != epoch && (++spins & 1023) == 0 &&
+                                (spins >= (1 << 20) || (*(volatile int *)err & CNT_SM_ERR_SCAN)))
+                                break;
+                        } while ((fl >> 2) != epoch);
+                        if ((fl >> 2) != epoch) {
+                            atomicOr(err, CNT_SM_ERR_SCAN);     // watchdog: never hang the GPU
+                        } else {
+                            state = fl & 3;
+                            val = state == 2 ? ld_v4(&sinc[idx]) : ld_v4(&sagg[idx]);
+                        }
+                    }
+                    const unsigned m = __ballot_sync(~0u, state == 2);
+                    const int first = m ? __ffs(m) - 1 : 32;
+                    if (lane > first) val = zero;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) val = val + shfl_down4(val, o);
+                    prefix = prefix + val;            // meaningful in lane 0
+                    if (m) break;
+                    look -= 32;
+                }
+                if (lane == 0) {
+                    sinc[tile] = prefix + total;
+                    st_release(&sflag[tile], epoch * 4 + 2);
+                }
+            }
+            if (lane == 0) {
+                s_prefix = prefix;
+                s_total = prefix + total;
+            }
+        }
+        __syncthreads();
+        V4 base = s_prefix + s_warp[wid] + ex;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            if (i0 + k < n) g(i0 + k, base, v[k]);
+            base = base + v[k];
+        }
+        if (tile == ntiles - 1 && tid == 0) fin(s_total);
+    }
+}
+
+__device__ __forceinline__ int net_of_row(const Sym &s, int r) { return cnt::find_segment(s.roff, s.B, r); }
+
+// ---------------------------------------------------------------------------------------
+// initialisation: round-0 edge slots (unique stick pairs of the CSR pattern, row-major), their
+// value lists (e0_ptr / e0_src), the hash, degrees, the first live / node lists
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
+    const int gt = blockIdx.x * TB + threadIdx.x, gn = gridDim.x * TB;
+    for (int b = gt; b < s.B; b += gn) s.nalive[b] = s.roff[b + 1] - s.roff[b];
+    auto f = [&](int i) {
+        const int base = s.roff[net_of_row(s, i)];
+        int prev = -1, nu = 0, nk = 0;
+        for (int k = s.rowptr[i]; k < s.rowptr[i + 1]; k++) {
+            const int c = s.col[k] + base;
+            if (c <= i) continue;
+            nk++;
+            if (c != prev) nu++;
+            prev = c;
+        }
+        return v4(nu, nk, 0, 0);
+    };
+    auto g = [&](int i, V4 ex, V4 own) {
+        const int net = net_of_row(s, i);
+        const int base = s.roff[net];
+        s.rnet[i] = net;
+        s.nodes[0][i] = i;
+        int prev = -1, prevu = -1, nd = 0, slot = ex.a - 1, kk = ex.b;
+        for (int k = s.rowptr[i]; k < s.rowptr[i + 1]; k++) {
+            const int c = s.col[k] + base;
+            if (c == i) continue;
+            if (c != prev) nd++;
+            prev = c;
+            if (c < i) continue;
+            if (c != prevu) {
+                slot++;
+                if (slot < s.capS) {
+                    s.eu[slot] = i;
+                    s.ew[slot] = c;
+                    s.live[0][slot] = slot;
+                    s.p.e0_ptr[slot] = kk;
+                    const int e = hash_find_or_insert(s, ((unsigned long long)(unsigned)i << 32) | (unsigned)c);
+                    if (e >= 0) s.htab[e].slot = slot;
+                }
+                prevu = c;
+            }
+            s.p.e0_src[kk++] = k;
+        }
+        s.deg[i] = nd;
+    };
+    auto fin = [&](V4 t) {
+        cnt_sm_info *info = s.p.info;
+        info->R = s.R;
+        info->nE0 = t.a;
+        if (t.a <= s.capS) s.p.e0_ptr[t.a] = t.b;
+        else {
+            atomicOr(&info->error, CNT_SM_ERR_SLOTS);
+            info->done = 1;
+        }
+        s.nlive[0] = t.a <= s.capS ? t.a : 0;
+        cnt_sm_round *r0 = &info->rounds[0];
+        r0->ebase = r0->lbase = r0->cbase = r0->gebase = r0->gnbase = 0;
+        r0->sbase = t.a;
+        r0->nnodes = s.R;
+        r0->nlive = t.a;
+    };
+    chained_scan(s.R, epoch, s.tickets, s.sflag, s.sagg, s.sinc, &s.p.info->error, f, g, fin);
+}
+
+// ---------------------------------------------------------------------------------------
+// round kernels
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TB) k_mark(Sym s, int r) {
+    if (s.p.info->done) return;
+    const int n = s.nlive[r];
+    const int32_t *L = s.live[r & 1];
+    for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
+        const int e = L[i], u = s.eu[e], w = s.ew[e];
+        const int net = s.rnet[u];
+        if (s.nalive[net] <= s.dense_max) continue;      // frozen network: left to the dense tail
+        const int base = s.roff[net];
+        const unsigned long long pu = priority(s.deg[u], u - base), pw = priority(s.deg[w], w - base);
+        s.blocked[pu > pw ? u : w] = r + 1;
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
+    cnt_sm_info *info = s.p.info;
+    if (info->done) return;
+    cnt_sm_round *rd = &info->rounds[r];
+    const int n = rd->nnodes, ebase = rd->ebase, lbase = rd->lbase;
+    const int32_t *N = s.nodes[r & 1];
+    int32_t *Nout = s.nodes[(r + 1) & 1];
+    auto f = [&](int i) {
+        const int v = N[i];
+        if (s.nalive[s.rnet[v]] <= s.dense_max) return v4(0, 0, 0, 0);        // frozen: leaves the list
+        if (s.blocked[v] == r + 1) return v4(0, 0, 0, 1);                       // survivor
+        const int d = s.deg[v];
+        const long long pairs = (long long)d * (d - 1) / 2;
+        return v4(1, d, pairs > SAT ? SAT : (int)pairs, 0);
+    };
+    auto g = [&](int i, V4 ex, V4 own) {
+        const int v = N[i];
+        if (own.a) {
+            const int m = ebase + ex.a;
+            s.p.piv[m] = v;
+            s.mid[v] = m;
+            if ((long long)lbase + ex.b <= s.capS) s.p.nptr[m] = lbase + ex.b;
+            s.pptr[ex.a] = ex.c;
+        } else if (own.d) {
+            Nout[ex.d] = v;
+        }
+    };
+    auto fin = [&](V4 t) {
+        int err = 0;
+        if ((long long)lbase + t.b > s.capS) err |= CNT_SM_ERR_SLOTS;
+        if ((long long)t.c + t.b > s.capI) err |= CNT_SM_ERR_ITEMS;
+        if ((long long)rd->cbase + t.c > s.capC) err |= CNT_SM_ERR_CONTRIB;
+        if (t.a > 0 && r + 1 >= CNT_SM_MAX_ROUNDS) err |= CNT_SM_ERR_ROUNDS;
+        if (err) {
+            atomicOr(&info->error, err);
+            t = v4(0, 0, 0, 0);
+        }
+        rd->nelim = t.a;
+        rd->nlist = t.b;
+        rd->npairs = t.c;
+        rd->nlive = s.nlive[r];
+        if (t.a == 0) {          // nothing left to eliminate (or an error): the rounds are over
+            info->nrounds = r;
+            __threadfence();
+            info->done = 1;
+            return;
+        }
+        s.p.nptr[ebase + t.a] = lbase + t.b;
+        s.pptr[t.a] = t.c;
+        info->rounds[r + 1].nnodes = t.d;
+    };
+    chained_scan(n, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
+}
+
+__global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
+    const cnt_sm_info *info = s.p.info;
+    if (info->done) return;
+    const int n = s.nlive[r], ebase = info->rounds[r].ebase;
+    const int32_t *L = s.live[r & 1];
+    int32_t *Lout = s.live[(r + 1) & 1];
+    const int nceil = (n + 31) & ~31;
+    for (int i = blockIdx.x * TB + threadIdx.x; i < nceil; i += gridDim.x * TB) {
+        bool keep = false;
+        int e = 0;
+        if (i < n) {
+            e = L[i];
+            const int u = s.eu[e], w = s.ew[e];
+            if (s.nalive[s.rnet[u]] > s.dense_max) {
+                const int mu = s.mid[u], mw = s.mid[w];
+                if (mu >= ebase) {
+                    const int k = s.p.nptr[mu] + atomicAdd(&s.fill[mu], 1);
+                    s.p.nbr[k] = w;
+                    s.p.eslot[k] = e;
+                } else if (mw >= ebase) {
+                    const int k = s.p.nptr[mw] + atomicAdd(&s.fill[mw], 1);
+                    s.p.nbr[k] = u;
+                    s.p.eslot[k] = e;
+                } else {
+                    keep = true;
+                }
+            }
+        }
+        const int pos = warp_append(&s.nlive[r + 1], keep);
+        if (keep) Lout[pos] = e;
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
+    cnt_sm_info *info = s.p.info;
+    if (info->done) return;
+    const int nelim = info->rounds[r].nelim, ebase = info->rounds[r].ebase;
+    const int nceil = (nelim + 31) & ~31;
+    for (int ml = blockIdx.x * TB + threadIdx.x; ml < nceil; ml += gridDim.x * TB) {
+        int d = 0, net = -1;
+        if (ml < nelim) {
+            const int m = ebase + ml;
+            const int k0 = s.p.nptr[m], k1 = s.p.nptr[m + 1];
+            d = k1 - k0;
+            for (int a = k0 + 1; a < k1; a++) {          // neighbours ascending (lists are short)
+                const int nb = s.p.nbr[a], es = s.p.eslot[a];
+                int c = a - 1;
+                while (c >= k0 && s.p.nbr[c] > nb) {
+                    s.p.nbr[c + 1] = s.p.nbr[c];
+                    s.p.eslot[c + 1] = s.p.eslot[c];
+                    c--;
+                }
+                s.p.nbr[c + 1] = nb;
+                s.p.eslot[c + 1] = es;
+            }
+            for (int k = k0; k < k1; k++) {
+                s.lm[k] = m;
+                atomicSub(&s.deg[s.p.nbr[k]], 1);
+            }
+            net = s.rnet[s.p.piv[m]];
+        }
+        // unknowns left per network: one atomic per run of equal networks inside the warp
+        const unsigned same = __match_any_sync(~0u, net);
+        if (net >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicSub(&s.nalive[net], __popc(same));
+        int dmax = d;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(~0u, dmax, o));
+        if ((threadIdx.x & 31) == 0 && dmax > 0) atomicMax(&info->max_deg, dmax);
+    }
+}
+
+// item t of a round: t < npairs = neighbour pair of a pivot, otherwise incident entry lbase + (t - npairs)
+__global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
+    const cnt_sm_info *info = s.p.info;
+    if (info->done) return;
+    const cnt_sm_round *rd = &info->rounds[r];
+    const int np = rd->npairs, nl = rd->nlist, nelim = rd->nelim, ebase = rd->ebase, lbase = rd->lbase;
+    for (int t = blockIdx.x * TB + threadIdx.x; t < np + nl; t += gridDim.x * TB) {
+        s.gsz[t] = 0;
+        if (t < np) {
+            int lo = 0, hi = nelim;                       // pptr[lo] <= t < pptr[hi]
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (s.pptr[mid] <= t) lo = mid; else hi = mid;
+            }
+            const int m = ebase + lo, k0 = s.p.nptr[m], d = s.p.nptr[m + 1] - k0;
+            int q = t - s.pptr[lo], i = 0;
+            while (q >= d - 1 - i) {
+                q -= d - 1 - i;
+                i++;
+            }
+            const int j = i + 1 + q;
+            const int u = s.p.nbr[k0 + i], w = s.p.nbr[k0 + j];
+            const int e = hash_find_or_insert(s, ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
+            s.pent[t] = e;
+            s.pm[t] = m;
+            s.pa[t] = s.p.eslot[k0 + i];
+            s.pb[t] = s.p.eslot[k0 + j];
+            s.pnext[t] = e >= 0 ? atomicExch(&s.htab[e].head, t) : -1;
+        } else {
+            const int o = s.p.nbr[lbase + (t - np)];
+            s.pent[t] = o;
+            s.pnext[t] = atomicExch(&s.nhead[o], t);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_items_b(Sym s, int r) {
+    const cnt_sm_info *info = s.p.info;
+    if (info->done || info->error) return;
+    const cnt_sm_round *rd = &info->rounds[r];
+    const int np = rd->npairs, nl = rd->nlist;
+    for (int t = blockIdx.x * TB + threadIdx.x; t < np + nl; t += gridDim.x * TB) {
+        const int e = s.pent[t];
+        const int head = t < np ? s.htab[e].head : s.nhead[e];
+        if (head != t) continue;                          // the last arrival speaks for the whole list
+        int cnt = 0, mn = t;
+        for (int x = t; x >= 0; x = s.pnext[x]) {
+            cnt++;
+            mn = min(mn, x);
+        }
+        const int isnew = t < np && s.htab[e].slot < 0;
+        s.gsz[mn] = cnt | (isnew << 30);
+        s.ghead[mn] = t;
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_items_scan(Sym s, int r, int epoch) {
+    cnt_sm_info *info = s.p.info;
+    if (info->done || info->error) return;
+    cnt_sm_round *rd = &info->rounds[r];
+    const int np = rd->npairs, nl = rd->nlist;
+    auto f = [&](int t) {
+        const int z = s.gsz[t];
+        return z ? v4(1, z & ((1 << 30) - 1), z >> 30, 0) : v4(0, 0, 0, 0);
+    };
+    auto g = [&](int t, V4 ex, V4 own) {
+        if (own.a) {
+            s.gidx[t] = ex.a;
+            s.goff[t] = ex.b;
+            s.gnew[t] = ex.c;
+        }
+        if (t == np) rd->nge = ex.a;                      // owners among the pairs (pairs come first)
+    };
+    auto fin = [&](V4 t) {
+        if (nl == 0) rd->nge = 0;
+        rd->ngn = t.a;                                    // all groups for now; k_items_c subtracts nge
+        rd->nnew = t.c;
+    };
+    chained_scan(np + nl, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
+}
+
+__global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
+    cnt_sm_info *info = s.p.info;
+    if (info->done || info->error) return;
+    cnt_sm_round *rd = &info->rounds[r];
+    const int np = rd->npairs, nl = rd->nlist, nge = rd->nge, ngn = rd->ngn - rd->nge, nnew = rd->nnew;
+    const int lbase = rd->lbase, cbase = rd->cbase, gebase = rd->gebase, gnbase = rd->gnbase, sbase = rd->sbase;
+    const bool over = (long long)sbase + nnew > s.capS;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {            // books of the next round
+        if (over) {
+            atomicOr(&info->error, CNT_SM_ERR_SLOTS);
+        } else {
+            cnt_sm_round *nx = &info->rounds[r + 1];
+            nx->ebase = rd->ebase + rd->nelim;
+            nx->lbase = lbase + nl;
+            nx->cbase = cbase + np;
+            nx->gebase = gebase + nge;
+            nx->gnbase = gnbase + ngn;
+            nx->sbase = sbase + nnew;
+        }
+    }
+    if (over) return;
+    const int n = np + nl, nceil = (n + 31) & ~31;
+    for (int t = blockIdx.x * TB + threadIdx.x; t < nceil; t += gridDim.x * TB) {
+        bool fresh = false;
+        int slot = -1;
+        const int z = t < n ? s.gsz[t] : 0;
+        if (z) {
+            const int cnt = z & ((1 << 30) - 1);
+            if (t < np) {
+                const int e = s.pent[t], off = cbase + s.goff[t], gi = gebase + s.gidx[t];
+                int k = 0;
+                for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {         // members ordered by item = by pivot
+                    int c = k - 1;
+                    while (c >= 0 && s.p.cm[off + c] > x) {
+                        s.p.cm[off + c + 1] = s.p.cm[off + c];
+                        c--;
+                    }
+                    s.p.cm[off + c + 1] = x;
+                    k++;
+                }
+                for (k = 0; k < cnt; k++) {
+                    const int x = s.p.cm[off + k];
+                    s.p.cm[off + k] = s.pm[x];
+                    s.p.ca[off + k] = s.pa[x];
+                    s.p.cb[off + k] = s.pb[x];
+                }
+                slot = s.htab[e].slot;
+                if (slot < 0) {                           // a fill edge: numbered in group order
+                    fresh = true;
+                    slot = sbase + s.gnew[t];
+                    const unsigned long long key = s.htab[e].key;
+                    const int u = (int)(key >> 32), w = (int)(key & 0xFFFFFFFFull);
+                    s.htab[e].slot = slot;
+                    s.eu[slot] = u;
+                    s.ew[slot] = w;
+                    atomicAdd(&s.deg[u], 1);
+                    atomicAdd(&s.deg[w], 1);
+                }
+                s.htab[e].head = -1;
+                s.p.tgt[gi] = slot;
+                s.p.cptr[gi] = off;
+            } else {
+                const int o = s.pent[t], off = lbase + (s.goff[t] - np), gi = gnbase + (s.gidx[t] - nge);
+                int k = 0;
+                for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {
+                    int c = k - 1;
+                    while (c >= 0 && s.p.tm[off + c] > x) {
+                        s.p.tm[off + c + 1] = s.p.tm[off + c];
+                        c--;
+                    }
+                    s.p.tm[off + c + 1] = x;
+                    k++;
+                }
+                for (k = 0; k < cnt; k++) {
+                    const int kk = lbase + (s.p.tm[off + k] - np);
+                    s.p.tm[off + k] = s.lm[kk];
+                    s.p.tslot[off + k] = s.p.eslot[kk];
+                }
+                s.nhead[o] = -1;
+                s.p.tn[gi] = o;
+                s.p.tptr[gi] = off;
+            }
+        }
+        const int pos = warp_append(&s.nlive[r + 1], fresh);
+        if (fresh) s.live[(r + 1) & 1][pos] = slot;
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// after the last round: totals, sentinels, and the dense tail (rows and edges left per network)
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_final_a(Sym s) {
+    cnt_sm_info *info = s.p.info;
+    if (!info->done || info->error) return;
+    __shared__ long long s_n[1024], s_q[1024];
+    __shared__ int s_max[1024];
+    const int t = threadIdx.x;
+    const int per = (s.B + 1023) / 1024;
+    const int lo = min(t * per, s.B), hi = min(lo + per, s.B);
+    long long sn = 0, sq = 0;
+    int mx = 0;
+    for (int b = lo; b < hi; b++) {
+        const int n = s.nalive[b];
+        sn += n;
+        sq += (long long)n * n;
+        mx = max(mx, n);
+    }
+    s_n[t] = sn;
+    s_q[t] = sq;
+    s_max[t] = mx;
+    __syncthreads();
+    if (t == 0) {
+        long long an = 0, aq = 0;
+        int m = 0;
+        for (int k = 0; k < 1024; k++) {
+            const long long cn = s_n[k], cq = s_q[k];
+            s_n[k] = an;
+            s_q[k] = aq;
+            an += cn;
+            aq += cq;
+            m = max(m, s_max[k]);
+        }
+        const cnt_sm_round *rd = &info->rounds[info->nrounds];
+        info->nelim = rd->ebase;
+        info->nlist = rd->lbase;
+        info->ncontrib = rd->cbase;
+        info->nge = rd->gebase;
+        info->ngn = rd->gnbase;
+        info->nslots = rd->sbase;
+        s.p.cptr[rd->gebase] = rd->cbase;
+        s.p.tptr[rd->gnbase] = rd->lbase;
+        info->dense_nnet = s.B;
+        info->dense_nmax = m;
+        info->dense_nnodes = (int)an;
+        info->dense_gpool = aq;
+        s.p.dptr[s.B] = (int)an;
+        s.p.doff[s.B] = aq;
+    }
+    __syncthreads();
+    sn = s_n[t];
+    sq = s_q[t];
+    for (int b = lo; b < hi; b++) {
+        const int n = s.nalive[b];
+        s.p.dptr[b] = (int)sn;
+        s.p.doff[b] = sq;
+        sn += n;
+        sq += (long long)n * n;
+    }
+}
+
+__global__ void __launch_bounds__(TB) k_final_nodes(Sym s, int epoch) {
+    cnt_sm_info *info = s.p.info;
+    if (!info->done || info->error) return;
+    auto f = [&](int v) { return v4(s.mid[v] < 0 ? 1 : 0, 0, 0, 0); };
+    auto g = [&](int v, V4 ex, V4 own) {
+        if (own.a) {
+            s.p.dnodes[ex.a] = v;
+            s.loc[v] = ex.a - s.p.dptr[s.rnet[v]];
+        }
+    };
+    auto fin = [&](V4) {};
+    chained_scan(s.R, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
+}
+
+__global__ void __launch_bounds__(TB) k_final_edges(Sym s) {
+    cnt_sm_info *info = s.p.info;
+    if (!info->done || info->error) return;
+    const int n = info->nslots, nceil = (n + 31) & ~31;
+    for (int e = blockIdx.x * TB + threadIdx.x; e < nceil; e += gridDim.x * TB) {
+        bool keep = false;
+        int u = 0, w = 0;
+        if (e < n) {
+            u = s.eu[e];
+            w = s.ew[e];
+            keep = s.mid[u] < 0 && s.mid[w] < 0;
+        }
+        const int pos = warp_append(&info->dense_nE, keep);
+        if (keep) {
+            const int net = s.rnet[u];
+            const long long nn = s.p.dptr[net + 1] - s.p.dptr[net];
+            s.p.dslot[pos] = e;
+            s.p.depos[pos] = s.p.doff[net] + (long long)s.loc[u] * nn + s.loc[w];
+        }
+    }
+}
+
+struct WsLayout {
+    int64_t eu, ew, lm, live0, live1, deg, rnet, loc, nodes0, nodes1, nalive, pptr, items, sagg, sinc, htab;
+    int64_t ones0, ones1;      // [mid, nhead]: memset 0xFF
+    int64_t zero0, zero1;      // [blocked, fill, nlive, tickets, sflag]: memset 0
+    int64_t mid, nhead, blocked, fill, nlive, tickets, sflag;
+    int64_t total;
+    unsigned hcap;
+    int64_t ntiles;
+};
+
+WsLayout ws_layout(int64_t R, int B, int64_t capS, int64_t capI) {
+    WsLayout L;
+    int64_t pos = 0;
+    auto take = [&](int64_t count, int64_t elem) {
+        int64_t at = pos;
+        pos += cnt::align_up((count > 0 ? count : 1) * elem, 256);
+        return at;
+    };
+    int64_t nmax = R > capS ? R : capS;
+    if (capI > nmax) nmax = capI;
+    L.ntiles = nmax / TILE + 2;
+    L.eu = take(capS, 4);
+    L.ew = take(capS, 4);
+    L.lm = take(capS, 4);
+    L.live0 = take(capS, 4);
+    L.live1 = take(capS, 4);
+    L.deg = take(R, 4);
+    L.rnet = take(R, 4);
+    L.loc = take(R, 4);
+    L.nodes0 = take(R, 4);
+    L.nodes1 = take(R, 4);
+    L.nalive = take(B, 4);
+    L.pptr = take(R + 1, 4);
+    L.items = take(10 * capI, 4);
+    L.sagg = take(L.ntiles, 16);
+    L.sinc = take(L.ntiles, 16);
+    L.ones0 = pos;
+    L.mid = take(R, 4);
+    L.nhead = take(R, 4);
+    L.ones1 = pos;
+    L.zero0 = pos;
+    L.blocked = take(R, 4);
+    L.fill = take(R, 4);
+    L.nlive = take(CNT_SM_MAX_ROUNDS + 2, 4);
+    L.tickets = take(2 * CNT_SM_MAX_ROUNDS + 8, 4);
+    L.sflag = take(L.ntiles, 4);
+    L.zero1 = pos;
+    int64_t hc = 2 * capS + 64;
+    L.hcap = (unsigned)hc;
+    L.htab = take(hc, (int64_t)sizeof(HEnt));
+    L.total = pos;
+    return L;
+}
+}  // namespace
+
+extern "C" int64_t cnt_sm_plan_layout(int64_t R, int B, int64_t NNZ, int64_t cap_slots, int64_t cap_contrib,
+                                      int64_t *offsets) {
+    int64_t off[CNT_SM_NARR + 1];
+    int64_t total = cnt::sm::plan_layout(R, B, NNZ, cap_slots, cap_contrib, off);
+    if (offsets)
+        for (int k = 0; k <= CNT_SM_NARR; k++) offsets[k] = off[k];
+    return total;
+}
+
+extern "C" int64_t cnt_sm_symbolic_workspace_bytes(int64_t R, int B, int64_t NNZ, int64_t cap_slots, int64_t cap_contrib,
+                                                   int64_t cap_items) {
+    (void)NNZ;
+    (void)cap_contrib;
+    return ws_layout(R, B, cap_slots, cap_items).total;
+}
+
+extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NNZ, const int32_t *rowptr,
+                               const int32_t *col, int dense_max, int rounds_hint, int64_t cap_slots,
+                               int64_t cap_contrib, int64_t cap_items, void *plan, int64_t plan_bytes, void *ws,
+                               int64_t ws_bytes, cnt_sm_info *h_info, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(B > 0 && roff && R > 0 && R < (1 << 26) && NNZ >= 0 && rowptr && (col || NNZ == 0) && plan && ws && h_info);
+    CNT_CHECK_ARG(dense_max >= 0 && cap_slots >= NNZ / 2 + 1 && cap_slots < (1 << 29) && cap_contrib > 0 &&
+                  cap_contrib < (1 << 29) && cap_items > 0 && cap_items < (1 << 29) && NNZ < (1ll << 31));
+    int64_t off[CNT_SM_NARR + 1];
+    if (cnt::sm::plan_layout(R, B, NNZ, cap_slots, cap_contrib, off) > plan_bytes) {
+        cnt::set_error("star-mesh plan buffer too small");
+        return CNT_ECAPACITY;
+    }
+    const WsLayout L = ws_layout(R, B, cap_slots, cap_items);
+    if (L.total > ws_bytes) {
+        cnt::set_error("star-mesh symbolic workspace too small");
+        return CNT_ECAPACITY;
+    }
+    char *w = (char *)ws;
+    Sym s;
+    s.B = B; s.R = (int)R; s.NNZ = (int)NNZ; s.dense_max = dense_max;
+    s.capS = (int)cap_slots; s.capC = (int)cap_contrib; s.capI = (int)cap_items;
+    s.hcap = L.hcap;
+    s.roff = roff; s.rowptr = rowptr; s.col = col;
+    s.p = cnt::sm::plan_view(plan, off);
+    s.eu = (int32_t *)(w + L.eu); s.ew = (int32_t *)(w + L.ew); s.lm = (int32_t *)(w + L.lm);
+    s.live[0] = (int32_t *)(w + L.live0); s.live[1] = (int32_t *)(w + L.live1);
+    s.deg = (int32_t *)(w + L.deg); s.rnet = (int32_t *)(w + L.rnet); s.loc = (int32_t *)(w + L.loc);
+    s.nodes[0] = (int32_t *)(w + L.nodes0); s.nodes[1] = (int32_t *)(w + L.nodes1);
+    s.nalive = (int32_t *)(w + L.nalive); s.pptr = (int32_t *)(w + L.pptr);
+    int32_t *items = (int32_t *)(w + L.items);
+    s.pent = items; s.pnext = items + cap_items; s.gsz = items + 2 * cap_items; s.ghead = items + 3 * cap_items;
+    s.pm = items + 4 * cap_items; s.pa = items + 5 * cap_items; s.pb = items + 6 * cap_items;
+    s.gidx = items + 7 * cap_items; s.goff = items + 8 * cap_items; s.gnew = items + 9 * cap_items;
+    s.sagg = (V4 *)(w + L.sagg); s.sinc = (V4 *)(w + L.sinc);
+    s.mid = (int32_t *)(w + L.mid); s.nhead = (int32_t *)(w + L.nhead);
+    s.blocked = (int32_t *)(w + L.blocked); s.fill = (int32_t *)(w + L.fill); s.nlive = (int32_t *)(w + L.nlive);
+    s.tickets = (int32_t *)(w + L.tickets); s.sflag = (int32_t *)(w + L.sflag);
+    s.htab = (HEnt *)(w + L.htab);
+
+    CNT_CUDA(cudaMemsetAsync(w + L.ones0, 0xFF, L.ones1 - L.ones0, st));
+    CNT_CUDA(cudaMemsetAsync(w + L.zero0, 0, L.zero1 - L.zero0, st));
+    CNT_CUDA(cudaMemsetAsync(s.htab, 0xFF, (size_t)L.hcap * sizeof(HEnt), st));
+    CNT_CUDA(cudaMemsetAsync(s.p.info, 0, sizeof(cnt_sm_info), st));
+
+    // epochs: 1 = init, 2 + 2r = k_select of round r, 3 + 2r = k_items_scan of round r, then the final scan;
+    // ticket counter [epoch] belongs to that invocation
+    k_init<<<GRID, TB, 0, st>>>(s, 1);
+    CNT_LAUNCHED();
+    int r = 0;
+    int chunk = rounds_hint > 0 ? rounds_hint : 40;
+    for (;;) {
+        const int rend = r + chunk < CNT_SM_MAX_ROUNDS - 1 ? r + chunk : CNT_SM_MAX_ROUNDS - 1;
+        for (; r < rend; r++) {
+            k_mark<<<GRID, TB, 0, st>>>(s, r);
+            k_select<<<GRID, TB, 0, st>>>(s, r, 2 + 2 * r);
+            k_incident<<<GRID, TB, 0, st>>>(s, r);
+            k_pivots<<<GRID, TB, 0, st>>>(s, r);
+            k_items_a<<<GRID, TB, 0, st>>>(s, r);
+            k_items_b<<<GRID, TB, 0, st>>>(s, r);
+            k_items_scan<<<GRID, TB, 0, st>>>(s, r, 3 + 2 * r);
+            k_items_c<<<GRID, TB, 0, st>>>(s, r);
+            cnt::count_launch(8);
+        }
+        CNT_CUDA(cudaGetLastError());
+        // the finals run only once the rounds are over (they check the flag themselves)
+        k_final_a<<<1, 1024, 0, st>>>(s);
+        k_final_nodes<<<GRID, TB, 0, st>>>(s, 2 * CNT_SM_MAX_ROUNDS + 4);
+        k_final_edges<<<GRID, TB, 0, st>>>(s);
+        cnt::count_launch(3);
+        CNT_CUDA(cudaGetLastError());
+        CNT_CUDA(cudaMemcpyAsync(h_info, s.p.info, sizeof(cnt_sm_info), cudaMemcpyDeviceToHost, st));
+        CNT_CUDA(cudaStreamSynchronize(st));
+        if (h_info->done || r >= CNT_SM_MAX_ROUNDS - 1) break;
+        // not finished: the final scan did not run (no ticket taken, no flag written), go on
+        chunk = 16;
+    }
+    if (h_info->error || !h_info->done) {
+        cnt::set_error("star-mesh symbolic phase: capacity exceeded (error bits %d, rounds %d)", h_info->error,
+                       h_info->nrounds);
+        if (!h_info->error) h_info->error = CNT_SM_ERR_ROUNDS;
+        return CNT_ECAPACITY;
+    }
+    return CNT_OK;
+}

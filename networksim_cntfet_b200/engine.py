@@ -141,6 +141,7 @@ class Engine(object):
                                        # iterative solvers and the reference); False = the exact-arithmetic system
         self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
                                        # needs prune)
+        self._direct_rounds_hint = 40  # rounds launched before the symbolic phase reads its header back
 
     def twin(self):
         """A second Engine on the same GPU (own stream and events, same settings).  Two engines
@@ -582,31 +583,20 @@ class Engine(object):
             plan = None
         if plan is None:
             with self._work("direct_symbolic"):
-                i64 = torch.int64
-                rowptr = b.rowptr[:R + 1].to(i64)
-                roff = torch.as_tensor(b.h_roff, device=self.device, dtype=i64)
-                rows = torch.arange(R, device=self.device, dtype=i64)
-                net_idx = torch.bucketize(rows, roff[1:], right=True)
-                net0 = roff[net_idx]                                                 # first row of the row's network
-                colg = b.col[:NNZ].to(i64) + torch.repeat_interleave(net0, rowptr.diff())
-                plan = starmesh.symbolic(rowptr, colg, R, max_fill=max_fill, local_ids=rows - net0, net_ids=net_idx,
-                                         nnet=b.B, dense_max=int(min(self.direct_dense_max, 1024)))      # k_sm_dense: <= 1400 rows
+                plan = starmesh.symbolic(self.lib, self.stream_ptr, self.device, b.B, b.roff, R, NNZ, b.rowptr, b.col,
+                                         dense_max=int(min(self.direct_dense_max, 1024)),       # k_sm_dense: <= 1400 rows
+                                         max_fill=max_fill, rounds_hint=self._direct_rounds_hint)
                 if plan is None:
                     b._sm_plan = False
                     return None
-                plan = starmesh.finalize(plan)
                 b._sm_plan = plan
+                self._direct_rounds_hint = min(plan.nrounds + 4, 400)     # first read-back of the next batch
         with self._work("direct_numeric"):
-            g = sysm["g"]
-            se, de = b.src_eid[:R].to(torch.int64), b.drn_eid[:R].to(torch.int64)
-            zero = torch.zeros((), dtype=torch.float64, device=self.device)
-            gs = torch.where(se >= 0, g[:, se.clamp(min=0)], zero).contiguous()
-            gd = torch.where(de >= 0, g[:, de.clamp(min=0)], zero).contiguous()
-            x = starmesh.solve_cuda(plan, self.lib, self.stream_ptr, b.rowptr, sysm["val"], gs, gd, sysm["rhs"],
-                                    leak=self.direct_leak)
+            x = starmesh.solve_cuda(plan, self.lib, self.stream_ptr, b.rowptr, sysm["val"], sysm["rhs"],
+                                    src_eid=b.src_eid, drn_eid=b.drn_eid, g=sysm["g"], leak=self.direct_leak)
         sym, num = starmesh.algorithmic_bytes(plan, sysm["val"].shape[0])
         self.last_direct = dict(rounds=plan.nrounds, nnzL=plan.nnzL, max_deg=plan.max_deg, npairs=plan.npairs,
-                                dense_nmax=plan.dense["nmax"] if plan.dense else 0,
+                                nE0=plan.nE0, nslots=plan.nslots, dense_nmax=plan.dense_nmax,
                                 bytes_symbolic=sym, bytes_numeric=num)
         self.direct_bytes_total = getattr(self, "direct_bytes_total", 0) + sym + num
         return x

@@ -23,7 +23,7 @@ def test_build_and_symbols():
     missing = [s for s in syms if not hasattr(lib, s)]
     assert not missing, missing
     lib.cnt_abi_version.restype = ctypes.c_int
-    assert lib.cnt_abi_version() == 1
+    assert lib.cnt_abi_version() == 2
 
 
 def test_binding_covers_header():
@@ -100,3 +100,35 @@ def test_slab_ctx_struct_matches_header():
     import ctypes
     # 8-byte members only after the two leading int32 pairs: no hidden padding
     assert ctypes.sizeof(slab.SlabCtx) == sum(ctypes.sizeof(f[1]) for f in slab.SlabCtx._fields_)
+
+
+def _struct_fields(name):
+    txt = open(os.path.join(ROOT, "include", "cntnet_b200.h")).read()
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), txt, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    names = []
+    for decl in body.split(";"):
+        decl = decl.strip().replace("const ", "")
+        if decl:
+            names += [re.sub(r"\[.*\]", "", n).strip().lstrip("*").strip() for n in decl.split(" ", 1)[1].split(",")]
+    return names
+
+
+def test_starmesh_structs_match_header():
+    """starmesh.SmRound / SmInfo mirror cnt_sm_round / cnt_sm_info; the plan layout query is host-only"""
+    from networksim_cntfet_b200 import _lib, starmesh
+    assert _struct_fields("cnt_sm_round") == [f[0] for f in starmesh.SmRound._fields_]
+    assert _struct_fields("cnt_sm_info") == [f[0] for f in starmesh.SmInfo._fields_]
+    assert ctypes.sizeof(starmesh.SmRound) == 64
+    assert ctypes.sizeof(starmesh.SmInfo) == 16 * 4 + 16 + 64 * starmesh.MAX_ROUNDS
+    txt = open(os.path.join(ROOT, "include", "cntnet_b200.h")).read()
+    assert int(re.search(r"#define CNT_SM_MAX_ROUNDS (\d+)", txt).group(1)) == starmesh.MAX_ROUNDS
+    enum = re.search(r"enum \{\s*CNT_SM_PIV = 0,(.*?)CNT_SM_NARR", txt, flags=re.S).group(1)
+    names = ["piv"] + [n.strip()[7:].lower().replace("e0ptr", "e0_ptr").replace("e0src", "e0_src") for n in enum.split(",") if n.strip()]
+    assert tuple(names) == starmesh.ARRAYS
+    lib = _lib.load()
+    off = (ctypes.c_int64 * (len(starmesh.ARRAYS) + 1))()
+    total = lib.cnt_sm_plan_layout(1000, 3, 5000, 6000, 20000, off)
+    assert total == off[len(starmesh.ARRAYS)] and list(off) == sorted(off) and off[0] == 0
+    assert off[starmesh.ARRAYS.index("cm") + 1] - off[starmesh.ARRAYS.index("cm")] >= 4 * 20000
+    assert lib.cnt_sm_symbolic_workspace_bytes(1000, 3, 5000, 6000, 20000, 12000) > 16 * 2 * 6000

@@ -34,57 +34,138 @@ def _element(name):
     return elements.FermiDiracTransistor if name == "fermidirac" else elements.LinExpTransistor
 
 
-def test_cuda_numeric_equals_torch_restatement(engine):
-    system = slab_ref.random_network_system(n=30, seed=4, nconf=3)
+def _gpu_plan(engine, roff, rowptr, col, dense_max=0, **kw):
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int32, device=engine.device)
+    with engine._work():
+        d_roff, d_rowptr, d_col = t(roff), t(rowptr), t(col)
+        plan = starmesh.symbolic(engine.lib, engine.stream_ptr, engine.device, len(roff) - 1, d_roff, int(roff[-1]),
+                                 len(col), d_rowptr, d_col, dense_max=dense_max, **kw)
+    engine.sync()
+    return plan, d_rowptr
+
+
+def _assert_same_plan(plan, ref):
+    """the CUDA plan equals the numpy restatement array by array (the layout is deterministic)"""
+    i = plan.info
+    assert i.done == 1 and i.error == 0
+    assert (i.R, i.nE0, i.nslots, i.nrounds) == (ref.R, ref.nE0, ref.nslots, len(ref.rounds))
+    for k, r in enumerate(ref.rounds):
+        got = plan.info.rounds[k]
+        for name, want in r.items():
+            assert getattr(got, name) == want, (k, name, getattr(got, name), want)
+    assert (i.nelim, i.nlist, i.ncontrib, i.nge, i.ngn) == (len(ref.piv), len(ref.nbr), len(ref.cm), len(ref.tgt), len(ref.tn))
+    assert i.max_deg == ref.max_deg
+    for name in ("piv", "nptr", "nbr", "eslot", "tgt", "cptr", "cm", "ca", "cb", "tn", "tptr", "tm", "tslot", "e0_ptr", "e0_src",
+                 "dptr", "dnodes", "doff"):
+        want = getattr(ref, name)
+        got = plan.array(name, len(want)).cpu().numpy()
+        assert np.array_equal(got, want), name
+    assert (i.dense_nmax, i.dense_gpool, i.dense_nnodes, i.dense_nE) == (ref.dense_nmax, ref.dense_gpool, len(ref.dnodes),
+                                                                          len(ref.dslot))
+    # the remaining edges are listed in arrival order: compare as a set of (slot, position) pairs
+    ds = plan.array("dslot", i.dense_nE).cpu().numpy()
+    dp = plan.array("depos", i.dense_nE).cpu().numpy()
+    o1, o2 = np.argsort(ds), np.argsort(ref.dslot)
+    assert np.array_equal(ds[o1], ref.dslot[o2]) and np.array_equal(dp[o1], ref.depos[o2])
+
+
+def _coupling(system):
     rowptr, col, val, diag, rhs, mats = system
     R = diag.shape[1]
     rows = np.repeat(np.arange(R), np.diff(rowptr))
-    c = diag + np.stack([np.bincount(rows, weights=v, minlength=R) for v in val])
-    t = lambda a, dt, dev: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
-    plan_c = starmesh.symbolic(t(rowptr, torch.int64, "cpu"), t(col, torch.int64, "cpu"), R)
-    want = starmesh_ref.solve(plan_c, t(val, torch.float64, "cpu"), t(c, torch.float64, "cpu"), t(rhs, torch.float64, "cpu"))
-    dev = engine.device
+    return diag + np.stack([np.bincount(rows, weights=v, minlength=R) for v in val])
+
+
+@pytest.mark.parametrize("n,seed,dense_max", [(3, 0, 0), (12, 1, 0), (30, 4, 0), (30, 5, 64), (47, 6, 300)])
+def test_cuda_plan_and_numeric_equal_the_restatement(engine, n, seed, dense_max):
+    system = slab_ref.random_network_system(n=n, seed=seed, nconf=3)
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    ref = starmesh_ref.symbolic([0, R], rowptr, col, dense_max=dense_max)
+    want = starmesh_ref.solve(ref, val, _coupling(system), rhs)
+    plan, d_rowptr = _gpu_plan(engine, [0, R], rowptr, col, dense_max=dense_max)
+    _assert_same_plan(plan, ref)
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=engine.device)
     with engine._work():
-        plan = starmesh.finalize(starmesh.symbolic(t(rowptr, torch.int64, dev), t(col, torch.int64, dev), R))
-        gd = t(c, torch.float64, dev)              # all of the coupling through one "electrode"
-        gs = torch.zeros_like(gd)
-        x = starmesh.solve_cuda(plan, engine.lib, engine.stream_ptr, t(rowptr, torch.int32, dev), t(val, torch.float64, dev),
-                                gs, gd, t(rhs, torch.float64, dev), leak=False)
+        x = starmesh.solve_cuda(plan, engine.lib, engine.stream_ptr, d_rowptr, t(val), t(rhs), coupling=t(_coupling(system)),
+                                leak=False)
     engine.sync()
-    assert plan.nrounds == len(plan_c.rounds)      # same plan on both devices
-    assert float((x.cpu() - want).abs().max()) <= 1e-13 * VDS
+    assert float(np.abs(x.cpu().numpy() - want).max()) <= 1e-13 * VDS
+    from scipy.sparse.linalg import spsolve
+    exact = np.stack([spsolve(A.tocsc(), b) for A, b in zip(mats, rhs)])
+    assert float(np.abs(x.cpu().numpy() - exact).max()) <= 1e-12 * VDS
+
+
+def test_cuda_plan_invariants_and_small_capacities(engine):
+    """the plan read back from the device satisfies the invariants of tests/test_starmesh_cpu.py; starting
+    from capacities that are too small the driver grows them and arrives at the same plan"""
+    from test_starmesh_cpu import check_plan_invariants
+    system = slab_ref.random_network_system(n=18, seed=12, nconf=1)
+    rowptr, col, val, diag, rhs, mats = system
+    R = diag.shape[1]
+    ref = starmesh_ref.symbolic([0, R], rowptr, col, dense_max=30)
+    plan, _ = _gpu_plan(engine, [0, R], rowptr, col, dense_max=30, slot_factor=1.0, fill_factor=0.1, slack=8)
+    _assert_same_plan(plan, ref)
+
+    class View(object):
+        pass
+    v = View()
+    i = plan.info
+    v.nE0, v.nslots, v.nnzL, v.dense_nmax = i.nE0, i.nslots, i.nlist, i.dense_nmax
+    v.rounds = [{n: getattr(i.rounds[k], n) for n in ref.rounds[0]} for k in range(i.nrounds)]
+    for name, cnt in (("piv", i.nelim), ("nptr", i.nelim + 1), ("nbr", i.nlist), ("eslot", i.nlist), ("tgt", i.nge),
+                      ("cptr", i.nge + 1), ("cm", i.ncontrib), ("ca", i.ncontrib), ("cb", i.ncontrib), ("tn", i.ngn),
+                      ("tptr", i.ngn + 1), ("tm", i.nlist), ("tslot", i.nlist), ("dnodes", i.dense_nnodes),
+                      ("dslot", i.dense_nE), ("depos", i.dense_nE)):
+        setattr(v, name, plan.array(name, cnt).cpu().numpy().astype(np.int64))
+    check_plan_invariants(v, mats[0], R, dense_max=30)
+
+
+def test_fill_budget_rejects_dense_graphs(engine):
+    """a dense, mesh-like pattern exceeds the contribution budget: symbolic() returns None and the
+    engine falls back to the iterative solvers (Engine.solve, 'auto')"""
+    n = 60
+    rows, cols = np.nonzero(~np.eye(n, dtype=bool))
+    rowptr = np.r_[0, np.cumsum(np.tile(np.bincount(rows, minlength=n), 40))]
+    colb = np.tile(cols, 40)
+    roff = np.arange(41) * n
+    plan, _ = _gpu_plan(engine, roff, rowptr, colb, max_fill=0.5)
+    assert plan is None
+    plan, _ = _gpu_plan(engine, roff, rowptr, colb, max_fill=None)
+    assert plan is not None and plan.max_deg == n - 1 and plan.npairs == 40 * sum(d * (d - 1) // 2 for d in range(n))
 
 
 @pytest.mark.parametrize("dense_max", [40, 1000])
-def test_cuda_dense_tail_equals_torch_restatement(engine, dense_max):
+def test_cuda_dense_tail_equals_restatement(engine, dense_max):
     """batch of two copies of a system; sparse rounds down to dense_max unknowns per network, then k_sm_dense"""
     system = slab_ref.random_network_system(n=16, seed=9, nconf=3)
     rowptr, col, val, diag, rhs, mats = system
     R = diag.shape[1]
-    rows = np.repeat(np.arange(R), np.diff(rowptr))
-    c = diag + np.stack([np.bincount(rows, weights=v, minlength=R) for v in val])
-    rowptr2, col2 = np.r_[rowptr, rowptr[-1] + rowptr[1:]], np.r_[col, col + R]
-    t = lambda a, dt, dev: torch.as_tensor(np.ascontiguousarray(a), dtype=dt, device=dev)
-    out = {}
-    for dev in ("cpu", engine.device):
-        kw = dict(local_ids=t(np.r_[np.arange(R), np.arange(R)], torch.int64, dev),
-                  net_ids=t(np.repeat([0, 1], R), torch.int64, dev), nnet=2, dense_max=dense_max)
-        if dev == "cpu":
-            plan = starmesh.symbolic(t(rowptr2, torch.int64, dev), t(col2, torch.int64, dev), 2 * R, **kw)
-            out[dev] = starmesh_ref.solve(plan, t(np.c_[val, val], torch.float64, dev), t(np.c_[c, c], torch.float64, dev),
-                                          t(np.c_[rhs, rhs], torch.float64, dev))
-        else:
-            with engine._work():
-                plan = starmesh.finalize(starmesh.symbolic(t(rowptr2, torch.int64, dev), t(col2, torch.int64, dev), 2 * R, **kw))
-                gd = t(np.c_[c, c], torch.float64, dev)
-                out["gpu"] = starmesh.solve_cuda(plan, engine.lib, engine.stream_ptr, t(rowptr2, torch.int32, dev),
-                                                 t(np.c_[val, val], torch.float64, dev), torch.zeros_like(gd), gd,
-                                                 t(np.c_[rhs, rhs], torch.float64, dev), leak=False)
-            engine.sync()
-            assert plan.dense is not None and plan.dense["nmax"] <= dense_max
-    x = out["gpu"].cpu()
-    assert float((x - out["cpu"]).abs().max()) <= 1e-13 * VDS
+    c = _coupling(system)
+    rowptr2, col2 = np.r_[rowptr, rowptr[-1] + rowptr[1:]], np.r_[col, col]
+    ref = starmesh_ref.symbolic([0, R, 2 * R], rowptr2, col2, dense_max=dense_max)
+    want = starmesh_ref.solve(ref, np.c_[val, val], np.c_[c, c], np.c_[rhs, rhs])
+    plan, d_rowptr = _gpu_plan(engine, [0, R, 2 * R], rowptr2, col2, dense_max=dense_max)
+    _assert_same_plan(plan, ref)
+    assert 0 < plan.dense_nmax <= dense_max
+    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.float64, device=engine.device)
+    with engine._work():
+        x = starmesh.solve_cuda(plan, engine.lib, engine.stream_ptr, d_rowptr, t(np.c_[val, val]), t(np.c_[rhs, rhs]),
+                                coupling=t(np.c_[c, c]), leak=False)
+    engine.sync()
+    x = x.cpu()
+    assert float(np.abs(x.numpy() - want).max()) <= 1e-13 * VDS
     assert torch.equal(x[:, :R], x[:, R:])
+
+
+def test_plan_of_a_real_batch_equals_restatement(direct):
+    """three 20x20 um networks through the engine: the plan of the batch pattern against the restatement"""
+    b = direct.generate([6400, 3000, 5200], 20.0, seed=8)
+    direct.measure_fullnet(b, onoffmap=1)
+    plan = b._sm_plan
+    ref = starmesh_ref.symbolic(b.roff.cpu().numpy(), b.rowptr[:b.R + 1].cpu().numpy(), b.col[:b.NNZ].cpu().numpy(),
+                                dense_max=direct.direct_dense_max)
+    _assert_same_plan(plan, ref)
 
 
 def test_dense_tail_switch_does_not_change_the_answer(direct):

@@ -1,18 +1,17 @@
-"""CPU: symbolic phase of the star-mesh direct solver (networksim_cntfet_b200/starmesh.py) with the
-torch restatement of its numeric phase (tests/starmesh_ref.py) against scipy's direct solve."""
+"""CPU: the numpy restatement of the star-mesh direct solver (tests/starmesh_ref.py -- the checker of
+csrc/starmesh_sym.cu + csrc/starmesh.cu on the GPU, tests/test_gpu_direct.py) against scipy's direct
+solve, and the invariants every plan must satisfy."""
 import os
 import sys
 
 import numpy as np
 import pytest
 import scipy.sparse as sp
-import torch
 from scipy.sparse.linalg import spsolve
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import slab_ref  # noqa: E402
 import starmesh_ref  # noqa: E402
-from networksim_cntfet_b200 import starmesh  # noqa: E402
 
 
 def _coupling(system):
@@ -28,54 +27,59 @@ def test_grid_systems(n, seed):
     system = slab_ref.random_network_system(n=n, seed=seed, nconf=3)
     rowptr, col, val, diag, rhs, mats = system
     R = diag.shape[1]
-    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
-    plan = starmesh.symbolic(t(rowptr, torch.int64), t(col, torch.int64), R)
+    plan = starmesh_ref.symbolic([0, R], rowptr, col)
     # every unknown is eliminated exactly once, in independent sets
-    E = torch.cat([r.E for r in plan.rounds])
-    assert np.array_equal(np.sort(E.numpy()), np.arange(R))
+    assert np.array_equal(np.sort(plan.piv), np.arange(R))
     A0 = (mats[0] != 0).astype(int)
     for r in plan.rounds[:3]:
-        sub = A0[r.E.numpy()][:, r.E.numpy()]
+        E = plan.piv[r["ebase"]:r["ebase"] + r["nelim"]]
+        sub = A0[E][:, E]
         assert (sub - sp.diags(sub.diagonal())).nnz == 0
-    x = starmesh_ref.solve(plan, t(val, torch.float64), t(_coupling(system), torch.float64), t(rhs, torch.float64)).numpy()
+    x = starmesh_ref.solve(plan, val, _coupling(system), rhs)
     want = np.stack([spsolve(A.tocsc(), b) for A, b in zip(mats, rhs)])
     assert np.max(np.abs(x - want)) <= 1e-12 * 0.1
 
 
 @pytest.mark.parametrize("dense_max", [4, 40, 1000])
 def test_dense_tail(dense_max):
-    """the rounds stop when no network has more than dense_max unknowns left; the rest is one dense
+    """a network stops as soon as it has no more than dense_max unknowns left; the rest is one dense
     star-mesh elimination per network (dense_max = 1000: no sparse round at all)"""
     system = slab_ref.random_network_system(n=14, seed=6, nconf=2)
     rowptr, col, val, diag, rhs, mats = system
     R = diag.shape[1]
     # two copies of the system as a batch of two networks
     rowptr2 = np.r_[rowptr, rowptr[-1] + rowptr[1:]]
-    col2 = np.r_[col, col + R]
-    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
-    net_ids = t(np.repeat([0, 1], R), torch.int64)
-    local = t(np.r_[np.arange(R), np.arange(R)], torch.int64)
-    plan = starmesh.symbolic(t(rowptr2, torch.int64), t(col2, torch.int64), 2 * R, local_ids=local, net_ids=net_ids, nnet=2,
-                             dense_max=dense_max)
-    assert plan.dense is not None and plan.dense["nmax"] <= dense_max
+    col2 = np.r_[col, col]
+    plan = starmesh_ref.symbolic([0, R, 2 * R], rowptr2, col2, dense_max=dense_max)
+    assert 0 < plan.dense_nmax <= dense_max
     if dense_max >= R:
         assert len(plan.rounds) == 0
     c = _coupling(system)
-    x = starmesh_ref.solve(plan, t(np.c_[val, val], torch.float64), t(np.c_[c, c], torch.float64),
-                           t(np.c_[rhs, rhs], torch.float64)).numpy()
+    x = starmesh_ref.solve(plan, np.c_[val, val], np.c_[c, c], np.c_[rhs, rhs])
     want = np.stack([spsolve(A.tocsc(), b) for A, b in zip(mats, rhs)])
     assert np.max(np.abs(x[:, :R] - want)) <= 1e-12 * 0.1
     assert np.array_equal(x[:, :R], x[:, R:])                 # same network, same bits, wherever it sits in the batch
-    plan = starmesh.finalize(plan, keep64=True)
-    assert plan.dense["dptr32"].dtype == torch.int32
+
+
+def test_batch_composition_does_not_change_a_networks_plan():
+    """pivot order, neighbour lists and contribution order of a network are the same alone and inside a batch"""
+    a = slab_ref.random_network_system(n=9, seed=3, nconf=1)
+    b = slab_ref.random_network_system(n=13, seed=4, nconf=1)
+    Ra, Rb = a[3].shape[1], b[3].shape[1]
+    alone = starmesh_ref.symbolic([0, Rb], b[0], b[1], dense_max=20)
+    both = starmesh_ref.symbolic([0, Ra, Ra + Rb], np.r_[a[0], a[0][-1] + b[0][1:]], np.r_[a[1], b[1]], dense_max=20)
+    seq = lambda p, lo, hi: [(int(v) - lo, tuple(p.nbr[p.nptr[m]:p.nptr[m + 1]] - lo)) for m, v in enumerate(p.piv)
+                             if lo <= v < hi]
+    assert seq(alone, 0, Rb) == seq(both, Ra, Ra + Rb)
+    assert np.array_equal(alone.dnodes, both.dnodes[both.dnodes >= Ra] - Ra)
 
 
 def test_batch_of_networks_and_parallel_entries():
-    """two disconnected networks in one pattern (global indices) and duplicate entries of a pair
-    (a virtual series junction next to a real one) are summed"""
+    """two disconnected networks in one pattern and duplicate entries of a pair (a virtual series
+    junction next to a real one) are summed"""
     rng = np.random.default_rng(5)
-    blocks, R = [], 0
-    rows, cols, vals = [], [], []
+    R = 0
+    rows, cols, lcols, vals, roff = [], [], [], [], [0]
     for nn in (17, 9):
         # ring + chords, some pairs twice
         e = [(i, (i + 1) % nn) for i in range(nn)] + [(0, nn // 2), (1, nn // 2), (0, nn // 2)]
@@ -83,10 +87,12 @@ def test_batch_of_networks_and_parallel_entries():
             g = float(np.exp(-5 * rng.random()))
             rows += [R + a, R + c]
             cols += [R + c, R + a]
+            lcols += [c, a]
             vals += [-g, -g]
         R += nn
+        roff.append(R)
     order = np.lexsort((cols, rows))
-    rows, cols, vals = np.array(rows)[order], np.array(cols)[order], np.array(vals)[order]
+    rows, cols, lcols, vals = (np.array(v)[order] for v in (rows, cols, lcols, vals))
     rowptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=R))]
     c = np.zeros(R)
     b = np.zeros(R)
@@ -95,12 +101,10 @@ def test_batch_of_networks_and_parallel_entries():
     c[[8, 25]] = 0.2
     A = sp.coo_matrix((vals, (rows, cols)), shape=(R, R)).tocsr()
     A = A + sp.diags(c - np.asarray(A.sum(1)).ravel())
-    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
-    plan = starmesh.symbolic(t(rowptr, torch.int64), t(cols, torch.int64), R)
-    x = starmesh_ref.solve(plan, t(vals[None], torch.float64), t(c[None], torch.float64), t(b[None], torch.float64)).numpy()[0]
+    plan = starmesh_ref.symbolic(roff, rowptr, lcols)
+    assert plan.nE0 == 17 + 2 + 9 + 2 and len(plan.e0_src) == len(vals) // 2
+    x = starmesh_ref.solve(plan, vals[None], c[None], b[None])[0]
     assert np.max(np.abs(x - spsolve(A.tocsc(), b))) <= 1e-13
-    plan = starmesh.finalize(plan, keep64=True)
-    assert plan.pool.dtype == torch.int32 and plan.nrounds == len(plan.rounds) and plan.nE_max >= plan.nE0
 
 
 def test_floating_cluster_is_componentwise_accurate():
@@ -120,9 +124,8 @@ def test_floating_cluster_is_componentwise_accurate():
     b = np.zeros(n)
     c[0], b[0] = 1e-12, 0.1 * 1e-12          # source contact
     c[n - 1] = 3e-12                           # drain contact
-    t = lambda a, dt: torch.as_tensor(np.ascontiguousarray(a), dtype=dt)
-    plan = starmesh.symbolic(t(rowptr, torch.int64), t(cols, torch.int64), n)
-    x = starmesh_ref.solve(plan, t(vals[None], torch.float64), t(c[None], torch.float64), t(b[None], torch.float64)).numpy()[0]
+    plan = starmesh_ref.symbolic([0, n], rowptr, cols)
+    x = starmesh_ref.solve(plan, vals[None], c[None], b[None])[0]
     # exact: series of g_s = 1e-12, (n-1) unit conductances, g_d = 3e-12
     rs, rd = 1 / 1e-12, 1 / 3e-12
     total = rs + (n - 1) + rd
@@ -130,21 +133,15 @@ def test_floating_cluster_is_componentwise_accurate():
     assert np.max(np.abs(x - want) / want) <= 1e-13
 
 
-def test_fill_budget_rejects_dense_graphs():
-    """a dense, mesh-like pattern exceeds the contribution budget: symbolic() returns None and the
-    engine falls back to the iterative solvers (Engine.solve, 'auto')"""
-    n = 60
+def test_complete_graphs_fill():
+    """40 complete graphs: eliminating one vertex pairs up all the others -- the contribution count the
+    fill budget of Engine.solve('auto') is compared with"""
+    n = 12
     rows, cols = np.nonzero(~np.eye(n, dtype=bool))
-    rowptr = np.r_[0, np.cumsum(np.bincount(rows, minlength=n))]
-    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int64)
-    # complete graph: eliminating one vertex pairs up all the others; far more than 100000 + 0.5 per edge
-    # only for big graphs, so shrink the constant part by scaling the problem: 40 disjoint copies
-    R = 40 * n
-    rowptr_b = np.r_[0, np.cumsum(np.tile(np.diff(rowptr), 40))]
-    cols_b = np.concatenate([cols + k * n for k in range(40)])
-    assert starmesh.symbolic(t(rowptr_b), t(cols_b), R, max_fill=0.5) is None
-    plan = starmesh.symbolic(t(rowptr_b), t(cols_b), R, max_fill=None)
-    assert plan is not None and plan.max_deg == n - 1
+    rowptr = np.r_[0, np.cumsum(np.tile(np.bincount(rows, minlength=n), 5))]
+    plan = starmesh_ref.symbolic(np.arange(6) * n, rowptr, np.tile(cols, 5))
+    assert plan.max_deg == n - 1
+    assert len(plan.cm) == 5 * sum(d * (d - 1) // 2 for d in range(n))
 
 
 def test_plan_invariants():
@@ -152,48 +149,68 @@ def test_plan_invariants():
     system = slab_ref.random_network_system(n=18, seed=12, nconf=1)
     rowptr, col, val, diag, rhs, mats = system
     R = diag.shape[1]
-    t = lambda a: torch.as_tensor(np.ascontiguousarray(a), dtype=torch.int64)
-    plan = starmesh.symbolic(t(rowptr), t(col), R, net_ids=torch.zeros(R, dtype=torch.int64), nnet=1, dense_max=30)
-    assert plan.dense is not None and 0 < plan.dense["nmax"] <= 30
-    A = (mats[0] != 0).astype(np.int64).tolil()
+    plan = starmesh_ref.symbolic([0, R], rowptr, col, dense_max=30)
+    check_plan_invariants(plan, mats[0], R, dense_max=30)
+
+
+def check_plan_invariants(plan, A, R, dense_max):
+    """shared with the GPU test, which runs it on the plan read back from cnt_sm_symbolic"""
+    assert 0 < plan.dense_nmax <= dense_max
+    A = (A != 0).astype(np.int64).tolil()
     A.setdiag(0)
     adj = {i: set(A.rows[i]) - {i} for i in range(R)}             # current graph, updated round by round
+    slot_pair = {e: (int(plan.eu[e]), int(plan.ew[e])) for e in range(plan.nE0)} if hasattr(plan, "eu") else None
     seen = np.zeros(R, bool)
-    gbase = 0
+    dead_slots = set()
+    nslots = plan.nE0
     for r in plan.rounds:
-        E = r.E.numpy()
+        E = plan.piv[r["ebase"]:r["ebase"] + r["nelim"]]
         assert np.all(np.diff(E) > 0) and not seen[E].any()
         seen[E] = True
-        nptr, nbr, eslot = r.nptr.numpy(), r.nbr.numpy(), r.eslot.numpy()
-        assert nptr[0] == 0 and nptr[-1] == len(nbr) and r.gbase == gbase
-        gbase += len(nbr)
+        nptr = plan.nptr[r["ebase"]:r["ebase"] + r["nelim"] + 1]
+        assert nptr[0] == r["lbase"] and nptr[-1] == r["lbase"] + r["nlist"]
+        lo, hi = nptr[0], nptr[-1]
+        nbr, eslot = plan.nbr[lo:hi], plan.eslot[lo:hi]
         for m, v in enumerate(E):
-            nb = nbr[nptr[m]:nptr[m + 1]]
+            nb = plan.nbr[nptr[m]:nptr[m + 1]]
             assert np.all(np.diff(nb) > 0) and set(nb.tolist()) == adj[int(v)]      # ascending, the true neighbourhood
             assert not (set(nb.tolist()) & set(E.tolist()))                          # independent set
-        assert len(np.unique(eslot)) == len(eslot) and eslot.max(initial=-1) < r.nE_old
-        # new edge list: every surviving edge copied exactly once, every pair contribution lands on an edge
-        cs = r.copy_src.numpy()
-        kept = cs[cs >= 0]
-        assert len(np.unique(kept)) == len(kept) and not (set(kept.tolist()) & set(eslot.tolist()))
-        assert len(kept) + len(eslot) == r.nE_old
-        cptr = r.cptr.numpy()
-        assert cptr[0] == 0 and cptr[-1] == r.cm.numel() and np.all(np.diff(cptr) >= 0) and len(cptr) == r.nE_new + 1
-        assert np.all((cs >= 0) | (np.diff(cptr) > 0))                               # a new edge has at least one contribution
+        assert len(np.unique(eslot)) == len(eslot) and eslot.max(initial=-1) < nslots
+        assert not (set(eslot.tolist()) & dead_slots)
+        # edge targets: distinct live slots; contributions reference this round's dead edges, ordered by pivot
+        gs = slice(r["gebase"], r["gebase"] + r["nge"])
+        tgt = plan.tgt[gs]
+        cptr = plan.cptr[r["gebase"]:r["gebase"] + r["nge"] + 1]
+        assert cptr[0] == r["cbase"] and cptr[-1] == r["cbase"] + r["npairs"] and np.all(np.diff(cptr) > 0)
+        assert len(np.unique(tgt)) == len(tgt) and not (set(tgt.tolist()) & (dead_slots | set(eslot.tolist())))
+        fresh = tgt[tgt >= nslots]
+        assert np.array_equal(fresh, nslots + np.arange(r["nnew"]))                  # fill slots numbered in group order
         inc = set(eslot.tolist())
-        assert set(r.ca.numpy().tolist()) <= inc and set(r.cb.numpy().tolist()) <= inc
-        tn = r.tn.numpy()
-        assert np.all(np.diff(tn) > 0) and set(tn.tolist()) == set(nbr.tolist())
-        assert r.tptr.numpy()[-1] == len(nbr) and sorted(r.tslot.numpy().tolist()) == sorted(eslot.tolist())
+        ks = slice(cptr[0], cptr[-1])
+        assert set(plan.ca[ks].tolist()) <= inc and set(plan.cb[ks].tolist()) <= inc
+        for k in range(r["nge"]):
+            cm = plan.cm[cptr[k]:cptr[k + 1]]
+            assert np.all(np.diff(cm) > 0) and cm.min() >= r["ebase"] and cm.max() < r["ebase"] + r["nelim"]
+        # node targets: every neighbour once, its entries ordered by pivot
+        tn = plan.tn[r["gnbase"]:r["gnbase"] + r["ngn"]]
+        tptr = plan.tptr[r["gnbase"]:r["gnbase"] + r["ngn"] + 1]
+        assert len(np.unique(tn)) == len(tn) and set(tn.tolist()) == set(nbr.tolist())
+        assert tptr[0] == r["lbase"] and tptr[-1] == r["lbase"] + r["nlist"]
+        assert sorted(plan.tslot[lo:hi].tolist()) == sorted(eslot.tolist())
+        for k in range(r["ngn"]):
+            assert np.all(np.diff(plan.tm[tptr[k]:tptr[k + 1]]) > 0)
         # update the graph: star-mesh
         for v in E:
             nb = adj.pop(int(v))
             for a in nb:
                 adj[a].discard(int(v))
                 adj[a] |= nb - {a}
-        assert r.nE_new == sum(len(s) for s in adj.values()) // 2
-    d = plan.dense
-    rest = d["dnodes"].numpy()
+        dead_slots |= inc
+        nslots += r["nnew"]
+        assert nslots - len(dead_slots) == sum(len(s) for s in adj.values()) // 2
+    assert nslots == plan.nslots
+    rest = plan.dnodes
     assert not seen[rest].any() and seen.sum() + len(rest) == R
-    assert d["nE"] == sum(len(s) for s in adj.values()) // 2 and len(np.unique(d["epos"].numpy())) == d["nE"]
-    assert plan.nnzL == gbase
+    assert len(plan.dslot) == sum(len(s) for s in adj.values()) // 2 and len(np.unique(plan.depos)) == len(plan.dslot)
+    assert not (set(plan.dslot.tolist()) & dead_slots)
+    assert plan.nnzL == len(plan.nbr)
