@@ -413,7 +413,7 @@ typedef struct cnt_sm_round {
     int32_t ebase, lbase, cbase;        /* running totals before this round: pivots, incident entries, contributions */
     int32_t gebase, gnbase, sbase;      /* ... edge groups, node groups, edge slots */
     int32_t nlive, nnodes;              /* live edges / unknowns still in play at the start of the round */
-    int32_t pad[2];
+    int32_t ngroups, pad;               /* nge + ngn */
 } cnt_sm_round;
 typedef struct cnt_sm_info {
     int32_t done, error, nrounds, max_deg;

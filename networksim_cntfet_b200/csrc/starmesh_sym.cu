@@ -321,6 +321,7 @@ __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
             info->done = 1;
         }
         s.nlive[0] = t.a <= s.capS ? t.a : 0;
+        s.p.nptr[0] = 0;
         cnt_sm_round *r0 = &info->rounds[0];
         r0->ebase = r0->lbase = r0->cbase = r0->gebase = r0->gnbase = 0;
         r0->sbase = t.a;
@@ -334,7 +335,7 @@ __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
 // round kernels
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(TB) k_mark(Sym s, int r) {
-    if (s.p.info->done) return;
+    if (s.p.info->done | s.p.info->error) return;
     const int n = s.nlive[r];
     const int32_t *L = s.live[r & 1];
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(TB) k_mark(Sym s, int r) {
 
 __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
     cnt_sm_info *info = s.p.info;
-    if (info->done) return;
+    if (info->done | info->error) return;
     cnt_sm_round *rd = &info->rounds[r];
     const int n = rd->nnodes, ebase = rd->ebase, lbase = rd->lbase;
     const int32_t *N = s.nodes[r & 1];
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
 
 __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
     const cnt_sm_info *info = s.p.info;
-    if (info->done) return;
+    if (info->done | info->error) return;
     const int n = s.nlive[r], ebase = info->rounds[r].ebase;
     const int32_t *L = s.live[r & 1];
     int32_t *Lout = s.live[(r + 1) & 1];
@@ -436,7 +437,7 @@ __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
 
 __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
     cnt_sm_info *info = s.p.info;
-    if (info->done) return;
+    if (info->done | info->error) return;
     const int nelim = info->rounds[r].nelim, ebase = info->rounds[r].ebase;
     const int nceil = (nelim + 31) & ~31;
     for (int ml = blockIdx.x * TB + threadIdx.x; ml < nceil; ml += gridDim.x * TB) {
@@ -475,7 +476,7 @@ __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
 // item t of a round: t < npairs = neighbour pair of a pivot, otherwise incident entry lbase + (t - npairs)
 __global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
     const cnt_sm_info *info = s.p.info;
-    if (info->done) return;
+    if (info->done | info->error) return;
     const cnt_sm_round *rd = &info->rounds[r];
     const int np = rd->npairs, nl = rd->nlist, nelim = rd->nelim, ebase = rd->ebase, lbase = rd->lbase;
     for (int t = blockIdx.x * TB + threadIdx.x; t < np + nl; t += gridDim.x * TB) {
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
 
 __global__ void __launch_bounds__(TB) k_items_b(Sym s, int r) {
     const cnt_sm_info *info = s.p.info;
-    if (info->done || info->error) return;
+    if (info->done | info->error) return;
     const cnt_sm_round *rd = &info->rounds[r];
     const int np = rd->npairs, nl = rd->nlist;
     for (int t = blockIdx.x * TB + threadIdx.x; t < np + nl; t += gridDim.x * TB) {
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(TB) k_items_b(Sym s, int r) {
 
 __global__ void __launch_bounds__(TB) k_items_scan(Sym s, int r, int epoch) {
     cnt_sm_info *info = s.p.info;
-    if (info->done || info->error) return;
+    if (info->done | info->error) return;
     cnt_sm_round *rd = &info->rounds[r];
     const int np = rd->npairs, nl = rd->nlist;
     auto f = [&](int t) {
@@ -547,7 +548,7 @@ __global__ void __launch_bounds__(TB) k_items_scan(Sym s, int r, int epoch) {
     };
     auto fin = [&](V4 t) {
         if (nl == 0) rd->nge = 0;
-        rd->ngn = t.a;                                    // all groups for now; k_items_c subtracts nge
+        rd->ngroups = t.a;                                // k_items_c splits it into nge + ngn
         rd->nnew = t.c;
     };
     chained_scan(np + nl, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
@@ -555,12 +556,13 @@ __global__ void __launch_bounds__(TB) k_items_scan(Sym s, int r, int epoch) {
 
 __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
     cnt_sm_info *info = s.p.info;
-    if (info->done || info->error) return;
+    if (info->done | info->error) return;
     cnt_sm_round *rd = &info->rounds[r];
-    const int np = rd->npairs, nl = rd->nlist, nge = rd->nge, ngn = rd->ngn - rd->nge, nnew = rd->nnew;
+    const int np = rd->npairs, nl = rd->nlist, nge = rd->nge, ngn = rd->ngroups - rd->nge, nnew = rd->nnew;
     const int lbase = rd->lbase, cbase = rd->cbase, gebase = rd->gebase, gnbase = rd->gnbase, sbase = rd->sbase;
     const bool over = (long long)sbase + nnew > s.capS;
     if (blockIdx.x == 0 && threadIdx.x == 0) {            // books of the next round
+        rd->ngn = ngn;
         if (over) {
             atomicOr(&info->error, CNT_SM_ERR_SLOTS);
         } else {
@@ -883,7 +885,7 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
         CNT_CUDA(cudaGetLastError());
         CNT_CUDA(cudaMemcpyAsync(h_info, s.p.info, sizeof(cnt_sm_info), cudaMemcpyDeviceToHost, st));
         CNT_CUDA(cudaStreamSynchronize(st));
-        if (h_info->done || r >= CNT_SM_MAX_ROUNDS - 1) break;
+        if (h_info->done || h_info->error || r >= CNT_SM_MAX_ROUNDS - 1) break;
         // not finished: the final scan did not run (no ticket taken, no flag written), go on
         chunk = 16;
     }

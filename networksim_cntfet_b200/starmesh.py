@@ -41,7 +41,7 @@ ARRAYS = ("piv", "nptr", "nbr", "eslot", "tgt", "cptr", "cm", "ca", "cb", "tn", 
 class SmRound(C.Structure):
     """mirror of cnt_sm_round (include/cntnet_b200.h)"""
     _fields_ = [(n, C.c_int32) for n in ("nelim", "nlist", "npairs", "nge", "ngn", "nnew", "ebase", "lbase", "cbase",
-                                         "gebase", "gnbase", "sbase", "nlive", "nnodes")] + [("pad", C.c_int32 * 2)]
+                                         "gebase", "gnbase", "sbase", "nlive", "nnodes", "ngroups", "pad")]
 
 
 class SmInfo(C.Structure):
