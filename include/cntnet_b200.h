@@ -391,14 +391,15 @@ int cnt_slab_update(const cnt_slab_ctx *c, void *stream);
  *        TN[ngn], TPTR[ngn+1], TM/TSLOT[nlist]: row receiving g[TSLOT] {c,b}[PIV[TM]] / d[TM], ordered by pivot
  *        E0PTR[nE0+1], E0SRC: round-0 edge e = sum of the CSR entries E0SRC[E0PTR[e] .. E0PTR[e+1])
  *        DPTR[B+1], DNODES: rows left to the dense tail per network (ascending); DSLOT/DEPOS[dense_nE]:
- *            remaining edge slots and their position in the pool of dense matrices; DOFF[B+1] (int64)
+ *            remaining edge slots and their position in the pool of dense matrices, grouped by network
+ *            (DEDGE[B+1]); DOFF[B+1] (int64): offset of every network's n x n matrix in the pool
  *        INFO: device copy of cnt_sm_info
  * ------------------------------------------------------------------------------------- */
 #define CNT_SM_MAX_ROUNDS 1024
 enum {
     CNT_SM_PIV = 0, CNT_SM_NPTR, CNT_SM_NBR, CNT_SM_ESLOT, CNT_SM_TGT, CNT_SM_CPTR, CNT_SM_CM, CNT_SM_CA, CNT_SM_CB,
     CNT_SM_TN, CNT_SM_TPTR, CNT_SM_TM, CNT_SM_TSLOT, CNT_SM_E0PTR, CNT_SM_E0SRC, CNT_SM_DPTR, CNT_SM_DNODES,
-    CNT_SM_DSLOT, CNT_SM_DOFF, CNT_SM_DEPOS, CNT_SM_INFO, CNT_SM_NARR
+    CNT_SM_DSLOT, CNT_SM_DOFF, CNT_SM_DEPOS, CNT_SM_INFO, CNT_SM_DEDGE, CNT_SM_NARR
 };
 /* error bits of cnt_sm_info.error */
 #define CNT_SM_ERR_SLOTS 1     /* more edge slots than cap_slots */
@@ -431,11 +432,14 @@ int64_t cnt_sm_symbolic_workspace_bytes(int64_t R, int B, int64_t NNZ, int64_t c
 /* roff[B+1] (device): first row of every network; rowptr[R+1] / col[NNZ] (device): symmetric off-diagonal
  * pattern, columns network-local and ascending inside a row (cnt_assemble_pattern_fill).  rounds_hint: number of
  * rounds launched before the header is read back for the first time (one stream synchronisation per read-back;
- * rounds beyond the last needed one exit immediately).  Returns CNT_ECAPACITY with h_info->error set when a
+ * rounds beyond the last needed one exit immediately).  hint (may be NULL): header of an earlier plan of a
+ * similar batch; its per-round sizes size the grids of the round kernels (performance only: every kernel
+ * strides over device-side counts).  Returns CNT_ECAPACITY with h_info->error set when a
  * capacity was exceeded (the caller retries with larger capacities or takes an iterative solver). */
 int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NNZ, const int32_t *rowptr, const int32_t *col,
                     int dense_max, int rounds_hint, int64_t cap_slots, int64_t cap_contrib, int64_t cap_items,
-                    void *plan, int64_t plan_bytes, void *ws, int64_t ws_bytes, cnt_sm_info *h_info, void *stream);
+                    const cnt_sm_info *hint, void *plan, int64_t plan_bytes, void *ws, int64_t ws_bytes,
+                    cnt_sm_info *h_info, void *stream);
 int64_t cnt_sm_solve_workspace_bytes(int NS, const cnt_sm_info *h_info);
 /* numeric phase.  val [NS, val_stride]: CSR off-diagonal values (-g) of cnt_assemble_values; electrode coupling of
  * row r = g[src_eid[r]] + g[drn_eid[r]] (either may be < 0 = none; src_eid / drn_eid / g may be NULL) + coupling[q, r]

@@ -63,7 +63,7 @@ PROTOTYPES = {
     "cnt_pcg_cluster_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, i32, vp, i64, vp]),
     "cnt_sm_plan_layout": (i64, [i64, i32, i64, i64, i64, C.POINTER(i64)]),
     "cnt_sm_symbolic_workspace_bytes": (i64, [i64, i32, i64, i64, i64, i64]),
-    "cnt_sm_symbolic": (i32, [i32, vp, i64, i64, vp, vp, i32, i32, i64, i64, i64, vp, i64, vp, i64, vp, vp]),
+    "cnt_sm_symbolic": (i32, [i32, vp, i64, i64, vp, vp, i32, i32, i64, i64, i64, vp, vp, i64, vp, i64, vp, vp]),
     "cnt_sm_solve_workspace_bytes": (i64, [i32, vp]),
     "cnt_sm_solve": (i32, [i32, i32, i64, i64, vp, vp, i64, i64, vp, vp, i64, vp, vp, vp, i64, vp, vp, i64, i32, vp, vp,
                            i64, vp]),

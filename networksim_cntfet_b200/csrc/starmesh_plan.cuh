@@ -12,7 +12,7 @@ struct Plan {
     int32_t *tgt, *cptr, *cm, *ca, *cb;            // edge-target groups and their star-mesh contributions
     int32_t *tn, *tptr, *tm, *tslot;               // node-target groups (c, b updates of the neighbours)
     int32_t *e0_ptr, *e0_src;                      // round-0 edge values: sums of CSR entries
-    int32_t *dptr, *dnodes, *dslot;                // dense tail: rows of every network, remaining edge slots
+    int32_t *dptr, *dnodes, *dslot, *dedge;        // dense tail: rows of every network, remaining edge slots (grouped by network)
     long long *doff, *depos;                       // ... matrix offsets, position of every remaining edge
     cnt_sm_info *info;                             // device copy of the header
 };
@@ -27,6 +27,7 @@ inline int64_t plan_layout(int64_t R, int B, int64_t NNZ, int64_t capS, int64_t 
         (int64_t)B + 1, R, capS,                   // dptr dnodes dslot
         2 * ((int64_t)B + 1), 2 * capS,            // doff depos (64-bit entries)
         (int64_t)((sizeof(cnt_sm_info) + 3) / 4),  // info
+        (int64_t)B + 1,                            // dedge
     };
     int64_t pos = 0;
     for (int k = 0; k < CNT_SM_NARR; k++) {
@@ -61,6 +62,7 @@ inline Plan plan_view(void *buf, const int64_t *off) {
     v.doff = (long long *)(p + off[CNT_SM_DOFF]);
     v.depos = (long long *)(p + off[CNT_SM_DEPOS]);
     v.info = (cnt_sm_info *)(p + off[CNT_SM_INFO]);
+    v.dedge = (int32_t *)(p + off[CNT_SM_DEDGE]);
     return v;
 }
 

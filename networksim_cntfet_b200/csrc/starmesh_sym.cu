@@ -24,16 +24,19 @@
 // layout itself is deterministic (the only nondeterministic orders -- arrival in the lists, position in
 // the live-edge list -- are internal).  A network freezes once it has <= dense_max unknowns left; the
 // frozen remainders are handed to the dense tail (k_final_*).
+#include <stdlib.h>
 #include "starmesh_plan.cuh"
 
 namespace {
 using cnt::sm::Plan;
 
 constexpr int TB = 256;
-constexpr int IPT = 8;                 // items per thread of the chained scans
+constexpr int IPT = 4;                 // items per thread of the chained scans
 constexpr int TILE = TB * IPT;
 constexpr int SAT = 1 << 29;           // saturation of the pair counter (overflow detection)
-constexpr int GRID = 148 * 6;          // fixed grid of the device-sized kernels
+constexpr int GRID = 148 * 8;          // full grid of the device-sized kernels (8 CTAs of 256 threads per SM)
+constexpr int SORT_SMEM = 512;         // longest neighbour list a warp sorts out of shared memory
+constexpr unsigned long long DEG1 = 1ull << 46;      // one unit of degree in a priority word
 
 struct __align__(16) HEnt {
     unsigned long long key;            // (u << 32) | w, u < w global rows; all ones = empty
@@ -92,11 +95,15 @@ struct Sym {
     Plan p;
     // workspace
     int32_t *eu, *ew;                  // [capS] endpoints of every slot (global rows, eu < ew)
-    int32_t *deg, *mid, *blocked, *rnet, *fill, *nhead, *loc;     // [R]
+    unsigned long long *pri;           // [R] (degree << 46) | (hash of the local index << 26) | local index
+    int32_t *mid, *blocked, *rnet, *fill, *nhead, *loc;     // [R]; mid: -1 in play, -2 frozen, >= 0 pivot index
     int32_t *lm;                       // [capS] pivot index of every incident entry
     int32_t *live[2];                  // [capS] live edge slots (ping-pong)
+    int2 *luw[2];                      // [capS] ... and their endpoints
+    long long *hoff;                   // [B + 1] hash region of every network (keeps the probes of a network together)
     int32_t *nodes[2];                 // [R] unknowns in play, ascending (ping-pong)
     int32_t *nalive;                   // [B] unknowns left per network
+    int32_t *dcount;                   // [B] remaining edges per network (dense tail)
     int32_t *nlive;                    // [MAX_ROUNDS + 2] size of the live list at the start of round r
     HEnt *htab;
     int32_t *pent, *pnext, *gsz, *ghead, *pm, *pa, *pb, *gidx, *goff, *gnew;     // [capI] per item of a round
@@ -112,23 +119,23 @@ __device__ __forceinline__ unsigned long long priority(int deg, int lid) {
     unsigned long long d = (unsigned long long)(deg < (1 << 18) - 1 ? deg : (1 << 18) - 1);
     return (d << 46) | ((unsigned long long)h << 26) | (unsigned long long)(unsigned)lid;
 }
-__device__ __forceinline__ unsigned hash_pos(unsigned long long key, unsigned hcap) {
+// entry of key in the hash region of its network, inserted when absent (slot stays -1); -1 when the region is full
+__device__ __forceinline__ int hash_find_or_insert(const Sym &s, int net, unsigned long long key) {
+    const long long h0 = s.hoff[net];
+    const unsigned hsize = (unsigned)(s.hoff[net + 1] - h0);
     unsigned long long z = key * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9ull;
     z ^= z >> 32;
-    return (unsigned)(((z & 0xFFFFFFFFull) * (unsigned long long)hcap) >> 32);
-}
-// entry of key, inserted when absent (slot stays -1); -1 when the table is full
-__device__ __forceinline__ int hash_find_or_insert(const Sym &s, unsigned long long key) {
-    unsigned h = hash_pos(key, s.hcap);
-    for (unsigned probes = 0; probes < s.hcap; probes++) {
-        unsigned long long old = s.htab[h].key;
-        if (old == key) return (int)h;
+    unsigned h = (unsigned)(((z & 0xFFFFFFFFull) * (unsigned long long)hsize) >> 32);
+    for (unsigned probes = 0; probes < hsize; probes++) {
+        HEnt *ent = s.htab + h0 + h;
+        unsigned long long old = ent->key;
+        if (old == key) return (int)(h0 + h);
         if (old == HEMPTY) {
-            old = atomicCAS(&s.htab[h].key, HEMPTY, key);
-            if (old == HEMPTY || old == key) return (int)h;
+            old = atomicCAS(&ent->key, HEMPTY, key);
+            if (old == HEMPTY || old == key) return (int)(h0 + h);
         }
-        h = h + 1 == s.hcap ? 0u : h + 1;
+        h = h + 1 == hsize ? 0u : h + 1;
     }
     atomicOr(&s.p.info->error, CNT_SM_ERR_HASH);
     return -1;
@@ -151,6 +158,8 @@ __device__ __forceinline__ int warp_append(int *counter, bool pred) {
 // aggregate, looks back over its predecessors a warp at a time, then publishes its inclusive
 // prefix.  Flags carry the invocation's epoch, so the status buffers are never cleared.
 //   f(i) -> V4 value of item i;  g(i, exclusive prefix, own value);  fin(grand total) once.
+// f and g are called with consecutive items on consecutive threads (coalesced); the values go through
+// shared memory to the blocked arrangement the scan needs.
 // ---------------------------------------------------------------------------------------
 template <class F, class G, class H>
 __device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int *sflag, V4 *sagg, V4 *sinc, int *err,
@@ -158,6 +167,7 @@ __device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int 
     __shared__ int s_tile;
     __shared__ V4 s_prefix, s_total;
     __shared__ V4 s_warp[TB / 32];
+    __shared__ V4 sv[TILE], se[TILE];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int ntiles = (n + TILE - 1) / TILE;
     const V4 zero = v4(0, 0, 0, 0);
@@ -171,14 +181,16 @@ __device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int 
         __syncthreads();
         const int tile = s_tile;
         if (tile >= ntiles) break;
-        const int i0 = tile * TILE + tid * IPT;
-        V4 v[IPT];
-        V4 sum = zero;
+        const int i0 = tile * TILE;
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
-            v[k] = i0 + k < n ? f(i0 + k) : zero;
-            sum = sum + v[k];
+            const int i = i0 + k * TB + tid;
+            sv[k * TB + tid] = i < n ? f(i) : zero;
         }
+        __syncthreads();
+        V4 sum = zero;
+#pragma unroll
+        for (int k = 0; k < IPT; k++) sum = sum + sv[tid * IPT + k];
         V4 inc = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -255,8 +267,14 @@ __device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int 
         V4 base = s_prefix + s_warp[wid] + ex;
 #pragma unroll
         for (int k = 0; k < IPT; k++) {
-            if (i0 + k < n) g(i0 + k, base, v[k]);
-            base = base + v[k];
+            se[tid * IPT + k] = base;
+            base = base + sv[tid * IPT + k];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const int i = i0 + k * TB + tid;
+            if (i < n) g(i, se[k * TB + tid], sv[k * TB + tid]);
         }
         if (tile == ntiles - 1 && tid == 0) fin(s_total);
     }
@@ -265,9 +283,41 @@ __device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int 
 __device__ __forceinline__ int net_of_row(const Sym &s, int r) { return cnt::find_segment(s.roff, s.B, r); }
 
 // ---------------------------------------------------------------------------------------
-// initialisation: round-0 edge slots (unique stick pairs of the CSR pattern, row-major), their
-// value lists (e0_ptr / e0_src), the hash, degrees, the first live / node lists
+// initialisation: hash regions; round-0 edge slots (unique stick pairs of the CSR pattern,
+// row-major), their value lists (e0_ptr / e0_src), the hash, priorities, the first live / node lists
 // ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_hoff(Sym s) {
+    // region of network b: share of the table proportional to its pattern entries (+64)
+    __shared__ long long s_n[1024];
+    const int t = threadIdx.x;
+    const int per = (s.B + 1023) / 1024;
+    const int lo = min(t * per, s.B), hi = min(lo + per, s.B);
+    const double scale = (double)(s.hcap - 64.0 * s.B) / (double)(s.NNZ > 0 ? s.NNZ : 1);
+    auto size_of = [&](int b) {
+        const long long nz = s.rowptr[s.roff[b + 1]] - s.rowptr[s.roff[b]];
+        return (long long)(scale * (double)nz) + 64;
+    };
+    long long sn = 0;
+    for (int b = lo; b < hi; b++) sn += size_of(b);
+    s_n[t] = sn;
+    __syncthreads();
+    if (t == 0) {
+        long long acc = 0;
+        for (int k = 0; k < 1024; k++) {
+            const long long c = s_n[k];
+            s_n[k] = acc;
+            acc += c;
+        }
+        s.hoff[s.B] = acc;
+    }
+    __syncthreads();
+    sn = s_n[t];
+    for (int b = lo; b < hi; b++) {
+        s.hoff[b] = sn;
+        sn += size_of(b);
+    }
+}
+
 __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
     const int gt = blockIdx.x * TB + threadIdx.x, gn = gridDim.x * TB;
     for (int b = gt; b < s.B; b += gn) s.nalive[b] = s.roff[b + 1] - s.roff[b];
@@ -301,15 +351,17 @@ __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
                     s.eu[slot] = i;
                     s.ew[slot] = c;
                     s.live[0][slot] = slot;
+                    s.luw[0][slot] = make_int2(i, c);
                     s.p.e0_ptr[slot] = kk;
-                    const int e = hash_find_or_insert(s, ((unsigned long long)(unsigned)i << 32) | (unsigned)c);
+                    const int e = hash_find_or_insert(s, net, ((unsigned long long)(unsigned)i << 32) | (unsigned)c);
                     if (e >= 0) s.htab[e].slot = slot;
                 }
                 prevu = c;
             }
             s.p.e0_src[kk++] = k;
         }
-        s.deg[i] = nd;
+        s.pri[i] = priority(nd, i - base);
+        if (nd >= (1 << 17)) atomicOr(&s.p.info->error, CNT_SM_ERR_SLOTS);      // degree field of the priority word
     };
     auto fin = [&](V4 t) {
         cnt_sm_info *info = s.p.info;
@@ -334,17 +386,15 @@ __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
 // ---------------------------------------------------------------------------------------
 // round kernels
 // ---------------------------------------------------------------------------------------
+// a frozen network's edges may still be in the list (k_incident drops them): blocking a frozen
+// unknown is harmless, k_select no longer looks at it
 __global__ void __launch_bounds__(TB) k_mark(Sym s, int r) {
     if (s.p.info->done | s.p.info->error) return;
     const int n = s.nlive[r];
-    const int32_t *L = s.live[r & 1];
+    const int2 *L = s.luw[r & 1];
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
-        const int e = L[i], u = s.eu[e], w = s.ew[e];
-        const int net = s.rnet[u];
-        if (s.nalive[net] <= s.dense_max) continue;      // frozen network: left to the dense tail
-        const int base = s.roff[net];
-        const unsigned long long pu = priority(s.deg[u], u - base), pw = priority(s.deg[w], w - base);
-        s.blocked[pu > pw ? u : w] = r + 1;
+        const int2 e = L[i];
+        s.blocked[s.pri[e.x] > s.pri[e.y] ? e.x : e.y] = r + 1;
     }
 }
 
@@ -359,7 +409,8 @@ __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
         const int v = N[i];
         if (s.nalive[s.rnet[v]] <= s.dense_max) return v4(0, 0, 0, 0);        // frozen: leaves the list
         if (s.blocked[v] == r + 1) return v4(0, 0, 0, 1);                       // survivor
-        const int d = s.deg[v];
+        const int d = (int)(s.pri[v] >> 46);
+        if (d >= (1 << 17)) atomicOr(&s.p.info->error, CNT_SM_ERR_SLOTS);       // degree field about to overflow
         const long long pairs = (long long)d * (d - 1) / 2;
         return v4(1, d, pairs > SAT ? SAT : (int)pairs, 0);
     };
@@ -373,6 +424,8 @@ __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
             s.pptr[ex.a] = ex.c;
         } else if (own.d) {
             Nout[ex.d] = v;
+        } else {
+            s.mid[v] = -2;                                                      // frozen from now on
         }
     };
     auto fin = [&](V4 t) {
@@ -407,69 +460,140 @@ __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
     if (info->done | info->error) return;
     const int n = s.nlive[r], ebase = info->rounds[r].ebase;
     const int32_t *L = s.live[r & 1];
+    const int2 *Luw = s.luw[r & 1];
     int32_t *Lout = s.live[(r + 1) & 1];
+    int2 *Luwout = s.luw[(r + 1) & 1];
     const int nceil = (n + 31) & ~31;
     for (int i = blockIdx.x * TB + threadIdx.x; i < nceil; i += gridDim.x * TB) {
         bool keep = false;
         int e = 0;
+        int2 uw = make_int2(0, 0);
         if (i < n) {
             e = L[i];
-            const int u = s.eu[e], w = s.ew[e];
-            if (s.nalive[s.rnet[u]] > s.dense_max) {
-                const int mu = s.mid[u], mw = s.mid[w];
-                if (mu >= ebase) {
-                    const int k = s.p.nptr[mu] + atomicAdd(&s.fill[mu], 1);
-                    s.p.nbr[k] = w;
-                    s.p.eslot[k] = e;
-                } else if (mw >= ebase) {
-                    const int k = s.p.nptr[mw] + atomicAdd(&s.fill[mw], 1);
-                    s.p.nbr[k] = u;
-                    s.p.eslot[k] = e;
-                } else {
-                    keep = true;
-                }
+            uw = Luw[i];
+            const int mu = s.mid[uw.x], mw = s.mid[uw.y];
+            if (mu >= ebase) {
+                const int k = s.p.nptr[mu] + atomicAdd(&s.fill[mu], 1);
+                s.p.nbr[k] = uw.y;
+                s.p.eslot[k] = e;
+            } else if (mw >= ebase) {
+                const int k = s.p.nptr[mw] + atomicAdd(&s.fill[mw], 1);
+                s.p.nbr[k] = uw.x;
+                s.p.eslot[k] = e;
+            } else {
+                keep = mu == -1;           // -2: frozen network, its edges leave the list
             }
         }
         const int pos = warp_append(&s.nlive[r + 1], keep);
-        if (keep) Lout[pos] = e;
+        if (keep) {
+            Lout[pos] = e;
+            Luwout[pos] = uw;
+        }
     }
 }
 
+// neighbours of one pivot ascending, by the whole warp: rank sort (out of shared memory when the list fits)
+// through the free tm / tslot ranges of the round (k_items_c fills them later); then lm, the neighbours'
+// degrees and the pivot of every pair of the round (pm)
+__device__ __forceinline__ void warp_pivot(const Sym &s, int m, int k0, int d, int t0, int npairs, int *sm /* SORT_SMEM */) {
+    const int lane = threadIdx.x & 31;
+    if (d > 1) {
+        const bool in_smem = d <= SORT_SMEM;
+        if (in_smem) {
+            for (int e = lane; e < d; e += 32) sm[e] = s.p.nbr[k0 + e];
+            __syncwarp();
+        }
+        for (int e = lane; e < d; e += 32) {
+            int rank = 0;
+            if (in_smem) {
+                const int v = sm[e];
+#pragma unroll 4
+                for (int j = 0; j < d; j++) rank += sm[j] < v;
+            } else {
+                const int v = s.p.nbr[k0 + e];
+                for (int j = 0; j < d; j++) rank += s.p.nbr[k0 + j] < v;
+            }
+            s.p.tm[k0 + rank] = in_smem ? sm[e] : s.p.nbr[k0 + e];
+            s.p.tslot[k0 + rank] = s.p.eslot[k0 + e];
+        }
+        __syncwarp();
+        for (int e = lane; e < d; e += 32) {
+            s.p.nbr[k0 + e] = s.p.tm[k0 + e];
+            s.p.eslot[k0 + e] = s.p.tslot[k0 + e];
+        }
+        __syncwarp();
+    }
+    for (int e = lane; e < d; e += 32) {
+        s.lm[k0 + e] = m;
+        atomicAdd(&s.pri[s.p.nbr[k0 + e]], 0ull - DEG1);
+    }
+    for (int t = lane; t < npairs; t += 32) s.pm[t0 + t] = m;
+}
+
 __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
+    __shared__ int s_sort[TB / 32][SORT_SMEM];
     cnt_sm_info *info = s.p.info;
     if (info->done | info->error) return;
     const int nelim = info->rounds[r].nelim, ebase = info->rounds[r].ebase;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    constexpr int SMALL = 8;
+    const int nwarps = gridDim.x * (TB / 32);
+    if (nelim <= nwarps) {
+        // few pivots (the late rounds, long lists): one warp each
+        const int ml = blockIdx.x * (TB / 32) + wid;
+        if (ml >= nelim) return;
+        const int m = ebase + ml, k0 = s.p.nptr[m], d = s.p.nptr[m + 1] - k0;
+        warp_pivot(s, m, k0, d, s.pptr[ml], s.pptr[ml + 1] - s.pptr[ml], s_sort[wid]);
+        if (lane == 0) {
+            atomicSub(&s.nalive[s.rnet[s.p.piv[m]]], 1);
+            atomicMax(&info->max_deg, d);
+        }
+        return;
+    }
     const int nceil = (nelim + 31) & ~31;
     for (int ml = blockIdx.x * TB + threadIdx.x; ml < nceil; ml += gridDim.x * TB) {
-        int d = 0, net = -1;
+        int d = 0, net = -1, k0 = 0, t0 = 0, np = 0;
+        const int m = ebase + ml;
         if (ml < nelim) {
-            const int m = ebase + ml;
-            const int k0 = s.p.nptr[m], k1 = s.p.nptr[m + 1];
+            k0 = s.p.nptr[m];
+            const int k1 = s.p.nptr[m + 1];
             d = k1 - k0;
-            for (int a = k0 + 1; a < k1; a++) {          // neighbours ascending (lists are short)
-                const int nb = s.p.nbr[a], es = s.p.eslot[a];
-                int c = a - 1;
-                while (c >= k0 && s.p.nbr[c] > nb) {
-                    s.p.nbr[c + 1] = s.p.nbr[c];
-                    s.p.eslot[c + 1] = s.p.eslot[c];
-                    c--;
+            t0 = s.pptr[ml];
+            np = s.pptr[ml + 1] - t0;
+            if (d <= SMALL) {
+                for (int a = k0 + 1; a < k1; a++) {          // neighbours ascending (short list: insertion sort)
+                    const int nb = s.p.nbr[a], es = s.p.eslot[a];
+                    int c = a - 1;
+                    while (c >= k0 && s.p.nbr[c] > nb) {
+                        s.p.nbr[c + 1] = s.p.nbr[c];
+                        s.p.eslot[c + 1] = s.p.eslot[c];
+                        c--;
+                    }
+                    s.p.nbr[c + 1] = nb;
+                    s.p.eslot[c + 1] = es;
                 }
-                s.p.nbr[c + 1] = nb;
-                s.p.eslot[c + 1] = es;
-            }
-            for (int k = k0; k < k1; k++) {
-                s.lm[k] = m;
-                atomicSub(&s.deg[s.p.nbr[k]], 1);
+                for (int k = k0; k < k1; k++) {
+                    s.lm[k] = m;
+                    atomicAdd(&s.pri[s.p.nbr[k]], 0ull - DEG1);
+                }
+                for (int t = 0; t < np; t++) s.pm[t0 + t] = m;
             }
             net = s.rnet[s.p.piv[m]];
         }
+        unsigned big = __ballot_sync(~0u, d > SMALL);
+        while (big) {                                         // longer lists: one at a time by the whole warp
+            const int src = __ffs(big) - 1;
+            big &= big - 1;
+            warp_pivot(s, __shfl_sync(~0u, m, src), __shfl_sync(~0u, k0, src), __shfl_sync(~0u, d, src),
+                       __shfl_sync(~0u, t0, src), __shfl_sync(~0u, np, src), s_sort[wid]);
+        }
         // unknowns left per network: one atomic per run of equal networks inside the warp
         const unsigned same = __match_any_sync(~0u, net);
-        if (net >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicSub(&s.nalive[net], __popc(same));
+        if (net >= 0 && lane == __ffs(same) - 1) atomicSub(&s.nalive[net], __popc(same));
         int dmax = d;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(~0u, dmax, o));
-        if ((threadIdx.x & 31) == 0 && dmax > 0) atomicMax(&info->max_deg, dmax);
+        if (lane == 0 && dmax > 0) atomicMax(&info->max_deg, dmax);
     }
 }
 
@@ -478,26 +602,21 @@ __global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
     const cnt_sm_info *info = s.p.info;
     if (info->done | info->error) return;
     const cnt_sm_round *rd = &info->rounds[r];
-    const int np = rd->npairs, nl = rd->nlist, nelim = rd->nelim, ebase = rd->ebase, lbase = rd->lbase;
+    const int np = rd->npairs, nl = rd->nlist, ebase = rd->ebase, lbase = rd->lbase;
     for (int t = blockIdx.x * TB + threadIdx.x; t < np + nl; t += gridDim.x * TB) {
         s.gsz[t] = 0;
         if (t < np) {
-            int lo = 0, hi = nelim;                       // pptr[lo] <= t < pptr[hi]
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (s.pptr[mid] <= t) lo = mid; else hi = mid;
-            }
-            const int m = ebase + lo, k0 = s.p.nptr[m], d = s.p.nptr[m + 1] - k0;
-            int q = t - s.pptr[lo], i = 0;
-            while (q >= d - 1 - i) {
-                q -= d - 1 - i;
-                i++;
-            }
-            const int j = i + 1 + q;
+            const int m = s.pm[t], k0 = s.p.nptr[m], d = s.p.nptr[m + 1] - k0;
+            // pair q of the pivot -> (i, j), i < j, row-major: row i starts at i (2d - i - 1) / 2
+            const int q = t - s.pptr[m - ebase];
+            int i = (int)(((2.0 * d - 1.0) - sqrt((2.0 * d - 1.0) * (2.0 * d - 1.0) - 8.0 * (double)q)) * 0.5);
+            i = max(0, min(i, d - 2));
+            while (i > 0 && (long long)i * (2 * d - i - 1) / 2 > q) i--;
+            while ((long long)(i + 1) * (2 * d - i - 2) / 2 <= q) i++;
+            const int j = i + 1 + (q - (int)((long long)i * (2 * d - i - 1) / 2));
             const int u = s.p.nbr[k0 + i], w = s.p.nbr[k0 + j];
-            const int e = hash_find_or_insert(s, ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
+            const int e = hash_find_or_insert(s, s.rnet[u], ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
             s.pent[t] = e;
-            s.pm[t] = m;
             s.pa[t] = s.p.eslot[k0 + i];
             s.pb[t] = s.p.eslot[k0 + j];
             s.pnext[t] = e >= 0 ? atomicExch(&s.htab[e].head, t) : -1;
@@ -580,58 +699,72 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
     for (int t = blockIdx.x * TB + threadIdx.x; t < nceil; t += gridDim.x * TB) {
         bool fresh = false;
         int slot = -1;
+        int2 uw = make_int2(0, 0);
         const int z = t < n ? s.gsz[t] : 0;
         if (z) {
             const int cnt = z & ((1 << 30) - 1);
             if (t < np) {
                 const int e = s.pent[t], off = cbase + s.goff[t], gi = gebase + s.gidx[t];
-                int k = 0;
-                for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {         // members ordered by item = by pivot
-                    int c = k - 1;
-                    while (c >= 0 && s.p.cm[off + c] > x) {
-                        s.p.cm[off + c + 1] = s.p.cm[off + c];
-                        c--;
+                if (cnt == 1) {
+                    s.p.cm[off] = s.pm[t];
+                    s.p.ca[off] = s.pa[t];
+                    s.p.cb[off] = s.pb[t];
+                } else {
+                    int k = 0;
+                    for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {     // members ordered by item = by pivot
+                        int c = k - 1;
+                        while (c >= 0 && s.p.cm[off + c] > x) {
+                            s.p.cm[off + c + 1] = s.p.cm[off + c];
+                            c--;
+                        }
+                        s.p.cm[off + c + 1] = x;
+                        k++;
                     }
-                    s.p.cm[off + c + 1] = x;
-                    k++;
+                    for (k = 0; k < cnt; k++) {
+                        const int x = s.p.cm[off + k];
+                        s.p.cm[off + k] = s.pm[x];
+                        s.p.ca[off + k] = s.pa[x];
+                        s.p.cb[off + k] = s.pb[x];
+                    }
                 }
-                for (k = 0; k < cnt; k++) {
-                    const int x = s.p.cm[off + k];
-                    s.p.cm[off + k] = s.pm[x];
-                    s.p.ca[off + k] = s.pa[x];
-                    s.p.cb[off + k] = s.pb[x];
-                }
-                slot = s.htab[e].slot;
+                HEnt *ent = s.htab + e;
+                slot = ent->slot;
                 if (slot < 0) {                           // a fill edge: numbered in group order
                     fresh = true;
                     slot = sbase + s.gnew[t];
-                    const unsigned long long key = s.htab[e].key;
-                    const int u = (int)(key >> 32), w = (int)(key & 0xFFFFFFFFull);
-                    s.htab[e].slot = slot;
-                    s.eu[slot] = u;
-                    s.ew[slot] = w;
-                    atomicAdd(&s.deg[u], 1);
-                    atomicAdd(&s.deg[w], 1);
+                    const unsigned long long key = ent->key;
+                    uw = make_int2((int)(key >> 32), (int)(key & 0xFFFFFFFFull));
+                    ent->slot = slot;
+                    s.eu[slot] = uw.x;
+                    s.ew[slot] = uw.y;
+                    atomicAdd(&s.pri[uw.x], DEG1);
+                    atomicAdd(&s.pri[uw.y], DEG1);
                 }
-                s.htab[e].head = -1;
+                ent->head = -1;
                 s.p.tgt[gi] = slot;
                 s.p.cptr[gi] = off;
             } else {
                 const int o = s.pent[t], off = lbase + (s.goff[t] - np), gi = gnbase + (s.gidx[t] - nge);
-                int k = 0;
-                for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {
-                    int c = k - 1;
-                    while (c >= 0 && s.p.tm[off + c] > x) {
-                        s.p.tm[off + c + 1] = s.p.tm[off + c];
-                        c--;
+                if (cnt == 1) {
+                    const int kk = lbase + (t - np);
+                    s.p.tm[off] = s.lm[kk];
+                    s.p.tslot[off] = s.p.eslot[kk];
+                } else {
+                    int k = 0;
+                    for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {
+                        int c = k - 1;
+                        while (c >= 0 && s.p.tm[off + c] > x) {
+                            s.p.tm[off + c + 1] = s.p.tm[off + c];
+                            c--;
+                        }
+                        s.p.tm[off + c + 1] = x;
+                        k++;
                     }
-                    s.p.tm[off + c + 1] = x;
-                    k++;
-                }
-                for (k = 0; k < cnt; k++) {
-                    const int kk = lbase + (s.p.tm[off + k] - np);
-                    s.p.tm[off + k] = s.lm[kk];
-                    s.p.tslot[off + k] = s.p.eslot[kk];
+                    for (k = 0; k < cnt; k++) {
+                        const int kk = lbase + (s.p.tm[off + k] - np);
+                        s.p.tm[off + k] = s.lm[kk];
+                        s.p.tslot[off + k] = s.p.eslot[kk];
+                    }
                 }
                 s.nhead[o] = -1;
                 s.p.tn[gi] = o;
@@ -639,7 +772,10 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
             }
         }
         const int pos = warp_append(&s.nlive[r + 1], fresh);
-        if (fresh) s.live[(r + 1) & 1][pos] = slot;
+        if (fresh) {
+            s.live[(r + 1) & 1][pos] = slot;
+            s.luw[(r + 1) & 1][pos] = uw;
+        }
     }
 }
 
@@ -719,33 +855,68 @@ __global__ void __launch_bounds__(TB) k_final_nodes(Sym s, int epoch) {
     chained_scan(s.R, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
 }
 
+// remaining edges grouped by network: count, scan (k_final_b), fill
+template <bool FILL>
 __global__ void __launch_bounds__(TB) k_final_edges(Sym s) {
     cnt_sm_info *info = s.p.info;
     if (!info->done || info->error) return;
     const int n = info->nslots, nceil = (n + 31) & ~31;
     for (int e = blockIdx.x * TB + threadIdx.x; e < nceil; e += gridDim.x * TB) {
-        bool keep = false;
-        int u = 0, w = 0;
+        int net = -1, u = 0, w = 0;
         if (e < n) {
             u = s.eu[e];
             w = s.ew[e];
-            keep = s.mid[u] < 0 && s.mid[w] < 0;
+            if (s.mid[u] < 0 && s.mid[w] < 0) net = s.rnet[u];
         }
-        const int pos = warp_append(&info->dense_nE, keep);
-        if (keep) {
-            const int net = s.rnet[u];
+        const unsigned same = __match_any_sync(~0u, net);
+        if (net < 0) continue;
+        const int lane = threadIdx.x & 31, leader = __ffs(same) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(&s.dcount[net], __popc(same));
+        base = __shfl_sync(same, base, leader);
+        if (FILL) {
+            const int pos = s.p.dedge[net] + base + __popc(same & ((1u << lane) - 1u));
             const long long nn = s.p.dptr[net + 1] - s.p.dptr[net];
             s.p.dslot[pos] = e;
             s.p.depos[pos] = s.p.doff[net] + (long long)s.loc[u] * nn + s.loc[w];
         }
     }
 }
+__global__ void __launch_bounds__(1024) k_final_b(Sym s) {
+    cnt_sm_info *info = s.p.info;
+    if (!info->done || info->error) return;
+    __shared__ int s_n[1024];
+    const int t = threadIdx.x;
+    const int per = (s.B + 1023) / 1024;
+    const int lo = min(t * per, s.B), hi = min(lo + per, s.B);
+    int sn = 0;
+    for (int b = lo; b < hi; b++) sn += s.dcount[b];
+    s_n[t] = sn;
+    __syncthreads();
+    if (t == 0) {
+        int acc = 0;
+        for (int k = 0; k < 1024; k++) {
+            const int c = s_n[k];
+            s_n[k] = acc;
+            acc += c;
+        }
+        info->dense_nE = acc;
+        s.p.dedge[s.B] = acc;
+    }
+    __syncthreads();
+    sn = s_n[t];
+    for (int b = lo; b < hi; b++) {
+        s.p.dedge[b] = sn;
+        sn += s.dcount[b];
+        s.dcount[b] = 0;
+    }
+}
 
 struct WsLayout {
-    int64_t eu, ew, lm, live0, live1, deg, rnet, loc, nodes0, nodes1, nalive, pptr, items, sagg, sinc, htab;
+    int64_t eu, ew, lm, live0, live1, luw0, luw1, pri, hoff, rnet, loc, nodes0, nodes1, nalive, pptr, items, sagg, sinc, htab;
     int64_t ones0, ones1;      // [mid, nhead]: memset 0xFF
     int64_t zero0, zero1;      // [blocked, fill, nlive, tickets, sflag]: memset 0
-    int64_t mid, nhead, blocked, fill, nlive, tickets, sflag;
+    int64_t mid, nhead, blocked, fill, nlive, tickets, sflag, dcount;
     int64_t total;
     unsigned hcap;
     int64_t ntiles;
@@ -767,7 +938,10 @@ WsLayout ws_layout(int64_t R, int B, int64_t capS, int64_t capI) {
     L.lm = take(capS, 4);
     L.live0 = take(capS, 4);
     L.live1 = take(capS, 4);
-    L.deg = take(R, 4);
+    L.luw0 = take(capS, 8);
+    L.luw1 = take(capS, 8);
+    L.pri = take(R, 8);
+    L.hoff = take((int64_t)B + 1, 8);
     L.rnet = take(R, 4);
     L.loc = take(R, 4);
     L.nodes0 = take(R, 4);
@@ -787,8 +961,9 @@ WsLayout ws_layout(int64_t R, int B, int64_t capS, int64_t capI) {
     L.nlive = take(CNT_SM_MAX_ROUNDS + 2, 4);
     L.tickets = take(2 * CNT_SM_MAX_ROUNDS + 8, 4);
     L.sflag = take(L.ntiles, 4);
+    L.dcount = take(B, 4);
     L.zero1 = pos;
-    int64_t hc = 2 * capS + 64;
+    int64_t hc = 2 * capS + 64 * ((int64_t)B + 1);
     L.hcap = (unsigned)hc;
     L.htab = take(hc, (int64_t)sizeof(HEnt));
     L.total = pos;
@@ -814,8 +989,8 @@ extern "C" int64_t cnt_sm_symbolic_workspace_bytes(int64_t R, int B, int64_t NNZ
 
 extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NNZ, const int32_t *rowptr,
                                const int32_t *col, int dense_max, int rounds_hint, int64_t cap_slots,
-                               int64_t cap_contrib, int64_t cap_items, void *plan, int64_t plan_bytes, void *ws,
-                               int64_t ws_bytes, cnt_sm_info *h_info, void *stream) {
+                               int64_t cap_contrib, int64_t cap_items, const cnt_sm_info *hint, void *plan,
+                               int64_t plan_bytes, void *ws, int64_t ws_bytes, cnt_sm_info *h_info, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && roff && R > 0 && R < (1 << 26) && NNZ >= 0 && rowptr && (col || NNZ == 0) && plan && ws && h_info);
     CNT_CHECK_ARG(dense_max >= 0 && cap_slots >= NNZ / 2 + 1 && cap_slots < (1 << 29) && cap_contrib > 0 &&
@@ -839,7 +1014,9 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
     s.p = cnt::sm::plan_view(plan, off);
     s.eu = (int32_t *)(w + L.eu); s.ew = (int32_t *)(w + L.ew); s.lm = (int32_t *)(w + L.lm);
     s.live[0] = (int32_t *)(w + L.live0); s.live[1] = (int32_t *)(w + L.live1);
-    s.deg = (int32_t *)(w + L.deg); s.rnet = (int32_t *)(w + L.rnet); s.loc = (int32_t *)(w + L.loc);
+    s.pri = (unsigned long long *)(w + L.pri); s.hoff = (long long *)(w + L.hoff);
+    s.luw[0] = (int2 *)(w + L.luw0); s.luw[1] = (int2 *)(w + L.luw1);
+    s.rnet = (int32_t *)(w + L.rnet); s.loc = (int32_t *)(w + L.loc);
     s.nodes[0] = (int32_t *)(w + L.nodes0); s.nodes[1] = (int32_t *)(w + L.nodes1);
     s.nalive = (int32_t *)(w + L.nalive); s.pptr = (int32_t *)(w + L.pptr);
     int32_t *items = (int32_t *)(w + L.items);
@@ -849,7 +1026,7 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
     s.sagg = (V4 *)(w + L.sagg); s.sinc = (V4 *)(w + L.sinc);
     s.mid = (int32_t *)(w + L.mid); s.nhead = (int32_t *)(w + L.nhead);
     s.blocked = (int32_t *)(w + L.blocked); s.fill = (int32_t *)(w + L.fill); s.nlive = (int32_t *)(w + L.nlive);
-    s.tickets = (int32_t *)(w + L.tickets); s.sflag = (int32_t *)(w + L.sflag);
+    s.tickets = (int32_t *)(w + L.tickets); s.sflag = (int32_t *)(w + L.sflag); s.dcount = (int32_t *)(w + L.dcount);
     s.htab = (HEnt *)(w + L.htab);
 
     CNT_CUDA(cudaMemsetAsync(w + L.ones0, 0xFF, L.ones1 - L.ones0, st));
@@ -859,6 +1036,18 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
 
     // epochs: 1 = init, 2 + 2r = k_select of round r, 3 + 2r = k_items_scan of round r, then the final scan;
     // ticket counter [epoch] belongs to that invocation
+    // CNT_SM_TIMING=1: CUDA-event time of every round kernel, printed to stderr (debugging aid)
+    static const bool timing = getenv("CNT_SM_TIMING") != nullptr;
+    constexpr int MAXEV = 9 * 128;
+    static cudaEvent_t ev[MAXEV];
+    static bool ev_made = false;
+    int nev = 0;
+    if (timing && !ev_made) {
+        for (int k = 0; k < MAXEV; k++) cudaEventCreate(&ev[k]);
+        ev_made = true;
+    }
+    k_hoff<<<1, 1024, 0, st>>>(s);
+    CNT_LAUNCHED();
     k_init<<<GRID, TB, 0, st>>>(s, 1);
     CNT_LAUNCHED();
     int r = 0;
@@ -866,28 +1055,77 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
     for (;;) {
         const int rend = r + chunk < CNT_SM_MAX_ROUNDS - 1 ? r + chunk : CNT_SM_MAX_ROUNDS - 1;
         for (; r < rend; r++) {
-            k_mark<<<GRID, TB, 0, st>>>(s, r);
-            k_select<<<GRID, TB, 0, st>>>(s, r, 2 + 2 * r);
-            k_incident<<<GRID, TB, 0, st>>>(s, r);
-            k_pivots<<<GRID, TB, 0, st>>>(s, r);
-            k_items_a<<<GRID, TB, 0, st>>>(s, r);
-            k_items_b<<<GRID, TB, 0, st>>>(s, r);
-            k_items_scan<<<GRID, TB, 0, st>>>(s, r, 3 + 2 * r);
-            k_items_c<<<GRID, TB, 0, st>>>(s, r);
+            // grids: sized from the rounds of the previous batch of the same kind when the caller passes its header
+            // (any size is correct -- the kernels stride over device-side counts --, small grids just start faster)
+            int gl = GRID, gn = GRID, gp = GRID, gi = GRID;
+            if (hint && hint->done && !hint->error && hint->nrounds > 0) {
+                const cnt_sm_round *hr = &hint->rounds[r < hint->nrounds ? r : hint->nrounds - 1];
+                const double scale = 1.5 * (double)R / (hint->R > 0 ? hint->R : 1);
+                auto fit = [&](double n, int per) {
+                    double g = scale * n / per + 4;
+                    return (int)(g < GRID ? g : GRID);
+                };
+                gl = fit(hr->nlive, 2 * TB);
+                gn = fit(hr->nnodes, TILE);
+                gp = fit(hr->nelim, TB);
+                gi = fit((double)hr->npairs + hr->nlist, 2 * TB);
+            }
+            const int gs = gi < gn ? gn : gi;
+            if (timing && nev + 9 <= MAXEV) cudaEventRecord(ev[nev++], st);
+#define CNT_SM_TICK() do { if (timing && nev < MAXEV) cudaEventRecord(ev[nev++], st); } while (0)
+            k_mark<<<gl, TB, 0, st>>>(s, r);
+            CNT_SM_TICK();
+            k_select<<<gn, TB, 0, st>>>(s, r, 2 + 2 * r);
+            CNT_SM_TICK();
+            k_incident<<<gl, TB, 0, st>>>(s, r);
+            CNT_SM_TICK();
+            k_pivots<<<gp, TB, 0, st>>>(s, r);
+            CNT_SM_TICK();
+            k_items_a<<<gi, TB, 0, st>>>(s, r);
+            CNT_SM_TICK();
+            k_items_b<<<gi, TB, 0, st>>>(s, r);
+            CNT_SM_TICK();
+            k_items_scan<<<gs, TB, 0, st>>>(s, r, 3 + 2 * r);
+            CNT_SM_TICK();
+            k_items_c<<<gi, TB, 0, st>>>(s, r);
+            CNT_SM_TICK();
             cnt::count_launch(8);
         }
         CNT_CUDA(cudaGetLastError());
         // the finals run only once the rounds are over (they check the flag themselves)
         k_final_a<<<1, 1024, 0, st>>>(s);
         k_final_nodes<<<GRID, TB, 0, st>>>(s, 2 * CNT_SM_MAX_ROUNDS + 4);
-        k_final_edges<<<GRID, TB, 0, st>>>(s);
-        cnt::count_launch(3);
+        k_final_edges<false><<<GRID, TB, 0, st>>>(s);
+        k_final_b<<<1, 1024, 0, st>>>(s);
+        k_final_edges<true><<<GRID, TB, 0, st>>>(s);
+        cnt::count_launch(5);
         CNT_CUDA(cudaGetLastError());
         CNT_CUDA(cudaMemcpyAsync(h_info, s.p.info, sizeof(cnt_sm_info), cudaMemcpyDeviceToHost, st));
         CNT_CUDA(cudaStreamSynchronize(st));
         if (h_info->done || h_info->error || r >= CNT_SM_MAX_ROUNDS - 1) break;
         // not finished: the final scan did not run (no ticket taken, no flag written), go on
         chunk = 16;
+    }
+    if (timing) {
+        static const char *names[8] = {"mark", "select", "incident", "pivots", "items_a", "items_b", "scan", "items_c"};
+        double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int k = 0; k + 8 < nev; k += 9) {
+            fprintf(stderr, "sm round %3d:", k / 9);
+            double sum = 0;
+            for (int j = 0; j < 8; j++) {
+                float ms = 0;
+                cudaEventElapsedTime(&ms, ev[k + j], ev[k + j + 1]);
+                fprintf(stderr, " %s=%.0f", names[j], ms * 1e3);
+                tot[j] += ms;
+                sum += ms;
+            }
+            const cnt_sm_round *rd = &h_info->rounds[k / 9];
+            fprintf(stderr, "  sum=%.0f us  (nodes %d live %d piv %d pairs %d list %d)\n", sum * 1e3, rd->nnodes, rd->nlive,
+                    rd->nelim, rd->npairs, rd->nlist);
+        }
+        fprintf(stderr, "sm totals (ms):");
+        for (int j = 0; j < 8; j++) fprintf(stderr, " %s=%.3f", names[j], tot[j]);
+        fprintf(stderr, "\n");
     }
     if (h_info->error || !h_info->done) {
         cnt::set_error("star-mesh symbolic phase: capacity exceeded (error bits %d, rounds %d)", h_info->error,

@@ -142,6 +142,7 @@ class Engine(object):
         self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
                                        # needs prune)
         self._direct_rounds_hint = 40  # rounds launched before the symbolic phase reads its header back
+        self._direct_hint = None       # header of the previous plan (grid sizes of the round kernels)
 
     def twin(self):
         """A second Engine on the same GPU (own stream and events, same settings).  Two engines
@@ -585,12 +586,15 @@ class Engine(object):
             with self._work("direct_symbolic"):
                 plan = starmesh.symbolic(self.lib, self.stream_ptr, self.device, b.B, b.roff, R, NNZ, b.rowptr, b.col,
                                          dense_max=int(min(self.direct_dense_max, 1024)),       # k_sm_dense: <= 1400 rows
-                                         max_fill=max_fill, rounds_hint=self._direct_rounds_hint)
+                                         max_fill=max_fill, rounds_hint=self._direct_rounds_hint,
+                                         hint=self._direct_hint)
                 if plan is None:
                     b._sm_plan = False
                     return None
                 b._sm_plan = plan
                 self._direct_rounds_hint = min(plan.nrounds + 4, 400)     # first read-back of the next batch
+                self._direct_hint = starmesh.Plan()                        # header only: sizes the next batch's grids
+                self._direct_hint.info = plan.info
         with self._work("direct_numeric"):
             x = starmesh.solve_cuda(plan, self.lib, self.stream_ptr, b.rowptr, sysm["val"], sysm["rhs"],
                                     src_eid=b.src_eid, drn_eid=b.drn_eid, g=sysm["g"], leak=self.direct_leak)

@@ -35,7 +35,7 @@ from ._lib import check
 
 MAX_ROUNDS = 1024
 ARRAYS = ("piv", "nptr", "nbr", "eslot", "tgt", "cptr", "cm", "ca", "cb", "tn", "tptr", "tm", "tslot", "e0_ptr", "e0_src",
-          "dptr", "dnodes", "dslot", "doff", "depos", "info")
+          "dptr", "dnodes", "dslot", "doff", "depos", "info", "dedge")
 
 
 class SmRound(C.Structure):
@@ -91,9 +91,10 @@ class Plan(object):
 
 
 def symbolic(lib, stream_ptr, device, B, roff, R, NNZ, rowptr, col, dense_max=0, max_fill=None, rounds_hint=0,
-             slot_factor=2.0, fill_factor=4.0, slack=4096):
+             slot_factor=2.0, fill_factor=4.0, slack=4096, hint=None):
     """cnt_sm_symbolic with growing capacities.  roff [B+1], rowptr [R+1], col [NNZ]: int32 device
-    tensors (network-local ascending columns).  Returns a Plan, or None when the elimination needs
+    tensors (network-local ascending columns); hint: Plan of an earlier, similar batch (sizes the grids).
+    Returns a Plan, or None when the elimination needs
     more than max_fill star-mesh contributions per round-0 edge (+100000): dense, mesh-like networks
     far above the percolation threshold, for which the caller takes an iterative solver."""
     assert roff.dtype == torch.int32 and rowptr.dtype == torch.int32 and col.dtype == torch.int32
@@ -118,7 +119,7 @@ def symbolic(lib, stream_ptr, device, B, roff, R, NNZ, rowptr, col, dense_max=0,
                                                                  cap_items)), dtype=torch.uint8, device=device)
         rc = lib.cnt_sm_symbolic(plan.B, vp(roff.data_ptr()), plan.R, plan.NNZ, vp(rowptr.data_ptr()),
                                  vp(col.data_ptr()), int(dense_max), int(rounds_hint), cap_slots, cap_contrib, cap_items,
-                                 vp(plan.buf.data_ptr()), int(nbytes), vp(ws.data_ptr()), ws.numel(),
+                                 C.byref(hint.info) if hint is not None else None, vp(plan.buf.data_ptr()), int(nbytes), vp(ws.data_ptr()), ws.numel(),
                                  C.byref(plan.info), stream_ptr)
         del ws
         if rc == 0:

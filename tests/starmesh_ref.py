@@ -168,6 +168,7 @@ def symbolic(roff, rowptr, col, dense_max=0):
             ds.append(e)
             dp.append(p.doff[net] + loc[u] * cnt[net] + loc[w])
     p.dslot, p.depos = i32(ds), i32(dp)
+    p.dedge = np.r_[0, np.cumsum(np.bincount(rnet[p.eu[p.dslot]], minlength=B))] if len(ds) else np.zeros(B + 1, dtype=np.int64)
     p.dense_nmax = int(cnt.max()) if B else 0
     p.dense_gpool = int(p.doff[-1])
     p.nnzL = len(nbr)

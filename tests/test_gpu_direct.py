@@ -56,17 +56,19 @@ def _assert_same_plan(plan, ref):
     assert (i.nelim, i.nlist, i.ncontrib, i.nge, i.ngn) == (len(ref.piv), len(ref.nbr), len(ref.cm), len(ref.tgt), len(ref.tn))
     assert i.max_deg == ref.max_deg
     for name in ("piv", "nptr", "nbr", "eslot", "tgt", "cptr", "cm", "ca", "cb", "tn", "tptr", "tm", "tslot", "e0_ptr", "e0_src",
-                 "dptr", "dnodes", "doff"):
+                 "dptr", "dnodes", "doff", "dedge"):
         want = getattr(ref, name)
         got = plan.array(name, len(want)).cpu().numpy()
         assert np.array_equal(got, want), name
     assert (i.dense_nmax, i.dense_gpool, i.dense_nnodes, i.dense_nE) == (ref.dense_nmax, ref.dense_gpool, len(ref.dnodes),
                                                                           len(ref.dslot))
-    # the remaining edges are listed in arrival order: compare as a set of (slot, position) pairs
+    # the remaining edges are grouped by network, in arrival order inside a network: compare as a set of (slot, position) pairs
     ds = plan.array("dslot", i.dense_nE).cpu().numpy()
     dp = plan.array("depos", i.dense_nE).cpu().numpy()
     o1, o2 = np.argsort(ds), np.argsort(ref.dslot)
     assert np.array_equal(ds[o1], ref.dslot[o2]) and np.array_equal(dp[o1], ref.depos[o2])
+    net = np.searchsorted(ref.doff[1:], dp, side="right")
+    assert np.all(np.diff(net) >= 0) and np.array_equal(np.r_[0, np.cumsum(np.bincount(net, minlength=ref.B))], ref.dedge)
 
 
 def _coupling(system):
