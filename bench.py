@@ -308,27 +308,35 @@ def gpu_arm(args):
                     "algorithmic_bytes": nbytes, "pcg_iterations": iters, "pcg_seconds": pcg_s,
                     "bytes_per_iteration": "12*nnz_offdiag + 116*rows per system"}
         if solver_used == "direct":
-            # default path: star-mesh direct solve.  Its time is ~95 % the symbolic phase (about 100 rounds of
-            # ~40 small sort / unique / searchsorted / scatter launches on shrinking edge lists) -- latency
-            # bound, far from any bandwidth roof; stated as measured
+            # default path: star-mesh direct solve, symbolic (cnt_sm_symbolic) + numeric (cnt_sm_solve) phases, both
+            # hand-written: rounds of small data-dependent passes over the live edges / pivots / neighbour pairs
             d_s = (stages.get("direct_symbolic", 0.0) + stages.get("direct_numeric", 0.0)) / 1e3
             achieved = direct_bytes / d_s / 1e9 if d_s > 0 else 0.0
-            roofline = {"bound": "hbm", "kernel": "star-mesh direct solve (symbolic: torch sort/unique/searchsorted of edge "
-                                                  "keys on the device; numeric: k_sm_pivot/newedges/targets/back)",
+            traffic = traffic_note = None
+            try:
+                cap = json.load(open(os.path.join(ROOT, "profiles", "r02_direct_stage_ncu.json")))
+                if args.batch == cap.get("batch") and world == 1:
+                    traffic = cap["dram_bytes_total"]
+                    traffic_note = cap.get("note")
+            except Exception:
+                pass
+            roofline = {"bound": "hbm", "kernel": "star-mesh direct solve (cnt_sm_symbolic: k_mark/k_select/k_incident/k_pivots/"
+                                                  "k_items_a/b/scan/c per round; cnt_sm_solve: k_sm_pivot/update/back per round + "
+                                                  "k_sm_dense_smem)",
                         "achieved": achieved, "peak": peak,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
-                        "frac": achieved / peak, "traffic": None,
+                        "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                         "algorithmic_bytes_per_launch": direct_bytes / max(args.steps, 1),
                         "algorithmic_bytes": direct_bytes, "seconds": d_s,
                         "symbolic_ms_per_step": stages.get("direct_symbolic", 0.0) / max(args.steps, 1),
                         "numeric_ms_per_step": stages.get("direct_numeric", 0.0) / max(args.steps, 1),
                         "last_batch": direct_info,
-                        "note": "algorithmic bytes = sorted edge keys of every elimination round read+written once, index "
-                                "lists written once and read once, per gate configuration the edge values of every round, "
-                                "the factor entries and the operands of every star-mesh contribution (starmesh."
-                                "algorithmic_bytes); the stage is latency bound (rounds x small launches), not bandwidth "
-                                "bound; the iterative solvers (--solver cluster: 57 networks/s, equivalent-work rate above "
-                                "the HBM peak because the kernel works out of shared memory) are kept for dense networks"}
+                        "note": "'launch' = one batch (all rounds of both phases); algorithmic bytes per starmesh.algorithmic_bytes: "
+                                "symbolic -- live-edge list read twice and unknowns in play once per round, 16 B per incident "
+                                "entry, 28 B per contribution, 16 B per edge slot; numeric, per gate configuration -- 8 B per "
+                                "slot, 32 B per incident entry, 36 B per contribution, 16 B per target group, 6 vectors.  The "
+                                "stage is a chain of ~45 rounds of short latency-bound passes (random gathers through the "
+                                "hash of stick pairs and the slot values), not a streaming kernel"}
         jt = stages.get("junctions", 0.0) / 1e3
         fp64_peak = eng.fp64_peak_tflops()
         line = {

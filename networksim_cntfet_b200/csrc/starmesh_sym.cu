@@ -105,6 +105,7 @@ struct Sym {
     int32_t *nalive;                   // [B] unknowns left per network
     int32_t *dcount;                   // [B] remaining edges per network (dense tail)
     int32_t *nlive;                    // [MAX_ROUNDS + 2] size of the live list at the start of round r
+    int32_t *nsurv;                    // [MAX_ROUNDS + 2] ... of which survivors of the round before (the fill edges follow)
     HEnt *htab;
     int32_t *pent, *pnext, *gsz, *ghead, *pm, *pa, *pb, *gidx, *goff, *gnew;     // [capI] per item of a round
     int32_t *pptr;                     // [R + 1] first pair of every pivot of the round
@@ -149,6 +150,28 @@ __device__ __forceinline__ int warp_append(int *counter, bool pred) {
     if (lane == leader) base = atomicAdd(counter, __popc(m));
     base = __shfl_sync(~0u, base, leader);
     return pred ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// the same with ONE atomic per CTA (same-address atomics are served one per L2 clock: a counter hit once per
+// warp becomes the bottleneck of a pass over millions of items).  Must be called by all threads of the CTA.
+__device__ __forceinline__ int block_append(int *counter, bool pred, int *s_cnt /* TB / 32 + 1 ints */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(~0u, pred);
+    if (lane == 0) s_cnt[wid] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int tot = 0;
+        for (int w = 0; w < TB / 32; w++) {
+            const int c = s_cnt[w];
+            s_cnt[w] = tot;
+            tot += c;
+        }
+        s_cnt[TB / 32] = tot ? atomicAdd(counter, tot) : 0;
+    }
+    __syncthreads();
+    const int pos = s_cnt[TB / 32] + s_cnt[wid] + __popc(m & ((1u << lane) - 1u));
+    __syncthreads();
+    return pred ? pos : -1;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -456,6 +479,7 @@ __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
 }
 
 __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
+    __shared__ int s_cnt[TB / 32 + 1];
     const cnt_sm_info *info = s.p.info;
     if (info->done | info->error) return;
     const int n = s.nlive[r], ebase = info->rounds[r].ebase;
@@ -463,8 +487,8 @@ __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
     const int2 *Luw = s.luw[r & 1];
     int32_t *Lout = s.live[(r + 1) & 1];
     int2 *Luwout = s.luw[(r + 1) & 1];
-    const int nceil = (n + 31) & ~31;
-    for (int i = blockIdx.x * TB + threadIdx.x; i < nceil; i += gridDim.x * TB) {
+    for (int i0 = blockIdx.x * TB; i0 < n; i0 += gridDim.x * TB) {        // CTA-uniform trip count
+        const int i = i0 + threadIdx.x;
         bool keep = false;
         int e = 0;
         int2 uw = make_int2(0, 0);
@@ -484,7 +508,7 @@ __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
                 keep = mu == -1;           // -2: frozen network, its edges leave the list
             }
         }
-        const int pos = warp_append(&s.nlive[r + 1], keep);
+        const int pos = block_append(&s.nsurv[r + 1], keep, s_cnt);
         if (keep) {
             Lout[pos] = e;
             Luwout[pos] = uw;
@@ -546,7 +570,7 @@ __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
         warp_pivot(s, m, k0, d, s.pptr[ml], s.pptr[ml + 1] - s.pptr[ml], s_sort[wid]);
         if (lane == 0) {
             atomicSub(&s.nalive[s.rnet[s.p.piv[m]]], 1);
-            atomicMax(&info->max_deg, d);
+            if (d > *(volatile int *)&info->max_deg) atomicMax(&info->max_deg, d);
         }
         return;
     }
@@ -593,7 +617,7 @@ __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
         int dmax = d;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(~0u, dmax, o));
-        if (lane == 0 && dmax > 0) atomicMax(&info->max_deg, dmax);
+        if (lane == 0 && dmax > *(volatile int *)&info->max_deg) atomicMax(&info->max_deg, dmax);
     }
 }
 
@@ -686,6 +710,7 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
             atomicOr(&info->error, CNT_SM_ERR_SLOTS);
         } else {
             cnt_sm_round *nx = &info->rounds[r + 1];
+            s.nlive[r + 1] = s.nsurv[r + 1] + nnew;       // survivors first, then the fill edges in slot order
             nx->ebase = rd->ebase + rd->nelim;
             nx->lbase = lbase + nl;
             nx->cbase = cbase + np;
@@ -695,12 +720,9 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
         }
     }
     if (over) return;
-    const int n = np + nl, nceil = (n + 31) & ~31;
-    for (int t = blockIdx.x * TB + threadIdx.x; t < nceil; t += gridDim.x * TB) {
-        bool fresh = false;
-        int slot = -1;
-        int2 uw = make_int2(0, 0);
-        const int z = t < n ? s.gsz[t] : 0;
+    const int n = np + nl, nsurv = s.nsurv[r + 1];
+    for (int t = blockIdx.x * TB + threadIdx.x; t < n; t += gridDim.x * TB) {
+        const int z = s.gsz[t];
         if (z) {
             const int cnt = z & ((1 << 30) - 1);
             if (t < np) {
@@ -728,17 +750,19 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
                     }
                 }
                 HEnt *ent = s.htab + e;
-                slot = ent->slot;
+                int slot = ent->slot;
                 if (slot < 0) {                           // a fill edge: numbered in group order
-                    fresh = true;
-                    slot = sbase + s.gnew[t];
+                    const int rank = s.gnew[t];
+                    slot = sbase + rank;
                     const unsigned long long key = ent->key;
-                    uw = make_int2((int)(key >> 32), (int)(key & 0xFFFFFFFFull));
+                    const int2 uw = make_int2((int)(key >> 32), (int)(key & 0xFFFFFFFFull));
                     ent->slot = slot;
                     s.eu[slot] = uw.x;
                     s.ew[slot] = uw.y;
                     atomicAdd(&s.pri[uw.x], DEG1);
                     atomicAdd(&s.pri[uw.y], DEG1);
+                    s.live[(r + 1) & 1][nsurv + rank] = slot;
+                    s.luw[(r + 1) & 1][nsurv + rank] = uw;
                 }
                 ent->head = -1;
                 s.p.tgt[gi] = slot;
@@ -770,11 +794,6 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
                 s.p.tn[gi] = o;
                 s.p.tptr[gi] = off;
             }
-        }
-        const int pos = warp_append(&s.nlive[r + 1], fresh);
-        if (fresh) {
-            s.live[(r + 1) & 1][pos] = slot;
-            s.luw[(r + 1) & 1][pos] = uw;
         }
     }
 }
@@ -916,7 +935,7 @@ struct WsLayout {
     int64_t eu, ew, lm, live0, live1, luw0, luw1, pri, hoff, rnet, loc, nodes0, nodes1, nalive, pptr, items, sagg, sinc, htab;
     int64_t ones0, ones1;      // [mid, nhead]: memset 0xFF
     int64_t zero0, zero1;      // [blocked, fill, nlive, tickets, sflag]: memset 0
-    int64_t mid, nhead, blocked, fill, nlive, tickets, sflag, dcount;
+    int64_t mid, nhead, blocked, fill, nlive, nsurv, tickets, sflag, dcount;
     int64_t total;
     unsigned hcap;
     int64_t ntiles;
@@ -959,6 +978,7 @@ WsLayout ws_layout(int64_t R, int B, int64_t capS, int64_t capI) {
     L.blocked = take(R, 4);
     L.fill = take(R, 4);
     L.nlive = take(CNT_SM_MAX_ROUNDS + 2, 4);
+    L.nsurv = take(CNT_SM_MAX_ROUNDS + 2, 4);
     L.tickets = take(2 * CNT_SM_MAX_ROUNDS + 8, 4);
     L.sflag = take(L.ntiles, 4);
     L.dcount = take(B, 4);
@@ -1025,7 +1045,7 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
     s.gidx = items + 7 * cap_items; s.goff = items + 8 * cap_items; s.gnew = items + 9 * cap_items;
     s.sagg = (V4 *)(w + L.sagg); s.sinc = (V4 *)(w + L.sinc);
     s.mid = (int32_t *)(w + L.mid); s.nhead = (int32_t *)(w + L.nhead);
-    s.blocked = (int32_t *)(w + L.blocked); s.fill = (int32_t *)(w + L.fill); s.nlive = (int32_t *)(w + L.nlive);
+    s.blocked = (int32_t *)(w + L.blocked); s.fill = (int32_t *)(w + L.fill); s.nlive = (int32_t *)(w + L.nlive); s.nsurv = (int32_t *)(w + L.nsurv);
     s.tickets = (int32_t *)(w + L.tickets); s.sflag = (int32_t *)(w + L.sflag); s.dcount = (int32_t *)(w + L.dcount);
     s.htab = (HEnt *)(w + L.htab);
 
@@ -1068,6 +1088,7 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
                 gl = fit(hr->nlive, 2 * TB);
                 gn = fit(hr->nnodes, TILE);
                 gp = fit(hr->nelim, TB);
+                if (1.5 * scale * hr->nelim <= GRID * (TB / 32)) gp = fit(hr->nelim, TB / 32);      // a warp per pivot
                 gi = fit((double)hr->npairs + hr->nlist, 2 * TB);
             }
             const int gs = gi < gn ? gn : gi;

@@ -129,18 +129,22 @@ class Engine(object):
         self.cluster_compressed = True  # cluster kernel keeps its matrix slice in shared memory (class codes)
         self.last_solver = None
         self.spatial_order = True      # Z-order the unknowns of every network (cnt_assemble_reorder)
-        self.prune = True              # peel dangling sticks off the system (cnt_prune_leaves; exact)
+        self.prune = "auto"            # peel dangling sticks off the system (cnt_prune_leaves; exact): True | False |
+                                       # "auto" = only when an iterative solver is expected (the direct solver eliminates
+                                       # leaves and series sticks in its first rounds at no extra cost; measured:
+                                       # tools/prune_sweep.py)
         self.slab_graph = os.environ.get("CNT_SLAB_GRAPH", "1") != "0"   # solve_sharded: replay blocks of iterations
                                        # (kernels + collectives) as one CUDA graph
         self.direct_auto = True        # solver 'auto' takes the direct solver when the pattern is sparse enough
         self.direct_max_degree = 8.0   # ... i.e. at most this many off-diagonal entries per unknown on average
         self.direct_max_fill = 12.0    # ... and the elimination creates at most this many contributions per edge
-        self.direct_dense_max = 384    # ... and finishes with one dense elimination per network once <= this many unknowns
-                                       # are left in every network (0 = sparse rounds to the end)
+        self.direct_dense_max = 192    # ... and finishes with one dense elimination per network once it has <= this many
+                                       # unknowns left (0 = sparse rounds to the end; <= 224: the dense matrix stays in
+                                       # shared memory)
         self.direct_leak = True        # direct solver: answer the assembled FP64 matrix (rounded diagonal, like the
                                        # iterative solvers and the reference); False = the exact-arithmetic system
-        self.series = True             # eliminate an independent set of series sticks (cnt_series_select; exact;
-                                       # needs prune)
+        self.series = "auto"           # eliminate an independent set of series sticks (cnt_series_select; exact;
+                                       # needs prune): True | False | "auto" (as above)
         self._direct_rounds_hint = 40  # rounds launched before the symbolic phase reads its header back
         self._direct_hint = None       # header of the previous plan (grid sizes of the round kernels)
 
@@ -340,7 +344,9 @@ class Engine(object):
             b.urow = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.roff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
             b.alive = b.attach = None
-            if self.prune and b.S > 0:
+            b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()      # D2H sync (B x 8 ints)
+            prune, series = self._want_reductions(b)
+            if prune and b.S > 0:
                 pws = self._ws(lib.cnt_prune_workspace_bytes(b.S))
                 b.alive = torch.empty(b.S, dtype=torch.uint8, device=self.device)
                 b.attach = torch.empty(b.S, dtype=torch.int32, device=self.device)
@@ -351,7 +357,7 @@ class Engine(object):
                 b.prune_rounds = rounds.value
             b.elim_vid = b.voff = b.va = b.vc = b.ve1 = b.ve2 = None
             b.NV = 0
-            if self.series and b.alive is not None and b.J > 0:
+            if series and b.alive is not None and b.J > 0:
                 sws_ = self._ws(lib.cnt_series_workspace_bytes(b.S))
                 i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
                 b.elim_vid, b.voff, b.va, b.vc, b.ve1, b.ve2 = i32(b.S), i32(b.B + 1), i32(b.S), i32(b.S), i32(b.S), i32(b.S)
@@ -367,7 +373,6 @@ class Engine(object):
                                         _p(b.urow), _p(b.roff), _p(ws), ws.numel(), self.stream_ptr))
             b.h_roff = [int(v) for v in b.roff.cpu().tolist()]          # D2H sync (B+1 ints)
             b.c_roff = _lib.i32_array(b.h_roff)
-            b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()
             b.R = b.h_roff[-1]
             R = b.R
             if self.spatial_order and R > 0 and getattr(b, "length", None) is not None:
@@ -397,6 +402,23 @@ class Engine(object):
                                                 _p(ws), ws.numel(), self.stream_ptr))
             check(lib.cnt_assemble_row_stick(b.B, _p(b.soff), b.S, _p(b.urow), _p(b.row_stick), self.stream_ptr))
         return b
+
+    def _want_reductions(self, b):
+        """(prune, series) for this batch: the "auto" settings apply the exact reductions only when the
+        solve is expected to be iterative -- solver 'cluster' / 'flat', or 'auto' with a junction graph
+        too dense for the direct solver (more than direct_max_degree off-diagonal entries per unknown)"""
+        if self.prune != "auto" and self.series != "auto":
+            return bool(self.prune), bool(self.series)
+        st = b.h_stats
+        perc = st[:, _lib.STAT_PERCOLATING] > 0
+        nodes = int(st[perc, _lib.STAT_NCOMP].sum())
+        edges = int(st[perc, _lib.STAT_ECOMP].sum())
+        direct = self.solver == "direct" or (self.solver == "auto" and self.direct_auto and
+                                              2 * edges <= self.direct_max_degree * max(nodes, 1))
+        auto = not direct
+        prune = auto if self.prune == "auto" else bool(self.prune)
+        series = auto if self.series == "auto" else bool(self.series)
+        return prune, series and prune
 
     def prepare(self, b):
         """junctions -> labels -> pattern (everything that does not depend on the gate)."""

@@ -111,7 +111,7 @@ def test_assembly_matches_oracle(engine, name):
     try:
         b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
     finally:
-        engine.prune = engine.series = True
+        engine.prune = engine.series = "auto"
     gs = GateState(engine, b).set_global(10)
     tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
     sysm = engine.assemble_values(b, [gs], [tab])
@@ -157,12 +157,11 @@ def test_pruned_assembly(engine, name):
     from networksim_cntfet_b200.engine import GateState
     from networksim_cntfet_b200.elements import conductance_table
     g = load_golden(name)
-    assert engine.prune
-    engine.series = False
+    engine.prune, engine.series = True, False
     try:
         b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
     finally:
-        engine.series = True
+        engine.prune = engine.series = "auto"
     gs = GateState(engine, b).set_global(10)
     tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
     sysm = engine.assemble_values(b, [gs], [tab])
@@ -209,8 +208,11 @@ def test_series_assembly(engine, name):
     from networksim_cntfet_b200.engine import GateState
     from networksim_cntfet_b200.elements import conductance_table
     g = load_golden(name)
-    assert engine.prune and engine.series
-    b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    engine.prune = engine.series = True
+    try:
+        b = engine.prepare(engine.batch_from_host([golden_sticks(g)]))
+    finally:
+        engine.prune = engine.series = "auto"
     gs = GateState(engine, b).set_global(10)
     tab = conductance_table(_element(golden_element(g)), int(g["onoffmap"]), gs.levels)
     sysm = engine.assemble_values(b, [gs], [tab])
