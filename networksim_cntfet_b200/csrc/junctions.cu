@@ -6,11 +6,16 @@
 // A stick whose length exceeds RMAX cells is "long" (the two electrodes, length 100, always
 // are): long sticks form a prefix of the length-sorted table and are handled by a dense
 // row kernel (they test every later stick, like the reference's radius-100 KD query).
-// All other sticks are binned by the cell of their centre; the cell kernel gives each
-// stick i (in cell order, so neighbouring threads share neighbourhoods in L1) the cells
-// overlapping [c_i - l_i, c_i + l_i]^2 and tests the sticks j > i found there.
-// Rows (junctions with stick1 == i) are produced by two passes (count, scan, fill) so the
-// output is compact, deterministic and sorted by (network, stick1, stick2).
+// All other sticks are binned by the cell of their centre.  The tile kernel (k_tiles) gives one CTA
+// a tile of 8 x 8 cells: it stages the records of the tile and of the halo its sticks reach into
+// SHARED MEMORY once, flattens the (home stick, candidate) pairs of the tile over all threads
+// (cheap part: j > i and the KD-ball test), compacts the survivors with warp ballot / prefix into
+// a queue, runs the FP64 predicate -- the two IEEE divisions -- on the queue with full warps, and
+// writes the tile's junctions grouped by home stick to a temporary table.  The predicate is
+// evaluated ONCE: after the scan of the row lengths k_place copies every row to its place and
+// orders it by stick2, so the output is compact, deterministic and sorted by
+// (network, stick1, stick2).  If the temporary table overflows (more than ~8 junctions per stick)
+// the rows are recomputed in place by the thread-per-stick kernel k_cells<true> instead.
 #include <vector>
 #include "common.cuh"
 #include "predicate.cuh"
@@ -22,16 +27,24 @@ constexpr int GMAX = 2048;
 constexpr int DENSE_T = 512;     // threads of the dense-row kernel
 constexpr int DENSE_ROWS = 8;    // grid.x of the dense-row kernel (rows strided)
 
-struct __align__(16) StickRec {  // 64 bytes, one per binned stick, in cell order
-    double m, b, xmin, xmax;     // CntLine
+struct __align__(16) RecA {      // 32 bytes: what the cheap tests need (one sector)
     double xc, yc, len;
-    int32_t idx;                 // local post-sort index
-    int32_t gid;                 // global stick id
+    int32_t idx, gid;
 };
+
+constexpr int TILE_C = 8;        // home cells per tile side
+constexpr int CT = 512;          // threads of the tile kernel
+constexpr int CAP_REC = 1024;    // staged records per tile (A + B halves: 64 KB)
+constexpr int CAP_HOME = 256;    // home sticks per batch of a tile
+constexpr int CAP_Q = 2048;      // candidate pairs per chunk = capacity of the survivor queue
+constexpr int CAP_HIT = 1024;    // junctions per batch of home sticks
+constexpr int MAX_RH = TILE_C + 2 * (RMAX + 2);      // rows / columns of the staged region
 
 struct Geo {                     // per-network grid geometry (host computed, uploaded)
     int32_t G;                   // cells per side
     int32_t coff;                // offset of the network's first cell in the global cell array
+    int32_t toff;                // offset of the network's first tile in the global tile list
+    int32_t TG;                  // tiles per side
 };
 
 static int isqrt_i(int64_t v) {
@@ -81,106 +94,398 @@ __global__ void k_bin(int64_t S, const int32_t *__restrict__ soff, int B, const 
                       const int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_fill,
                       const CntLine *__restrict__ line, const double *__restrict__ xc,
                       const double *__restrict__ yc, const double *__restrict__ len,
-                      StickRec *__restrict__ rec) {
+                      RecA *__restrict__ recA, CntLine *__restrict__ recB) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int key = cellkey[s];
     if (key < 0) return;
     int b = cnt::find_segment(soff, B, (int)s);
     int pos = cell_start[key] + atomicAdd(cell_fill + key, 1);
-    CntLine l = line[s];
-    StickRec r;
-    r.m = l.m; r.b = l.b; r.xmin = l.xmin; r.xmax = l.xmax;
+    RecA r;
     r.xc = xc[s]; r.yc = yc[s]; r.len = len[s];
     r.idx = (int)s - soff[b];
     r.gid = (int)s;
-    rec[pos] = r;
+    recA[pos] = r;
+    recB[pos] = line[s];
 }
 
-// ---- cell kernel: one thread per binned stick (home stick i, candidates j > i) ---------
-template <bool FILL>
-__global__ void __launch_bounds__(128) k_cells(int B, const int32_t *__restrict__ soff, const Geo *__restrict__ geo,
-                                               const int32_t *__restrict__ cell_start, int32_t total_cells,
-                                               const StickRec *__restrict__ rec,
-                                               int32_t *__restrict__ jcount, unsigned long long *__restrict__ ntests,
-                                               const int32_t *__restrict__ jstart, const uint8_t *__restrict__ kind,
-                                               int32_t *__restrict__ stick1, int32_t *__restrict__ stick2,
-                                               double *__restrict__ jx, double *__restrict__ jy,
-                                               uint8_t *__restrict__ kind2) {
-    int p = blockIdx.x * blockDim.x + threadIdx.x;
-    int nbinned = __ldg(cell_start + total_cells);
-    bool active = p < nbinned;
-    int cnt = 0;
-    unsigned long long tests = 0;
-    int b = -1;
-    if (active) {
-        StickRec me = rec[p];
-        b = cnt::find_segment(soff, B, me.gid);
-        Geo g = geo[b];
-        CntLine l1{me.m, me.b, me.xmin, me.xmax};
-        double G = (double)g.G;
-        // cells overlapping the bounding square of the ball; 1e-6 cell of slack covers the
-        // rounding of the products (cells are >= 1/2048 wide, the ball test is exact)
-        int cx0 = (int)floor((me.xc - me.len) * G - 1e-6), cx1 = (int)floor((me.xc + me.len) * G + 1e-6);
-        int cy0 = (int)floor((me.yc - me.len) * G - 1e-6), cy1 = (int)floor((me.yc + me.len) * G + 1e-6);
-        cx0 = max(cx0, 0); cy0 = max(cy0, 0);
-        cx1 = min(cx1, g.G - 1); cy1 = min(cy1, g.G - 1);
-        int base = FILL ? jstart[me.gid] : 0;
-        int s0 = soff[b];
-        for (int cy = cy0; cy <= cy1; cy++) {
-            int q0 = __ldg(cell_start + g.coff + cy * g.G + cx0);
-            int q1 = __ldg(cell_start + g.coff + cy * g.G + cx1 + 1);
-            for (int q = q0; q < q1; q++) {
-                const StickRec *o = rec + q;
-                int j = __ldg(&o->idx);
-                if (j <= me.idx) continue;
-                double oxc = __ldg(&o->xc), oyc = __ldg(&o->yc);
-                if (!cnt_in_ball(me.xc, me.yc, me.len, oxc, oyc)) continue;
-                tests++;
-                CntLine l2{__ldg(&o->m), __ldg(&o->b), __ldg(&o->xmin), __ldg(&o->xmax)};
-                double xi, yi;
-                if (cnt_junction(l1, l2, &xi, &yi)) {
-                    if (FILL) {
-                        int w = base + cnt;
-                        stick1[w] = me.idx;
-                        stick2[w] = j;
-                        jx[w] = xi;
-                        jy[w] = yi;
-                        kind2[w] = (uint8_t)(3 * kind[me.gid] + kind[s0 + j]);
-                    }
-                    cnt++;
-                }
-            }
+// cells overlapping the bounding square of the ball of a stick; 1e-6 cell of slack covers the rounding
+// of the products (cells are >= 1/2048 wide, the ball test is exact)
+__device__ __forceinline__ void cell_range(const RecA &me, int G, int &cx0, int &cx1, int &cy0, int &cy1) {
+    const double g = (double)G;
+    cx0 = (int)floor((me.xc - me.len) * g - 1e-6); cx1 = (int)floor((me.xc + me.len) * g + 1e-6);
+    cy0 = (int)floor((me.yc - me.len) * g - 1e-6); cy1 = (int)floor((me.yc + me.len) * g + 1e-6);
+    cx0 = max(cx0, 0); cy0 = max(cy0, 0);
+    cx1 = min(cx1, G - 1); cy1 = min(cy1, G - 1);
+}
+
+// ---- tile kernel: one CTA per tile of TILE_C x TILE_C cells ---------------------------------
+struct Hit {
+    int32_t hr;                  // home stick (batch-local) << 16 | arrival rank inside its row
+    int32_t j;
+    double x, y;
+};
+
+__global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo,
+                                              const int32_t *__restrict__ cell_start, const RecA *__restrict__ gA,
+                                              const CntLine *__restrict__ gB, int32_t *__restrict__ jcount,
+                                              int32_t *__restrict__ jtmp, unsigned long long *__restrict__ ntests,
+                                              int32_t *__restrict__ tj, double *__restrict__ tx, double *__restrict__ ty,
+                                              int64_t cap_tmp, int32_t *__restrict__ ntmp, int32_t *__restrict__ errflag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    RecA *sA = (RecA *)smem_raw;                                  // [CAP_REC]
+    CntLine *sB = (CntLine *)(sA + CAP_REC);                      // [CAP_REC]
+    Hit *s_hit = (Hit *)(sB + CAP_REC);                           // [CAP_HIT]
+    int32_t *s_q = (int32_t *)(s_hit + CAP_HIT);                  // [CAP_Q] survivor queue: home << 23 | region index
+    int32_t *s_cs = s_q + CAP_Q;                                  // [MAX_RH * (MAX_RH + 1)] cell starts (region index)
+    int32_t *s_gq0 = s_cs + MAX_RH * (MAX_RH + 1);                // [MAX_RH] first global record of every region row
+    int32_t *s_rb = s_gq0 + MAX_RH;                               // [MAX_RH + 1] first region index of every region row
+    int32_t *s_pre = s_rb + MAX_RH + 1;                           // [CAP_HOME + 1] first pair of every home stick
+    int32_t *s_rng = s_pre + CAP_HOME + 1;                        // [CAP_HOME] packed cell range (region-relative)
+    int32_t *s_cnt = s_rng + CAP_HOME;                            // [CAP_HOME + 1] junctions per home stick / row offsets
+    int32_t *s_hq = s_cnt + CAP_HOME + 1;                         // [CAP_HOME] region index of every home stick
+    __shared__ int s_red[8];
+    __shared__ int s_nq, s_nhit, s_base, s_warp[CT / 32];
+    __shared__ unsigned long long s_tests;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    int b = 0;
+    {
+        int lo = 0, hi = B;                                       // geo[lo].toff <= blockIdx.x < geo[hi].toff
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (geo[mid].toff <= (int)blockIdx.x) lo = mid; else hi = mid;
         }
-        if (FILL) {
-            // order the row by stick2 (rows are short: insertion sort in place)
-            for (int a = 1; a < cnt; a++) {
-                int w = base + a;
-                int kj = stick2[w];
-                double kx = jx[w], ky = jy[w];
-                uint8_t kk = kind2[w];
-                int c = w - 1;
-                while (c >= base && stick2[c] > kj) {
-                    stick2[c + 1] = stick2[c]; jx[c + 1] = jx[c]; jy[c + 1] = jy[c]; kind2[c + 1] = kind2[c];
-                    c--;
-                }
-                stick2[c + 1] = kj; jx[c + 1] = kx; jy[c + 1] = ky; kind2[c + 1] = kk;
-            }
-        } else {
-            jcount[me.gid] = cnt;
+        b = lo;
+    }
+    const Geo g = geo[b];
+    const int tloc = blockIdx.x - g.toff, tyi = tloc / g.TG, txi = tloc - tyi * g.TG;
+    const int hx0 = txi * TILE_C, hy0 = tyi * TILE_C;
+    const int hx1 = min(hx0 + TILE_C, g.G) - 1, hy1 = min(hy0 + TILE_C, g.G) - 1;
+    const int32_t *cs = cell_start + g.coff;
+    // home sticks: the records of the home cells, row by row
+    int nh_row[TILE_C + 1];
+    int nhome = 0;
+#pragma unroll
+    for (int r = 0; r < TILE_C; r++) {
+        nh_row[r] = nhome;
+        if (hy0 + r <= hy1) nhome += __ldg(cs + (hy0 + r) * g.G + hx1 + 1) - __ldg(cs + (hy0 + r) * g.G + hx0);
+    }
+    nh_row[TILE_C] = nhome;
+    if (nhome == 0) return;
+    auto home_q = [&](int h) {                                    // global record index of home stick h of the tile
+        int r = 0;
+#pragma unroll
+        for (int k = 1; k < TILE_C; k++) r += h >= nh_row[k];
+        return __ldg(cs + (hy0 + r) * g.G + hx0) + (h - nh_row[r]);
+    };
+    // region = union of the cell ranges of the home sticks
+    int rx0 = g.G, rx1 = -1, ry0 = g.G, ry1 = -1;
+    for (int h = tid; h < nhome; h += CT) {
+        const RecA me = gA[home_q(h)];
+        int cx0, cx1, cy0, cy1;
+        cell_range(me, g.G, cx0, cx1, cy0, cy1);
+        rx0 = min(rx0, cx0); rx1 = max(rx1, cx1); ry0 = min(ry0, cy0); ry1 = max(ry1, cy1);
+    }
+    if (tid == 0) {
+        s_red[0] = g.G; s_red[1] = -1; s_red[2] = g.G; s_red[3] = -1;
+        s_tests = 0ull;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        rx0 = min(rx0, __shfl_xor_sync(~0u, rx0, o)); rx1 = max(rx1, __shfl_xor_sync(~0u, rx1, o));
+        ry0 = min(ry0, __shfl_xor_sync(~0u, ry0, o)); ry1 = max(ry1, __shfl_xor_sync(~0u, ry1, o));
+    }
+    if (lane == 0) {
+        atomicMin(&s_red[0], rx0); atomicMax(&s_red[1], rx1); atomicMin(&s_red[2], ry0); atomicMax(&s_red[3], ry1);
+    }
+    __syncthreads();
+    rx0 = s_red[0]; rx1 = s_red[1]; ry0 = s_red[2]; ry1 = s_red[3];
+    const int RW = rx1 - rx0 + 1, RH = ry1 - ry0 + 1;            // <= MAX_RH by construction (len * G <= RMAX)
+    // region rows: global start, region-index start; cell starts as region indices
+    if (tid < RH) s_gq0[tid] = __ldg(cs + (ry0 + tid) * g.G + rx0);
+    __syncthreads();
+    if (tid == 0) {
+        int acc = 0;
+        for (int r = 0; r < RH; r++) {
+            s_rb[r] = acc;
+            acc += __ldg(cs + (ry0 + r) * g.G + rx1 + 1) - s_gq0[r];
+        }
+        s_rb[RH] = acc;
+    }
+    __syncthreads();
+    const int nrec = s_rb[RH];
+    for (int k = tid; k < RH * (RW + 1); k += CT) {
+        const int r = k / (RW + 1), c = k - r * (RW + 1);
+        s_cs[k] = s_rb[r] + (__ldg(cs + (ry0 + r) * g.G + rx0 + c) - s_gq0[r]);
+    }
+    const bool staged = nrec <= CAP_REC;
+    if (staged) {
+        for (int k = tid; k < nrec; k += CT) {
+            int r = 0;
+            while (k >= s_rb[r + 1]) r++;
+            const int q = s_gq0[r] + (k - s_rb[r]);
+            sA[k] = gA[q];
+            sB[k] = gB[q];
         }
     }
-    if (!FILL) {
-        // per-network test counter: warp-aggregate when the warp sits in one network
-        int b0 = __shfl_sync(0xffffffffu, b, 0);
-        if (__all_sync(0xffffffffu, b == b0 || !active)) {
-            unsigned long long t = tests;
+    __syncthreads();
+    // record accessors: region index -> record (shared memory when staged, global memory otherwise)
+    auto recA = [&](int v) -> RecA {
+        if (staged) return sA[v];
+        int r = 0;
+        while (v >= s_rb[r + 1]) r++;
+        return gA[s_gq0[r] + (v - s_rb[r])];
+    };
+    auto recB = [&](int v) -> CntLine {
+        if (staged) return sB[v];
+        int r = 0;
+        while (v >= s_rb[r + 1]) r++;
+        return gB[s_gq0[r] + (v - s_rb[r])];
+    };
+    unsigned long long tests = 0;
+    for (int hb = 0; hb < nhome; hb += CAP_HOME) {               // batches of home sticks
+        const int nb = min(CAP_HOME, nhome - hb);
+        // candidate count of every home stick
+        int ncand = 0;
+        if (tid < nb) {
+            const int q = home_q(hb + tid);
+            // region index of the home stick: its cell row inside the region
+            int hr = 0;
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_down_sync(0xffffffffu, t, o);
-            if ((threadIdx.x & 31) == 0 && t && b0 >= 0) atomicAdd(ntests + b0, t);
-        } else if (active && tests) {
-            atomicAdd(ntests + b, tests);
+            for (int k = 1; k < TILE_C; k++) hr += (hb + tid) >= nh_row[k];
+            const int v = s_rb[hy0 + hr - ry0] + (q - s_gq0[hy0 + hr - ry0]);
+            s_hq[tid] = v;
+            const RecA me = recA(v);
+            int cx0, cx1, cy0, cy1;
+            cell_range(me, g.G, cx0, cx1, cy0, cy1);
+            for (int cy = cy0; cy <= cy1; cy++)
+                ncand += s_cs[(cy - ry0) * (RW + 1) + (cx1 + 1 - rx0)] - s_cs[(cy - ry0) * (RW + 1) + (cx0 - rx0)];
+            s_rng[tid] = (cx0 - rx0) | ((cx1 - rx0) << 8) | ((cy0 - ry0) << 16) | ((cy1 - ry0) << 24);
+            s_cnt[tid] = 0;
         }
+        // exclusive scan of the counts over the batch (nb <= CAP_HOME <= CT)
+        int inc = tid < nb ? ncand : 0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(~0u, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_warp[wid] = inc;
+        if (tid == 0) s_nhit = 0;
+        __syncthreads();
+        if (wid == 0) {
+            int w = lane < CT / 32 ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(~0u, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < CT / 32) s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        if (tid < nb) s_pre[tid] = s_warp[wid] + inc - ncand;
+        if (tid == nb - 1) s_pre[nb] = s_warp[wid] + inc;
+        __syncthreads();
+        const int P = s_pre[nb];
+        for (int p0 = 0; p0 < P; p0 += CAP_Q) {                  // chunks of candidate pairs
+            if (tid == 0) s_nq = 0;
+            __syncthreads();
+            // phase 1 (cheap): j > i and the KD ball; survivors -> queue (warp ballot + one shared atomic per warp)
+            const int pend = min(P, p0 + CAP_Q);
+            for (int pp = p0 + tid; pp < ((pend + 31) & ~31); pp += CT) {
+                bool pass = false;
+                int entry = 0;
+                if (pp < pend) {
+                    int lo = 0, hi = nb;                          // s_pre[lo] <= pp < s_pre[hi]
+                    while (hi - lo > 1) {
+                        const int mid = (lo + hi) >> 1;
+                        if (s_pre[mid] <= pp) lo = mid; else hi = mid;
+                    }
+                    const int h = lo, rng = s_rng[h];
+                    const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
+                    int c = pp - s_pre[h], v = -1;
+                    for (int cy = cy0; cy <= cy1; cy++) {
+                        const int a0 = s_cs[cy * (RW + 1) + cx0], a1 = s_cs[cy * (RW + 1) + cx1 + 1];
+                        if (c < a1 - a0) {
+                            v = a0 + c;
+                            break;
+                        }
+                        c -= a1 - a0;
+                    }
+                    const RecA me = recA(s_hq[h]), o = recA(v);
+                    pass = o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc);
+                    entry = (h << 23) | v;
+                }
+                const unsigned m = __ballot_sync(~0u, pass);
+                if (m) {
+                    int base = 0;
+                    if (lane == __ffs(m) - 1) base = atomicAdd(&s_nq, __popc(m));
+                    base = __shfl_sync(~0u, base, __ffs(m) - 1);
+                    if (pass) {
+                        s_q[base + __popc(m & ((1u << lane) - 1u))] = entry;
+                        tests++;
+                    }
+                }
+            }
+            __syncthreads();
+            // phase 2 (FP64 predicate) on the compacted queue: full warps
+            const int nq = s_nq;
+            for (int k = tid; k < nq; k += CT) {
+                const int entry = s_q[k], h = entry >> 23, v = entry & ((1 << 23) - 1);
+                const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
+                double xi, yi;
+                if (cnt_junction(l1, l2, &xi, &yi)) {
+                    const int rank = atomicAdd(&s_cnt[h], 1);
+                    const int at = atomicAdd(&s_nhit, 1);
+                    if (at < CAP_HIT) {
+                        Hit hh;
+                        hh.hr = (h << 16) | (rank & 0xFFFF);
+                        hh.j = recA(v).idx;
+                        hh.x = xi;
+                        hh.y = yi;
+                        s_hit[at] = hh;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // rows of the batch: offsets (exclusive scan of s_cnt), space in the temporary table, write-out
+        const int nhit = s_nhit;
+        int cnt_h = tid < nb ? s_cnt[tid] : 0;
+        int inc2 = cnt_h;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int t = __shfl_up_sync(~0u, inc2, o);
+            if (lane >= o) inc2 += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_warp[wid] = inc2;
+        __syncthreads();
+        if (wid == 0) {
+            int w = lane < CT / 32 ? s_warp[lane] : 0, wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int t = __shfl_up_sync(~0u, wi, o);
+                if (lane >= o) wi += t;
+            }
+            if (lane < CT / 32) s_warp[lane] = wi - w;
+        }
+        __syncthreads();
+        const int roff = s_warp[wid] + inc2 - cnt_h;
+        if (tid == 0) {
+            bool ok = nhit <= CAP_HIT;
+            int base = -1;
+            if (ok && nhit > 0) {
+                base = atomicAdd(ntmp, nhit);
+                if ((int64_t)base + nhit > cap_tmp) ok = false;
+            }
+            if (!ok) atomicOr(errflag, 2);                        // rows will be recomputed by k_cells<true>
+            s_base = ok ? base : -1;
+        }
+        __syncthreads();
+        const int base = s_base;
+        if (tid < nb) {
+            const int gid = recA(s_hq[tid]).gid;
+            jcount[gid] = cnt_h;
+            jtmp[gid] = base >= 0 ? base + roff : -1;
+            s_cnt[tid] = roff;                                    // row offset from now on
+        }
+        __syncthreads();
+        if (base >= 0) {
+            for (int k = tid; k < nhit; k += CT) {
+                const Hit hh = s_hit[k];
+                const int at = base + s_cnt[hh.hr >> 16] + (hh.hr & 0xFFFF);
+                tj[at] = hh.j;
+                tx[at] = hh.x;
+                ty[at] = hh.y;
+            }
+        }
+        __syncthreads();
+    }
+    // candidate pairs inside the ball (the reference's KD-tree query count), one atomic per CTA
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tests += __shfl_down_sync(~0u, tests, o);
+    if (lane == 0 && tests) atomicAdd(&s_tests, tests);
+    __syncthreads();
+    if (tid == 0 && s_tests) atomicAdd(ntests + b, s_tests);
+}
+
+// every binned stick's row from the temporary table to its place, ordered by stick2
+__global__ void k_place(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ jtmp,
+                        const int32_t *__restrict__ jstart /* [S + 1] */,
+                        const int32_t *__restrict__ tj, const double *__restrict__ tx, const double *__restrict__ ty,
+                        const uint8_t *__restrict__ kind, const int32_t *__restrict__ errflag,
+                        int32_t *__restrict__ stick1, int32_t *__restrict__ stick2, double *__restrict__ jx,
+                        double *__restrict__ jy, uint8_t *__restrict__ kind2) {
+    if (*errflag & 2) return;                                     // temporary table overflowed: k_cells<true> fills
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const int t0 = jtmp[s], base = jstart[s], cnt = jstart[s + 1] - base;
+    if (t0 < 0 || cnt == 0) return;                               // long stick (k_dense) or empty row
+    const int b = cnt::find_segment(soff, B, (int)s);
+    const int s0 = soff[b], i = (int)s - s0;
+    const uint8_t ki = kind[s];
+    for (int a = 0; a < cnt; a++) {                               // insertion by stick2 (rows are short)
+        const int kj = tj[t0 + a];
+        const double kx = tx[t0 + a], ky = ty[t0 + a];
+        int c = base + a - 1;
+        while (c >= base && stick2[c] > kj) {
+            stick2[c + 1] = stick2[c]; jx[c + 1] = jx[c]; jy[c + 1] = jy[c];
+            c--;
+        }
+        stick2[c + 1] = kj; jx[c + 1] = kx; jy[c + 1] = ky;
+    }
+    for (int a = 0; a < cnt; a++) {
+        stick1[base + a] = i;
+        kind2[base + a] = (uint8_t)(3 * ki + kind[s0 + stick2[base + a]]);
+    }
+}
+
+// ---- fallback: one thread per binned stick recomputes its row in place (temporary table overflowed) ----
+__global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__restrict__ soff, const Geo *__restrict__ geo,
+                                                    const int32_t *__restrict__ cell_start, int32_t total_cells,
+                                                    const RecA *__restrict__ recA, const CntLine *__restrict__ recB,
+                                                    const int32_t *__restrict__ errflag,
+                                                    const int32_t *__restrict__ jstart, const uint8_t *__restrict__ kind,
+                                                    int32_t *__restrict__ stick1, int32_t *__restrict__ stick2,
+                                                    double *__restrict__ jx, double *__restrict__ jy,
+                                                    uint8_t *__restrict__ kind2) {
+    if (!(*errflag & 2)) return;
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    int nbinned = __ldg(cell_start + total_cells);
+    if (p >= nbinned) return;
+    const RecA me = recA[p];
+    const int b = cnt::find_segment(soff, B, me.gid);
+    const Geo g = geo[b];
+    const CntLine l1 = recB[p];
+    int cx0, cx1, cy0, cy1;
+    cell_range(me, g.G, cx0, cx1, cy0, cy1);
+    const int base = jstart[me.gid], s0 = soff[b];
+    int cnt = 0;
+    for (int cy = cy0; cy <= cy1; cy++) {
+        const int q0 = __ldg(cell_start + g.coff + cy * g.G + cx0);
+        const int q1 = __ldg(cell_start + g.coff + cy * g.G + cx1 + 1);
+        for (int q = q0; q < q1; q++) {
+            const RecA o = recA[q];
+            if (o.idx <= me.idx || !cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc)) continue;
+            double xi, yi;
+            if (cnt_junction(l1, recB[q], &xi, &yi)) {
+                // insertion by stick2 (rows are short)
+                int c = base + cnt - 1;
+                while (c >= base && stick2[c] > o.idx) {
+                    stick2[c + 1] = stick2[c]; jx[c + 1] = jx[c]; jy[c + 1] = jy[c];
+                    c--;
+                }
+                stick2[c + 1] = o.idx; jx[c + 1] = xi; jy[c + 1] = yi;
+                cnt++;
+            }
+        }
+    }
+    for (int a = 0; a < cnt; a++) {
+        stick1[base + a] = me.idx;
+        kind2[base + a] = (uint8_t)(3 * kind[me.gid] + kind[s0 + stick2[base + a]]);
     }
 }
 
@@ -253,51 +558,72 @@ __global__ void k_joff(int B, const int32_t *__restrict__ soff, const int32_t *_
 }
 
 struct Plan {
-    int64_t S, total_cells;
+    int64_t S, total_cells, total_tiles, cap_tmp;
     std::vector<Geo> geo;
     // workspace carve-up
     Geo *d_geo;
     CntLine *line;
-    StickRec *rec;
-    int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag;
+    RecA *recA;
+    CntLine *recB;
+    int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag, *ntmp, *jtmp, *tj;
+    double *tx, *ty;
     void *scan_ws;
     int64_t scan_ws_bytes;
 };
 
+static int64_t tmp_capacity(int64_t S) { return 8 * S + 65536; }
+
 static int64_t plan_bytes(int B, int64_t S, int64_t total_cells) {
     using cnt::ws_bytes_for;
-    return ws_bytes_for(B, sizeof(Geo)) + ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, sizeof(StickRec)) +
-           ws_bytes_for(S, 4) + ws_bytes_for(total_cells + 1, 4) + ws_bytes_for(total_cells + 1, 4) +
-           ws_bytes_for(B, 4) + ws_bytes_for(1, 4) + cnt_scan_workspace_bytes(total_cells + 1);
+    const int64_t ct = tmp_capacity(S);
+    return ws_bytes_for(B + 1, sizeof(Geo)) + ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, sizeof(RecA)) +
+           ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, 4) + ws_bytes_for(total_cells + 1, 4) +
+           ws_bytes_for(total_cells + 1, 4) + ws_bytes_for(B, 4) + ws_bytes_for(2, 4) + ws_bytes_for(S + 1, 4) +
+           ws_bytes_for(ct, 4) + 2 * ws_bytes_for(ct, 8) + cnt_scan_workspace_bytes(total_cells + 1);
 }
 
-static void make_geo(int B, const int32_t *h_soff, std::vector<Geo> &geo, int64_t &total_cells) {
-    geo.resize(B);
+static void make_geo(int B, const int32_t *h_soff, std::vector<Geo> &geo, int64_t &total_cells, int64_t &total_tiles) {
+    geo.resize(B + 1);
     total_cells = 0;
+    total_tiles = 0;
     for (int b = 0; b < B; b++) {
         int g = grid_dim_for(h_soff[b + 1] - h_soff[b]);
         geo[b].G = g;
         geo[b].coff = (int32_t)total_cells;
+        geo[b].TG = (g + TILE_C - 1) / TILE_C;
+        geo[b].toff = (int32_t)total_tiles;
         total_cells += (int64_t)g * g;
+        total_tiles += (int64_t)geo[b].TG * geo[b].TG;
     }
+    geo[B].G = 0;
+    geo[B].coff = (int32_t)total_cells;
+    geo[B].TG = 0;
+    geo[B].toff = (int32_t)total_tiles;
 }
 
 static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_bytes) {
     p.S = h_soff[B];
-    make_geo(B, h_soff, p.geo, p.total_cells);
-    if (p.total_cells >= (int64_t)1 << 31) {
+    make_geo(B, h_soff, p.geo, p.total_cells, p.total_tiles);
+    if (p.total_cells >= (int64_t)1 << 31 || p.total_tiles >= (int64_t)1 << 31) {
         cnt::set_error("too many cells");
         return CNT_EINVAL;
     }
+    p.cap_tmp = tmp_capacity(p.S);
     cnt::Workspace w(ws, ws_bytes);
-    p.d_geo = w.take<Geo>(B);
+    p.d_geo = w.take<Geo>(B + 1);
     p.line = w.take<CntLine>(p.S);
-    p.rec = w.take<StickRec>(p.S);
+    p.recA = w.take<RecA>(p.S);
+    p.recB = w.take<CntLine>(p.S);
     p.cellkey = w.take<int32_t>(p.S);
     p.cell_count = w.take<int32_t>(p.total_cells + 1);
     p.cell_fill = w.take<int32_t>(p.total_cells + 1);
     p.nlong = w.take<int32_t>(B);
-    p.errflag = w.take<int32_t>(1);
+    p.errflag = w.take<int32_t>(2);
+    p.ntmp = p.errflag ? p.errflag + 1 : nullptr;
+    p.jtmp = w.take<int32_t>(p.S + 1);
+    p.tj = w.take<int32_t>(p.cap_tmp);
+    p.tx = w.take<double>(p.cap_tmp);
+    p.ty = w.take<double>(p.cap_tmp);
     p.scan_ws_bytes = cnt_scan_workspace_bytes(p.total_cells + 1);
     p.scan_ws = w.take<char>(p.scan_ws_bytes);
     if (!p.scan_ws) {
@@ -307,13 +633,19 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
     }
     return CNT_OK;
 }
+
+static size_t tiles_smem() {
+    return (size_t)CAP_REC * (sizeof(RecA) + sizeof(CntLine)) + (size_t)CAP_HIT * sizeof(Hit) +
+           4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
+                CAP_HOME);
+}
 }  // namespace
 
 extern "C" int64_t cnt_junction_workspace_bytes(int B, const int32_t *h_soff) {
     if (B <= 0 || !h_soff) return 0;
     std::vector<Geo> geo;
-    int64_t tc;
-    make_geo(B, h_soff, geo, tc);
+    int64_t tc, tt;
+    make_geo(B, h_soff, geo, tc, tt);
     return plan_bytes(B, h_soff[B], tc);
 }
 
@@ -332,24 +664,29 @@ extern "C" int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_s
         CNT_CUDA(cudaMemsetAsync(ntests, 0, sizeof(unsigned long long) * B, st));
         return CNT_OK;
     }
-    CNT_CUDA(cudaMemcpyAsync(p.d_geo, p.geo.data(), sizeof(Geo) * B, cudaMemcpyHostToDevice, st));
+    CNT_CUDA(cudaMemcpyAsync(p.d_geo, p.geo.data(), sizeof(Geo) * (B + 1), cudaMemcpyHostToDevice, st));
     CNT_CUDA(cudaMemsetAsync(p.cell_count, 0, 4 * (p.total_cells + 1), st));
     CNT_CUDA(cudaMemsetAsync(p.cell_fill, 0, 4 * (p.total_cells + 1), st));
     CNT_CUDA(cudaMemsetAsync(p.nlong, 0, 4 * B, st));
-    CNT_CUDA(cudaMemsetAsync(p.errflag, 0, 4, st));
+    CNT_CUDA(cudaMemsetAsync(p.errflag, 0, 8, st));
     CNT_CUDA(cudaMemsetAsync(ntests, 0, sizeof(unsigned long long) * B, st));
     CNT_CUDA(cudaMemsetAsync(jcount, 0, 4 * (p.S + 1), st));
+    CNT_CUDA(cudaMemsetAsync(p.jtmp, 0xFF, 4 * (p.S + 1), st));
     k_prep<<<cnt::grid_for(p.S, 256), 256, 0, st>>>(B, soff, p.d_geo, p.S, xa, ya, xb, yb, xc, yc, length, p.line,
                                                     p.cellkey, p.cell_count, p.nlong, p.errflag);
     CNT_LAUNCHED();
     rc = cnt_exclusive_scan_i32(p.cell_count, p.cell_count, p.total_cells, 1, p.scan_ws, p.scan_ws_bytes, stream);
     if (rc) return rc;
     k_bin<<<cnt::grid_for(p.S, 256), 256, 0, st>>>(p.S, soff, B, p.cellkey, p.cell_count, p.cell_fill, p.line, xc, yc,
-                                                   length, p.rec);
+                                                   length, p.recA, p.recB);
     CNT_LAUNCHED();
-    k_cells<false><<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells,
-                                                            p.rec, jcount, ntests, nullptr, nullptr, nullptr, nullptr,
-                                                            nullptr, nullptr, nullptr);
+    static bool attr_set = false;
+    if (!attr_set) {
+        CNT_CUDA(cudaFuncSetAttribute(k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles_smem()));
+        attr_set = true;
+    }
+    k_tiles<<<(unsigned)p.total_tiles, CT, tiles_smem(), st>>>(B, p.d_geo, p.cell_count, p.recA, p.recB, jcount, p.jtmp,
+                                                               ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag);
     CNT_LAUNCHED();
     k_dense<false><<<dim3(DENSE_ROWS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, jcount, ntests,
                                                             nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
@@ -373,9 +710,11 @@ extern "C" int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_so
     k_joff<<<cnt::grid_for(B + 1, 128), 128, 0, st>>>(B, soff, jstart, joff);
     CNT_LAUNCHED();
     if (p.S == 0 || J == 0) return CNT_OK;
-    k_cells<true><<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells,
-                                                           p.rec, nullptr, nullptr, jstart, kind, stick1, stick2, jx,
-                                                           jy, kind2);
+    k_place<<<cnt::grid_for(p.S, 256), 256, 0, st>>>(B, soff, p.S, p.jtmp, jstart, p.tj, p.tx, p.ty, kind, p.errflag, stick1,
+                                                     stick2, jx, jy, kind2);
+    CNT_LAUNCHED();
+    k_cells_fill<<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells, p.recA,
+                                                          p.recB, p.errflag, jstart, kind, stick1, stick2, jx, jy, kind2);
     CNT_LAUNCHED();
     k_dense<true><<<dim3(DENSE_ROWS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, nullptr, nullptr,
                                                            jstart, kind, stick1, stick2, jx, jy, kind2);

@@ -304,8 +304,9 @@ class Engine(object):
             off = flagp.value - b._jws.data_ptr()
             # one small D2H: total junction count + sortedness flag
             total = int(jstart[b.S].item())
-            unsorted = int(b._jws[off:off + 4].view(torch.int32).item())
-            if unsorted:
+            flag = int(b._jws[off:off + 4].view(torch.int32).item())
+            b.junction_rows_recomputed = bool(flag & 2)      # temporary junction table overflowed: slower fill path
+            if flag & 1:
                 raise _lib.CntError("stick table is not sorted by length descending (netsim.py:133)")
             b.J = total
             b.jstart = jstart
