@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     int32_t *s_rng = s_pre + CAP_HOME + 1;                        // [CAP_HOME] packed cell range (region-relative)
     int32_t *s_cnt = s_rng + CAP_HOME;                            // [CAP_HOME + 1] junctions per home stick / row offsets
     int32_t *s_hq = s_cnt + CAP_HOME + 1;                         // [CAP_HOME] region index of every home stick
+    int32_t *s_blk = s_hq + CAP_HOME;                             // [CAP_Q / 32] home stick of every 32nd pair of a chunk
     __shared__ int s_red[8];
     __shared__ int s_nq, s_nhit, s_base, s_warp[CT / 32];
     __shared__ unsigned long long s_tests;
@@ -164,20 +165,31 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     const int hx1 = min(hx0 + TILE_C, g.G) - 1, hy1 = min(hy0 + TILE_C, g.G) - 1;
     const int32_t *cs = cell_start + g.coff;
     // home sticks: the records of the home cells, row by row
-    int nh_row[TILE_C + 1];
-    int nhome = 0;
-#pragma unroll
-    for (int r = 0; r < TILE_C; r++) {
-        nh_row[r] = nhome;
-        if (hy0 + r <= hy1) nhome += __ldg(cs + (hy0 + r) * g.G + hx1 + 1) - __ldg(cs + (hy0 + r) * g.G + hx0);
+    __shared__ int s_nhrow[TILE_C + 1], s_hq0[TILE_C];
+    if (tid == 0) {
+        int acc = 0;
+        for (int r = 0; r < TILE_C; r++) {
+            s_nhrow[r] = acc;
+            s_hq0[r] = 0;
+            if (hy0 + r <= hy1) {
+                s_hq0[r] = __ldg(cs + (hy0 + r) * g.G + hx0);
+                acc += __ldg(cs + (hy0 + r) * g.G + hx1 + 1) - s_hq0[r];
+            }
+        }
+        s_nhrow[TILE_C] = acc;
     }
-    nh_row[TILE_C] = nhome;
+    __syncthreads();
+    const int nhome = s_nhrow[TILE_C];
     if (nhome == 0) return;
-    auto home_q = [&](int h) {                                    // global record index of home stick h of the tile
+    auto home_row = [&](int h) {
         int r = 0;
 #pragma unroll
-        for (int k = 1; k < TILE_C; k++) r += h >= nh_row[k];
-        return __ldg(cs + (hy0 + r) * g.G + hx0) + (h - nh_row[r]);
+        for (int k = 1; k < TILE_C; k++) r += h >= s_nhrow[k];
+        return r;
+    };
+    auto home_q = [&](int h) {                                    // global record index of home stick h of the tile
+        const int r = home_row(h);
+        return s_hq0[r] + (h - s_nhrow[r]);
     };
     // region = union of the cell ranges of the home sticks
     int rx0 = g.G, rx1 = -1, ry0 = g.G, ry1 = -1;
@@ -252,9 +264,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         if (tid < nb) {
             const int q = home_q(hb + tid);
             // region index of the home stick: its cell row inside the region
-            int hr = 0;
-#pragma unroll
-            for (int k = 1; k < TILE_C; k++) hr += (hb + tid) >= nh_row[k];
+            const int hr = home_row(hb + tid);
             const int v = s_rb[hy0 + hr - ry0] + (q - s_gq0[hy0 + hr - ry0]);
             s_hq[tid] = v;
             const RecA me = recA(v);
@@ -291,6 +301,11 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         const int P = s_pre[nb];
         for (int p0 = 0; p0 < P; p0 += CAP_Q) {                  // chunks of candidate pairs
             if (tid == 0) s_nq = 0;
+            // s_blk[k] = home stick owning pair p0 + 32 k: every home stick fills the blocks that start inside its range
+            if (tid < nb) {
+                const int a = max(s_pre[tid], p0), e = min(s_pre[tid + 1], min(P, p0 + CAP_Q));
+                for (int k = (a - p0 + 31) >> 5; p0 + 32 * k < e; k++) s_blk[k] = tid;
+            }
             __syncthreads();
             // phase 1 (cheap): j > i and the KD ball; survivors -> queue (warp ballot + one shared atomic per warp)
             const int pend = min(P, p0 + CAP_Q);
@@ -298,12 +313,9 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                 bool pass = false;
                 int entry = 0;
                 if (pp < pend) {
-                    int lo = 0, hi = nb;                          // s_pre[lo] <= pp < s_pre[hi]
-                    while (hi - lo > 1) {
-                        const int mid = (lo + hi) >> 1;
-                        if (s_pre[mid] <= pp) lo = mid; else hi = mid;
-                    }
-                    const int h = lo, rng = s_rng[h];
+                    int h = s_blk[(pp - p0) >> 5];                // home stick of the first pair of this warp's 32 pairs
+                    while (s_pre[h + 1] <= pp) h++;               // ... a few steps further for this lane
+                    const int rng = s_rng[h];
                     const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
                     int c = pp - s_pre[h], v = -1;
                     for (int cy = cy0; cy <= cy1; cy++) {
@@ -637,7 +649,7 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
 static size_t tiles_smem() {
     return (size_t)CAP_REC * (sizeof(RecA) + sizeof(CntLine)) + (size_t)CAP_HIT * sizeof(Hit) +
            4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
-                CAP_HOME);
+                CAP_HOME + CAP_Q / 32);
 }
 }  // namespace
 
