@@ -52,79 +52,126 @@ __global__ void k_uf_union(int B, const int32_t *__restrict__ soff, const int32_
     }
 }
 
+// every stick2 of a junction starts under its smallest stick1 (stick1 < stick2 in every row of the table): most of
+// the forest exists before the first find, the union pass only has to join what is left
+__global__ void k_uf_hook_min(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff, int64_t J,
+                              const int32_t *__restrict__ stick1, const int32_t *__restrict__ stick2, int32_t *parent,
+                              uint8_t *__restrict__ hasj) {
+    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= J) return;
+    int b = cnt::find_segment(joff, B, (int)e);
+    int s0 = soff[b];
+    int a = s0 + stick1[e], c = s0 + stick2[e];
+    hasj[a] = 1;
+    hasj[c] = 1;
+    atomicMin(parent + c, a);
+}
+
 __global__ void k_uf_flatten(int B, const int32_t *__restrict__ soff, int64_t S, int32_t *parent,
                              int32_t *__restrict__ label, int32_t *__restrict__ size) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    int b = cnt::find_segment(soff, B, (int)s);
-    int r = uf_find(parent, (int)s);
-    label[s] = r - soff[b];
-    atomicAdd(size + r, 1);
+    int r = -1;
+    if (s < S) {
+        int b = cnt::find_segment(soff, B, (int)s);
+        r = uf_find(parent, (int)s);
+        label[s] = r - soff[b];
+    }
+    // component sizes: one atomic per group of equal roots inside the warp (the big component is most of a network)
+    const unsigned same = __match_any_sync(0xffffffffu, r);
+    if (r >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(size + r, __popc(same));
 }
 
-// one block per network
-__global__ void __launch_bounds__(256) k_cluster_stats(const int32_t *__restrict__ soff,
-                                                       const int32_t *__restrict__ joff,
-                                                       const int32_t *__restrict__ stick1,
-                                                       const int32_t *__restrict__ label,
-                                                       const int32_t *__restrict__ size,
-                                                       const uint8_t *__restrict__ hasj,
-                                                       const int32_t *__restrict__ orig, int32_t *__restrict__ stats) {
-    __shared__ int s_nroots, s_nmulti, s_max, s_first, s_iso, s_ecomp;
-    int b = blockIdx.x;
-    int s0 = soff[b], n = soff[b + 1] - s0;
-    if (threadIdx.x == 0) {
-        s_nroots = 0; s_nmulti = 0; s_max = 0; s_first = 0x7fffffff; s_iso = 0; s_ecomp = 0;
+// per-network statistics, pass 1 over the sticks: components, multi-stick components, largest, first stick with a junction
+__global__ void k_stats_sticks(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ size,
+                               const uint8_t *__restrict__ hasj, int32_t *__restrict__ acc /* [B][8] */) {
+    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int b = -1, sz = 0, first = 0x7fffffff;
+    if (s < S) {
+        b = cnt::find_segment(soff, B, (int)s);
+        sz = size[s];           // non-zero only at roots
+        if (hasj[s]) first = (int)s - soff[b];
     }
-    __syncthreads();
-    int nroots = 0, nmulti = 0, mx = 0, first = 0x7fffffff;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        int sz = size[s0 + i];   // non-zero only at roots
-        if (sz > 0) {
-            nroots++;
-            if (sz > 1) nmulti++;
-            mx = max(mx, sz);
+    // one set of atomics per group of lanes of the same network
+    const unsigned same = __match_any_sync(0xffffffffu, b);
+    const unsigned roots = __ballot_sync(0xffffffffu, sz > 0) & same, multi = __ballot_sync(0xffffffffu, sz > 1) & same;
+    int mx = sz, fi = first;
+    for (int o = 16; o > 0; o >>= 1) {      // max / min over the whole warp is only used when the warp is one network
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        fi = min(fi, __shfl_xor_sync(0xffffffffu, fi, o));
+    }
+    if (b < 0) return;
+    int32_t *a = acc + (int64_t)b * 8;
+    if (same == 0xffffffffu) {
+        if (lane == 0) {
+            if (roots) atomicAdd(a + 0, __popc(roots));
+            if (multi) atomicAdd(a + 1, __popc(multi));
+            if (mx > 0) atomicMax(a + 2, mx);
+            if (fi < *(volatile int32_t *)(a + 3)) atomicMin(a + 3, fi);
         }
-        if (hasj[s0 + i]) first = min(first, i);
+    } else {                                // a warp across a network boundary (or the tail): per lane
+        if (sz > 0) {
+            atomicAdd(a + 0, 1);
+            if (sz > 1) atomicAdd(a + 1, 1);
+            atomicMax(a + 2, sz);
+        }
+        if (first < *(volatile int32_t *)(a + 3)) atomicMin(a + 3, first);
     }
-    atomicAdd(&s_nroots, nroots);
-    atomicAdd(&s_nmulti, nmulti);
-    atomicMax(&s_max, mx);
-    atomicMin(&s_first, first);
-    __syncthreads();
-    // reference quirk: sticks with a junction carry the component ordinal
-    // 0..K-1 (K = components with >1 stick), isolated sticks keep their pre-sort index
-    int K = s_nmulti, iso = 0;
-    if (orig) {
-        for (int i = threadIdx.x; i < n; i += blockDim.x)
-            if (!hasj[s0 + i] && orig[s0 + i] >= K) iso++;
-        atomicAdd(&s_iso, iso);
+}
+// pass 2: the reference's quirky cluster count needs K = multi-stick components (pass 1); junctions of the
+// percolating component
+__global__ void k_stats_second(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff, int64_t S,
+                               int64_t J, const int32_t *__restrict__ stick1, const int32_t *__restrict__ label,
+                               const uint8_t *__restrict__ hasj, const int32_t *__restrict__ orig,
+                               int32_t *__restrict__ acc) {
+    int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int b = -1, slot = 4;
+    if (t < S) {
+        // reference quirk: sticks with a junction carry the component ordinal 0..K-1 (K = components
+        // with >1 stick), isolated sticks keep their pre-sort index
+        if (orig && !hasj[t]) {
+            const int bb = cnt::find_segment(soff, B, (int)t);
+            if (orig[t] >= acc[(int64_t)bb * 8 + 1]) b = bb;
+        }
+    } else if (t - S < J) {
+        const int64_t e = t - S;
+        const int bb = cnt::find_segment(joff, B, (int)e);
+        const int s0 = soff[bb], n = soff[bb + 1] - s0;
+        const bool perc = n >= 2 && label[s0] == 0 && label[s0 + 1] == 0;
+        if (perc && label[s0 + stick1[e]] == 0) b = bb;
+        slot = 5;
     }
-    bool perc = n >= 2 && label[s0] == 0 && label[s0 + 1] == 0;
-    int ec = 0;
-    if (perc) {
-        int j0 = joff[b], j1 = joff[b + 1];
-        for (int e = j0 + threadIdx.x; e < j1; e += blockDim.x)
-            if (label[s0 + stick1[e]] == 0) ec++;
-        atomicAdd(&s_ecomp, ec);
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        int32_t *o = stats + (int64_t)b * CNT_NSTAT;
-        o[CNT_STAT_PERCOLATING] = perc ? 1 : 0;
-        o[CNT_STAT_NCLUST_TRUE] = s_nroots;
-        o[CNT_STAT_MAXCLUST_TRUE] = s_max;
-        o[CNT_STAT_NCLUST_REF] = orig ? K + s_iso : -1;
-        o[CNT_STAT_MAXCLUST_REF] = s_first == 0x7fffffff ? 0 : size[s0 + label[s0 + s_first]];
-        o[CNT_STAT_NCOMP] = perc ? size[s0] : 0;
-        o[CNT_STAT_ECOMP] = s_ecomp;
-        o[7] = 0;
-    }
+    const unsigned same = __match_any_sync(0xffffffffu, b * 8 + slot);
+    if (b >= 0 && lane == __ffs(same) - 1) atomicAdd(acc + (int64_t)b * 8 + slot, __popc(same));
+}
+__global__ void k_stats_finish(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ label,
+                               const int32_t *__restrict__ size, const int32_t *__restrict__ orig,
+                               const int32_t *__restrict__ acc, int32_t *__restrict__ stats) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int s0 = soff[b], n = soff[b + 1] - s0;
+    const int32_t *a = acc + (int64_t)b * 8;
+    const bool perc = n >= 2 && label[s0] == 0 && label[s0 + 1] == 0;
+    int32_t *o = stats + (int64_t)b * CNT_NSTAT;
+    o[CNT_STAT_PERCOLATING] = perc ? 1 : 0;
+    o[CNT_STAT_NCLUST_TRUE] = a[0];
+    o[CNT_STAT_MAXCLUST_TRUE] = a[2];
+    o[CNT_STAT_NCLUST_REF] = orig ? a[1] + a[4] : -1;
+    o[CNT_STAT_MAXCLUST_REF] = a[3] == 0x7fffffff ? 0 : size[s0 + label[s0 + a[3]]];
+    o[CNT_STAT_NCOMP] = perc ? size[s0] : 0;
+    o[CNT_STAT_ECOMP] = a[5];
+    o[7] = 0;
+}
+__global__ void k_stats_init(int B, int32_t *__restrict__ acc) {
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < B * 8) acc[t] = (t & 7) == 3 ? 0x7fffffff : 0;
 }
 }  // namespace
 
 extern "C" int64_t cnt_cluster_workspace_bytes(int64_t S) {
-    return cnt::ws_bytes_for(S, 4) * 2 + cnt::ws_bytes_for(S, 1);
+    // parent, size, hasj + the per-network accumulators of the statistics (every network has its two electrodes: B <= S / 2)
+    return cnt::ws_bytes_for(S, 4) * 2 + cnt::ws_bytes_for(S, 1) + cnt::ws_bytes_for(4 * S + 16, 4);
 }
 
 extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
@@ -137,7 +184,8 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
     int32_t *parent = w.take<int32_t>(S);
     int32_t *size = w.take<int32_t>(S);
     uint8_t *hasj = w.take<uint8_t>(S);
-    if (!hasj) {
+    int32_t *acc = w.take<int32_t>(8 * (int64_t)B);
+    if (!hasj || !acc) {
         cnt::set_error("cluster workspace too small");
         return CNT_ECAPACITY;
     }
@@ -146,6 +194,8 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
         CNT_LAUNCHED();
     }
     if (J > 0) {
+        k_uf_hook_min<<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, parent, hasj);
+        CNT_LAUNCHED();
         k_uf_union<<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, parent, hasj);
         CNT_LAUNCHED();
     }
@@ -153,7 +203,15 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
         k_uf_flatten<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, parent, label, size);
         CNT_LAUNCHED();
     }
-    k_cluster_stats<<<B, 256, 0, st>>>(soff, joff, stick1, label, size, hasj, orig, stats);
+    k_stats_init<<<cnt::grid_for(8 * (int64_t)B, 256), 256, 0, st>>>(B, acc);
+    CNT_LAUNCHED();
+    if (S > 0) {
+        k_stats_sticks<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, size, hasj, acc);
+        CNT_LAUNCHED();
+        k_stats_second<<<cnt::grid_for(S + J, 256), 256, 0, st>>>(B, soff, joff, S, J, stick1, label, hasj, orig, acc);
+        CNT_LAUNCHED();
+    }
+    k_stats_finish<<<cnt::grid_for(B, 128), 128, 0, st>>>(B, soff, label, size, orig, acc, stats);
     CNT_LAUNCHED();
     return CNT_OK;
 }

@@ -60,6 +60,14 @@ class NetworkBatch(object):
     def n_sticks(self, b):
         return self.h_soff[b + 1] - self.h_soff[b]
 
+    @property
+    def h_nzoff(self):
+        """off-diagonal entries up to every network's first row (host list, fetched on first use)"""
+        if getattr(self, "_h_nzoff", None) is None:
+            idx = torch.as_tensor(self.h_roff, device=self.rowptr.device, dtype=torch.long)
+            self._h_nzoff = [int(v) for v in self.rowptr[idx].cpu().tolist()]
+        return self._h_nzoff
+
 
 class GateState(object):
     """Per-junction gate-voltage state of a batch, as a small table of distinct voltage
@@ -302,9 +310,8 @@ class Engine(object):
             flagp = C.c_void_p()
             check(lib.cnt_junction_errflag_ptr(b.B, b.c_soff, _p(b._jws), b._jws.numel(), C.byref(flagp)))
             off = flagp.value - b._jws.data_ptr()
-            # one small D2H: total junction count + sortedness flag
-            total = int(jstart[b.S].item())
-            flag = int(b._jws[off:off + 4].view(torch.int32).item())
+            # one small D2H: total junction count + flags (bit 0: table not sorted, bit 1: temporary table overflowed)
+            total, flag = torch.cat([jstart[b.S:b.S + 1], b._jws[off:off + 4].view(torch.int32)]).cpu().tolist()
             b.junction_rows_recomputed = bool(flag & 2)      # temporary junction table overflowed: slower fill path
             if flag & 1:
                 raise _lib.CntError("stick table is not sorted by length descending (netsim.py:133)")
@@ -345,7 +352,6 @@ class Engine(object):
             b.urow = torch.empty(max(b.S, 1), dtype=torch.int32, device=self.device)
             b.roff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
             b.alive = b.attach = None
-            b.h_stats = b.stats.cpu().numpy().reshape(b.B, _lib.CNT_NSTAT).copy()      # D2H sync (B x 8 ints)
             prune, series = self._want_reductions(b)
             if prune and b.S > 0:
                 pws = self._ws(lib.cnt_prune_workspace_bytes(b.S))
@@ -372,7 +378,9 @@ class Engine(object):
             ws = self._ws(lib.cnt_assemble_workspace_bytes(b.S))
             check(lib.cnt_assemble_rows(b.B, _p(b.soff), b.S, _p(b.label), _p(b.stats), _p(b.alive), _p(b.elim_vid),
                                         _p(b.urow), _p(b.roff), _p(ws), ws.numel(), self.stream_ptr))
-            b.h_roff = [int(v) for v in b.roff.cpu().tolist()]          # D2H sync (B+1 ints)
+            hdr = torch.cat([b.roff, b.stats]).cpu().numpy()            # one D2H sync: row offsets + statistics
+            b.h_roff = [int(v) for v in hdr[:b.B + 1]]
+            b.h_stats = hdr[b.B + 1:].reshape(b.B, _lib.CNT_NSTAT).copy()
             b.c_roff = _lib.i32_array(b.h_roff)
             b.R = b.h_roff[-1]
             R = b.R
@@ -387,10 +395,8 @@ class Engine(object):
             sws = self._ws(lib.cnt_scan_workspace_bytes(R + 1))
             b.rowptr = torch.empty(R + 1, dtype=torch.int32, device=self.device)
             check(lib.cnt_exclusive_scan_i32(_p(rowcnt), _p(b.rowptr), R, 1, _p(sws), sws.numel(), self.stream_ptr))
-            # off-diagonal entries up to every network's first row: D2H sync (B+1 ints)
-            b.h_nzoff = [int(v) for v in b.rowptr[torch.as_tensor(b.h_roff, device=self.device,
-                                                                  dtype=torch.long)].cpu().tolist()]
-            b.NNZ = b.h_nzoff[-1]
+            b._h_nzoff = None
+            b.NNZ = int(b.rowptr[R].item())                             # D2H sync (total off-diagonal entries)
             n = max(b.NNZ, 1)
             b.col = torch.empty(n, dtype=torch.int32, device=self.device)
             b.nz_eid = torch.empty(n, dtype=torch.int32, device=self.device)
@@ -407,15 +413,12 @@ class Engine(object):
     def _want_reductions(self, b):
         """(prune, series) for this batch: the "auto" settings apply the exact reductions only when the
         solve is expected to be iterative -- solver 'cluster' / 'flat', or 'auto' with a junction graph
-        too dense for the direct solver (more than direct_max_degree off-diagonal entries per unknown)"""
+        too dense for the direct solver (more than direct_max_degree / 2 junctions per stick)"""
         if self.prune != "auto" and self.series != "auto":
             return bool(self.prune), bool(self.series)
-        st = b.h_stats
-        perc = st[:, _lib.STAT_PERCOLATING] > 0
-        nodes = int(st[perc, _lib.STAT_NCOMP].sum())
-        edges = int(st[perc, _lib.STAT_ECOMP].sum())
+        # decided from what the host already knows (no read-back): junctions per stick of the batch
         direct = self.solver == "direct" or (self.solver == "auto" and self.direct_auto and
-                                              2 * edges <= self.direct_max_degree * max(nodes, 1))
+                                              2 * b.J <= self.direct_max_degree * max(b.S, 1))
         auto = not direct
         prune = auto if self.prune == "auto" else bool(self.prune)
         series = auto if self.series == "auto" else bool(self.series)
@@ -551,8 +554,10 @@ class Engine(object):
                 if auto and xd is None:
                     method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
                 compressed = method == "cluster" and self.cluster_compressed and "cls" in sysm
-                max_nnz = max(b.h_nzoff[n + 1] - b.h_nzoff[n] for n in nets)
-                chunk_C = lib.cnt_pcg_cluster_size(max_rows, max_nnz) if compressed else 0
+                chunk_C = 0
+                if compressed:
+                    max_nnz = max(b.h_nzoff[n + 1] - b.h_nzoff[n] for n in nets)
+                    chunk_C = lib.cnt_pcg_cluster_size(max_rows, max_nnz)
                 if auto and compressed and lib.cnt_pcg_cluster_active(chunk_C) <= 0:
                     method, compressed, chunk_C = "flat", False, 0      # cluster launch not possible here
                 with self._work("pcg_aggregates"):
@@ -890,7 +895,8 @@ class Engine(object):
         out["sticks"] = np.asarray([int(n) for n in ns])
         out["seed"] = np.asarray(seeds, dtype=np.uint64)
         out["rows"] = np.diff(np.asarray(b.h_roff))
-        out["nnz_offdiag"] = self.nnz_per_network(b)
+        # per-network entry counts cost one more read-back: only fetched for the iterative solvers' traffic accounting
+        out["nnz_offdiag"] = self.nnz_per_network(b) if self.last_solver != "direct" else np.zeros(b.B, dtype=np.int64)
         return out
 
     def run_pipelined(self, jobs, fn, other=None):
