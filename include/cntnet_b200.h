@@ -261,6 +261,9 @@ int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, con
                        int32_t *row_q, double *row_einv, int32_t *cta_seg_off, int32_t *cta_seg,
                        int32_t *cta_agg_off, int32_t *cta_agg /* capacity of seg_* */, int32_t *row_slot,
                        int32_t *seg_home /* capacity of seg_* */,
+                       int64_t seg_capacity /* entries of the seg_* / cta_agg / seg_home arrays (cta_seg: 4x + 4 per CTA):
+                                               NSLAB*R/2 + NSLAB*R/256 + 2 is enough for chunk_C == 0, NSLAB*R + 2 always;
+                                               CNT_ECAPACITY when the tables need more */,
                        int64_t *h_nagg, int64_t *h_nseg,
                        void *ws, int64_t ws_bytes, void *stream);
 

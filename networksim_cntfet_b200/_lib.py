@@ -52,7 +52,7 @@ PROTOTYPES = {
     "cnt_assemble_values": (i32, [i64, vp, vp, vp, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "cnt_pcg_aggregate_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_aggregates": (i32, [i32, i32, i32, I32P, I32P, I32P, vp, i64, i64, vp, vp, vp, vp, f64] + [vp] * 9 +
-                           [i32, vp, vp, vp, vp, vp, vp, vp, vp, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
+                           [i32, vp, vp, vp, vp, vp, vp, vp, vp, i64, C.POINTER(i64), C.POINTER(i64), vp, i64, vp]),
     "cnt_pcg_workspace_bytes": (i64, [i32, i32, i64]),
     "cnt_pcg_solve": (i32, [i32, i32, i32, I32P, I32P, I32P, i64, i64, vp, vp, vp, vp, vp, vp, f64, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "cnt_pcg_cluster_max_rows": (i64, []),

@@ -153,6 +153,11 @@ class ConductionNetwork(object):
         self.source_currents_estimators = isrc
         self._graph_dirty = True
 
+    def sheet_conductance(self):
+        """G_sq = I_source / Vds of the square sample for the current gate state (derived quantity: the reference
+        stops at source_currents, cnet.py:135)"""
+        return float(np.sum(self.source_currents)) / self.vds
+
     def solve_mna(self):
         """cnet.py:147-149: returns [V of the non-ground nodes ..., source current]."""
         self.update()

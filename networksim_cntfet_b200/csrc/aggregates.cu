@@ -329,12 +329,13 @@ extern "C" int64_t cnt_pcg_aggregate_workspace_bytes(int NSYS, int NSLAB, int64_
     int64_t n = (int64_t)NSLAB * R;
     int64_t nt = (int64_t)NSYS * ((R + TILE - 1) / TILE + 1);
     return ws_bytes_for(n, 4) + ws_bytes_for(NSYS, 8) + 2 * ws_bytes_for(n, 8) + 2 * ws_bytes_for(n, 4) +
-           ws_bytes_for(nt, sizeof(ATile)) + ws_bytes_for(NSYS, sizeof(ASys)) + ws_bytes_for(n / 2 + n / SEGW + 2, 8) +
+           ws_bytes_for(nt, sizeof(ATile)) + ws_bytes_for(NSYS, sizeof(ASys)) + ws_bytes_for(n + 2, 8) +
            cnt::segsort_workspace_bytes(n, 2 * NSYS + 2) + 5 * ws_bytes_for(n + 1, 4) + ws_bytes_for(NSYS, sizeof(ASysD)) +
            cnt_scan_workspace_bytes(n + 1);
 }
 
-// Capacity the caller must provide: agg_of_row, mem: NSLAB*R; seg_*: NSLAB*R/2 + NSLAB*R/256 + 1;
+// Capacity the caller must provide: agg_of_row, mem: NSLAB*R; seg_* (seg_capacity entries; checked): NSLAB*R/2 +
+// NSLAB*R/256 + 2 for chunk_C == 0, NSLAB*R + 2 for the cluster tables (segments also end at CTA chunk boundaries);
 // agg_seg0: NSLAB*R/2 + 2; agg_einv: NSLAB*R/2 + 1.  Synchronises the stream (the run structure
 // of the sorted roots is read back once to build the segment tables).
 extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_sys_net, const int32_t *h_sys_slab,
@@ -344,7 +345,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
                                   int32_t *seg_count, int32_t *seg_agg, int32_t *seg_sys, int32_t *agg_seg0,
                                   double *agg_einv, int32_t *sys_seg, int chunk_C, int32_t *row_q, double *row_einv,
                                   int32_t *cta_seg_off, int32_t *cta_seg, int32_t *cta_agg_off, int32_t *cta_agg,
-                                  int32_t *row_slot, int32_t *seg_home,
+                                  int32_t *row_slot, int32_t *seg_home, int64_t seg_capacity,
                                   int64_t *h_nagg, int64_t *h_nseg, void *ws, int64_t ws_bytes, void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     CNT_CHECK_ARG(B > 0 && NSYS > 0 && NSLAB > 0 && h_sys_net && h_sys_slab && h_roff && roff && R >= 0 && h_nagg &&
@@ -402,7 +403,7 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
     uint32_t *valA = w.take<uint32_t>(n), *valB = w.take<uint32_t>(n);
     ATile *d_tiles = w.take<ATile>((int64_t)NSYS * ((R + TILE - 1) / TILE + 1));
     ASys *d_sys = w.take<ASys>(NSYS);
-    double *segE = w.take<double>(n / 2 + n / SEGW + 2);
+    double *segE = w.take<double>(n + 2);          // nseg <= n (segments also end at CTA chunk boundaries)
     int64_t sb = cnt::segsort_workspace_bytes(n, 2 * NSYS + 2);
     void *sws = w.take<char>(sb);
     int32_t *tA = w.take<int32_t>(n + 1), *tB = w.take<int32_t>(n + 1), *tC = w.take<int32_t>(n + 1);
@@ -470,6 +471,11 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
         CNT_CUDA(cudaStreamSynchronize(st));          // the ordv upload is complete as well
         nseg = h_tot[0];
         nagg = h_tot[1];
+        if (nseg > seg_capacity) {
+            cnt::set_error("aggregate tables: %lld segments exceed the caller's seg_* capacity %lld", (long long)nseg,
+                           (long long)seg_capacity);
+            return CNT_ECAPACITY;
+        }
         t1 = t2 = tnow();
         k_emit<<<gn, 256, 0, st>>>(n, ks, vs, d_ord, NSYS, chunk_C, tE, tB, tD, seg_start, seg_count, seg_agg, seg_sys,
                                    tC, agg_seg0);                                               // tC: CTA of segment
@@ -525,6 +531,11 @@ extern "C" int cnt_pcg_aggregates(int B, int NSYS, int NSLAB, const int32_t *h_s
 
         nagg = (int64_t)h_agg_seg0.size();
         nseg = (int64_t)h_seg_start.size();
+        if (nseg > seg_capacity) {
+            cnt::set_error("aggregate tables: %lld segments exceed the caller's seg_* capacity %lld", (long long)nseg,
+                           (long long)seg_capacity);
+            return CNT_ECAPACITY;
+        }
         t2 = tnow();
         // segments of one system are contiguous (the member array is ordered by system)
         h_sys_seg.assign(2 * (size_t)NSYS, 0);

@@ -52,21 +52,6 @@ __global__ void k_uf_union(int B, const int32_t *__restrict__ soff, const int32_
     }
 }
 
-// every stick2 of a junction starts under its smallest stick1 (stick1 < stick2 in every row of the table): most of
-// the forest exists before the first find, the union pass only has to join what is left
-__global__ void k_uf_hook_min(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff, int64_t J,
-                              const int32_t *__restrict__ stick1, const int32_t *__restrict__ stick2, int32_t *parent,
-                              uint8_t *__restrict__ hasj) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= J) return;
-    int b = cnt::find_segment(joff, B, (int)e);
-    int s0 = soff[b];
-    int a = s0 + stick1[e], c = s0 + stick2[e];
-    hasj[a] = 1;
-    hasj[c] = 1;
-    atomicMin(parent + c, a);
-}
-
 __global__ void k_uf_flatten(int B, const int32_t *__restrict__ soff, int64_t S, int32_t *parent,
                              int32_t *__restrict__ label, int32_t *__restrict__ size) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -194,8 +179,6 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
         CNT_LAUNCHED();
     }
     if (J > 0) {
-        k_uf_hook_min<<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, parent, hasj);
-        CNT_LAUNCHED();
         k_uf_union<<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, parent, hasj);
         CNT_LAUNCHED();
     }

@@ -115,10 +115,20 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long *bar, uint32_t 
         : "memory");
     return ok != 0;
 }
-// bounded wait: a protocol error must not hang the GPU -- record it and abort the kernel
+// bounded wait: a protocol error must not hang the GPU -- record it and abort the kernel.  The bound is WALL TIME
+// (20 s on the global timer, looked at every 2^16 polls), not a poll count: a peer CTA that is merely slow -- time
+// slicing, the twin-engine co-run, a profiler replay -- must not trip it, because a trap poisons the whole context.
 __device__ __forceinline__ void mbar_wait(unsigned long long *bar, uint32_t parity, int *assert_flag, int id) {
-    for (int i = 0; i < (1 << 24); i++)
+    unsigned long long t0 = 0;
+    for (unsigned i = 1;; i++) {
         if (mbar_try_wait(bar, parity)) return;
+        if ((i & 0xFFFFu) == 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 20000000000ull) break;
+        }
+    }
     atomicCAS(assert_flag, 0, id);
     __trap();
 }

@@ -481,7 +481,8 @@ class Engine(object):
         NS = sysm["val"].shape[0]
         n = NS * b.R
         nsys = len(sys_net)
-        cap_seg = n // 2 + n // 256 + 2
+        # segments end every 256 members and, for the cluster tables, at every CTA chunk boundary: up to one per row
+        cap_seg = n + 2 if chunk_C else n // 2 + n // 256 + 2
         i32 = lambda k: torch.empty(max(k, 1), dtype=torch.int32, device=self.device)
         t = dict(agg_of_row=i32(n), mem=i32(n), seg_start=i32(cap_seg), seg_count=i32(cap_seg), seg_agg=i32(cap_seg),
                  seg_sys=i32(cap_seg), agg_seg0=i32(n // 2 + 2), sys_seg=i32(2 * nsys),
@@ -499,7 +500,7 @@ class Engine(object):
                                      _p(t["seg_count"]), _p(t["seg_agg"]), _p(t["seg_sys"]), _p(t["agg_seg0"]),
                                      _p(t["agg_einv"]), _p(t["sys_seg"]), int(chunk_C), _p(t["row_q"]), _p(t["row_einv"]),
                                      _p(t["cta_seg_off"]), _p(t["cta_seg"]), _p(t["cta_agg_off"]), _p(t["cta_agg"]),
-                                     _p(t["row_slot"]), _p(t["seg_home"]), C.byref(nagg), C.byref(nseg), _p(ws),
+                                     _p(t["row_slot"]), _p(t["seg_home"]), cap_seg, C.byref(nagg), C.byref(nseg), _p(ws),
                                      ws.numel(),
                                      self.stream_ptr))
         st = _lib.Aggregates(t["agg_of_row"].data_ptr(), t["mem"].data_ptr(), t["seg_start"].data_ptr(),
@@ -812,7 +813,10 @@ class Engine(object):
             relres[mine] = res["relres"].cpu().numpy()
             status[mine] = res["status"].cpu().numpy()
         cur = np.where(perc[None, :], isrc[:, :, 2], 0.0)     # power form (see currents.cu)
-        out = dict(percolating=perc, nclust=st[:, _lib.STAT_NCLUST_REF].copy(),
+        # sheet conductance of the square sample, G_sq = I_source / Vds (Vds = 0.1 V, netsim.py:182), per
+        # gate configuration [ion, back, total, partial]
+        sheet = cur / 0.1
+        out = dict(percolating=perc, sheet_conductance=sheet, nclust=st[:, _lib.STAT_NCLUST_REF].copy(),
                    maxclust=st[:, _lib.STAT_MAXCLUST_REF].copy(),
                    nclust_true=st[:, _lib.STAT_NCLUST_TRUE].copy(), maxclust_true=st[:, _lib.STAT_MAXCLUST_TRUE].copy(),
                    ncomp=st[:, _lib.STAT_NCOMP].copy(), ecomp=st[:, _lib.STAT_ECOMP].copy(),

@@ -22,6 +22,7 @@ from . import get_engine, netsim, set_engine  # noqa: F401
 from .cnet import FermiDiracTransistor, LinExpTransistor
 
 elements = [FermiDiracTransistor, LinExpTransistor]
+VDS = 0.1                                   # netsim.py:182
 FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'ioff', 'gate', 'fname', 'seed',
                    'onoffmap']
 PIPELINE = False              # True: the batches of a call alternate between two engines / host threads (measured
@@ -113,8 +114,23 @@ def single_measure(n, scaling, l='exp', dump=False, savedir='test', seed=0, onof
     return data, fname
 
 
-def _rows_from_ensemble(res, ns, scaling, seeds, onoffmap, fnames=None):
-    """per-network statistics -> the reference's measure_fullnet rows (measure_perc.py:190-197)"""
+def _check_status(res):
+    """the reference's direct solve either succeeds or raises; an iterative solve that stopped at maxit (status 1)
+    or broke down (status 2) must not end up in a CSV unnoticed"""
+    st = np.asarray(res.get("status", 0))
+    if np.any(st != 0):
+        import warnings
+        bad = np.argwhere(st != 0)
+        warnings.warn("measure_perc: %d of %d solves did not converge (first: configuration %d, network %d, status %d, "
+                      "relres %.3g); their currents are unreliable -- re-run with Engine.solver = 'direct' or 'flat'"
+                      % (len(bad), st.size, bad[0][0], bad[0][1], int(st[tuple(bad[0])]),
+                         float(np.asarray(res["relres"])[tuple(bad[0])])), RuntimeWarning, stacklevel=3)
+
+
+def _rows_from_ensemble(res, ns, scaling, seeds, onoffmap, fnames=None, sheet=False):
+    """per-network statistics -> the reference's measure_fullnet rows (measure_perc.py:190-197); sheet=True appends
+    the sheet conductances G_sq = I / Vds of the on state and of the row's gate (not a column of the reference)"""
+    _check_status(res)
     rows = []
     for k, n in enumerate(ns):
         fname = fnames[k] if fnames else ''
@@ -126,11 +142,15 @@ def _rows_from_ensemble(res, ns, scaling, seeds, onoffmap, fnames=None):
             rows.append(base + [ion, float(res["ioff_partial"][k]), 'partial', fname, int(seeds[k]), onoffmap])
         else:
             rows.append(base + [0, 0, 'back', fname, int(seeds[k]), onoffmap])
-    return pd.DataFrame(rows, columns=FULLNET_COLUMNS)
+    df = pd.DataFrame(rows, columns=FULLNET_COLUMNS)
+    if sheet:
+        df["gsheet_on"] = df["ion"] / VDS
+        df["gsheet_off"] = df["ioff"] / VDS
+    return df
 
 
 def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l='exp', rtol=1e-15,
-                     return_io=False, engine=None):
+                     return_io=False, engine=None, sheet=False):
     """GPU body shared by measure_fullnet / measure_async: host arrays (ns, seeds) in, the
     reference's rows out.  ns/seeds are staged in pinned host memory and copied to the device;
     results come back as one statistics row per network."""
@@ -163,7 +183,7 @@ def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l
     d2h = 0
     for sl, res in zip(batches, results):
         d2h += sum(int(np.asarray(v).nbytes) for k, v in res.items() if isinstance(v, np.ndarray))
-        frames.append(_rows_from_ensemble(res, ns[sl], scaling, seeds_np[sl], onoffmap))
+        frames.append(_rows_from_ensemble(res, ns[sl], scaling, seeds_np[sl], onoffmap, sheet=sheet))
     del dev_in
     df = pd.concat(frames, ignore_index=True) if frames else pd.DataFrame(columns=FULLNET_COLUMNS)
     if return_io:
@@ -287,6 +307,13 @@ def measure_async(cores, start, step, number, scaling, save=False, onoffmap=[1],
     if not (len(seeds) == number):
         seeds = np.random.randint(low=0, high=2 ** 32, size=number)
     lo, hi, rank, world = _shard(number)
+    if world > 1:
+        # the seeds file is the reproducibility record (measure_perc.py:226-229): every rank must work from rank 0's
+        # seeds and run id, not from its own random draw
+        import torch.distributed as dist
+        shared = [np.asarray(seeds).tolist(), str(uuid)]
+        dist.broadcast_object_list(shared, src=0)
+        seeds, uuid = np.asarray(shared[0], dtype=np.uint64), shared[1]
     if rank == 0 and not os.path.isfile("seeds_{}.csv".format(uuid)):
         np.savetxt("seeds_{}.csv".format(uuid), seeds, delimiter=",")
     output = []

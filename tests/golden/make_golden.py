@@ -127,9 +127,29 @@ def build(name, cls="RandomCNTNetwork", trivial=False, element="LinExpTransistor
         name, n, len(st1), bool(net.percolating), out.get("isrc0"), out["nclust_ref"], out["maxclust_ref"]))
 
 
+def dump_reference_system(name, **kw):
+    """`<name>_sticks.csv` / `<name>_intersects.csv` written by the REFERENCE's own save_system (netsim.py:228-236),
+    plus the reference's currents for that network -- the N2 parity input: the GPU path loads the reference's dump
+    through load_system (tests/test_gpu_api.py::test_load_reference_dump)"""
+    netsim, cnet = refshim.load(hoist=True)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        net = netsim.RandomCNTNetwork(**kw)
+    net.save_system(os.path.join(HERE, name))
+    V, isrc = snapshot_solution(net)
+    cur = [net.gate(vg, gname) for gname in ("back", "partial", "total") for vg in (-10.0, 0.0, 10.0)]
+    np.savez_compressed(os.path.join(HERE, name + "_answers.npz"), V0=V, isrc0=np.float64(isrc),
+                        sweep_current=np.array(cur, dtype=np.float64), percolating=np.bool_(net.percolating),
+                        onoffmap=np.int64(net.onoffmap), scaling=np.float64(net.scaling))
+    print("%-28s dumped by the reference: %d sticks, %d junctions, isrc0=%r" % (name, len(net.sticks), len(net.intersects), isrc))
+
+
 def main():
     if not refshim.available():
         sys.exit("reference not available; goldens can only be generated in the build container")
+    dump_reference_system("refdump_s5_n300_seed1", n=300, scaling=5, seed=1, onoffmap=0)
+    if "--dump-only" in sys.argv:
+        return
     build("trivial", trivial=True)
     build("trivial_om1", trivial=True, onoffmap=1)
     build("s5_n300_seed1", n=300, scaling=5, seed=1, onoffmap=0)

@@ -50,7 +50,10 @@ def _worker(rank, world, port, tmpdir, q):
         from networksim_cntfet_b200 import measure_perc
         lo, hi, r, w = measure_perc._shard(11)
         df = _run_async(os.path.join(tmpdir, "r%d" % rank))
-        q.put((rank, (lo, hi, r, w), df.reset_index(drop=True).to_dict("list")))
+        # default seeds: drawn on rank 0 and broadcast, so every rank works from the same array and the one
+        # seeds file rank 0 writes is the record of the whole run
+        rnd = measure_perc.measure_async(2, 150, 25, 6, 5, onoffmap=[0])
+        q.put((rank, (lo, hi, r, w), df.reset_index(drop=True).to_dict("list"), [int(v) for v in rnd.seed.tolist()]))
     finally:
         dist.destroy_process_group()
 
@@ -81,6 +84,10 @@ def test_measure_async_world2_gloo(tmp_path):
     got.sort()
     assert got[0][1] == (0, 5, 0, 2) and got[1][1] == (5, 11, 1, 2)        # contiguous, balanced shards
     frames = [pd.DataFrame(g[2]) for g in got]
+    assert got[0][3] == got[1][3] and len(set(got[0][3])) > 1              # both ranks used rank 0's random seeds
+    files = sorted(n for n in os.listdir(tmp_path / "r0") if n.startswith("seeds_"))
+    recorded = [np.loadtxt(tmp_path / "r0" / n, delimiter=",").astype(np.uint64).tolist() for n in files]
+    assert sorted(set(got[0][3])) in [sorted(set(r)) for r in recorded]
     cwd = os.getcwd()
     try:
         single = _run_async(str(tmp_path / "single")).reset_index(drop=True)

@@ -105,6 +105,47 @@ def test_philox_class_and_save_load(api):
     assert info[0] == 400 and info[7] is True
 
 
+def test_load_reference_dump(api):
+    """N2 parity input: `_sticks.csv` / `_intersects.csv` written by the REFERENCE's own save_system
+    (netsim.py:228-236; tests/golden/make_golden.py dump_reference_system) load through load_system, and the GPU
+    solve of that table reproduces the reference's currents, voltages and gate sweep; sheet conductance = I / Vds"""
+    from conftest import GOLDEN_DIR
+    netsim, _, _ = api
+    ans = np.load(os.path.join(GOLDEN_DIR, "refdump_s5_n300_seed1_answers.npz"))
+    net = netsim.RandomCNTNetwork(fname="refdump_s5_n300_seed1", directory=GOLDEN_DIR, onoffmap=int(ans["onoffmap"]))
+    assert net.percolating == bool(ans["percolating"]) and len(net.sticks) == 302 and len(net.intersects) == 537
+    # the reference under this pandas puts the x = 0.99 electrode at index 0 (SURVEY H2): the dump is used as it is
+    assert net.sticks.xc[0] == 0.99 and net.sticks.kind[0] == "v"
+    i0 = float(sum(net.cnet.source_currents))
+    assert abs(i0 - float(ans["isrc0"])) <= 1e-9 * float(ans["isrc0"])
+    assert abs(net.cnet.sheet_conductance() - float(ans["isrc0"]) / 0.1) <= 1e-9 * float(ans["isrc0"]) / 0.1
+    V = net.cnet.voltages()
+    m = ~np.isnan(ans["V0"])
+    assert np.max(np.abs(V[m] - ans["V0"][m])) <= 1e-9 * 0.1
+    cur = [net.gate(vg, gname) for gname in ("back", "partial", "total") for vg in (-10.0, 0.0, 10.0)]
+    # the reference's own SuperLU answer at Vg = +10 is only ~2e-9 accurate (DESIGN.md section 2)
+    assert np.all(np.abs(np.array(cur) - ans["sweep_current"]) <= 5e-9 * ans["sweep_current"])
+
+
+def test_sheet_conductance_of_an_ensemble(api, engine):
+    """sheet conductance G_sq = I_source / Vds for the four measure_fullnet gates against the oracle (1e-9) and
+    as extra columns of the ensemble frame"""
+    from oracle import cntnet_oracle as O
+    _, _, mp = api
+    seeds = np.arange(200, 206, dtype=np.uint64)
+    res = engine.measure_ensemble([300] * 6, 5.0, seeds, onoffmap=1)
+    assert res["sheet_conductance"].shape == (4, 6)
+    for k in range(6):
+        s = engine.sticks_to_host(engine.generate([300], 5.0, seeds=seeds[k:k + 1]))[0]
+        m = O.measure_fullnet(s, onoffmap=1, refine=3)
+        for q, key in enumerate(("ion", "ioff_back", "ioff_total", "ioff_partial")):
+            want = m[key] / 0.1
+            assert abs(res["sheet_conductance"][q, k] - want) <= 1e-9 * want if m["percolating"] else res["sheet_conductance"][q, k] == 0
+    df = mp.measure_ensemble([300] * 6, 5, seeds, onoffmap=1, sheet=True)
+    assert list(df.columns)[-2:] == ["gsheet_on", "gsheet_off"]
+    assert np.allclose(df.gsheet_on.values, df.ion.values / 0.1, rtol=0, atol=0)
+
+
 def test_measure_fullnet_and_async(api):
     _, _, mp = api
     df = mp.measure_fullnet(300, 5, seed=7, onoffmap=1)

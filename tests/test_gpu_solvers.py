@@ -256,3 +256,23 @@ def test_two_level_preconditioner(solver, n, scaling, method):
     for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
         assert again[k][0] == two[k][0]
     assert np.array_equal(again["iters"], two["iters"])
+
+
+def test_cluster_without_spatial_order(solver):
+    """rows in stick (length) order instead of Z-order: the members of small aggregates land in different CTA
+    chunks, so the segment tables of the cluster kernel need up to one segment per aggregated row -- sized and
+    checked through seg_capacity (cnt_pcg_aggregates); same currents as with the spatial order"""
+    solver.solver = "cluster"
+    res = {}
+    for order in (True, False):
+        solver.spatial_order = order
+        try:
+            b = solver.generate([100000], 100.0, seed=5)
+            res[order] = solver.measure_fullnet(b, onoffmap=1)
+        finally:
+            solver.spatial_order = True
+        assert np.all(res[order]["status"] == 0)
+        nagg, nseg = solver.last_aggregates
+        assert nagg > 0 and nseg >= nagg
+    for k in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert abs(res[False][k][0] - res[True][k][0]) <= 1e-9 * res[True][k][0]
