@@ -44,7 +44,8 @@ def workload(args):
         "workload": "ensemble of %dx%d um networks, n=%d sticks (+2 electrodes) each, density %.3g /um^2, "
                     "measure_fullnet (4 solves: Vg=0, back/total/partial gate 10 V), LinExp element, onoffmap %d"
                     % (args.scaling, args.scaling, args.n, args.n / args.scaling ** 2, args.onoffmap),
-        "networks_per_gpu_per_step": args.batch, "n": args.n, "scaling": args.scaling, "onoffmap": args.onoffmap,
+        "networks_per_gpu_per_step": args.batch * max(1, args.engines), "batches_in_flight_per_gpu": max(1, args.engines),
+        "n": args.n, "scaling": args.scaling, "onoffmap": args.onoffmap,
         "pcg_rtol": args.rtol, "solver": args.solver,
         "l2": "working set per step (%d networks x ~34 MB) exceeds the 126 MB L2; fresh seeds every step"
               % args.batch,
@@ -168,6 +169,193 @@ def pcg_algorithmic_bytes(res):
     return float((it * per_iter[None, :]).sum()), float(it.sum())
 
 
+# ------------------------------------------------------------------------- further legs of the same JSON line
+def spmv_leg(eng, side, reps=20):
+    """CG SpMV against the HBM peak (the metric's third clause): y = diag .* x + A x on the reduced MNA matrices of
+    ONE side x side um network (prune + series reductions, as the PCG solvers see them), the four
+    measure_fullnet gate configurations per launch, through the C-ABI entry point cnt_spmv_csr (the kernel the
+    row-sharded PCG runs, csrc/spmv_stream.cuh).  Working set far beyond L2; CUDA events on the engine stream."""
+    import ctypes as C
+    import torch
+    from networksim_cntfet_b200 import _lib
+    from networksim_cntfet_b200.elements import LinExpTransistor, conductance_table
+    lib = _lib.load()
+    old = (eng.prune, eng.series)
+    eng.prune, eng.series = True, True
+    try:
+        n = int(10 * side * side)
+        b = eng.prepare(eng.generate([n], side, seed=77))
+        gates = [g for _, g in eng.fullnet_gates(b)]
+        sysm = eng.assemble_values(b, gates, [conductance_table(LinExpTransistor, 1, g.levels) for g in gates])
+    finally:
+        eng.prune, eng.series = old
+    NS, R, NNZ = len(gates), b.R, b.NNZ
+    if not R:
+        return {"error": "network does not percolate"}
+    vp = lambda t: C.c_void_p(t.data_ptr())
+    with eng._work():
+        x = torch.rand((NS, R), dtype=torch.float64, device=eng.device)
+        y = torch.empty((NS, R), dtype=torch.float64, device=eng.device)
+        val, diag = sysm["val"], sysm["diag"]
+
+        def launch():
+            _lib.check(lib.cnt_spmv_csr(NS, R, NNZ, vp(b.rowptr), vp(b.col), vp(val), val.stride(0), vp(diag), diag.stride(0),
+                                        vp(x), x.stride(0), vp(y), y.stride(0), eng.stream_ptr))
+        for _ in range(3):
+            launch()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.stream)
+        for _ in range(reps):
+            launch()
+        e1.record(eng.stream)
+    eng.sync()
+    sec = e0.elapsed_time(e1) / 1e3 / reps
+    alg = NS * (12.0 * NNZ + 20.0 * R)
+    out = {"kernel": "k_spmv_stream (cnt_spmv_csr)", "workload": "%gx%g um network, %d sticks: %d rows, %d off-diagonal entries, "
+           "%d gate configurations per launch" % (side, side, n, R, NNZ, NS), "rows": R, "nnz_offdiag": NNZ, "configurations": NS,
+           "us_per_launch": sec * 1e6, "algorithmic_bytes_per_launch": alg,
+           "accounting": "SURVEY 8(d): 12 B per entry (val 8 + col 4) + 20 B per row (rowptr 4, x 8, y 8) per configuration; the "
+                         "kernel also reads the 8-byte diagonal, which is not counted",
+           "achieved": alg / sec / 1e9, "unit": "GB/s"}
+    return out
+
+
+def extra_legs(args, eng, world, rank, dist, peak):
+    """driver-visible numbers for the other BASELINE configs with the CURRENT default solver, the PCG path, the SpMV"""
+    import tempfile
+    import numpy as np
+    import torch
+    from networksim_cntfet_b200 import measure_perc, netsim
+    out = {}
+
+    def sync():
+        eng.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def leg(name, fn, every_rank=False):
+        try:
+            if every_rank or rank == 0:
+                out[name] = fn()
+        except Exception as e:       # a failed leg must not take the headline with it
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+        sync()
+
+    # config 2: ensemble of 20x20 um networks swept across the percolation threshold (measure_perc.measure_async)
+    def config2():
+        number = args.ens_number
+        step = (8000 - 400) / max(number - 1, 1)
+        cwd = os.getcwd()
+        os.chdir(tempfile.mkdtemp(prefix="cntbench"))
+        try:
+            import contextlib, io
+            with contextlib.redirect_stdout(io.StringIO()):
+                measure_perc.measure_async(1, 400, step, max(number // 10, world), 20, onoffmap=[1],
+                                           seeds=list(range(5001, 5001 + max(number // 10, world))))
+                sync()
+                t0 = time.perf_counter()
+                df = measure_perc.measure_async(1, 400, step, number, 20, onoffmap=[1], seeds=list(range(1, number + 1)))
+                sync()
+            dt = time.perf_counter() - t0
+        finally:
+            os.chdir(cwd)
+        return {"workload": "%d networks of 20x20 um, n = 400..8000 (density 1..20 /um^2), measure_async -> rows; sharded over "
+                            "%d rank(s), rows all-gathered" % (number, world), "networks": number, "seconds": dt,
+                "value": number / dt, "unit": "networks/s", "timing": "wall clock between synchronisations (host API, CSV rows out)",
+                "percolating_rows": int((df.ion > 0).sum()), "solver": eng.last_solver}
+    leg("config2_ensemble_20um", config2, every_rank=True)
+
+    # config 4: gate sweep of one 60x60 um device, 11 voltages x {back, partial, total} (slurm/gatesweep.sh)
+    def config4():
+        side, vgs = 60.0, np.linspace(-10, 10, 11)
+        res = []
+        for rep in range(3):
+            sync_local()
+            t0 = time.perf_counter()
+            dev = netsim.RandomCNTNetwork(n=int(10 * side * side), scaling=side, seed=1234 + rep, onoffmap=0, rng='philox')
+            sync_local()
+            t1 = time.perf_counter()
+            cur = dev.gate_sweep(vgs, ['back', 'partial', 'total'])
+            sync_local()
+            t2 = time.perf_counter()
+            res.append((t1 - t0, t2 - t1, len(cur), bool(dev.percolating)))
+        build, sweep, steps, perc = res[-1]
+        return {"workload": "60x60 um device (36000 sticks), gate sweep 11 voltages x back/partial/total = %d re-solves over one "
+                            "pattern and one symbolic plan" % steps, "device_build_ms": build * 1e3, "sweep_ms": sweep * 1e3,
+                "ms_per_gate_step": sweep * 1e3 / max(steps, 1), "gate_steps_per_s": steps / sweep, "percolating": perc,
+                "solver": eng.last_solver, "timing": "wall clock, third repetition (rank 0)"}
+
+    def sync_local():
+        eng.sync()
+        torch.cuda.synchronize()
+    leg("config4_gate_sweep_60um", config4)
+
+    # config 5 (scaled): ONE large network; N = 1: default solver on one GPU; N > 1: unknown rows sharded over the ranks
+    def config5():
+        side = float(args.big_side)
+        n = int(10 * side * side)
+        best = None
+        for rep in range(2):
+            sync()
+            t0 = time.perf_counter()
+            if world > 1:
+                df, res = measure_perc.measure_fullnet_distributed(n, side, seed=5, mode="rows")
+            else:
+                b = eng.generate([n], side, seeds=[5])
+                res = eng.measure_fullnet(b, onoffmap=1)
+            sync()
+            best = time.perf_counter() - t0
+        return {"workload": "ONE %gx%g um network, %d sticks, measure_fullnet (4 solves)" % (side, side, n), "seconds": best,
+                "sticks_per_s": n / best, "ranks": world, "solver": eng.last_solver,
+                "mode": "rows of the system sharded over the ranks (halo exchange + all-reduces over NCCL)" if world > 1
+                        else "one GPU", "ion": float(res["ion"][0]), "iters": [int(v) for v in res["iters"][:, 0]],
+                "timing": "wall clock between synchronisations, second repetition"}
+    leg("config5_single_network", config5, every_rank=True)
+
+    # the iterative path (persistent cluster PCG) on a small batch of the headline workload, so that it stays measured
+    def cluster():
+        old = eng.solver
+        eng.solver = "cluster"
+        try:
+            nb = 14
+            from networksim_cntfet_b200.engine import network_seeds
+            eng.measure_ensemble([args.n] * nb, args.scaling, network_seeds(args.seed + 7, 0, nb), onoffmap=args.onoffmap)
+            eng.stage_times_ms(reset=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(eng.stream)
+            res = eng.measure_ensemble([args.n] * nb, args.scaling, network_seeds(args.seed + 8, 0, nb), onoffmap=args.onoffmap)
+            e1.record(eng.stream)
+            eng.sync()
+            st = eng.stage_times_ms(reset=True)
+            nbytes, iters = pcg_algorithmic_bytes(res)
+            sec = st.get("pcg", 0.0) / 1e3
+            return {"workload": "%d networks of the headline workload, solver 'cluster' (two-level Jacobi PCG, persistent "
+                                "thread-block-cluster kernel)" % nb, "value": nb / (e0.elapsed_time(e1) / 1e3), "unit": "networks/s",
+                    "solver": eng.last_solver, "pcg_iterations": iters, "pcg_seconds": sec,
+                    "equivalent_GBps": nbytes / sec / 1e9 if sec > 0 else None,
+                    "note": "equivalent-work rate of an unfused HBM-streaming PCG (12 nnz + 116 rows per iteration); the kernel "
+                            "works out of shared memory", "status_nonzero": int((res["status"] != 0).sum())}
+        finally:
+            eng.solver = old
+    leg("pcg_cluster_path", cluster)
+
+    def spmv():
+        d = spmv_leg(eng, float(args.spmv_side))
+        if "achieved" in d:
+            d["peak"] = peak
+            d["frac"] = d["achieved"] / peak
+            try:
+                cap = json.load(open(os.path.join(ROOT, "profiles", "r02_spmv_ncu.json")))
+                d["traffic"] = cap.get("dram_bytes_total")
+                d["traffic_note"] = cap.get("command")
+            except Exception:
+                d["traffic"] = None
+        return d
+    leg("spmv", spmv)
+    return out
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -191,8 +379,11 @@ def gpu_arm(args):
     B = args.batch
     ns = [args.n] * B
 
-    def seeds_for(phase, step):
-        return network_seeds(args.seed + phase, (step * world + rank) * B, B)
+    E = max(1, args.engines)               # batches of a step in flight at once (one engine = stream + host thread each)
+    measure_perc.PIPELINE = E > 1
+
+    def seeds_for(phase, step, sub=0, count=B):
+        return network_seeds(args.seed + phase, ((step * E + sub) * world + rank) * B, count)
 
     def barrier():
         eng.sync()
@@ -209,13 +400,21 @@ def gpu_arm(args):
         dist.all_gather(out, t)
         return torch.cat(out).cpu().numpy()
 
+    def one_batch(e, sub_phase_step):
+        sub, phase, step = sub_phase_step
+        return e.measure_ensemble(ns, args.scaling, seeds_for(phase, step, sub), onoffmap=args.onoffmap, rtol=args.rtol,
+                                  check_every=args.check_every)
+
     def device_step(phase, step):
-        res = eng.measure_ensemble(ns, args.scaling, seeds_for(phase, step), onoffmap=args.onoffmap, rtol=args.rtol,
-                                   check_every=args.check_every)
-        rows = np.stack([res["percolating"].astype(np.float64), res["ion"], res["ioff_back"], res["ioff_total"],
-                         res["ioff_partial"], res["nclust"].astype(np.float64), res["maxclust"].astype(np.float64)], 1)
+        """one step = E batches of B networks; E > 1: the batches run on E engines (own stream + host thread each), so
+        the latency-bound rounds of one batch's solve overlap the front end of the other"""
+        jobs = [(sub, phase, step) for sub in range(E)]
+        outs = eng.run_pipelined(jobs, one_batch) if E > 1 else [one_batch(eng, jobs[0])]
+        rows = np.concatenate([np.stack([res["percolating"].astype(np.float64), res["ion"], res["ioff_back"],
+                                         res["ioff_total"], res["ioff_partial"], res["nclust"].astype(np.float64),
+                                         res["maxclust"].astype(np.float64)], 1) for res in outs])
         gather_rows(rows)
-        return res
+        return outs
 
     # ---- warm-up
     for k in range(args.warmup):
@@ -228,32 +427,39 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.cnt_launch_count()
-    direct_bytes0 = getattr(eng, "direct_bytes_total", 0)
+    def direct_total():
+        tw = getattr(eng, "_twin", None)
+        return getattr(eng, "direct_bytes_total", 0) + (getattr(tw, "direct_bytes_total", 0) if tw is not None else 0)
+    direct_bytes0 = direct_total()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     t_wall0 = time.perf_counter()
-    e0.record(eng.stream)
-    results = [device_step(1, k) for k in range(args.steps)]
-    e1.record(eng.stream)
+    cur_stream = torch.cuda.current_stream()         # every engine stream is ordered after / before it (Engine._work)
+    e0.record(cur_stream)
+    results = [res for k in range(args.steps) for res in device_step(1, k)]
+    e1.record(cur_stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.cnt_launch_count() - launches0
-    direct_bytes = getattr(eng, "direct_bytes_total", 0) - direct_bytes0
+    direct_bytes = direct_total() - direct_bytes0
     solver_used = eng.last_solver
     direct_info = dict(getattr(eng, "last_direct", None) or {})
     dev_ms = e0.elapsed_time(e1)
     stages = eng.stage_times_ms(reset=True)
+    if E > 1 and getattr(eng, "_twin", None) is not None:       # stage times of both engines (they overlap in time)
+        for k, v in eng._twin.stage_times_ms(reset=True).items():
+            stages[k] = stages.get(k, 0.0) + v
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- timed: end to end through the public host API
-    measure_perc.measure_ensemble(ns, args.scaling, seeds_for(2, 0), onoffmap=args.onoffmap, rtol=args.rtol)  # warm
+    measure_perc.measure_ensemble(ns * E, args.scaling, seeds_for(2, 0, count=B * E), onoffmap=args.onoffmap, rtol=args.rtol)  # warm
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
     for k in range(args.steps):
-        df, io = measure_perc.measure_ensemble(ns, args.scaling, seeds_for(3, k), onoffmap=args.onoffmap,
+        df, io = measure_perc.measure_ensemble(ns * E, args.scaling, seeds_for(3, k, count=B * E), onoffmap=args.onoffmap,
                                                rtol=args.rtol, return_io=True)
-        fixed = np.full((3 * B, 2), np.nan)                      # <= 3 rows per network; equal shape on every rank
+        fixed = np.full((3 * B * E, 2), np.nan)                      # <= 3 rows per network; equal shape on every rank
         fixed[:len(df)] = df[["ion", "ioff"]].to_numpy(dtype=np.float64)
         gather_rows(fixed)
         h2d, d2h = io["h2d_bytes"], io["d2h_bytes"]
@@ -267,7 +473,13 @@ def gpu_arm(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
     dev_ms, e2e_ms, wall_ms = [float(v) for v in tt.cpu()]
-    total_networks = args.steps * B * world
+    total_networks = args.steps * B * E * world
+    peaks0 = {}
+    try:
+        peaks0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    extras = {} if args.no_extra else extra_legs(args, eng, world, rank, dist, float(peaks0.get("hbm_gbs", 6650.0)))
     value = total_networks / (dev_ms / 1e3)
     e2e_value = total_networks / (e2e_ms / 1e3)
 
@@ -326,10 +538,10 @@ def gpu_arm(args):
                         "achieved": achieved, "peak": peak,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                        "algorithmic_bytes_per_launch": direct_bytes / max(args.steps, 1),
+                        "algorithmic_bytes_per_launch": direct_bytes / max(args.steps * E, 1),
                         "algorithmic_bytes": direct_bytes, "seconds": d_s,
-                        "symbolic_ms_per_step": stages.get("direct_symbolic", 0.0) / max(args.steps, 1),
-                        "numeric_ms_per_step": stages.get("direct_numeric", 0.0) / max(args.steps, 1),
+                        "symbolic_ms_per_batch": stages.get("direct_symbolic", 0.0) / max(args.steps * E, 1),
+                        "numeric_ms_per_batch": stages.get("direct_numeric", 0.0) / max(args.steps * E, 1),
                         "last_batch": direct_info,
                         "note": "'launch' = one batch (all rounds of both phases); algorithmic bytes per starmesh.algorithmic_bytes: "
                                 "symbolic -- live-edge list read twice and unknowns in play once per round, 16 B per incident "
@@ -358,6 +570,8 @@ def gpu_arm(args):
             "percolating_fraction": float(np.mean([r["percolating"].mean() for r in results])),
             "pcg_iters_mean_per_solve": [float(np.mean([r["iters"][q].mean() for r in results])) for q in range(4)],
         }
+        line["spmv"] = extras.pop("spmv", None)
+        line["configs"] = extras
         if world == 1 and not args.no_cpu_baseline:
             cores = os.cpu_count() or 1
             count = min(cores, args.cpu_sample or cores)
@@ -393,6 +607,12 @@ def main():
     ap.add_argument("--guess", default="zero", choices=["linear", "zero"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="networks in the CPU sample (default: one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--engines", type=int, default=1, choices=[1, 2],
+                    help="batches of a step in flight per GPU (2: two engines = two streams + two host threads)")
+    ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / 4 / 5, cluster-PCG and SpMV legs")
+    ap.add_argument("--ens-number", type=int, default=1000, help="networks of the config-2 leg")
+    ap.add_argument("--big-side", type=float, default=300.0, help="side (um) of the single large network of the config-5 leg")
+    ap.add_argument("--spmv-side", type=float, default=600.0, help="side (um) of the network whose matrices the SpMV leg streams")
     args = ap.parse_args()
     if args.impl == "reference":
         return reference_arm(args)

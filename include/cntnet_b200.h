@@ -370,6 +370,18 @@ int cnt_slab_direction(const cnt_slab_ctx *c, int first, void *stream);
 int cnt_slab_spmv(const cnt_slab_ctx *c, void *stream);
 int cnt_slab_update(const cnt_slab_ctx *c, void *stream);
 
+/* The SpMV of the PCG solvers on its own (the operator application inside the SuperLU-replacing solve,
+ * cnet.py:147-149): y[q] = diag[q] .* x[q] + A[q] x[q] for NS value sets over ONE CSR pattern of off-diagonal
+ * entries (rowptr [n_rows+1], col [nnz] = row index in 0..n_rows-1 -- or beyond, when x is longer than
+ * n_rows (halo copies behind the own rows); val / diag / x / y: configuration q at base + q * stride;
+ * diag may be NULL).  Streaming kernel (csrc/spmv_stream.cuh): a CTA reads the contiguous entry range of
+ * its 256 rows with coalesced 16-byte loads (needs col and val + q * val_stride 16-byte aligned; otherwise
+ * a scalar path), products through shared memory, one thread per row sums in CSR order (deterministic).
+ * Algorithmic bytes per configuration: 12 nnz + 20 n_rows (+ 8 n_rows with diag). */
+int cnt_spmv_csr(int NS, int64_t n_rows, int64_t nnz, const int32_t *rowptr, const int32_t *col, const double *val,
+                 int64_t val_stride, const double *diag, int64_t diag_stride, const double *x, int64_t x_stride,
+                 double *y, int64_t y_stride, void *stream);
+
 /* ---------------------------------------------------------------------------------------
  * (5c) direct solve by parallel star-mesh elimination -- replaces solve_mna (cnet.py:147-149) by
  *      sparse Cholesky written on the conductances (every quantity a sum of positive terms):
@@ -462,13 +474,17 @@ int cnt_sm_solve(int NS, int B, int64_t R, int64_t NNZ, const cnt_sm_info *h_inf
  * isrc[b*3+0] = sum_j g_0j (0.1 - V_j)  (== x[-1] of the MNA system, cnet.py:135)
  * isrc[b*3+1] = sum_j g_1j V_j          (current into the ground electrode)
  * isrc[b*3+2] = sum_e g_e dV_e^2 / 0.1  (dissipated power / Vds)
+ * The sums run over chunks of 8192 junctions counted from the network's own first junction, then over the
+ * chunks in order: fixed order, independent of the batch.  ws: cnt_currents_workspace_bytes(B, J) bytes.
  * ------------------------------------------------------------------------------------- */
+int64_t cnt_currents_workspace_bytes(int B, int64_t J);
 int cnt_currents(int B, const int32_t *soff, const int32_t *joff, int64_t S, int64_t J,
                  const int32_t *stick1, const int32_t *stick2, const int32_t *label, const int32_t *stats,
                  const int32_t *urow, const int32_t *attach /* from cnt_prune_leaves, or NULL */,
                  const int32_t *elim_vid, const int32_t *va, const int32_t *vc, const int32_t *ve1,
                  const int32_t *ve2 /* from cnt_series_select, or all NULL */,
-                 const double *g, const double *x, double *V, double *I, double *isrc, void *stream);
+                 const double *g, const double *x, double *V, double *I, double *isrc, void *ws, int64_t ws_bytes,
+                 void *stream);
 
 #ifdef __cplusplus
 }

@@ -72,7 +72,9 @@ PROTOTYPES = {
     "cnt_slab_direction": (i32, [vp, i32, vp]),
     "cnt_slab_spmv": (i32, [vp, vp]),
     "cnt_slab_update": (i32, [vp, vp]),
-    "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "cnt_spmv_csr": (i32, [i32, i64, i64, vp, vp, vp, i64, vp, i64, vp, i64, vp, i64, vp]),
+    "cnt_currents_workspace_bytes": (i64, [i32, i64]),
+    "cnt_currents": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
 }
 # entry points that may be absent from an older build of the library (checked by tests
 # against the header, never silently replaced)

@@ -15,7 +15,7 @@ OBJDIR = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libcntnet_b200.so")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
-SOURCES = ["util.cu", "radix.cu", "sticks.cu", "junctions.cu", "clusters.cu", "prune.cu", "assemble.cu", "aggregates.cu", "pcg.cu", "pcg_cluster.cu", "pcg_slab.cu", "starmesh.cu", "starmesh_sym.cu",
+SOURCES = ["util.cu", "radix.cu", "sticks.cu", "junctions.cu", "clusters.cu", "prune.cu", "assemble.cu", "aggregates.cu", "pcg.cu", "pcg_cluster.cu", "pcg_slab.cu", "spmv.cu", "starmesh.cu", "starmesh_sym.cu",
            "currents.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE]
@@ -52,7 +52,7 @@ def build(force=False, verbose=False):
     headers = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
     headers.append(os.path.join(INCLUDE, "cntnet_b200.h"))
     objs = []
-    rebuilt = False
+    jobs = []
     for src in sources():
         path = os.path.join(CSRC, src)
         obj = os.path.join(OBJDIR, src.replace(".cu", ".o"))
@@ -61,18 +61,25 @@ def build(force=False, verbose=False):
             flags = flags + ["-Xptxas", "-v"]
         stamp = obj + ".sha"
         dig = _digest([path] + headers, " ".join(flags))
+        objs.append(obj)
         if not force and os.path.isfile(obj) and os.path.isfile(stamp) and open(stamp).read() == dig:
-            objs.append(obj)
             continue
-        cmd = [nvcc] + flags + ["-c", path, "-o", obj]
+        jobs.append((src, [nvcc] + flags + ["-c", path, "-o", obj], stamp, dig))
+
+    def compile_one(job):
+        src, cmd, stamp, dig = job
         r = subprocess.run(cmd, capture_output=True, text=True)
         if verbose or r.returncode:
             sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
         if r.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
         open(stamp, "w").write(dig)
-        objs.append(obj)
-        rebuilt = True
+
+    if jobs:       # translation units are independent: compile them side by side
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(jobs), os.cpu_count() or 1, 8)) as pool:
+            list(pool.map(compile_one, jobs))
+    rebuilt = bool(jobs)
     if rebuilt or force or not os.path.isfile(LIB):
         cmd = [nvcc, "-shared", "-o", LIB] + objs + ARCH
         r = subprocess.run(cmd, capture_output=True, text=True)

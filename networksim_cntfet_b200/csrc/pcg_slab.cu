@@ -18,10 +18,11 @@
 // rank evaluates identically from the reduced S.  All partial sums are reduced in a fixed order
 // (block partials, then one block per configuration), so a rank's arithmetic is deterministic.
 // Stopping rule as in pcg.cu: recurrence residual ||r|| <= rtol ||b||.
-#include "common.cuh"
+#include "spmv_stream.cuh"
 
 namespace {
 constexpr int TB = 256;
+static_assert(TB == cnt::spmv::TB, "k_slab_spmv: one row per thread of the streaming SpMV");
 
 __device__ __forceinline__ const int32_t *row_i32(const int32_t *base, int q, int64_t stride) {
     return base + (int64_t)q * stride;
@@ -57,22 +58,24 @@ __global__ void k_slab_unpack(cnt_slab_ctx c) {
     c.p[(int64_t)q * (c.n_own + c.n_halo) + c.n_own + h] = c.recvbuf[c.halo_src[h] + (int64_t)q * c.emax];
 }
 
-// q = A p on the own rows (one thread per row; neighbouring rows are neighbouring sticks, their
-// entries are adjacent in memory), block partial of p.q
+// q = A p on the own rows: the CTA streams the contiguous entry range of its 256 rows with coalesced 16-byte
+// loads through shared memory (spmv_stream.cuh), thread t then sums row t in CSR order; block partial of p.q
 __global__ void __launch_bounds__(TB) k_slab_spmv(cnt_slab_ctx c) {
     __shared__ double sm[32];
+    __shared__ __align__(16) double s_prod[cnt::spmv::CAP];
     const int q = blockIdx.y;
-    const int64_t i = (int64_t)blockIdx.x * TB + threadIdx.x;
+    if (c.done[q]) {                                         // CTA-uniform
+        if (threadIdx.x == 0) c.part[((int64_t)q * 3 + 2) * c.nblk + blockIdx.x] = 0.0;
+        return;
+    }
+    const int64_t r0 = (int64_t)blockIdx.x * TB, i = r0 + threadIdx.x;
+    const double *p = c.p + (int64_t)q * (c.n_own + c.n_halo);
+    const double acc = cnt::spmv::stream_rows(r0, c.n_own, (int64_t)c.rowptr[c.n_own], c.rowptr, c.col,
+                                              c.val + (int64_t)q * c.val_stride, c.diag + (int64_t)q * c.n_own, p, s_prod);
     double pq = 0.0;
-    if (i < c.n_own && !c.done[q]) {
-        const double *p = c.p + (int64_t)q * (c.n_own + c.n_halo);
-        const double *val = c.val + (int64_t)q * c.val_stride;
-        const int k0 = __ldg(c.rowptr + i), k1 = __ldg(c.rowptr + i + 1);
-        const double pi = p[i];
-        double acc = c.diag[(int64_t)q * c.n_own + i] * pi;
-        for (int k = k0; k < k1; k++) acc += __ldg(val + k) * p[__ldg(c.col + k)];
+    if (i < c.n_own) {
         c.q[(int64_t)q * c.n_own + i] = acc;
-        pq = pi * acc;
+        pq = p[i] * acc;
     }
     pq = cnt::block_sum(pq, sm);
     if (threadIdx.x == 0) c.part[((int64_t)q * 3 + 2) * c.nblk + blockIdx.x] = pq;

@@ -709,11 +709,12 @@ class Engine(object):
             V = torch.empty(max(b.S, 1), dtype=torch.float64, device=self.device)
             I = torch.empty(max(b.J, 1), dtype=torch.float64, device=self.device)
             isrc = torch.zeros((b.B, 3), dtype=torch.float64, device=self.device)
+            ws = self._ws(lib.cnt_currents_workspace_bytes(b.B, b.J))
             check(lib.cnt_currents(b.B, _p(b.soff), _p(b.joff), b.S, b.J, _p(b.stick1), _p(b.stick2), _p(b.label),
                                    _p(b.stats), _p(b.urow), _p(getattr(b, "attach", None)),
                                    _p(getattr(b, "elim_vid", None)), _p(getattr(b, "va", None)),
                                    _p(getattr(b, "vc", None)), _p(getattr(b, "ve1", None)), _p(getattr(b, "ve2", None)),
-                                   _p(g), _p(x), _p(V), _p(I), _p(isrc), self.stream_ptr))
+                                   _p(g), _p(x), _p(V), _p(I), _p(isrc), _p(ws), ws.numel(), self.stream_ptr))
         return V, I, isrc
 
     # ------------------------------------------------------------------ measure_fullnet, batched

@@ -3,7 +3,7 @@
 # ncu: k_tiles / k_uf_union full capture, DRAM bytes of every direct-stage launch of one batch
 cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_api.py::test_load_reference_dump tests/test_gpu_direct.py::test_full_size_truth -m gpu -q -s --timeout=600 -p no:cacheprovider 2>&1 | tail -15 > gpurun_out/pytest_fix.log
+timeout 600 python -m pytest tests/test_gpu_api.py::test_load_reference_dump tests/test_gpu_direct.py::test_full_size_truth tests/test_gpu_spmv.py tests/test_gpu_slab.py -m gpu -q -s --timeout=600 -p no:cacheprovider 2>&1 | tail -25 > gpurun_out/pytest_fix.log
 CNT_SM_TIMING=1 timeout 300 python bench.py --steps 1 --warmup 2 --no-cpu-baseline > gpurun_out/bench_timing.log 2> gpurun_out/bench_timing.err
 BIG_SIDE=300 BIG_CHECK=0 timeout 300 python tools/big_network.py > gpurun_out/big300.log 2>&1
 BIG_SIDE=1000 BIG_CHECK=0 timeout 400 python tools/big_network.py > gpurun_out/big1000.log 2>&1
