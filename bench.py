@@ -48,7 +48,7 @@ def workload(args):
         "n": args.n, "scaling": args.scaling, "onoffmap": args.onoffmap,
         "pcg_rtol": args.rtol, "solver": args.solver,
         "l2": "working set per step (%d networks x ~34 MB) exceeds the 126 MB L2; fresh seeds every step"
-              % args.batch,
+              % (args.batch * max(1, args.engines)),
     }
 
 
@@ -594,9 +594,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=56,
-                    help="networks per GPU per step (56 x 4 solves = 32 systems for each of the 7 resident clusters: "
-                         "the work queue's tail costs 1 %% instead of 7 %% at 14)")
+    ap.add_argument("--batch", type=int, default=224,
+                    help="networks per GPU per step (the ~45 rounds of the direct solve are a fixed latency per batch: "
+                         "measured 1999 / 2240 / 2346 networks/s at 56 / 112 / 224)")
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--scaling", type=int, default=100)
     ap.add_argument("--onoffmap", type=int, default=1)

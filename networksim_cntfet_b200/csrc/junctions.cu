@@ -144,7 +144,6 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     int32_t *s_rng = s_pre + CAP_HOME + 1;                        // [CAP_HOME] packed cell range (region-relative)
     int32_t *s_cnt = s_rng + CAP_HOME;                            // [CAP_HOME + 1] junctions per home stick / row offsets
     int32_t *s_hq = s_cnt + CAP_HOME + 1;                         // [CAP_HOME] region index of every home stick
-    int32_t *s_blk = s_hq + CAP_HOME;                             // [CAP_Q / 32] home stick of every 32nd pair of a chunk
     __shared__ int s_red[8];
     __shared__ int s_nq, s_nhit, s_base, s_warp[CT / 32];
     __shared__ unsigned long long s_tests;
@@ -298,70 +297,93 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         if (tid < nb) s_pre[tid] = s_warp[wid] + inc - ncand;
         if (tid == nb - 1) s_pre[nb] = s_warp[wid] + inc;
         __syncthreads();
-        const int P = s_pre[nb];
-        for (int p0 = 0; p0 < P; p0 += CAP_Q) {                  // chunks of candidate pairs
-            if (tid == 0) s_nq = 0;
-            // s_blk[k] = home stick owning pair p0 + 32 k: every home stick fills the blocks that start inside its range
-            if (tid < nb) {
-                const int a = max(s_pre[tid], p0), e = min(s_pre[tid + 1], min(P, p0 + CAP_Q));
-                for (int k = (a - p0 + 31) >> 5; p0 + 32 * k < e; k++) s_blk[k] = tid;
+        // chunks of home sticks whose candidate pairs (s_pre) fit the survivor queue; inside a chunk every home stick
+        // is walked by a group of GL lanes: cell rows one after the other, the records of a row (contiguous in the
+        // region) GL at a time.  Phase 1 (cheap): j > i and the KD ball; survivors -> queue (ballot over the lanes
+        // that are converged + one shared atomic per ballot).  Phase 2 (FP64 predicate, two IEEE divisions) on the
+        // compacted queue with full warps.
+        constexpr int GL = 8, NGRP = CT / GL;
+        const int grp = tid / GL, sub = tid - grp * GL;
+        auto emit = [&](int h, int v) {                          // predicate of (home stick h of the batch, region record v)
+            const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
+            double xi, yi;
+            if (cnt_junction(l1, l2, &xi, &yi)) {
+                const int rank = atomicAdd(&s_cnt[h], 1);
+                const int at = atomicAdd(&s_nhit, 1);
+                if (at < CAP_HIT) {
+                    Hit hh;
+                    hh.hr = (h << 16) | (rank & 0xFFFF);
+                    hh.j = recA(v).idx;
+                    hh.x = xi;
+                    hh.y = yi;
+                    s_hit[at] = hh;
+                }
             }
+        };
+        for (int h_lo = 0; h_lo < nb;) {
+            // largest h_hi with s_pre[h_hi] - s_pre[h_lo] <= CAP_Q (uniform: every thread computes the same)
+            const int lim = s_pre[h_lo] + CAP_Q;
+            int h_hi = h_lo + 1;
+            const bool giant = s_pre[h_hi] > lim;                // ONE home stick with more candidates than the queue holds
+            if (!giant) {
+                int lo = h_hi, hi = nb;
+                while (lo < hi) {
+                    const int mid = (lo + hi + 1) >> 1;
+                    if (s_pre[mid] <= lim) lo = mid; else hi = mid - 1;
+                }
+                h_hi = lo;
+            }
+            if (tid == 0) s_nq = 0;
             __syncthreads();
-            // phase 1 (cheap): j > i and the KD ball; survivors -> queue (warp ballot + one shared atomic per warp)
-            const int pend = min(P, p0 + CAP_Q);
-            for (int pp = p0 + tid; pp < ((pend + 31) & ~31); pp += CT) {
-                bool pass = false;
-                int entry = 0;
-                if (pp < pend) {
-                    int h = s_blk[(pp - p0) >> 5];                // home stick of the first pair of this warp's 32 pairs
-                    while (s_pre[h + 1] <= pp) h++;               // ... a few steps further for this lane
+            if (giant) {
+                // no queue: the whole CTA walks the stick's candidates and evaluates the predicate in place
+                const int h = h_lo, rng = s_rng[h];
+                const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
+                const RecA me = recA(s_hq[h]);
+                for (int cy = cy0; cy <= cy1; cy++) {
+                    const int a0 = s_cs[cy * (RW + 1) + cx0], a1 = s_cs[cy * (RW + 1) + cx1 + 1];
+                    for (int v = a0 + tid; v < a1; v += CT) {
+                        const RecA o = recA(v);
+                        if (o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc)) {
+                            tests++;
+                            emit(h, v);
+                        }
+                    }
+                }
+            } else {
+                for (int h = h_lo + grp; h < h_hi; h += NGRP) {
                     const int rng = s_rng[h];
                     const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
-                    int c = pp - s_pre[h], v = -1;
+                    const RecA me = recA(s_hq[h]);
                     for (int cy = cy0; cy <= cy1; cy++) {
                         const int a0 = s_cs[cy * (RW + 1) + cx0], a1 = s_cs[cy * (RW + 1) + cx1 + 1];
-                        if (c < a1 - a0) {
-                            v = a0 + c;
-                            break;
+                        for (int v = a0 + sub; v < a1; v += GL) {
+                            const RecA o = recA(v);
+                            const bool pass = o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc);
+                            const unsigned act = __activemask();
+                            const unsigned m = __ballot_sync(act, pass);
+                            if (m) {
+                                const int leader = __ffs(m) - 1;
+                                int base = 0;
+                                if (lane == leader) base = atomicAdd(&s_nq, __popc(m));
+                                base = __shfl_sync(act, base, leader);
+                                if (pass) {
+                                    s_q[base + __popc(m & ((1u << lane) - 1u))] = (h << 23) | v;
+                                    tests++;
+                                }
+                            }
                         }
-                        c -= a1 - a0;
                     }
-                    const RecA me = recA(s_hq[h]), o = recA(v);
-                    pass = o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc);
-                    entry = (h << 23) | v;
                 }
-                const unsigned m = __ballot_sync(~0u, pass);
-                if (m) {
-                    int base = 0;
-                    if (lane == __ffs(m) - 1) base = atomicAdd(&s_nq, __popc(m));
-                    base = __shfl_sync(~0u, base, __ffs(m) - 1);
-                    if (pass) {
-                        s_q[base + __popc(m & ((1u << lane) - 1u))] = entry;
-                        tests++;
-                    }
+                __syncthreads();
+                const int nq = s_nq;
+                for (int k = tid; k < nq; k += CT) {
+                    const int entry = s_q[k];
+                    emit(entry >> 23, entry & ((1 << 23) - 1));
                 }
             }
             __syncthreads();
-            // phase 2 (FP64 predicate) on the compacted queue: full warps
-            const int nq = s_nq;
-            for (int k = tid; k < nq; k += CT) {
-                const int entry = s_q[k], h = entry >> 23, v = entry & ((1 << 23) - 1);
-                const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
-                double xi, yi;
-                if (cnt_junction(l1, l2, &xi, &yi)) {
-                    const int rank = atomicAdd(&s_cnt[h], 1);
-                    const int at = atomicAdd(&s_nhit, 1);
-                    if (at < CAP_HIT) {
-                        Hit hh;
-                        hh.hr = (h << 16) | (rank & 0xFFFF);
-                        hh.j = recA(v).idx;
-                        hh.x = xi;
-                        hh.y = yi;
-                        s_hit[at] = hh;
-                    }
-                }
-            }
-            __syncthreads();
+            h_lo = h_hi;
         }
         // rows of the batch: offsets (exclusive scan of s_cnt), space in the temporary table, write-out
         const int nhit = s_nhit;
@@ -649,7 +671,7 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
 static size_t tiles_smem() {
     return (size_t)CAP_REC * (sizeof(RecA) + sizeof(CntLine)) + (size_t)CAP_HIT * sizeof(Hit) +
            4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
-                CAP_HOME + CAP_Q / 32);
+                CAP_HOME);
 }
 }  // namespace
 

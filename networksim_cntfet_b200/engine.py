@@ -144,8 +144,10 @@ class Engine(object):
         self.slab_graph = os.environ.get("CNT_SLAB_GRAPH", "1") != "0"   # solve_sharded: replay blocks of iterations
                                        # (kernels + collectives) as one CUDA graph
         self.direct_auto = True        # solver 'auto' takes the direct solver when the pattern is sparse enough
-        self.direct_max_degree = 8.0   # ... i.e. at most this many off-diagonal entries per unknown on average
-        self.direct_max_fill = 12.0    # ... and the elimination creates at most this many contributions per edge
+        self.direct_max_degree = 16.0  # ... i.e. at most this many off-diagonal entries per unknown on average
+        self.direct_max_fill = 40.0    # ... and the elimination creates at most this many contributions per edge
+                                       # (measured: the 20x20 um density sweep 1..20 /um^2 of BASELINE config 2 needs 12.4
+                                       # and runs 4.6x faster through the direct solver than through the cluster PCG)
         self.direct_dense_max = 192    # ... and finishes with one dense elimination per network once it has <= this many
                                        # unknowns left (0 = sparse rounds to the end; <= 224: the dense matrix stays in
                                        # shared memory)

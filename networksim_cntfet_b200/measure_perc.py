@@ -27,9 +27,9 @@ FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'io
                    'onoffmap']
 PIPELINE = False              # True: the batches of a call alternate between two engines / host threads (measured
                               # gain at 100x100 um: 0.7-2 %, the step is one long kernel already; results identical)
-BATCH_STICKS = 5_800_000      # sticks per GPU batch of the ensemble path (56 networks at 100x100 um = 32 systems for
-                              # each of the 7 resident 16-CTA clusters; measured 53.6 / 55.7 / 57.1 networks/s at
-                              # 14 / 28 / 56 networks per batch: the tail of the work queue is amortised; ~2 GB)
+BATCH_STICKS = 23_200_000     # sticks per GPU batch of the ensemble path (224 networks at 100x100 um, ~8 GB): the
+                              # direct solver's ~45 rounds are a fixed latency per batch, measured 1999 / 2240 / 2346
+                              # networks/s at 56 / 112 / 224 networks per batch
 
 
 def checkdir(directoryname):

@@ -10,6 +10,11 @@ from networksim_cntfet_b200.engine import Engine
 
 number = int(os.environ.get("ENS_NUMBER", "1000"))
 eng = pkg.set_engine(Engine(profile=True))
+eng.solver = os.environ.get("ENS_SOLVER", "auto")
+if os.environ.get("ENS_MAX_FILL"):
+    eng.direct_max_fill = float(os.environ["ENS_MAX_FILL"])
+if os.environ.get("ENS_MAX_DEGREE"):
+    eng.direct_max_degree = float(os.environ["ENS_MAX_DEGREE"])
 os.makedirs("/tmp/ens20", exist_ok=True); os.chdir("/tmp/ens20")
 seeds = list(range(1, number + 1))
 step = (8000 - 400) / max(number - 1, 1)
@@ -22,3 +27,4 @@ for rep in range(2):
     nets = df.seed.nunique()
     print("rep%d: %d networks (n = 400..8000) in %.2f s -> %.1f networks/s; percolating rows %d; stages ms %s"
           % (rep, nets, dt, nets / dt, int((df.ion > 0).sum()), {k: round(v, 1) for k, v in st.items()}), flush=True)
+    print("   solver", eng.last_solver, getattr(eng, "last_direct", None), flush=True)
