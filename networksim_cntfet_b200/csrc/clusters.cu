@@ -8,10 +8,16 @@
 
 namespace {
 
-__device__ __forceinline__ int uf_find(int *parent, int x) {
-    // path halving; plain loads/stores are safe: parents only ever decrease towards the root
+// path halving; plain loads/stores are safe: parents only ever decrease towards the root.  `s0` is the first
+// stick of x's network: the smallest id of the network, hence ALWAYS a root -- it is recognised without
+// loading parent[s0].  In a percolating network s0 (the source electrode) is the root of the giant component,
+// i.e. the end of almost every chase: that one cache line was read ~130k times per network through L2
+// (volatile), serialised at the slice, and made the union pass latency-bound (ncu: 3 % issue slots busy).
+__device__ __forceinline__ int uf_find(int *parent, int x, int s0) {
+    if (x == s0) return x;
     int p = ((volatile int *)parent)[x];
     while (p != x) {
+        if (p == s0) return p;
         int gp = ((volatile int *)parent)[p];
         if (gp != p) ((volatile int *)parent)[x] = gp;
         x = p;
@@ -30,25 +36,80 @@ __global__ void k_uf_init(int64_t S, int32_t *__restrict__ parent, int32_t *__re
     }
 }
 
-__global__ void k_uf_union(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff, int64_t J,
-                           const int32_t *__restrict__ stick1, const int32_t *__restrict__ stick2,
-                           int32_t *parent, uint8_t *__restrict__ hasj) {
-    int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= J) return;
-    int b = cnt::find_segment(joff, B, (int)e);
-    int s0 = soff[b];
-    int a = s0 + stick1[e], c = s0 + stick2[e];
-    hasj[a] = 1;
-    hasj[c] = 1;
-    while (true) {
-        a = uf_find(parent, a);
-        c = uf_find(parent, c);
-        if (a == c) break;
-        int hi = a > c ? a : c, lo = a > c ? c : a;
-        int old = atomicCAS(parent + hi, hi, lo);
-        if (old == hi) break;
-        a = hi;  // someone else re-parented hi: retry from the current roots
-        c = lo;
+// Every thread walks UF_K junctions at once: the 2 * UF_K root chases are independent chains of L2 round trips
+// (volatile loads, ~18 hops each), so their loads are issued side by side -- the pass is latency-bound (ncu on the
+// one-junction-per-thread version: 3 % of the issue slots busy, 430 cycles per instruction), memory-level
+// parallelism per thread is what it lacked.  Junction e of a thread = first + k * stride (coalesced index loads).
+constexpr int UF_K = 4;
+__global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff,
+                                                  int64_t J, const int32_t *__restrict__ stick1,
+                                                  const int32_t *__restrict__ stick2, int32_t *parent,
+                                                  uint8_t *__restrict__ hasj) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    volatile int *vp = (volatile int *)parent;
+    int cur[2 * UF_K], par[2 * UF_K], base[UF_K];
+    bool live[UF_K];
+#pragma unroll
+    for (int k = 0; k < UF_K; k++) {
+        const int64_t e = first + k * stride;
+        live[k] = e < J;
+        base[k] = 0;
+        cur[2 * k] = cur[2 * k + 1] = 0;
+        if (live[k]) {
+            const int b = cnt::find_segment(joff, B, (int)e);
+            const int s0 = soff[b];
+            base[k] = s0;
+            cur[2 * k] = s0 + stick1[e];
+            cur[2 * k + 1] = s0 + stick2[e];
+            hasj[cur[2 * k]] = 1;
+            hasj[cur[2 * k + 1]] = 1;
+        }
+    }
+    // roots of all endpoints, path halving, the chases interleaved; s0 of a network is a root by construction
+#pragma unroll
+    for (int k = 0; k < 2 * UF_K; k++) par[k] = live[k >> 1] && cur[k] != base[k >> 1] ? vp[cur[k]] : cur[k];
+    for (;;) {
+        bool any = false;
+        int gp[2 * UF_K];
+#pragma unroll
+        for (int k = 0; k < 2 * UF_K; k++) {
+            gp[k] = par[k];
+            if (par[k] != cur[k] && par[k] != base[k >> 1]) {
+                gp[k] = vp[par[k]];
+                any = true;
+            }
+        }
+        if (!any) break;
+#pragma unroll
+        for (int k = 0; k < 2 * UF_K; k++) {
+            if (par[k] != cur[k]) {
+                if (par[k] == base[k >> 1]) {          // reached the network's first stick: a root
+                    cur[k] = par[k];
+                } else {
+                    if (gp[k] != par[k]) vp[cur[k]] = gp[k];
+                    cur[k] = par[k];
+                    par[k] = gp[k];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 2 * UF_K; k++)
+        if (par[k] != cur[k]) cur[k] = par[k];          // stopped at s0
+    // hook the larger root under the smaller; a lost race is replayed from the current roots
+#pragma unroll
+    for (int k = 0; k < UF_K; k++) {
+        if (!live[k]) continue;
+        int a = cur[2 * k], c = cur[2 * k + 1];
+        const int s0 = base[k];
+        while (a != c) {
+            const int hi = a > c ? a : c, lo = a > c ? c : a;
+            const int old = atomicCAS(parent + hi, hi, lo);
+            if (old == hi) break;
+            a = uf_find(parent, hi, s0);  // someone else re-parented hi: retry from the current roots
+            c = uf_find(parent, lo, s0);
+        }
     }
 }
 
@@ -58,7 +119,7 @@ __global__ void k_uf_flatten(int B, const int32_t *__restrict__ soff, int64_t S,
     int r = -1;
     if (s < S) {
         int b = cnt::find_segment(soff, B, (int)s);
-        r = uf_find(parent, (int)s);
+        r = uf_find(parent, (int)s, soff[b]);
         label[s] = r - soff[b];
     }
     // component sizes: one atomic per group of equal roots inside the warp (the big component is most of a network)
@@ -179,7 +240,7 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
         CNT_LAUNCHED();
     }
     if (J > 0) {
-        k_uf_union<<<cnt::grid_for(J, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, parent, hasj);
+        k_uf_union<<<cnt::grid_for((J + UF_K - 1) / UF_K, 256), 256, 0, st>>>(B, soff, joff, J, stick1, stick2, parent, hasj);
         CNT_LAUNCHED();
     }
     if (S > 0) {

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     int32_t *s_rng = s_pre + CAP_HOME + 1;                        // [CAP_HOME] packed cell range (region-relative)
     int32_t *s_cnt = s_rng + CAP_HOME;                            // [CAP_HOME + 1] junctions per home stick / row offsets
     int32_t *s_hq = s_cnt + CAP_HOME + 1;                         // [CAP_HOME] region index of every home stick
+    int32_t *s_blk = s_hq + CAP_HOME;                             // [CAP_Q / 32] home stick of every 32nd pair of a chunk
     __shared__ int s_red[8];
     __shared__ int s_nq, s_nhit, s_base, s_warp[CT / 32];
     __shared__ unsigned long long s_tests;
@@ -165,17 +166,23 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     const int32_t *cs = cell_start + g.coff;
     // home sticks: the records of the home cells, row by row
     __shared__ int s_nhrow[TILE_C + 1], s_hq0[TILE_C];
-    if (tid == 0) {
-        int acc = 0;
-        for (int r = 0; r < TILE_C; r++) {
-            s_nhrow[r] = acc;
-            s_hq0[r] = 0;
-            if (hy0 + r <= hy1) {
-                s_hq0[r] = __ldg(cs + (hy0 + r) * g.G + hx0);
-                acc += __ldg(cs + (hy0 + r) * g.G + hx1 + 1) - s_hq0[r];
-            }
+    if (wid == 0) {                                               // one lane per home row: loads side by side, warp scan
+        int q0 = 0, cnt_r = 0;
+        if (lane < TILE_C && hy0 + lane <= hy1) {
+            q0 = __ldg(cs + (hy0 + lane) * g.G + hx0);
+            cnt_r = __ldg(cs + (hy0 + lane) * g.G + hx1 + 1) - q0;
         }
-        s_nhrow[TILE_C] = acc;
+        int inc = cnt_r;
+#pragma unroll
+        for (int o = 1; o < TILE_C; o <<= 1) {
+            const int t = __shfl_up_sync(~0u, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane < TILE_C) {
+            s_hq0[lane] = q0;
+            s_nhrow[lane] = inc - cnt_r;
+        }
+        if (lane == TILE_C - 1) s_nhrow[TILE_C] = inc;
     }
     __syncthreads();
     const int nhome = s_nhrow[TILE_C];
@@ -215,15 +222,22 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     rx0 = s_red[0]; rx1 = s_red[1]; ry0 = s_red[2]; ry1 = s_red[3];
     const int RW = rx1 - rx0 + 1, RH = ry1 - ry0 + 1;            // <= MAX_RH by construction (len * G <= RMAX)
     // region rows: global start, region-index start; cell starts as region indices
-    if (tid < RH) s_gq0[tid] = __ldg(cs + (ry0 + tid) * g.G + rx0);
-    __syncthreads();
-    if (tid == 0) {
-        int acc = 0;
-        for (int r = 0; r < RH; r++) {
-            s_rb[r] = acc;
-            acc += __ldg(cs + (ry0 + r) * g.G + rx1 + 1) - s_gq0[r];
+    static_assert(MAX_RH <= 32, "region rows are scanned by one warp");
+    if (wid == 0) {                                               // one lane per region row
+        int q0 = 0, cnt_r = 0;
+        if (lane < RH) {
+            q0 = __ldg(cs + (ry0 + lane) * g.G + rx0);
+            cnt_r = __ldg(cs + (ry0 + lane) * g.G + rx1 + 1) - q0;
+            s_gq0[lane] = q0;
         }
-        s_rb[RH] = acc;
+        int inc = cnt_r;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(~0u, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane < RH) s_rb[lane] = inc - cnt_r;
+        if (lane == RH - 1) s_rb[RH] = inc;
     }
     __syncthreads();
     const int nrec = s_rb[RH];
@@ -297,93 +311,70 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         if (tid < nb) s_pre[tid] = s_warp[wid] + inc - ncand;
         if (tid == nb - 1) s_pre[nb] = s_warp[wid] + inc;
         __syncthreads();
-        // chunks of home sticks whose candidate pairs (s_pre) fit the survivor queue; inside a chunk every home stick
-        // is walked by a group of GL lanes: cell rows one after the other, the records of a row (contiguous in the
-        // region) GL at a time.  Phase 1 (cheap): j > i and the KD ball; survivors -> queue (ballot over the lanes
-        // that are converged + one shared atomic per ballot).  Phase 2 (FP64 predicate, two IEEE divisions) on the
-        // compacted queue with full warps.
-        constexpr int GL = 8, NGRP = CT / GL;
-        const int grp = tid / GL, sub = tid - grp * GL;
-        auto emit = [&](int h, int v) {                          // predicate of (home stick h of the batch, region record v)
-            const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
-            double xi, yi;
-            if (cnt_junction(l1, l2, &xi, &yi)) {
-                const int rank = atomicAdd(&s_cnt[h], 1);
-                const int at = atomicAdd(&s_nhit, 1);
-                if (at < CAP_HIT) {
-                    Hit hh;
-                    hh.hr = (h << 16) | (rank & 0xFFFF);
-                    hh.j = recA(v).idx;
-                    hh.x = xi;
-                    hh.y = yi;
-                    s_hit[at] = hh;
-                }
-            }
-        };
-        for (int h_lo = 0; h_lo < nb;) {
-            // largest h_hi with s_pre[h_hi] - s_pre[h_lo] <= CAP_Q (uniform: every thread computes the same)
-            const int lim = s_pre[h_lo] + CAP_Q;
-            int h_hi = h_lo + 1;
-            const bool giant = s_pre[h_hi] > lim;                // ONE home stick with more candidates than the queue holds
-            if (!giant) {
-                int lo = h_hi, hi = nb;
-                while (lo < hi) {
-                    const int mid = (lo + hi + 1) >> 1;
-                    if (s_pre[mid] <= lim) lo = mid; else hi = mid - 1;
-                }
-                h_hi = lo;
-            }
+        const int P = s_pre[nb];
+        for (int p0 = 0; p0 < P; p0 += CAP_Q) {                  // chunks of candidate pairs
             if (tid == 0) s_nq = 0;
+            // s_blk[k] = home stick owning pair p0 + 32 k: every home stick fills the blocks that start inside its range
+            if (tid < nb) {
+                const int a = max(s_pre[tid], p0), e = min(s_pre[tid + 1], min(P, p0 + CAP_Q));
+                for (int k = (a - p0 + 31) >> 5; p0 + 32 * k < e; k++) s_blk[k] = tid;
+            }
             __syncthreads();
-            if (giant) {
-                // no queue: the whole CTA walks the stick's candidates and evaluates the predicate in place
-                const int h = h_lo, rng = s_rng[h];
-                const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
-                const RecA me = recA(s_hq[h]);
-                for (int cy = cy0; cy <= cy1; cy++) {
-                    const int a0 = s_cs[cy * (RW + 1) + cx0], a1 = s_cs[cy * (RW + 1) + cx1 + 1];
-                    for (int v = a0 + tid; v < a1; v += CT) {
-                        const RecA o = recA(v);
-                        if (o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc)) {
-                            tests++;
-                            emit(h, v);
-                        }
-                    }
-                }
-            } else {
-                for (int h = h_lo + grp; h < h_hi; h += NGRP) {
+            // phase 1 (cheap): j > i and the KD ball; survivors -> queue (warp ballot + one shared atomic per warp)
+            const int pend = min(P, p0 + CAP_Q);
+            for (int pp = p0 + tid; pp < ((pend + 31) & ~31); pp += CT) {
+                bool pass = false;
+                int entry = 0;
+                if (pp < pend) {
+                    int h = s_blk[(pp - p0) >> 5];                // home stick of the first pair of this warp's 32 pairs
+                    while (s_pre[h + 1] <= pp) h++;               // ... a few steps further for this lane
                     const int rng = s_rng[h];
                     const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
-                    const RecA me = recA(s_hq[h]);
+                    int c = pp - s_pre[h], v = -1;
                     for (int cy = cy0; cy <= cy1; cy++) {
                         const int a0 = s_cs[cy * (RW + 1) + cx0], a1 = s_cs[cy * (RW + 1) + cx1 + 1];
-                        for (int v = a0 + sub; v < a1; v += GL) {
-                            const RecA o = recA(v);
-                            const bool pass = o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc);
-                            const unsigned act = __activemask();
-                            const unsigned m = __ballot_sync(act, pass);
-                            if (m) {
-                                const int leader = __ffs(m) - 1;
-                                int base = 0;
-                                if (lane == leader) base = atomicAdd(&s_nq, __popc(m));
-                                base = __shfl_sync(act, base, leader);
-                                if (pass) {
-                                    s_q[base + __popc(m & ((1u << lane) - 1u))] = (h << 23) | v;
-                                    tests++;
-                                }
-                            }
+                        if (c < a1 - a0) {
+                            v = a0 + c;
+                            break;
                         }
+                        c -= a1 - a0;
                     }
+                    const RecA me = recA(s_hq[h]), o = recA(v);
+                    pass = o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc);
+                    entry = (h << 23) | v;
                 }
-                __syncthreads();
-                const int nq = s_nq;
-                for (int k = tid; k < nq; k += CT) {
-                    const int entry = s_q[k];
-                    emit(entry >> 23, entry & ((1 << 23) - 1));
+                const unsigned m = __ballot_sync(~0u, pass);
+                if (m) {
+                    int base = 0;
+                    if (lane == __ffs(m) - 1) base = atomicAdd(&s_nq, __popc(m));
+                    base = __shfl_sync(~0u, base, __ffs(m) - 1);
+                    if (pass) {
+                        s_q[base + __popc(m & ((1u << lane) - 1u))] = entry;
+                        tests++;
+                    }
                 }
             }
             __syncthreads();
-            h_lo = h_hi;
+            // phase 2 (FP64 predicate) on the compacted queue: full warps
+            const int nq = s_nq;
+            for (int k = tid; k < nq; k += CT) {
+                const int entry = s_q[k], h = entry >> 23, v = entry & ((1 << 23) - 1);
+                const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
+                double xi, yi;
+                if (cnt_junction(l1, l2, &xi, &yi)) {
+                    const int rank = atomicAdd(&s_cnt[h], 1);
+                    const int at = atomicAdd(&s_nhit, 1);
+                    if (at < CAP_HIT) {
+                        Hit hh;
+                        hh.hr = (h << 16) | (rank & 0xFFFF);
+                        hh.j = recA(v).idx;
+                        hh.x = xi;
+                        hh.y = yi;
+                        s_hit[at] = hh;
+                    }
+                }
+            }
+            __syncthreads();
         }
         // rows of the batch: offsets (exclusive scan of s_cnt), space in the temporary table, write-out
         const int nhit = s_nhit;
@@ -524,33 +515,54 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
 }
 
 // ---- dense rows: long stick i against every later stick of its network ------------------
+// Rows 0 and 1 of a network (the electrodes: ~100k candidates each) are cut into DENSE_SEGS segments handled by
+// different CTAs -- 16 CTAs per network instead of 2; the count pass leaves the junctions per segment in segcnt
+// (and their sum in jcount), the fill pass starts every segment behind its predecessors, so the row comes out in
+// stick2 order.  Further long rows (small networks, where a body stick can span more than RMAX cells) are
+// walked by one CTA each (segment 0).
+constexpr int DENSE_SEGS = 8;    // segments of an electrode row
+constexpr int DENSE_SPLIT = 2;   // rows that are split
 template <bool FILL>
 __global__ void __launch_bounds__(DENSE_T) k_dense(int B, const int32_t *__restrict__ soff,
                                                    const int32_t *__restrict__ nlong,
                                                    const CntLine *__restrict__ line, const double *__restrict__ xc,
                                                    const double *__restrict__ yc, const double *__restrict__ len,
                                                    int32_t *__restrict__ jcount, unsigned long long *__restrict__ ntests,
+                                                   int32_t *__restrict__ segcnt /* [B][DENSE_SPLIT][DENSE_SEGS] */,
                                                    const int32_t *__restrict__ jstart, const uint8_t *__restrict__ kind,
                                                    int32_t *__restrict__ stick1, int32_t *__restrict__ stick2,
                                                    double *__restrict__ jx, double *__restrict__ jy,
                                                    uint8_t *__restrict__ kind2) {
     __shared__ int warp_cnt[DENSE_T / 32];
     __shared__ double red[32];
-    int b = blockIdx.y;
-    int s0 = soff[b], n = soff[b + 1] - s0;
-    int nl = nlong[b];
-    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    for (int i = blockIdx.x; i < nl; i += gridDim.x) {
+    const int b = blockIdx.y;
+    const int s0 = soff[b], n = soff[b + 1] - s0;
+    const int nl = nlong[b];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int rowslot = blockIdx.x / DENSE_SEGS, seg = blockIdx.x - rowslot * DENSE_SEGS;
+    for (int i = rowslot; i < nl; i += DENSE_ROWS) {
+        const bool split = i < DENSE_SPLIT;
+        if (!split && seg != 0) continue;                        // CTA-uniform
+        int jb = i + 1, je = n;
+        int32_t *sc = split ? segcnt + ((int64_t)b * DENSE_SPLIT + i) * DENSE_SEGS : nullptr;
+        int before_seg = 0;
+        if (split) {
+            const int seglen = ((n - i - 1 + DENSE_SEGS - 1) / DENSE_SEGS + DENSE_T - 1) / DENSE_T * DENSE_T;
+            jb = i + 1 + seg * seglen;
+            je = min(n, jb + seglen);
+            if (FILL)
+                for (int k = 0; k < seg; k++) before_seg += sc[k];
+        }
         CntLine l1 = line[s0 + i];
         double xci = xc[s0 + i], yci = yc[s0 + i], li = len[s0 + i];
-        int base = FILL ? jstart[s0 + i] : 0;
+        int base = FILL ? jstart[s0 + i] + before_seg : 0;
         int written = 0;                       // identical in every thread
         unsigned long long tests = 0;
-        for (int j0 = i + 1; j0 < n; j0 += DENSE_T) {
+        for (int j0 = jb; j0 < je; j0 += DENSE_T) {
             int j = j0 + threadIdx.x;
             bool hit = false;
             double xi = 0, yi = 0;
-            if (j < n && cnt_in_ball(xci, yci, li, xc[s0 + j], yc[s0 + j])) {
+            if (j < je && cnt_in_ball(xci, yci, li, xc[s0 + j], yc[s0 + j])) {
                 tests++;
                 CntLine l2 = line[s0 + j];
                 hit = cnt_junction(l1, l2, &xi, &yi);
@@ -578,7 +590,14 @@ __global__ void __launch_bounds__(DENSE_T) k_dense(int B, const int32_t *__restr
             __syncthreads();
         }
         if (!FILL) {
-            if (threadIdx.x == 0) jcount[s0 + i] = written;
+            if (threadIdx.x == 0) {
+                if (split) {
+                    sc[seg] = written;
+                    if (written) atomicAdd(jcount + s0 + i, written);     // jcount is cleared before the pass
+                } else {
+                    jcount[s0 + i] = written;
+                }
+            }
             double t = cnt::block_sum((double)tests, red);   // exact: counts < 2^53
             if (threadIdx.x == 0 && t > 0) atomicAdd(ntests + b, (unsigned long long)t);
         }
@@ -599,7 +618,7 @@ struct Plan {
     CntLine *line;
     RecA *recA;
     CntLine *recB;
-    int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag, *ntmp, *jtmp, *tj;
+    int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag, *ntmp, *jtmp, *tj, *segcnt;
     double *tx, *ty;
     void *scan_ws;
     int64_t scan_ws_bytes;
@@ -613,6 +632,7 @@ static int64_t plan_bytes(int B, int64_t S, int64_t total_cells) {
     return ws_bytes_for(B + 1, sizeof(Geo)) + ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, sizeof(RecA)) +
            ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, 4) + ws_bytes_for(total_cells + 1, 4) +
            ws_bytes_for(total_cells + 1, 4) + ws_bytes_for(B, 4) + ws_bytes_for(2, 4) + ws_bytes_for(S + 1, 4) +
+           ws_bytes_for((int64_t)B * DENSE_SPLIT * DENSE_SEGS, 4) +
            ws_bytes_for(ct, 4) + 2 * ws_bytes_for(ct, 8) + cnt_scan_workspace_bytes(total_cells + 1);
 }
 
@@ -655,6 +675,7 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
     p.errflag = w.take<int32_t>(2);
     p.ntmp = p.errflag ? p.errflag + 1 : nullptr;
     p.jtmp = w.take<int32_t>(p.S + 1);
+    p.segcnt = w.take<int32_t>((int64_t)B * DENSE_SPLIT * DENSE_SEGS);
     p.tj = w.take<int32_t>(p.cap_tmp);
     p.tx = w.take<double>(p.cap_tmp);
     p.ty = w.take<double>(p.cap_tmp);
@@ -671,7 +692,7 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
 static size_t tiles_smem() {
     return (size_t)CAP_REC * (sizeof(RecA) + sizeof(CntLine)) + (size_t)CAP_HIT * sizeof(Hit) +
            4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
-                CAP_HOME);
+                CAP_HOME + CAP_Q / 32);
 }
 }  // namespace
 
@@ -722,9 +743,9 @@ extern "C" int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_s
     k_tiles<<<(unsigned)p.total_tiles, CT, tiles_smem(), st>>>(B, p.d_geo, p.cell_count, p.recA, p.recB, jcount, p.jtmp,
                                                                ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag);
     CNT_LAUNCHED();
-    k_dense<false><<<dim3(DENSE_ROWS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, jcount, ntests,
-                                                            nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                                            nullptr);
+    k_dense<false><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, jcount,
+                                                                         ntests, p.segcnt, nullptr, nullptr, nullptr, nullptr,
+                                                                         nullptr, nullptr, nullptr);
     CNT_LAUNCHED();
     return CNT_OK;
 }
@@ -750,8 +771,9 @@ extern "C" int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_so
     k_cells_fill<<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells, p.recA,
                                                           p.recB, p.errflag, jstart, kind, stick1, stick2, jx, jy, kind2);
     CNT_LAUNCHED();
-    k_dense<true><<<dim3(DENSE_ROWS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, nullptr, nullptr,
-                                                           jstart, kind, stick1, stick2, jx, jy, kind2);
+    k_dense<true><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, nullptr,
+                                                                        nullptr, p.segcnt, jstart, kind, stick1, stick2, jx, jy,
+                                                                        kind2);
     CNT_LAUNCHED();
     return CNT_OK;
 }
