@@ -427,6 +427,7 @@ def gpu_arm(args):
     if rank == 0:
         sampler.start()
     launches0 = lib.cnt_launch_count()
+    mem0 = torch.cuda.memory_stats()
     def direct_total():
         tw = getattr(eng, "_twin", None)
         return getattr(eng, "direct_bytes_total", 0) + (getattr(tw, "direct_bytes_total", 0) if tw is not None else 0)
@@ -436,11 +437,16 @@ def gpu_arm(args):
     t_wall0 = time.perf_counter()
     cur_stream = torch.cuda.current_stream()         # every engine stream is ordered after / before it (Engine._work)
     e0.record(cur_stream)
-    results = [res for k in range(args.steps) for res in device_step(1, k)]
+    results, step_wall = [], []
+    for k in range(args.steps):
+        ts = time.perf_counter()
+        results.extend(device_step(1, k))
+        step_wall.append(1e3 * (time.perf_counter() - ts))
     e1.record(cur_stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.cnt_launch_count() - launches0
+    mem1 = torch.cuda.memory_stats()
     direct_bytes = direct_total() - direct_bytes0
     solver_used = eng.last_solver
     direct_info = dict(getattr(eng, "last_direct", None) or {})
@@ -456,15 +462,27 @@ def gpu_arm(args):
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
+    e2e_parts = [0.0, 0.0, 0.0]
     for k in range(args.steps):
-        df, io = measure_perc.measure_ensemble(ns * E, args.scaling, seeds_for(3, k, count=B * E), onoffmap=args.onoffmap,
+        ta = time.perf_counter()
+        sd = seeds_for(3, k, count=B * E)
+        tb = time.perf_counter()
+        df, io = measure_perc.measure_ensemble(ns * E, args.scaling, sd, onoffmap=args.onoffmap,
                                                rtol=args.rtol, return_io=True)
+        tc = time.perf_counter()
         fixed = np.full((3 * B * E, 2), np.nan)                      # <= 3 rows per network; equal shape on every rank
         fixed[:len(df)] = df[["ion", "ioff"]].to_numpy(dtype=np.float64)
         gather_rows(fixed)
         h2d, d2h = io["h2d_bytes"], io["d2h_bytes"]
+        td = time.perf_counter()
+        e2e_parts = [e2e_parts[0] + tb - ta, e2e_parts[1] + tc - tb, e2e_parts[2] + td - tc]
     barrier()
     e2e_s = time.perf_counter() - t0
+    mem2 = torch.cuda.memory_stats()
+    memkeys = ("num_device_alloc", "num_device_free", "num_alloc_retries")
+    allocator = {"timed_device_loop": {k: mem1.get(k, 0) - mem0.get(k, 0) for k in memkeys},
+                 "e2e_loop": {k: mem2.get(k, 0) - mem1.get(k, 0) for k in memkeys},
+                 "reserved_GB": mem2.get("reserved_bytes.all.peak", 0) / 1e9}
 
     # ---- reduce over ranks (max time)
     tt = torch.tensor([dev_ms, e2e_s * 1e3, t_wall * 1e3], dtype=torch.float64, device=eng.device)
@@ -557,7 +575,12 @@ def gpu_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload(args), "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-            "gpu_launches": int(cnt.item()), "clocks": clocks,
+            "gpu_launches": int(cnt.item()), "clocks": clocks, "allocator_cudaMalloc_calls": allocator, "wall_ms_of_every_timed_step": [round(v, 2) for v in step_wall],
+            "symbolic_attempts_total": getattr(eng, "direct_attempts", None),
+            "junction_fallback_batches": getattr(eng, "junction_fallbacks", 0),
+            "e2e_host_breakdown_ms_per_step": {"seeds": 1e3 * e2e_parts[0] / max(args.steps, 1),
+                                               "measure_ensemble": 1e3 * e2e_parts[1] / max(args.steps, 1),
+                                               "rows_gather": 1e3 * e2e_parts[2] / max(args.steps, 1)},
             "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
             "junction_tests_per_s": (ntests / jt) if jt > 0 else None, "junction_tests": ntests,
             "junction_roofline": {"bound": "fp64", "unit": "TFLOP/s", "flops_per_test": 17,

@@ -14,8 +14,9 @@
 // writes the tile's junctions grouped by home stick to a temporary table.  The predicate is
 // evaluated ONCE: after the scan of the row lengths k_place copies every row to its place and
 // orders it by stick2, so the output is compact, deterministic and sorted by
-// (network, stick1, stick2).  If the temporary table overflows (more than ~8 junctions per stick)
-// the rows are recomputed in place by the thread-per-stick kernel k_cells<true> instead.
+// (network, stick1, stick2).  A batch of home sticks that runs out of hit buffer (more than CAP_HIT junctions) or
+// of temporary table space (more than ~8 junctions per stick overall) only counts; exactly its rows are then
+// recomputed in place by the thread-per-row kernel k_cells_fill.
 #include <vector>
 #include "common.cuh"
 #include "predicate.cuh"
@@ -406,7 +407,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                 base = atomicAdd(ntmp, nhit);
                 if ((int64_t)base + nhit > cap_tmp) ok = false;
             }
-            if (!ok) atomicOr(errflag, 2);                        // rows will be recomputed by k_cells<true>
+            if (!ok) atomicOr(errflag, 2);                        // the rows of this batch will be recomputed by k_cells_fill
             s_base = ok ? base : -1;
         }
         __syncthreads();
@@ -444,11 +445,11 @@ __global__ void k_place(int B, const int32_t *__restrict__ soff, int64_t S, cons
                         const uint8_t *__restrict__ kind, const int32_t *__restrict__ errflag,
                         int32_t *__restrict__ stick1, int32_t *__restrict__ stick2, double *__restrict__ jx,
                         double *__restrict__ jy, uint8_t *__restrict__ kind2) {
-    if (*errflag & 2) return;                                     // temporary table overflowed: k_cells<true> fills
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     const int t0 = jtmp[s], base = jstart[s], cnt = jstart[s + 1] - base;
-    if (t0 < 0 || cnt == 0) return;                               // long stick (k_dense) or empty row
+    if (t0 < 0 || cnt == 0) return;                               // long stick (k_dense), empty row, or a row whose tile
+                                                                  // ran out of buffer space (k_cells_fill recomputes it)
     const int b = cnt::find_segment(soff, B, (int)s);
     const int s0 = soff[b], i = (int)s - s0;
     const uint8_t ki = kind[s];
@@ -468,11 +469,12 @@ __global__ void k_place(int B, const int32_t *__restrict__ soff, int64_t S, cons
     }
 }
 
-// ---- fallback: one thread per binned stick recomputes its row in place (temporary table overflowed) ----
+// ---- fallback: the rows of home-stick batches that ran out of hit buffer / temporary table space (jtmp < 0) are
+// recomputed in place, one thread per row; errflag bit 1 says whether there is any such row ----
 __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__restrict__ soff, const Geo *__restrict__ geo,
                                                     const int32_t *__restrict__ cell_start, int32_t total_cells,
                                                     const RecA *__restrict__ recA, const CntLine *__restrict__ recB,
-                                                    const int32_t *__restrict__ errflag,
+                                                    const int32_t *__restrict__ errflag, const int32_t *__restrict__ jtmp,
                                                     const int32_t *__restrict__ jstart, const uint8_t *__restrict__ kind,
                                                     int32_t *__restrict__ stick1, int32_t *__restrict__ stick2,
                                                     double *__restrict__ jx, double *__restrict__ jy,
@@ -482,6 +484,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
     int nbinned = __ldg(cell_start + total_cells);
     if (p >= nbinned) return;
     const RecA me = recA[p];
+    if (jtmp[me.gid] >= 0 || jstart[me.gid + 1] == jstart[me.gid]) return;       // placed by k_place / nothing to place
     const int b = cnt::find_segment(soff, B, me.gid);
     const Geo g = geo[b];
     const CntLine l1 = recB[p];
@@ -769,7 +772,7 @@ extern "C" int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_so
                                                      stick2, jx, jy, kind2);
     CNT_LAUNCHED();
     k_cells_fill<<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells, p.recA,
-                                                          p.recB, p.errflag, jstart, kind, stick1, stick2, jx, jy, kind2);
+                                                          p.recB, p.errflag, p.jtmp, jstart, kind, stick1, stick2, jx, jy, kind2);
     CNT_LAUNCHED();
     k_dense<true><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, nullptr,
                                                                         nullptr, p.segcnt, jstart, kind, stick1, stick2, jx, jy,

@@ -125,6 +125,14 @@ class Engine(object):
         self.lib = _lib.load()
         self.device = torch.device(device if device is not None else "cuda:%d" % torch.cuda.current_device())
         torch.cuda.set_device(self.device)
+        # the buffers of a batch are sized by its junction / row / entry counts, which differ by a fraction of a
+        # percent from batch to batch: without rounding almost every large request misses the caching allocator's free
+        # blocks and goes to cudaMalloc (a device synchronisation each).  16 size classes per power of two.
+        if os.environ.get("CNT_ALLOC_ROUNDING", "1") != "0":
+            try:
+                torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:16")
+            except Exception:
+                pass
         self.stream = torch.cuda.Stream(device=self.device)
         self.stream_ptr = C.c_void_p(self.stream.cuda_stream)
         self.profile = bool(profile)
@@ -314,7 +322,8 @@ class Engine(object):
             off = flagp.value - b._jws.data_ptr()
             # one small D2H: total junction count + flags (bit 0: table not sorted, bit 1: temporary table overflowed)
             total, flag = torch.cat([jstart[b.S:b.S + 1], b._jws[off:off + 4].view(torch.int32)]).cpu().tolist()
-            b.junction_rows_recomputed = bool(flag & 2)      # temporary junction table overflowed: slower fill path
+            b.junction_rows_recomputed = bool(flag & 2)      # some tile ran out of buffer space: its rows are recomputed
+            self.junction_fallbacks = getattr(self, "junction_fallbacks", 0) + int(bool(flag & 2))
             if flag & 1:
                 raise _lib.CntError("stick table is not sorted by length descending (netsim.py:133)")
             b.J = total
@@ -623,6 +632,7 @@ class Engine(object):
                     b._sm_plan = False
                     return None
                 b._sm_plan = plan
+                self.direct_attempts = getattr(self, "direct_attempts", 0) + plan.attempts    # > 1 per plan: capacities grew
                 self._direct_rounds_hint = min(plan.nrounds + 4, 400)     # first read-back of the next batch
                 self._direct_hint = starmesh.Plan()                        # header only: sizes the next batch's grids
                 self._direct_hint.info = plan.info

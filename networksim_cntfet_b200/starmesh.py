@@ -103,7 +103,9 @@ def symbolic(lib, stream_ptr, device, B, roff, R, NNZ, rowptr, col, dense_max=0,
     plan = Plan()
     plan.R, plan.B, plan.NNZ = int(R), int(B), int(NNZ)
     vp = C.c_void_p
+    plan.attempts = 0
     while True:
+        plan.attempts += 1
         cap_slots = int(slot_factor * nE0) + slack
         cap_contrib = int(fill_factor * nE0) + slack
         if budget is not None:

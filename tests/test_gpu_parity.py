@@ -72,6 +72,22 @@ def test_junctions_and_clusters_ragged_batch(engine):
             assert stats[i, _lib.STAT_ECOMP] == int((g["label"][g["stick1"]] == 0).sum())
 
 
+def test_tile_buffer_overflow_rows_are_recomputed(engine):
+    """dense networks (constant stick length 1 um on 10x10 um: ~38 junctions per stick) overflow the tile kernel's
+    hit buffer and the temporary table: exactly the rows of the affected home-stick batches are recomputed by
+    k_cells_fill; a sparse network in the same batch keeps the fast path.  Sets, coordinates, ntests vs the oracle."""
+    b = engine.generate([6000, 300, 3000], [10.0, 5.0, 8.0], seed=9, l=1.0)
+    engine.find_junctions(b)
+    assert b.junction_rows_recomputed
+    js = _junction_slices(b)
+    nt = b.ntests.cpu().numpy()
+    for i, s in enumerate(engine.sticks_to_host(b)):
+        j = O.find_junctions(s)
+        assert len(j["stick1"]) > 0
+        _check_junctions(js[i], dict(stick1=j["stick1"], stick2=j["stick2"], jx=j["x"], jy=j["y"], kind2=j["kind2"]))
+        assert int(nt[i]) == j["ntests"]
+
+
 def test_scan(engine):
     import torch
     from networksim_cntfet_b200 import _lib
