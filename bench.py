@@ -300,7 +300,7 @@ def extra_legs(args, eng, world, rank, dist, peak):
             sync()
             t0 = time.perf_counter()
             if world > 1:
-                df, res = measure_perc.measure_fullnet_distributed(n, side, seed=5, mode="rows")
+                df, res = measure_perc.measure_fullnet_distributed(n, side, seed=5, mode="slab")
             else:
                 b = eng.generate([n], side, seeds=[5])
                 res = eng.measure_fullnet(b, onoffmap=1)
@@ -308,8 +308,8 @@ def extra_legs(args, eng, world, rank, dist, peak):
             best = time.perf_counter() - t0
         return {"workload": "ONE %gx%g um network, %d sticks, measure_fullnet (4 solves)" % (side, side, n), "seconds": best,
                 "sticks_per_s": n / best, "ranks": world, "solver": eng.last_solver,
-                "mode": "rows of the system sharded over the ranks (halo exchange + all-reduces over NCCL)" if world > 1
-                        else "one GPU", "ion": float(res["ion"][0]), "iters": [int(v) for v in res["iters"][:, 0]],
+                "mode": "junction search sharded by spatial slab over the ranks, junction rows exchanged over NCCL; labels, "
+                        "assembly and direct solve replicated" if world > 1 else "one GPU", "ion": float(res["ion"][0]), "iters": [int(v) for v in res["iters"][:, 0]],
                 "timing": "wall clock between synchronisations, second repetition"}
     leg("config5_single_network", config5, every_rank=True)
 

@@ -100,6 +100,26 @@ int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_soff,
                       const int32_t *jstart, int64_t J,
                       int32_t *stick1, int32_t *stick2, double *jx, double *jy, uint8_t *kind2,
                       int32_t *joff, void *ws, int64_t ws_bytes, void *stream);
+
+/* The same search sharded by spatial slab over `shard_world` ranks (one process per GPU; BASELINE config 5, a single
+ * huge network -- the reference cannot spread one make_intersects_kdtree over workers).  The unit box is cut into
+ * vertical slabs of whole tile columns (8 cells); rank r evaluates the home sticks whose centre lies in slab r
+ * against the sticks around them (the halo across the slab boundary is read from the stick table, which every
+ * rank holds), rank 0 also the long sticks (electrodes).  _count_slab leaves 0 in jcount for the rows of other
+ * ranks: the caller ADDS jcount and ntests over the ranks (all-reduce), scans, and calls _fill_slab on zero-filled
+ * tables; the tables of the ranks have disjoint supports, so adding them (all-reduce; the doubles as int64 bit
+ * patterns) gives bit for bit the table of the unsharded search.  shard_world = 1 is cnt_junction_count / _fill. */
+int cnt_junction_count_slab(int B, const int32_t *soff, const int32_t *h_soff,
+                            const double *xa, const double *ya, const double *xb, const double *yb,
+                            const double *xc, const double *yc, const double *length,
+                            int32_t *jcount, unsigned long long *ntests,
+                            void *ws, int64_t ws_bytes, int shard_rank, int shard_world, void *stream);
+int cnt_junction_fill_slab(int B, const int32_t *soff, const int32_t *h_soff,
+                           const double *xa, const double *ya, const double *xb, const double *yb,
+                           const double *xc, const double *yc, const double *length, const uint8_t *kind,
+                           const int32_t *jstart, int64_t J, int32_t *stick1, int32_t *stick2, double *jx,
+                           double *jy, uint8_t *kind2, int32_t *joff, void *ws, int64_t ws_bytes,
+                           int shard_rank, int shard_world, void *stream);
 /* device pointer (inside ws) of the sortedness flag written by the last _count: non-zero if
  * some network's table was not sorted by length descending (netsim.py:133 invariant). */
 int cnt_junction_errflag_ptr(int B, const int32_t *h_soff, void *ws, int64_t ws_bytes, int32_t **out);

@@ -34,6 +34,8 @@ PROTOTYPES = {
     "cnt_junction_workspace_bytes": (i64, [i32, I32P]),
     "cnt_junction_count": (i32, [i32, vp, I32P] + [vp] * 7 + [vp, vp, vp, i64, vp]),
     "cnt_junction_fill": (i32, [i32, vp, I32P] + [vp] * 8 + [vp, i64] + [vp] * 5 + [vp, vp, i64, vp]),
+    "cnt_junction_count_slab": (i32, [i32, vp, I32P] + [vp] * 7 + [vp, vp, vp, i64, i32, i32, vp]),
+    "cnt_junction_fill_slab": (i32, [i32, vp, I32P] + [vp] * 8 + [vp, i64] + [vp] * 5 + [vp, vp, i64, i32, i32, vp]),
     "cnt_junction_errflag_ptr": (i32, [i32, I32P, vp, i64, C.POINTER(vp)]),
     "cnt_cluster_workspace_bytes": (i64, [i64]),
     "cnt_label_clusters": (i32, [i32, vp, vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),

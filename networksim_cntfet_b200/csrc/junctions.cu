@@ -121,6 +121,15 @@ __device__ __forceinline__ void cell_range(const RecA &me, int G, int &cx0, int 
 }
 
 // ---- tile kernel: one CTA per tile of TILE_C x TILE_C cells ---------------------------------
+// Slab sharding of ONE junction search over several ranks (config 5: a single huge network on several GPUs).  The unit
+// box is cut into `world` vertical slabs of whole tile columns; a rank evaluates the tiles -- i.e. the home sticks
+// whose centre lies -- in its slab, reading the halo sticks around it from the (replicated) binned table, and leaves
+// the rows of all other home sticks empty.  Rank 0 also takes the long sticks (electrodes).  The caller adds the
+// per-rank jcount / ntests and the per-rank tables (disjoint supports, everything else zero) over the ranks.
+__host__ __device__ __forceinline__ int slab_owner(int tile_col, int TG, int world) {
+    return (int)(((long long)tile_col * world) / TG);
+}
+
 struct Hit {
     int32_t hr;                  // home stick (batch-local) << 16 | arrival rank inside its row
     int32_t j;
@@ -132,7 +141,8 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                                               const CntLine *__restrict__ gB, int32_t *__restrict__ jcount,
                                               int32_t *__restrict__ jtmp, unsigned long long *__restrict__ ntests,
                                               int32_t *__restrict__ tj, double *__restrict__ tx, double *__restrict__ ty,
-                                              int64_t cap_tmp, int32_t *__restrict__ ntmp, int32_t *__restrict__ errflag) {
+                                              int64_t cap_tmp, int32_t *__restrict__ ntmp, int32_t *__restrict__ errflag,
+                                              int shard_rank, int shard_world) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RecA *sA = (RecA *)smem_raw;                                  // [CAP_REC]
     CntLine *sB = (CntLine *)(sA + CAP_REC);                      // [CAP_REC]
@@ -162,6 +172,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     }
     const Geo g = geo[b];
     const int tloc = blockIdx.x - g.toff, tyi = tloc / g.TG, txi = tloc - tyi * g.TG;
+    if (shard_world > 1 && slab_owner(txi, g.TG, shard_world) != shard_rank) return;     // another rank's slab
     const int hx0 = txi * TILE_C, hy0 = tyi * TILE_C;
     const int hx1 = min(hx0 + TILE_C, g.G) - 1, hy1 = min(hy0 + TILE_C, g.G) - 1;
     const int32_t *cs = cell_start + g.coff;
@@ -478,7 +489,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
                                                     const int32_t *__restrict__ jstart, const uint8_t *__restrict__ kind,
                                                     int32_t *__restrict__ stick1, int32_t *__restrict__ stick2,
                                                     double *__restrict__ jx, double *__restrict__ jy,
-                                                    uint8_t *__restrict__ kind2) {
+                                                    uint8_t *__restrict__ kind2, int shard_rank, int shard_world) {
     if (!(*errflag & 2)) return;
     int p = blockIdx.x * blockDim.x + threadIdx.x;
     int nbinned = __ldg(cell_start + total_cells);
@@ -487,6 +498,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
     if (jtmp[me.gid] >= 0 || jstart[me.gid + 1] == jstart[me.gid]) return;       // placed by k_place / nothing to place
     const int b = cnt::find_segment(soff, B, me.gid);
     const Geo g = geo[b];
+    if (shard_world > 1 && slab_owner(cell_of(me.xc, g.G) / TILE_C, g.TG, shard_world) != shard_rank) return;
     const CntLine l1 = recB[p];
     int cx0, cx1, cy0, cy1;
     cell_range(me, g.G, cx0, cx1, cy0, cy1);
@@ -707,11 +719,13 @@ extern "C" int64_t cnt_junction_workspace_bytes(int B, const int32_t *h_soff) {
     return plan_bytes(B, h_soff[B], tc);
 }
 
-extern "C" int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
-                                  const double *ya, const double *xb, const double *yb, const double *xc,
-                                  const double *yc, const double *length, int32_t *jcount,
-                                  unsigned long long *ntests, void *ws, int64_t ws_bytes, void *stream) {
+static int junction_count(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
+                          const double *ya, const double *xb, const double *yb, const double *xc,
+                          const double *yc, const double *length, int32_t *jcount,
+                          unsigned long long *ntests, void *ws, int64_t ws_bytes, void *stream, int shard_rank,
+                          int shard_world) {
     cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world);
     CNT_CHECK_ARG(B > 0 && soff && h_soff && xa && ya && xb && yb && xc && yc && length && jcount && ntests && ws);
     CNT_CHECK_ARG(h_soff[0] == 0 && B <= 65535);
     for (int b = 0; b < B; b++) CNT_CHECK_ARG(h_soff[b + 1] >= h_soff[b]);
@@ -744,8 +758,10 @@ extern "C" int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_s
         attr_set = true;
     }
     k_tiles<<<(unsigned)p.total_tiles, CT, tiles_smem(), st>>>(B, p.d_geo, p.cell_count, p.recA, p.recB, jcount, p.jtmp,
-                                                               ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag);
+                                                               ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag,
+                                                               shard_rank, shard_world);
     CNT_LAUNCHED();
+    if (shard_rank != 0) return CNT_OK;                           // the long sticks (electrodes) are rank 0's
     k_dense<false><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, jcount,
                                                                          ntests, p.segcnt, nullptr, nullptr, nullptr, nullptr,
                                                                          nullptr, nullptr, nullptr);
@@ -753,13 +769,29 @@ extern "C" int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_s
     return CNT_OK;
 }
 
-extern "C" int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
-                                 const double *ya, const double *xb, const double *yb, const double *xc,
-                                 const double *yc, const double *length, const uint8_t *kind,
-                                 const int32_t *jstart, int64_t J, int32_t *stick1, int32_t *stick2, double *jx,
-                                 double *jy, uint8_t *kind2, int32_t *joff, void *ws, int64_t ws_bytes,
-                                 void *stream) {
+extern "C" int cnt_junction_count(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
+                                  const double *ya, const double *xb, const double *yb, const double *xc,
+                                  const double *yc, const double *length, int32_t *jcount,
+                                  unsigned long long *ntests, void *ws, int64_t ws_bytes, void *stream) {
+    return junction_count(B, soff, h_soff, xa, ya, xb, yb, xc, yc, length, jcount, ntests, ws, ws_bytes, stream, 0, 1);
+}
+extern "C" int cnt_junction_count_slab(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
+                                       const double *ya, const double *xb, const double *yb, const double *xc,
+                                       const double *yc, const double *length, int32_t *jcount,
+                                       unsigned long long *ntests, void *ws, int64_t ws_bytes, int shard_rank,
+                                       int shard_world, void *stream) {
+    return junction_count(B, soff, h_soff, xa, ya, xb, yb, xc, yc, length, jcount, ntests, ws, ws_bytes, stream, shard_rank,
+                          shard_world);
+}
+
+static int junction_fill(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
+                         const double *ya, const double *xb, const double *yb, const double *xc,
+                         const double *yc, const double *length, const uint8_t *kind,
+                         const int32_t *jstart, int64_t J, int32_t *stick1, int32_t *stick2, double *jx,
+                         double *jy, uint8_t *kind2, int32_t *joff, void *ws, int64_t ws_bytes,
+                         void *stream, int shard_rank, int shard_world) {
     cudaStream_t st = (cudaStream_t)stream;
+    CNT_CHECK_ARG(shard_world >= 1 && shard_rank >= 0 && shard_rank < shard_world);
     CNT_CHECK_ARG(B > 0 && soff && h_soff && kind && jstart && joff && ws && J >= 0);
     CNT_CHECK_ARG(J == 0 || (stick1 && stick2 && jx && jy && kind2));
     Plan p;   // same carve-up as _count: the binned records built there are reused
@@ -772,13 +804,34 @@ extern "C" int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_so
                                                      stick2, jx, jy, kind2);
     CNT_LAUNCHED();
     k_cells_fill<<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells, p.recA,
-                                                          p.recB, p.errflag, p.jtmp, jstart, kind, stick1, stick2, jx, jy, kind2);
+                                                          p.recB, p.errflag, p.jtmp, jstart, kind, stick1, stick2, jx, jy, kind2,
+                                                          shard_rank, shard_world);
     CNT_LAUNCHED();
+    if (shard_rank != 0) return CNT_OK;
     k_dense<true><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, nullptr,
                                                                         nullptr, p.segcnt, jstart, kind, stick1, stick2, jx, jy,
                                                                         kind2);
     CNT_LAUNCHED();
     return CNT_OK;
+}
+
+extern "C" int cnt_junction_fill(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
+                                 const double *ya, const double *xb, const double *yb, const double *xc,
+                                 const double *yc, const double *length, const uint8_t *kind,
+                                 const int32_t *jstart, int64_t J, int32_t *stick1, int32_t *stick2, double *jx,
+                                 double *jy, uint8_t *kind2, int32_t *joff, void *ws, int64_t ws_bytes,
+                                 void *stream) {
+    return junction_fill(B, soff, h_soff, xa, ya, xb, yb, xc, yc, length, kind, jstart, J, stick1, stick2, jx, jy, kind2, joff,
+                         ws, ws_bytes, stream, 0, 1);
+}
+extern "C" int cnt_junction_fill_slab(int B, const int32_t *soff, const int32_t *h_soff, const double *xa,
+                                      const double *ya, const double *xb, const double *yb, const double *xc,
+                                      const double *yc, const double *length, const uint8_t *kind,
+                                      const int32_t *jstart, int64_t J, int32_t *stick1, int32_t *stick2, double *jx,
+                                      double *jy, uint8_t *kind2, int32_t *joff, void *ws, int64_t ws_bytes,
+                                      int shard_rank, int shard_world, void *stream) {
+    return junction_fill(B, soff, h_soff, xa, ya, xb, yb, xc, yc, length, kind, jstart, J, stick1, stick2, jx, jy, kind2, joff,
+                         ws, ws_bytes, stream, shard_rank, shard_world);
 }
 
 // sortedness flag of the last _count on this workspace (1 = a network was not sorted by

@@ -130,7 +130,8 @@ class Engine(object):
         # blocks and goes to cudaMalloc (a device synchronisation each).  16 size classes per power of two.
         if os.environ.get("CNT_ALLOC_ROUNDING", "1") != "0":
             try:
-                torch.cuda.memory._set_allocator_settings("roundup_power2_divisions:16")
+                setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or torch.cuda.memory._set_allocator_settings
+                setter("roundup_power2_divisions:16")
             except Exception:
                 pass
         self.stream = torch.cuda.Stream(device=self.device)
@@ -303,8 +304,12 @@ class Engine(object):
         return [{k: host[k][b.h_soff[i]:b.h_soff[i + 1]].copy() for k in keys} for i in range(b.B)]
 
     # ------------------------------------------------------------------ stage 1: junctions
-    def find_junctions(self, b):
-        """netsim.py:135-150.  Fills b.stick1, stick2, jx, jy, kind2, joff, ntests."""
+    def find_junctions(self, b, comm=None):
+        """netsim.py:135-150.  Fills b.stick1, stick2, jx, jy, kind2, joff, ntests.  comm (slab.DistComm /
+        slab.LocalComm) with more than one rank: the search is sharded by spatial slab over the ranks
+        (_find_junctions_slab); every rank ends up with the full, bit-identical table."""
+        if comm is not None and comm.world > 1:
+            return self._find_junctions_slab(b, comm)
         lib = self.lib
         with self._work("junctions"):
             wsb = lib.cnt_junction_workspace_bytes(b.B, b.c_soff)
@@ -340,6 +345,69 @@ class Engine(object):
                                         _p(b.stick1), _p(b.stick2), _p(b.jx), _p(b.jy), _p(b.kind2), _p(b.joff),
                                         _p(b._jws), b._jws.numel(), self.stream_ptr))
             b._jws = None
+        return b
+
+    def _find_junctions_slab(self, b, comm):
+        """One junction search over the ranks of `comm` (BASELINE config 5: a single huge network on several GPUs).
+        Every rank holds the whole stick table (it is regenerated from the seed, 70 B per stick) and evaluates the
+        home sticks whose centre lies in its vertical slab of the unit box -- the FP64 tests, 98 % of the stage --
+        reading the halo sticks across the slab boundary from that table (cnt_junction_count_slab / _fill_slab).
+        Exchange over NCCL / NVLink: one all-reduce of the per-stick junction counts and one of the (zero-padded,
+        disjoint) tables, the doubles as int64 bit patterns, so the result is bit for bit the unsharded table on
+        every rank."""
+        from . import slab
+        lib = self.lib
+        W = comm.world
+        i32, i64, f64, u8 = torch.int32, torch.int64, torch.float64, torch.uint8
+        with self._work("junctions"):
+            wsb = lib.cnt_junction_workspace_bytes(b.B, b.c_soff)
+            parts = []
+            for r in comm.local_ranks:
+                ws = self._ws(wsb)
+                jc = torch.empty(b.S + 1, dtype=i32, device=self.device)
+                nt = torch.zeros(b.B, dtype=i64, device=self.device)
+                check(lib.cnt_junction_count_slab(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                                  _p(b.xc), _p(b.yc), _p(b.length), _p(jc), _p(nt), _p(ws), ws.numel(),
+                                                  int(r), W, self.stream_ptr))
+                parts.append(dict(rank=r, ws=ws, jcount=jc, ntests=nt))
+            with self._work("junction_exchange"):
+                comm.all_reduce([p["jcount"] for p in parts])
+                comm.all_reduce([p["ntests"] for p in parts])
+            jcount, b.ntests = parts[0]["jcount"], parts[0]["ntests"]
+            sws = self._ws(lib.cnt_scan_workspace_bytes(b.S + 1))
+            jstart = torch.empty(b.S + 1, dtype=i32, device=self.device)
+            check(lib.cnt_exclusive_scan_i32(_p(jcount), _p(jstart), b.S, 1, _p(sws), sws.numel(), self.stream_ptr))
+            flags = []
+            for p in parts:
+                flagp = C.c_void_p()
+                check(lib.cnt_junction_errflag_ptr(b.B, b.c_soff, _p(p["ws"]), p["ws"].numel(), C.byref(flagp)))
+                off = flagp.value - p["ws"].data_ptr()
+                flags.append(p["ws"][off:off + 4].view(i32))
+            head = torch.cat([jstart[b.S:b.S + 1]] + flags).cpu().tolist()
+            total, flag = head[0], 0
+            for f in head[1:]:
+                flag |= f
+            b.junction_rows_recomputed = bool(flag & 2)
+            if flag & 1:
+                raise _lib.CntError("stick table is not sorted by length descending (netsim.py:133)")
+            b.J = total
+            b.jstart = jstart
+            n = max(total, 1)
+            for p in parts:
+                p.update(stick1=torch.zeros(n, dtype=i32, device=self.device), stick2=torch.zeros(n, dtype=i32, device=self.device),
+                         jx=torch.zeros(n, dtype=f64, device=self.device), jy=torch.zeros(n, dtype=f64, device=self.device),
+                         kind2=torch.zeros(n, dtype=u8, device=self.device),
+                         joff=torch.empty(b.B + 1, dtype=i32, device=self.device))
+                check(lib.cnt_junction_fill_slab(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                                 _p(b.xc), _p(b.yc), _p(b.length), _p(b.kind), _p(jstart), total,
+                                                 _p(p["stick1"]), _p(p["stick2"]), _p(p["jx"]), _p(p["jy"]), _p(p["kind2"]),
+                                                 _p(p["joff"]), _p(p["ws"]), p["ws"].numel(), int(p["rank"]), W,
+                                                 self.stream_ptr))
+            with self._work("junction_exchange"):
+                for key in ("stick1", "stick2", "jx", "jy", "kind2"):
+                    slab.sum_disjoint(comm, [p[key] for p in parts])
+            first = parts[0]
+            b.stick1, b.stick2, b.jx, b.jy, b.kind2, b.joff = (first[k] for k in ("stick1", "stick2", "jx", "jy", "kind2", "joff"))
         return b
 
     # ------------------------------------------------------------------ stage 2: clusters
@@ -435,9 +503,10 @@ class Engine(object):
         series = auto if self.series == "auto" else bool(self.series)
         return prune, series and prune
 
-    def prepare(self, b):
-        """junctions -> labels -> pattern (everything that does not depend on the gate)."""
-        self.find_junctions(b)
+    def prepare(self, b, comm=None):
+        """junctions -> labels -> pattern (everything that does not depend on the gate); comm: junction search
+        sharded by spatial slab over the ranks (find_junctions)"""
+        self.find_junctions(b, comm)
         self.label_clusters(b)
         self.assemble_pattern(b)
         return b

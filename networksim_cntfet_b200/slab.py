@@ -71,6 +71,20 @@ class LocalComm(object):
             r.copy_(cat)
 
 
+def junction_slab_owner(tile_col, tiles_per_side, world):
+    """rank that evaluates the home sticks of a tile column in the slab-sharded junction search (mirror of
+    slab_owner in csrc/junctions.cu): contiguous, balanced slabs of whole tile columns"""
+    return (int(tile_col) * int(world)) // int(tiles_per_side)
+
+
+def sum_disjoint(comm, tensors):
+    """all-reduce (sum) of per-rank arrays with DISJOINT supports (zero wherever another rank wrote): floating-point
+    arrays travel as their int64 bit patterns, so every element -- including -0.0 and NaN payloads -- arrives
+    unchanged.  tensors: one per local rank of `comm`, reduced in place."""
+    views = [t.view(torch.int64) if t.dtype == torch.float64 else t for t in tensors]
+    comm.all_reduce(views)
+
+
 # --------------------------------------------------------------------------- plan
 class SlabState(object):
     """Slice of the system owned by one rank + work vectors (all tensors on one device)."""

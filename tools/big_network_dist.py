@@ -1,6 +1,7 @@
 #!/usr/bin/env python3
-"""One large network spread over the ranks of a torchrun job: BIG_MODE=gates (gate configurations
-sharded, <= 4 useful ranks) or BIG_MODE=rows (unknown rows sharded, halo exchange + all-reduces over NCCL)."""
+"""One large network spread over the ranks of a torchrun job: BIG_MODE=slab (default: junction search sharded by
+spatial slab, junction rows exchanged over NCCL, direct solve replicated), BIG_MODE=rows (unknown rows of the PCG
+sharded, halo exchange + all-reduces over NCCL) or BIG_MODE=gates (gate configurations sharded, <= 4 useful ranks)."""
 import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, torch.distributed as dist
@@ -12,9 +13,9 @@ from networksim_cntfet_b200 import measure_perc
 from networksim_cntfet_b200.engine import Engine
 eng = pkg.set_engine(Engine("cuda:%d" % local))
 side = float(os.environ.get("BIG_SIDE", "300")); n = int(10 * side * side)
-mode = os.environ.get("BIG_MODE", "rows")
+mode = os.environ.get("BIG_MODE", "slab")
 eng.profile = True
-for rep in range(2):
+for rep in range(int(os.environ.get("BIG_REPS", "3"))):
     dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
     df, res = measure_perc.measure_fullnet_distributed(n, side, seed=5, mode=mode)
     torch.cuda.synchronize(); dist.barrier(); dt = time.perf_counter() - t0
