@@ -60,6 +60,17 @@ static int grid_dim_for(int64_t n) {
     return g;
 }
 
+// Length classes of a stick in a grid of G cells per side: "dense" (the electrodes: longer than a quarter of the box,
+// or than RMAX cells in a small grid) -> rows of k_dense, not binned; "wide" (longer than RMAX cells: a handful of
+// body sticks out of millions, the tail of the length distribution) -> binned like everybody else, so shorter home
+// sticks find them, but their own row is walked by a warp over their (large) cell range in k_wide instead of a
+// tile; everything else is a tile home stick.
+__device__ __forceinline__ bool is_dense(double len, int G) {
+    const double lg = len * (double)G, lim = (double)(G / 4 > RMAX ? G / 4 : RMAX);
+    return lg > lim || !(len == len);
+}
+__device__ __forceinline__ bool is_wide(double len, int G) { return len * (double)G > (double)RMAX && !is_dense(len, G); }
+
 __device__ __forceinline__ int cell_of(double v, int G) {
     int c = (int)floor(v * (double)G);
     return c < 0 ? 0 : (c >= G ? G - 1 : c);
@@ -71,7 +82,8 @@ __global__ void k_prep(int B, const int32_t *__restrict__ soff, const Geo *__res
                        const double *__restrict__ xb, const double *__restrict__ yb,
                        const double *__restrict__ xc, const double *__restrict__ yc,
                        const double *__restrict__ len, CntLine *__restrict__ line, int32_t *__restrict__ cellkey,
-                       int32_t *__restrict__ cell_count, int32_t *__restrict__ nlong, int32_t *__restrict__ errflag) {
+                       int32_t *__restrict__ cell_count, int32_t *__restrict__ nlong, int32_t *__restrict__ errflag,
+                       int32_t *__restrict__ nwide, int32_t *__restrict__ widelist) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int b = cnt::find_segment(soff, B, (int)s);
@@ -80,10 +92,11 @@ __global__ void k_prep(int B, const int32_t *__restrict__ soff, const Geo *__res
     double l = len[s];
     if (i + 1 < n && l < len[s + 1]) atomicOr(errflag, 1);   // table must be sorted by length desc
     Geo g = geo[b];
-    if (l * (double)g.G > (double)RMAX || !(l == l)) {
+    if (is_dense(l, g.G)) {
         cellkey[s] = -1;
         atomicAdd(nlong + b, 1);
     } else {
+        if (is_wide(l, g.G)) widelist[atomicAdd(nwide, 1)] = (int)s;      // order irrelevant: every row stands alone
         int key = g.coff + cell_of(yc[s], g.G) * g.G + cell_of(xc[s], g.G);
         cellkey[s] = key;
         atomicAdd(cell_count + key, 1);
@@ -213,6 +226,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     int rx0 = g.G, rx1 = -1, ry0 = g.G, ry1 = -1;
     for (int h = tid; h < nhome; h += CT) {
         const RecA me = gA[home_q(h)];
+        if (is_wide(me.len, g.G)) continue;                       // its row is k_wide's
         int cx0, cx1, cy0, cy1;
         cell_range(me, g.G, cx0, cx1, cy0, cy1);
         rx0 = min(rx0, cx0); rx1 = max(rx1, cx1); ry0 = min(ry0, cy0); ry1 = max(ry1, cy1);
@@ -232,6 +246,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     }
     __syncthreads();
     rx0 = s_red[0]; rx1 = s_red[1]; ry0 = s_red[2]; ry1 = s_red[3];
+    if (rx1 < rx0) return;                                        // only wide home sticks in this tile (uniform)
     const int RW = rx1 - rx0 + 1, RH = ry1 - ry0 + 1;            // <= MAX_RH by construction (len * G <= RMAX)
     // region rows: global start, region-index start; cell starts as region indices
     static_assert(MAX_RH <= 32, "region rows are scanned by one warp");
@@ -288,17 +303,20 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         int ncand = 0;
         if (tid < nb) {
             const int q = home_q(hb + tid);
-            // region index of the home stick: its cell row inside the region
-            const int hr = home_row(hb + tid);
-            const int v = s_rb[hy0 + hr - ry0] + (q - s_gq0[hy0 + hr - ry0]);
-            s_hq[tid] = v;
-            const RecA me = recA(v);
-            int cx0, cx1, cy0, cy1;
-            cell_range(me, g.G, cx0, cx1, cy0, cy1);
-            for (int cy = cy0; cy <= cy1; cy++)
-                ncand += s_cs[(cy - ry0) * (RW + 1) + (cx1 + 1 - rx0)] - s_cs[(cy - ry0) * (RW + 1) + (cx0 - rx0)];
-            s_rng[tid] = (cx0 - rx0) | ((cx1 - rx0) << 8) | ((cy0 - ry0) << 16) | ((cy1 - ry0) << 24);
             s_cnt[tid] = 0;
+            s_rng[tid] = 0;
+            s_hq[tid] = -1;                                       // wide stick: no pairs here, its row is k_wide's
+            const RecA me = gA[q];
+            if (!is_wide(me.len, g.G)) {
+                // region index of the home stick: its cell row inside the region
+                const int hr = home_row(hb + tid);
+                s_hq[tid] = s_rb[hy0 + hr - ry0] + (q - s_gq0[hy0 + hr - ry0]);
+                int cx0, cx1, cy0, cy1;
+                cell_range(me, g.G, cx0, cx1, cy0, cy1);
+                for (int cy = cy0; cy <= cy1; cy++)
+                    ncand += s_cs[(cy - ry0) * (RW + 1) + (cx1 + 1 - rx0)] - s_cs[(cy - ry0) * (RW + 1) + (cx0 - rx0)];
+                s_rng[tid] = (cx0 - rx0) | ((cx1 - rx0) << 8) | ((cy0 - ry0) << 16) | ((cy1 - ry0) << 24);
+            }
         }
         // exclusive scan of the counts over the batch (nb <= CAP_HOME <= CT)
         int inc = tid < nb ? ncand : 0;
@@ -424,9 +442,11 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         __syncthreads();
         const int base = s_base;
         if (tid < nb) {
-            const int gid = recA(s_hq[tid]).gid;
-            jcount[gid] = cnt_h;
-            jtmp[gid] = base >= 0 ? base + roff : -1;
+            if (s_hq[tid] >= 0) {
+                const int gid = recA(s_hq[tid]).gid;
+                jcount[gid] = cnt_h;
+                jtmp[gid] = base >= 0 ? base + roff : -1;
+            }
             s_cnt[tid] = roff;                                    // row offset from now on
         }
         __syncthreads();
@@ -498,6 +518,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
     if (jtmp[me.gid] >= 0 || jstart[me.gid + 1] == jstart[me.gid]) return;       // placed by k_place / nothing to place
     const int b = cnt::find_segment(soff, B, me.gid);
     const Geo g = geo[b];
+    if (is_wide(me.len, g.G)) return;                             // k_wide's row
     if (shard_world > 1 && slab_owner(cell_of(me.xc, g.G) / TILE_C, g.TG, shard_world) != shard_rank) return;
     const CntLine l1 = recB[p];
     int cx0, cx1, cy0, cy1;
@@ -526,6 +547,91 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
     for (int a = 0; a < cnt; a++) {
         stick1[base + a] = me.idx;
         kind2[base + a] = (uint8_t)(3 * kind[me.gid] + kind[s0 + stick2[base + a]]);
+    }
+}
+
+// ---- wide rows: one warp per wide stick walks the records of its cell range (any radius) ----------------
+// COUNT: junctions and in-ball tests of the row; FILL: the row in walk order (deterministic: cells in order, lanes
+// in order), then lane 0 orders it by stick2 (a wide stick crosses a few dozen others).
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_wide(int B, const int32_t *__restrict__ soff, const Geo *__restrict__ geo,
+                                              const int32_t *__restrict__ cell_start, const RecA *__restrict__ recA,
+                                              const CntLine *__restrict__ recB, const int32_t *__restrict__ nwide,
+                                              const int32_t *__restrict__ widelist, const CntLine *__restrict__ line,
+                                              const double *__restrict__ xc, const double *__restrict__ yc,
+                                              const double *__restrict__ len, int32_t *__restrict__ jcount,
+                                              unsigned long long *__restrict__ ntests, const int32_t *__restrict__ jstart,
+                                              const uint8_t *__restrict__ kind, int32_t *__restrict__ stick1,
+                                              int32_t *__restrict__ stick2, double *__restrict__ jx, double *__restrict__ jy,
+                                              uint8_t *__restrict__ kind2, int shard_rank, int shard_world) {
+    const int lane = threadIdx.x & 31;
+    const int nw = *nwide;
+    for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nw; w += (gridDim.x * blockDim.x) >> 5) {
+        const int s = widelist[w];
+        const int b = cnt::find_segment(soff, B, s);
+        const Geo g = geo[b];
+        const int s0 = soff[b];
+        RecA me;
+        me.xc = xc[s]; me.yc = yc[s]; me.len = len[s]; me.idx = s - s0; me.gid = s;
+        if (shard_world > 1 && slab_owner(cell_of(me.xc, g.G) / TILE_C, g.TG, shard_world) != shard_rank) continue;
+        const CntLine l1 = line[s];
+        int cx0, cx1, cy0, cy1;
+        cell_range(me, g.G, cx0, cx1, cy0, cy1);
+        const int base = FILL ? jstart[s] : 0;
+        int written = 0;                                          // identical in every lane
+        unsigned long long tests = 0;
+        for (int cy = cy0; cy <= cy1; cy++) {
+            const int q0 = __ldg(cell_start + g.coff + cy * g.G + cx0);
+            const int q1 = __ldg(cell_start + g.coff + cy * g.G + cx1 + 1);
+            for (int qq = q0; qq < q1; qq += 32) {
+                const int q = qq + lane;
+                bool hit = false;
+                double xi = 0, yi = 0;
+                int oj = 0;
+                if (q < q1) {
+                    const RecA o = recA[q];
+                    if (o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc)) {
+                        tests++;
+                        hit = cnt_junction(l1, recB[q], &xi, &yi);
+                        oj = o.idx;
+                    }
+                }
+                const unsigned m = __ballot_sync(~0u, hit);
+                if (FILL && hit) {
+                    const int o = base + written + __popc(m & ((1u << lane) - 1u));
+                    stick2[o] = oj;
+                    jx[o] = xi;
+                    jy[o] = yi;
+                }
+                written += __popc(m);
+            }
+        }
+        if (!FILL) {
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) tests += __shfl_down_sync(~0u, tests, o);
+            if (lane == 0) {
+                jcount[s] = written;
+                if (tests) atomicAdd(ntests + b, tests);
+            }
+        } else {
+            __syncwarp();
+            if (lane == 0) {
+                for (int a = 1; a < written; a++) {               // insertion by stick2
+                    const int kj = stick2[base + a];
+                    const double kx = jx[base + a], ky = jy[base + a];
+                    int c = base + a - 1;
+                    while (c >= base && stick2[c] > kj) {
+                        stick2[c + 1] = stick2[c]; jx[c + 1] = jx[c]; jy[c + 1] = jy[c];
+                        c--;
+                    }
+                    stick2[c + 1] = kj; jx[c + 1] = kx; jy[c + 1] = ky;
+                }
+                for (int a = 0; a < written; a++) {
+                    stick1[base + a] = me.idx;
+                    kind2[base + a] = (uint8_t)(3 * kind[s] + kind[s0 + stick2[base + a]]);
+                }
+            }
+        }
     }
 }
 
@@ -633,7 +739,7 @@ struct Plan {
     CntLine *line;
     RecA *recA;
     CntLine *recB;
-    int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag, *ntmp, *jtmp, *tj, *segcnt;
+    int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag, *ntmp, *jtmp, *tj, *segcnt, *nwide, *widelist;
     double *tx, *ty;
     void *scan_ws;
     int64_t scan_ws_bytes;
@@ -647,7 +753,7 @@ static int64_t plan_bytes(int B, int64_t S, int64_t total_cells) {
     return ws_bytes_for(B + 1, sizeof(Geo)) + ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, sizeof(RecA)) +
            ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, 4) + ws_bytes_for(total_cells + 1, 4) +
            ws_bytes_for(total_cells + 1, 4) + ws_bytes_for(B, 4) + ws_bytes_for(2, 4) + ws_bytes_for(S + 1, 4) +
-           ws_bytes_for((int64_t)B * DENSE_SPLIT * DENSE_SEGS, 4) +
+           ws_bytes_for((int64_t)B * DENSE_SPLIT * DENSE_SEGS, 4) + ws_bytes_for(S + 1, 4) +
            ws_bytes_for(ct, 4) + 2 * ws_bytes_for(ct, 8) + cnt_scan_workspace_bytes(total_cells + 1);
 }
 
@@ -691,6 +797,9 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
     p.ntmp = p.errflag ? p.errflag + 1 : nullptr;
     p.jtmp = w.take<int32_t>(p.S + 1);
     p.segcnt = w.take<int32_t>((int64_t)B * DENSE_SPLIT * DENSE_SEGS);
+    p.widelist = w.take<int32_t>(p.S + 1);                        // [0]: number of wide sticks, then their ids
+    p.nwide = p.widelist;
+    if (p.widelist) p.widelist += 1;
     p.tj = w.take<int32_t>(p.cap_tmp);
     p.tx = w.take<double>(p.cap_tmp);
     p.ty = w.take<double>(p.cap_tmp);
@@ -740,12 +849,13 @@ static int junction_count(int B, const int32_t *soff, const int32_t *h_soff, con
     CNT_CUDA(cudaMemsetAsync(p.cell_count, 0, 4 * (p.total_cells + 1), st));
     CNT_CUDA(cudaMemsetAsync(p.cell_fill, 0, 4 * (p.total_cells + 1), st));
     CNT_CUDA(cudaMemsetAsync(p.nlong, 0, 4 * B, st));
+    CNT_CUDA(cudaMemsetAsync(p.nwide, 0, 4, st));
     CNT_CUDA(cudaMemsetAsync(p.errflag, 0, 8, st));
     CNT_CUDA(cudaMemsetAsync(ntests, 0, sizeof(unsigned long long) * B, st));
     CNT_CUDA(cudaMemsetAsync(jcount, 0, 4 * (p.S + 1), st));
     CNT_CUDA(cudaMemsetAsync(p.jtmp, 0xFF, 4 * (p.S + 1), st));
     k_prep<<<cnt::grid_for(p.S, 256), 256, 0, st>>>(B, soff, p.d_geo, p.S, xa, ya, xb, yb, xc, yc, length, p.line,
-                                                    p.cellkey, p.cell_count, p.nlong, p.errflag);
+                                                    p.cellkey, p.cell_count, p.nlong, p.errflag, p.nwide, p.widelist);
     CNT_LAUNCHED();
     rc = cnt_exclusive_scan_i32(p.cell_count, p.cell_count, p.total_cells, 1, p.scan_ws, p.scan_ws_bytes, stream);
     if (rc) return rc;
@@ -760,6 +870,10 @@ static int junction_count(int B, const int32_t *soff, const int32_t *h_soff, con
     k_tiles<<<(unsigned)p.total_tiles, CT, tiles_smem(), st>>>(B, p.d_geo, p.cell_count, p.recA, p.recB, jcount, p.jtmp,
                                                                ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag,
                                                                shard_rank, shard_world);
+    CNT_LAUNCHED();
+    k_wide<false><<<148 * 2, 256, 0, st>>>(B, soff, p.d_geo, p.cell_count, p.recA, p.recB, p.nwide, p.widelist, p.line, xc, yc,
+                                           length, jcount, ntests, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                           nullptr, shard_rank, shard_world);
     CNT_LAUNCHED();
     if (shard_rank != 0) return CNT_OK;                           // the long sticks (electrodes) are rank 0's
     k_dense<false><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, jcount,
@@ -806,6 +920,10 @@ static int junction_fill(int B, const int32_t *soff, const int32_t *h_soff, cons
     k_cells_fill<<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells, p.recA,
                                                           p.recB, p.errflag, p.jtmp, jstart, kind, stick1, stick2, jx, jy, kind2,
                                                           shard_rank, shard_world);
+    CNT_LAUNCHED();
+    k_wide<true><<<148 * 2, 256, 0, st>>>(B, soff, p.d_geo, p.cell_count, p.recA, p.recB, p.nwide, p.widelist, p.line, xc, yc,
+                                          length, nullptr, nullptr, jstart, kind, stick1, stick2, jx, jy, kind2, shard_rank,
+                                          shard_world);
     CNT_LAUNCHED();
     if (shard_rank != 0) return CNT_OK;
     k_dense<true><<<dim3(DENSE_ROWS * DENSE_SEGS, B), DENSE_T, 0, st>>>(B, soff, p.nlong, p.line, xc, yc, length, nullptr,

@@ -316,9 +316,10 @@ class Engine(object):
             b._jws = self._ws(wsb)
             jcount = torch.empty(b.S + 1, dtype=torch.int32, device=self.device)
             b.ntests = torch.zeros(b.B, dtype=torch.int64, device=self.device)
-            check(lib.cnt_junction_count(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
-                                         _p(b.xc), _p(b.yc), _p(b.length), _p(jcount), _p(b.ntests),
-                                         _p(b._jws), b._jws.numel(), self.stream_ptr))
+            with self._work("junction_count"):
+                check(lib.cnt_junction_count(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                             _p(b.xc), _p(b.yc), _p(b.length), _p(jcount), _p(b.ntests),
+                                             _p(b._jws), b._jws.numel(), self.stream_ptr))
             sws = self._ws(lib.cnt_scan_workspace_bytes(b.S + 1))
             jstart = torch.empty(b.S + 1, dtype=torch.int32, device=self.device)
             check(lib.cnt_exclusive_scan_i32(_p(jcount), _p(jstart), b.S, 1, _p(sws), sws.numel(), self.stream_ptr))
@@ -340,10 +341,11 @@ class Engine(object):
             b.jy = torch.empty(n, dtype=torch.float64, device=self.device)
             b.kind2 = torch.empty(n, dtype=torch.uint8, device=self.device)
             b.joff = torch.empty(b.B + 1, dtype=torch.int32, device=self.device)
-            check(lib.cnt_junction_fill(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
-                                        _p(b.xc), _p(b.yc), _p(b.length), _p(b.kind), _p(jstart), total,
-                                        _p(b.stick1), _p(b.stick2), _p(b.jx), _p(b.jy), _p(b.kind2), _p(b.joff),
-                                        _p(b._jws), b._jws.numel(), self.stream_ptr))
+            with self._work("junction_fill"):
+                check(lib.cnt_junction_fill(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                            _p(b.xc), _p(b.yc), _p(b.length), _p(b.kind), _p(jstart), total,
+                                            _p(b.stick1), _p(b.stick2), _p(b.jx), _p(b.jy), _p(b.kind2), _p(b.joff),
+                                            _p(b._jws), b._jws.numel(), self.stream_ptr))
             b._jws = None
         return b
 
@@ -366,9 +368,10 @@ class Engine(object):
                 ws = self._ws(wsb)
                 jc = torch.empty(b.S + 1, dtype=i32, device=self.device)
                 nt = torch.zeros(b.B, dtype=i64, device=self.device)
-                check(lib.cnt_junction_count_slab(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                with self._work("junction_count"):
+                  check(lib.cnt_junction_count_slab(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
                                                   _p(b.xc), _p(b.yc), _p(b.length), _p(jc), _p(nt), _p(ws), ws.numel(),
-                                                  int(r), W, self.stream_ptr))
+                                                    int(r), W, self.stream_ptr))
                 parts.append(dict(rank=r, ws=ws, jcount=jc, ntests=nt))
             with self._work("junction_exchange"):
                 comm.all_reduce([p["jcount"] for p in parts])
@@ -398,11 +401,12 @@ class Engine(object):
                          jx=torch.zeros(n, dtype=f64, device=self.device), jy=torch.zeros(n, dtype=f64, device=self.device),
                          kind2=torch.zeros(n, dtype=u8, device=self.device),
                          joff=torch.empty(b.B + 1, dtype=i32, device=self.device))
-                check(lib.cnt_junction_fill_slab(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
-                                                 _p(b.xc), _p(b.yc), _p(b.length), _p(b.kind), _p(jstart), total,
-                                                 _p(p["stick1"]), _p(p["stick2"]), _p(p["jx"]), _p(p["jy"]), _p(p["kind2"]),
-                                                 _p(p["joff"]), _p(p["ws"]), p["ws"].numel(), int(p["rank"]), W,
-                                                 self.stream_ptr))
+                with self._work("junction_fill"):
+                    check(lib.cnt_junction_fill_slab(b.B, _p(b.soff), b.c_soff, _p(b.xa), _p(b.ya), _p(b.xb), _p(b.yb),
+                                                     _p(b.xc), _p(b.yc), _p(b.length), _p(b.kind), _p(jstart), total,
+                                                     _p(p["stick1"]), _p(p["stick2"]), _p(p["jx"]), _p(p["jy"]),
+                                                     _p(p["kind2"]), _p(p["joff"]), _p(p["ws"]), p["ws"].numel(),
+                                                     int(p["rank"]), W, self.stream_ptr))
             with self._work("junction_exchange"):
                 for key in ("stick1", "stick2", "jx", "jy", "kind2"):
                     slab.sum_disjoint(comm, [p[key] for p in parts])

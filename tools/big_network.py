@@ -8,10 +8,12 @@ from oracle import cntnet_oracle as O
 side = float(os.environ.get("BIG_SIDE", "300")); dens = float(os.environ.get("BIG_DENSITY", "10"))
 n = int(dens * side * side)
 eng = Engine(profile=True)
-torch.cuda.synchronize(); t0 = time.perf_counter()
-b = eng.generate([n], side, seed=5)
-res = eng.measure_fullnet(b, onoffmap=1)
-torch.cuda.synchronize(); dt = time.perf_counter() - t0
+for rep in range(int(os.environ.get("BIG_REPS", "2"))):
+    eng.stage_times_ms()
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    b = eng.generate([n], side, seed=5)
+    res = eng.measure_fullnet(b, onoffmap=1)
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
 print("%gx%g um, n=%d: %.2f s total; solver %s; rows %d; junctions %d; tests %d; percolating %s; iters %s; status %s"
       % (side, side, n, dt, eng.last_solver, b.R, res["njunctions"][0], res["ntests"][0], res["percolating"][0],
          res["iters"][:, 0].tolist(), res["status"][:, 0].tolist()), flush=True)
