@@ -419,6 +419,11 @@ def gpu_arm(args):
     # ---- warm-up
     for k in range(args.warmup):
         device_step(0, k)
+    # everything imported and allocated so far leaves the garbage collector's generations: a full collection walks
+    # ~1M module-level objects (torch, pandas, scipy) and showed up as sporadic 20-40 ms pauses inside a step
+    import gc
+    gc.collect()
+    gc.freeze()
     eng.stage_times_ms(reset=True)
     barrier()
 
@@ -463,6 +468,7 @@ def gpu_arm(args):
     t0 = time.perf_counter()
     h2d = d2h = 0
     e2e_parts = [0.0, 0.0, 0.0]
+    e2e_steps = []
     for k in range(args.steps):
         ta = time.perf_counter()
         sd = seeds_for(3, k, count=B * E)
@@ -476,6 +482,7 @@ def gpu_arm(args):
         h2d, d2h = io["h2d_bytes"], io["d2h_bytes"]
         td = time.perf_counter()
         e2e_parts = [e2e_parts[0] + tb - ta, e2e_parts[1] + tc - tb, e2e_parts[2] + td - tc]
+        e2e_steps.append(round(1e3 * (td - ta), 2))
     barrier()
     e2e_s = time.perf_counter() - t0
     mem2 = torch.cuda.memory_stats()
@@ -578,6 +585,7 @@ def gpu_arm(args):
             "gpu_launches": int(cnt.item()), "clocks": clocks, "allocator_cudaMalloc_calls": allocator, "wall_ms_of_every_timed_step": [round(v, 2) for v in step_wall],
             "symbolic_attempts_total": getattr(eng, "direct_attempts", None),
             "junction_fallback_batches": getattr(eng, "junction_fallbacks", 0),
+            "wall_ms_of_every_e2e_step": e2e_steps,
             "e2e_host_breakdown_ms_per_step": {"seeds": 1e3 * e2e_parts[0] / max(args.steps, 1),
                                                "measure_ensemble": 1e3 * e2e_parts[1] / max(args.steps, 1),
                                                "rows_gather": 1e3 * e2e_parts[2] / max(args.steps, 1)},

@@ -375,9 +375,7 @@ __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
                     s.ew[slot] = c;
                     s.live[0][slot] = slot;
                     s.luw[0][slot] = make_int2(i, c);
-                    s.p.e0_ptr[slot] = kk;
-                    const int e = hash_find_or_insert(s, net, ((unsigned long long)(unsigned)i << 32) | (unsigned)c);
-                    if (e >= 0) s.htab[e].slot = slot;
+                    s.p.e0_ptr[slot] = kk;              // the hash entry of the slot: k_init_hash (one thread per slot)
                 }
                 prevu = c;
             }
@@ -404,6 +402,19 @@ __global__ void __launch_bounds__(TB) k_init(Sym s, int epoch) {
         r0->nlive = t.a;
     };
     chained_scan(s.R, epoch, s.tickets, s.sflag, s.sagg, s.sinc, &s.p.info->error, f, g, fin);
+}
+
+// round-0 edges into the hash, one thread per slot: convergent and fully parallel (inside the per-row loops of
+// k_init the probe loops ran with 6 of 32 lanes active)
+__global__ void __launch_bounds__(TB) k_init_hash(Sym s) {
+    const cnt_sm_info *info = s.p.info;
+    if (info->done | info->error) return;
+    const int n = info->nE0;
+    for (int e = blockIdx.x * TB + threadIdx.x; e < n; e += gridDim.x * TB) {
+        const int u = s.eu[e], w = s.ew[e];
+        const int h = hash_find_or_insert(s, s.rnet[u], ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
+        if (h >= 0) s.htab[h].slot = e;
+    }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1066,10 +1077,18 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
         for (int k = 0; k < MAXEV; k++) cudaEventCreate(&ev[k]);
         ev_made = true;
     }
+    static cudaEvent_t evi[4];
+    if (timing && !evi[0])
+        for (int k = 0; k < 4; k++) cudaEventCreate(&evi[k]);
+    if (timing) cudaEventRecord(evi[0], st);
     k_hoff<<<1, 1024, 0, st>>>(s);
     CNT_LAUNCHED();
     k_init<<<GRID, TB, 0, st>>>(s, 1);
     CNT_LAUNCHED();
+    if (timing) cudaEventRecord(evi[1], st);
+    k_init_hash<<<GRID, TB, 0, st>>>(s);
+    CNT_LAUNCHED();
+    if (timing) cudaEventRecord(evi[2], st);
     int r = 0;
     int chunk = rounds_hint > 0 ? rounds_hint : 40;
     for (;;) {
@@ -1128,6 +1147,11 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
         chunk = 16;
     }
     if (timing) {
+        float t01 = 0, t12 = 0;
+        cudaEventElapsedTime(&t01, evi[0], evi[1]);
+        cudaEventElapsedTime(&t12, evi[1], evi[2]);
+        fprintf(stderr, "sm init: k_hoff + k_init %.0f us, k_init_hash %.0f us (B %d R %d nE0 %d rounds %d)\n", t01 * 1e3, t12 * 1e3, B,
+                (int)R, h_info->nE0, h_info->nrounds);
         static const char *names[8] = {"mark", "select", "incident", "pivots", "items_a", "items_b", "scan", "items_c"};
         double tot[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int k = 0; k + 8 < nev; k += 9) {

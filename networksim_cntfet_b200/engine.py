@@ -127,11 +127,13 @@ class Engine(object):
         torch.cuda.set_device(self.device)
         # the buffers of a batch are sized by its junction / row / entry counts, which differ by a fraction of a
         # percent from batch to batch: without rounding almost every large request misses the caching allocator's free
-        # blocks and goes to cudaMalloc (a device synchronisation each).  16 size classes per power of two.
+        # blocks and goes to cudaMalloc (a device synchronisation each).  16 size classes per power of two; expandable
+        # segments, so that a request one class larger than anything cached maps a few more pages instead of a new
+        # multi-GB block (measured: a 125 ms hiccup whenever a batch crossed a class boundary for the first time).
         if os.environ.get("CNT_ALLOC_ROUNDING", "1") != "0":
             try:
                 setter = getattr(torch._C, "_accelerator_setAllocatorSettings", None) or torch.cuda.memory._set_allocator_settings
-                setter("roundup_power2_divisions:16")
+                setter(os.environ.get("CNT_ALLOC_CONF", "roundup_power2_divisions:16,expandable_segments:True"))
             except Exception:
                 pass
         self.stream = torch.cuda.Stream(device=self.device)
@@ -164,6 +166,7 @@ class Engine(object):
                                        # iterative solvers and the reference); False = the exact-arithmetic system
         self.series = "auto"           # eliminate an independent set of series sticks (cnt_series_select; exact;
                                        # needs prune): True | False | "auto" (as above)
+        self._pool = {}                # persistent grow-only work areas of the direct solver (starmesh.scratch)
         self._direct_rounds_hint = 40  # rounds launched before the symbolic phase reads its header back
         self._direct_hint = None       # header of the previous plan (grid sizes of the round kernels)
 
@@ -700,7 +703,7 @@ class Engine(object):
                 plan = starmesh.symbolic(self.lib, self.stream_ptr, self.device, b.B, b.roff, R, NNZ, b.rowptr, b.col,
                                          dense_max=int(min(self.direct_dense_max, 1024)),       # k_sm_dense: <= 1400 rows
                                          max_fill=max_fill, rounds_hint=self._direct_rounds_hint,
-                                         hint=self._direct_hint)
+                                         hint=self._direct_hint, pool=self._pool)
                 if plan is None:
                     b._sm_plan = False
                     return None
@@ -711,7 +714,7 @@ class Engine(object):
                 self._direct_hint.info = plan.info
         with self._work("direct_numeric"):
             x = starmesh.solve_cuda(plan, self.lib, self.stream_ptr, b.rowptr, sysm["val"], sysm["rhs"],
-                                    src_eid=b.src_eid, drn_eid=b.drn_eid, g=sysm["g"], leak=self.direct_leak)
+                                    src_eid=b.src_eid, drn_eid=b.drn_eid, g=sysm["g"], leak=self.direct_leak, pool=self._pool)
         sym, num = starmesh.algorithmic_bytes(plan, sysm["val"].shape[0])
         self.last_direct = dict(rounds=plan.nrounds, nnzL=plan.nnzL, max_deg=plan.max_deg, npairs=plan.npairs,
                                 nE0=plan.nE0, nslots=plan.nslots, dense_nmax=plan.dense_nmax,

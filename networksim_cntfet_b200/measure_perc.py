@@ -25,6 +25,7 @@ elements = [FermiDiracTransistor, LinExpTransistor]
 VDS = 0.1                                   # netsim.py:182
 FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'ioff', 'gate', 'fname', 'seed',
                    'onoffmap']
+_PINNED = None
 PIPELINE = False              # True: the batches of a call alternate between two engines / host threads (measured
                               # gain at 100x100 um: 0.7-2 %, the step is one long kernel already; results identical)
 BATCH_STICKS = 23_200_000     # sticks per GPU batch of the ensemble path (224 networks at 100x100 um, ~8 GB): the
@@ -158,7 +159,12 @@ def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l
     eng = engine or get_engine()
     ns = [int(n) for n in ns]
     seeds_np = np.asarray(seeds, dtype=np.uint64)
-    pinned = torch.empty(2 * len(ns), dtype=torch.int64).pin_memory()
+    # pinned staging buffer, kept between calls (cudaHostAlloc per call costs up to tens of ms); the previous call's
+    # copy has completed: every call ends with its results on the host
+    global _PINNED
+    if _PINNED is None or _PINNED.numel() < 2 * len(ns):
+        _PINNED = torch.empty(max(2 * len(ns), 4096), dtype=torch.int64).pin_memory()
+    pinned = _PINNED[:2 * len(ns)]
     pinned[:len(ns)] = torch.as_tensor(ns, dtype=torch.int64)
     pinned[len(ns):] = torch.from_numpy(seeds_np.view(np.int64).copy())
     dev_in = pinned.to(eng.device, non_blocking=True)          # H2D of this call's inputs

@@ -55,11 +55,30 @@ class SmInfo(C.Structure):
 ERR_SLOTS, ERR_CONTRIB, ERR_ITEMS, ERR_HASH, ERR_SCAN, ERR_ROUNDS = 1, 2, 4, 8, 16, 32
 
 
+def scratch(pool, name, nbytes, device, take=False):
+    """uint8 device buffer of at least nbytes.  With a pool (dict owned by an Engine) the buffer is persistent and
+    grow-only with 15 % headroom: the multi-GB work areas of the direct solver differ by a fraction of a percent from
+    batch to batch, and every first crossing of an allocator size class cost a 40-125 ms cudaMalloc / page mapping.
+    take=True removes the buffer from the pool (the caller owns it and may hand it back with pool[name] = buf)."""
+    nbytes = int(nbytes)
+    if pool is None:
+        return torch.empty(nbytes, dtype=torch.uint8, device=device)
+    t = pool.get(name)
+    if t is None or t.numel() < nbytes or t.device != torch.device(device):
+        pool[name] = t = None
+        t = torch.empty(nbytes + nbytes // 7 + (1 << 20), dtype=torch.uint8, device=device)
+        pool[name] = t
+    if take:
+        pool[name] = None
+    return t
+
+
 class Plan(object):
     """symbolic factorisation of a batch pattern: one device buffer + the host copy of its header"""
 
     def __init__(self):
         self.buf = None
+        self._pool = None
         self.info = SmInfo()
         self.R = self.B = self.NNZ = 0
         self.cap_slots = self.cap_contrib = 0
@@ -89,9 +108,17 @@ class Plan(object):
     def rounds(self):
         return [self.info.rounds[k] for k in range(self.nrounds)]
 
+    def __del__(self):
+        # hand the plan buffer back to the engine's pool (kept only if the slot is free)
+        try:
+            if self._pool is not None and self.buf is not None and self._pool.get("sm_plan") is None:
+                self._pool["sm_plan"] = self.buf
+        except Exception:
+            pass
+
 
 def symbolic(lib, stream_ptr, device, B, roff, R, NNZ, rowptr, col, dense_max=0, max_fill=None, rounds_hint=0,
-             slot_factor=2.0, fill_factor=4.0, slack=4096, hint=None):
+             slot_factor=2.0, fill_factor=4.0, slack=4096, hint=None, pool=None):
     """cnt_sm_symbolic with growing capacities.  roff [B+1], rowptr [R+1], col [NNZ]: int32 device
     tensors (network-local ascending columns); hint: Plan of an earlier, similar batch (sizes the grids).
     Returns a Plan, or None when the elimination needs
@@ -116,12 +143,16 @@ def symbolic(lib, stream_ptr, device, B, roff, R, NNZ, rowptr, col, dense_max=0,
             return None
         plan.cap_slots, plan.cap_contrib = cap_slots, cap_contrib
         nbytes = lib.cnt_sm_plan_layout(plan.R, plan.B, plan.NNZ, cap_slots, cap_contrib, None)
-        plan.buf = torch.empty(int(nbytes), dtype=torch.uint8, device=device)
-        ws = torch.empty(int(lib.cnt_sm_symbolic_workspace_bytes(plan.R, plan.B, plan.NNZ, cap_slots, cap_contrib,
-                                                                 cap_items)), dtype=torch.uint8, device=device)
+        if plan.buf is not None and pool is not None and pool.get("sm_plan") is None:
+            pool["sm_plan"] = plan.buf                      # retry with larger capacities: the old buffer goes back first
+        plan.buf = scratch(pool, "sm_plan", nbytes, device, take=True)
+        plan._pool = pool
+        ws = scratch(pool, "sm_symbolic_ws", lib.cnt_sm_symbolic_workspace_bytes(plan.R, plan.B, plan.NNZ, cap_slots,
+                                                                               cap_contrib, cap_items), device)
         rc = lib.cnt_sm_symbolic(plan.B, vp(roff.data_ptr()), plan.R, plan.NNZ, vp(rowptr.data_ptr()),
                                  vp(col.data_ptr()), int(dense_max), int(rounds_hint), cap_slots, cap_contrib, cap_items,
-                                 C.byref(hint.info) if hint is not None else None, vp(plan.buf.data_ptr()), int(nbytes), vp(ws.data_ptr()), ws.numel(),
+                                 C.byref(hint.info) if hint is not None else None, vp(plan.buf.data_ptr()), plan.buf.numel(),
+                                 vp(ws.data_ptr()), ws.numel(),
                                  C.byref(plan.info), stream_ptr)
         del ws
         if rc == 0:
@@ -148,14 +179,15 @@ def symbolic(lib, stream_ptr, device, B, roff, R, NNZ, rowptr, col, dense_max=0,
             check(rc)
 
 
-def solve_cuda(plan, lib, stream_ptr, rowptr, val, rhs, src_eid=None, drn_eid=None, g=None, coupling=None, leak=True):
+def solve_cuda(plan, lib, stream_ptr, rowptr, val, rhs, src_eid=None, drn_eid=None, g=None, coupling=None, leak=True,
+               pool=None):
     """Numeric phase on the GPU.  rowptr [R+1] int32; val [NS, >=NNZ] (CSR off-diagonals, -g); rhs [NS, >=R];
     electrode coupling of row r = g[q, src_eid[r]] + g[q, drn_eid[r]] (+ coupling[q, r]).  Returns x [NS, R]."""
     NS, R = val.shape[0], plan.R
     dev = val.device
     assert val.stride(1) == 1 and rhs.stride(1) == 1
     x = torch.empty((NS, R), dtype=torch.float64, device=dev)
-    ws = torch.empty(int(lib.cnt_sm_solve_workspace_bytes(NS, C.byref(plan.info))), dtype=torch.uint8, device=dev)
+    ws = scratch(pool, "sm_solve_ws", lib.cnt_sm_solve_workspace_bytes(NS, C.byref(plan.info)), dev)
     vp = C.c_void_p
     ptr = lambda t: None if t is None else vp(t.data_ptr())
     if g is not None:
