@@ -416,6 +416,11 @@ def gpu_arm(args):
         gather_rows(rows)
         return outs
 
+    # ---- clock sampler: started BEFORE the warm-up (the start-up of nvidia-smi -- NVML initialisation in a second
+    # process -- stalled the first timed step by up to 35 ms), its samples counted from the start of the timed region
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     # ---- warm-up
     for k in range(args.warmup):
         device_step(0, k)
@@ -428,9 +433,8 @@ def gpu_arm(args):
     barrier()
 
     # ---- timed: device-side value
-    sampler = ClockSampler(local)
     if rank == 0:
-        sampler.start()
+        sampler.rows = []                 # keep only the samples of the timed region
     launches0 = lib.cnt_launch_count()
     mem0 = torch.cuda.memory_stats()
     def direct_total():

@@ -13,6 +13,17 @@ namespace {
 // loading parent[s0].  In a percolating network s0 (the source electrode) is the root of the giant component,
 // i.e. the end of almost every chase: that one cache line was read ~130k times per network through L2
 // (volatile), serialised at the slice, and made the union pass latency-bound (ncu: 3 % issue slots busy).
+// Loads of the chases go through L1 (ld.global.ca): a line may be stale, but a stale parent is still an ancestor
+// (parents only move towards the root, and indices strictly decrease along a chain), so a chase over stale lines
+// ends at a true ancestor; only the hook needs the truth, and it is an atomicCAS whose return value -- the real
+// parent -- is where a failed attempt continues.  The upper levels of the trees, shared by every chase of an SM,
+// are L1 hits instead of L2 round trips.
+__device__ __forceinline__ int ld_ca(const int *p) {
+    int v;
+    asm volatile("ld.global.ca.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ int uf_find(int *parent, int x, int s0) {
     if (x == s0) return x;
     int p = ((volatile int *)parent)[x];
@@ -47,7 +58,6 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
                                                   uint8_t *__restrict__ hasj) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    volatile int *vp = (volatile int *)parent;
     int cur[2 * UF_K], par[2 * UF_K], base[UF_K];
     bool live[UF_K];
 #pragma unroll
@@ -68,7 +78,7 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
     }
     // roots of all endpoints, path halving, the chases interleaved; s0 of a network is a root by construction
 #pragma unroll
-    for (int k = 0; k < 2 * UF_K; k++) par[k] = live[k >> 1] && cur[k] != base[k >> 1] ? vp[cur[k]] : cur[k];
+    for (int k = 0; k < 2 * UF_K; k++) par[k] = live[k >> 1] && cur[k] != base[k >> 1] ? ld_ca(parent + cur[k]) : cur[k];
     for (;;) {
         bool any = false;
         int gp[2 * UF_K];
@@ -76,7 +86,7 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
         for (int k = 0; k < 2 * UF_K; k++) {
             gp[k] = par[k];
             if (par[k] != cur[k] && par[k] != base[k >> 1]) {
-                gp[k] = vp[par[k]];
+                gp[k] = ld_ca(parent + par[k]);
                 any = true;
             }
         }
@@ -87,7 +97,7 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
                 if (par[k] == base[k >> 1]) {          // reached the network's first stick: a root
                     cur[k] = par[k];
                 } else {
-                    if (gp[k] != par[k]) vp[cur[k]] = gp[k];
+                    if (gp[k] != par[k]) parent[cur[k]] = gp[k];
                     cur[k] = par[k];
                     par[k] = gp[k];
                 }
@@ -107,8 +117,8 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
             const int hi = a > c ? a : c, lo = a > c ? c : a;
             const int old = atomicCAS(parent + hi, hi, lo);
             if (old == hi) break;
-            a = uf_find(parent, hi, s0);  // someone else re-parented hi: retry from the current roots
-            c = uf_find(parent, lo, s0);
+            a = uf_find(parent, old, s0);  // hi is not a root (any more): its true parent comes back from the CAS; the
+            c = uf_find(parent, lo, s0);   // volatile chases from there see L2
         }
     }
 }
@@ -127,42 +137,65 @@ __global__ void k_uf_flatten(int B, const int32_t *__restrict__ soff, int64_t S,
     if (r >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(size + r, __popc(same));
 }
 
-// per-network statistics, pass 1 over the sticks: components, multi-stick components, largest, first stick with a junction
-__global__ void k_stats_sticks(int B, const int32_t *__restrict__ soff, int64_t S, const int32_t *__restrict__ size,
-                               const uint8_t *__restrict__ hasj, int32_t *__restrict__ acc /* [B][8] */) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// per-network statistics, pass 1 over the sticks: components, multi-stick components, largest, first stick with a junction.
+// All sticks of a network are neighbours in the table, so every CTA in flight works on the same two or three networks:
+// with one set of global atomics per WARP the pass was serialised on those few 32-byte lines (ncu: 285 cycles of
+// long-scoreboard stall per issued instruction, 2.1 ms for 22M sticks).  A CTA that lies inside one network -- all
+// but B of them -- reduces in shared memory and issues ONE set.
+constexpr int STATS_T = 1024;
+__global__ void __launch_bounds__(STATS_T) k_stats_sticks(int B, const int32_t *__restrict__ soff, int64_t S,
+                                                         const int32_t *__restrict__ size, const uint8_t *__restrict__ hasj,
+                                                         int32_t *__restrict__ acc /* [B][8] */) {
+    __shared__ int s_acc[4];
+    __shared__ int s_b[2];
+    const int64_t s0 = (int64_t)blockIdx.x * STATS_T, s = s0 + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        s_acc[0] = s_acc[1] = s_acc[2] = 0;
+        s_acc[3] = 0x7fffffff;
+        const int64_t last = s0 + STATS_T - 1 < S - 1 ? s0 + STATS_T - 1 : S - 1;
+        s_b[0] = cnt::find_segment(soff, B, (int)s0);
+        s_b[1] = cnt::find_segment(soff, B, (int)last);
+    }
+    __syncthreads();
+    const bool uniform = s_b[0] == s_b[1];                       // the CTA lies inside one network
     int b = -1, sz = 0, first = 0x7fffffff;
     if (s < S) {
-        b = cnt::find_segment(soff, B, (int)s);
+        b = uniform ? s_b[0] : cnt::find_segment(soff, B, (int)s);
         sz = size[s];           // non-zero only at roots
         if (hasj[s]) first = (int)s - soff[b];
     }
-    // one set of atomics per group of lanes of the same network
-    const unsigned same = __match_any_sync(0xffffffffu, b);
-    const unsigned roots = __ballot_sync(0xffffffffu, sz > 0) & same, multi = __ballot_sync(0xffffffffu, sz > 1) & same;
-    int mx = sz, fi = first;
-    for (int o = 16; o > 0; o >>= 1) {      // max / min over the whole warp is only used when the warp is one network
-        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        fi = min(fi, __shfl_xor_sync(0xffffffffu, fi, o));
-    }
-    if (b < 0) return;
-    int32_t *a = acc + (int64_t)b * 8;
-    if (same == 0xffffffffu) {
+    if (uniform) {
+        const unsigned roots = __ballot_sync(0xffffffffu, sz > 0), multi = __ballot_sync(0xffffffffu, sz > 1);
+        int mx = sz, fi = first;
+        for (int o = 16; o > 0; o >>= 1) {
+            mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            fi = min(fi, __shfl_xor_sync(0xffffffffu, fi, o));
+        }
         if (lane == 0) {
-            if (roots) atomicAdd(a + 0, __popc(roots));
-            if (multi) atomicAdd(a + 1, __popc(multi));
-            if (mx > 0) atomicMax(a + 2, mx);
-            if (fi < *(volatile int32_t *)(a + 3)) atomicMin(a + 3, fi);
+            if (roots) atomicAdd(&s_acc[0], __popc(roots));
+            if (multi) atomicAdd(&s_acc[1], __popc(multi));
+            if (mx > 0) atomicMax(&s_acc[2], mx);
+            if (fi != 0x7fffffff) atomicMin(&s_acc[3], fi);
         }
-    } else {                                // a warp across a network boundary (or the tail): per lane
-        if (sz > 0) {
-            atomicAdd(a + 0, 1);
-            if (sz > 1) atomicAdd(a + 1, 1);
-            atomicMax(a + 2, sz);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int32_t *a = acc + (int64_t)s_b[0] * 8;
+            if (s_acc[0]) atomicAdd(a + 0, s_acc[0]);
+            if (s_acc[1]) atomicAdd(a + 1, s_acc[1]);
+            if (s_acc[2] > 0) atomicMax(a + 2, s_acc[2]);
+            if (s_acc[3] != 0x7fffffff) atomicMin(a + 3, s_acc[3]);
         }
-        if (first < *(volatile int32_t *)(a + 3)) atomicMin(a + 3, first);
+        return;
     }
+    if (b < 0) return;                                           // a CTA across a network boundary (or the tail): per lane
+    int32_t *a = acc + (int64_t)b * 8;
+    if (sz > 0) {
+        atomicAdd(a + 0, 1);
+        if (sz > 1) atomicAdd(a + 1, 1);
+        atomicMax(a + 2, sz);
+    }
+    if (first != 0x7fffffff) atomicMin(a + 3, first);
 }
 // pass 2: the reference's quirky cluster count needs K = multi-stick components (pass 1); junctions of the
 // percolating component
@@ -250,7 +283,7 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
     k_stats_init<<<cnt::grid_for(8 * (int64_t)B, 256), 256, 0, st>>>(B, acc);
     CNT_LAUNCHED();
     if (S > 0) {
-        k_stats_sticks<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, size, hasj, acc);
+        k_stats_sticks<<<cnt::grid_for(S, STATS_T), STATS_T, 0, st>>>(B, soff, S, size, hasj, acc);
         CNT_LAUNCHED();
         k_stats_second<<<cnt::grid_for(S + J, 256), 256, 0, st>>>(B, soff, joff, S, J, stick1, label, hasj, orig, acc);
         CNT_LAUNCHED();
