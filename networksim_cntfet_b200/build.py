@@ -22,6 +22,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 # bit-exact FP64 predicate: no FMA contraction anywhere in that translation unit (the kernels
 # also use explicit __d*_rn intrinsics; this is belt and braces)
 PER_FILE = {"junctions.cu": ["-fmad=false"]}
+if os.environ.get("CNT_TILE_FLAGS"):          # A/B of the tile kernel's shape: e.g. "-DCNT_TILE_CT=256 -DCNT_TILE_Q=1024"
+    PER_FILE["junctions.cu"] = PER_FILE["junctions.cu"] + os.environ["CNT_TILE_FLAGS"].split()
 if os.environ.get("CNT_CLUSTER_THREADS"):
     PER_FILE["pcg_cluster.cu"] = ["-DCNT_CLUSTER_THREADS=" + os.environ["CNT_CLUSTER_THREADS"]]
 

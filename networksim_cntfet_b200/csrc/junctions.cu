@@ -3,20 +3,20 @@
 //
 // Layout.  Sticks of all B networks are concatenated (soff).  Network b gets a G_b x G_b
 // uniform grid over the unit box, G_b = clamp(isqrt(n_b/2), 1, 2048) (~2 sticks per cell).
-// A stick whose length exceeds RMAX cells is "long" (the two electrodes, length 100, always
-// are): long sticks form a prefix of the length-sorted table and are handled by a dense
-// row kernel (they test every later stick, like the reference's radius-100 KD query).
-// All other sticks are binned by the cell of their centre.  The tile kernel (k_tiles) gives one CTA
-// a tile of 8 x 8 cells: it stages the records of the tile and of the halo its sticks reach into
-// SHARED MEMORY once, flattens the (home stick, candidate) pairs of the tile over all threads
-// (cheap part: j > i and the KD-ball test), compacts the survivors with warp ballot / prefix into
-// a queue, runs the FP64 predicate -- the two IEEE divisions -- on the queue with full warps, and
-// writes the tile's junctions grouped by home stick to a temporary table.  The predicate is
-// evaluated ONCE: after the scan of the row lengths k_place copies every row to its place and
-// orders it by stick2, so the output is compact, deterministic and sorted by
-// (network, stick1, stick2).  A batch of home sticks that runs out of hit buffer (more than CAP_HIT junctions) or
-// of temporary table space (more than ~8 junctions per stick overall) only counts; exactly its rows are then
-// recomputed in place by the thread-per-row kernel k_cells_fill.
+// Three length classes (is_dense / is_wide below): the electrodes (longer than a quarter of the box) are DENSE rows
+// -- they test every later stick, like the reference's radius-100 KD query -- cut into segments (k_dense); everything
+// else is binned by the cell of its centre; of those, the few sticks longer than RMAX cells are WIDE: candidates
+// like everybody else, but their own row is walked by a warp over their cell range (k_wide).  All other sticks are
+// home sticks of the tile kernel (k_tiles): one CTA per tile of 8 x 8 cells stages the records (centre, length, ids)
+// of the tile and of the halo its sticks reach into SHARED MEMORY once, flattens the (home stick, candidate) pairs
+// of the tile over all threads (cheap part: j > i and the KD-ball test), compacts the survivors with warp ballot /
+// prefix into a queue, runs the FP64 predicate -- the two IEEE divisions -- on the queue with full warps (line
+// records of the survivors through L1 / L2), and writes the tile's junctions grouped by home stick to a temporary
+// table.  The predicate is evaluated ONCE: after the scan of the row lengths k_place copies every row to its place
+// and orders it by stick2, so the output is compact, deterministic and sorted by (network, stick1, stick2).  A batch
+// of home sticks that runs out of hit buffer (more than CAP_HIT junctions) or of temporary table space (more than ~8
+// junctions per stick overall) only counts; exactly its rows are then recomputed in place by the thread-per-row kernel
+// k_cells_fill.  cnt_junction_*_slab shard the search by spatial slab over ranks (slab_owner below).
 #include <vector>
 #include "common.cuh"
 #include "predicate.cuh"
@@ -34,11 +34,25 @@ struct __align__(16) RecA {      // 32 bytes: what the cheap tests need (one sec
 };
 
 constexpr int TILE_C = 8;        // home cells per tile side
-constexpr int CT = 512;          // threads of the tile kernel
-constexpr int CAP_REC = 1024;    // staged records per tile (A + B halves: 64 KB)
+// shape of the tile kernel (A/B on the GPU box, tools/gpu_tile_ab.sh; junction count pass per 56 networks):
+// 512 threads / 2048 pairs / 1024 hits + staged line records (105 KB, 2 CTAs per SM) 4.18 ms; without staged line
+// records 4.49 (512 threads, 2 CTAs per SM by registers), 4.03 (384 threads), 3.86 ms (256 threads / 1024 / 512: 53 KB,
+// 4 CTAs per SM -- four independent tiles per SM hide each other's barriers)
+#ifndef CNT_TILE_CT
+#define CNT_TILE_CT 256
+#endif
+#ifndef CNT_TILE_Q
+#define CNT_TILE_Q 1024
+#endif
+#ifndef CNT_TILE_HIT
+#define CNT_TILE_HIT 512
+#endif
+constexpr int CT = CNT_TILE_CT;  // threads of the tile kernel
+constexpr int CAP_REC = 1024;    // staged records per tile (32 KB)
 constexpr int CAP_HOME = 256;    // home sticks per batch of a tile
-constexpr int CAP_Q = 2048;      // candidate pairs per chunk = capacity of the survivor queue
-constexpr int CAP_HIT = 1024;    // junctions per batch of home sticks
+constexpr int CAP_Q = CNT_TILE_Q;      // candidate pairs per chunk = capacity of the survivor queue
+constexpr int CAP_HIT = CNT_TILE_HIT;  // junctions per batch of home sticks
+static_assert(CAP_HOME <= CT, "the scans over a batch of home sticks use one thread per stick");
 constexpr int MAX_RH = TILE_C + 2 * (RMAX + 2);      // rows / columns of the staged region
 
 struct Geo {                     // per-network grid geometry (host computed, uploaded)
@@ -151,15 +165,14 @@ struct Hit {
 
 __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo,
                                               const int32_t *__restrict__ cell_start, const RecA *__restrict__ gA,
-                                              const CntLine *__restrict__ gB, int32_t *__restrict__ jcount,
+                                              const CntLine *__restrict__ line, int32_t *__restrict__ jcount,
                                               int32_t *__restrict__ jtmp, unsigned long long *__restrict__ ntests,
                                               int32_t *__restrict__ tj, double *__restrict__ tx, double *__restrict__ ty,
                                               int64_t cap_tmp, int32_t *__restrict__ ntmp, int32_t *__restrict__ errflag,
                                               int shard_rank, int shard_world) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RecA *sA = (RecA *)smem_raw;                                  // [CAP_REC]
-    CntLine *sB = (CntLine *)(sA + CAP_REC);                      // [CAP_REC]
-    Hit *s_hit = (Hit *)(sB + CAP_REC);                           // [CAP_HIT]
+    Hit *s_hit = (Hit *)(sA + CAP_REC);                           // [CAP_HIT]
     int32_t *s_q = (int32_t *)(s_hit + CAP_HIT);                  // [CAP_Q] survivor queue: home << 23 | region index
     int32_t *s_cs = s_q + CAP_Q;                                  // [MAX_RH * (MAX_RH + 1)] cell starts (region index)
     int32_t *s_gq0 = s_cs + MAX_RH * (MAX_RH + 1);                // [MAX_RH] first global record of every region row
@@ -279,7 +292,6 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
             while (k >= s_rb[r + 1]) r++;
             const int q = s_gq0[r] + (k - s_rb[r]);
             sA[k] = gA[q];
-            sB[k] = gB[q];
         }
     }
     __syncthreads();
@@ -290,12 +302,9 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         while (v >= s_rb[r + 1]) r++;
         return gA[s_gq0[r] + (v - s_rb[r])];
     };
-    auto recB = [&](int v) -> CntLine {
-        if (staged) return sB[v];
-        int r = 0;
-        while (v >= s_rb[r + 1]) r++;
-        return gB[s_gq0[r] + (v - s_rb[r])];
-    };
+    // line record of a region record: only the survivors of the ball test (a quarter of the candidates) need it, so it
+    // is not staged -- 32 KB less shared memory per CTA is a third CTA per SM -- but read through L1 / L2 by stick id
+    auto recB = [&](int v) -> CntLine { return line[recA(v).gid]; };
     unsigned long long tests = 0;
     for (int hb = 0; hb < nhome; hb += CAP_HOME) {               // batches of home sticks
         const int nb = min(CAP_HOME, nhome - hb);
@@ -854,7 +863,7 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
 }
 
 static size_t tiles_smem() {
-    return (size_t)CAP_REC * (sizeof(RecA) + sizeof(CntLine)) + (size_t)CAP_HIT * sizeof(Hit) +
+    return (size_t)CAP_REC * sizeof(RecA) + (size_t)CAP_HIT * sizeof(Hit) +
            4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
                 CAP_HOME + CAP_Q / 32);
 }
@@ -907,7 +916,7 @@ static int junction_count(int B, const int32_t *soff, const int32_t *h_soff, con
         CNT_CUDA(cudaFuncSetAttribute(k_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tiles_smem()));
         attr_set = true;
     }
-    k_tiles<<<(unsigned)p.total_tiles, CT, tiles_smem(), st>>>(B, p.d_geo, p.cell_count, p.recA, p.recB, jcount, p.jtmp,
+    k_tiles<<<(unsigned)p.total_tiles, CT, tiles_smem(), st>>>(B, p.d_geo, p.cell_count, p.recA, p.line, jcount, p.jtmp,
                                                                ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag,
                                                                shard_rank, shard_world);
     CNT_LAUNCHED();

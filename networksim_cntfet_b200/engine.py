@@ -159,9 +159,10 @@ class Engine(object):
         self.direct_max_fill = 40.0    # ... and the elimination creates at most this many contributions per edge
                                        # (measured: the 20x20 um density sweep 1..20 /um^2 of BASELINE config 2 needs 12.4
                                        # and runs 4.6x faster through the direct solver than through the cluster PCG)
-        self.direct_dense_max = 192    # ... and finishes with one dense elimination per network once it has <= this many
+        self.direct_dense_max = 128    # ... and finishes with one dense elimination per network once it has <= this many
                                        # unknowns left (0 = sparse rounds to the end; <= 224: the dense matrix stays in
-                                       # shared memory)
+                                       # shared memory; 128 = 69 KB, three CTAs per SM: measured 42.8 / 42.9 / 44.5 ms
+                                       # symbolic + numeric per 224 networks at 128 / 160 / 192)
         self.direct_leak = True        # direct solver: answer the assembled FP64 matrix (rounded diagonal, like the
                                        # iterative solvers and the reference); False = the exact-arithmetic system
         self.series = "auto"           # eliminate an independent set of series sticks (cnt_series_select; exact;
