@@ -251,8 +251,8 @@ def extra_legs(args, eng, world, rank, dist, peak):
         try:
             import contextlib, io
             with contextlib.redirect_stdout(io.StringIO()):
-                measure_perc.measure_async(1, 400, step, max(number // 10, world), 20, onoffmap=[1],
-                                           seeds=list(range(5001, 5001 + max(number // 10, world))))
+                # warm call of the same shape (other seeds): buffer sizes and plan capacities of this ensemble exist
+                measure_perc.measure_async(1, 400, step, number, 20, onoffmap=[1], seeds=list(range(5001, 5001 + number)))
                 sync()
                 t0 = time.perf_counter()
                 df = measure_perc.measure_async(1, 400, step, number, 20, onoffmap=[1], seeds=list(range(1, number + 1)))
