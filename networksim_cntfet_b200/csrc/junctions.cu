@@ -33,7 +33,13 @@ struct __align__(16) RecA {      // 32 bytes: what the cheap tests need (one sec
     int32_t idx, gid;
 };
 
-constexpr int TILE_C = 8;        // home cells per tile side
+#ifndef CNT_TILE_C
+#define CNT_TILE_C 8
+#endif
+#ifndef CNT_TILE_HOME
+#define CNT_TILE_HOME 256
+#endif
+constexpr int TILE_C = CNT_TILE_C;     // home cells per tile side
 // shape of the tile kernel (A/B on the GPU box, tools/gpu_tile_ab.sh; junction count pass per 56 networks):
 // 512 threads / 2048 pairs / 1024 hits + staged line records (105 KB, 2 CTAs per SM) 4.18 ms; without staged line
 // records 4.49 (512 threads, 2 CTAs per SM by registers), 4.03 (384 threads), 3.86 ms (256 threads / 1024 / 512: 53 KB,
@@ -49,8 +55,9 @@ constexpr int TILE_C = 8;        // home cells per tile side
 #endif
 constexpr int CT = CNT_TILE_CT;  // threads of the tile kernel
 constexpr int CAP_REC = 1024;    // staged records per tile (32 KB)
-constexpr int CAP_HOME = 256;    // home sticks per batch of a tile
-constexpr int CAP_Q = CNT_TILE_Q;      // candidate pairs per chunk = capacity of the survivor queue
+constexpr int CAP_HOME = CNT_TILE_HOME;   // home sticks per batch of a tile
+constexpr int WQ = 64;                 // per-warp survivor queue (ring buffer: < 32 left over + 32 new)
+constexpr int CAP_Q = (CNT_TILE_CT / 32) * WQ;     // all queues of a CTA
 constexpr int CAP_HIT = CNT_TILE_HIT;  // junctions per batch of home sticks
 static_assert(CAP_HOME <= CT, "the scans over a batch of home sticks use one thread per stick");
 constexpr int MAX_RH = TILE_C + 2 * (RMAX + 2);      // rows / columns of the staged region
@@ -173,7 +180,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     extern __shared__ __align__(16) unsigned char smem_raw[];
     RecA *sA = (RecA *)smem_raw;                                  // [CAP_REC]
     Hit *s_hit = (Hit *)(sA + CAP_REC);                           // [CAP_HIT]
-    int32_t *s_q = (int32_t *)(s_hit + CAP_HIT);                  // [CAP_Q] survivor queue: home << 23 | region index
+    int32_t *s_q = (int32_t *)(s_hit + CAP_HIT);                  // [CT / 32][WQ] survivor queues: home << 23 | region index
     int32_t *s_cs = s_q + CAP_Q;                                  // [MAX_RH * (MAX_RH + 1)] cell starts (region index)
     int32_t *s_gq0 = s_cs + MAX_RH * (MAX_RH + 1);                // [MAX_RH] first global record of every region row
     int32_t *s_rb = s_gq0 + MAX_RH;                               // [MAX_RH + 1] first region index of every region row
@@ -181,9 +188,8 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
     int32_t *s_rng = s_pre + CAP_HOME + 1;                        // [CAP_HOME] packed cell range (region-relative)
     int32_t *s_cnt = s_rng + CAP_HOME;                            // [CAP_HOME + 1] junctions per home stick / row offsets
     int32_t *s_hq = s_cnt + CAP_HOME + 1;                         // [CAP_HOME] region index of every home stick
-    int32_t *s_blk = s_hq + CAP_HOME;                             // [CAP_Q / 32] home stick of every 32nd pair of a chunk
     __shared__ int s_red[8];
-    __shared__ int s_nq, s_nhit, s_base, s_warp[CT / 32];
+    __shared__ int s_nhit, s_base, s_warp[CT / 32];
     __shared__ unsigned long long s_tests;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -350,23 +356,52 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         if (tid < nb) s_pre[tid] = s_warp[wid] + inc - ncand;
         if (tid == nb - 1) s_pre[nb] = s_warp[wid] + inc;
         __syncthreads();
+        // The P candidate pairs of the batch are cut into one contiguous range per warp.  A warp walks its range 32
+        // pairs at a time: cheap tests (j > i, KD ball), survivors compacted by ballot into the warp's OWN queue; as
+        // soon as the queue holds 32 entries the warp evaluates the FP64 predicate on them with all lanes.  No CTA-wide
+        // barrier between the two phases (the version with one shared queue per CTA and chunks of pairs spent 3 of
+        // every 15 cycles per issued instruction waiting at them).
         const int P = s_pre[nb];
-        for (int p0 = 0; p0 < P; p0 += CAP_Q) {                  // chunks of candidate pairs
-            if (tid == 0) s_nq = 0;
-            // s_blk[k] = home stick owning pair p0 + 32 k: every home stick fills the blocks that start inside its range
-            if (tid < nb) {
-                const int a = max(s_pre[tid], p0), e = min(s_pre[tid + 1], min(P, p0 + CAP_Q));
-                for (int k = (a - p0 + 31) >> 5; p0 + 32 * k < e; k++) s_blk[k] = tid;
+        {
+            constexpr int NW = CT / 32;
+            const int per = ((P + NW * 32 - 1) / (NW * 32)) * 32;            // pairs per warp, a multiple of 32
+            const int pbeg = wid * per, pend = min(P, pbeg + per);
+            int32_t *wq = s_q + wid * WQ;
+            int qh = 0, qn = 0;                                              // ring buffer: head, entries (warp-uniform)
+            auto emit = [&](int entry) {
+                const int h = entry >> 23, v = entry & ((1 << 23) - 1);
+                const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
+                double xi, yi;
+                if (cnt_junction(l1, l2, &xi, &yi)) {
+                    const int rank = atomicAdd(&s_cnt[h], 1);
+                    const int at = atomicAdd(&s_nhit, 1);
+                    if (at < CAP_HIT) {
+                        Hit hh;
+                        hh.hr = (h << 16) | (rank & 0xFFFF);
+                        hh.j = recA(v).idx;
+                        hh.x = xi;
+                        hh.y = yi;
+                        s_hit[at] = hh;
+                    }
+                }
+            };
+            int hcur = 0;
+            if (pbeg < pend) {                                               // home stick of the warp's first pair
+                int lo = 0, hi = nb - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (s_pre[mid + 1] <= pbeg) lo = mid + 1; else hi = mid;
+                }
+                hcur = lo;
             }
-            __syncthreads();
-            // phase 1 (cheap): j > i and the KD ball; survivors -> queue (warp ballot + one shared atomic per warp)
-            const int pend = min(P, p0 + CAP_Q);
-            for (int pp = p0 + tid; pp < ((pend + 31) & ~31); pp += CT) {
+            for (int pp0 = pbeg; pp0 < pend; pp0 += 32) {
+                while (s_pre[hcur + 1] <= pp0) hcur++;                       // uniform
+                const int pp = pp0 + lane;
                 bool pass = false;
                 int entry = 0;
                 if (pp < pend) {
-                    int h = s_blk[(pp - p0) >> 5];                // home stick of the first pair of this warp's 32 pairs
-                    while (s_pre[h + 1] <= pp) h++;               // ... a few steps further for this lane
+                    int h = hcur;
+                    while (s_pre[h + 1] <= pp) h++;                          // a few steps further for this lane
                     const int rng = s_rng[h];
                     const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
                     int c = pp - s_pre[h], v = -1;
@@ -383,38 +418,22 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                     entry = (h << 23) | v;
                 }
                 const unsigned m = __ballot_sync(~0u, pass);
-                if (m) {
-                    int base = 0;
-                    if (lane == __ffs(m) - 1) base = atomicAdd(&s_nq, __popc(m));
-                    base = __shfl_sync(~0u, base, __ffs(m) - 1);
-                    if (pass) {
-                        s_q[base + __popc(m & ((1u << lane) - 1u))] = entry;
-                        tests++;
-                    }
+                if (pass) {
+                    wq[(qh + qn + __popc(m & ((1u << lane) - 1u))) & (WQ - 1)] = entry;
+                    tests++;
+                }
+                qn += __popc(m);
+                __syncwarp();
+                if (qn >= 32) {
+                    emit(wq[(qh + lane) & (WQ - 1)]);
+                    qh = (qh + 32) & (WQ - 1);
+                    qn -= 32;
+                    __syncwarp();
                 }
             }
-            __syncthreads();
-            // phase 2 (FP64 predicate) on the compacted queue: full warps
-            const int nq = s_nq;
-            for (int k = tid; k < nq; k += CT) {
-                const int entry = s_q[k], h = entry >> 23, v = entry & ((1 << 23) - 1);
-                const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
-                double xi, yi;
-                if (cnt_junction(l1, l2, &xi, &yi)) {
-                    const int rank = atomicAdd(&s_cnt[h], 1);
-                    const int at = atomicAdd(&s_nhit, 1);
-                    if (at < CAP_HIT) {
-                        Hit hh;
-                        hh.hr = (h << 16) | (rank & 0xFFFF);
-                        hh.j = recA(v).idx;
-                        hh.x = xi;
-                        hh.y = yi;
-                        s_hit[at] = hh;
-                    }
-                }
-            }
-            __syncthreads();
+            if (lane < qn) emit(wq[(qh + lane) & (WQ - 1)]);
         }
+        __syncthreads();
         // rows of the batch: offsets (exclusive scan of s_cnt), space in the temporary table, write-out
         const int nhit = s_nhit;
         int cnt_h = tid < nb ? s_cnt[tid] : 0;
@@ -865,7 +884,7 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
 static size_t tiles_smem() {
     return (size_t)CAP_REC * sizeof(RecA) + (size_t)CAP_HIT * sizeof(Hit) +
            4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
-                CAP_HOME + CAP_Q / 32);
+                CAP_HOME);
 }
 }  // namespace
 
