@@ -520,10 +520,12 @@ class Engine(object):
         return b
 
     # ------------------------------------------------------------------ stage 4+5: values + solve
-    def assemble_values(self, b, gates, gtables):
+    def assemble_values(self, b, gates, gtables, want_cls=True):
         """One value pass per gate configuration (cnet.py:99-131).  gates: list of GateState,
         gtables: list of [9, nlevels] float64 arrays.  Returns dict(g[NS,J], val[NS,NNZ],
-        diag[NS,R], rhs[NS,R])."""
+        diag[NS,R], rhs[NS,R]) (+ cls, gneg: the class-compressed form of the cluster PCG; want_cls=False leaves
+        them out -- the direct solver does not read them and they cost two random byte gathers per entry -- and
+        _ensure_classes adds them if the solve falls back to the cluster kernel)."""
         lib = self.lib
         NS = len(gates)
         R, NNZ, J = b.R, b.NNZ, b.J
@@ -539,7 +541,7 @@ class Engine(object):
             def nclasses(nl):       # base classes + (with virtual series junctions) their unordered pairs
                 nb = 9 * nl
                 return nb + nb * (nb + 1) // 2 if nv else nb
-            use_cls = all(nclasses(len(gs.levels)) <= 256 for gs in gates)
+            use_cls = want_cls and all(nclasses(len(gs.levels)) <= 256 for gs in gates)
             cls = torch.empty((NS, max(NNZ, 1)), dtype=torch.uint8, device=self.device) if use_cls else None
             gneg = np.zeros((NS, 256), dtype=np.float64)
             for q, (gs, tab) in enumerate(zip(gates, gtables)):
@@ -561,7 +563,20 @@ class Engine(object):
             out = dict(g=g, val=val, diag=diag, rhs=rhs)
             if use_cls:
                 out.update(cls=cls, gneg=self._dev(np.nan_to_num(gneg, nan=0.0), torch.float64))
+            elif not want_cls:
+                out["_cls_args"] = (gates, gtables)
         return out
+
+    def _ensure_classes(self, b, sysm):
+        """class-compressed values for the cluster PCG when assemble_values left them out (direct solve expected, but
+        the elimination exceeded its fill budget)"""
+        if "cls" in sysm or "_cls_args" not in sysm:
+            return
+        gates, gtables = sysm.pop("_cls_args")
+        full = self.assemble_values(b, gates, gtables, want_cls=True)
+        for k in ("cls", "gneg"):
+            if k in full:
+                sysm[k] = full[k]
 
     def _aggregates(self, b, sysm, sys_net, sys_slab, chunk_C=0):
         """tables of the two-level preconditioner (cnt_pcg_aggregates); returns (struct, keepalive)"""
@@ -642,6 +657,8 @@ class Engine(object):
                         method = "direct"
                 if auto and xd is None:
                     method = "cluster" if max_rows <= lib.cnt_pcg_cluster_max_rows() else "flat"
+                if method == "cluster" and self.cluster_compressed:
+                    self._ensure_classes(b, sysm)
                 compressed = method == "cluster" and self.cluster_compressed and "cls" in sysm
                 chunk_C = 0
                 if compressed:
@@ -839,7 +856,8 @@ class Engine(object):
         iters/relres/status[NS,B] (+ V[NS,S], I[NS,J], g[NS,J], x when want_fields)."""
         from .elements import conductance_table
         tabs = [conductance_table(element, onoffmap, gs.levels) for gs in gates]
-        sysm = self.assemble_values(b, gates, tabs)
+        direct_expected = row_shard is None and (self.solver == "direct" or (self.solver == "auto" and self._direct_ok(b)))
+        sysm = self.assemble_values(b, gates, tabs, want_cls=not direct_expected)
         prio = [max(abs(v) for v in gs.levels) for gs in gates]   # higher |Vg| -> more iterations -> first
         x0 = self.linear_guess(b, len(gates)) if self.initial_guess == "linear" else None
         if (row_shard is None and b.B == 1 and self.solver == "auto" and self.precond == "twolevel" and

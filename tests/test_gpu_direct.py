@@ -137,6 +137,24 @@ def test_fill_budget_rejects_dense_graphs(engine):
     assert plan is not None and plan.max_deg == n - 1 and plan.npairs == 40 * sum(d * (d - 1) // 2 for d in range(n))
 
 
+def test_auto_falls_back_to_the_cluster_solver_with_classes(engine):
+    """solver 'auto' expects the direct solver and skips the class-compressed values; when the elimination exceeds its
+    fill budget the cluster PCG takes over and gets them after the fact (Engine._ensure_classes): same currents"""
+    b = engine.generate([6400, 3000], 20.0, seed=21)
+    ref = engine.measure_fullnet(b, onoffmap=1)
+    assert engine.last_solver == "direct"
+    old = engine.direct_max_fill
+    engine.direct_max_fill = 1e-6            # no budget at all -> plan rejected
+    try:
+        b2 = engine.generate([6400, 3000], 20.0, seed=21)
+        res = engine.measure_fullnet(b2, onoffmap=1)
+        assert engine.last_solver.startswith("cluster") and np.all(res["status"] == 0)
+    finally:
+        engine.direct_max_fill = old
+    for key in ("ion", "ioff_back", "ioff_total", "ioff_partial"):
+        assert np.all(np.abs(res[key] - ref[key]) <= 1e-9 * np.abs(ref[key])), key
+
+
 @pytest.mark.parametrize("dense_max", [40, 1000])
 def test_cuda_dense_tail_equals_restatement(engine, dense_max):
     """batch of two copies of a system; sparse rounds down to dense_max unknowns per network, then k_sm_dense"""
