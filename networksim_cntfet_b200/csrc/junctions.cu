@@ -56,6 +56,7 @@ constexpr int TILE_C = CNT_TILE_C;     // home cells per tile side
 constexpr int CT = CNT_TILE_CT;  // threads of the tile kernel
 constexpr int CAP_REC = 1024;    // staged records per tile (32 KB)
 constexpr int CAP_HOME = CNT_TILE_HOME;   // home sticks per batch of a tile
+constexpr int MAXRUN = 1024;           // runs (home stick, cell row) per batch of home sticks
 constexpr int WQ = 64;                 // per-warp survivor queue (ring buffer: < 32 left over + 32 new)
 constexpr int CAP_Q = (CNT_TILE_CT / 32) * WQ;     // all queues of a CTA
 constexpr int CAP_HIT = CNT_TILE_HIT;  // junctions per batch of home sticks
@@ -178,18 +179,21 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                                               int64_t cap_tmp, int32_t *__restrict__ ntmp, int32_t *__restrict__ errflag,
                                               int shard_rank, int shard_world) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    RecA *sA = (RecA *)smem_raw;                                  // [CAP_REC]
-    Hit *s_hit = (Hit *)(sA + CAP_REC);                           // [CAP_HIT]
-    int32_t *s_q = (int32_t *)(s_hit + CAP_HIT);                  // [CT / 32][WQ] survivor queues: home << 23 | region index
+    double *s_xc = (double *)smem_raw;                            // [CAP_REC] staged records of the region, SoA: centre,
+    double *s_yc = s_xc + CAP_REC;                                // [CAP_REC]
+    double *s_hlen = s_yc + CAP_REC;                              // [CAP_HOME] length of every home stick of the batch
+    Hit *s_hit = (Hit *)(s_hlen + CAP_HOME);                      // [CAP_HIT]
+    int32_t *s_idx = (int32_t *)(s_hit + CAP_HIT);                // [CAP_REC] ... and network-local stick index
+    int32_t *s_q = s_idx + CAP_REC;                               // [CT / 32][WQ] survivor queues: home << 23 | region index
     int32_t *s_cs = s_q + CAP_Q;                                  // [MAX_RH * (MAX_RH + 1)] cell starts (region index)
     int32_t *s_gq0 = s_cs + MAX_RH * (MAX_RH + 1);                // [MAX_RH] first global record of every region row
     int32_t *s_rb = s_gq0 + MAX_RH;                               // [MAX_RH + 1] first region index of every region row
-    int32_t *s_pre = s_rb + MAX_RH + 1;                           // [CAP_HOME + 1] first pair of every home stick
-    int32_t *s_rng = s_pre + CAP_HOME + 1;                        // [CAP_HOME] packed cell range (region-relative)
-    int32_t *s_cnt = s_rng + CAP_HOME;                            // [CAP_HOME + 1] junctions per home stick / row offsets
+    int32_t *s_rpre = s_rb + MAX_RH + 1;                          // [MAXRUN + 1] first pair of every run of the batch
+    int32_t *s_rpack = s_rpre + MAXRUN + 1;                       // [MAXRUN] run: home << 23 | first region index
+    int32_t *s_cnt = s_rpack + MAXRUN;                            // [CAP_HOME + 1] junctions per home stick / row offsets
     int32_t *s_hq = s_cnt + CAP_HOME + 1;                         // [CAP_HOME] region index of every home stick
     __shared__ int s_red[8];
-    __shared__ int s_nhit, s_base, s_warp[CT / 32];
+    __shared__ int s_nhit, s_base, s_warp[CT / 32], s_warp2[CT / 32], s_P;
     __shared__ unsigned long long s_tests;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -292,36 +296,49 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         s_cs[k] = s_rb[r] + (__ldg(cs + (ry0 + r) * g.G + rx0 + c) - s_gq0[r]);
     }
     const bool staged = nrec <= CAP_REC;
+    int s0net;                                                    // first stick of the network: gid = s0net + idx
+    {
+        const RecA r0 = gA[home_q(0)];
+        s0net = r0.gid - r0.idx;
+    }
     if (staged) {
         for (int k = tid; k < nrec; k += CT) {
             int r = 0;
             while (k >= s_rb[r + 1]) r++;
-            const int q = s_gq0[r] + (k - s_rb[r]);
-            sA[k] = gA[q];
+            const RecA rec = gA[s_gq0[r] + (k - s_rb[r])];
+            s_xc[k] = rec.xc;
+            s_yc[k] = rec.yc;
+            s_idx[k] = rec.idx;
         }
     }
     __syncthreads();
-    // record accessors: region index -> record (shared memory when staged, global memory otherwise)
-    auto recA = [&](int v) -> RecA {
-        if (staged) return sA[v];
+    // record accessor: region index -> centre and index (shared memory when staged, global memory otherwise)
+    auto cand = [&](int v, double &xc, double &yc, int &idx) {
+        if (staged) {
+            xc = s_xc[v];
+            yc = s_yc[v];
+            idx = s_idx[v];
+            return;
+        }
         int r = 0;
         while (v >= s_rb[r + 1]) r++;
-        return gA[s_gq0[r] + (v - s_rb[r])];
+        const RecA rec = gA[s_gq0[r] + (v - s_rb[r])];
+        xc = rec.xc;
+        yc = rec.yc;
+        idx = rec.idx;
     };
-    // line record of a region record: only the survivors of the ball test (a quarter of the candidates) need it, so it
-    // is not staged -- 32 KB less shared memory per CTA is a third CTA per SM -- but read through L1 / L2 by stick id
-    auto recB = [&](int v) -> CntLine { return line[recA(v).gid]; };
     unsigned long long tests = 0;
-    for (int hb = 0; hb < nhome; hb += CAP_HOME) {               // batches of home sticks
-        const int nb = min(CAP_HOME, nhome - hb);
-        // candidate count of every home stick
-        int ncand = 0;
-        if (tid < nb) {
+    for (int hb = 0; hb < nhome;) {                              // batches of home sticks
+        const int nb0 = min(CAP_HOME, nhome - hb);
+        // candidate pairs and runs (one per cell row of its range) of every home stick
+        int ncand = 0, nrows = 0, rng = 0;
+        double mylen = 0.0;
+        if (tid < nb0) {
             const int q = home_q(hb + tid);
             s_cnt[tid] = 0;
-            s_rng[tid] = 0;
             s_hq[tid] = -1;                                       // wide stick: no pairs here, its row is k_wide's
             const RecA me = gA[q];
+            mylen = me.len;
             if (!is_wide(me.len, g.G)) {
                 // region index of the home stick: its cell row inside the region
                 const int hr = home_row(hb + tid);
@@ -330,38 +347,69 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                 cell_range(me, g.G, cx0, cx1, cy0, cy1);
                 for (int cy = cy0; cy <= cy1; cy++)
                     ncand += s_cs[(cy - ry0) * (RW + 1) + (cx1 + 1 - rx0)] - s_cs[(cy - ry0) * (RW + 1) + (cx0 - rx0)];
-                s_rng[tid] = (cx0 - rx0) | ((cx1 - rx0) << 8) | ((cy0 - ry0) << 16) | ((cy1 - ry0) << 24);
+                nrows = cy1 - cy0 + 1;
+                rng = (cx0 - rx0) | ((cx1 - rx0) << 8) | ((cy0 - ry0) << 16) | ((cy1 - ry0) << 24);
             }
         }
-        // exclusive scan of the counts over the batch (nb <= CAP_HOME <= CT)
-        int inc = tid < nb ? ncand : 0;
+        // exclusive scans of both counts over the batch (nb0 <= CAP_HOME <= CT)
+        int inc = ncand, incr = nrows;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            int t = __shfl_up_sync(~0u, inc, o);
-            if (lane >= o) inc += t;
+            const int t = __shfl_up_sync(~0u, inc, o), tr = __shfl_up_sync(~0u, incr, o);
+            if (lane >= o) {
+                inc += t;
+                incr += tr;
+            }
         }
-        if (lane == 31) s_warp[wid] = inc;
+        if (lane == 31) {
+            s_warp[wid] = inc;
+            s_warp2[wid] = incr;
+        }
         if (tid == 0) s_nhit = 0;
         __syncthreads();
         if (wid == 0) {
-            int w = lane < CT / 32 ? s_warp[lane] : 0, wi = w;
+            int w = lane < CT / 32 ? s_warp[lane] : 0, wi = w, w2 = lane < CT / 32 ? s_warp2[lane] : 0, wi2 = w2;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                int t = __shfl_up_sync(~0u, wi, o);
-                if (lane >= o) wi += t;
+                const int t = __shfl_up_sync(~0u, wi, o), t2 = __shfl_up_sync(~0u, wi2, o);
+                if (lane >= o) {
+                    wi += t;
+                    wi2 += t2;
+                }
             }
-            if (lane < CT / 32) s_warp[lane] = wi - w;
+            if (lane < CT / 32) {
+                s_warp[lane] = wi - w;
+                s_warp2[lane] = wi2 - w2;
+            }
         }
         __syncthreads();
-        if (tid < nb) s_pre[tid] = s_warp[wid] + inc - ncand;
-        if (tid == nb - 1) s_pre[nb] = s_warp[wid] + inc;
+        const int pre = s_warp[wid] + inc - ncand, rpre = s_warp2[wid] + incr - nrows;     // first pair / run of this home
+        // the batch ends where the run table is full (prefixes are monotone: the home sticks that fit are a prefix)
+        const int nb = __syncthreads_count(tid < nb0 && rpre + nrows <= MAXRUN);
+        if (tid < nb) {
+            s_hlen[tid] = mylen;
+            const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255;
+            int pp = pre;
+            for (int k = 0; k < nrows; k++) {
+                const int a0 = s_cs[(cy0 + k) * (RW + 1) + cx0], a1 = s_cs[(cy0 + k) * (RW + 1) + cx1 + 1];
+                s_rpre[rpre + k] = pp;
+                s_rpack[rpre + k] = (tid << 23) | a0;
+                pp += a1 - a0;
+            }
+            if (tid == nb - 1) {
+                s_rpre[rpre + nrows] = pp;                        // sentinel: total pairs of the batch
+                s_P = pp;
+                s_warp2[0] = rpre + nrows;                        // runs of the batch
+            }
+        }
         __syncthreads();
         // The P candidate pairs of the batch are cut into one contiguous range per warp.  A warp walks its range 32
-        // pairs at a time: cheap tests (j > i, KD ball), survivors compacted by ballot into the warp's OWN queue; as
-        // soon as the queue holds 32 entries the warp evaluates the FP64 predicate on them with all lanes.  No CTA-wide
-        // barrier between the two phases (the version with one shared queue per CTA and chunks of pairs spent 3 of
-        // every 15 cycles per issued instruction waiting at them).
-        const int P = s_pre[nb];
+        // pairs at a time; pair p lies in run r (s_rpre[r] <= p < s_rpre[r + 1]: a short forward search from the run of
+        // the warp's first pair) and is candidate a0 + (p - s_rpre[r]) of that run's home stick -- runs are contiguous in
+        // the region.  Cheap tests (j > i, KD ball), survivors compacted by ballot into the warp's OWN queue; as soon as
+        // the queue holds 32 entries the warp evaluates the FP64 predicate on them with all lanes.  No CTA-wide barrier
+        // between the two phases.
+        const int P = s_P, nruns = s_warp2[0];
         {
             constexpr int NW = CT / 32;
             const int per = ((P + NW * 32 - 1) / (NW * 32)) * 32;            // pairs per warp, a multiple of 32
@@ -370,7 +418,11 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
             int qh = 0, qn = 0;                                              // ring buffer: head, entries (warp-uniform)
             auto emit = [&](int entry) {
                 const int h = entry >> 23, v = entry & ((1 << 23) - 1);
-                const CntLine l1 = recB(s_hq[h]), l2 = recB(v);
+                double xh, yh, xo, yo;
+                int ih, io;
+                cand(s_hq[h], xh, yh, ih);
+                cand(v, xo, yo, io);
+                const CntLine l1 = line[s0net + ih], l2 = line[s0net + io];
                 double xi, yi;
                 if (cnt_junction(l1, l2, &xi, &yi)) {
                     const int rank = atomicAdd(&s_cnt[h], 1);
@@ -378,43 +430,37 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
                     if (at < CAP_HIT) {
                         Hit hh;
                         hh.hr = (h << 16) | (rank & 0xFFFF);
-                        hh.j = recA(v).idx;
+                        hh.j = io;
                         hh.x = xi;
                         hh.y = yi;
                         s_hit[at] = hh;
                     }
                 }
             };
-            int hcur = 0;
-            if (pbeg < pend) {                                               // home stick of the warp's first pair
-                int lo = 0, hi = nb - 1;
+            int rcur = 0;
+            if (pbeg < pend) {                                               // run of the warp's first pair
+                int lo = 0, hi = nruns - 1;
                 while (lo < hi) {
                     const int mid = (lo + hi) >> 1;
-                    if (s_pre[mid + 1] <= pbeg) lo = mid + 1; else hi = mid;
+                    if (s_rpre[mid + 1] <= pbeg) lo = mid + 1; else hi = mid;
                 }
-                hcur = lo;
+                rcur = lo;
             }
             for (int pp0 = pbeg; pp0 < pend; pp0 += 32) {
-                while (s_pre[hcur + 1] <= pp0) hcur++;                       // uniform
+                while (s_rpre[rcur + 1] <= pp0) rcur++;                      // uniform
                 const int pp = pp0 + lane;
                 bool pass = false;
                 int entry = 0;
                 if (pp < pend) {
-                    int h = hcur;
-                    while (s_pre[h + 1] <= pp) h++;                          // a few steps further for this lane
-                    const int rng = s_rng[h];
-                    const int cx0 = rng & 255, cx1 = (rng >> 8) & 255, cy0 = (rng >> 16) & 255, cy1 = rng >> 24;
-                    int c = pp - s_pre[h], v = -1;
-                    for (int cy = cy0; cy <= cy1; cy++) {
-                        const int a0 = s_cs[cy * (RW + 1) + cx0], a1 = s_cs[cy * (RW + 1) + cx1 + 1];
-                        if (c < a1 - a0) {
-                            v = a0 + c;
-                            break;
-                        }
-                        c -= a1 - a0;
-                    }
-                    const RecA me = recA(s_hq[h]), o = recA(v);
-                    pass = o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc);
+                    int r = rcur;
+                    while (s_rpre[r + 1] <= pp) r++;                         // a few steps further for this lane
+                    const int pack = s_rpack[r];
+                    const int h = pack >> 23, v = (pack & ((1 << 23) - 1)) + (pp - s_rpre[r]);
+                    double xh, yh, xo, yo;
+                    int ih, io;
+                    cand(s_hq[h], xh, yh, ih);
+                    cand(v, xo, yo, io);
+                    pass = io > ih && cnt_in_ball(xh, yh, s_hlen[h], xo, yo);
                     entry = (h << 23) | v;
                 }
                 const unsigned m = __ballot_sync(~0u, pass);
@@ -471,7 +517,10 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
         const int base = s_base;
         if (tid < nb) {
             if (s_hq[tid] >= 0) {
-                const int gid = recA(s_hq[tid]).gid;
+                double xh, yh;
+                int ih;
+                cand(s_hq[tid], xh, yh, ih);
+                const int gid = s0net + ih;
                 jcount[gid] = cnt_h;
                 jtmp[gid] = base >= 0 ? base + roff : -1;
             }
@@ -488,6 +537,7 @@ __global__ void __launch_bounds__(CT) k_tiles(int B, const Geo *__restrict__ geo
             }
         }
         __syncthreads();
+        hb += nb;
     }
     // candidate pairs inside the ball (the reference's KD-tree query count), one atomic per CTA
 #pragma unroll
@@ -882,8 +932,8 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
 }
 
 static size_t tiles_smem() {
-    return (size_t)CAP_REC * sizeof(RecA) + (size_t)CAP_HIT * sizeof(Hit) +
-           4 * ((size_t)CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (CAP_HOME + 1) + CAP_HOME + (CAP_HOME + 1) +
+    return 8 * ((size_t)2 * CAP_REC + CAP_HOME) + (size_t)CAP_HIT * sizeof(Hit) +
+           4 * ((size_t)CAP_REC + CAP_Q + MAX_RH * (MAX_RH + 1) + MAX_RH + (MAX_RH + 1) + (MAXRUN + 1) + MAXRUN + (CAP_HOME + 1) +
                 CAP_HOME);
 }
 }  // namespace
