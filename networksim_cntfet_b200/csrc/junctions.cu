@@ -130,7 +130,7 @@ __global__ void k_bin(int64_t S, const int32_t *__restrict__ soff, int B, const 
                       const int32_t *__restrict__ cell_start, int32_t *__restrict__ cell_fill,
                       const CntLine *__restrict__ line, const double *__restrict__ xc,
                       const double *__restrict__ yc, const double *__restrict__ len,
-                      RecA *__restrict__ recA, CntLine *__restrict__ recB) {
+                      RecA *__restrict__ recA) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int key = cellkey[s];
@@ -141,8 +141,7 @@ __global__ void k_bin(int64_t S, const int32_t *__restrict__ soff, int B, const 
     r.xc = xc[s]; r.yc = yc[s]; r.len = len[s];
     r.idx = (int)s - soff[b];
     r.gid = (int)s;
-    recA[pos] = r;
-    recB[pos] = line[s];
+    recA[pos] = r;                // the line records stay in stick order: only survivors of the ball test read them
 }
 
 // cells overlapping the bounding square of the ball of a stick; 1e-6 cell of slack covers the rounding
@@ -622,7 +621,7 @@ __global__ void k_place(int B, const int32_t *__restrict__ soff, int64_t S, cons
 // recomputed in place, one thread per row; errflag bit 1 says whether there is any such row ----
 __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__restrict__ soff, const Geo *__restrict__ geo,
                                                     const int32_t *__restrict__ cell_start, int32_t total_cells,
-                                                    const RecA *__restrict__ recA, const CntLine *__restrict__ recB,
+                                                    const RecA *__restrict__ recA, const CntLine *__restrict__ line,
                                                     const int32_t *__restrict__ errflag, const int32_t *__restrict__ jtmp,
                                                     const int32_t *__restrict__ jstart, const uint8_t *__restrict__ kind,
                                                     int32_t *__restrict__ stick1, int32_t *__restrict__ stick2,
@@ -638,7 +637,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
     const Geo g = geo[b];
     if (is_wide(me.len, g.G)) return;                             // k_wide's row
     if (shard_world > 1 && slab_owner(cell_of(me.xc, g.G) / TILE_C, g.TG, shard_world) != shard_rank) return;
-    const CntLine l1 = recB[p];
+    const CntLine l1 = line[me.gid];
     int cx0, cx1, cy0, cy1;
     cell_range(me, g.G, cx0, cx1, cy0, cy1);
     const int base = jstart[me.gid], s0 = soff[b];
@@ -650,7 +649,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
             const RecA o = recA[q];
             if (o.idx <= me.idx || !cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc)) continue;
             double xi, yi;
-            if (cnt_junction(l1, recB[q], &xi, &yi)) {
+            if (cnt_junction(l1, line[o.gid], &xi, &yi)) {
                 // insertion by stick2 (rows are short)
                 int c = base + cnt - 1;
                 while (c >= base && stick2[c] > o.idx) {
@@ -674,7 +673,7 @@ __global__ void __launch_bounds__(128) k_cells_fill(int B, const int32_t *__rest
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_wide(int B, const int32_t *__restrict__ soff, const Geo *__restrict__ geo,
                                               const int32_t *__restrict__ cell_start, const RecA *__restrict__ recA,
-                                              const CntLine *__restrict__ recB, const int32_t *__restrict__ nwide,
+                                              const int32_t *__restrict__ nwide,
                                               const int32_t *__restrict__ widelist, const CntLine *__restrict__ line,
                                               const double *__restrict__ xc, const double *__restrict__ yc,
                                               const double *__restrict__ len, int32_t *__restrict__ jcount,
@@ -710,7 +709,7 @@ __global__ void __launch_bounds__(256) k_wide(int B, const int32_t *__restrict__
                     const RecA o = recA[q];
                     if (o.idx > me.idx && cnt_in_ball(me.xc, me.yc, me.len, o.xc, o.yc)) {
                         tests++;
-                        hit = cnt_junction(l1, recB[q], &xi, &yi);
+                        hit = cnt_junction(l1, line[o.gid], &xi, &yi);
                         oj = o.idx;
                     }
                 }
@@ -856,7 +855,6 @@ struct Plan {
     Geo *d_geo;
     CntLine *line;
     RecA *recA;
-    CntLine *recB;
     int32_t *cellkey, *cell_count /* total_cells+1, scanned in place */, *cell_fill, *nlong, *errflag, *ntmp, *jtmp, *tj, *segcnt, *nwide, *widelist;
     double *tx, *ty;
     void *scan_ws;
@@ -869,7 +867,7 @@ static int64_t plan_bytes(int B, int64_t S, int64_t total_cells) {
     using cnt::ws_bytes_for;
     const int64_t ct = tmp_capacity(S);
     return ws_bytes_for(B + 1, sizeof(Geo)) + ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, sizeof(RecA)) +
-           ws_bytes_for(S, sizeof(CntLine)) + ws_bytes_for(S, 4) + ws_bytes_for(total_cells + 1, 4) +
+           ws_bytes_for(S, 4) + ws_bytes_for(total_cells + 1, 4) +
            ws_bytes_for(total_cells + 1, 4) + ws_bytes_for(B, 4) + ws_bytes_for(2, 4) + ws_bytes_for(S + 1, 4) +
            ws_bytes_for((int64_t)B * DENSE_SPLIT * DENSE_SEGS, 4) + ws_bytes_for(S + 1, 4) +
            ws_bytes_for(ct, 4) + 2 * ws_bytes_for(ct, 8) + cnt_scan_workspace_bytes(total_cells + 1);
@@ -906,7 +904,6 @@ static int carve(Plan &p, int B, const int32_t *h_soff, void *ws, int64_t ws_byt
     p.d_geo = w.take<Geo>(B + 1);
     p.line = w.take<CntLine>(p.S);
     p.recA = w.take<RecA>(p.S);
-    p.recB = w.take<CntLine>(p.S);
     p.cellkey = w.take<int32_t>(p.S);
     p.cell_count = w.take<int32_t>(p.total_cells + 1);
     p.cell_fill = w.take<int32_t>(p.total_cells + 1);
@@ -978,7 +975,7 @@ static int junction_count(int B, const int32_t *soff, const int32_t *h_soff, con
     rc = cnt_exclusive_scan_i32(p.cell_count, p.cell_count, p.total_cells, 1, p.scan_ws, p.scan_ws_bytes, stream);
     if (rc) return rc;
     k_bin<<<cnt::grid_for(p.S, 256), 256, 0, st>>>(p.S, soff, B, p.cellkey, p.cell_count, p.cell_fill, p.line, xc, yc,
-                                                   length, p.recA, p.recB);
+                                                   length, p.recA);
     CNT_LAUNCHED();
     static bool attr_set = false;
     if (!attr_set) {
@@ -989,7 +986,7 @@ static int junction_count(int B, const int32_t *soff, const int32_t *h_soff, con
                                                                ntests, p.tj, p.tx, p.ty, p.cap_tmp, p.ntmp, p.errflag,
                                                                shard_rank, shard_world);
     CNT_LAUNCHED();
-    k_wide<false><<<148 * 2, 256, 0, st>>>(B, soff, p.d_geo, p.cell_count, p.recA, p.recB, p.nwide, p.widelist, p.line, xc, yc,
+    k_wide<false><<<148 * 2, 256, 0, st>>>(B, soff, p.d_geo, p.cell_count, p.recA, p.nwide, p.widelist, p.line, xc, yc,
                                            length, jcount, ntests, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
                                            nullptr, shard_rank, shard_world);
     CNT_LAUNCHED();
@@ -1036,10 +1033,10 @@ static int junction_fill(int B, const int32_t *soff, const int32_t *h_soff, cons
                                                      stick2, jx, jy, kind2);
     CNT_LAUNCHED();
     k_cells_fill<<<cnt::grid_for(p.S, 128), 128, 0, st>>>(B, soff, p.d_geo, p.cell_count, (int32_t)p.total_cells, p.recA,
-                                                          p.recB, p.errflag, p.jtmp, jstart, kind, stick1, stick2, jx, jy, kind2,
+                                                          p.line, p.errflag, p.jtmp, jstart, kind, stick1, stick2, jx, jy, kind2,
                                                           shard_rank, shard_world);
     CNT_LAUNCHED();
-    k_wide<true><<<148 * 2, 256, 0, st>>>(B, soff, p.d_geo, p.cell_count, p.recA, p.recB, p.nwide, p.widelist, p.line, xc, yc,
+    k_wide<true><<<148 * 2, 256, 0, st>>>(B, soff, p.d_geo, p.cell_count, p.recA, p.nwide, p.widelist, p.line, xc, yc,
                                           length, nullptr, nullptr, jstart, kind, stick1, stick2, jx, jy, kind2, shard_rank,
                                           shard_world);
     CNT_LAUNCHED();
