@@ -214,3 +214,26 @@ def check_plan_invariants(plan, A, R, dense_max):
     assert len(plan.dslot) == sum(len(s) for s in adj.values()) // 2 and len(np.unique(plan.depos)) == len(plan.dslot)
     assert not (set(plan.dslot.tolist()) & dead_slots)
     assert plan.nnzL == len(plan.nbr)
+
+
+def test_scratch_pool_is_grow_only_and_plans_hand_their_buffer_back():
+    """host logic of the direct solver's persistent work areas (starmesh.scratch): reuse while the request fits, growth
+    with headroom, exclusive ownership of a taken buffer, return of a plan's buffer when the plan dies"""
+    import torch
+    from networksim_cntfet_b200 import starmesh
+    pool = {}
+    a = starmesh.scratch(pool, "ws", 1000, "cpu")
+    assert a.numel() >= 1000 and starmesh.scratch(pool, "ws", 900, "cpu") is a          # fits: same buffer
+    b = starmesh.scratch(pool, "ws", a.numel() + 1, "cpu")
+    assert b is not a and b.numel() >= (a.numel() + 1) * 8 // 7 and pool["ws"] is b      # grew with headroom
+    assert starmesh.scratch(None, "ws", 10, "cpu").numel() == 10                         # no pool: exact size
+    p = starmesh.Plan()
+    p.buf = starmesh.scratch(pool, "sm_plan", 5000, "cpu", take=True)
+    p._pool = pool
+    assert pool["sm_plan"] is None                                                        # the plan owns it
+    q = starmesh.scratch(pool, "sm_plan", 5000, "cpu", take=True)                         # a second live plan gets its own
+    assert q is not p.buf
+    buf = p.buf
+    del p
+    assert pool["sm_plan"] is buf                                                         # handed back
+    assert starmesh.scratch(pool, "sm_plan", 4000, "cpu", take=True) is buf and pool["sm_plan"] is None
