@@ -14,10 +14,11 @@
 // purpose: for these Laplacians the TRUE residual stagnates near 1e-12 ||b|| while the error
 // keeps falling with the recurrence residual ("PCG accuracy").
 #include <vector>
-#include "common.cuh"
+#include "spmv_stream.cuh"
 
 namespace {
 constexpr int TILE = 256;
+static_assert(TILE == cnt::spmv::TB, "k_spmv: one row per thread of the streaming SpMV");
 
 struct Tile {
     int32_t sys;    // system index
@@ -110,17 +111,22 @@ __global__ void k_scal_init(Ctx c, int ntiles_total, double rtol, int nsys) {
     c.scal[s] = sc;
 }
 
+// q = A p of one tile of 256 rows of one system: the streaming SpMV of spmv_stream.cuh (the tile's entries are one
+// contiguous range, read with coalesced 16-byte loads, products through shared memory, rows summed in CSR order)
 __global__ void __launch_bounds__(TILE) k_spmv(Ctx c) {
     __shared__ double sm[32];
+    __shared__ __align__(16) double s_prod[cnt::spmv::CAP];
     Tile t = c.tiles[blockIdx.x];
-    if (c.scal[t.sys].done) return;
+    if (c.scal[t.sys].done) return;                    // CTA-uniform
     Sys s = c.sys[t.sys];
     int i = threadIdx.x;
+    const double *pslab = c.p + (int64_t)t.slab * c.R;
+    const double qi = cnt::spmv::stream_rows(t.row0, (int64_t)t.row0 + t.nrows, c.NNZ, c.rowptr, c.col,
+                                             c.val + (int64_t)t.slab * c.NNZ, c.diag + (int64_t)t.slab * c.R,
+                                             pslab + s.row0, s_prod, pslab);
     double pq = 0;
     if (i < t.nrows) {
-        int row = t.row0 + i;
-        int64_t v = (int64_t)t.slab * c.R + row;
-        double qi = spmv_row(c, t.slab, s.row0, row, c.p);
+        int64_t v = (int64_t)t.slab * c.R + t.row0 + i;
         c.q[v] = qi;
         pq = c.p[v] * qi;
     }

@@ -22,7 +22,7 @@ constexpr int CAP = 2048;          // products staged per trip (16 KB)
 __device__ __forceinline__ double stream_rows(int64_t r0, int64_t n_rows, int64_t nnz, const int32_t *__restrict__ rowptr,
                                               const int32_t *__restrict__ col, const double *__restrict__ val,
                                               const double *__restrict__ diag, const double *__restrict__ x,
-                                              double *s_prod) {
+                                              double *s_prod, const double *__restrict__ xd = nullptr) {
     const int t = threadIdx.x;
     const int64_t r = r0 + t, rend = r0 + TB < n_rows ? r0 + TB : n_rows;
     const int kb = __ldg(rowptr + r0), ke = __ldg(rowptr + rend);
@@ -31,7 +31,8 @@ __device__ __forceinline__ double stream_rows(int64_t r0, int64_t n_rows, int64_
     if (r < n_rows) {
         rs = __ldg(rowptr + r);
         re = __ldg(rowptr + r + 1);
-        if (diag) acc = __ldg(diag + r) * __ldg(x + r);
+        if (diag) acc = __ldg(diag + r) * __ldg((xd ? xd : x) + r);     // xd: x indexed like the rows when the columns
+                                                                        // are relative to another base (batched systems)
     }
     const bool vec = ((reinterpret_cast<uintptr_t>(col) & 15) == 0) && ((reinterpret_cast<uintptr_t>(val) & 15) == 0);
     for (int kc = kb & ~3; kc < ke; kc += CAP) {
