@@ -47,10 +47,15 @@ __global__ void k_uf_init(int64_t S, int32_t *__restrict__ parent, int32_t *__re
     }
 }
 
-// Every thread walks UF_K junctions at once: the 2 * UF_K root chases are independent chains of L2 round trips
-// (volatile loads, ~18 hops each), so their loads are issued side by side -- the pass is latency-bound (ncu on the
-// one-junction-per-thread version: 3 % of the issue slots busy, 430 cycles per instruction), memory-level
-// parallelism per thread is what it lacked.  Junction e of a thread = first + k * stride (coalesced index loads).
+// Union pass: Rem's algorithm with splicing (the scheme the ConnectIt study found fastest among the concurrent
+// union-finds), UF_K junctions per thread interleaved.  For a junction (u, v) the two climbs advance in lock step --
+// always the side whose parent has the larger index -- and stop as soon as both sides see the same parent: a junction
+// inside an already connected neighbourhood ends after a hop or two instead of two full chases to the root.  On
+// the way every visited stick is spliced onto the other side's (smaller) parent with an atomicMin, which compresses
+// the paths.  A root is hooked with an atomicCAS under the other side's parent (smaller index: the root of a tree
+// stays its minimum stick id == the canonical label).  Loads go through L1: a stale parent is still an ancestor, a
+// stale "root" fails its CAS and continues from the parent the CAS returns.  The network's first stick is the smallest
+// id of the network, hence always a root: it is recognised without loading its (hot) line.
 constexpr int UF_K = 4;
 __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff,
                                                   int64_t J, const int32_t *__restrict__ stick1,
@@ -58,68 +63,57 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
                                                   uint8_t *__restrict__ hasj) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const int64_t first = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    int cur[2 * UF_K], par[2 * UF_K], base[UF_K];
+    int rx[UF_K], ry[UF_K], px[UF_K], py[UF_K], base[UF_K];
     bool live[UF_K];
+    auto load = [&](int x, int s0) { return x == s0 ? s0 : ld_ca(parent + x); };
 #pragma unroll
     for (int k = 0; k < UF_K; k++) {
         const int64_t e = first + k * stride;
         live[k] = e < J;
-        base[k] = 0;
-        cur[2 * k] = cur[2 * k + 1] = 0;
+        rx[k] = ry[k] = px[k] = py[k] = base[k] = 0;
         if (live[k]) {
             const int b = cnt::find_segment(joff, B, (int)e);
             const int s0 = soff[b];
             base[k] = s0;
-            cur[2 * k] = s0 + stick1[e];
-            cur[2 * k + 1] = s0 + stick2[e];
-            hasj[cur[2 * k]] = 1;
-            hasj[cur[2 * k + 1]] = 1;
+            rx[k] = s0 + stick1[e];
+            ry[k] = s0 + stick2[e];
+            hasj[rx[k]] = 1;
+            hasj[ry[k]] = 1;
         }
     }
-    // roots of all endpoints, path halving, the chases interleaved; s0 of a network is a root by construction
 #pragma unroll
-    for (int k = 0; k < 2 * UF_K; k++) par[k] = live[k >> 1] && cur[k] != base[k >> 1] ? ld_ca(parent + cur[k]) : cur[k];
+    for (int k = 0; k < UF_K; k++) {
+        if (live[k]) {
+            px[k] = load(rx[k], base[k]);
+            py[k] = load(ry[k], base[k]);
+        }
+    }
     for (;;) {
         bool any = false;
-        int gp[2 * UF_K];
 #pragma unroll
-        for (int k = 0; k < 2 * UF_K; k++) {
-            gp[k] = par[k];
-            if (par[k] != cur[k] && par[k] != base[k >> 1]) {
-                gp[k] = ld_ca(parent + par[k]);
-                any = true;
+        for (int k = 0; k < UF_K; k++) {
+            if (!live[k]) continue;
+            if (px[k] == py[k]) {                              // both sides under one parent: same component
+                live[k] = false;
+                continue;
+            }
+            any = true;
+            if (px[k] < py[k]) {                               // x: the side whose parent has the larger index
+                int t = rx[k]; rx[k] = ry[k]; ry[k] = t;
+                t = px[k]; px[k] = py[k]; py[k] = t;
+            }
+            if (rx[k] == px[k]) {                              // x is a root (as far as this thread knows): hook it
+                const int old = atomicCAS(parent + rx[k], rx[k], py[k]);
+                if (old == rx[k]) live[k] = false;
+                else px[k] = old;                              // it was not (any more): its true parent
+            } else {                                           // splice x onto y's parent, climb
+                const int z = px[k];
+                atomicMin(parent + rx[k], py[k]);
+                rx[k] = z;
+                px[k] = load(z, base[k]);
             }
         }
         if (!any) break;
-#pragma unroll
-        for (int k = 0; k < 2 * UF_K; k++) {
-            if (par[k] != cur[k]) {
-                if (par[k] == base[k >> 1]) {          // reached the network's first stick: a root
-                    cur[k] = par[k];
-                } else {
-                    if (gp[k] != par[k]) parent[cur[k]] = gp[k];
-                    cur[k] = par[k];
-                    par[k] = gp[k];
-                }
-            }
-        }
-    }
-#pragma unroll
-    for (int k = 0; k < 2 * UF_K; k++)
-        if (par[k] != cur[k]) cur[k] = par[k];          // stopped at s0
-    // hook the larger root under the smaller; a lost race is replayed from the current roots
-#pragma unroll
-    for (int k = 0; k < UF_K; k++) {
-        if (!live[k]) continue;
-        int a = cur[2 * k], c = cur[2 * k + 1];
-        const int s0 = base[k];
-        while (a != c) {
-            const int hi = a > c ? a : c, lo = a > c ? c : a;
-            const int old = atomicCAS(parent + hi, hi, lo);
-            if (old == hi) break;
-            a = uf_find(parent, old, s0);  // hi is not a root (any more): its true parent comes back from the CAS; the
-            c = uf_find(parent, lo, s0);   // volatile chases from there see L2
-        }
     }
 }
 
