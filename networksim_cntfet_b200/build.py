@@ -24,6 +24,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE
 PER_FILE = {"junctions.cu": ["-fmad=false"]}
 if os.environ.get("CNT_TILE_FLAGS"):          # A/B of the tile kernel's shape: e.g. "-DCNT_TILE_CT=256 -DCNT_TILE_Q=1024"
     PER_FILE["junctions.cu"] = PER_FILE["junctions.cu"] + os.environ["CNT_TILE_FLAGS"].split()
+if os.environ.get("CNT_UF_K"):                # A/B: junctions per thread of the union pass
+    PER_FILE["clusters.cu"] = ["-DCNT_UF_K=" + os.environ["CNT_UF_K"]]
 if os.environ.get("CNT_CLUSTER_THREADS"):
     PER_FILE["pcg_cluster.cu"] = ["-DCNT_CLUSTER_THREADS=" + os.environ["CNT_CLUSTER_THREADS"]]
 

@@ -56,7 +56,10 @@ __global__ void k_uf_init(int64_t S, int32_t *__restrict__ parent, int32_t *__re
 // stays its minimum stick id == the canonical label).  Loads go through L1: a stale parent is still an ancestor, a
 // stale "root" fails its CAS and continues from the parent the CAS returns.  The network's first stick is the smallest
 // id of the network, hence always a root: it is recognised without loading its (hot) line.
-constexpr int UF_K = 4;
+#ifndef CNT_UF_K
+#define CNT_UF_K 4
+#endif
+constexpr int UF_K = CNT_UF_K;
 __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ joff,
                                                   int64_t J, const int32_t *__restrict__ stick1,
                                                   const int32_t *__restrict__ stick2, int32_t *parent,
