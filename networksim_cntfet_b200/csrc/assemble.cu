@@ -222,7 +222,7 @@ __device__ __forceinline__ uint32_t spread16(uint32_t v) {
     return v;
 }
 __global__ void k_morton_keys(int64_t S, const int32_t *__restrict__ urow, const double *__restrict__ xc,
-                              const double *__restrict__ yc, unsigned long long *__restrict__ key,
+                              const double *__restrict__ yc, uint32_t *__restrict__ key,
                               uint32_t *__restrict__ val) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
@@ -233,7 +233,7 @@ __global__ void k_morton_keys(int64_t S, const int32_t *__restrict__ urow, const
     uint32_t iy = y < 0 ? 0u : (y >= 65535.0 ? 65535u : (uint32_t)y);
     if (!(x == x)) ix = 0;
     if (!(y == y)) iy = 0;
-    key[r] = (unsigned long long)(spread16(ix) | (spread16(iy) << 1));
+    key[r] = spread16(ix) | (spread16(iy) << 1);
     val[r] = (uint32_t)s;
 }
 __global__ void k_apply_order(int64_t R, const uint32_t *__restrict__ order, int32_t *__restrict__ urow) {
@@ -259,7 +259,7 @@ extern "C" int cnt_assemble_reorder(int B, const int32_t *h_roff, int64_t S, int
     if (R == 0) return CNT_OK;
     CNT_CHECK_ARG(xc && yc);
     cnt::Workspace w(ws, ws_bytes);
-    unsigned long long *keyA = w.take<unsigned long long>(R), *keyB = w.take<unsigned long long>(R);
+    uint32_t *keyA = (uint32_t *)w.take<unsigned long long>(R), *keyB = (uint32_t *)w.take<unsigned long long>(R);   // 32-bit keys
     uint32_t *valA = w.take<uint32_t>(R), *valB = w.take<uint32_t>(R);
     int64_t sb = cnt::segsort_workspace_bytes(R, B);
     void *sws = w.take<char>(sb);
@@ -269,9 +269,8 @@ extern "C" int cnt_assemble_reorder(int B, const int32_t *h_roff, int64_t S, int
     }
     k_morton_keys<<<cnt::grid_for(S, 256), 256, 0, st>>>(S, urow, xc, yc, keyA, valA);
     CNT_LAUNCHED();
-    unsigned long long *ks;
-    uint32_t *order;
-    int rc = cnt::segsort_pairs(B, h_roff, keyA, valA, keyB, valB, 4, sws, sb, st, &ks, &order);
+    uint32_t *ks, *order;
+    int rc = cnt::segsort_pairs32(B, h_roff, keyA, valA, keyB, valB, 4, sws, sb, st, &ks, &order);
     if (rc) return rc;
     k_apply_order<<<cnt::grid_for(R, 256), 256, 0, st>>>(R, order, urow);
     CNT_LAUNCHED();

@@ -8,7 +8,7 @@
 
 namespace {
 
-// path halving; plain loads/stores are safe: parents only ever decrease towards the root.  `s0` is the first
+// Parents only ever decrease towards the root.  `s0` is the first
 // stick of x's network: the smallest id of the network, hence ALWAYS a root -- it is recognised without
 // loading parent[s0].  In a percolating network s0 (the source electrode) is the root of the giant component,
 // i.e. the end of almost every chase: that one cache line was read ~130k times per network through L2
@@ -24,17 +24,17 @@ __device__ __forceinline__ int ld_ca(const int *p) {
     return v;
 }
 
+// root of x after the union pass (k_uf_flatten).  The loads go through L1 here too: the sticks just below the roots are
+// on the path of thousands of chases, and as volatile loads they were served one at a time by their L2 slice.  The
+// only writes of the pass are shortcuts to the root (still ancestors), so a stale line costs hops, not correctness.
 __device__ __forceinline__ int uf_find(int *parent, int x, int s0) {
     if (x == s0) return x;
-    int p = ((volatile int *)parent)[x];
-    while (p != x) {
-        if (p == s0) return p;
-        int gp = ((volatile int *)parent)[p];
-        if (gp != p) ((volatile int *)parent)[x] = gp;
+    int p = ld_ca(parent + x);
+    while (p != x && p != s0) {
         x = p;
-        p = gp;
+        p = ld_ca(parent + x);
     }
-    return x;
+    return p;
 }
 
 __global__ void k_uf_init(int64_t S, int32_t *__restrict__ parent, int32_t *__restrict__ size,
@@ -120,18 +120,36 @@ __global__ void __launch_bounds__(256) k_uf_union(int B, const int32_t *__restri
     }
 }
 
-__global__ void k_uf_flatten(int B, const int32_t *__restrict__ soff, int64_t S, int32_t *parent,
-                             int32_t *__restrict__ label, int32_t *__restrict__ size) {
-    int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// One atomic per WARP on the size of the giant component (the root of almost every stick of a percolating network)
+// serialised the pass on a few hundred addresses (ncu: 3.1 ms for 22M sticks at 106 GB/s of DRAM traffic): the sticks
+// whose root is the first stick of the CTA's first network -- nearly all of them -- are counted in shared memory and
+// reach the size table with ONE atomic per CTA.
+constexpr int FLAT_T = 1024;
+__global__ void __launch_bounds__(FLAT_T) k_uf_flatten(int B, const int32_t *__restrict__ soff, int64_t S, int32_t *parent,
+                                                      int32_t *__restrict__ label, int32_t *__restrict__ size) {
+    __shared__ int s_hot, s_cnt;
+    const int64_t s = (int64_t)blockIdx.x * FLAT_T + threadIdx.x;
+    if (threadIdx.x == 0) {
+        s_hot = soff[cnt::find_segment(soff, B, (int)((int64_t)blockIdx.x * FLAT_T))];
+        s_cnt = 0;
+    }
+    __syncthreads();
+    const int hot = s_hot;
     int r = -1;
     if (s < S) {
         int b = cnt::find_segment(soff, B, (int)s);
         r = uf_find(parent, (int)s, soff[b]);
+        parent[s] = r;                                  // shortcut for the chases that pass through s
         label[s] = r - soff[b];
     }
-    // component sizes: one atomic per group of equal roots inside the warp (the big component is most of a network)
+    // component sizes: one atomic per group of equal roots inside the warp
     const unsigned same = __match_any_sync(0xffffffffu, r);
-    if (r >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) atomicAdd(size + r, __popc(same));
+    if (r >= 0 && (threadIdx.x & 31) == __ffs(same) - 1) {
+        if (r == hot) atomicAdd(&s_cnt, __popc(same));
+        else atomicAdd(size + r, __popc(same));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(size + hot, s_cnt);
 }
 
 // per-network statistics, pass 1 over the sticks: components, multi-stick components, largest, first stick with a junction.
@@ -200,8 +218,16 @@ __global__ void k_stats_second(int B, const int32_t *__restrict__ soff, const in
                                int64_t J, const int32_t *__restrict__ stick1, const int32_t *__restrict__ label,
                                const uint8_t *__restrict__ hasj, const int32_t *__restrict__ orig,
                                int32_t *__restrict__ acc) {
+    __shared__ int s_hot, s_cnt;
     int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {           // the key most threads of the CTA will add to
+        const int64_t t0 = (int64_t)blockIdx.x * blockDim.x;
+        s_hot = t0 < S ? cnt::find_segment(soff, B, (int)t0) * 8 + 4
+                       : (t0 - S < J ? cnt::find_segment(joff, B, (int)(t0 - S)) * 8 + 5 : -2);
+        s_cnt = 0;
+    }
+    __syncthreads();
     int b = -1, slot = 4;
     if (t < S) {
         // reference quirk: sticks with a junction carry the component ordinal 0..K-1 (K = components
@@ -218,8 +244,16 @@ __global__ void k_stats_second(int B, const int32_t *__restrict__ soff, const in
         if (perc && label[s0 + stick1[e]] == 0) b = bb;
         slot = 5;
     }
-    const unsigned same = __match_any_sync(0xffffffffu, b * 8 + slot);
-    if (b >= 0 && lane == __ffs(same) - 1) atomicAdd(acc + (int64_t)b * 8 + slot, __popc(same));
+    // the junctions of a CTA belong to one or two networks: their counts meet in shared memory first (one global atomic per
+    // CTA and network instead of one per warp on the same few addresses)
+    const int key = b >= 0 ? b * 8 + slot : -1;
+    const unsigned same = __match_any_sync(0xffffffffu, key);
+    if (key >= 0 && lane == __ffs(same) - 1) {
+        if (key == s_hot) atomicAdd(&s_cnt, __popc(same));
+        else atomicAdd(acc + key, __popc(same));
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && s_cnt) atomicAdd(acc + s_hot, s_cnt);
 }
 __global__ void k_stats_finish(int B, const int32_t *__restrict__ soff, const int32_t *__restrict__ label,
                                const int32_t *__restrict__ size, const int32_t *__restrict__ orig,
@@ -274,7 +308,7 @@ extern "C" int cnt_label_clusters(int B, const int32_t *soff, const int32_t *jof
         CNT_LAUNCHED();
     }
     if (S > 0) {
-        k_uf_flatten<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, parent, label, size);
+        k_uf_flatten<<<cnt::grid_for(S, FLAT_T), FLAT_T, 0, st>>>(B, soff, S, parent, label, size);
         CNT_LAUNCHED();
     }
     k_stats_init<<<cnt::grid_for(8 * (int64_t)B, 256), 256, 0, st>>>(B, acc);

@@ -45,6 +45,8 @@ int64_t segsort_workspace_bytes(int64_t n, int nseg);
 int segsort_pairs(int nseg, const int32_t *h_off, unsigned long long *keyA, uint32_t *valA, unsigned long long *keyB,
                   uint32_t *valB, int npasses, void *ws, int64_t ws_bytes, cudaStream_t st,
                   unsigned long long **key_out, uint32_t **val_out);
+int segsort_pairs32(int nseg, const int32_t *h_off, uint32_t *keyA, uint32_t *valA, uint32_t *keyB, uint32_t *valB, int npasses,
+                    void *ws, int64_t ws_bytes, cudaStream_t st, uint32_t **key_out, uint32_t **val_out);
 
 static inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 static inline unsigned grid_for(int64_t n, int block) { return (unsigned)((n + block - 1) / block); }

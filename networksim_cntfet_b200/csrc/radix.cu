@@ -1,4 +1,4 @@
-// Segmented stable LSD radix sort of (u64 key, u32 value) pairs, 8-bit digits.
+// Segmented stable LSD radix sort of (u64 or u32 key, u32 value) pairs, 8-bit digits.
 // Used for the reference's length sort (netsim.py:133) and for the spatial (Morton) ordering
 // of the unknowns of the MNA system.
 //
@@ -20,8 +20,9 @@ struct SortTile {
     int32_t stride;    // tiles in this segment (distance between consecutive digits)
 };
 
+template <class K>
 __global__ void __launch_bounds__(RS_T) k_rs_hist(const SortTile *__restrict__ tiles,
-                                                   const unsigned long long *__restrict__ key, int shift,
+                                                   const K *__restrict__ key, int shift,
                                                    int32_t *__restrict__ hist) {
     __shared__ int h[256];
     SortTile t = tiles[blockIdx.x];
@@ -32,10 +33,11 @@ __global__ void __launch_bounds__(RS_T) k_rs_hist(const SortTile *__restrict__ t
     hist[t.hist0 + threadIdx.x * t.stride] = h[threadIdx.x];
 }
 
+template <class K>
 __global__ void __launch_bounds__(RS_T) k_rs_scatter(const SortTile *__restrict__ tiles,
-                                                      const unsigned long long *__restrict__ key_in,
+                                                      const K *__restrict__ key_in,
                                                       const uint32_t *__restrict__ val_in,
-                                                      unsigned long long *__restrict__ key_out,
+                                                      K *__restrict__ key_out,
                                                       uint32_t *__restrict__ val_out, int shift,
                                                       const int32_t *__restrict__ hist_scan) {
     __shared__ int base[256];
@@ -49,7 +51,7 @@ __global__ void __launch_bounds__(RS_T) k_rs_scatter(const SortTile *__restrict_
     for (int r0 = 0; r0 < t.count; r0 += RS_T) {
         int k = r0 + threadIdx.x;
         bool valid = k < t.count;
-        unsigned long long kk = 0;
+        K kk = 0;
         uint32_t vv = 0;
         int d = 256 + lane;                         // invalid lanes: unique pseudo-digit
         if (valid) {
@@ -80,6 +82,10 @@ __global__ void __launch_bounds__(RS_T) k_rs_scatter(const SortTile *__restrict_
 }
 
 static int64_t max_tiles(int64_t n, int nseg) { return n / RS_TILE + nseg + 1; }
+
+template <class K>
+int segsort_pairs_t(int nseg, const int32_t *h_off, K *keyA, uint32_t *valA, K *keyB, uint32_t *valB, int npasses, void *ws,
+                    int64_t ws_bytes, cudaStream_t st, K **key_out, uint32_t **val_out);
 }  // namespace
 
 namespace cnt {
@@ -91,6 +97,19 @@ int64_t segsort_workspace_bytes(int64_t n, int nseg) {
 int segsort_pairs(int nseg, const int32_t *h_off, unsigned long long *keyA, uint32_t *valA, unsigned long long *keyB,
                   uint32_t *valB, int npasses, void *ws, int64_t ws_bytes, cudaStream_t st,
                   unsigned long long **key_out, uint32_t **val_out) {
+    return segsort_pairs_t<unsigned long long>(nseg, h_off, keyA, valA, keyB, valB, npasses, ws, ws_bytes, st, key_out, val_out);
+}
+// the same with 32-bit keys (8 instead of 12 bytes moved per element and pass)
+int segsort_pairs32(int nseg, const int32_t *h_off, uint32_t *keyA, uint32_t *valA, uint32_t *keyB, uint32_t *valB, int npasses,
+                    void *ws, int64_t ws_bytes, cudaStream_t st, uint32_t **key_out, uint32_t **val_out) {
+    return segsort_pairs_t<uint32_t>(nseg, h_off, keyA, valA, keyB, valB, npasses, ws, ws_bytes, st, key_out, val_out);
+}
+}  // namespace cnt
+
+namespace {
+template <class K>
+int segsort_pairs_t(int nseg, const int32_t *h_off, K *keyA, uint32_t *valA, K *keyB, uint32_t *valB, int npasses, void *ws,
+                    int64_t ws_bytes, cudaStream_t st, K **key_out, uint32_t **val_out) {
     std::vector<SortTile> tiles;
     int64_t tile_base = 0;
     for (int b = 0; b < nseg; b++) {
@@ -111,29 +130,29 @@ int segsort_pairs(int nseg, const int32_t *h_off, unsigned long long *keyA, uint
     *key_out = keyA;
     *val_out = valA;
     if (nt == 0) return CNT_OK;
-    Workspace w(ws, ws_bytes);
+    cnt::Workspace w(ws, ws_bytes);
     SortTile *d_tiles = w.take<SortTile>(nt_alloc);
     int32_t *hist = w.take<int32_t>(nt_alloc * 256 + 1);
     int64_t sb = cnt_scan_workspace_bytes(nt_alloc * 256 + 1);
     void *sws = w.take<char>(sb);
     if (!sws) {
-        set_error("segsort workspace too small");
+        cnt::set_error("segsort workspace too small");
         return CNT_ECAPACITY;
     }
     CNT_CUDA(cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(SortTile) * nt, cudaMemcpyHostToDevice, st));
     for (int pass = 0; pass < npasses; pass++) {
         int shift = 8 * pass;
-        k_rs_hist<<<(unsigned)nt, RS_T, 0, st>>>(d_tiles, keyA, shift, hist);
+        k_rs_hist<K><<<(unsigned)nt, RS_T, 0, st>>>(d_tiles, keyA, shift, hist);
         CNT_LAUNCHED();
         int rc = cnt_exclusive_scan_i32(hist, hist, nhist, 0, sws, sb, (void *)st);
         if (rc) return rc;
-        k_rs_scatter<<<(unsigned)nt, RS_T, 0, st>>>(d_tiles, keyA, valA, keyB, valB, shift, hist);
+        k_rs_scatter<K><<<(unsigned)nt, RS_T, 0, st>>>(d_tiles, keyA, valA, keyB, valB, shift, hist);
         CNT_LAUNCHED();
-        unsigned long long *tk = keyA; keyA = keyB; keyB = tk;
+        K *tk = keyA; keyA = keyB; keyB = tk;
         uint32_t *tv = valA; valA = valB; valB = tv;
     }
     *key_out = keyA;
     *val_out = valA;
     return CNT_OK;
 }
-}  // namespace cnt
+}  // namespace

@@ -8,9 +8,12 @@
 // seed to every network too, measure_perc.py:226-233).  The stream is statistically, not
 // bitwise, the reference's (numpy MT19937); parity tests always feed reference sticks.
 //
-// Sort: segmented stable LSD radix sort (radix.cu), 8 passes over a 64-bit key.
+// Sort: segmented stable LSD radix sort (radix.cu).
 // Key: source electrode 0, drain electrode 1, body sticks ~bits(length) (longer first);
-// stability keeps generation order among equal lengths.
+// stability keeps generation order among equal lengths.  Random lengths: 4 passes over the UPPER 32 bits of the key
+// (8 bytes moved per stick and pass), then k_tie_fix orders the few runs of sticks that share those 32 bits (sign,
+// exponent, 20 bits of mantissa: ~1e3 pairs per 100k sticks) by the lower 32 bits -- the same permutation as 8 passes
+// over the 64-bit key (12 bytes per stick and pass), which constant lengths (one long run) still take.
 #include <math.h>
 #include "common.cuh"
 
@@ -45,7 +48,7 @@ __global__ void k_generate(const unsigned long long *__restrict__ seeds, int B, 
                            const double *__restrict__ scaling, double pm, int len_mode, double len_const,
                            double *__restrict__ xc, double *__restrict__ yc, double *__restrict__ ang,
                            double *__restrict__ len, uint8_t *__restrict__ kind, unsigned long long *__restrict__ key,
-                           uint32_t *__restrict__ val) {
+                           uint32_t *__restrict__ key32, uint32_t *__restrict__ val) {
     int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= S) return;
     int b = cnt::find_segment(soff, B, (int)s);
@@ -57,7 +60,9 @@ __global__ void k_generate(const unsigned long long *__restrict__ seeds, int B, 
         ang[s] = M_PI / 2 - 1e-6;
         len[s] = 100.0;
         kind[s] = 0;
-        key[s] = (i == 0 && n > 1) || n == 1 ? 0ull : 1ull;
+        const unsigned long long ek = (i == 0 && n > 1) || n == 1 ? 0ull : 1ull;
+        if (key32) key32[s] = (uint32_t)ek;          // below every body stick: the upper word of ~bits(l > 0) is >= 0x800fffff
+        else key[s] = ek;
         return;
     }
     unsigned long long seed = seeds[b];
@@ -81,7 +86,34 @@ __global__ void k_generate(const unsigned long long *__restrict__ seeds, int B, 
         l = len_const / scaling[b];                    // netsim.py:111
     }
     len[s] = l;
-    key[s] = ~(unsigned long long)__double_as_longlong(l);
+    const unsigned long long k = ~(unsigned long long)__double_as_longlong(l);
+    if (key32) key32[s] = (uint32_t)(k >> 32);
+    else key[s] = k;
+}
+
+// after the sort by the upper key word: runs of equal words ordered by the lower word (stable insertion sort by the
+// thread at the head of the run; runs are pairs or triples).  Electrodes (keys 0 and 1) are runs of one.
+__global__ void k_tie_fix(int B, const int32_t *__restrict__ soff, int64_t S, const uint32_t *__restrict__ key32,
+                          uint32_t *__restrict__ perm, const double *__restrict__ ulen) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S || s + 1 >= S) return;
+    const uint32_t k = key32[s];
+    if (key32[s + 1] != k || k <= 1u) return;
+    const int b = cnt::find_segment(soff, B, (int)s);
+    const int64_t lo = soff[b], hi = soff[b + 1];
+    if (s > lo && key32[s - 1] == k) return;                       // not the head of its run
+    int64_t e = s + 1;
+    while (e < hi && key32[e] == k) e++;
+    auto low = [&](uint32_t p) { return ~(uint32_t)(unsigned long long)__double_as_longlong(ulen[p]); };
+    for (int64_t a = s + 1; a < e; a++) {
+        const uint32_t pa = perm[a], ka = low(pa);
+        int64_t c = a - 1;
+        while (c >= s && low(perm[c]) > ka) {
+            perm[c + 1] = perm[c];
+            c--;
+        }
+        perm[c + 1] = pa;
+    }
 }
 
 // final gather into sorted order + end points (netsim.py:97-103)
@@ -138,12 +170,21 @@ extern "C" int cnt_gen_sticks(const uint64_t *seeds, int B, const int32_t *soff,
         return CNT_ECAPACITY;
     }
     k_generate<<<cnt::grid_for(S, 256), 256, 0, st>>>((const unsigned long long *)seeds, B, soff, S, scaling, pm,
-                                                      len_mode, len_const, uxc, uyc, uang, ulen, ukind, keyA, valA);
+                                                      len_mode, len_const, uxc, uyc, uang, ulen, ukind, keyA,
+                                                      len_mode == 0 ? (uint32_t *)keyA : nullptr, valA);
     CNT_LAUNCHED();
-    unsigned long long *ks;
     uint32_t *perm;
-    int rc = cnt::segsort_pairs(B, h_soff, keyA, valA, keyB, valB, 8, sws, sb, st, &ks, &perm);
-    if (rc) return rc;
+    if (len_mode == 0) {
+        uint32_t *ks;
+        int rc = cnt::segsort_pairs32(B, h_soff, (uint32_t *)keyA, valA, (uint32_t *)keyB, valB, 4, sws, sb, st, &ks, &perm);
+        if (rc) return rc;
+        k_tie_fix<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, ks, perm, ulen);
+        CNT_LAUNCHED();
+    } else {
+        unsigned long long *ks;
+        int rc = cnt::segsort_pairs(B, h_soff, keyA, valA, keyB, valB, 8, sws, sb, st, &ks, &perm);
+        if (rc) return rc;
+    }
     k_gather<<<cnt::grid_for(S, 256), 256, 0, st>>>(B, soff, S, perm, uxc, uyc, uang, ulen, ukind, xc, yc, angle, length,
                                                     kind, xa, ya, xb, yb, orig);
     CNT_LAUNCHED();
