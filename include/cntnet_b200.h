@@ -422,8 +422,10 @@ int cnt_spmv_csr(int NS, int64_t n_rows, int64_t nnz, const int32_t *rowptr, con
  *        PIV[nelim] eliminated row by pivot index m (rounds back to back, rows ascending inside a round)
  *        NPTR[nelim+1], NBR[nlist], ESLOT[nlist]: neighbours of pivot m (ascending) and the edge slots to them
  *        TGT[nge], CPTR[nge+1], CM/CA/CB[ncontrib]: edge slot receiving the contributions
- *            g[CA] g[CB] / d[CM], contributions of a target ordered by pivot
- *        TN[ngn], TPTR[ngn+1], TM/TSLOT[nlist]: row receiving g[TSLOT] {c,b}[PIV[TM]] / d[TM], ordered by pivot
+ *            gl[CA] gl[CB] / d[CM], contributions of a target ordered by pivot.  CA, CB (and TSLOT) name a
+ *            dead edge by its POSITION in NBR/ESLOT: gl[k] = g[ESLOT[k]] is final once its pivot is
+ *            eliminated, and the numeric phase keeps it in list order (sequential reads instead of gathers)
+ *        TN[ngn], TPTR[ngn+1], TM/TSLOT[nlist]: row receiving gl[TSLOT] {c,b}[PIV[TM]] / d[TM], ordered by pivot
  *        E0PTR[nE0+1], E0SRC: round-0 edge e = sum of the CSR entries E0SRC[E0PTR[e] .. E0PTR[e+1])
  *        DPTR[B+1], DNODES: rows left to the dense tail per network (ascending); DSLOT/DEPOS[dense_nE]:
  *            remaining edge slots and their position in the pool of dense matrices, grouped by network

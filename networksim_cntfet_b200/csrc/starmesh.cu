@@ -44,7 +44,7 @@ __global__ void k_sm_coupling(int NS, int R, const int32_t *__restrict__ rowptr,
                               int64_t val_stride, const int32_t *__restrict__ src_eid,
                               const int32_t *__restrict__ drn_eid, const double *__restrict__ gj, int64_t g_stride,
                               const double *__restrict__ extra, const double *__restrict__ rhs, int64_t rhs_stride,
-                              int leak, double *__restrict__ c, double *__restrict__ b) {
+                              int leak, double2 *__restrict__ cb) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)R * NS) return;
     const int r = (int)(t / NS), q = (int)(t - (int64_t)r * NS);
@@ -67,14 +67,18 @@ __global__ void k_sm_coupling(int NS, int R, const int32_t *__restrict__ rowptr,
         out = __dsub_rn(out, err);        // exact sum = sum + err  ->  fl - exact = -err
     }
     if (extra) out += extra[(int64_t)q * R + r];
-    c[t] = out;
-    b[t] = rhs[(int64_t)q * rhs_stride + r];
+    cb[t] = make_double2(out, rhs[(int64_t)q * rhs_stride + r]);
 }
 
 struct Num {
     int R, NS;
     const int32_t *piv, *nptr, *nbr, *eslot, *tgt, *cptr, *cm, *ca, *cb, *tn, *tptr, *tm, *tslot;
-    double *g, *c, *b, *x, *dinv;
+    double *g, *x, *dinv;
+    double2 *nv;           // [R, NS] (c, b) of every unknown side by side: the node updates touch both, and DRAM moves 64 bytes
+                           // per access -- with separate arrays every 32-byte gather paid for a line and used half of it
+    double *gl;            // [nlist, NS] values of the dead edges in the order of the incident lists: final once their
+                           // pivot is eliminated, copied by k_sm_pivot, so that the contributions of a round (ca, cb, tslot
+                           // = list positions) and the back-substitution read them in order instead of gathering g[slot]
     double *xout;          // [NS, R] configuration-major copy of the solution for the caller
 };
 
@@ -83,18 +87,22 @@ __global__ void k_sm_pivot(Num a, int ebase, int nelim) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= (int64_t)nelim * a.NS) return;
     const int ml = (int)(t / a.NS), q = (int)(t - (int64_t)ml * a.NS), m = ebase + ml, NS = a.NS;
-    double d = a.c[(int64_t)a.piv[m] * NS + q];
-    for (int k = a.nptr[m]; k < a.nptr[m + 1]; k++) d += a.g[(int64_t)a.eslot[k] * NS + q];
+    double d = a.nv[(int64_t)a.piv[m] * NS + q].x;
+    for (int k = a.nptr[m]; k < a.nptr[m + 1]; k++) {
+        const double v = a.g[(int64_t)a.eslot[k] * NS + q];
+        a.gl[(int64_t)k * NS + q] = v;
+        d += v;
+    }
     a.dinv[(int64_t)m * NS + q] = 1.0 / d;
 }
-// targets of a round: first the edge groups (g[tgt] += sum g[ca] g[cb] / d[cm]), then the node groups
-// (c, b of a neighbour += sum g[tslot] / d[tm] * {c, b}[piv[tm]]); contributions ordered by pivot
+// targets of a round: first the edge groups (g[tgt] += sum gl[ca] gl[cb] / d[cm]), then the node groups
+// (c, b of a neighbour += sum gl[tslot] / d[tm] * {c, b}[piv[tm]]); contributions ordered by pivot
 __global__ void k_sm_update(Num a, int gebase, int nge, int gnbase, int ngn) {
     const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int NS = a.NS;
     if (t >= (int64_t)(nge + ngn) * NS) return;
     const int it = (int)(t / NS), q = (int)(t - (int64_t)it * NS);
-    const double *g = a.g;
+    const double *g = a.gl;
     if (it < nge) {
         const int gi = gebase + it;
         double v = 0.0;
@@ -108,12 +116,15 @@ __global__ void k_sm_update(Num a, int gebase, int nge, int gnbase, int ngn) {
             const int m = a.tm[k];
             const double w = g[(int64_t)a.tslot[k] * NS + q] * a.dinv[(int64_t)m * NS + q];
             const int64_t v = (int64_t)a.piv[m] * NS + q;
-            sc += w * a.c[v];
-            sb += w * a.b[v];
+            const double2 cbv = a.nv[v];
+            sc += w * cbv.x;
+            sb += w * cbv.y;
         }
         const int64_t u = (int64_t)a.tn[gi] * NS + q;
-        a.c[u] += sc;
-        a.b[u] += sb;
+        double2 t2 = a.nv[u];
+        t2.x += sc;
+        t2.y += sb;
+        a.nv[u] = t2;
     }
 }
 __global__ void k_sm_back(Num a, int ebase, int nelim) {
@@ -121,8 +132,8 @@ __global__ void k_sm_back(Num a, int ebase, int nelim) {
     if (t >= (int64_t)nelim * a.NS) return;
     const int ml = (int)(t / a.NS), q = (int)(t - (int64_t)ml * a.NS), m = ebase + ml, NS = a.NS;
     const int v = a.piv[m];
-    double s = a.b[(int64_t)v * NS + q];
-    for (int k = a.nptr[m]; k < a.nptr[m + 1]; k++) s += a.g[(int64_t)a.eslot[k] * NS + q] * a.x[(int64_t)a.nbr[k] * NS + q];
+    double s = a.nv[(int64_t)v * NS + q].y;
+    for (int k = a.nptr[m]; k < a.nptr[m + 1]; k++) s += a.gl[(int64_t)k * NS + q] * a.x[(int64_t)a.nbr[k] * NS + q];
     s *= a.dinv[(int64_t)m * NS + q];
     a.x[(int64_t)v * NS + q] = s;
     a.xout[(int64_t)q * a.R + v] = s;
@@ -146,8 +157,8 @@ __global__ void k_sm_dense_fill(int NS, int nE, const int32_t *__restrict__ dslo
 }
 __global__ void __launch_bounds__(DENSE_TB) k_sm_dense(int NS, int R, const long long *__restrict__ doff,
                                                        const int32_t *__restrict__ dptr, const int32_t *__restrict__ dnodes,
-                                                       double *__restrict__ Gall, int64_t gpool, const double *__restrict__ c_in,
-                                                       const double *__restrict__ b_in, double *__restrict__ x_int,
+                                                       double *__restrict__ Gall, int64_t gpool, const double2 *__restrict__ cb_in,
+                                                       double *__restrict__ x_int,
                                                        double *__restrict__ x_out, int nmax) {
     extern __shared__ double smd[];
     double *rowk = smd, *cc = smd + nmax, *bb = smd + 2 * nmax, *dinv = smd + 3 * nmax, *red = smd + 4 * nmax;
@@ -158,8 +169,9 @@ __global__ void __launch_bounds__(DENSE_TB) k_sm_dense(int NS, int R, const long
     double *G = Gall + (int64_t)q * gpool + doff[net];
     const int t = threadIdx.x, lane = t & 31, w = t >> 5, nw = DENSE_TB >> 5;
     for (int i = t; i < n; i += DENSE_TB) {
-        cc[i] = c_in[(int64_t)nodes[i] * NS + q];
-        bb[i] = b_in[(int64_t)nodes[i] * NS + q];
+        const double2 cbv = cb_in[(int64_t)nodes[i] * NS + q];
+        cc[i] = cbv.x;
+        bb[i] = cbv.y;
     }
     __syncthreads();
     for (int k = 0; k < n; k++) {
@@ -214,8 +226,8 @@ __global__ void __launch_bounds__(DENSE_TB) k_sm_dense_smem(int NS, int R, int n
                                                             const int32_t *__restrict__ dptr,
                                                             const int32_t *__restrict__ dnodes,
                                                             const int32_t *__restrict__ dedge /* [nnet+1] */,
-                                                            const double *__restrict__ g, const double *__restrict__ c_in,
-                                                            const double *__restrict__ b_in, double *__restrict__ x_int,
+                                                            const double *__restrict__ g, const double2 *__restrict__ cb_in,
+                                                            double *__restrict__ x_int,
                                                             double *__restrict__ x_out) {
     extern __shared__ double smd[];
     const int net = blockIdx.x, q = blockIdx.y;
@@ -227,8 +239,9 @@ __global__ void __launch_bounds__(DENSE_TB) k_sm_dense_smem(int NS, int R, int n
     const int ntri = n * (n - 1) / 2;
     for (int i = t; i < ntri; i += DENSE_TB) T[i] = 0.0;
     for (int i = t; i < n; i += DENSE_TB) {
-        cc[i] = c_in[(int64_t)nodes[i] * NS + q];
-        bb[i] = b_in[(int64_t)nodes[i] * NS + q];
+        const double2 cbv = cb_in[(int64_t)nodes[i] * NS + q];
+        cc[i] = cbv.x;
+        bb[i] = cbv.y;
     }
     __syncthreads();
     const long long base = doff[net];
@@ -277,7 +290,7 @@ __global__ void __launch_bounds__(DENSE_TB) k_sm_dense_smem(int NS, int R, int n
 }
 
 struct NumWs {
-    int64_t g, c, b, dinv, x, G, total;
+    int64_t g, gl, cb, dinv, x, G, total;
 };
 bool dense_in_smem(const cnt_sm_info *h) { return h->dense_nmax <= DENSE_SMEM_N; }
 NumWs num_layout(int NS, const cnt_sm_info *h) {
@@ -289,8 +302,8 @@ NumWs num_layout(int NS, const cnt_sm_info *h) {
         return at;
     };
     L.g = take((int64_t)NS * (h->nslots > 0 ? h->nslots : 1));
-    L.c = take((int64_t)NS * h->R);
-    L.b = take((int64_t)NS * h->R);
+    L.gl = take((int64_t)NS * (h->nlist > 0 ? h->nlist : 1));
+    L.cb = take(2 * (int64_t)NS * h->R);
     L.dinv = take((int64_t)NS * h->R);
     L.x = take((int64_t)NS * h->R);
     L.G = take(dense_in_smem(h) ? 1 : (int64_t)NS * (h->dense_gpool > 0 ? h->dense_gpool : 1));
@@ -328,8 +341,9 @@ extern "C" int cnt_sm_solve(int NS, int B, int64_t R, int64_t NNZ, const cnt_sm_
     a.NS = NS;
     a.piv = p.piv; a.nptr = p.nptr; a.nbr = p.nbr; a.eslot = p.eslot; a.tgt = p.tgt; a.cptr = p.cptr; a.cm = p.cm;
     a.ca = p.ca; a.cb = p.cb; a.tn = p.tn; a.tptr = p.tptr; a.tm = p.tm; a.tslot = p.tslot;
-    a.g = (double *)(w + L.g); a.c = (double *)(w + L.c); a.b = (double *)(w + L.b); a.x = (double *)(w + L.x);
+    a.g = (double *)(w + L.g); a.nv = (double2 *)(w + L.cb); a.x = (double *)(w + L.x);
     a.dinv = (double *)(w + L.dinv);
+    a.gl = (double *)(w + L.gl);
     a.xout = x;
     double *G = (double *)(w + L.G);
     auto grid = [&](int64_t items) { return cnt::grid_for(items * NS, TB); };
@@ -339,7 +353,7 @@ extern "C" int cnt_sm_solve(int NS, int B, int64_t R, int64_t NNZ, const cnt_sm_
         CNT_LAUNCHED();
     }
     k_sm_coupling<<<grid(R), TB, 0, st>>>(NS, (int)R, rowptr, val, val_stride, src_eid, drn_eid, gj, g_stride, coupling, rhs,
-                                          rhs_stride, leak, a.c, a.b);
+                                          rhs_stride, leak, a.nv);
     CNT_LAUNCHED();
     for (int k = 0; k < h->nrounds; k++) {
         const cnt_sm_round *r = &h->rounds[k];
@@ -356,7 +370,7 @@ extern "C" int cnt_sm_solve(int NS, int B, int64_t R, int64_t NNZ, const cnt_sm_
             const size_t smem = sizeof(double) * (4 * (size_t)n + 32 + (size_t)n * (n - 1) / 2);
             CNT_CUDA(cudaFuncSetAttribute(k_sm_dense_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             k_sm_dense_smem<<<dim3(h->dense_nnet, NS, 1), DENSE_TB, smem, st>>>(NS, (int)R, h->dense_nE, p.dslot, p.depos, p.doff,
-                                                                                p.dptr, p.dnodes, p.dedge, a.g, a.c, a.b, a.x,
+                                                                                p.dptr, p.dnodes, p.dedge, a.g, a.nv, a.x,
                                                                                 x);
             CNT_LAUNCHED();
         } else {
@@ -367,7 +381,7 @@ extern "C" int cnt_sm_solve(int NS, int B, int64_t R, int64_t NNZ, const cnt_sm_
             }
             size_t smem = sizeof(double) * (4 * (size_t)h->dense_nmax + 32);
             k_sm_dense<<<dim3(h->dense_nnet, NS, 1), DENSE_TB, smem, st>>>(NS, (int)R, p.doff, p.dptr, p.dnodes, G,
-                                                                           h->dense_gpool, a.c, a.b, a.x, x, h->dense_nmax);
+                                                                           h->dense_gpool, a.nv, a.x, x, h->dense_nmax);
             CNT_LAUNCHED();
         }
     }

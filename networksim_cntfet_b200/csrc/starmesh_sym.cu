@@ -653,8 +653,8 @@ __global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
             const int u = s.p.nbr[k0 + i], w = s.p.nbr[k0 + j];
             const int e = hash_find_or_insert(s, s.rnet[u], ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
             s.pent[t] = e;
-            s.pa[t] = s.p.eslot[k0 + i];
-            s.pb[t] = s.p.eslot[k0 + j];
+            s.pa[t] = k0 + i;                 // the two dead edges of the pair by their position in the incident list:
+            s.pb[t] = k0 + j;                 // the numeric phase keeps a copy of their values in list order (gl)
             s.pnext[t] = e >= 0 ? atomicExch(&s.htab[e].head, t) : -1;
         } else {
             const int o = s.p.nbr[lbase + (t - np)];
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
                 if (cnt == 1) {
                     const int kk = lbase + (t - np);
                     s.p.tm[off] = s.lm[kk];
-                    s.p.tslot[off] = s.p.eslot[kk];
+                    s.p.tslot[off] = kk;
                 } else {
                     int k = 0;
                     for (int x = s.ghead[t]; x >= 0; x = s.pnext[x]) {
@@ -799,7 +799,7 @@ __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
                     for (k = 0; k < cnt; k++) {
                         const int kk = lbase + (s.p.tm[off + k] - np);
                         s.p.tm[off + k] = s.lm[kk];
-                        s.p.tslot[off + k] = s.p.eslot[kk];
+                        s.p.tslot[off + k] = kk;
                     }
                 }
                 s.nhead[o] = -1;

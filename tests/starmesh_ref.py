@@ -88,9 +88,10 @@ def symbolic(roff, rowptr, col, dense_max=0):
                 inc[w].append((u, e))
             else:
                 newlive.append(e)
-        pairs = []       # (m, slot_i, slot_j, key)
+        pairs = []       # (m, list position of edge i, of edge j, key)
         for ml, v in enumerate(P):
             lst = sorted(inc[v])
+            k0 = len(nbr)
             piv.append(v)
             max_deg = max(max_deg, len(lst))
             for o, e in lst:
@@ -101,7 +102,7 @@ def symbolic(roff, rowptr, col, dense_max=0):
             nalive[rnet[v]] -= 1
             for i in range(len(lst)):
                 for j in range(i + 1, len(lst)):
-                    pairs.append((ebase + ml, lst[i][1], lst[j][1], (lst[i][0], lst[j][0])))
+                    pairs.append((ebase + ml, k0 + i, k0 + j, (lst[i][0], lst[j][0])))
         # edge-target groups in order of their first pair
         groups = {}
         for t, (m, sa, sb, key) in enumerate(pairs):
@@ -135,7 +136,7 @@ def symbolic(roff, rowptr, col, dense_max=0):
             tptr.append(len(tm))
             for k in members:
                 tm.append(int(lm[k - lbase]))
-                tslot.append(eslot[k])
+                tslot.append(k)
         rounds.append(dict(nelim=len(P), nlist=len(nbr) - lbase, npairs=len(pairs), nge=len(groups), ngn=len(ngroups),
                            nnew=nnew, ebase=ebase, lbase=lbase, cbase=cbase, gebase=gebase, gnbase=gnbase, sbase=sbase,
                            nlive=len(live), nnodes=len(nodes)))
@@ -190,23 +191,25 @@ def solve(plan, val, c, b):
     g = np.zeros((NS, max(plan.nslots, 1)))
     g[:, :plan.nE0] = _segsum(-val[:, plan.e0_src], plan.e0_ptr)
     dinv = np.zeros((NS, plan.R))
+    gl = np.zeros((NS, max(len(plan.nbr), 1)))
     for r in plan.rounds:
         ms = np.arange(r["ebase"], r["ebase"] + r["nelim"])
         ptr = plan.nptr[r["ebase"]:r["ebase"] + r["nelim"] + 1]
         ge = g[:, plan.eslot[ptr[0]:ptr[-1]]]
+        gl[:, ptr[0]:ptr[-1]] = ge                  # dead edges in list order: what ca / cb / tslot index
         d = c[:, plan.piv[ms]] + _segsum(ge, ptr - ptr[0])
         dinv[:, ms] = 1.0 / d
         if r["nge"]:
             gs = slice(r["gebase"], r["gebase"] + r["nge"])
             cp = plan.cptr[r["gebase"]:r["gebase"] + r["nge"] + 1]
             ks = slice(cp[0], cp[-1])
-            add = _segsum(g[:, plan.ca[ks]] * g[:, plan.cb[ks]] * dinv[:, plan.cm[ks]], cp - cp[0])
+            add = _segsum(gl[:, plan.ca[ks]] * gl[:, plan.cb[ks]] * dinv[:, plan.cm[ks]], cp - cp[0])
             g[:, plan.tgt[gs]] += add
         if r["ngn"]:
             gs = slice(r["gnbase"], r["gnbase"] + r["ngn"])
             tp = plan.tptr[r["gnbase"]:r["gnbase"] + r["ngn"] + 1]
             ks = slice(tp[0], tp[-1])
-            w = g[:, plan.tslot[ks]] * dinv[:, plan.tm[ks]]
+            w = gl[:, plan.tslot[ks]] * dinv[:, plan.tm[ks]]
             pv = plan.piv[plan.tm[ks]]
             c[:, plan.tn[gs]] += _segsum(w * c[:, pv], tp - tp[0])
             b[:, plan.tn[gs]] += _segsum(w * b[:, pv], tp - tp[0])
@@ -217,7 +220,7 @@ def solve(plan, val, c, b):
         ptr = plan.nptr[r["ebase"]:r["ebase"] + r["nelim"] + 1]
         ks = slice(ptr[0], ptr[-1])
         v = plan.piv[ms]
-        x[:, v] = (b[:, v] + _segsum(g[:, plan.eslot[ks]] * x[:, plan.nbr[ks]], ptr - ptr[0])) * dinv[:, ms]
+        x[:, v] = (b[:, v] + _segsum(gl[:, ks] * x[:, plan.nbr[ks]], ptr - ptr[0])) * dinv[:, ms]
     return x
 
 

@@ -186,8 +186,9 @@ def check_plan_invariants(plan, A, R, dense_max):
         fresh = tgt[tgt >= nslots]
         assert np.array_equal(fresh, nslots + np.arange(r["nnew"]))                  # fill slots numbered in group order
         inc = set(eslot.tolist())
+        pos = set(range(lo, hi))                     # ca / cb / tslot: positions in this round's incident lists
         ks = slice(cptr[0], cptr[-1])
-        assert set(plan.ca[ks].tolist()) <= inc and set(plan.cb[ks].tolist()) <= inc
+        assert set(plan.ca[ks].tolist()) <= pos and set(plan.cb[ks].tolist()) <= pos
         for k in range(r["nge"]):
             cm = plan.cm[cptr[k]:cptr[k + 1]]
             assert np.all(np.diff(cm) > 0) and cm.min() >= r["ebase"] and cm.max() < r["ebase"] + r["nelim"]
@@ -196,7 +197,7 @@ def check_plan_invariants(plan, A, R, dense_max):
         tptr = plan.tptr[r["gnbase"]:r["gnbase"] + r["ngn"] + 1]
         assert len(np.unique(tn)) == len(tn) and set(tn.tolist()) == set(nbr.tolist())
         assert tptr[0] == r["lbase"] and tptr[-1] == r["lbase"] + r["nlist"]
-        assert sorted(plan.tslot[lo:hi].tolist()) == sorted(eslot.tolist())
+        assert sorted(plan.tslot[lo:hi].tolist()) == list(range(lo, hi))
         for k in range(r["ngn"]):
             assert np.all(np.diff(plan.tm[tptr[k]:tptr[k + 1]]) > 0)
         # update the graph: star-mesh
