@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libcntnet_b200.so")
+# CNT_B200_LIB: another build of the same library (A/B measurements of kernel variants); never a fallback
+LIB_PATH = os.environ.get("CNT_B200_LIB") or os.path.join(HERE, "libcntnet_b200.so")
 
 CNT_NSTAT = 8
 STAT_PERCOLATING, STAT_NCLUST_TRUE, STAT_MAXCLUST_TRUE, STAT_NCLUST_REF, STAT_MAXCLUST_REF, STAT_NCOMP, STAT_ECOMP = range(7)

@@ -11,8 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJDIR = os.path.join(HERE, "_build")
-LIB = os.path.join(HERE, "libcntnet_b200.so")
+OBJDIR = os.environ.get("CNT_B200_OBJDIR") or os.path.join(HERE, "_build")     # variants for A/B runs: own object directory
+LIB = os.environ.get("CNT_B200_LIB") or os.path.join(HERE, "libcntnet_b200.so")   # ... and library name
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 
 SOURCES = ["util.cu", "radix.cu", "sticks.cu", "junctions.cu", "clusters.cu", "prune.cu", "assemble.cu", "aggregates.cu", "pcg.cu", "pcg_cluster.cu", "pcg_slab.cu", "spmv.cu", "starmesh.cu", "starmesh_sym.cu",
@@ -26,6 +26,8 @@ if os.environ.get("CNT_TILE_FLAGS"):          # A/B of the tile kernel's shape: 
     PER_FILE["junctions.cu"] = PER_FILE["junctions.cu"] + os.environ["CNT_TILE_FLAGS"].split()
 if os.environ.get("CNT_UF_K"):                # A/B: junctions per thread of the union pass
     PER_FILE["clusters.cu"] = ["-DCNT_UF_K=" + os.environ["CNT_UF_K"]]
+if os.environ.get("CNT_SM_LB"):               # A/B: look-back width of the chained scans
+    PER_FILE["starmesh_sym.cu"] = ["-DCNT_SM_LB=" + os.environ["CNT_SM_LB"]]
 if os.environ.get("CNT_CLUSTER_THREADS"):
     PER_FILE["pcg_cluster.cu"] = ["-DCNT_CLUSTER_THREADS=" + os.environ["CNT_CLUSTER_THREADS"]]
 

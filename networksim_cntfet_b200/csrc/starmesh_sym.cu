@@ -36,6 +36,7 @@ constexpr int IPT = 4;                 // items per thread of the chained scans 
 constexpr int TILE = TB * IPT;
 constexpr int SAT = 1 << 29;           // saturation of the pair counter (overflow detection)
 constexpr int GRID = 148 * 8;          // full grid of the device-sized kernels (8 CTAs of 256 threads per SM)
+constexpr int GRID_SCAN = 148 * 4;     // grid of the chunked scans: one chunk per CTA, all CTAs resident (48 / 57 registers)
 constexpr int SORT_SMEM = 512;         // longest neighbour list a warp sorts out of shared memory
 constexpr unsigned long long DEG1 = 1ull << 46;      // one unit of degree in a priority word
 
@@ -304,6 +305,136 @@ __device__ __forceinline__ void chained_scan(int n, int epoch, int *ticket, int 
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// The scans of the rounds without the chain: reduce, then scan.  In the chained scan the inclusive prefix of a tile
+// hangs on that of a predecessor ~100 tiles back, hop by hop (ncu, round 0 of 224 networks: 63 % of the warp samples
+// at the barrier behind warp 0's look-back, two membars and 3.3 look-back steps per tile of 1024 items: 17 us per tile
+// and CTA, 60 G items/s however many CTAs are in flight).  Here every CTA takes ONE contiguous chunk of tiles (chunk
+// numbers by ticket, so the lower chunks are always held by running CTAs), (1) sums its chunk and publishes the
+// total, (2) waits ONCE for the totals of the lower chunks -- nobody waits for anybody before publishing, so there is
+// no chain --, (3) walks its chunk again tile by tile with a running prefix and calls g.
+//   An item is described by a 32-bit code: code1(i) produces it in pass (1) (loads only), park(i, code) may keep it
+//   in an array, code3(i) returns it again in pass (3), dec(code) -> V4.  Both passes give item i to the same thread.
+// Pass (3) scans a tile in the striped arrangement the loads come in: one shuffle scan per row of 256 items, the
+// IPT * 8 = 32 warp totals scanned by warp 0 -- no transposition through shared memory (the blocked V4 accesses of
+// the chained scan are 4-way bank conflicts), two barriers per tile.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ V4 block_sum4(V4 v, V4 *s_warp /* TB / 32 */) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = v + shfl_down4(v, o);
+    if (lane == 0) s_warp[wid] = v;
+    __syncthreads();
+    V4 t = s_warp[0];
+#pragma unroll
+    for (int w = 1; w < TB / 32; w++) t = t + s_warp[w];
+    __syncthreads();
+    return t;
+}
+template <class C1, class P, class C3, class D, class G, class H>
+__device__ __forceinline__ void chunked_scan(int n, int epoch, int *ticket, int *sflag, V4 *sagg, int *err, C1 code1, P park,
+                                             C3 code3, D dec, G g, H fin) {
+    constexpr int NW = TB / 32;
+    static_assert(IPT * NW == 32, "the warp totals of a tile are scanned by one warp");
+    __shared__ int s_chunk;
+    __shared__ V4 s_warp[NW];
+    __shared__ V4 s_part[2][32], s_off[2][32], s_tot[2];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int ntiles = (n + TILE - 1) / TILE;
+    const V4 zero = v4(0, 0, 0, 0);
+    if (ntiles == 0) {
+        if (blockIdx.x == 0 && tid == 0) fin(zero);
+        return;
+    }
+    const int nchunks = (int)gridDim.x < ntiles ? (int)gridDim.x : ntiles;
+    if (tid == 0) s_chunk = atomicAdd(ticket, 1);
+    __syncthreads();
+    const int c = s_chunk;
+    if (c >= nchunks) return;
+    const int q = ntiles / nchunks, rem = ntiles % nchunks;
+    const int t0 = c * q + (c < rem ? c : rem), t1 = t0 + q + (c < rem ? 1 : 0);
+    // (1) total of the chunk
+    V4 sum = zero;
+    for (int tile = t0; tile < t1; tile++) {
+        int cd[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {                  // the loads of the IPT items first (independent chains in flight) ...
+            const int i = tile * TILE + k * TB + tid;
+            cd[k] = i < n ? code1(i) : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {                  // ... then whatever code1 wants to keep of them
+            const int i = tile * TILE + k * TB + tid;
+            if (i < n) {
+                park(i, cd[k]);
+                sum = sum + dec(cd[k]);
+            }
+        }
+    }
+    const V4 total = block_sum4(sum, s_warp);
+    if (tid == 0) {
+        sagg[c] = total;
+        st_release(&sflag[c], epoch * 4 + 1);
+    }
+    // (2) totals of the lower chunks
+    V4 pre = zero;
+    for (int j = tid; j < c; j += TB) {
+        int fl, spins = 0;
+        do {
+            fl = ld_acquire(&sflag[j]);
+            if ((fl >> 2) != epoch && (++spins & 1023) == 0 && (spins >= (1 << 20) || (*(volatile int *)err & CNT_SM_ERR_SCAN)))
+                break;
+        } while ((fl >> 2) != epoch);
+        if ((fl >> 2) != epoch) atomicOr(err, CNT_SM_ERR_SCAN);     // watchdog: never hang the GPU
+        else pre = pre + ld_v4(&sagg[j]);
+    }
+    V4 carry = block_sum4(pre, s_warp);
+    // (3) the chunk again, tile by tile
+    int buf = 0;
+    for (int tile = t0; tile < t1; tile++, buf ^= 1) {
+        const int i0 = tile * TILE;
+        V4 val[IPT], ex[IPT];
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const int i = i0 + k * TB + tid;
+            val[k] = i < n ? dec(code3(i)) : zero;
+        }
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            V4 inc = val[k];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                V4 t = shfl_up4(inc, o);
+                if (lane >= o) inc = t + inc;
+            }
+            ex[k] = shfl_up4(inc, 1);
+            if (lane == 0) ex[k] = zero;
+            if (lane == 31) s_part[buf][k * NW + wid] = inc;
+        }
+        __syncthreads();
+        if (wid == 0) {
+            V4 inc = s_part[buf][lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                V4 t = shfl_up4(inc, o);
+                if (lane >= o) inc = t + inc;
+            }
+            V4 e = shfl_up4(inc, 1);
+            if (lane == 0) e = zero;
+            s_off[buf][lane] = e;
+            if (lane == 31) s_tot[buf] = inc;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < IPT; k++) {
+            const int i = i0 + k * TB + tid;
+            if (i < n) g(i, carry + s_off[buf][k * NW + wid] + ex[k], val[k]);
+        }
+        carry = carry + s_tot[buf];
+    }
+    if (c == nchunks - 1 && tid == 0) fin(carry);
+}
+
 __device__ __forceinline__ int net_of_row(const Sym &s, int r) { return cnt::find_segment(s.roff, s.B, r); }
 
 // ---------------------------------------------------------------------------------------
@@ -440,12 +571,21 @@ __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
     const int n = rd->nnodes, ebase = rd->ebase, lbase = rd->lbase;
     const int32_t *N = s.nodes[r & 1];
     int32_t *Nout = s.nodes[(r + 1) & 1];
-    auto f = [&](int i) {
+    // code of an unknown: 0 frozen (leaves the list), 1 survivor, 2 + degree pivot; parked in s.loc (free until the finals)
+    auto code1 = [&](int i) {
         const int v = N[i];
-        if (s.nalive[s.rnet[v]] <= s.dense_max) return v4(0, 0, 0, 0);        // frozen: leaves the list
-        if (s.blocked[v] == r + 1) return v4(0, 0, 0, 1);                       // survivor
-        const int d = (int)(s.pri[v] >> 46);
-        if (d >= (1 << 17)) atomicOr(&s.p.info->error, CNT_SM_ERR_SLOTS);       // degree field about to overflow
+        if (s.nalive[s.rnet[v]] <= s.dense_max) return 0;
+        if (s.blocked[v] == r + 1) return 1;
+        return 2 + (int)(s.pri[v] >> 46);
+    };
+    auto park = [&](int i, int code) {
+        if (code - 2 >= (1 << 17)) atomicOr(&s.p.info->error, CNT_SM_ERR_SLOTS);    // degree field about to overflow
+        s.loc[i] = code;
+    };
+    auto code3 = [&](int i) { return s.loc[i]; };
+    auto dec = [&](int code) {
+        if (code < 2) return v4(0, 0, 0, code);
+        const int d = code - 2;
         const long long pairs = (long long)d * (d - 1) / 2;
         return v4(1, d, pairs > SAT ? SAT : (int)pairs, 0);
     };
@@ -487,7 +627,7 @@ __global__ void __launch_bounds__(TB) k_select(Sym s, int r, int epoch) {
         s.pptr[t.a] = t.c;
         info->rounds[r + 1].nnodes = t.d;
     };
-    chained_scan(n, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
+    chunked_scan(n, epoch, s.tickets + epoch, s.sflag, s.sagg, &info->error, code1, park, code3, dec, g, fin);
 }
 
 __global__ void __launch_bounds__(TB) k_incident(Sym s, int r) {
@@ -689,10 +829,9 @@ __global__ void __launch_bounds__(TB) k_items_scan(Sym s, int r, int epoch) {
     if (info->done | info->error) return;
     cnt_sm_round *rd = &info->rounds[r];
     const int np = rd->npairs, nl = rd->nlist;
-    auto f = [&](int t) {
-        const int z = s.gsz[t];
-        return z ? v4(1, z & ((1 << 30) - 1), z >> 30, 0) : v4(0, 0, 0, 0);
-    };
+    auto code = [&](int t) { return s.gsz[t]; };
+    auto park = [&](int, int) {};
+    auto dec = [&](int z) { return z ? v4(1, z & ((1 << 30) - 1), z >> 30, 0) : v4(0, 0, 0, 0); };
     auto g = [&](int t, V4 ex, V4 own) {
         if (own.a) {
             s.gidx[t] = ex.a;
@@ -706,7 +845,7 @@ __global__ void __launch_bounds__(TB) k_items_scan(Sym s, int r, int epoch) {
         rd->ngroups = t.a;                                // k_items_c splits it into nge + ngn
         rd->nnew = t.c;
     };
-    chained_scan(np + nl, epoch, s.tickets + epoch, s.sflag, s.sagg, s.sinc, &info->error, f, g, fin);
+    chunked_scan(np + nl, epoch, s.tickets + epoch, s.sflag, s.sagg, &info->error, code, park, code, dec, g, fin);
 }
 
 __global__ void __launch_bounds__(TB) k_items_c(Sym s, int r) {
@@ -1111,7 +1250,9 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
                 if (1.5 * scale * hr->nelim <= GRID * (TB / 32)) gp = fit(hr->nelim, TB / 32);      // a warp per pivot
                 gi = fit((double)hr->npairs + hr->nlist, 2 * TB);
             }
-            const int gs = gi < gn ? gn : gi;
+            // the two scans: one chunk per CTA, so no more CTAs than fit on the device at once
+            if (gn > GRID_SCAN) gn = GRID_SCAN;
+            const int gs = gi < gn ? gn : (gi < GRID_SCAN ? gi : GRID_SCAN);
             if (timing && nev + 9 <= MAXEV) cudaEventRecord(ev[nev++], st);
 #define CNT_SM_TICK() do { if (timing && nev < MAXEV) cudaEventRecord(ev[nev++], st); } while (0)
             k_mark<<<gl, TB, 0, st>>>(s, r);
