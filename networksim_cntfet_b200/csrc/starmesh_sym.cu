@@ -111,6 +111,8 @@ struct Sym {
     HEnt *htab;
     int32_t *pent, *pnext, *gsz, *ghead, *pm, *pa, *pb, *gidx, *goff, *gnew;     // [capI] per item of a round
     int32_t *pptr;                     // [R + 1] first pair of every pivot of the round
+    uint2 *phash;                      // [R] hash region (first entry, size) of every pivot of the round: k_items_a finds it
+                                       // with ONE load next to nptr / pptr instead of nbr -> rnet -> hoff (two levels of its chain)
     // chained scans
     int32_t *tickets;                  // one per scan invocation
     int32_t *sflag;
@@ -123,9 +125,12 @@ __device__ __forceinline__ unsigned long long priority(int deg, int lid) {
     return (d << 46) | ((unsigned long long)h << 26) | (unsigned long long)(unsigned)lid;
 }
 // entry of key in the hash region of its network, inserted when absent (slot stays -1); -1 when the region is full
+__device__ __forceinline__ int hash_find_or_insert(const Sym &s, long long h0, unsigned hsize, unsigned long long key);
 __device__ __forceinline__ int hash_find_or_insert(const Sym &s, int net, unsigned long long key) {
     const long long h0 = s.hoff[net];
-    const unsigned hsize = (unsigned)(s.hoff[net + 1] - h0);
+    return hash_find_or_insert(s, h0, (unsigned)(s.hoff[net + 1] - h0), key);
+}
+__device__ __forceinline__ int hash_find_or_insert(const Sym &s, long long h0, unsigned hsize, unsigned long long key) {
     unsigned long long z = key * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 29)) * 0xBF58476D1CE4E5B9ull;
     z ^= z >> 32;
@@ -721,12 +726,16 @@ __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
         const int m = ebase + ml, k0 = s.p.nptr[m], d = s.p.nptr[m + 1] - k0;
         warp_pivot(s, m, k0, d, s.pptr[ml], s.pptr[ml + 1] - s.pptr[ml], s_sort[wid]);
         if (lane == 0) {
-            atomicSub(&s.nalive[s.rnet[s.p.piv[m]]], 1);
+            const int net = s.rnet[s.p.piv[m]];
+            const long long h0 = s.hoff[net];
+            s.phash[ml] = make_uint2((unsigned)h0, (unsigned)(s.hoff[net + 1] - h0));
+            atomicSub(&s.nalive[net], 1);
             if (d > *(volatile int *)&info->max_deg) atomicMax(&info->max_deg, d);
         }
         return;
     }
     const int nceil = (nelim + 31) & ~31;
+    int dmax_all = 0;
     for (int ml = blockIdx.x * TB + threadIdx.x; ml < nceil; ml += gridDim.x * TB) {
         int d = 0, net = -1, k0 = 0, t0 = 0, np = 0;
         const int m = ebase + ml;
@@ -737,24 +746,41 @@ __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
             t0 = s.pptr[ml];
             np = s.pptr[ml + 1] - t0;
             if (d <= SMALL) {
-                for (int a = k0 + 1; a < k1; a++) {          // neighbours ascending (short list: insertion sort)
-                    const int nb = s.p.nbr[a], es = s.p.eslot[a];
-                    int c = a - 1;
-                    while (c >= k0 && s.p.nbr[c] > nb) {
-                        s.p.nbr[c + 1] = s.p.nbr[c];
-                        s.p.eslot[c + 1] = s.p.eslot[c];
-                        c--;
-                    }
-                    s.p.nbr[c + 1] = nb;
-                    s.p.eslot[c + 1] = es;
+                // neighbours ascending: the short list is loaded at once (independent loads), ordered in registers by a
+                // sorting network and written back (the insertion sort in global memory was 38 % of the kernel's stalls)
+                int nb[SMALL], es[SMALL];
+#pragma unroll
+                for (int a = 0; a < SMALL; a++) {
+                    nb[a] = a < d ? s.p.nbr[k0 + a] : 0x7fffffff;
+                    es[a] = a < d ? s.p.eslot[k0 + a] : 0;
                 }
-                for (int k = k0; k < k1; k++) {
-                    s.lm[k] = m;
-                    atomicAdd(&s.pri[s.p.nbr[k]], 0ull - DEG1);
+#define CNT_CE(i, j)                                   \
+    if (nb[i] > nb[j]) {                               \
+        int t_ = nb[i]; nb[i] = nb[j]; nb[j] = t_;     \
+        t_ = es[i]; es[i] = es[j]; es[j] = t_;         \
+    }
+                if (d > 4) {
+                    CNT_CE(0, 1) CNT_CE(2, 3) CNT_CE(4, 5) CNT_CE(6, 7) CNT_CE(0, 2) CNT_CE(1, 3) CNT_CE(4, 6) CNT_CE(5, 7)
+                    CNT_CE(1, 2) CNT_CE(5, 6) CNT_CE(0, 4) CNT_CE(3, 7) CNT_CE(1, 5) CNT_CE(2, 6) CNT_CE(1, 4) CNT_CE(3, 6)
+                    CNT_CE(2, 4) CNT_CE(3, 5) CNT_CE(3, 4)
+                } else if (d > 1) {
+                    CNT_CE(0, 1) CNT_CE(2, 3) CNT_CE(0, 2) CNT_CE(1, 3) CNT_CE(1, 2)
+                }
+#undef CNT_CE
+#pragma unroll
+                for (int a = 0; a < SMALL; a++) {
+                    if (a < d) {
+                        s.p.nbr[k0 + a] = nb[a];
+                        s.p.eslot[k0 + a] = es[a];
+                        s.lm[k0 + a] = m;
+                        atomicAdd(&s.pri[nb[a]], 0ull - DEG1);
+                    }
                 }
                 for (int t = 0; t < np; t++) s.pm[t0 + t] = m;
             }
             net = s.rnet[s.p.piv[m]];
+            const long long h0 = s.hoff[net];
+            s.phash[ml] = make_uint2((unsigned)h0, (unsigned)(s.hoff[net + 1] - h0));
         }
         unsigned big = __ballot_sync(~0u, d > SMALL);
         while (big) {                                         // longer lists: one at a time by the whole warp
@@ -766,11 +792,11 @@ __global__ void __launch_bounds__(TB) k_pivots(Sym s, int r) {
         // unknowns left per network: one atomic per run of equal networks inside the warp
         const unsigned same = __match_any_sync(~0u, net);
         if (net >= 0 && lane == __ffs(same) - 1) atomicSub(&s.nalive[net], __popc(same));
-        int dmax = d;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dmax = max(dmax, __shfl_xor_sync(~0u, dmax, o));
-        if (lane == 0 && dmax > *(volatile int *)&info->max_deg) atomicMax(&info->max_deg, dmax);
+        dmax_all = max(dmax_all, d);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dmax_all = max(dmax_all, __shfl_xor_sync(~0u, dmax_all, o));
+    if (lane == 0 && dmax_all > *(volatile int *)&info->max_deg) atomicMax(&info->max_deg, dmax_all);
 }
 
 // item t of a round: t < npairs = neighbour pair of a pivot, otherwise incident entry lbase + (t - npairs)
@@ -783,6 +809,7 @@ __global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
         s.gsz[t] = 0;
         if (t < np) {
             const int m = s.pm[t], k0 = s.p.nptr[m], d = s.p.nptr[m + 1] - k0;
+            const uint2 hreg = s.phash[m - ebase];
             // pair q of the pivot -> (i, j), i < j, row-major: row i starts at i (2d - i - 1) / 2
             const int q = t - s.pptr[m - ebase];
             int i = (int)(((2.0 * d - 1.0) - sqrt((2.0 * d - 1.0) * (2.0 * d - 1.0) - 8.0 * (double)q)) * 0.5);
@@ -791,7 +818,7 @@ __global__ void __launch_bounds__(TB) k_items_a(Sym s, int r) {
             while ((long long)(i + 1) * (2 * d - i - 2) / 2 <= q) i++;
             const int j = i + 1 + (q - (int)((long long)i * (2 * d - i - 1) / 2));
             const int u = s.p.nbr[k0 + i], w = s.p.nbr[k0 + j];
-            const int e = hash_find_or_insert(s, s.rnet[u], ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
+            const int e = hash_find_or_insert(s, (long long)hreg.x, hreg.y, ((unsigned long long)(unsigned)u << 32) | (unsigned)w);
             s.pent[t] = e;
             s.pa[t] = k0 + i;                 // the two dead edges of the pair by their position in the incident list:
             s.pb[t] = k0 + j;                 // the numeric phase keeps a copy of their values in list order (gl)
@@ -1083,7 +1110,7 @@ __global__ void __launch_bounds__(1024) k_final_b(Sym s) {
 }
 
 struct WsLayout {
-    int64_t eu, ew, lm, live0, live1, luw0, luw1, pri, hoff, rnet, loc, nodes0, nodes1, nalive, pptr, items, sagg, sinc, htab;
+    int64_t eu, ew, lm, live0, live1, luw0, luw1, pri, hoff, rnet, loc, nodes0, nodes1, nalive, pptr, phash, items, sagg, sinc, htab;
     int64_t ones0, ones1;      // [mid, nhead]: memset 0xFF
     int64_t zero0, zero1;      // [blocked, fill, nlive, tickets, sflag]: memset 0
     int64_t mid, nhead, blocked, fill, nlive, nsurv, tickets, sflag, dcount;
@@ -1118,6 +1145,7 @@ WsLayout ws_layout(int64_t R, int B, int64_t capS, int64_t capI) {
     L.nodes1 = take(R, 4);
     L.nalive = take(B, 4);
     L.pptr = take(R + 1, 4);
+    L.phash = take(R, 8);
     L.items = take(10 * capI, 4);
     L.sagg = take(L.ntiles, 16);
     L.sinc = take(L.ntiles, 16);
@@ -1190,6 +1218,7 @@ extern "C" int cnt_sm_symbolic(int B, const int32_t *roff, int64_t R, int64_t NN
     s.rnet = (int32_t *)(w + L.rnet); s.loc = (int32_t *)(w + L.loc);
     s.nodes[0] = (int32_t *)(w + L.nodes0); s.nodes[1] = (int32_t *)(w + L.nodes1);
     s.nalive = (int32_t *)(w + L.nalive); s.pptr = (int32_t *)(w + L.pptr);
+    s.phash = (uint2 *)(w + L.phash);
     int32_t *items = (int32_t *)(w + L.items);
     s.pent = items; s.pnext = items + cap_items; s.gsz = items + 2 * cap_items; s.ghead = items + 3 * cap_items;
     s.pm = items + 4 * cap_items; s.pa = items + 5 * cap_items; s.pb = items + 6 * cap_items;
