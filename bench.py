@@ -465,6 +465,23 @@ def gpu_arm(args):
         for k, v in eng._twin.stage_times_ms(reset=True).items():
             stages[k] = stages.get(k, 0.0) + v
     clocks = sampler.stop() if rank == 0 else None
+    stages_two_streams = None
+    roof_steps = 0
+    if E > 1:
+        # Two streams: the CUDA-event time of a stage on one stream includes the kernels the other stream ran in between, so
+        # the roofline objects take their stage durations (and their bytes / test counts) from a second timed region: a few
+        # steps of the SAME batches on ONE engine / stream, right after the device-timed loop.  `value` is untouched.
+        stages_two_streams = {k: round(v, 3) for k, v in stages.items()}
+        roof_steps = min(3, args.steps)
+        one_batch(eng, (0, 4, 0))                                # same shapes: nothing to warm up but the hint of the grids
+        eng.stage_times_ms(reset=True)
+        direct_bytes0 = direct_total()
+        results = [one_batch(eng, (0, 5, k)) for k in range(roof_steps)]
+        eng.sync()
+        direct_bytes = direct_total() - direct_bytes0
+        direct_info = dict(getattr(eng, "last_direct", None) or {})
+        stages = eng.stage_times_ms(reset=True)
+    roof_batches = roof_steps if E > 1 else args.steps          # batches behind `stages`, `results`, `direct_bytes`
 
     # ---- timed: end to end through the public host API
     measure_perc.measure_ensemble(ns * E, args.scaling, seeds_for(2, 0, count=B * E), onoffmap=args.onoffmap, rtol=args.rtol)  # warm
@@ -567,10 +584,13 @@ def gpu_arm(args):
                         "achieved": achieved, "peak": peak,
                         "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback", "unit": "GB/s",
                         "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
-                        "algorithmic_bytes_per_launch": direct_bytes / max(args.steps * E, 1),
-                        "algorithmic_bytes": direct_bytes, "seconds": d_s,
-                        "symbolic_ms_per_batch": stages.get("direct_symbolic", 0.0) / max(args.steps * E, 1),
-                        "numeric_ms_per_batch": stages.get("direct_numeric", 0.0) / max(args.steps * E, 1),
+                        "algorithmic_bytes_per_launch": direct_bytes / max(roof_batches, 1),
+                        "algorithmic_bytes": direct_bytes, "seconds": d_s, "batches": roof_batches,
+                        "timed_region": ("%d steps of one batch of %d networks on ONE engine / stream right after the device-timed "
+                                         "loop (under two streams the CUDA-event time of a stage includes the other stream's "
+                                         "kernels)" % (roof_steps, B)) if E > 1 else "the device-timed loop",
+                        "symbolic_ms_per_batch": stages.get("direct_symbolic", 0.0) / max(roof_batches, 1),
+                        "numeric_ms_per_batch": stages.get("direct_numeric", 0.0) / max(roof_batches, 1),
                         "last_batch": direct_info,
                         "note": "'launch' = one batch (all rounds of both phases); algorithmic bytes per starmesh.algorithmic_bytes: "
                                 "symbolic -- live-edge list read twice and unknowns in play once per round, 16 B per incident "
@@ -593,7 +613,8 @@ def gpu_arm(args):
             "e2e_host_breakdown_ms_per_step": {"seeds": 1e3 * e2e_parts[0] / max(args.steps, 1),
                                                "measure_ensemble": 1e3 * e2e_parts[1] / max(args.steps, 1),
                                                "rows_gather": 1e3 * e2e_parts[2] / max(args.steps, 1)},
-            "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()},
+            "stages_ms_rank0": {k: round(v, 3) for k, v in stages.items()}, "stages_batches": roof_batches,
+            "stages_ms_two_streams_rank0": stages_two_streams,
             "junction_tests_per_s": (ntests / jt) if jt > 0 else None, "junction_tests": ntests,
             "junction_roofline": {"bound": "fp64", "unit": "TFLOP/s", "flops_per_test": 17,
                                   "achieved": (17.0 * ntests / jt / 1e12) if jt > 0 else None,
@@ -629,9 +650,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=224,
-                    help="networks per GPU per step (the ~45 rounds of the direct solve are a fixed latency per batch: "
-                         "measured 1999 / 2240 / 2346 networks/s at 56 / 112 / 224)")
+    ap.add_argument("--batch", type=int, default=160,
+                    help="networks per batch (a step = engines x batch networks per GPU).  Measured, device / end to end "
+                         "networks/s: 1 x 224: 3250 / 3140; 2 x 112: 3370 / 3250; 2 x 160: 3450 / 3300; 2 x 224: 3320 / 3200 "
+                         "(profiles/r02_batch_sweep.txt)")
     ap.add_argument("--n", type=int, default=100000)
     ap.add_argument("--scaling", type=int, default=100)
     ap.add_argument("--onoffmap", type=int, default=1)
@@ -642,8 +664,9 @@ def main():
     ap.add_argument("--guess", default="zero", choices=["linear", "zero"])
     ap.add_argument("--cpu-sample", type=int, default=0, help="networks in the CPU sample (default: one per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--engines", type=int, default=1, choices=[1, 2],
-                    help="batches of a step in flight per GPU (2: two engines = two streams + two host threads)")
+    ap.add_argument("--engines", type=int, default=2, choices=[1, 2],
+                    help="batches of a step in flight per GPU (2: two engines = two streams + two host threads: the host work "
+                         "and the latency-bound late rounds of one batch's solve overlap the kernels of the other)")
     ap.add_argument("--no-extra", action="store_true", help="skip the config 2 / 4 / 5, cluster-PCG and SpMV legs")
     ap.add_argument("--ens-number", type=int, default=1000, help="networks of the config-2 leg")
     ap.add_argument("--big-side", type=float, default=300.0, help="side (um) of the single large network of the config-5 leg")

@@ -26,11 +26,13 @@ VDS = 0.1                                   # netsim.py:182
 FULLNET_COLUMNS = ['sticks', 'size', 'density', 'nclust', 'maxclust', 'ion', 'ioff', 'gate', 'fname', 'seed',
                    'onoffmap']
 _PINNED = None
-PIPELINE = False              # True: the batches of a call alternate between two engines / host threads (measured
-                              # gain at 100x100 um: 0.7-2 %, the step is one long kernel already; results identical)
-BATCH_STICKS = 23_200_000     # sticks per GPU batch of the ensemble path (224 networks at 100x100 um, ~8 GB): the
-                              # direct solver's ~45 rounds are a fixed latency per batch, measured 1999 / 2240 / 2346
-                              # networks/s at 56 / 112 / 224 networks per batch
+PIPELINE = True               # the batches of a call alternate between two engines (two streams, two host threads): the host
+                              # work and the latency-bound late rounds of one batch overlap the kernels of the other.
+                              # Measured at 100x100 um, device / end to end networks/s: one engine x 224 networks per batch
+                              # 3250 / 3140, two engines x 112: 3370 / 3250, x 160: 3450 / 3300, x 224: 3320 / 3200; results
+                              # identical (networks are independent and seeded one by one)
+PIPELINE_MIN_STICKS = 2_000_000   # ... for calls of at least this many sticks (below: one batch, one engine)
+BATCH_STICKS = 16_100_000     # sticks per GPU batch of the ensemble path (160 networks at 100x100 um, ~6 GB)
 
 
 def checkdir(directoryname):
@@ -170,9 +172,14 @@ def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l
     dev_in = pinned.to(eng.device, non_blocking=True)          # H2D of this call's inputs
     batches = []
     start = 0
+    cap = BATCH_STICKS
+    total = sum(ns) + 2 * len(ns)
+    pipeline = PIPELINE and len(ns) > 1 and total >= PIPELINE_MIN_STICKS
+    if pipeline:                                               # two engines: at least two batches per call
+        cap = min(cap, max((total + 1) // 2, 1))
     while start < len(ns):                                     # batches bounded by stick count
         stop, tot = start, 0
-        while stop < len(ns) and (stop == start or tot + ns[stop] + 2 <= BATCH_STICKS):
+        while stop < len(ns) and (stop == start or tot + ns[stop] + 2 <= cap):
             tot += ns[stop] + 2
             stop += 1
         batches.append(slice(start, stop))
@@ -184,7 +191,7 @@ def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l
 
     # two engines on two host threads: the next batch is generated and assembled while the PCG
     # kernel of the current one runs (Engine.run_pipelined)
-    results = eng.run_pipelined(batches, one) if PIPELINE else [one(eng, sl) for sl in batches]
+    results = eng.run_pipelined(batches, one) if pipeline else [one(eng, sl) for sl in batches]
     frames = []
     d2h = 0
     for sl, res in zip(batches, results):

@@ -165,6 +165,7 @@ def test_pipelined_batches_equal_sequential(engine, monkeypatch):
     ns = [3000, 3600, 4000, 4400, 5200, 6400, 3800, 4100]
     seeds = list(range(501, 509))
     monkeypatch.setattr(measure_perc, "BATCH_STICKS", 9000)        # 2 networks per batch -> 4+ batches
+    monkeypatch.setattr(measure_perc, "PIPELINE_MIN_STICKS", 0)    # (small calls stay on one engine by default)
     monkeypatch.setattr(measure_perc, "PIPELINE", False)
     a = measure_perc.measure_ensemble(ns, 20, seeds, onoffmap=1)
     monkeypatch.setattr(measure_perc, "PIPELINE", True)
