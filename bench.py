@@ -270,7 +270,7 @@ def extra_legs(args, eng, world, rank, dist, peak):
     def config4():
         side, vgs = 60.0, np.linspace(-10, 10, 11)
         res = []
-        for rep in range(3):
+        for rep in range(5):
             sync_local()
             t0 = time.perf_counter()
             dev = netsim.RandomCNTNetwork(n=int(10 * side * side), scaling=side, seed=1234 + rep, onoffmap=0, rng='philox')
@@ -280,11 +280,15 @@ def extra_legs(args, eng, world, rank, dist, peak):
             sync_local()
             t2 = time.perf_counter()
             res.append((t1 - t0, t2 - t1, len(cur), bool(dev.percolating)))
-        build, sweep, steps, perc = res[-1]
+        # wall clock of a 10-50 ms host-driven job right after the multi-GB main loops: single repetitions were seen anywhere
+        # between 10 and 250 ms (allocator housekeeping of the first large requests after the ensemble batches are freed), so
+        # the line quotes the fastest of repetitions 2..5 and lists all of them
+        build, sweep, steps, perc = min(res[1:], key=lambda r: r[1])
         return {"workload": "60x60 um device (36000 sticks), gate sweep 11 voltages x back/partial/total = %d re-solves over one "
                             "pattern and one symbolic plan" % steps, "device_build_ms": build * 1e3, "sweep_ms": sweep * 1e3,
                 "ms_per_gate_step": sweep * 1e3 / max(steps, 1), "gate_steps_per_s": steps / sweep, "percolating": perc,
-                "solver": eng.last_solver, "timing": "wall clock, third repetition (rank 0)"}
+                "sweep_ms_of_every_repetition": [round(r[1] * 1e3, 2) for r in res],
+                "solver": eng.last_solver, "timing": "wall clock, fastest of repetitions 2..5 (rank 0)"}
 
     def sync_local():
         eng.sync()
@@ -484,7 +488,8 @@ def gpu_arm(args):
     roof_batches = roof_steps if E > 1 else args.steps          # batches behind `stages`, `results`, `direct_bytes`
 
     # ---- timed: end to end through the public host API
-    measure_perc.measure_ensemble(ns * E, args.scaling, seeds_for(2, 0, count=B * E), onoffmap=args.onoffmap, rtol=args.rtol)  # warm
+    for k in range(2):          # warm: pinned staging buffer, and both engines see one more pair of batches (grow-only work areas)
+        measure_perc.measure_ensemble(ns * E, args.scaling, seeds_for(2, k, count=B * E), onoffmap=args.onoffmap, rtol=args.rtol)
     barrier()
     t0 = time.perf_counter()
     h2d = d2h = 0
