@@ -35,6 +35,26 @@ PIPELINE_MIN_STICKS = 2_000_000   # ... for calls of at least this many sticks (
 BATCH_STICKS = 16_100_000     # sticks per GPU batch of the ensemble path (160 networks at 100x100 um, ~6 GB)
 
 
+def _split_batches(ns):
+    """(slices of consecutive networks, use two engines?): batches of at most BATCH_STICKS sticks (electrodes included; a
+    network larger than that is a batch of its own); a call of at least PIPELINE_MIN_STICKS sticks and two networks is cut
+    into at least two batches, which alternate between two engines (Engine.run_pipelined)"""
+    total = sum(ns) + 2 * len(ns)
+    pipeline = bool(PIPELINE) and len(ns) > 1 and total >= PIPELINE_MIN_STICKS
+    cap = BATCH_STICKS
+    if pipeline:
+        cap = min(cap, max((total + 1) // 2, 1))
+    batches, start = [], 0
+    while start < len(ns):
+        stop, tot = start, 0
+        while stop < len(ns) and (stop == start or tot + ns[stop] + 2 <= cap):
+            tot += ns[stop] + 2
+            stop += 1
+        batches.append(slice(start, stop))
+        start = stop
+    return batches, pipeline and len(batches) > 1
+
+
 def checkdir(directoryname):
     """create the directory if it does not exist (measure_perc.py:28-38)"""
     if directoryname and not os.path.isdir(directoryname):
@@ -170,20 +190,7 @@ def measure_ensemble(ns, scaling, seeds, onoffmap=1, element=LinExpTransistor, l
     pinned[:len(ns)] = torch.as_tensor(ns, dtype=torch.int64)
     pinned[len(ns):] = torch.from_numpy(seeds_np.view(np.int64).copy())
     dev_in = pinned.to(eng.device, non_blocking=True)          # H2D of this call's inputs
-    batches = []
-    start = 0
-    cap = BATCH_STICKS
-    total = sum(ns) + 2 * len(ns)
-    pipeline = PIPELINE and len(ns) > 1 and total >= PIPELINE_MIN_STICKS
-    if pipeline:                                               # two engines: at least two batches per call
-        cap = min(cap, max((total + 1) // 2, 1))
-    while start < len(ns):                                     # batches bounded by stick count
-        stop, tot = start, 0
-        while stop < len(ns) and (stop == start or tot + ns[stop] + 2 <= cap):
-            tot += ns[stop] + 2
-            stop += 1
-        batches.append(slice(start, stop))
-        start = stop
+    batches, pipeline = _split_batches(ns)
 
     def one(e, sl):
         return e.measure_ensemble(ns[sl], scaling, seeds_np[sl], onoffmap=onoffmap, element=element, l=l, rtol=rtol,

@@ -104,3 +104,40 @@ def test_measure_async_world2_gloo(tmp_path):
     # only rank 0 writes the seeds file (measure_perc.py:226-229)
     assert any(n.startswith("seeds_") for n in os.listdir(tmp_path / "r0"))
     assert not any(n.startswith("seeds_") for n in os.listdir(tmp_path / "r1"))
+
+
+def test_ensemble_call_is_cut_into_batches_for_two_engines(monkeypatch):
+    """host logic of measure_perc.measure_ensemble: batches bounded by BATCH_STICKS (electrodes counted), a large call is
+    cut into at least two batches so that two engines can alternate, a small call stays one batch on one engine, every
+    network lands in exactly one batch and the order is kept"""
+    from networksim_cntfet_b200 import measure_perc as mp
+
+    def covered(batches, n):
+        idx = [i for sl in batches for i in range(sl.start, sl.stop)]
+        return idx == list(range(n))
+
+    # the bench's end-to-end call: 320 networks of 100k sticks -> two batches of 160
+    b, pipe = mp._split_batches([100000] * 320)
+    assert pipe and [(s.start, s.stop) for s in b] == [(0, 160), (160, 320)]
+    # a long ensemble: batches of <= BATCH_STICKS sticks alternate between the engines
+    b, pipe = mp._split_batches([100000] * 1000)
+    assert pipe and covered(b, 1000) and all(sum(100002 for _ in range(s.start, s.stop)) <= mp.BATCH_STICKS for s in b)
+    assert len(b) == 7 and b[0].stop == 160
+    # small calls: one batch, one engine
+    b, pipe = mp._split_batches([300] * 5)
+    assert not pipe and [(s.start, s.stop) for s in b] == [(0, 5)]
+    # one network, however large, cannot be split
+    b, pipe = mp._split_batches([10_000_000])
+    assert not pipe and len(b) == 1
+    # a network larger than the cap is a batch of its own; ragged sizes keep their order
+    ns = [4000, 20_000_000, 5000, 6000]
+    b, pipe = mp._split_batches(ns)
+    assert pipe and covered(b, 4) and any(s.stop - s.start == 1 and ns[s.start] == 20_000_000 for s in b)
+    # switched off: the stick bound alone decides
+    monkeypatch.setattr(mp, "PIPELINE", False)
+    b, pipe = mp._split_batches([100000] * 320)
+    assert not pipe and [(s.start, s.stop) for s in b] == [(0, 160), (160, 320)]
+    monkeypatch.setattr(mp, "BATCH_STICKS", 9000)
+    b, pipe = mp._split_batches([3000, 3600, 4000, 4400])
+    assert [(s.start, s.stop) for s in b] == [(0, 2), (2, 4)] and not pipe
+    assert mp._split_batches([]) == ([], False)
