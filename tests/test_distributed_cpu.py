@@ -141,3 +141,51 @@ def test_ensemble_call_is_cut_into_batches_for_two_engines(monkeypatch):
     b, pipe = mp._split_batches([3000, 3600, 4000, 4400])
     assert [(s.start, s.stop) for s in b] == [(0, 2), (2, 4)] and not pipe
     assert mp._split_batches([]) == ([], False)
+
+
+def _rows_loop(res, ns, scaling, seeds, onoffmap, fnames=None):
+    """the row loop of measure_perc.py:190-197 (what _rows_from_ensemble builds as arrays)"""
+    import pandas as pd
+    from networksim_cntfet_b200.measure_perc import FULLNET_COLUMNS
+    rows = []
+    for k, n in enumerate(ns):
+        fname = fnames[k] if fnames else ''
+        base = [n, scaling, n / scaling ** 2, int(res["nclust"][k]), int(res["maxclust"][k])]
+        if res["percolating"][k]:
+            ion = float(res["ion"][k])
+            rows.append(base + [ion, float(res["ioff_back"][k]), 'back', fname, int(seeds[k]), onoffmap])
+            rows.append(base + [ion, float(res["ioff_total"][k]), 'total', fname, int(seeds[k]), onoffmap])
+            rows.append(base + [ion, float(res["ioff_partial"][k]), 'partial', fname, int(seeds[k]), onoffmap])
+        else:
+            rows.append(base + [0, 0, 'back', fname, int(seeds[k]), onoffmap])
+    return pd.DataFrame(rows, columns=FULLNET_COLUMNS)
+
+
+def test_rows_of_an_ensemble_equal_the_reference_loop():
+    """_rows_from_ensemble (columns as arrays) against the reference's row loop: values, order, dtypes, CSV text"""
+    import numpy as np
+    from networksim_cntfet_b200 import measure_perc as mp
+    rng = np.random.default_rng(5)
+
+    def fake(B, perc):
+        return dict(percolating=np.asarray(perc, dtype=bool), ion=rng.random(B) * 1e-4, ioff_back=rng.random(B) * 1e-6,
+                    ioff_total=rng.random(B) * 1e-7, ioff_partial=rng.random(B) * 1e-8,
+                    nclust=rng.integers(1, 500, B).astype(np.int32), maxclust=rng.integers(1, 90000, B).astype(np.int32),
+                    status=np.zeros((4, B), dtype=np.int32))
+
+    cases = [
+        ([300, 350, 4000, 100000, 7], 5, [True, False, True, True, False], np.arange(11, 16, dtype=np.uint64), 1, None),
+        ([300, 301], 5.0, [False, False], [3, 4], 0, None),                                   # nothing percolates: integer zeros
+        ([1000, 2000, 3000], 20, [True, True, True], np.array([2 ** 63 + 5, 1, 2], dtype=np.uint64), 2, ['a', 'b', 'c']),
+        ([], 5, [], [], 1, None),
+    ]
+    for ns, scaling, perc, seeds, onoff, fnames in cases:
+        res = fake(len(ns), perc)
+        a = _rows_loop(res, ns, scaling, seeds, onoff, fnames)
+        b = mp._rows_from_ensemble(res, ns, scaling, seeds, onoff, fnames=fnames)
+        assert list(a.columns) == list(b.columns) and len(a) == len(b)
+        if len(a):
+            assert a.dtypes.astype(str).tolist() == b.dtypes.astype(str).tolist(), (a.dtypes, b.dtypes)
+        for col in a.columns:
+            assert a[col].tolist() == b[col].tolist(), col
+        assert a.to_csv() == b.to_csv()
