@@ -395,14 +395,29 @@ def gpu_arm(args):
         if world > 1:
             dist.barrier()
 
-    def gather_rows(rows):
-        """the path's only collective: all-gather of the per-network statistics rows"""
+    pending = []                         # all-gathers of the device-timed steps that have been issued, not yet waited for
+
+    def gather_rows(rows, wait=True):
+        """the path's only collective: all-gather of the per-network statistics rows.  wait=False (device-timed loop): the
+        collective is issued and the next step starts; all of them are waited for before the end of the timed region, so
+        the ranks -- independent shards of the ensemble -- do not stop for each other after every step"""
         if world == 1:
             return rows
         t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=eng.device)
         out = [torch.empty_like(t) for _ in range(world)]
+        if not wait:
+            pending.append((dist.all_gather(out, t, async_op=True), out, t))
+            return None
         dist.all_gather(out, t)
         return torch.cat(out).cpu().numpy()
+
+    def finish_gathers():
+        last = None
+        for work, out, t in pending:
+            work.wait()
+            last = out
+        pending.clear()
+        return torch.cat(last).cpu().numpy() if last is not None else None
 
     def one_batch(e, sub_phase_step):
         sub, phase, step = sub_phase_step
@@ -417,7 +432,7 @@ def gpu_arm(args):
         rows = np.concatenate([np.stack([res["percolating"].astype(np.float64), res["ion"], res["ioff_back"],
                                          res["ioff_total"], res["ioff_partial"], res["nclust"].astype(np.float64),
                                          res["maxclust"].astype(np.float64)], 1) for res in outs])
-        gather_rows(rows)
+        gather_rows(rows, wait=False)
         return outs
 
     # ---- clock sampler: started BEFORE the warm-up (the start-up of nvidia-smi -- NVML initialisation in a second
@@ -428,6 +443,7 @@ def gpu_arm(args):
     # ---- warm-up
     for k in range(args.warmup):
         device_step(0, k)
+    finish_gathers()
     # everything imported and allocated so far leaves the garbage collector's generations: a full collection walks
     # ~1M module-level objects (torch, pandas, scipy) and showed up as sporadic 20-40 ms pauses inside a step
     import gc
@@ -455,6 +471,7 @@ def gpu_arm(args):
         ts = time.perf_counter()
         results.extend(device_step(1, k))
         step_wall.append(1e3 * (time.perf_counter() - ts))
+    finish_gathers()                                 # every step's rows have arrived on every rank
     e1.record(cur_stream)
     barrier()
     t_wall = time.perf_counter() - t_wall0
