@@ -26,8 +26,6 @@ if os.environ.get("CNT_TILE_FLAGS"):          # A/B of the tile kernel's shape: 
     PER_FILE["junctions.cu"] = PER_FILE["junctions.cu"] + os.environ["CNT_TILE_FLAGS"].split()
 if os.environ.get("CNT_UF_K"):                # A/B: junctions per thread of the union pass
     PER_FILE["clusters.cu"] = ["-DCNT_UF_K=" + os.environ["CNT_UF_K"]]
-if os.environ.get("CNT_SM_LB"):               # A/B: look-back width of the chained scans
-    PER_FILE["starmesh_sym.cu"] = ["-DCNT_SM_LB=" + os.environ["CNT_SM_LB"]]
 if os.environ.get("CNT_CLUSTER_THREADS"):
     PER_FILE["pcg_cluster.cu"] = ["-DCNT_CLUSTER_THREADS=" + os.environ["CNT_CLUSTER_THREADS"]]
 
