@@ -8,14 +8,14 @@
 //
 //   k_mark      live edges: the endpoint with the larger (degree, hash, index) is blocked
 //   k_select    unknowns in play: unblocked -> pivot (an independent set of local minima);
-//               one chained scan numbers the pivots, sizes their incident lists and pair ranges
+//               one single-launch scan (chunked_scan) numbers the pivots, sizes their lists and pair ranges
 //               and compacts the survivors
 //   k_incident  live edges: an edge of a pivot goes to the pivot's incident list, the rest survive
 //   k_pivots    per pivot: neighbours ascending; degrees of the neighbours, unknowns left per network
 //   k_items_a   per neighbour pair (u, w) of a pivot: find-or-insert (u, w) in the hash and link the
 //               pair into the target's list; per incident entry: link into the neighbour's list
 //   k_items_b   the last arrival of every list counts it and names its owner (smallest item)
-//   k_items_scan  chained scan over the owners: group numbers, offsets, new slot numbers
+//   k_items_scan  the same scan over the owners: group numbers, offsets, new slot numbers
 //   k_items_c   per owner: members ordered by item index (= by pivot), written as the contribution
 //               list of the target edge / the update list of the neighbour; new edges get their slot
 //
