@@ -360,6 +360,40 @@ def extra_legs(args, eng, world, rank, dist, peak):
     return out
 
 
+class RowGather:
+    """The path's only collective: all-gather of the per-network statistics rows of a step.  gather(rows) returns the rows
+    of all ranks (rank order).  gather(rows, wait=False) -- the device-timed loop -- issues the collective and returns: the
+    next step starts at once, finish() waits for everything issued so far (before the timed region ends) and returns the
+    rows of the last step; so the ranks, independent shards of the ensemble, do not stop for each other after every step.
+    One rank: nothing to gather.  (CPU test with gloo, world 2: tests/test_distributed_cpu.py.)"""
+
+    def __init__(self, dist, world, device):
+        self.dist, self.world, self.device = dist, world, device
+        self.pending = []                # (work handle, output tensors, input tensor) of the collectives not yet waited for
+
+    def gather(self, rows, wait=True):
+        if self.world == 1:
+            return rows
+        import numpy as np
+        import torch
+        t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=self.device)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        if not wait:
+            self.pending.append((self.dist.all_gather(out, t, async_op=True), out, t))
+            return None
+        self.dist.all_gather(out, t)
+        return torch.cat(out).cpu().numpy()
+
+    def finish(self):
+        import torch
+        last = None
+        for work, out, t in self.pending:
+            work.wait()
+            last = out
+        self.pending = []
+        return torch.cat(last).cpu().numpy() if last is not None else None
+
+
 def gpu_arm(args):
     import numpy as np
     import torch
@@ -395,29 +429,8 @@ def gpu_arm(args):
         if world > 1:
             dist.barrier()
 
-    pending = []                         # all-gathers of the device-timed steps that have been issued, not yet waited for
-
-    def gather_rows(rows, wait=True):
-        """the path's only collective: all-gather of the per-network statistics rows.  wait=False (device-timed loop): the
-        collective is issued and the next step starts; all of them are waited for before the end of the timed region, so
-        the ranks -- independent shards of the ensemble -- do not stop for each other after every step"""
-        if world == 1:
-            return rows
-        t = torch.as_tensor(np.ascontiguousarray(rows), dtype=torch.float64, device=eng.device)
-        out = [torch.empty_like(t) for _ in range(world)]
-        if not wait:
-            pending.append((dist.all_gather(out, t, async_op=True), out, t))
-            return None
-        dist.all_gather(out, t)
-        return torch.cat(out).cpu().numpy()
-
-    def finish_gathers():
-        last = None
-        for work, out, t in pending:
-            work.wait()
-            last = out
-        pending.clear()
-        return torch.cat(last).cpu().numpy() if last is not None else None
+    rg = RowGather(dist, world, eng.device)
+    gather_rows, finish_gathers = rg.gather, rg.finish
 
     def one_batch(e, sub_phase_step):
         sub, phase, step = sub_phase_step

@@ -189,3 +189,50 @@ def test_rows_of_an_ensemble_equal_the_reference_loop():
         for col in a.columns:
             assert a[col].tolist() == b[col].tolist(), col
         assert a.to_csv() == b.to_csv()
+
+
+def _gather_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import bench
+        rg = bench.RowGather(dist, world, torch.device("cpu"))
+        rows = lambda step: np.full((3, 7), 100.0 * step + rank) + np.arange(7)
+        # the blocking form (end-to-end loop): every rank gets the rows of all ranks in rank order
+        full = rg.gather(rows(0))
+        # the non-blocking form (device-timed loop): issue one per step, nobody waits; finish() completes them all
+        issued = [rg.gather(rows(k), wait=False) for k in range(1, 5)]
+        n_pending = len(rg.pending)
+        last = rg.finish()
+        q.put((rank, full.tolist(), issued, n_pending, last.tolist(), len(rg.pending), rg.finish()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_bench_row_gather_world2_gloo():
+    """bench.RowGather, the only collective of the ensemble path: blocking and non-blocking all-gather of the statistics
+    rows on two gloo ranks; one rank gathers nothing"""
+    import bench
+    one = bench.RowGather(None, 1, None)
+    r = np.arange(6.0).reshape(2, 3)
+    assert one.gather(r) is r and one.gather(r, wait=False) is r and one.finish() is None
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r_, 2, port, q)) for r_ in range(2)]
+    for p in procs:
+        p.start()
+    got = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    expect = lambda step: np.concatenate([np.full((3, 7), 100.0 * step + rk) + np.arange(7) for rk in range(2)]).tolist()
+    for rank, full, issued, n_pending, last, left, again in got:
+        assert full == expect(0)
+        assert issued == [None] * 4 and n_pending == 4
+        assert last == expect(4) and left == 0 and again is None
